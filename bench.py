@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""bench.py - ms per Newton-step assembly (gradient + restricted Hessian + objective) on fem2d L=8.
+
+One "step" = one pass of the hot path at a fixed seeded feasible iterate on the finest level:
+apply_D -> barrier F/F1/F2 -> gradient -> Hessian numeric phase -> R'HR values (BASELINE.json metric).
+
+  value     device-resident inputs, CUDA events on the launching stream, L2 flushed between steps
+  e2e       the same step through the C ABI with HOST buffers (mgb_assemble_host): H2D of the
+            Newton unknown, D2H of gradient + Hessian values + scalars inside the timed region
+  roofline  dominant kernel (element_kernel): algorithmic bytes / event time vs measured HBM peak
+  cpu_baseline / --impl reference: the CPU oracle restatement (the Julia reference cannot run here:
+            no julia/mpiexec in the image) timed on the host cores.
+
+N > 1 (torchrun): quadrature rows (whole elements) are sharded across ranks, every rank assembles
+the contributions of its own rows (no data-path collective inside the timed region; the owner-side
+sum of the few shared interface rows is part of the solve seam), scaling = "strong".
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ms per Newton-step assembly (fem2d L=8)"
+
+
+def build_problem(L: int, p: float, seed: int = 20261018):
+    import mgb_b200
+    from mgb_b200 import amg as amg_mod
+    geom = mgb_b200.fem2d(L)
+    M, _ = amg_mod.amg(geom)
+    n = geom.x.shape[0]
+    g, f = amg_mod.DEFAULT_G[2], amg_mod.DEFAULT_F[2]
+    z0 = np.array([g(geom.x[i]) for i in range(n)], dtype=float).reshape(-1, order="F")
+    c = np.array([f(geom.x[i]) for i in range(n)], dtype=float)
+    R = M.R_fine[-1]
+    rng = np.random.default_rng(seed)
+    s = 1e-3 * rng.uniform(-1.0, 1.0, size=R.shape[1])
+    Dz0 = np.stack([Dk @ z0 for Dk in M.D], axis=1)
+    return dict(geom=geom, M=M, R=R, D=M.D, z0=z0, c=c, s=s, Dz0=Dz0, idx=[1, 2, 3], p=p)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([v.strip() for v in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def start(self):
+        self._th = threading.Thread(target=self._run, daemon=True)
+        self._th.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._th:
+            self._th.join(timeout=6)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows for k in range(4) if len(r) >= 6 and r[2 + k] == "Active"})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def peak_hbm():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_assembly_sample(pr, t, reps):
+    """CPU oracle restatement of one assembly (f1 + f2 + f0), `reps` times; returns ms per assembly."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mgb_oracle as O
+    Q = O.EuclidianPower(idx=pr["idx"], p=pr["p"])
+    args = (pr["s"], pr["geom"].x, pr["geom"].w, t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        O.f0(*args)
+        O.f1(*args)
+        O.f2(*args)
+        times.append((time.perf_counter() - t0) * 1e3)
+    return float(np.mean(times))
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    pr = build_problem(args.L, args.p)
+    for _ in range(min(args.warmup, 1)):
+        cpu_assembly_sample(pr, args.t, 1)
+    ms = cpu_assembly_sample(pr, args.t, max(1, args.steps))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly (n={pr['geom'].x.shape[0]})",
+                   "note": "CPU restatement (oracle/mgb_oracle.py, scipy CSC), not the Julia reference: julia/mpiexec absent"},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": 1, "kind": "port",
+                         "sample": f"{max(1, args.steps)} full assemblies (f0+f1+f2) at L={args.L}"},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--L", type=int, default=8)
+    ap.add_argument("--p", type=float, default=1.0)
+    ap.add_argument("--t", type=float, default=1.0)
+    ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--cpu-reps", type=int, default=3)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from mgb_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    pr = build_problem(args.L, args.p)
+    geom = pr["geom"]
+    n = geom.x.shape[0]
+    B = geom.block
+    E = n // B
+    e0, e1 = (E * rank) // world, (E * (rank + 1)) // world
+    rows = (e0 * B, e1 * B)
+    stream = torch.cuda.current_stream(dev)
+    ctx = capi.Context(local_rank, stream.cuda_stream)
+    t_plan = time.perf_counter()
+    plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows)
+    t_plan = time.perf_counter() - t_plan
+    nloc = rows[1] - rows[0]
+    flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
+    f64 = torch.float64
+    s_d = torch.from_numpy(pr["s"]).to(dev)
+    Dz0_d = torch.from_numpy(np.asfortranarray(pr["Dz0"][rows[0]:rows[1]]).T.copy()).to(dev)  # (nD, nloc) = column-major
+    c_d = torch.from_numpy(np.asfortranarray(pr["c"][rows[0]:rows[1]]).T.copy()).to(dev)
+    scal_d = torch.zeros(4, dtype=f64, device=dev)
+    grad_d = torch.zeros(plan.m, dtype=f64, device=dev)
+    hval_d = torch.zeros(max(plan.nnzH, 1), dtype=f64, device=dev)
+    flush = not args.no_flush
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- warm-up
+    plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, args.warmup, flush, split=False)
+    launches0 = capi.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    ms_total, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
+                                                     args.steps, flush, split=False)
+    launches = capi.launch_count() - launches0
+    barrier()
+    wall = time.perf_counter() - wall0
+    # per-kernel split (separate pass, not part of `value`)
+    _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
+                                               max(10, args.steps // 2), flush, split=True)
+    # ---- e2e through host buffers
+    s_h = pr["s"].copy()
+    Dz0_h = np.asfortranarray(pr["Dz0"][rows[0]:rows[1]])
+    c_h = np.asfortranarray(pr["c"][rows[0]:rows[1]])
+    plan.assemble_host(s_h, Dz0_h, c_h, args.t, flags, upload_inputs=True)
+    for _ in range(2):
+        plan.assemble_host(s_h, None, None, args.t, flags, upload_inputs=False)
+    barrier()
+    e2e_steps = max(5, min(args.steps, 20))
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = plan.assemble_host(s_h, None, None, args.t, flags, upload_inputs=False)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    clocks = sampler.stop()
+
+    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms], dtype=f64, device=dev)
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    ms_total, ms_elem, ms_gather, e2e_ms = (float(v) for v in vals.cpu())
+
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        info = plan.info
+        alg = info["alg_bytes"]
+        # element kernel share of the algorithmic bytes: everything except the restriction line
+        nnzS = 154 * info["elements"] if info["nodes_per_element"] == 7 else 0
+        restr = nnzS * 8 + pr["R"].nnz * 24 + info["nnzH"] * 8
+        alg_elem = alg - restr
+        ach = alg_elem / (ms_elem * 1e-3) / 1e9 if ms_elem > 0 else 0.0
+        ach_all = alg / (ms_total * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": ms_total, "unit": "ms", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_total, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly: n={n} quadrature points, "
+                                   f"m={info['m']} dofs, nnz(R'HR)={info['nnzH']}",
+                       "l2": "flushed between steps (256 MiB write)" if flush else "not flushed",
+                       "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
+                       "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
+                       "rows_per_rank": nloc},
+            "clocks": clocks,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(plan.m * 8),
+                    "d2h_bytes_per_step": int((plan.m + plan.nnzH + 4) * 8)},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "element_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes": int(alg_elem), "kernel_ms": ms_elem,
+                         "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all,
+                                      "frac": ach_all / peak, "gather_ms": ms_gather}},
+            "wall_s_timed_region": wall,
+        }
+        try:
+            cpu_ms = cpu_assembly_sample(pr, args.t, args.cpu_reps) if world == 1 else None
+        except Exception as exc:  # pragma: no cover
+            cpu_ms = None
+            line["cpu_baseline_error"] = str(exc)
+        if cpu_ms is not None:
+            line["cpu_baseline"] = {"value": cpu_ms, "unit": "ms", "cores": 1, "kind": "port",
+                                    "sample": f"{args.cpu_reps} full assemblies (f0+f1+f2) at L={args.L}, scipy CSC restatement"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

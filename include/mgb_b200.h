@@ -1,0 +1,145 @@
+/*
+ * mgb_b200.h - C ABI of libmgb_b200.so: B200-native (sm_100a) Newton-step assembly for the
+ * MultiGridBarrier(MPI).jl hot path.
+ *
+ * The reference has no FFI boundary of its own: it plugs into the solver through Julia multiple
+ * dispatch (reference src/MultiGridBarrierMPI.jl:62-192).  Every entry point below therefore cites
+ * the Julia method / upstream body whose work it replaces; the `ccall` stubs a maintainer would add
+ * are in INTEGRATION.md and multigridbarriermpi.jl_b200/julia/MGBB200.jl.
+ *
+ * Conventions
+ *   - plain C types only; all indices int32 (HPCSparseMatrix default Ti=Int32, src:260), values double;
+ *   - CSR inputs are 0-based or 1-based (index_base), i.e. the local CSR view of an HPCSparseMatrix
+ *     (rowptr/colval of src:216-221, a12 in SURVEY.md) can be passed zero-copy from Julia (base 1);
+ *   - dense n x k matrices are column-major (Julia layout; column c is contiguous);
+ *   - every function returns 0 on success, non-zero on error; mgb_last_error() gives the message of
+ *     the last failing call on the calling thread.  Nothing here calls exit()/abort().
+ *   - NaN/Inf in an iterate is data, not an error: it is reported through `all_finite` like
+ *     amgb_all_isfinite (src:121-133).
+ *   - *_dev pointers are device pointers on the context's GPU; *_host pointers are host memory.
+ */
+#ifndef MGB_B200_H
+#define MGB_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgb_ctx mgb_ctx;
+typedef struct mgb_plan mgb_plan;
+
+/* Local CSR block of a sparse operator (host memory). */
+typedef struct {
+    int64_t nrows, ncols, nnz;
+    const int32_t* rowptr; /* nrows+1 */
+    const int32_t* colidx; /* nnz */
+    const double* vals;    /* nnz */
+    int32_t index_base;    /* 0 (C) or 1 (Julia) */
+} mgb_csr;
+
+/* Pointwise convex set / barrier (upstream convex_Euclidian_power): on the Dz row y,
+ * F = -log(s^(2/p) - |q|^2) - mu(p) log s with (q..., s) = y[idx] (0-based idx, last entry = s);
+ * slack != 0 adds the last Dz column to s (feasibility phase). */
+typedef struct {
+    int32_t kind; /* MGB_BARRIER_EUCLIDIAN_POWER */
+    int32_t nidx;
+    int32_t idx[8];
+    double p;
+    int32_t slack;
+} mgb_barrier;
+
+#define MGB_BARRIER_EUCLIDIAN_POWER 1
+
+/* what an assemble call computes */
+#define MGB_WANT_F0 1   /* objective            (upstream f0)                                   */
+#define MGB_WANT_GRAD 2 /* gradient  R' sum_k D_k' (w .* (F1_k + t c_k))       (upstream f1)    */
+#define MGB_WANT_HESS 4 /* Hessian values on the fixed pattern, R' (sum D_j' diag D_k) R (f2)   */
+#define MGB_STORE_DZ 8  /* also store Dz = Dz0 + (D R) s  (n x nD, apply_D)                     */
+
+/* plan kinds reported by mgb_plan_info */
+#define MGB_PATH_ELEMENT 1 /* fused element-block kernels (broken-element operators detected) */
+#define MGB_PATH_CSR 2     /* general CSR kernels                                              */
+
+const char* mgb_last_error(void);
+int mgb_version(void);
+
+/* Context = one GPU + one stream.  stream==NULL creates an owned stream.  Not re-entrant per ctx
+ * (one Julia thread drives a rank: SURVEY.md 8b). */
+int mgb_ctx_create(int device, void* stream, mgb_ctx** out);
+int mgb_ctx_destroy(mgb_ctx* ctx);
+int mgb_ctx_sync(mgb_ctx* ctx);
+
+/* Symbolic phase, once per multigrid level.  Replaces the per-Newton-step structural work of the
+ * reference: amgb_diag's spdiagm + structural hash (src:137-147, tools/profile_hash.jl:41-66), the
+ * SpGEMM plans of D_j' * diag * D_k and R' * H * R (test/test_map_rows_compare.jl:102-123,165-171).
+ *   D[k]  : nD operators, each n x N  (upstream D0[L,k] = hcat(Z.., op, ..Z), test/test_d0_construction.jl:91-100)
+ *   R     : N x m  (upstream R_fine[l] = blockdiag(...), test/test_d0_construction.jl:81-83)
+ *   x     : n x dim column-major nodes, w : n quadrature weights (host)
+ *   row0,row1 : this rank's block of quadrature rows [row0,row1) (HPCSparseArrays row partition, a13);
+ *               pass 0,n for a single rank.
+ *   force_path: 0 = auto, MGB_PATH_ELEMENT / MGB_PATH_CSR to force one.
+ *   ctx == NULL builds a symbolic-only plan (mgb_plan_info / mgb_plan_pattern work; every numeric
+ *   entry point fails: there is no CPU numeric path). */
+int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R,
+                    int32_t dim, const double* x_host, const double* w_host,
+                    const mgb_barrier* barrier, int64_t row0, int64_t row1, int32_t force_path,
+                    mgb_plan** out);
+int mgb_plan_destroy(mgb_plan* plan);
+
+/* sizes: info[0]=path, [1]=n_local, [2]=nD, [3]=m, [4]=nnzH, [5]=elements, [6]=nodes/element,
+ * [7]=local cols/var, [8]=slots/element, [9]=Hessian contributions, [10]=gradient contributions,
+ * [11]=plan device bytes, [12]=N, [13]=nu, [14]=algorithmic bytes per assembly (SURVEY 8d formula) */
+int mgb_plan_info(const mgb_plan* plan, int64_t* info, int32_t ninfo);
+
+/* Fixed sparsity pattern of R' H R (CSR, 0-based, sorted columns) -> host buffers. */
+int mgb_plan_pattern(const mgb_plan* plan, int32_t* rowptr_host, int32_t* colidx_host);
+
+/* Numeric phase (per Newton step / line-search point); everything on the ctx stream, asynchronous.
+ *   s_dev   : m      Newton unknown on this level (z = z0 + R s)
+ *   Dz0_dev : n_local x nD column-major, D*z0 for the local rows (NULL = 0)
+ *   c_dev   : n_local x nD column-major linear term (upstream c), scaled by t inside
+ *   flags   : MGB_WANT_* | MGB_STORE_DZ
+ * outputs (device; may be NULL when not requested):
+ *   scal_dev: 4 doubles {f0, all_finite (1.0/0.0), <c,Dz>_w, reserved}
+ *   grad_dev: m,  hval_dev: nnzH (same order as mgb_plan_pattern),  Dz_dev: n_local x nD.
+ * Replaces upstream f0/f1/f2 (map_rows at src:161-170 + apply_D test/test_apply_d.jl:44 +
+ * the triple-product loop test/test_map_rows_compare.jl:102-123 + R'..R :165-171). */
+int mgb_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev,
+                 double t, int32_t flags, double* scal_dev, double* grad_dev, double* hval_dev,
+                 double* Dz_dev);
+
+/* Same call through HOST buffers (what a CPU-array caller of f1/f2 sees): copies s (and, when
+ * upload_inputs!=0, Dz0 and c) to the device, runs mgb_assemble, copies the requested results back
+ * and synchronises. */
+int mgb_assemble_host(mgb_plan* plan, const double* s_host, const double* Dz0_host,
+                      const double* c_host, int32_t upload_inputs, double t, int32_t flags,
+                      double* scal_host, double* grad_host, double* hval_host, double* Dz_host);
+
+/* Separately callable pieces (the reference's own unit seams). */
+/* apply_D: Dz = Dz0 + (D R) s   (test/test_apply_d.jl:44-49) */
+int mgb_apply_D(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, double* Dz_dev);
+/* map_rows of the barrier over (x, Dz): which = 0 -> F (n), 1 -> F1 (n x nD), 2 -> F2 (n x nD^2,
+ * column (j*nD+k), test/test_map_rows_compare.jl:62-73).  (src:161-170) */
+int mgb_map_barrier(mgb_plan* plan, const double* Dz_dev, int32_t which, double* out_dev);
+/* amgb_all_isfinite (src:121-133): *flag_host = 1 if every entry finite. */
+int mgb_all_isfinite(mgb_ctx* ctx, const double* v_dev, int64_t len, int32_t* flag_host);
+/* amgb_diag (src:137-147) as a device map: out = w .* y[:,col] (the diagonal the reference wraps in a sparse matrix) */
+int mgb_diag_scale(mgb_ctx* ctx, const double* w_dev, const double* y_dev, int64_t n, int64_t ld,
+                   int32_t col, double* out_dev);
+
+/* timing helper: runs `reps` assemblies back to back on the ctx stream, returns average ms measured
+ * with CUDA events on that stream (bench.py uses it so the events sit on the launching stream). */
+int mgb_time_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev,
+                      double t, int32_t flags, double* scal_dev, double* grad_dev, double* hval_dev,
+                      int32_t reps, int32_t flush_l2, float* ms_total, float* ms_kernel_element,
+                      float* ms_kernel_gather);
+
+/* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
+int64_t mgb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB_B200_H */

@@ -1,0 +1,243 @@
+"""ctypes binding of libmgb_b200.so (include/mgb_b200.h).
+
+This is the Python twin of the Julia ``ccall`` shim in ``julia/MGBB200.jl``: the reference's host
+language (Julia) is absent from this image, so the C ABI is exercised from here.  There is no CPU
+fallback: if the library or a GPU is missing every numeric call raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import build as _build
+
+WANT_F0, WANT_GRAD, WANT_HESS, STORE_DZ = 1, 2, 4, 8
+PATH_ELEMENT, PATH_CSR = 1, 2
+BARRIER_EUCLIDIAN_POWER = 1
+
+EXPORTS = [
+    "mgb_last_error", "mgb_version", "mgb_ctx_create", "mgb_ctx_destroy", "mgb_ctx_sync", "mgb_plan_create",
+    "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
+    "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
+]
+
+
+class MgbError(RuntimeError):
+    pass
+
+
+class _Csr(C.Structure):
+    _fields_ = [("nrows", C.c_int64), ("ncols", C.c_int64), ("nnz", C.c_int64),
+                ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
+                ("index_base", C.c_int32)]
+
+
+class _Barrier(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("nidx", C.c_int32), ("idx", C.c_int32 * 8), ("p", C.c_double),
+                ("slack", C.c_int32)]
+
+
+_lib = None
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load(build_if_missing: bool = True):
+    """Load the shared library (building it in-tree with nvcc when absent and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.needs_build():
+        try:
+            _build.build()
+        except Exception as exc:  # no nvcc on this box: fall through to the existence check
+            if not os.path.exists(path):
+                raise MgbError(f"libmgb_b200.so is not built and cannot be built here: {exc}") from exc
+    if not os.path.exists(path):
+        raise MgbError("libmgb_b200.so missing: run __graft_entry__.build() (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.mgb_last_error.restype = C.c_char_p
+    lib.mgb_version.restype = C.c_int
+    lib.mgb_launch_count.restype = C.c_int64
+    lib.mgb_ctx_create.argtypes = [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mgb_ctx_destroy.argtypes = [C.c_void_p]
+    lib.mgb_ctx_sync.argtypes = [C.c_void_p]
+    lib.mgb_plan_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_Csr), C.POINTER(_Csr), C.c_int32,
+                                    C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int64, C.c_int64, C.c_int32,
+                                    C.POINTER(C.c_void_p)]
+    lib.mgb_plan_destroy.argtypes = [C.c_void_p]
+    lib.mgb_plan_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mgb_plan_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mgb_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
+                                 C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mgb_assemble_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
+                                      C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mgb_apply_D.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mgb_map_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.mgb_all_isfinite.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+    lib.mgb_diag_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
+    lib.mgb_time_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
+                                      C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise MgbError(load().mgb_last_error().decode("utf-8", "replace"))
+
+
+def _ptr(a) -> Optional[int]:
+    """device pointer of a torch tensor / host pointer of a numpy array / None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    if isinstance(a, int):
+        return a
+    return a.data_ptr()
+
+
+def launch_count() -> int:
+    return int(load().mgb_launch_count())
+
+
+class Context:
+    """One GPU + one stream (mgb_ctx)."""
+
+    def __init__(self, device: int = 0, stream: Optional[int] = None):
+        lib = load()
+        h = C.c_void_p()
+        _check(lib.mgb_ctx_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def sync(self):
+        _check(load().mgb_ctx_sync(self._h))
+
+    def all_isfinite(self, v_dev, length: int) -> bool:
+        flag = C.c_int32(0)
+        _check(load().mgb_all_isfinite(self._h, _ptr(v_dev), int(length), C.byref(flag)))
+        return bool(flag.value)
+
+    def diag_scale(self, w_dev, y_dev, n: int, ld: int, col: int, out_dev):
+        _check(load().mgb_diag_scale(self._h, _ptr(w_dev), _ptr(y_dev), int(n), int(ld), int(col), _ptr(out_dev)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().mgb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _csr_struct(A: sp.spmatrix, keep: list) -> _Csr:
+    A = sp.csr_matrix(A)
+    A.sort_indices()
+    if A.nnz >= 2 ** 31:
+        raise MgbError("operator has >= 2^31 stored entries; Int32 indices (reference default Ti=Int32) overflow")
+    rp = np.ascontiguousarray(A.indptr, dtype=np.int32)
+    ci = np.ascontiguousarray(A.indices, dtype=np.int32)
+    va = np.ascontiguousarray(A.data, dtype=np.float64)
+    keep.extend([rp, ci, va])
+    return _Csr(A.shape[0], A.shape[1], A.nnz, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 0)
+
+
+class Plan:
+    """Per-level symbolic plan (mgb_plan): frozen sparsity of R'HR plus replay lists.
+    ``ctx=None`` builds a symbolic-only plan (pattern/info queries; numeric calls raise)."""
+
+    INFO = ["path", "n_local", "nD", "m", "nnzH", "elements", "nodes_per_element", "cols_per_var",
+            "slots_per_element", "hess_contribs", "grad_contribs", "plan_bytes", "N", "nu", "alg_bytes"]
+
+    def __init__(self, ctx: Context, D: Sequence[sp.spmatrix], R: sp.spmatrix, x: np.ndarray, w: np.ndarray,
+                 idx: Sequence[int], p: float, slack: bool = False, rows=None, force_path: int = 0):
+        lib = load()
+        self.ctx = ctx
+        n = D[0].shape[0]
+        keep: list = []
+        Ds = (_Csr * len(D))(*[_csr_struct(d, keep) for d in D])
+        Rs = _csr_struct(R, keep)
+        bar = _Barrier()
+        bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
+        for j, v in enumerate(idx):
+            bar.idx[j] = int(v)
+        x = np.asfortranarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        row0, row1 = (0, n) if rows is None else rows
+        h = C.c_void_p()
+        _check(lib.mgb_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1], x.ctypes.data, w.ctypes.data,
+                                   C.byref(bar), int(row0), int(row1), int(force_path), C.byref(h)))
+        self._h = h
+        info = np.zeros(15, dtype=np.int64)
+        _check(lib.mgb_plan_info(h, info.ctypes.data, 15))
+        self.info = dict(zip(self.INFO, (int(v) for v in info)))
+        self.n_local, self.nD, self.m, self.nnzH = (self.info[k] for k in ("n_local", "nD", "m", "nnzH"))
+        self._pattern = None
+
+    def pattern(self):
+        """(rowptr, colidx) of the fixed CSR pattern of R'HR (0-based)."""
+        if self._pattern is None:
+            rp = np.zeros(self.m + 1, dtype=np.int32)
+            ci = np.zeros(max(self.nnzH, 1), dtype=np.int32)
+            _check(load().mgb_plan_pattern(self._h, rp.ctypes.data, ci.ctypes.data))
+            self._pattern = (rp, ci[: self.nnzH])
+        return self._pattern
+
+    def assemble(self, s_dev, Dz0_dev, c_dev, t: float, flags: int, scal_dev=None, grad_dev=None, hval_dev=None,
+                 Dz_dev=None):
+        _check(load().mgb_assemble(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags),
+                                   _ptr(scal_dev), _ptr(grad_dev), _ptr(hval_dev), _ptr(Dz_dev)))
+
+    def assemble_host(self, s, Dz0, c, t: float, flags: int, upload_inputs: bool = True):
+        """Host-buffer call; returns dict(scal, grad, hval, Dz) of numpy arrays (only requested ones)."""
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        assert s.shape == (self.m,)
+        nd = self.n_local * self.nD
+        Dz0 = None if Dz0 is None else np.asfortranarray(Dz0, dtype=np.float64)
+        c = None if c is None else np.asfortranarray(c, dtype=np.float64)
+        scal = np.zeros(4)
+        grad = np.zeros(self.m) if flags & WANT_GRAD else None
+        hval = np.zeros(self.nnzH) if flags & WANT_HESS else None
+        Dz = np.zeros((self.n_local, self.nD), order="F") if flags & STORE_DZ else None
+        _check(load().mgb_assemble_host(self._h, _ptr(s), _ptr(Dz0), _ptr(c), int(upload_inputs), float(t), int(flags),
+                                        _ptr(scal), _ptr(grad), _ptr(hval), _ptr(Dz)))
+        assert nd >= 0
+        return dict(scal=scal, grad=grad, hval=hval, Dz=Dz)
+
+    def apply_D(self, s_dev, Dz0_dev, Dz_dev):
+        _check(load().mgb_apply_D(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(Dz_dev)))
+
+    def map_barrier(self, Dz_dev, which: int, out_dev):
+        _check(load().mgb_map_barrier(self._h, _ptr(Dz_dev), int(which), _ptr(out_dev)))
+
+    def time_assemble(self, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, reps: int,
+                      flush_l2: bool, split: bool = True):
+        tot, tel, tga = C.c_float(0), C.c_float(0), C.c_float(0)
+        _check(load().mgb_time_assemble(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags),
+                                        _ptr(scal_dev), _ptr(grad_dev), _ptr(hval_dev), int(reps), int(flush_l2),
+                                        C.byref(tot), C.byref(tel) if split else None, C.byref(tga) if split else None))
+        return tot.value, tel.value, tga.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().mgb_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

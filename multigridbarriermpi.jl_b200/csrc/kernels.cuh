@@ -1,0 +1,511 @@
+// Numeric phase kernels (sm_100a).  Float64 throughout; no atomics on the value arrays; every
+// reduction has a fixed tree so results are bit-reproducible run to run.
+//
+//   element_kernel : one LPE-lane group per broken element.  Fuses, per quadrature point kept in
+//                    registers:  z gather (R), apply_D (reference test/test_apply_d.jl:44), the
+//                    barrier map F/F1/F2 (src/MultiGridBarrierMPI.jl:161-170), w.*y scaling
+//                    (amgb_diag, src:137-147), the element-local part of D_j' diag D_k and of
+//                    R'(.)R (test/test_map_rows_compare.jl:102-123,165-171) and of the gradient.
+//                    Cross-point sums use a transposing butterfly over warp shuffles.
+//   gather_kernel  : replays the frozen contribution lists into the preallocated CSR value array
+//                    and the gradient; finishes the scalar reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgb {
+
+struct ElemParams {
+    // geometry / plan (device)
+    int64_t E, nloc;
+    const int32_t* lcols;    // [NU][E][LPE]
+    const double* opd;       // [dim][B][nloc]
+    const double* idd;       // coarse [NU][B][nloc]
+    const double* own_val;   // fine [NU][nloc]
+    const uint8_t* own_lq;   // fine [NU][nloc]
+    const double* w;         // nloc
+    // per call
+    const double* s;         // m
+    const double* Dz0;       // nloc x ND or null
+    const double* c;         // nloc x ND
+    double t, p;
+    // outputs
+    double* sel;             // E*NS
+    double* rel;             // E*NU*LPE
+    double* part;            // gridDim.x * 4  {f0, cdot, nonfinite count, -}
+    double* Dz;              // nloc x ND or null
+    int off_uu, off_us, off_ss, off_ut, off_st, off_tt, NS;
+};
+
+template <int V>
+struct Pow2Ceil { static constexpr int value = (V <= 1) ? 1 : 2 * Pow2Ceil<(V + 1) / 2>::value; };
+
+__device__ __forceinline__ double shfl_d(double v, int src, int width) {
+    return __shfl_sync(0xffffffffu, v, src, width);
+}
+__device__ __forceinline__ double shfl_xor_d(double v, int mask) {
+    return __shfl_xor_sync(0xffffffffu, v, mask);
+}
+
+// Transposing butterfly: every lane of an LPE-lane group holds NV partial values; afterwards lane l
+// holds the group sums of entries [l*NV/LPE, (l+1)*NV/LPE) in v[0 .. NV/LPE).
+template <int NV, int LPE>
+__device__ __forceinline__ void group_reduce(double (&v)[NV], int lane) {
+    static_assert(NV % LPE == 0, "NV must be a multiple of the group width");
+    int len = NV;
+#pragma unroll
+    for (int M = LPE / 2; M >= 1; M >>= 1) {
+        const int half = len / 2;
+        const bool up = (lane & M) != 0;
+#pragma unroll
+        for (int r = 0; r < NV / 2; ++r) {
+            if (r < half) {
+                const double lo = v[r], hi = v[r + half];
+                const double send = up ? lo : hi;
+                const double keep = up ? hi : lo;
+                v[r] = keep + shfl_xor_d(send, M);
+            }
+        }
+        len = half;
+    }
+}
+
+struct BarrierOut {
+    double F, gq[3], gs, Hqq[3][3], Hqs[3], Hss;
+    bool feasible;
+};
+
+// Euclidian power cone barrier on (q_0..q_{D-1}, s): F = -log(s^a - |q|^2) - mu log s, a = 2/p.
+template <int D, bool WANT_F, bool WANT_D>
+__device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, double p, BarrierOut& o) {
+    const double a = 2.0 / p;
+    const double mu = (p == 1.0) ? 0.0 : ((p < 2.0) ? 1.0 : 2.0);
+    double sa, sa1, sa2;  // s^a, s^(a-1), s^(a-2)
+    const double is = 1.0 / s;
+    if (p == 1.0) { sa = s * s; sa1 = s; sa2 = 1.0; }
+    else if (p == 2.0) { sa = s; sa1 = 1.0; sa2 = is; }
+    else { sa = pow(s, a); sa1 = sa * is; sa2 = sa1 * is; }
+    double qq = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) qq += q[j] * q[j];
+    const double phi = sa - qq;
+    o.feasible = (s > 0.0) && (phi > 0.0);
+    if (WANT_F) o.F = o.feasible ? (-log(phi) - mu * log(s)) : __longlong_as_double(0x7ff0000000000000LL);
+    if (WANT_D) {
+        const double ip = 1.0 / phi, ip2 = ip * ip;
+        const double ds = a * sa1;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            o.gq[j] = 2.0 * q[j] * ip;
+            o.Hqs[j] = -2.0 * q[j] * ds * ip2;
+#pragma unroll
+            for (int j2 = 0; j2 < D; ++j2) o.Hqq[j][j2] = 4.0 * q[j] * q[j2] * ip2 + (j == j2 ? 2.0 * ip : 0.0);
+        }
+        o.gs = -ds * ip - mu * is;
+        o.Hss = -a * (a - 1.0) * sa2 * ip + ds * ds * ip2 + mu * is * is;
+    }
+}
+
+// FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
+template <int B, int D, bool SLACK, bool FINE, int FLAGS>
+__global__ void __launch_bounds__(128) element_kernel(const ElemParams P) {
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr int ND = D + 2 + (SLACK ? 1 : 0);
+    constexpr int NU = 2 + (SLACK ? 1 : 0);
+    constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
+    constexpr int NTRI = (B * (B + 1) / 2 + LPE - 1) / LPE * LPE;
+    constexpr int NFULL = (B * B + LPE - 1) / LPE * LPE;
+
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = tid / LPE;
+    const int l = (int)(tid % LPE);
+    const bool act_e = e < P.E;
+    const bool act = act_e && (l < B);
+    const int64_t i = act ? e * B + l : 0;
+    const int64_t n = P.nloc;
+
+    // ---- gather the element's unknowns: lane q holds z[var][q]
+    double zl[NU];
+#pragma unroll
+    for (int v = 0; v < NU; ++v) {
+        const int32_t col = act_e ? __ldg(&P.lcols[((int64_t)v * P.E + e) * LPE + l]) : -1;
+        zl[v] = (col >= 0) ? __ldg(&P.s[col]) : 0.0;
+    }
+    // ---- operator rows of this point in element-local columns
+    double a[D][B];
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+        for (int q = 0; q < B; ++q) a[k][q] = act ? __ldg(&P.opd[((int64_t)k * B + q) * n + i]) : 0.0;
+    double aid[FINE ? 1 : NU][FINE ? 1 : B];
+    double oval[NU];
+    int olq[NU];
+    bool oh[NU];  // this point owns a column of variable v (false: eliminated dof, e.g. Dirichlet)
+    if (FINE) {
+#pragma unroll
+        for (int v = 0; v < NU; ++v) {
+            oval[v] = act ? __ldg(&P.own_val[(int64_t)v * n + i]) : 0.0;
+            olq[v] = act ? (int)__ldg(&P.own_lq[(int64_t)v * n + i]) : 255;
+            oh[v] = olq[v] != 255;
+            if (!oh[v]) { oval[v] = 0.0; olq[v] = 0; }
+        }
+    } else {
+#pragma unroll
+        for (int v = 0; v < NU; ++v)
+#pragma unroll
+            for (int q = 0; q < B; ++q) aid[FINE ? 0 : v][FINE ? 0 : q] = act ? __ldg(&P.idd[((int64_t)v * B + q) * n + i]) : 0.0;
+    }
+    double wi = act ? __ldg(&P.w[i]) : 0.0;
+    double cc[ND], dz[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        cc[k] = act ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
+        dz[k] = (act && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+    }
+    // ---- apply_D: Dz = Dz0 + (D R) s
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+        const double zq = shfl_d(zl[0], q, LPE);
+#pragma unroll
+        for (int k = 0; k < D; ++k) dz[1 + k] = fma(a[k][q], zq, dz[1 + k]);
+        if (!FINE) dz[0] = fma(aid[0][FINE ? 0 : q], zq, dz[0]);
+    }
+    if (FINE) {
+#pragma unroll
+        for (int v = 0; v < NU; ++v) {
+            const double zo = shfl_d(zl[v], olq[v], LPE);
+            const int k = (v == 0) ? 0 : D + v;
+            dz[k] = fma(oval[v], zo, dz[k]);
+        }
+    } else {
+#pragma unroll
+        for (int v = 1; v < NU; ++v)
+#pragma unroll
+            for (int q = 0; q < B; ++q) dz[D + v] = fma(aid[FINE ? 0 : v][FINE ? 0 : q], shfl_d(zl[v], q, LPE), dz[D + v]);
+    }
+    if (WDZ && act && P.Dz) {
+#pragma unroll
+        for (int k = 0; k < ND; ++k) P.Dz[(int64_t)k * n + i] = dz[k];
+    }
+    // ---- barrier at this point
+    double qv[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) qv[j] = dz[1 + j];
+    double sv = dz[D + 1];
+    if (SLACK) sv += dz[D + 2];
+    if (!act) { sv = 1.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) qv[j] = 0.0; }
+    BarrierOut bo;
+    barrier_eval<D, WF, (WG || WH)>(qv, sv, P.p, bo);
+
+    // ---- objective / feasibility partials (fixed-order block reduction)
+    {
+        double cd = 0.0;
+#pragma unroll
+        for (int k = 0; k < ND; ++k) cd = fma(cc[k], dz[k], cd);
+        double v0 = 0.0, v1 = act ? wi * cd : 0.0;
+        if (WF) v0 = act ? wi * bo.F : 0.0;
+        double v2 = (act && !bo.feasible) ? 1.0 : 0.0;
+#pragma unroll
+        for (int mk = 16; mk >= 1; mk >>= 1) {
+            v0 += shfl_xor_d(v0, mk);
+            v1 += shfl_xor_d(v1, mk);
+            v2 += shfl_xor_d(v2, mk);
+        }
+        __shared__ double red[3][4];
+        const int wid = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) { red[0][wid] = v0; red[1][wid] = v1; red[2][wid] = v2; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+            const int nw = blockDim.x >> 5;
+            for (int r = 0; r < nw; ++r) { s0 += red[0][r]; s1 += red[1][r]; s2 += red[2][r]; }
+            P.part[(int64_t)blockIdx.x * 4 + 0] = s0;
+            P.part[(int64_t)blockIdx.x * 4 + 1] = s1;
+            P.part[(int64_t)blockIdx.x * 4 + 2] = s2;
+        }
+    }
+    if (!(WG || WH)) return;
+    // an infeasible point produces NaN/Inf values; they flow to the outputs as data (the caller
+    // reads all_finite, like amgb_all_isfinite in the reference, src:121-133)
+
+    // ---- gradient: r[var][q] = sum_points sum_k a_k[q] * w (F1_k + t c_k)
+    if (WG) {
+        double gy[ND];
+        gy[0] = wi * (P.t * cc[0]);
+#pragma unroll
+        for (int j = 0; j < D; ++j) gy[1 + j] = wi * (bo.gq[j] + P.t * cc[1 + j]);
+        gy[D + 1] = wi * (bo.gs + P.t * cc[D + 1]);
+        if (SLACK) gy[D + 2] = wi * (bo.gs + P.t * cc[D + 2]);
+        double ru[LPE];
+#pragma unroll
+        for (int q = 0; q < LPE; ++q) {
+            double r = 0.0;
+            if (q < B) {
+#pragma unroll
+                for (int k = 0; k < D; ++k) r = fma(a[k][q < B ? q : 0], gy[1 + k], r);
+                if (FINE) r += (q == olq[0]) ? oval[0] * gy[0] : 0.0;
+                else r = fma(aid[0][FINE ? 0 : (q < B ? q : 0)], gy[0], r);
+            }
+            ru[q] = r;
+        }
+        group_reduce<LPE, LPE>(ru, l);
+        if (act_e) P.rel[(e * NU + 0) * LPE + l] = ru[0];
+        if (FINE) {
+#pragma unroll
+            for (int v = 1; v < NU; ++v)
+                if (act && oh[v]) P.rel[(e * NU + v) * LPE + olq[v]] = oval[v] * gy[D + v];
+        } else {
+#pragma unroll
+            for (int v = 1; v < NU; ++v) {
+                double rs[LPE];
+#pragma unroll
+                for (int q = 0; q < LPE; ++q) rs[q] = (q < B) ? aid[FINE ? 0 : v][FINE ? 0 : (q < B ? q : 0)] * gy[D + v] : 0.0;
+                group_reduce<LPE, LPE>(rs, l);
+                if (act_e) P.rel[(e * NU + v) * LPE + l] = rs[0];
+            }
+        }
+    }
+    if (!WH) return;
+
+    // ---- Hessian: element-local blocks of sum_jk a_j' (w Y_jk) a_k
+    double* sel = P.sel + e * (int64_t)P.NS;
+    // u-u block (derivative operators only: the u.id row of F2 is identically zero)
+    {
+        double T[D][B];
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+#pragma unroll
+            for (int q = 0; q < B; ++q) {
+                double tacc = 0.0;
+#pragma unroll
+                for (int j2 = 0; j2 < D; ++j2) tacc = fma(wi * bo.Hqq[j][j2], a[j2][q], tacc);
+                T[j][q] = tacc;
+            }
+        double v[NTRI];
+#pragma unroll
+        for (int r = 0; r < NTRI; ++r) v[r] = 0.0;
+#pragma unroll
+        for (int q = 0; q < B; ++q)
+#pragma unroll
+            for (int q2 = q; q2 < B; ++q2) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) acc = fma(a[j][q], T[j][q2], acc);
+                v[q * B - q * (q - 1) / 2 + (q2 - q)] = acc;
+            }
+        group_reduce<NTRI, LPE>(v, l);
+        if (act_e) {
+#pragma unroll
+            for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + l * (NTRI / LPE) + r] = v[r];
+        }
+    }
+    // u-s (and u-slack) blocks
+    double bs[B];
+#pragma unroll
+    for (int q = 0; q < B; ++q) {
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(a[j][q], wi * bo.Hqs[j], acc);
+        bs[q] = acc;
+    }
+    const double vss = wi * bo.Hss;
+    if (FINE) {
+        if (act && oh[1]) {
+#pragma unroll
+            for (int q = 0; q < B; ++q) sel[P.off_us + q * LPE + olq[1]] = bs[q] * oval[1];
+            sel[P.off_ss + olq[1]] = vss * oval[1] * oval[1];
+        }
+        if (SLACK && act && oh[SLACK ? 2 : 0]) {
+            constexpr int VT = SLACK ? 2 : 0;
+#pragma unroll
+            for (int q = 0; q < B; ++q) sel[P.off_ut + q * LPE + olq[VT]] = bs[q] * oval[VT];
+            if (oh[1]) sel[P.off_st + l] = vss * oval[1] * oval[VT];
+            sel[P.off_tt + olq[VT]] = vss * oval[VT] * oval[VT];
+        }
+    } else {
+#pragma unroll
+        for (int v2 = 1; v2 < NU; ++v2) {  // u x {s, slack}
+            double v[NFULL];
+#pragma unroll
+            for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = 0; q2 < B; ++q2) v[q * B + q2] = bs[q] * aid[FINE ? 0 : v2][FINE ? 0 : q2];
+            group_reduce<NFULL, LPE>(v, l);
+            const int off = (v2 == 1) ? P.off_us : P.off_ut;
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NFULL / LPE; ++r) sel[off + l * (NFULL / LPE) + r] = v[r];
+            }
+        }
+#pragma unroll
+        for (int v1 = 1; v1 < NU; ++v1) {  // {s,slack} x {s,slack} symmetric diagonal blocks
+            double v[NTRI];
+#pragma unroll
+            for (int r = 0; r < NTRI; ++r) v[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = q; q2 < B; ++q2)
+                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = vss * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
+            group_reduce<NTRI, LPE>(v, l);
+            const int off = (v1 == 1) ? P.off_ss : P.off_tt;
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NTRI / LPE; ++r) sel[off + l * (NTRI / LPE) + r] = v[r];
+            }
+        }
+        if (SLACK) {  // s x slack full block
+            double v[NFULL];
+#pragma unroll
+            for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = 0; q2 < B; ++q2)
+                    v[q * B + q2] = vss * aid[FINE ? 0 : 1][FINE ? 0 : q] * aid[FINE ? 0 : (SLACK ? 2 : 0)][FINE ? 0 : q2];
+            group_reduce<NFULL, LPE>(v, l);
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + l * (NFULL / LPE) + r] = v[r];
+            }
+        }
+    }
+}
+
+struct GatherParams {
+    int64_t nnzH, m;
+    const int64_t* h_cptr;
+    const int32_t* h_cidx;
+    const int64_t* g_cptr;
+    const int32_t* g_cidx;
+    const double* sel;
+    const double* rel;
+    double* hval;
+    double* grad;
+    const double* part;
+    int64_t nparts;
+    double* scal;  // {f0, all_finite, cdot, nonfinite count}
+    double t;
+    int want_h, want_g;
+};
+
+// thread per output entry: H values first, then gradient entries; the last block folds the scalar
+// partials in a fixed order.
+__global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
+    const int64_t nh = P.want_h ? P.nnzH : 0;
+    const int64_t ng = P.want_g ? P.m : 0;
+    const int64_t nblk_work = (nh + ng + blockDim.x - 1) / blockDim.x;
+    if ((int64_t)blockIdx.x < nblk_work) {
+        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        if (tid < nh) {
+            const int64_t c0 = __ldg(&P.h_cptr[tid]), c1 = __ldg(&P.h_cptr[tid + 1]);
+            double acc = 0.0;
+            for (int64_t cix = c0; cix < c1; ++cix) acc += P.sel[__ldg(&P.h_cidx[cix])];
+            P.hval[tid] = acc;
+        } else if (tid < nh + ng) {
+            const int64_t a = tid - nh;
+            const int64_t c0 = __ldg(&P.g_cptr[a]), c1 = __ldg(&P.g_cptr[a + 1]);
+            double acc = 0.0;
+            for (int64_t cix = c0; cix < c1; ++cix) acc += P.rel[__ldg(&P.g_cidx[cix])];
+            P.grad[a] = acc;
+        }
+        return;
+    }
+    // scalar block
+    __shared__ double sh[3][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {
+        s0 += P.part[r * 4 + 0];
+        s1 += P.part[r * 4 + 1];
+        s2 += P.part[r * 4 + 2];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && P.scal) {
+        P.scal[0] = sh[0][0] + P.t * sh[1][0];
+        P.scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
+        P.scal[2] = sh[1][0];
+        P.scal[3] = sh[2][0];
+    }
+}
+
+// warp per output entry (long contribution lists: coarse multigrid levels)
+__global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, const int64_t* __restrict__ cptr,
+                                                          const int32_t* __restrict__ cidx,
+                                                          const double* __restrict__ src, double* __restrict__ dst) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid >= nout) return;
+    const int64_t c0 = cptr[wid], c1 = cptr[wid + 1];
+    double acc = 0.0;
+    for (int64_t cix = c0 + lane; cix < c1; cix += 32) acc += src[cidx[cix]];
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+    if (lane == 0) dst[wid] = acc;
+}
+
+// ---------------------------------------------------------------- small utilities
+__global__ void isfinite_kernel(const double* __restrict__ v, int64_t len, int* __restrict__ flag) {
+    int bad = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        bad |= !isfinite(v[i]);
+    if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 0;  // idempotent store, not an accumulation
+}
+
+__global__ void diag_scale_kernel(const double* __restrict__ w, const double* __restrict__ y, int64_t n,
+                                  double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = w[i] * y[i];
+}
+
+__global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
+        buf[i] = v;
+}
+
+// map_rows of the barrier over Dz rows (separately callable seam; reference src:161-170)
+template <int D>
+__global__ void map_barrier_kernel(const double* __restrict__ Dz, int64_t n, int ND, int slack, double p, int which,
+                                   double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) q[j] = Dz[(int64_t)(1 + j) * n + i];
+    double s = Dz[(int64_t)(D + 1) * n + i];
+    if (slack) s += Dz[(int64_t)(D + 2) * n + i];
+    BarrierOut bo;
+    barrier_eval<D, true, true>(q, s, p, bo);
+    if (which == 0) { out[i] = bo.F; return; }
+    const int ns = slack ? 2 : 1;
+    if (which == 1) {
+        out[i] = 0.0;
+        for (int j = 0; j < D; ++j) out[(int64_t)(1 + j) * n + i] = bo.gq[j];
+        for (int r = 0; r < ns; ++r) out[(int64_t)(D + 1 + r) * n + i] = bo.gs;
+        return;
+    }
+    for (int c = 0; c < ND * ND; ++c) out[(int64_t)c * n + i] = 0.0;
+    for (int j = 0; j < D; ++j) {
+        for (int j2 = 0; j2 < D; ++j2) out[(int64_t)((1 + j) * ND + 1 + j2) * n + i] = bo.Hqq[j][j2];
+        for (int r = 0; r < ns; ++r) {
+            out[(int64_t)((1 + j) * ND + D + 1 + r) * n + i] = bo.Hqs[j];
+            out[(int64_t)((D + 1 + r) * ND + 1 + j) * n + i] = bo.Hqs[j];
+        }
+    }
+    for (int r = 0; r < ns; ++r)
+        for (int r2 = 0; r2 < ns; ++r2) out[(int64_t)((D + 1 + r) * ND + D + 1 + r2) * n + i] = bo.Hss;
+}
+
+}  // namespace mgb

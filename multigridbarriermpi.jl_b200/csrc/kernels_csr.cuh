@@ -1,0 +1,342 @@
+// General CSR path: the same numeric phase for operators WITHOUT broken-element block structure
+// (or operator tables other than [u.id; u.d*; s.id]).  One kernel per seam of the reference:
+//   csr_apply_kernel    Dz = Dz0 + E_k s            (apply_D, reference test/test_apply_d.jl:44)
+//   csr_barrier_kernel  w.*F1, w.*F2, objective    (map_rows src:161-170 + amgb_diag src:137-147)
+//   csr_grad_kernel     g = sum_k E_k' (w.*(y1_k + t c_k))   (gather over the stored transpose)
+//   csr_hess_kernel     warp per output row: numeric-only replay of sum_jk E_j' diag E_k on the
+//                       frozen pattern, accumulators in shared memory, no atomics
+//                       (test/test_map_rows_compare.jl:102-123 with R folded in: E_k = D_k R)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan_host.h"
+
+namespace mgb {
+
+struct CsrOpDev {
+    const int64_t* ptr;
+    const int32_t* idx;
+    const double* val;
+};
+
+struct CsrDev {
+    int ND = 0;
+    int64_t nloc = 0, m = 0, nnzH = 0, nprod = 0;
+    int max_row = 0;
+    BarrierDesc bar;
+    std::vector<void*> owned;  // device allocations
+    CsrOpDev E[8], Et[8];
+    const int32_t* h_rowptr = nullptr;
+    const int64_t* seg_ptr = nullptr;
+    const int32_t* seg_i = nullptr;
+    const int32_t* seg_pair = nullptr;
+    const double* seg_alpha = nullptr;
+    const int64_t* seg_dst = nullptr;
+    const int32_t* dst = nullptr;
+    double* Dz = nullptr;    // nloc x ND
+    double* gy = nullptr;    // nloc x ND
+    double* V = nullptr;     // nloc x ND^2
+    double* part = nullptr;  // nblk x 4
+    int64_t nblk = 0;
+    ~CsrDev() { for (void* p : owned) cudaFree(p); }
+};
+
+template <class T>
+static const T* csr_up(CsrDev& d, const std::vector<T>& h, cudaStream_t st, size_t& bytes) {
+    T* p = nullptr;
+    const size_t nb = std::max<size_t>(h.size(), 1) * sizeof(T);
+    if (cudaMalloc(&p, nb) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (csr plan)");
+    d.owned.push_back(p);
+    if (!h.empty() && cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        throw std::runtime_error("cudaMemcpyAsync failed (csr plan)");
+    bytes += nb;
+    return p;
+}
+
+static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, cudaStream_t st) {
+    size_t bytes = 0;
+    d.ND = cp.ND; d.nloc = cp.nloc; d.m = cp.m; d.nnzH = (int64_t)cp.h_colidx.size();
+    d.nprod = (int64_t)cp.dst.size(); d.max_row = cp.max_row; d.bar = bar;
+    for (int k = 0; k < cp.ND; ++k) {
+        d.E[k] = {csr_up(d, cp.E[k].ptr, st, bytes), csr_up(d, cp.E[k].idx, st, bytes), csr_up(d, cp.E[k].val, st, bytes)};
+        d.Et[k] = {csr_up(d, cp.Et[k].ptr, st, bytes), csr_up(d, cp.Et[k].idx, st, bytes), csr_up(d, cp.Et[k].val, st, bytes)};
+    }
+    d.h_rowptr = csr_up(d, cp.h_rowptr, st, bytes);
+    d.seg_ptr = csr_up(d, cp.seg_ptr, st, bytes);
+    d.seg_i = csr_up(d, cp.seg_i, st, bytes);
+    d.seg_pair = csr_up(d, cp.seg_pair, st, bytes);
+    d.seg_alpha = csr_up(d, cp.seg_alpha, st, bytes);
+    d.seg_dst = csr_up(d, cp.seg_dst, st, bytes);
+    d.dst = csr_up(d, cp.dst, st, bytes);
+    auto scratch = [&](size_t count) {
+        double* p = nullptr;
+        if (cudaMalloc(&p, std::max<size_t>(count, 1) * 8) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (csr scratch)");
+        d.owned.push_back(p);
+        bytes += count * 8;
+        return p;
+    };
+    d.Dz = scratch((size_t)cp.nloc * cp.ND);
+    d.gy = scratch((size_t)cp.nloc * cp.ND);
+    d.V = scratch((size_t)cp.nloc * cp.ND * cp.ND);
+    d.nblk = (cp.nloc + 255) / 256;
+    d.part = scratch((size_t)d.nblk * 4);
+    if ((size_t)cp.max_row * 8 * 4 > 200 * 1024) throw std::runtime_error("csr path: Hessian row too long for shared-memory accumulation");
+    return bytes;
+}
+
+struct CsrApplyParams {
+    CsrOpDev E[8];
+    int ND;
+    int64_t n;
+    const double* s;
+    const double* Dz0;
+    double* Dz;
+};
+
+__global__ void __launch_bounds__(256) csr_apply_kernel(const CsrApplyParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n) return;
+    for (int k = 0; k < P.ND; ++k) {
+        double acc = P.Dz0 ? P.Dz0[(int64_t)k * P.n + i] : 0.0;
+        const int64_t p0 = P.E[k].ptr[i], p1 = P.E[k].ptr[i + 1];
+        for (int64_t p = p0; p < p1; ++p) acc = fma(P.E[k].val[p], __ldg(&P.s[P.E[k].idx[p]]), acc);
+        P.Dz[(int64_t)k * P.n + i] = acc;
+    }
+}
+
+struct CsrBarrierParams {
+    int ND, nq, slack;
+    int idx[8];
+    int64_t n;
+    double p, t;
+    const double* Dz;
+    const double* c;
+    const double* w;
+    double* gy;
+    double* V;
+    double* part;
+    int want_f, want_g, want_h;
+};
+
+__global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams P) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool act = i < P.n;
+    const int64_t n = P.n;
+    double v0 = 0.0, v1 = 0.0, v2 = 0.0;
+    if (act) {
+        double q[3] = {0.0, 0.0, 0.0};
+        for (int j = 0; j < P.nq; ++j) q[j] = P.Dz[(int64_t)P.idx[j] * n + i];
+        const int scol = P.idx[P.nq];
+        double s = P.Dz[(int64_t)scol * n + i];
+        if (P.slack) s += P.Dz[(int64_t)(P.ND - 1) * n + i];
+        BarrierOut bo;
+        barrier_eval<3, true, true>(q, s, P.p, bo);
+        const double wi = P.w[i];
+        double cd = 0.0;
+        for (int k = 0; k < P.ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
+        v0 = P.want_f ? wi * bo.F : 0.0;
+        v1 = wi * cd;
+        v2 = bo.feasible ? 0.0 : 1.0;
+        const int ns = P.slack ? 2 : 1;
+        const int scols[2] = {scol, P.ND - 1};
+        if (P.want_g) {
+            for (int k = 0; k < P.ND; ++k) P.gy[(int64_t)k * n + i] = wi * (P.t * P.c[(int64_t)k * n + i]);
+            for (int j = 0; j < P.nq; ++j) P.gy[(int64_t)P.idx[j] * n + i] += wi * bo.gq[j];
+            for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * bo.gs;
+        }
+        if (P.want_h) {
+            const int ND = P.ND;
+            for (int cidx = 0; cidx < ND * ND; ++cidx) P.V[(int64_t)cidx * n + i] = 0.0;
+            for (int j = 0; j < P.nq; ++j) {
+                for (int j2 = 0; j2 < P.nq; ++j2) P.V[(int64_t)(P.idx[j] * ND + P.idx[j2]) * n + i] = wi * bo.Hqq[j][j2];
+                for (int r = 0; r < ns; ++r) {
+                    P.V[(int64_t)(P.idx[j] * ND + scols[r]) * n + i] = wi * bo.Hqs[j];
+                    P.V[(int64_t)(scols[r] * ND + P.idx[j]) * n + i] = wi * bo.Hqs[j];
+                }
+            }
+            for (int r = 0; r < ns; ++r)
+                for (int r2 = 0; r2 < ns; ++r2) P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] = wi * bo.Hss;
+        }
+    }
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) {
+        v0 += shfl_xor_d(v0, mk);
+        v1 += shfl_xor_d(v1, mk);
+        v2 += shfl_xor_d(v2, mk);
+    }
+    __shared__ double red[3][8];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][wid] = v0; red[1][wid] = v1; red[2][wid] = v2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < 8; ++r) { s0 += red[0][r]; s1 += red[1][r]; s2 += red[2][r]; }
+        P.part[(int64_t)blockIdx.x * 4 + 0] = s0;
+        P.part[(int64_t)blockIdx.x * 4 + 1] = s1;
+        P.part[(int64_t)blockIdx.x * 4 + 2] = s2;
+    }
+}
+
+struct CsrGradParams {
+    CsrOpDev Et[8];
+    int ND;
+    int64_t n, m;
+    const double* gy;
+    double* grad;
+};
+
+__global__ void __launch_bounds__(256) csr_grad_kernel(const CsrGradParams P) {
+    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= P.m) return;
+    double acc = 0.0;
+    for (int k = 0; k < P.ND; ++k) {
+        const int64_t p0 = P.Et[k].ptr[a], p1 = P.Et[k].ptr[a + 1];
+        for (int64_t p = p0; p < p1; ++p) acc = fma(P.Et[k].val[p], P.gy[(int64_t)k * P.n + P.Et[k].idx[p]], acc);
+    }
+    P.grad[a] = acc;
+}
+
+struct CsrHessParams {
+    CsrOpDev E[8];
+    int ND, max_row;
+    int64_t n, m;
+    const int32_t* h_rowptr;
+    const int64_t* seg_ptr;
+    const int32_t* seg_i;
+    const int32_t* seg_pair;
+    const double* seg_alpha;
+    const int64_t* seg_dst;
+    const int32_t* dst;
+    const double* V;
+    double* hval;
+};
+
+// one warp per output row; lanes run over the entries of one E_kb row at a time (distinct
+// destinations inside a segment), segments are serialised -> fixed summation order, no atomics
+__global__ void __launch_bounds__(128) csr_hess_kernel(const CsrHessParams P) {
+    extern __shared__ double acc_all[];
+    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
+    if (a >= P.m) return;
+    double* acc = acc_all + (size_t)wib * P.max_row;
+    const int h0 = P.h_rowptr[a], hl = P.h_rowptr[a + 1] - h0;
+    for (int j = lane; j < hl; j += 32) acc[j] = 0.0;
+    __syncwarp();
+    const int64_t g0 = P.seg_ptr[a], g1 = P.seg_ptr[a + 1];
+    for (int64_t g = g0; g < g1; ++g) {
+        const int32_t i = P.seg_i[g];
+        const int pair = P.seg_pair[g];
+        const int kb = pair % P.ND;
+        const double coef = P.seg_alpha[g] * P.V[(int64_t)pair * P.n + i];
+        const int64_t r0 = P.E[kb].ptr[i];
+        const int len = (int)(P.E[kb].ptr[i + 1] - r0);
+        const int64_t d0 = P.seg_dst[g];
+        for (int r = lane; r < len; r += 32) acc[P.dst[d0 + r]] = fma(coef, P.E[kb].val[r0 + r], acc[P.dst[d0 + r]]);
+        __syncwarp();
+    }
+    for (int j = lane; j < hl; j += 32) P.hval[h0 + j] = acc[j];
+}
+
+__global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
+                                                            double* __restrict__ scal) {
+    __shared__ double sh[3][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = threadIdx.x; r < nparts; r += blockDim.x) {
+        s0 += part[r * 4 + 0];
+        s1 += part[r * 4 + 1];
+        s2 += part[r * 4 + 2];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        scal[0] = sh[0][0] + t * sh[1][0];
+        scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
+        scal[2] = sh[1][0];
+        scal[3] = sh[2][0];
+    }
+}
+
+static void csr_check(cudaError_t e, const char* what) {
+    if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// returns the number of kernels launched
+static int csr_assemble(CsrDev& d, const double* w, const double* s, const double* Dz0, const double* c, double t,
+                        int flags, double* scal, double* grad, double* hval, double* Dz_out, cudaStream_t st) {
+    int launches = 0;
+    const int64_t n = d.nloc;
+    double* Dz = ((flags & 8) && Dz_out) ? Dz_out : d.Dz;
+    if ((flags & 2) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
+    if ((flags & 4) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
+    {
+        CsrApplyParams P{};
+        for (int k = 0; k < d.ND; ++k) P.E[k] = d.E[k];
+        P.ND = d.ND; P.n = n; P.s = s; P.Dz0 = Dz0; P.Dz = Dz;
+        csr_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
+        ++launches;
+    }
+    {
+        CsrBarrierParams P{};
+        P.ND = d.ND; P.nq = d.bar.nidx - 1; P.slack = d.bar.slack;
+        for (int j = 0; j < d.bar.nidx; ++j) P.idx[j] = d.bar.idx[j];
+        P.n = n; P.p = d.bar.p; P.t = t; P.Dz = Dz; P.c = c; P.w = w; P.gy = d.gy; P.V = d.V; P.part = d.part;
+        P.want_f = (flags & 1) ? 1 : 0; P.want_g = (flags & 2) ? 1 : 0; P.want_h = (flags & 4) ? 1 : 0;
+        csr_barrier_kernel<<<(unsigned)d.nblk, 256, 0, st>>>(P);
+        ++launches;
+    }
+    if (flags & 2) {
+        CsrGradParams P{};
+        for (int k = 0; k < d.ND; ++k) P.Et[k] = d.Et[k];
+        P.ND = d.ND; P.n = n; P.m = d.m; P.gy = d.gy; P.grad = grad;
+        csr_grad_kernel<<<(unsigned)((d.m + 255) / 256), 256, 0, st>>>(P);
+        ++launches;
+    }
+    if (flags & 4) {
+        CsrHessParams P{};
+        for (int k = 0; k < d.ND; ++k) P.E[k] = d.E[k];
+        P.ND = d.ND; P.max_row = d.max_row; P.n = n; P.m = d.m; P.h_rowptr = d.h_rowptr; P.seg_ptr = d.seg_ptr;
+        P.seg_i = d.seg_i; P.seg_pair = d.seg_pair; P.seg_alpha = d.seg_alpha; P.seg_dst = d.seg_dst; P.dst = d.dst;
+        P.V = d.V; P.hval = hval;
+        const size_t smem = (size_t)4 * d.max_row * sizeof(double);
+        if (smem > 48 * 1024)
+            csr_check(cudaFuncSetAttribute(csr_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+        csr_hess_kernel<<<(unsigned)((d.m + 3) / 4), 128, smem, st>>>(P);
+        ++launches;
+    }
+    scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);
+    ++launches;
+    csr_check(cudaGetLastError(), "csr_assemble launch");
+    return launches;
+}
+
+static int csr_map_barrier(const BarrierDesc& bar, int ND, int64_t n, const double* Dz, int which, double* out,
+                           cudaStream_t st) {
+    // only the contiguous idx = (1..d+1) layout is exposed through this seam
+    const int d = bar.nidx - 1;
+    for (int j = 0; j < bar.nidx; ++j)
+        if (bar.idx[j] != 1 + j) throw std::runtime_error("map_barrier: idx must be (1..d+1)");
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    if (d == 1) map_barrier_kernel<1><<<nb, 256, 0, st>>>(Dz, n, ND, bar.slack, bar.p, which, out);
+    else if (d == 2) map_barrier_kernel<2><<<nb, 256, 0, st>>>(Dz, n, ND, bar.slack, bar.p, which, out);
+    else if (d == 3) map_barrier_kernel<3><<<nb, 256, 0, st>>>(Dz, n, ND, bar.slack, bar.p, which, out);
+    else throw std::runtime_error("map_barrier: unsupported number of derivative columns");
+    csr_check(cudaGetLastError(), "map_barrier launch");
+    return 1;
+}
+
+}  // namespace mgb

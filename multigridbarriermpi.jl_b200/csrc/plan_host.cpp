@@ -1,0 +1,453 @@
+// Host symbolic phase.  See plan_host.h.
+#include "plan_host.h"
+
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+#include <stdexcept>
+
+namespace mgb {
+
+HostCSR spgemm(const HostCSR& A, const HostCSR& B) {
+    if (A.ncols != B.nrows) throw std::runtime_error("spgemm: inner dimensions differ");
+    HostCSR C;
+    C.nrows = A.nrows;
+    C.ncols = B.ncols;
+    C.ptr.assign(A.nrows + 1, 0);
+    std::vector<int64_t> mark(B.ncols, -1);
+    std::vector<double> acc(B.ncols, 0.0);
+    std::vector<int32_t> cols;
+    for (int64_t i = 0; i < A.nrows; ++i) {
+        cols.clear();
+        for (int64_t pa = A.ptr[i]; pa < A.ptr[i + 1]; ++pa) {
+            const int32_t k = A.idx[pa];
+            const double av = A.val[pa];
+            for (int64_t pb = B.ptr[k]; pb < B.ptr[k + 1]; ++pb) {
+                const int32_t j = B.idx[pb];
+                if (mark[j] != i) {
+                    mark[j] = i;
+                    acc[j] = 0.0;
+                    cols.push_back(j);
+                }
+                acc[j] += av * B.val[pb];
+            }
+        }
+        std::sort(cols.begin(), cols.end());
+        for (int32_t j : cols) {
+            C.idx.push_back(j);
+            C.val.push_back(acc[j]);
+        }
+        C.ptr[i + 1] = (int64_t)C.idx.size();
+    }
+    return C;
+}
+
+HostCSR transpose(const HostCSR& A) {
+    HostCSR T;
+    T.nrows = A.ncols;
+    T.ncols = A.nrows;
+    T.ptr.assign(A.ncols + 1, 0);
+    for (int32_t j : A.idx) T.ptr[j + 1]++;
+    for (int64_t j = 0; j < A.ncols; ++j) T.ptr[j + 1] += T.ptr[j];
+    T.idx.resize(A.nnz());
+    T.val.resize(A.nnz());
+    std::vector<int64_t> pos(T.ptr.begin(), T.ptr.end() - 1);
+    for (int64_t i = 0; i < A.nrows; ++i)
+        for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
+            const int64_t d = pos[A.idx[p]]++;
+            T.idx[d] = (int32_t)i;
+            T.val[d] = A.val[p];
+        }
+    return T;
+}
+
+int64_t count_gram_pattern(const std::vector<HostCSR>& D) {
+    const int64_t n = D[0].nrows, N = D[0].ncols;
+    // union pattern U (n x N) of all operators, and its transpose
+    HostCSR U;
+    U.nrows = n; U.ncols = N; U.ptr.assign(n + 1, 0);
+    std::vector<int32_t> cols;
+    for (int64_t i = 0; i < n; ++i) {
+        cols.clear();
+        for (const HostCSR& A : D)
+            for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) cols.push_back(A.idx[p]);
+        std::sort(cols.begin(), cols.end());
+        cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+        U.idx.insert(U.idx.end(), cols.begin(), cols.end());
+        U.ptr[i + 1] = (int64_t)U.idx.size();
+    }
+    U.val.assign(U.idx.size(), 1.0);
+    HostCSR Ut = transpose(U);
+    std::vector<int64_t> mark(N, -1);
+    int64_t total = 0;
+    for (int64_t p = 0; p < N; ++p)
+        for (int64_t r = Ut.ptr[p]; r < Ut.ptr[p + 1]; ++r) {
+            const int64_t i = Ut.idx[r];
+            for (int64_t c = U.ptr[i]; c < U.ptr[i + 1]; ++c)
+                if (mark[U.idx[c]] != p) { mark[U.idx[c]] = p; ++total; }
+        }
+    return total;
+}
+
+static int pow2ceil(int v) {
+    int p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+static int round_up(int v, int a) { return (v + a - 1) / a * a; }
+
+void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_) {
+    B = B_;
+    dim = dim_;
+    slack = slack_;
+    fine = fine_;
+    LPE = pow2ceil(B);
+    NU = 2 + (slack ? 1 : 0);
+    const int ntri = round_up(B * (B + 1) / 2, LPE);
+    const int nfull = fine ? B * LPE : round_up(B * B, LPE);
+    const int ndiag = fine ? LPE : ntri;
+    int o = 0;
+    off_uu = o, o += ntri;
+    off_us = o, o += nfull;
+    off_ss = o, o += ndiag;
+    if (slack) {
+        off_ut = o, o += nfull;
+        off_st = o, o += fine ? LPE : round_up(B * B, LPE);
+        off_tt = o, o += ndiag;
+    }
+    NS = o;
+}
+
+int SlotLayout::tri(int q, int q2) const { return q * B - q * (q - 1) / 2 + (q2 - q); }
+
+namespace {
+struct UF {
+    std::vector<int64_t> p;
+    explicit UF(int64_t n) : p(n) { std::iota(p.begin(), p.end(), 0); }
+    int64_t find(int64_t a) {
+        while (p[a] != a) {
+            p[a] = p[p[a]];
+            a = p[a];
+        }
+        return a;
+    }
+    void unite(int64_t a, int64_t b) {
+        a = find(a), b = find(b);
+        if (a != b) p[std::max(a, b)] = std::min(a, b);
+    }
+};
+}  // namespace
+
+void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
+                        const BarrierDesc& bar, ElementPlan& P) {
+    P.ok = false;
+    const int ND = (int)D.size();
+    const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
+    if (N % n_global) { P.why = "N is not a multiple of n"; return; }
+    const int nu = (int)(N / n_global);
+    const bool slack = bar.slack != 0;
+    const int dim = ND - 2 - (slack ? 1 : 0);
+    if (bar.kind != 1 || dim < 1 || dim > 3 || nu != 2 + (slack ? 1 : 0)) { P.why = "not the p-Laplace operator table"; return; }
+    if (bar.nidx != dim + 1) { P.why = "barrier idx does not select (derivatives, s)"; return; }
+    for (int j = 0; j <= dim; ++j)
+        if (bar.idx[j] != 1 + j) { P.why = "barrier idx does not select (derivatives, s)"; return; }
+    // operator -> state variable
+    std::vector<int> var(ND, 0);
+    for (int k = 0; k < ND; ++k) {
+        int64_t lo = N, hi = -1;
+        for (int32_t j : D[k].idx) lo = std::min<int64_t>(lo, j), hi = std::max<int64_t>(hi, j);
+        if (hi >= 0) {
+            if (lo / n_global != hi / n_global) { P.why = "operator spans several state variables"; return; }
+            var[k] = (int)(lo / n_global);
+        } else {
+            var[k] = (k <= dim) ? 0 : (k - dim);
+        }
+        const int expect = (k <= dim) ? 0 : (k - dim);
+        if (var[k] != expect) { P.why = "operator table is not [u.id; u.d*; s.id; (slack.id)]"; return; }
+    }
+    // elements = connected components of the row/column graph of the fine operators
+    UF uf(nloc);
+    {
+        std::vector<int64_t> first(N, -1);
+        for (int k = 0; k < ND; ++k)
+            for (int64_t i = 0; i < nloc; ++i)
+                for (int64_t p = D[k].ptr[i]; p < D[k].ptr[i + 1]; ++p) {
+                    int64_t& f = first[D[k].idx[p]];
+                    if (f < 0) f = i; else uf.unite(i, f);
+                }
+    }
+    int64_t B = 0;
+    {
+        int64_t run = 0, root = -1;
+        for (int64_t i = 0; i <= nloc; ++i) {
+            const int64_t r = (i < nloc) ? uf.find(i) : -2;
+            if (r != root) {
+                if (root >= 0) {
+                    if (B == 0) B = run;
+                    if (run != B) { P.why = "elements are not uniform consecutive row blocks"; return; }
+                }
+                if (i < nloc && r != i) { P.why = "element rows are not consecutive"; return; }
+                root = r;
+                run = 0;
+            }
+            ++run;
+        }
+    }
+    if (B < 1 || B > 8) { P.why = "element block size not supported by the fused kernels (1..8)"; return; }
+    const int64_t E = nloc / B;
+    P.B = (int)B; P.dim = dim; P.NU = nu; P.ND = ND; P.slack = slack;
+    P.E = E; P.nloc = nloc; P.m = m;
+    const int LPE = pow2ceil((int)B);
+    P.LPE = LPE;
+
+    std::vector<HostCSR> Ek(ND);
+    for (int k = 0; k < ND; ++k) Ek[k] = spgemm(D[k], R);
+
+    // local column lists
+    P.lcols.assign((size_t)nu * E * LPE, -1);
+    std::vector<int32_t> tmp;
+    for (int v = 0; v < nu; ++v)
+        for (int64_t e = 0; e < E; ++e) {
+            tmp.clear();
+            for (int k = 0; k < ND; ++k) {
+                if (var[k] != v) continue;
+                for (int64_t i = e * B; i < (e + 1) * B; ++i)
+                    for (int64_t p = Ek[k].ptr[i]; p < Ek[k].ptr[i + 1]; ++p) tmp.push_back(Ek[k].idx[p]);
+            }
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            if ((int64_t)tmp.size() > B) { P.why = "element touches more dofs per variable than it has nodes"; return; }
+            for (size_t q = 0; q < tmp.size(); ++q) P.lcols[((size_t)v * E + e) * LPE + q] = tmp[q];
+        }
+    auto local_of = [&](int v, int64_t e, int32_t col) -> int {
+        const int32_t* lc = &P.lcols[((size_t)v * E + e) * LPE];
+        for (int q = 0; q < (int)B; ++q)
+            if (lc[q] == col) return q;
+        return -1;
+    };
+    // id-like operators: fine (one owned column per row) or dense
+    const int idop[3] = {0, dim + 1, dim + 2};
+    bool fine = true;
+    for (int v = 0; v < nu && fine; ++v) {
+        const HostCSR& A = Ek[idop[v]];
+        for (int64_t e = 0; e < E && fine; ++e) {
+            unsigned used = 0;
+            for (int64_t i = e * B; i < (e + 1) * B; ++i) {
+                const int64_t cnt = A.ptr[i + 1] - A.ptr[i];
+                if (cnt > 1) { fine = false; break; }
+                if (cnt == 1) {
+                    const int q = local_of(v, e, A.idx[A.ptr[i]]);
+                    if (used & (1u << q)) { fine = false; break; }
+                    used |= 1u << q;
+                }
+            }
+        }
+    }
+    P.fine = fine;
+    P.lay.build((int)B, dim, slack, fine);
+    const SlotLayout& lay = P.lay;
+
+    // operator rows in element-local columns
+    P.opd.assign((size_t)dim * B * nloc, 0.0);
+    for (int kd = 0; kd < dim; ++kd) {
+        const HostCSR& A = Ek[1 + kd];
+        for (int64_t i = 0; i < nloc; ++i) {
+            const int64_t e = i / B;
+            for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
+                const int q = local_of(0, e, A.idx[p]);
+                P.opd[((size_t)kd * B + q) * nloc + i] = A.val[p];
+            }
+        }
+    }
+    if (fine) {
+        P.own_val.assign((size_t)nu * nloc, 0.0);
+        P.own_lq.assign((size_t)nu * nloc, 255);
+        for (int v = 0; v < nu; ++v) {
+            const HostCSR& A = Ek[idop[v]];
+            for (int64_t i = 0; i < nloc; ++i)
+                if (A.ptr[i + 1] > A.ptr[i]) {
+                    P.own_val[(size_t)v * nloc + i] = A.val[A.ptr[i]];
+                    P.own_lq[(size_t)v * nloc + i] = (uint8_t)local_of(v, i / B, A.idx[A.ptr[i]]);
+                }
+        }
+    } else {
+        P.idd.assign((size_t)nu * B * nloc, 0.0);
+        for (int v = 0; v < nu; ++v) {
+            const HostCSR& A = Ek[idop[v]];
+            for (int64_t i = 0; i < nloc; ++i)
+                for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
+                    const int q = local_of(v, i / B, A.idx[p]);
+                    P.idd[((size_t)v * B + q) * nloc + i] = A.val[p];
+                }
+        }
+    }
+
+    // structural pattern of R'(sum_jk D_j' diag D_k)R = union_i U_i x U_i, U_i = support of point i
+    // over all operators (products keep structural zeros; see DESIGN.md "explicit-zero policy").
+    const int NL = nu * (int)B;  // local index alpha = v*B + q
+    auto slot_of = [&](int a1, int a2, const std::vector<int>& own /*[nu][B] local col per point*/) -> int {
+        int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
+        if (v1 > v2 || (v1 == v2 && q1 > q2)) { std::swap(v1, v2); std::swap(q1, q2); }
+        const int full_stride = lay.fine ? lay.LPE : lay.B;
+        if (v1 == 0 && v2 == 0) return lay.off_uu + lay.tri(q1, q2);
+        if (v1 == 0 && v2 == 1) return lay.off_us + q1 * full_stride + q2;
+        if (v1 == 0 && v2 == 2) return lay.off_ut + q1 * full_stride + q2;
+        if (v1 == 1 && v2 == 1) return lay.fine ? (q1 == q2 ? lay.off_ss + q1 : -1) : lay.off_ss + lay.tri(q1, q2);
+        if (v1 == 2 && v2 == 2) return lay.fine ? (q1 == q2 ? lay.off_tt + q1 : -1) : lay.off_tt + lay.tri(q1, q2);
+        if (v1 == 1 && v2 == 2) {
+            if (!lay.fine) return lay.off_st + q1 * lay.B + q2;
+            for (int l = 0; l < (int)B; ++l)
+                if (own[1 * B + l] == q1 && own[2 * B + l] == q2) return lay.off_st + l;
+            return -1;
+        }
+        return -1;
+    };
+
+    std::vector<int64_t> rowcnt(m + 1, 0);
+    std::vector<uint8_t> pres((size_t)NL * NL);
+    std::vector<uint8_t> U((size_t)B * NL);
+    std::vector<int> own((size_t)nu * B, -1);
+    // two passes: count, fill
+    std::vector<int32_t> tb, ts;
+    std::vector<int64_t> fillpos;
+    for (int pass = 0; pass < 2; ++pass) {
+        if (pass == 1) {
+            for (int64_t a = 0; a < m; ++a) rowcnt[a + 1] += rowcnt[a];
+            tb.resize(rowcnt[m]);
+            ts.resize(rowcnt[m]);
+            fillpos.assign(rowcnt.begin(), rowcnt.end() - 1);
+        }
+        for (int64_t e = 0; e < E; ++e) {
+            std::fill(U.begin(), U.end(), 0);
+            std::fill(own.begin(), own.end(), -1);
+            for (int k = 0; k < ND; ++k) {
+                const HostCSR& A = Ek[k];
+                const int v = var[k];
+                for (int l = 0; l < (int)B; ++l) {
+                    const int64_t i = e * B + l;
+                    for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
+                        const int q = local_of(v, e, A.idx[p]);
+                        U[(size_t)l * NL + v * B + q] = 1;
+                        if (k == idop[v]) own[v * B + l] = q;
+                    }
+                }
+            }
+            std::fill(pres.begin(), pres.end(), 0);
+            for (int l = 0; l < (int)B; ++l)
+                for (int a1 = 0; a1 < NL; ++a1)
+                    if (U[(size_t)l * NL + a1])
+                        for (int a2 = 0; a2 < NL; ++a2)
+                            if (U[(size_t)l * NL + a2]) pres[(size_t)a1 * NL + a2] = 1;
+            for (int a1 = 0; a1 < NL; ++a1) {
+                const int32_t ga = P.lcols[((size_t)(a1 / B) * E + e) * LPE + a1 % B];
+                if (ga < 0) continue;
+                for (int a2 = 0; a2 < NL; ++a2) {
+                    if (!pres[(size_t)a1 * NL + a2]) continue;
+                    const int32_t gb = P.lcols[((size_t)(a2 / B) * E + e) * LPE + a2 % B];
+                    if (gb < 0) continue;
+                    if (pass == 0) { rowcnt[ga + 1]++; continue; }
+                    const int sl = slot_of(a1, a2, own);
+                    if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
+                    const int64_t d = fillpos[ga]++;
+                    tb[d] = gb;
+                    ts[d] = (int32_t)(e * lay.NS + sl);
+                }
+            }
+        }
+    }
+    if ((int64_t)E * lay.NS > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
+    // sort each row by (column, source) and compress
+    P.h_rowptr.assign(m + 1, 0);
+    P.h_colidx.clear();
+    P.h_cptr.clear();
+    P.h_cidx.resize(tb.size());
+    std::vector<std::pair<int32_t, int32_t>> rowbuf;
+    int64_t outc = 0;
+    for (int64_t a = 0; a < m; ++a) {
+        rowbuf.clear();
+        for (int64_t d = rowcnt[a]; d < rowcnt[a + 1]; ++d) rowbuf.emplace_back(tb[d], ts[d]);
+        std::sort(rowbuf.begin(), rowbuf.end());
+        int32_t last = -1;
+        for (auto& pr : rowbuf) {
+            if (pr.first != last) {
+                P.h_colidx.push_back(pr.first);
+                P.h_cptr.push_back(outc);
+                last = pr.first;
+            }
+            P.h_cidx[outc++] = pr.second;
+        }
+        if ((int64_t)P.h_colidx.size() > INT32_MAX) throw std::runtime_error("nnz(H) exceeds int32 indexing");
+        P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
+    }
+    P.h_cptr.push_back(outc);
+
+    // gradient replay lists
+    std::vector<int64_t> gcnt(m + 1, 0);
+    for (int v = 0; v < nu; ++v)
+        for (int64_t e = 0; e < E; ++e)
+            for (int q = 0; q < (int)B; ++q) {
+                const int32_t a = P.lcols[((size_t)v * E + e) * LPE + q];
+                if (a >= 0) gcnt[a + 1]++;
+            }
+    for (int64_t a = 0; a < m; ++a) gcnt[a + 1] += gcnt[a];
+    P.g_cptr = gcnt;
+    P.g_cidx.resize(gcnt[m]);
+    std::vector<int64_t> gpos(gcnt.begin(), gcnt.end() - 1);
+    for (int64_t e = 0; e < E; ++e)  // element-major so every list is ordered by element
+        for (int v = 0; v < nu; ++v)
+            for (int q = 0; q < (int)B; ++q) {
+                const int32_t a = P.lcols[((size_t)v * E + e) * LPE + q];
+                if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
+            }
+    P.ok = true;
+}
+
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P) {
+    const int ND = (int)D.size();
+    P.ND = ND;
+    P.nloc = D[0].nrows;
+    P.m = R.ncols;
+    const int64_t m = P.m;
+    P.E.resize(ND);
+    P.Et.resize(ND);
+    for (int k = 0; k < ND; ++k) {
+        P.E[k] = spgemm(D[k], R);
+        P.Et[k] = transpose(P.E[k]);
+    }
+    // pattern: row a = union over (ka, i in column a of E_ka) of union_kb supp(E_kb[i,:])
+    P.h_rowptr.assign(m + 1, 0);
+    P.seg_ptr.assign(m + 1, 0);
+    std::vector<int32_t> mark(m, -1), pos(m, 0), cols;
+    for (int64_t a = 0; a < m; ++a) {
+        cols.clear();
+        for (int ka = 0; ka < ND; ++ka)
+            for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {
+                const int32_t i = P.Et[ka].idx[p];
+                for (int kb = 0; kb < ND; ++kb)
+                    for (int64_t r = P.E[kb].ptr[i]; r < P.E[kb].ptr[i + 1]; ++r) {
+                        const int32_t b = P.E[kb].idx[r];
+                        if (mark[b] != (int32_t)a) { mark[b] = (int32_t)a; cols.push_back(b); }
+                    }
+            }
+        std::sort(cols.begin(), cols.end());
+        for (size_t t = 0; t < cols.size(); ++t) { pos[cols[t]] = (int32_t)t; P.h_colidx.push_back(cols[t]); }
+        P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
+        P.max_row = std::max<int32_t>(P.max_row, (int32_t)cols.size());
+        for (int ka = 0; ka < ND; ++ka)
+            for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {
+                const int32_t i = P.Et[ka].idx[p];
+                for (int kb = 0; kb < ND; ++kb) {
+                    const int64_t r0 = P.E[kb].ptr[i], r1 = P.E[kb].ptr[i + 1];
+                    if (r1 == r0) continue;
+                    P.seg_i.push_back(i);
+                    P.seg_pair.push_back(ka * ND + kb);
+                    P.seg_alpha.push_back(P.Et[ka].val[p]);
+                    P.seg_dst.push_back((int64_t)P.dst.size());
+                    for (int64_t r = r0; r < r1; ++r) P.dst.push_back(pos[P.E[kb].idx[r]]);
+                }
+            }
+        P.seg_ptr[a + 1] = (int64_t)P.seg_i.size();
+    }
+}
+
+}  // namespace mgb

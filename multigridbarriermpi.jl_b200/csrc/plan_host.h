@@ -1,0 +1,87 @@
+// Symbolic phase (host, once per multigrid level): everything structural that the reference redoes
+// on every Newton step (spdiagm + structural hash in amgb_diag, reference
+// src/MultiGridBarrierMPI.jl:137-147 and tools/profile_hash.jl:41-66; SpGEMM symbolic of
+// D_j' * diag * D_k and R' * H * R, test/test_map_rows_compare.jl:102-123,165-171) is computed here
+// exactly once and frozen into index arrays the numeric kernels replay.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace mgb {
+
+struct HostCSR {
+    int64_t nrows = 0, ncols = 0;
+    std::vector<int64_t> ptr;
+    std::vector<int32_t> idx;
+    std::vector<double> val;
+    int64_t nnz() const { return (int64_t)idx.size(); }
+};
+
+// C = A * B, sorted columns, keeps structural zeros (Julia spmatmul semantics).
+HostCSR spgemm(const HostCSR& A, const HostCSR& B);
+HostCSR transpose(const HostCSR& A);
+// nnz of the structural pattern of sum_{j,k} D_j' * diag * D_k
+int64_t count_gram_pattern(const std::vector<HostCSR>& D);
+
+// Layout of the per-element slot record written by the element kernel and replayed by the gather
+// kernel.  Shared by host symbolic code and device code (see kernels.cuh: must stay in sync).
+struct SlotLayout {
+    int B = 0, LPE = 0, NU = 0, dim = 0;
+    bool slack = false, fine = false;
+    int off_uu = 0, off_us = 0, off_ss = 0, off_ut = 0, off_st = 0, off_tt = 0;
+    int NS = 0;  // doubles per element
+    void build(int B_, int dim_, bool slack_, bool fine_);
+    int tri(int q, int q2) const;  // packed upper-triangle index, q <= q2 < B
+};
+
+struct ElementPlan {
+    bool ok = false;       // element-block structure detected and supported by the fused kernels
+    std::string why;       // reason when !ok
+    int B = 0, LPE = 0, dim = 0, NU = 0, ND = 0;
+    bool slack = false, fine = false;
+    int64_t E = 0, nloc = 0, m = 0;
+    SlotLayout lay;
+    std::vector<int32_t> lcols;    // [NU][E][LPE]  global dof or -1
+    std::vector<double> opd;       // dense derivative rows [dim][B][nloc]
+    std::vector<double> idd;       // coarse: dense id-like rows [NU][B][nloc]
+    std::vector<double> own_val;   // fine: [NU][nloc]
+    std::vector<uint8_t> own_lq;   // fine: [NU][nloc]  local column or 255
+    // fixed output pattern + replay lists
+    std::vector<int32_t> h_rowptr, h_colidx;  // m+1, nnzH
+    std::vector<int64_t> h_cptr;              // nnzH+1
+    std::vector<int32_t> h_cidx;              // contribution -> e*NS + slot
+    std::vector<int64_t> g_cptr;              // m+1
+    std::vector<int32_t> g_cidx;              // contribution -> (e*NU+v)*LPE + q
+};
+
+struct BarrierDesc {
+    int kind = 1, nidx = 0, idx[8] = {0};
+    double p = 1.0;
+    int slack = 0;
+};
+
+// D: nD operators restricted to the local rows (nloc x N), R: N x m.
+// Tries to detect the broken-element block structure the fused kernels exploit.
+void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
+                        const BarrierDesc& bar, ElementPlan& out);
+
+struct CsrPlan {
+    int ND = 0, NU = 0;
+    int64_t nloc = 0, m = 0;
+    std::vector<HostCSR> E;   // E_k = D_k R   (nloc x m)
+    std::vector<HostCSR> Et;  // transposes   (m x nloc)
+    std::vector<int32_t> h_rowptr, h_colidx;
+    // warp-per-row replay: for output row a, segments (k_a, entry in column a of E_ka) x k_b
+    std::vector<int64_t> seg_ptr;   // m+1 -> segments of row a
+    std::vector<int32_t> seg_i;     // quadrature row i
+    std::vector<int32_t> seg_pair;  // ka*ND+kb
+    std::vector<double> seg_alpha;  // E_ka[i,a]
+    std::vector<int64_t> seg_dst;   // start into dst (length = nnz of row i of E_kb)
+    std::vector<int32_t> dst;       // position inside H row a
+    int32_t max_row = 0;
+};
+
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& out);
+
+}  // namespace mgb

@@ -1,0 +1,110 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/mgb_b200.h declares;
+the symbolic phase (host C++) reproduces the oracle's structural sparsity bit-exactly; numeric entry
+points refuse to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgb_b200
+from mgb_b200 import capi
+import mgb_oracle as O
+
+from helpers import problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    header = open(os.path.join(ROOT, "include", "mgb_b200.h")).read()
+    declared = set(re.findall(r"\b(mgb_[a-z_0-9A-Z]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert set(capi.EXPORTS) == declared
+
+
+def _structural_pattern(pr):
+    n = pr["x"].shape[0]
+    nD = len(pr["D"])
+    y2 = np.abs(np.random.default_rng(0).normal(size=(n, nD * nD))) + 0.1
+    Hs = O.hessian_fine(y2, pr["w"], pr["D"])
+    H = (pr["R"].T.tocsc() @ Hs @ pr["R"].tocsc()).tocsr()
+    H.sort_indices()
+    return H
+
+
+@pytest.mark.parametrize("gen,L,slack,level", [
+    ("fem1d", 1, False, None), ("fem1d", 4, False, None), ("fem1d", 4, False, 1), ("fem1d", 3, True, None),
+    ("fem2d", 1, False, None), ("fem2d", 3, False, None), ("fem2d", 3, False, 0), ("fem2d", 4, False, 2),
+    ("fem2d", 2, True, None), ("fem2d", 3, True, 1)])
+@pytest.mark.parametrize("path", [0, capi.PATH_CSR])
+def test_symbolic_pattern_bit_exact(gen, L, slack, level, path):
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom, slack=slack, level=level)
+    plan = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, slack=slack, force_path=path)
+    rp, ci = plan.pattern()
+    H = _structural_pattern(pr)
+    assert plan.nnzH == H.nnz
+    assert np.array_equal(rp, H.indptr) and np.array_equal(ci, H.indices)
+    if path == 0:
+        assert plan.info["path"] == capi.PATH_ELEMENT
+        assert plan.info["nodes_per_element"] == geom.block
+
+
+def test_fem3d_uses_csr_path_for_now():
+    geom = mgb_b200.fem3d(2, k=1)
+    pr = problem(geom)
+    plan = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
+    H = _structural_pattern(pr)
+    rp, ci = plan.pattern()
+    assert np.array_equal(rp, H.indptr) and np.array_equal(ci, H.indices)
+
+
+def test_numeric_calls_fail_loudly_without_gpu_context():
+    pr = problem(mgb_b200.fem1d(2))
+    plan = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
+    with pytest.raises(capi.MgbError, match="no CPU path"):
+        plan.assemble_host(pr["s"], None, pr["c"], 1.0, capi.WANT_F0)
+
+
+def test_bad_inputs_return_errors_not_crashes():
+    pr = problem(mgb_b200.fem1d(2))
+    with pytest.raises(capi.MgbError):
+        capi.Plan(None, pr["D"], pr["R"][:-1], pr["x"], pr["w"], pr["idx"], 1.0)   # R rows != D cols
+    with pytest.raises(capi.MgbError):
+        capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], [1, 9], 1.0)           # idx outside 0..nD-1
+    with pytest.raises(capi.MgbError):
+        capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 0.5)        # p < 1
+
+
+def test_one_based_csr_input_accepted():
+    """Julia passes 1-based rowptr/colval (index_base=1) zero-copy."""
+    import ctypes as C
+    pr = problem(mgb_b200.fem1d(3))
+    lib = capi.load()
+    keep = []
+
+    def one_based(A):
+        A = sp.csr_matrix(A); A.sort_indices()
+        rp = (A.indptr + 1).astype(np.int32); ci = (A.indices + 1).astype(np.int32); va = A.data.astype(np.float64)
+        keep.extend([rp, ci, va])
+        return capi._Csr(A.shape[0], A.shape[1], A.nnz, rp.ctypes.data, ci.ctypes.data, va.ctypes.data, 1)
+
+    Ds = (capi._Csr * len(pr["D"]))(*[one_based(d) for d in pr["D"]])
+    Rs = one_based(pr["R"])
+    bar = capi._Barrier(); bar.kind = 1; bar.nidx = 2; bar.idx[0] = 1; bar.idx[1] = 2; bar.p = 1.0; bar.slack = 0
+    x = np.asfortranarray(pr["x"]); w = pr["w"]
+    h = C.c_void_p()
+    n = pr["x"].shape[0]
+    rc = lib.mgb_plan_create(None, n, len(pr["D"]), Ds, C.byref(Rs), 1, x.ctypes.data, w.ctypes.data, C.byref(bar),
+                             0, n, 0, C.byref(h))
+    assert rc == 0, lib.mgb_last_error()
+    info = np.zeros(15, dtype=np.int64)
+    lib.mgb_plan_info(h, info.ctypes.data, 15)
+    ref = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
+    assert info[4] == ref.nnzH and info[3] == ref.m
+    lib.mgb_plan_destroy(h)
