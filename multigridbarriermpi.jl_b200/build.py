@@ -8,7 +8,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmgb_b200.so")
+LIB = os.environ.get("MGB_B200_LIB") or os.path.join(HERE, "libmgb_b200.so")
 SOURCES = ["mgb_b200.cu", "plan_host.cpp"]
 HEADERS = ["kernels.cuh", "kernels_csr.cuh", "plan_host.h", os.path.join("..", "..", "include", "mgb_b200.h")]
 
@@ -28,11 +28,12 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) -> str:
+    """``out``/``extra`` build tuning variants (e.g. -DMGB_ELEM_MINBLOCKS=6) next to the default library."""
+    if not force and out == LIB and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "--shared", "-Xcompiler", "-fPIC,-O3", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "--shared", "-Xcompiler", "-fPIC,-O3", *extra, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -41,7 +42,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         sys.stderr.write(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -13,6 +13,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef MGB_ELEM_MINBLOCKS
+#define MGB_ELEM_MINBLOCKS 5
+#endif
+
 namespace mgb {
 
 struct ElemParams {
@@ -108,7 +112,7 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
 
 // FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
 template <int B, int D, bool SLACK, bool FINE, int FLAGS>
-__global__ void __launch_bounds__(128) element_kernel(const ElemParams P) {
+__global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
     constexpr int LPE = Pow2Ceil<B>::value;
     constexpr int ND = D + 2 + (SLACK ? 1 : 0);
     constexpr int NU = 2 + (SLACK ? 1 : 0);
@@ -378,8 +382,10 @@ __global__ void __launch_bounds__(128) element_kernel(const ElemParams P) {
 
 struct GatherParams {
     int64_t nnzH, m;
-    const int64_t* h_cptr;
-    const int32_t* h_cidx;
+    const int2* h_src2;       // per entry: {first, second} contribution slot; second = -1 if none;
+                              // first < 0 : entry -1-first of the long list (more than two contributions)
+    const int64_t* h_lptr;    // long list pointers
+    const int32_t* h_lidx;    // long list slots
     const int64_t* g_cptr;
     const int32_t* g_cidx;
     const double* sel;
@@ -391,23 +397,48 @@ struct GatherParams {
     double* scal;  // {f0, all_finite, cdot, nonfinite count}
     double t;
     int want_h, want_g;
+    int64_t nblk_h, nblk_g;
 };
 
-// thread per output entry: H values first, then gradient entries; the last block folds the scalar
-// partials in a fixed order.
+constexpr int GATHER_UNROLL = 4;
+
+// Replays the frozen contribution lists: blocks [0,nblk_h) produce Hessian values (GATHER_UNROLL
+// entries per thread, two-deep dependent loads), blocks [nblk_h, nblk_h+nblk_g) the gradient, the
+// last block folds the scalar partials in a fixed order.
 __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
-    const int64_t nh = P.want_h ? P.nnzH : 0;
-    const int64_t ng = P.want_g ? P.m : 0;
-    const int64_t nblk_work = (nh + ng + blockDim.x - 1) / blockDim.x;
-    if ((int64_t)blockIdx.x < nblk_work) {
-        const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-        if (tid < nh) {
-            const int64_t c0 = __ldg(&P.h_cptr[tid]), c1 = __ldg(&P.h_cptr[tid + 1]);
-            double acc = 0.0;
-            for (int64_t cix = c0; cix < c1; ++cix) acc += P.sel[__ldg(&P.h_cidx[cix])];
-            P.hval[tid] = acc;
-        } else if (tid < nh + ng) {
-            const int64_t a = tid - nh;
+    const int64_t b = blockIdx.x;
+    if (b < P.nblk_h) {
+        const int64_t base = b * (256 * GATHER_UNROLL) + threadIdx.x;
+        int2 src[GATHER_UNROLL];
+#pragma unroll
+        for (int j = 0; j < GATHER_UNROLL; ++j) {
+            const int64_t t = base + (int64_t)j * 256;
+            src[j] = (t < P.nnzH) ? __ldg(&P.h_src2[t]) : make_int2(0, -1);
+        }
+        double v0[GATHER_UNROLL], v1[GATHER_UNROLL];
+#pragma unroll
+        for (int j = 0; j < GATHER_UNROLL; ++j) {
+            v0[j] = (src[j].x >= 0) ? P.sel[src[j].x] : 0.0;
+            v1[j] = (src[j].y >= 0) ? P.sel[src[j].y] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < GATHER_UNROLL; ++j) {
+            const int64_t t = base + (int64_t)j * 256;
+            if (t >= P.nnzH) continue;
+            double acc = v0[j] + v1[j];
+            if (src[j].x < 0) {
+                const int64_t li = -1 - (int64_t)src[j].x;
+                const int64_t c0 = P.h_lptr[li], c1 = P.h_lptr[li + 1];
+                acc = 0.0;
+                for (int64_t cix = c0; cix < c1; ++cix) acc += P.sel[__ldg(&P.h_lidx[cix])];
+            }
+            P.hval[t] = acc;
+        }
+        return;
+    }
+    if (b < P.nblk_h + P.nblk_g) {
+        const int64_t a = (b - P.nblk_h) * 256 + threadIdx.x;
+        if (a < P.m) {
             const int64_t c0 = __ldg(&P.g_cptr[a]), c1 = __ldg(&P.g_cptr[a + 1]);
             double acc = 0.0;
             for (int64_t cix = c0; cix < c1; ++cix) acc += P.rel[__ldg(&P.g_cidx[cix])];

@@ -78,7 +78,9 @@ struct mgb_plan {
     // ---- element path
     mgb::ElementPlan ep;  // host arrays are released after upload except the pattern
     DevBuf<int32_t> d_lcols, d_hcidx, d_gcidx;
-    DevBuf<int64_t> d_hcptr, d_gcptr;
+    DevBuf<int64_t> d_hcptr, d_gcptr, d_hlptr;
+    DevBuf<int2> d_hsrc2;
+    DevBuf<int32_t> d_hlidx;
     DevBuf<double> d_opd, d_idd, d_ownval, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     DevBuf<uint8_t> d_ownlq;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
@@ -205,7 +207,8 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
 
     mgb::GatherParams G{};
     G.nnzH = pl->nnzH; G.m = pl->m;
-    G.h_cptr = pl->d_hcptr.p; G.h_cidx = pl->d_hcidx.p; G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
+    G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p;
+    G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
     G.sel = pl->d_sel.p; G.rel = pl->d_rel.p; G.hval = hval; G.grad = grad;
     G.part = pl->d_part.p; G.nparts = pl->nblocks_elem; G.scal = scal ? scal : pl->d_scal_tmp.p; G.t = t;
     G.want_h = (flags & MGB_WANT_HESS) ? 1 : 0;
@@ -214,7 +217,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         // coarse levels: few output entries with long lists -> warp per entry
         if (G.want_h) {
             const int64_t nb = (pl->nnzH * 32 + 255) / 256;
-            mgb::gather_warp_kernel<<<(unsigned)nb, 256, 0, st>>>(pl->nnzH, G.h_cptr, G.h_cidx, G.sel, hval);
+            mgb::gather_warp_kernel<<<(unsigned)nb, 256, 0, st>>>(pl->nnzH, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval);
             g_launches++;
         }
         if (G.want_g) {
@@ -224,9 +227,9 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         }
         G.want_h = G.want_g = 0;
     }
-    const int64_t work = (G.want_h ? pl->nnzH : 0) + (G.want_g ? pl->m : 0);
-    const int64_t nb = (work + 255) / 256 + 1;
-    mgb::gather_kernel<<<(unsigned)nb, 256, 0, st>>>(G);
+    G.nblk_h = G.want_h ? (pl->nnzH + 256 * mgb::GATHER_UNROLL - 1) / (256 * mgb::GATHER_UNROLL) : 0;
+    G.nblk_g = G.want_g ? (pl->m + 255) / 256 : 0;
+    mgb::gather_kernel<<<(unsigned)(G.nblk_h + G.nblk_g + 1), 256, 0, st>>>(G);
     g_launches++;
     CUDA_OK(cudaGetLastError());
 }
@@ -329,7 +332,32 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
           if (!host_only) {
             pl->d_lcols.upload(ep.lcols, st); pl->d_opd.upload(ep.opd, st);
             pl->d_idd.upload(ep.idd, st); pl->d_ownval.upload(ep.own_val, st); pl->d_ownlq.upload(ep.own_lq, st);
-            pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
+            {
+                const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
+                pl->long_lists = avg > 12.0;
+            }
+            if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
+                pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
+            } else {   // two-wide ELL + long list for the thread-per-entry gather
+                std::vector<int2> src2(pl->nnzH);
+                std::vector<int64_t> lptr(1, 0);
+                std::vector<int32_t> lidx;
+                for (int64_t t = 0; t < pl->nnzH; ++t) {
+                    const int64_t c0 = ep.h_cptr[t], c1 = ep.h_cptr[t + 1];
+                    if (c1 - c0 <= 2) {
+                        src2[t].x = (c1 > c0) ? ep.h_cidx[c0] : 0;
+                        src2[t].y = (c1 - c0 == 2) ? ep.h_cidx[c0 + 1] : -1;
+                        if (c1 == c0) throw std::runtime_error("internal: Hessian entry without contribution");
+                    } else {
+                        src2[t].x = (int32_t)(-1 - (int64_t)(lptr.size() - 1));
+                        src2[t].y = -1;
+                        lidx.insert(lidx.end(), ep.h_cidx.begin() + c0, ep.h_cidx.begin() + c1);
+                        lptr.push_back((int64_t)lidx.size());
+                    }
+                }
+                pl->d_hsrc2.upload(src2, st); pl->d_hlptr.upload(lptr, st); pl->d_hlidx.upload(lidx, st);
+                CUDA_OK(cudaStreamSynchronize(st));
+            }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
             pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);
             pl->d_rel.alloc((size_t)ep.E * ep.NU * ep.LPE);
@@ -339,12 +367,10 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             pl->nblocks_elem = (ep.E + epb - 1) / epb;
             pl->d_part.alloc((size_t)pl->nblocks_elem * 4);
             pl->d_scal_tmp.alloc(4);
-            const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
-            pl->long_lists = avg > 12.0;
             CUDA_OK(cudaStreamSynchronize(st));
             pl->dev_bytes = pl->d_lcols.bytes() + pl->d_opd.bytes() + pl->d_idd.bytes() + pl->d_ownval.bytes() +
                             pl->d_ownlq.bytes() + pl->d_hcptr.bytes() + pl->d_hcidx.bytes() + pl->d_gcptr.bytes() +
-                            pl->d_gcidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
+                            pl->d_gcidx.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
           }
             // release host copies that are no longer needed
             std::vector<int32_t>().swap(ep.h_cidx); std::vector<int64_t>().swap(ep.h_cptr);
