@@ -61,6 +61,8 @@ typedef struct {
 /* plan kinds reported by mgb_plan_info */
 #define MGB_PATH_ELEMENT 1 /* fused element-block kernels (broken-element operators detected) */
 #define MGB_PATH_CSR 2     /* general CSR kernels                                              */
+/* OR-ed into force_path: build no Hessian pattern / replay lists (operator-only plan, e.g. Dz0 = D z) */
+#define MGB_PLAN_NO_HESSIAN 16
 
 const char* mgb_last_error(void);
 int mgb_version(void);
@@ -128,6 +130,21 @@ int mgb_all_isfinite(mgb_ctx* ctx, const double* v_dev, int64_t len, int32_t* fl
 /* amgb_diag (src:137-147) as a device map: out = w .* y[:,col] (the diagonal the reference wraps in a sparse matrix) */
 int mgb_diag_scale(mgb_ctx* ctx, const double* w_dev, const double* y_dev, int64_t n, int64_t ld,
                    int32_t col, double* out_dev);
+
+/* ---- small device-side sparse-matrix handle: the HPCSparseMatrix * HPCVector products the Newton
+ * driver needs outside the fused assembly (z = z0 + R s: reference test/test_nonsquare.jl:45-55;
+ * R' v: :57-72).  A' x uses a stored transpose (gather, no atomics). */
+typedef struct mgb_spmat mgb_spmat;
+int mgb_spmat_create(mgb_ctx* ctx, const mgb_csr* A, mgb_spmat** out);
+int mgb_spmat_destroy(mgb_spmat* A);
+/* y = alpha * op(A) x + beta * y0  (y0 may be NULL = 0; y may alias y0); trans != 0 -> op(A) = A' */
+int mgb_spmat_mv(mgb_spmat* A, int32_t trans, double alpha, const double* x_dev, double beta,
+                 const double* y0_dev, double* y_dev);
+
+/* ---- index pack / unpack used by the multi-GPU interface exchange of Hessian rows and gradient
+ * entries: out[k] = src[idx[k]]  and  dst[idx[k]] += src[k] (idx unique per call). */
+int mgb_gather_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* out_dev);
+int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* dst_dev);
 
 /* timing helper: runs `reps` assemblies back to back on the ctx stream, returns average ms measured
  * with CUDA events on that stream (bench.py uses it so the events sit on the launching stream). */

@@ -17,12 +17,14 @@ from . import build as _build
 
 WANT_F0, WANT_GRAD, WANT_HESS, STORE_DZ = 1, 2, 4, 8
 PATH_ELEMENT, PATH_CSR = 1, 2
+PLAN_NO_HESSIAN = 16
 BARRIER_EUCLIDIAN_POWER = 1
 
 EXPORTS = [
     "mgb_last_error", "mgb_version", "mgb_ctx_create", "mgb_ctx_destroy", "mgb_ctx_sync", "mgb_plan_create",
     "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
+    "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx",
 ]
 
 
@@ -86,6 +88,11 @@ def load(build_if_missing: bool = True):
     lib.mgb_time_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
                                       C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.mgb_spmat_create.argtypes = [C.c_void_p, C.POINTER(_Csr), C.POINTER(C.c_void_p)]
+    lib.mgb_spmat_destroy.argtypes = [C.c_void_p]
+    lib.mgb_spmat_mv.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
+    lib.mgb_gather_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mgb_scatter_add_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = lib
     return lib
 
@@ -130,6 +137,12 @@ class Context:
 
     def diag_scale(self, w_dev, y_dev, n: int, ld: int, col: int, out_dev):
         _check(load().mgb_diag_scale(self._h, _ptr(w_dev), _ptr(y_dev), int(n), int(ld), int(col), _ptr(out_dev)))
+
+    def gather_idx(self, src_dev, idx_dev, count: int, out_dev):
+        _check(load().mgb_gather_idx(self._h, _ptr(src_dev), _ptr(idx_dev), int(count), _ptr(out_dev)))
+
+    def scatter_add_idx(self, src_dev, idx_dev, count: int, dst_dev):
+        _check(load().mgb_scatter_add_idx(self._h, _ptr(src_dev), _ptr(idx_dev), int(count), _ptr(dst_dev)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -234,6 +247,34 @@ class Plan:
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             load().mgb_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpMat:
+    """Device CSR matrix with y = alpha*op(A) x + beta*y0 (mgb_spmat)."""
+
+    def __init__(self, ctx: Context, A: sp.spmatrix):
+        keep: list = []
+        cs = _csr_struct(A, keep)
+        h = C.c_void_p()
+        _check(load().mgb_spmat_create(ctx._h, C.byref(cs), C.byref(h)))
+        self._h = h
+        self.shape = A.shape
+        self.ctx = ctx
+
+    def mv(self, x_dev, y_dev, trans: bool = False, alpha: float = 1.0, beta: float = 0.0, y0_dev=None):
+        _check(load().mgb_spmat_mv(self._h, int(trans), float(alpha), _ptr(x_dev), float(beta), _ptr(y0_dev),
+                                   _ptr(y_dev)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().mgb_spmat_destroy(self._h)
             self._h = None
 
     def __del__(self):

@@ -506,6 +506,30 @@ __global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v)
         buf[i] = v;
 }
 
+// y = alpha * A x + beta * y0, thread per row (operator / restriction rows are short)
+__global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int64_t* __restrict__ ptr,
+                                                   const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                                   double alpha, const double* __restrict__ x, double beta,
+                                                   const double* __restrict__ y0, double* __restrict__ y) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    double acc = 0.0;
+    for (int64_t p = ptr[i]; p < ptr[i + 1]; ++p) acc = fma(val[p], __ldg(&x[idx[p]]), acc);
+    y[i] = alpha * acc + ((y0 && beta != 0.0) ? beta * y0[i] : 0.0);
+}
+
+__global__ void __launch_bounds__(256) gather_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
+                                                         int64_t count, double* __restrict__ out) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) out[k] = src[idx[k]];
+}
+
+__global__ void __launch_bounds__(256) scatter_add_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
+                                                              int64_t count, double* __restrict__ dst) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < count) dst[idx[k]] += src[k];  // idx unique within a call: plain read-modify-write
+}
+
 // map_rows of the barrier over Dz rows (separately callable seam; reference src:161-170)
 template <int D>
 __global__ void map_barrier_kernel(const double* __restrict__ Dz, int64_t n, int ND, int slack, double p, int which,

@@ -84,12 +84,21 @@ struct mgb_plan {
     DevBuf<double> d_opd, d_idd, d_ownval, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     DevBuf<uint8_t> d_ownlq;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
+    bool has_hessian = true;
     bool long_lists = false;
     // ---- csr path
     mgb::CsrDev csr;
     // ---- host staging for the *_host entry point
     DevBuf<double> st_s, st_dz0, st_c, st_scal, st_grad, st_hval, st_dz;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct mgb_spmat {
+    mgb_ctx* ctx = nullptr;
+    int64_t nrows = 0, ncols = 0;
+    DevBuf<int64_t> ptr, tptr;
+    DevBuf<int32_t> idx, tidx;
+    DevBuf<double> val, tval;
 };
 
 namespace {
@@ -315,8 +324,11 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         pl->NU = (int)(pl->N / n);
         cudaStream_t st = host_only ? nullptr : ctx->stream;
         bool use_elem = false;
+        const bool want_hess = (force_path & MGB_PLAN_NO_HESSIAN) == 0;
+        force_path &= 3;
+        pl->has_hessian = want_hess;
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, pl->bar, pl->ep);
+            mgb::build_element_plan(Dh, Rh, n, pl->bar, pl->ep, want_hess);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
                 return fail("mgb_plan_create: element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
@@ -379,7 +391,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         } else {
             pl->path = MGB_PATH_CSR;
             mgb::CsrPlan cp;
-            mgb::build_csr_plan(Dh, Rh, cp);
+            mgb::build_csr_plan(Dh, Rh, cp, want_hess);
             pl->nnzH = (int64_t)cp.h_colidx.size();
             pl->h_rowptr = cp.h_rowptr; pl->h_colidx = cp.h_colidx;
             pl->n_hcontrib = (int64_t)cp.dst.size();
@@ -430,6 +442,7 @@ int mgb_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const
     try {
         if (!pl || !s_dev || !c_dev) return fail("mgb_assemble: NULL argument");
         if (!pl->ctx) return fail("mgb_assemble: symbolic-only plan (created without a GPU context); no CPU path exists");
+        if ((flags & MGB_WANT_HESS) && !pl->has_hessian) return fail("mgb_assemble: plan was created with MGB_PLAN_NO_HESSIAN");
         CUDA_OK(cudaSetDevice(pl->ctx->device));
         if (pl->path == MGB_PATH_ELEMENT)
             assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev);
@@ -532,6 +545,75 @@ int mgb_diag_scale(mgb_ctx* ctx, const double* w_dev, const double* y_dev, int64
         CUDA_OK(cudaGetLastError());
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_diag_scale: ") + ex.what()); }
+}
+
+int mgb_spmat_create(mgb_ctx* ctx, const mgb_csr* A, mgb_spmat** out) {
+    try {
+        if (!ctx || !A || !out) return fail("mgb_spmat_create: NULL argument");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        mgb::HostCSR H = to_host_csr(*A, 0, A->nrows);
+        mgb::HostCSR T = mgb::transpose(H);
+        auto M = std::make_unique<mgb_spmat>();
+        M->ctx = ctx; M->nrows = H.nrows; M->ncols = H.ncols;
+        cudaStream_t st = ctx->stream;
+        M->ptr.upload(H.ptr, st); M->idx.upload(H.idx, st); M->val.upload(H.val, st);
+        M->tptr.upload(T.ptr, st); M->tidx.upload(T.idx, st); M->tval.upload(T.val, st);
+        CUDA_OK(cudaStreamSynchronize(st));
+        *out = M.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_spmat_create: ") + ex.what()); }
+}
+
+int mgb_spmat_destroy(mgb_spmat* A) {
+    if (!A) return 0;
+    cudaSetDevice(A->ctx->device);
+    cudaStreamSynchronize(A->ctx->stream);
+    delete A;
+    return 0;
+}
+
+int mgb_spmat_mv(mgb_spmat* A, int32_t trans, double alpha, const double* x_dev, double beta, const double* y0_dev,
+                 double* y_dev) {
+    try {
+        if (!A || !x_dev || !y_dev) return fail("mgb_spmat_mv: NULL argument");
+        CUDA_OK(cudaSetDevice(A->ctx->device));
+        const int64_t nr = trans ? A->ncols : A->nrows;
+        if (nr > 0) {
+            if (trans)
+                mgb::spmv_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, A->ctx->stream>>>(nr, A->tptr.p, A->tidx.p, A->tval.p, alpha, x_dev, beta, y0_dev, y_dev);
+            else
+                mgb::spmv_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, A->ctx->stream>>>(nr, A->ptr.p, A->idx.p, A->val.p, alpha, x_dev, beta, y0_dev, y_dev);
+            g_launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_spmat_mv: ") + ex.what()); }
+}
+
+int mgb_gather_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* out_dev) {
+    try {
+        if (!ctx) return fail("mgb_gather_idx: NULL argument");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        if (count > 0) {
+            mgb::gather_idx_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src_dev, idx_dev, count, out_dev);
+            g_launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_gather_idx: ") + ex.what()); }
+}
+
+int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* dst_dev) {
+    try {
+        if (!ctx) return fail("mgb_scatter_add_idx: NULL argument");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        if (count > 0) {
+            mgb::scatter_add_idx_kernel<<<(unsigned)((count + 255) / 256), 256, 0, ctx->stream>>>(src_dev, idx_dev, count, dst_dev);
+            g_launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_scatter_add_idx: ") + ex.what()); }
 }
 
 int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,

@@ -139,7 +139,7 @@ struct UF {
 }  // namespace
 
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
-                        const BarrierDesc& bar, ElementPlan& P) {
+                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian) {
     P.ok = false;
     const int ND = (int)D.size();
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
@@ -303,6 +303,9 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         return -1;
     };
 
+    P.h_rowptr.assign(m + 1, 0);
+    P.h_cptr.assign(1, 0);
+    if (want_hessian) {
     std::vector<int64_t> rowcnt(m + 1, 0);
     std::vector<uint8_t> pres((size_t)NL * NL);
     std::vector<uint8_t> U((size_t)B * NL);
@@ -380,6 +383,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
     }
     P.h_cptr.push_back(outc);
+    }  // want_hessian
 
     // gradient replay lists
     std::vector<int64_t> gcnt(m + 1, 0);
@@ -402,7 +406,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     P.ok = true;
 }
 
-void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P) {
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P, bool want_hessian) {
     const int ND = (int)D.size();
     P.ND = ND;
     P.nloc = D[0].nrows;
@@ -418,7 +422,7 @@ void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P)
     P.h_rowptr.assign(m + 1, 0);
     P.seg_ptr.assign(m + 1, 0);
     std::vector<int32_t> mark(m, -1), pos(m, 0), cols;
-    for (int64_t a = 0; a < m; ++a) {
+    for (int64_t a = 0; a < m && want_hessian; ++a) {
         cols.clear();
         for (int ka = 0; ka < ND; ++ka)
             for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {

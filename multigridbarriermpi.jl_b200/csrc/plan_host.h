@@ -64,7 +64,7 @@ struct BarrierDesc {
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.
 // Tries to detect the broken-element block structure the fused kernels exploit.
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
-                        const BarrierDesc& bar, ElementPlan& out);
+                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
 
 struct CsrPlan {
     int ND = 0, NU = 0;
@@ -82,6 +82,6 @@ struct CsrPlan {
     int32_t max_row = 0;
 };
 
-void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& out);
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& out, bool want_hessian = true);
 
 }  // namespace mgb

@@ -1,0 +1,268 @@
+"""Host driver for the barrier solve with device-resident state: ``amgb`` / ``parabolic_solve``.
+
+The outer algorithm (central path, multigrid sweep, damped Newton) is upstream
+``MultiGridBarrier.amgb`` - outside the reference repository, reached through
+``fem{1,2,3}d_mpi_solve`` (reference src/MultiGridBarrierMPI.jl:594-600, 661-667, 735-745).  It is
+restated here so the GPU assembly can be driven end to end; every f0/f1/f2 evaluation goes through
+the C ABI (``capi.Plan.assemble``), and the only work left on the host per Newton step is the sparse
+direct solve ``H \\ g`` - the solve seam the north-star leaves outside the graft
+(reference test/test_newton_matrix_compare.jl:33-51), timed separately in ``SOL_main``.
+"""
+from __future__ import annotations
+
+import math
+import time
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+import torch
+
+from . import capi
+from .amg import AMG, DEFAULT_D, DEFAULT_F, DEFAULT_G, DEFAULT_STATE, amg_helper
+from .geometry import Geometry
+
+EPS = float(np.finfo(np.float64).eps)
+
+
+def solve(H: sp.spmatrix, g: np.ndarray) -> np.ndarray:
+    """MultiGridBarrier.solve(A, b) = A \\ b.  Host sparse LU stands in for MUMPS (outside the graft)."""
+    return spla.splu(sp.csc_matrix(H)).solve(g)
+
+
+class LevelState:
+    """Plan + preallocated device buffers of one multigrid level."""
+
+    def __init__(self, prob: "DeviceProblem", J: int):
+        self.plan = capi.Plan(prob.ctx, prob.M.D, prob.M.R_fine[J], prob.M.x, prob.M.w, prob.idx, prob.p,
+                              slack=prob.slack)
+        dev = prob.device
+        m, nnz = self.plan.m, self.plan.nnzH
+        f64 = torch.float64
+        self.s = torch.zeros(m, dtype=f64, device=dev)
+        self.trial = torch.zeros(m, dtype=f64, device=dev)
+        self.step = torch.zeros(m, dtype=f64, device=dev)
+        self.grad = torch.zeros(m, dtype=f64, device=dev)
+        self.hval = torch.zeros(max(nnz, 1), dtype=f64, device=dev)
+        self.scal = torch.zeros(4, dtype=f64, device=dev)
+        self.R = capi.SpMat(prob.ctx, prob.M.R_fine[J])
+        rp, ci = self.plan.pattern()
+        self.rowptr, self.colidx = rp.astype(np.int64), ci.astype(np.int64)
+        # pinned host mirrors for the solve seam
+        self.h_hval = torch.zeros(max(nnz, 1), dtype=f64).pin_memory()
+        self.h_grad = torch.zeros(m, dtype=f64).pin_memory()
+        self.h_step = torch.zeros(m, dtype=f64).pin_memory()
+
+
+class DeviceProblem:
+    """One AMG hierarchy resident on one GPU."""
+
+    def __init__(self, M: AMG, idx: Sequence[int], p: float, slack: bool = False, device: int = 0,
+                 ctx: Optional[capi.Context] = None):
+        self.M, self.idx, self.p, self.slack = M, list(idx), float(p), bool(slack)
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.current_stream(self.device)
+        self.ctx = ctx or capi.Context(device, self.stream.cuda_stream)
+        self.n = M.x.shape[0]
+        self.N = M.nu * self.n
+        self.levels: Dict[int, LevelState] = {}
+        # operator-only plan with R = I: Dz0 = D z for any fine-space z
+        self.op_plan = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
+                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN)
+        self.Dz0 = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)  # column-major n x nD
+        self.stats = dict(assemblies=0, f0_evals=0, solve_s=0.0, assemble_s=0.0)
+
+    def level(self, J: int) -> LevelState:
+        if J not in self.levels:
+            self.levels[J] = LevelState(self, J)
+        return self.levels[J]
+
+    def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        out = self.Dz0 if out is None else out
+        self.op_plan.apply_D(z_dev, None, out)
+        return out
+
+
+def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor, t: float, maxit: int,
+                  alpha: float = 0.1, beta: float = 0.25, solve_fn: Callable = solve):
+    """Damped Newton on level J for s -> f(z + R_J s); same decisions as the oracle's ``newton``."""
+    lv = prob.level(J)
+    plan = lv.plan
+    Dz0 = prob.apply_D(z)
+    lv.s.zero_()
+    F0, FG, FH = capi.WANT_F0, capi.WANT_GRAD, capi.WANT_HESS
+    t0 = time.perf_counter()
+    plan.assemble(lv.s, Dz0, c, t, F0 | FG | FH, lv.scal, lv.grad, lv.hval)
+    sc = lv.scal.cpu()
+    prob.stats["assemblies"] += 1
+    y = float(sc[0])
+    if not (sc[1] == 1.0 and math.isfinite(y)):
+        raise RuntimeError("newton: infeasible start")
+    k, converged = 0, False
+    while k < maxit:
+        lv.h_hval.copy_(lv.hval, non_blocking=True)
+        lv.h_grad.copy_(lv.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        prob.stats["assemble_s"] += time.perf_counter() - t0
+        ts = time.perf_counter()
+        H = sp.csr_matrix((lv.h_hval.numpy()[: plan.nnzH], lv.colidx, lv.rowptr), shape=(plan.m, plan.m))
+        g = lv.h_grad.numpy()
+        nstep = solve_fn(H, g)
+        inc = float(np.dot(g, nstep))
+        prob.stats["solve_s"] += time.perf_counter() - ts
+        t0 = time.perf_counter()
+        if not math.isfinite(inc) or inc <= 16 * EPS * max(1.0, abs(y)):
+            converged = True
+            break
+        k += 1
+        lv.h_step.copy_(torch.from_numpy(nstep))
+        lv.step.copy_(lv.h_step, non_blocking=True)
+        sstep, ok = 1.0, False
+        while sstep > 1e-12:
+            torch.add(lv.s, lv.step, alpha=-sstep, out=lv.trial)
+            plan.assemble(lv.trial, Dz0, c, t, F0, lv.scal)
+            sc = lv.scal.cpu()
+            prob.stats["f0_evals"] += 1
+            yn = float(sc[0])
+            if sc[1] == 1.0 and math.isfinite(yn) and yn <= y - alpha * sstep * inc:
+                ok = True
+                break
+            sstep *= beta
+        if not ok:
+            converged = True
+            k -= 1
+            break
+        lv.s.copy_(lv.trial)
+        y = yn
+        plan.assemble(lv.s, Dz0, c, t, FG | FH, lv.scal, lv.grad, lv.hval)
+        prob.stats["assemblies"] += 1
+    prob.stats["assemble_s"] += time.perf_counter() - t0
+    # z <- z + R s
+    lv.R.mv(lv.s, z, beta=1.0, y0_dev=z)
+    return dict(k=k, converged=converged, y=y)
+
+
+@dataclass
+class AMGBSOL:
+    """Mirror of upstream AMGBSOL (reference src/MultiGridBarrierMPI.jl:467-473): z, SOL_feasibility,
+    SOL_main (ts, its, c_dot_Dz, t_elapsed), log, geometry."""
+    z: np.ndarray
+    SOL_feasibility: Optional[dict]
+    SOL_main: dict
+    log: str
+    geometry: Geometry
+    stats: dict = field(default_factory=dict)
+
+
+def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, kappa, maxit, max_newton_fine,
+              verbose=False, solve_fn=solve, logfile=None):
+    L = len(prob.M.R_fine)
+    t = t0
+    ts, its, cdots = [], [], []
+    t_begin = time.time()
+    kk = 0
+    scal = torch.zeros(4, dtype=torch.float64, device=prob.device)
+    while t <= 1.0 / tol:
+        kk += 1
+        ts.append(t)
+        row = [0] * L
+
+        def level(J, mi):
+            sol = newton_device(prob, J, z, c, t, mi, solve_fn=solve_fn)
+            row[J] += sol["k"]
+            return sol["converged"]
+
+        ok = False
+        if kk > 1:
+            ok = level(L - 1, max_newton_fine)
+        if not ok:
+            for J in range(L):
+                ok = level(J, maxit)
+        its.append(row)
+        Dz0 = prob.apply_D(z)
+        # <c, Dz>_w through the objective kernel on the finest plan (s = 0)
+        lv = prob.level(L - 1)
+        lv.s.zero_()
+        lv.plan.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0, scal)
+        cdots.append(float(scal.cpu()[2]))
+        if verbose:
+            print(f"t={t:.3e} its={row} c.Dz={cdots[-1]:.12e}", file=logfile)
+        t *= kappa
+    return dict(ts=np.array(ts), its=np.array(its).T, c_dot_Dz=np.array(cdots), t_elapsed=time.time() - t_begin)
+
+
+def _cm(a: np.ndarray, device) -> torch.Tensor:
+    """n x k host matrix -> column-major device buffer (k, n) contiguous."""
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=np.float64).T)).to(device)
+
+
+def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float = 0.1, kappa: float = 10.0,
+         maxit: int = 50, max_newton: Optional[int] = None, state_variables=DEFAULT_STATE, D=None, f=None, g=None,
+         verbose: bool = False, logfile=None, device: int = 0, solve_fn: Callable = solve, **_ignored) -> AMGBSOL:
+    """Barrier solve of the default p-Laplace-type problem on ``geom`` with GPU assembly.
+    Keyword names follow the reference's documented ``amgb`` keys (docs/src/guide.md:148-152);
+    unknown keys are ignored because ``femNd_mpi_solve`` forwards the same kwargs to the geometry
+    constructor and to ``amgb`` (src/MultiGridBarrierMPI.jl:594-600)."""
+    dim = geom.dim
+    D = DEFAULT_D[dim] if D is None else list(D)
+    f = DEFAULT_F[dim] if f is None else f
+    g = DEFAULT_G[dim] if g is None else g
+    M = amg_helper(geom, state_variables, D)
+    n = geom.x.shape[0]
+    idx = list(range(1, dim + 2))
+    z0 = np.array([g(geom.x[i]) for i in range(n)], dtype=float)
+    cmat = np.array([f(geom.x[i]) for i in range(n)], dtype=float)
+    if max_newton is None:
+        max_newton = int(math.ceil(math.log2(1.0 / tol) + 2))
+    prob = DeviceProblem(M, idx, p, slack=False, device=device)
+    z = torch.from_numpy(z0.reshape(-1, order="F").copy()).to(prob.device)
+    c = _cm(cmat, prob.device)
+    # strict feasibility of the start (upstream skips the feasibility phase when it holds)
+    lv = prob.level(len(M.R_fine) - 1)
+    Dz0 = prob.apply_D(z)
+    lv.s.zero_()
+    lv.plan.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0, lv.scal)
+    sol_feas = None
+    if float(lv.scal.cpu()[1]) != 1.0:
+        z, sol_feas = feasibility_phase(geom, prob, z, state_variables, D, tol, t, kappa, maxit, solve_fn, device)
+    sol_main = amgb_core(prob, z, c, tol, t, kappa, maxit, max_newton, verbose, solve_fn, logfile)
+    zz = z.cpu().numpy().reshape(n, M.nu, order="F")
+    return AMGBSOL(zz, sol_feas, sol_main, "", geom, dict(prob.stats))
+
+
+def feasibility_phase(geom, prob: DeviceProblem, z, state_variables, D, tol, t0, kappa, maxit, solve_fn, device):
+    n = geom.x.shape[0]
+    sv1 = tuple(state_variables) + (("feasibility_slack", "full"),)
+    D1 = list(D) + [("feasibility_slack", "id")]
+    M1 = amg_helper(geom, sv1, D1)
+    prob1 = DeviceProblem(M1, prob.idx, prob.p, slack=True, device=device, ctx=prob.ctx)
+    Dz = prob.apply_D(z).cpu().numpy().T  # n x nD
+    q = Dz[:, prob.idx[:-1]]
+    s = Dz[:, prob.idx[-1]]
+    need = np.sum(q * q, axis=1) ** (prob.p / 2.0) - s
+    slack0 = max(1.0, 2.0 * float(np.max(need)) + 1.0)
+    z1 = torch.cat([z, torch.full((n,), slack0, dtype=torch.float64, device=prob.device)])
+    c1 = np.zeros((n, len(D1)))
+    c1[:, -1] = 1.0
+    c1d = _cm(c1, prob.device)
+    t = t0
+    ts, its = [], []
+    J = len(M1.R_fine) - 1
+    lvm = prob.level(len(prob.M.R_fine) - 1)
+    czero = torch.zeros((len(D), n), dtype=torch.float64, device=prob.device)
+    while True:
+        sol = newton_device(prob1, J, z1, c1d, t, maxit, solve_fn=solve_fn)
+        ts.append(t), its.append(sol["k"])
+        zt = z1[: prob.N].clone()
+        Dz0 = prob.apply_D(zt)
+        lvm.s.zero_()
+        lvm.plan.assemble(lvm.s, Dz0, czero, 0.0, capi.WANT_F0, lvm.scal)
+        feasible = float(lvm.scal.cpu()[1]) == 1.0
+        if feasible and float(z1[prob.N:].max().cpu()) < 0:
+            return zt, dict(ts=np.array(ts), its=np.array(its))
+        t *= kappa
+        if t > 1.0 / tol:
+            raise RuntimeError("feasibility phase failed")
