@@ -124,7 +124,8 @@ int mgb_assemble_host(mgb_plan* plan, const double* s_host, const double* Dz0_ho
 int mgb_apply_D(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, double* Dz_dev);
 /* map_rows of the barrier over (x, Dz): which = 0 -> F (n), 1 -> F1 (n x nD), 2 -> F2 (n x nD^2,
  * column (j*nD+k), test/test_map_rows_compare.jl:62-73).  (src:161-170) */
-int mgb_map_barrier(mgb_plan* plan, const double* Dz_dev, int32_t which, double* out_dev);
+int mgb_map_barrier(mgb_ctx* ctx, const mgb_barrier* barrier, int32_t nD, int64_t n, const double* Dz_dev,
+                    int32_t which, double* out_dev);
 /* amgb_all_isfinite (src:121-133): *flag_host = 1 if every entry finite. */
 int mgb_all_isfinite(mgb_ctx* ctx, const double* v_dev, int64_t len, int32_t* flag_host);
 /* amgb_diag (src:137-147) as a device map: out = w .* y[:,col] (the diagonal the reference wraps in a sparse matrix) */

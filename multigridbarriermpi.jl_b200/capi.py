@@ -82,7 +82,7 @@ def load(build_if_missing: bool = True):
     lib.mgb_assemble_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double,
                                       C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mgb_apply_D.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.mgb_map_barrier.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
+    lib.mgb_map_barrier.argtypes = [C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
     lib.mgb_all_isfinite.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
     lib.mgb_diag_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     lib.mgb_time_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
@@ -137,6 +137,14 @@ class Context:
 
     def diag_scale(self, w_dev, y_dev, n: int, ld: int, col: int, out_dev):
         _check(load().mgb_diag_scale(self._h, _ptr(w_dev), _ptr(y_dev), int(n), int(ld), int(col), _ptr(out_dev)))
+
+    def map_barrier(self, idx, p: float, slack: bool, nD: int, n: int, Dz_dev, which: int, out_dev):
+        """map_rows of the barrier F / F1 / F2 over the rows of Dz (n x nD column-major)."""
+        bar = _Barrier()
+        bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
+        for j, v in enumerate(idx):
+            bar.idx[j] = int(v)
+        _check(load().mgb_map_barrier(self._h, C.byref(bar), int(nD), int(n), _ptr(Dz_dev), int(which), _ptr(out_dev)))
 
     def gather_idx(self, src_dev, idx_dev, count: int, out_dev):
         _check(load().mgb_gather_idx(self._h, _ptr(src_dev), _ptr(idx_dev), int(count), _ptr(out_dev)))
@@ -232,9 +240,6 @@ class Plan:
 
     def apply_D(self, s_dev, Dz0_dev, Dz_dev):
         _check(load().mgb_apply_D(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(Dz_dev)))
-
-    def map_barrier(self, Dz_dev, which: int, out_dev):
-        _check(load().mgb_map_barrier(self._h, _ptr(Dz_dev), int(which), _ptr(out_dev)))
 
     def time_assemble(self, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, reps: int,
                       flush_l2: bool, split: bool = True):

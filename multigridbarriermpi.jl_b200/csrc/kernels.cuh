@@ -202,6 +202,14 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
         for (int j = 0; j < D; ++j) qv[j] = 0.0; }
     BarrierOut bo;
     barrier_eval<D, WF, (WG || WH)>(qv, sv, P.p, bo);
+    // feasibility phase: the slack tau is bounded below by the extra barrier -log(1 + tau)
+    double tau1 = 1.0, itau = 1.0;
+    if (SLACK) {
+        tau1 = act ? 1.0 + dz[D + 2] : 1.0;
+        itau = 1.0 / tau1;
+        if (WF) bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
+        bo.feasible = bo.feasible && (tau1 > 0.0);
+    }
 
     // ---- objective / feasibility partials (fixed-order block reduction)
     {
@@ -241,7 +249,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
 #pragma unroll
         for (int j = 0; j < D; ++j) gy[1 + j] = wi * (bo.gq[j] + P.t * cc[1 + j]);
         gy[D + 1] = wi * (bo.gs + P.t * cc[D + 1]);
-        if (SLACK) gy[D + 2] = wi * (bo.gs + P.t * cc[D + 2]);
+        if (SLACK) gy[D + 2] = wi * (bo.gs - itau + P.t * cc[D + 2]);
         double ru[LPE];
 #pragma unroll
         for (int q = 0; q < LPE; ++q) {
@@ -315,6 +323,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
         bs[q] = acc;
     }
     const double vss = wi * bo.Hss;
+    const double vtt = SLACK ? vss + wi * itau * itau : vss;  // slack-slack curvature incl. -log(1+tau)
     if (FINE) {
         if (act && oh[1]) {
 #pragma unroll
@@ -326,7 +335,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
 #pragma unroll
             for (int q = 0; q < B; ++q) sel[P.off_ut + q * LPE + olq[VT]] = bs[q] * oval[VT];
             if (oh[1]) sel[P.off_st + l] = vss * oval[1] * oval[VT];
-            sel[P.off_tt + olq[VT]] = vss * oval[VT] * oval[VT];
+            sel[P.off_tt + olq[VT]] = vtt * oval[VT] * oval[VT];
         }
     } else {
 #pragma unroll
@@ -354,7 +363,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
             for (int q = 0; q < B; ++q)
 #pragma unroll
                 for (int q2 = q; q2 < B; ++q2)
-                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = vss * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
+                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = (v1 == 2 ? vtt : vss) * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
             group_reduce<NTRI, LPE>(v, l);
             const int off = (v1 == 1) ? P.off_ss : P.off_tt;
             if (act_e) {
@@ -543,12 +552,17 @@ __global__ void map_barrier_kernel(const double* __restrict__ Dz, int64_t n, int
     if (slack) s += Dz[(int64_t)(D + 2) * n + i];
     BarrierOut bo;
     barrier_eval<D, true, true>(q, s, p, bo);
+    double tau1 = 1.0;
+    if (slack) {
+        tau1 = 1.0 + Dz[(int64_t)(D + 2) * n + i];
+        bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
+    }
     if (which == 0) { out[i] = bo.F; return; }
     const int ns = slack ? 2 : 1;
     if (which == 1) {
         out[i] = 0.0;
         for (int j = 0; j < D; ++j) out[(int64_t)(1 + j) * n + i] = bo.gq[j];
-        for (int r = 0; r < ns; ++r) out[(int64_t)(D + 1 + r) * n + i] = bo.gs;
+        for (int r = 0; r < ns; ++r) out[(int64_t)(D + 1 + r) * n + i] = bo.gs - (r == 1 ? 1.0 / tau1 : 0.0);
         return;
     }
     for (int c = 0; c < ND * ND; ++c) out[(int64_t)c * n + i] = 0.0;
@@ -560,7 +574,8 @@ __global__ void map_barrier_kernel(const double* __restrict__ Dz, int64_t n, int
         }
     }
     for (int r = 0; r < ns; ++r)
-        for (int r2 = 0; r2 < ns; ++r2) out[(int64_t)((D + 1 + r) * ND + D + 1 + r2) * n + i] = bo.Hss;
+        for (int r2 = 0; r2 < ns; ++r2)
+            out[(int64_t)((D + 1 + r) * ND + D + 1 + r2) * n + i] = bo.Hss + ((r == 1 && r2 == 1) ? 1.0 / (tau1 * tau1) : 0.0);
 }
 
 }  // namespace mgb

@@ -138,6 +138,12 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
         if (P.slack) s += P.Dz[(int64_t)(P.ND - 1) * n + i];
         BarrierOut bo;
         barrier_eval<3, true, true>(q, s, P.p, bo);
+        double tau1 = 1.0;
+        if (P.slack) {  // slack bounded below by -log(1 + tau)
+            tau1 = 1.0 + P.Dz[(int64_t)(P.ND - 1) * n + i];
+            bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
+            bo.feasible = bo.feasible && (tau1 > 0.0);
+        }
         const double wi = P.w[i];
         double cd = 0.0;
         for (int k = 0; k < P.ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
@@ -149,7 +155,7 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
         if (P.want_g) {
             for (int k = 0; k < P.ND; ++k) P.gy[(int64_t)k * n + i] = wi * (P.t * P.c[(int64_t)k * n + i]);
             for (int j = 0; j < P.nq; ++j) P.gy[(int64_t)P.idx[j] * n + i] += wi * bo.gq[j];
-            for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * bo.gs;
+            for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * (bo.gs - (r == 1 ? 1.0 / tau1 : 0.0));
         }
         if (P.want_h) {
             const int ND = P.ND;
@@ -162,7 +168,8 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
                 }
             }
             for (int r = 0; r < ns; ++r)
-                for (int r2 = 0; r2 < ns; ++r2) P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] = wi * bo.Hss;
+                for (int r2 = 0; r2 < ns; ++r2)
+                    P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] = wi * (bo.Hss + ((r == 1 && r2 == 1) ? 1.0 / (tau1 * tau1) : 0.0));
         }
     }
 #pragma unroll

@@ -503,13 +503,19 @@ int mgb_apply_D(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, double
     } catch (const std::exception& ex) { return fail(std::string("mgb_apply_D: ") + ex.what()); }
 }
 
-int mgb_map_barrier(mgb_plan* pl, const double* Dz_dev, int32_t which, double* out_dev) {
+int mgb_map_barrier(mgb_ctx* ctx, const mgb_barrier* barrier, int32_t nD, int64_t n, const double* Dz_dev,
+                    int32_t which, double* out_dev) {
     try {
-        if (!pl || !Dz_dev || !out_dev) return fail("mgb_map_barrier: NULL argument");
-        if (!pl->ctx) return fail("mgb_map_barrier: symbolic-only plan; no CPU path exists");
+        if (!ctx || !barrier || !Dz_dev || !out_dev) return fail("mgb_map_barrier: NULL argument");
         if (which < 0 || which > 2) return fail("mgb_map_barrier: which must be 0,1,2");
-        CUDA_OK(cudaSetDevice(pl->ctx->device));
-        g_launches += mgb::csr_map_barrier(pl->bar, pl->ND, pl->nloc, Dz_dev, which, out_dev, pl->ctx->stream);
+        if (barrier->kind != MGB_BARRIER_EUCLIDIAN_POWER || barrier->nidx < 2 || barrier->nidx > 4)
+            return fail("mgb_map_barrier: unsupported barrier");
+        if (nD < barrier->nidx + 1 + (barrier->slack ? 1 : 0)) return fail("mgb_map_barrier: nD too small for idx");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        mgb::BarrierDesc bd;
+        bd.kind = barrier->kind; bd.nidx = barrier->nidx; bd.p = barrier->p; bd.slack = barrier->slack;
+        for (int j = 0; j < barrier->nidx; ++j) bd.idx[j] = barrier->idx[j];
+        if (n > 0) g_launches += mgb::csr_map_barrier(bd, nD, n, Dz_dev, which, out_dev, ctx->stream);
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_map_barrier: ") + ex.what()); }
 }

@@ -1,0 +1,135 @@
+"""Host-side mirror of the HPCSparseArrays types the reference dispatches on
+(``HPCVector`` / ``HPCMatrix`` / ``HPCSparseMatrix``, reference src/MultiGridBarrierMPI.jl:47-50) with
+device-resident storage.  Layouts follow the reference:
+
+* row-block partition, 1-based start offsets of length P+1 (``[1, n+1]`` for one rank;
+  tools/profile_solve.jl:24);
+* dense local block column-major (Julia ``Matrix``): stored as a (k, n_local) contiguous tensor so
+  column c is the contiguous slice the kernels read;
+* sparse local block = CSR rows of the owned row range with global column ids
+  (src/MultiGridBarrierMPI.jl:216-221).
+
+torch is used for device memory only; arithmetic on the hot path goes through the C ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+
+def uniform_partition(n: int, nranks: int, block: int = 1) -> np.ndarray:
+    """1-based row-block offsets, length nranks+1.  The first ``r = units mod P`` ranks get one extra
+    unit (HPCSparseArrays' split rule is not pinned by any reference test - test/test_partitions.jl:36-39
+    only prints it - so it lives in this one function).  ``block`` keeps whole broken elements
+    (7 / 2 / (k+1)^3 rows) on one rank so that apply_D needs no halo."""
+    units = n // block
+    assert units * block == n, "n must be a multiple of the element block"
+    base, extra = divmod(units, nranks)
+    sizes = np.array([(base + (1 if r < extra else 0)) * block for r in range(nranks)], dtype=np.int64)
+    return np.concatenate([[1], 1 + np.cumsum(sizes)]).astype(np.int64)
+
+
+@dataclass
+class Backend:
+    """HPCBackend{T,Ti,Device,Comm,Solver} (reference src/MultiGridBarrierMPI.jl:86-114)."""
+    T: type = np.float64
+    Ti: type = np.int32
+    device: str = "cuda"     # DeviceCUDA
+    comm: str = "nccl"       # one rank per GPU (test/test_2d.jl:14-25)
+    solver: str = "host-lu"  # the solve seam stays outside the graft
+    index: int = 0
+    rank: int = 0
+    nranks: int = 1
+
+    @property
+    def torch_device(self):
+        return torch.device("cuda", self.index) if self.device == "cuda" else torch.device("cpu")
+
+
+def backend_cuda(index: int = 0, rank: int = 0, nranks: int = 1) -> Backend:
+    return Backend(index=index, rank=rank, nranks=nranks)
+
+
+class HPCVector:
+    def __init__(self, v, backend: Backend, partition: Optional[np.ndarray] = None, local: bool = False):
+        """``v``: full host vector (scattered by ``partition``) or, with ``local=True``, this rank's block."""
+        self.backend = backend
+        if isinstance(v, torch.Tensor) and local:
+            n_glob = None
+            self.v = v
+        else:
+            v = np.asarray(v, dtype=np.float64)
+            n_glob = v.shape[0]
+            self.partition = uniform_partition(n_glob, backend.nranks) if partition is None else np.asarray(partition)
+            lo, hi = self.partition[backend.rank] - 1, self.partition[backend.rank + 1] - 1
+            self.v = torch.from_numpy(np.ascontiguousarray(v[lo:hi])).to(backend.torch_device)
+        if n_glob is None:
+            assert partition is not None
+            self.partition = np.asarray(partition)
+        self.n = int(self.partition[-1] - 1)
+
+    def __len__(self):
+        return self.n
+
+    @property
+    def shape(self):
+        return (self.n,)
+
+
+class HPCMatrix:
+    def __init__(self, A, backend: Backend, row_partition: Optional[np.ndarray] = None, local: bool = False):
+        self.backend = backend
+        if isinstance(A, torch.Tensor) and local:
+            assert row_partition is not None
+            self.A = A  # (k, n_local) contiguous == column-major n_local x k
+            self.row_partition = np.asarray(row_partition)
+        else:
+            A = np.asarray(A, dtype=np.float64)
+            self.row_partition = uniform_partition(A.shape[0], backend.nranks) if row_partition is None else np.asarray(row_partition)
+            lo, hi = self.row_partition[backend.rank] - 1, self.row_partition[backend.rank + 1] - 1
+            self.A = torch.from_numpy(np.ascontiguousarray(A[lo:hi].T)).to(backend.torch_device)
+        self.n = int(self.row_partition[-1] - 1)
+        self.k = int(self.A.shape[0])
+
+    @property
+    def shape(self):
+        return (self.n, self.k)
+
+
+class HPCSparseMatrix:
+    """Row-partitioned sparse matrix.  The replicated host CSR is kept (every rank builds the same
+    native geometry, src/MultiGridBarrierMPI.jl:239-240); ``local`` is this rank's row block."""
+
+    def __init__(self, A: sp.spmatrix, backend: Backend, row_partition: Optional[np.ndarray] = None,
+                 Ti=np.int32):
+        self.backend = backend
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        if A.nnz >= np.iinfo(Ti).max:
+            raise OverflowError("index type too small for this matrix; pass Ti=np.int64 (src/MultiGridBarrierMPI.jl:233-234)")
+        self.Ti = Ti
+        self.host = A
+        self.row_partition = uniform_partition(A.shape[0], backend.nranks) if row_partition is None else np.asarray(row_partition)
+        self.col_partition = uniform_partition(A.shape[1], backend.nranks)
+
+    @property
+    def shape(self):
+        return self.host.shape
+
+    @property
+    def local(self) -> sp.csr_matrix:
+        lo, hi = self.row_partition[self.backend.rank] - 1, self.row_partition[self.backend.rank + 1] - 1
+        return self.host[lo:hi]
+
+    @property
+    def rowptr(self):
+        """1-based local row pointer in the index type Ti (reference src/MultiGridBarrierMPI.jl:364)."""
+        return (self.local.indptr + 1).astype(self.Ti)
+
+    @property
+    def nnz(self):
+        return self.host.nnz

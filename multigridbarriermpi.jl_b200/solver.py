@@ -157,6 +157,14 @@ class AMGBSOL:
     stats: dict = field(default_factory=dict)
 
 
+@dataclass
+class ParabolicSOL:
+    """Mirror of upstream ParabolicSOL (reference src/MultiGridBarrierMPI.jl:512-516): geometry, ts, u."""
+    geometry: Geometry
+    ts: np.ndarray
+    u: List[np.ndarray]
+
+
 def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, kappa, maxit, max_newton_fine,
               verbose=False, solve_fn=solve, logfile=None):
     L = len(prob.M.R_fine)
@@ -227,13 +235,18 @@ def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float =
     lv.plan.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0, lv.scal)
     sol_feas = None
     if float(lv.scal.cpu()[1]) != 1.0:
-        z, sol_feas = feasibility_phase(geom, prob, z, state_variables, D, tol, t, kappa, maxit, solve_fn, device)
+        z, sol_feas = feasibility_phase(geom, prob, z, cmat, state_variables, D, tol, t, kappa, maxit, solve_fn, device)
     sol_main = amgb_core(prob, z, c, tol, t, kappa, maxit, max_newton, verbose, solve_fn, logfile)
     zz = z.cpu().numpy().reshape(n, M.nu, order="F")
     return AMGBSOL(zz, sol_feas, sol_main, "", geom, dict(prob.stats))
 
 
-def feasibility_phase(geom, prob: DeviceProblem, z, state_variables, D, tol, t0, kappa, maxit, solve_fn, device):
+SLACK_COST = 10.0
+
+
+def feasibility_phase(geom, prob: DeviceProblem, z, cmat, state_variables, D, tol, t0, kappa, maxit, solve_fn, device):
+    """Phase 1 with the extra state variable tau (:feasibility_slack, :full; operator :id): central path
+    of c.Dz + SLACK_COST*tau s.t. (q, s + tau) in Q, tau > -1, until tau < 0 everywhere."""
     n = geom.x.shape[0]
     sv1 = tuple(state_variables) + (("feasibility_slack", "full"),)
     D1 = list(D) + [("feasibility_slack", "id")]
@@ -245,8 +258,7 @@ def feasibility_phase(geom, prob: DeviceProblem, z, state_variables, D, tol, t0,
     need = np.sum(q * q, axis=1) ** (prob.p / 2.0) - s
     slack0 = max(1.0, 2.0 * float(np.max(need)) + 1.0)
     z1 = torch.cat([z, torch.full((n,), slack0, dtype=torch.float64, device=prob.device)])
-    c1 = np.zeros((n, len(D1)))
-    c1[:, -1] = 1.0
+    c1 = np.hstack([cmat, np.full((n, 1), SLACK_COST)])
     c1d = _cm(c1, prob.device)
     t = t0
     ts, its = [], []

@@ -67,7 +67,8 @@ def _mu(p: float) -> float:
 @dataclass
 class EuclidianPower:
     """{(q,s): s >= |q|^p}; F = -log(s^(2/p) - |q|^2) - mu(p) log s on y[idx] = (q..., s).
-    ``idx`` is 0-based into the Dz row.  ``slack`` (feasibility phase) adds the last Dz column to s."""
+    ``idx`` is 0-based into the Dz row.  ``slack`` (feasibility phase) adds the last Dz column tau to
+    s and bounds it below with the extra term -log(1 + tau) (keeps the phase-1 Hessian nonsingular)."""
     idx: Sequence[int]
     p: float
     slack: bool = False
@@ -85,7 +86,12 @@ class EuclidianPower:
         with np.errstate(all="ignore"):
             phi = np.where(s > 0, np.abs(s) ** a, -np.inf) - np.sum(q * q, axis=-1)
             out = -np.log(phi) - _mu(self.p) * np.log(s)
-        return np.where((phi > 0) & (s > 0), out, np.inf)
+            ok = (phi > 0) & (s > 0)
+            if self.slack:
+                tau1 = 1.0 + np.asarray(y, dtype=float)[..., -1]
+                out = out - np.log(tau1)
+                ok = ok & (tau1 > 0)
+        return np.where(ok, out, np.inf)
 
     def F1(self, x, y):
         y = np.asarray(y, dtype=float)
@@ -99,7 +105,7 @@ class EuclidianPower:
             g[..., k] = 2.0 * q[..., m] / phi
         g[..., idx[-1]] = gs
         if self.slack:
-            g[..., -1] = gs
+            g[..., -1] = gs - 1.0 / (1.0 + y[..., -1])
         return g
 
     def F2(self, x, y):
@@ -122,6 +128,8 @@ class EuclidianPower:
         for sv in svars:
             for sv2 in svars:
                 H[..., sv, sv2] = hss
+        if self.slack:
+            H[..., -1, -1] = hss + 1.0 / (1.0 + y[..., -1]) ** 2
         return H
 
 
@@ -356,15 +364,19 @@ def amgb(geom, p=1.0, tol=math.sqrt(EPS), t0=0.1, kappa=10.0, maxit=50, max_newt
     Dz = apply_D(M.D, z)
     sol_feas = None
     if not np.all(np.isfinite(Q.F(geom.x, Dz))):
-        z, sol_feas = feasibility_phase(geom, M, Q, z, state_variables, D, tol, t0, kappa, maxit,
+        z, sol_feas = feasibility_phase(geom, M, Q, z, c, state_variables, D, tol, t0, kappa, maxit,
                                         max_newton, solve_fn)
     z, sol_main = amgb_core(M, Q, z, c, tol, t0, kappa, maxit, max_newton, verbose, solve_fn, hook)
     return AMGBSOL(z.reshape(n, M.nu, order="F"), sol_feas, sol_main, "", geom)
 
 
-def feasibility_phase(geom, M, Q, z, state_variables, D, tol, t0, kappa, maxit, max_newton, solve_fn):
-    """Phase 1: add a slack state variable (:feasibility_slack, :full) with operator :id, minimise
-    the slack until the original constraints are strictly feasible."""
+SLACK_COST = 10.0
+
+
+def feasibility_phase(geom, M, Q, z, c, state_variables, D, tol, t0, kappa, maxit, max_newton, solve_fn):
+    """Phase 1: add a slack state variable tau (:feasibility_slack, :full) with operator :id; follow the
+    central path of  c.Dz + SLACK_COST*tau  s.t. (q, s + tau) in Q, tau > -1  until tau < 0 everywhere,
+    i.e. the original constraints hold strictly."""
     n = geom.x.shape[0]
     sv1 = tuple(state_variables) + (("feasibility_slack", "full"),)
     D1 = list(D) + [("feasibility_slack", "id")]
@@ -375,8 +387,7 @@ def feasibility_phase(geom, M, Q, z, state_variables, D, tol, t0, kappa, maxit, 
     need = np.sum(q * q, axis=-1) ** (Q.p / 2.0) - s
     slack0 = max(1.0, 2.0 * float(np.max(need)) + 1.0)
     z1 = np.concatenate([z, np.full(n, slack0)])
-    c1 = np.zeros((n, len(D1)))
-    c1[:, -1] = 1.0
+    c1 = np.hstack([c, np.full((n, 1), SLACK_COST)])
     t = t0
     ts, its = [], []
     while True:

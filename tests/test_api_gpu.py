@@ -1,0 +1,110 @@
+"""The reference's unit-level checks of its overloads (test/test_helpers.jl:47-167) against the
+Python mirror of the same names, plus the integration pattern of test/test_quick.jl."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+import mgb_b200
+import mgb_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    from mgb_b200 import api as a
+    return a
+
+
+@pytest.fixture(scope="module")
+def be(api):
+    return api.backend_cuda()
+
+
+def test_amgb_zeros_diag_blockdiag(api, be):
+    from mgb_b200.hpc import HPCSparseMatrix, HPCMatrix, HPCVector
+    A = HPCSparseMatrix(sp.csr_matrix((10, 10)), be)
+    Z = api.amgb_zeros(A, 5, 5)
+    assert isinstance(Z, HPCSparseMatrix) and Z.shape == (5, 5)
+    Zd = api.amgb_zeros(HPCMatrix(np.zeros((10, 10)), be), 4, 6)
+    assert isinstance(Zd, HPCMatrix) and Zd.shape == (4, 6)
+    v = HPCVector(np.array([1.0, 2, 3]), be)
+    Dm = api.amgb_diag(A, v)
+    assert isinstance(Dm, HPCSparseMatrix) and Dm.shape == (3, 3)
+    assert np.array_equal(api.to_host(Dm).diagonal(), [1, 2, 3])
+    D4 = api.amgb_diag(A, np.array([1.0, 2, 3, 4]))
+    assert D4.shape == (4, 4)
+    # reference test/test_diag.jl:28-46
+    assert np.array_equal(api.to_host(api.amgb_diag(A, np.arange(1.0, 11.0))).diagonal(), np.arange(1.0, 11.0))
+    C = api.amgb_blockdiag(HPCSparseMatrix(sp.identity(2, format="csr"), be), HPCSparseMatrix(sp.identity(3, format="csr"), be))
+    assert C.shape == (5, 5)
+
+
+def test_amgb_all_isfinite(api, be):
+    from mgb_b200.hpc import HPCVector, HPCMatrix
+    assert api.amgb_all_isfinite(HPCVector(np.array([1.0, 2, 3]), be)) is True
+    assert api.amgb_all_isfinite(HPCVector(np.array([1.0, np.inf, 3]), be)) is False
+    assert api.amgb_all_isfinite(HPCMatrix(np.array([[1.0, np.nan], [0, 1]]), be)) is False
+    assert api.amgb_all_isfinite(HPCVector(np.zeros(0), be)) is True   # empty
+
+
+def test_map_rows_kats(api, be):
+    from mgb_b200.hpc import HPCVector, HPCMatrix
+    x = HPCMatrix(np.array([[1.0, 2], [3, 4], [5, 6]]), be)
+    r = api.map_rows(lambda row: sum(row), x)
+    assert isinstance(r, HPCVector) and np.array_equal(api.to_host(r), [3, 7, 11])
+    x = HPCMatrix(np.array([[1.0, 2], [3, 4]]), be)
+    r = api.map_rows(lambda row: (row.sum(), row.prod()), x)
+    assert isinstance(r, HPCMatrix) and np.array_equal(api.to_host(r), [[3, 2], [7, 12]])
+    y = HPCVector(np.array([10.0, 20.0]), be)
+    r = api.map_rows(lambda rx, ry: sum(rx) + ry[0], x, y)
+    assert np.array_equal(api.to_host(r), [13, 27])
+    r = api.map_rows_gpu(lambda rx, ry: (rx[0] ** 2, ry[0] * rx[1]), x, y)
+    assert np.array_equal(api.to_host(r), [[1, 20], [9, 80]])
+
+
+@pytest.mark.parametrize("p,slack", [(1.0, False), (1.5, False), (2.0, True)])
+def test_map_rows_barrier_matches_oracle(api, be, p, slack):
+    from mgb_b200.hpc import HPCMatrix
+    rng = np.random.default_rng(3)
+    n, nD = 1000, 5 if slack else 4
+    Dz = rng.normal(size=(n, nD)) * 0.4
+    Dz[:, 3] = 2.5 + rng.uniform(size=n)
+    if slack:
+        Dz[:, 4] = rng.uniform(-0.5, 0.5, size=n)
+    x = HPCMatrix(rng.normal(size=(n, 2)), be)
+    Dzm = HPCMatrix(Dz, be)
+    Q = api.convex_Euclidian_power([1, 2, 3], p)
+    Q.slack = slack
+    Qo = O.EuclidianPower(idx=[1, 2, 3], p=p, slack=slack)
+    F = api.to_host(api.map_rows_gpu(Q.F, x, Dzm))
+    F1 = api.to_host(api.map_rows_gpu(Q.F1, x, Dzm))
+    F2 = api.to_host(api.map_rows_gpu(Q.F2, x, Dzm))
+    assert np.allclose(F, Qo.F(None, Dz), rtol=1e-13, atol=1e-13)
+    assert np.allclose(F1, Qo.F1(None, Dz), rtol=1e-13, atol=1e-13)
+    assert np.allclose(F2, Qo.F2(None, Dz).reshape(n, nD * nD), rtol=1e-13, atol=1e-13)
+
+
+def test_geometry_roundtrip_and_solve(api, be):
+    # reference test/test_quick.jl:52-140
+    from mgb_b200.hpc import HPCMatrix, HPCVector, HPCSparseMatrix
+    g = api.fem1d_mpi(L=3, backend=be)
+    assert isinstance(g.x, HPCMatrix) and isinstance(g.w, HPCVector) and isinstance(g.operators["id"], HPCSparseMatrix)
+    gn = api.mpi_to_native(g)
+    ref = mgb_b200.fem1d(3)
+    assert np.allclose(gn.x, ref.x) and np.allclose(gn.w, ref.w)
+    assert (gn.operators["dx"] - ref.operators["dx"]).nnz == 0
+    assert g.operators["id"].rowptr.dtype == np.int32 and g.operators["id"].rowptr[0] == 1
+    sol = api.amgb(g, p=1.0, verbose=False, tol=1e-10)
+    soln = api.mpi_to_native(sol)
+    assert soln.z.shape == (16, 2)
+    sol_ref = O.amgb(ref, p=1.0, tol=1e-10)
+    assert np.linalg.norm(soln.z - sol_ref.z) < 1e-10 * 1000   # reference tolerance: TOL*1000, test_quick.jl:140
+
+
+def test_fem2d_mpi_solve_wrapper(api):
+    sol = api.fem2d_mpi_solve(L=2, p=2.0, verbose=False)       # reference test/test_2d.jl L=2 p=2
+    soln = api.mpi_to_native(sol)
+    sol_ref = O.amgb(mgb_b200.fem2d(2), p=2.0)
+    assert np.linalg.norm(soln.z - sol_ref.z) / np.linalg.norm(sol_ref.z) < 1e-9
+    assert np.array_equal(soln.SOL_main["its"], sol_ref.SOL_main["its"])
