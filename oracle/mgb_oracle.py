@@ -31,6 +31,8 @@ import scipy.sparse as sp
 import scipy.sparse.linalg as spla
 
 EPS = np.finfo(np.float64).eps
+# Newton stops once the decrement is within the rounding noise of the objective (see solver.py)
+NEWTON_NOISE = 1024.0
 
 
 # --------------------------------------------------------------------------------------
@@ -260,7 +262,7 @@ def newton(F0, F1, F2, x, maxit=50, alpha=0.1, beta=0.25, solve_fn=solve):
         H = F2(x)
         n = solve_fn(H, g)
         inc = float(np.dot(g, n))
-        if not math.isfinite(inc) or inc <= 16 * EPS * max(1.0, abs(y)):
+        if not math.isfinite(inc) or inc <= NEWTON_NOISE * EPS * max(1.0, abs(y)):
             converged = True
             break
         k += 1
