@@ -67,7 +67,8 @@ typedef struct {
 const char* mgb_last_error(void);
 int mgb_version(void);
 
-/* Context = one GPU + one stream.  stream==NULL creates an owned stream.  Not re-entrant per ctx
+/* Context = one GPU + one stream (a cudaStream_t owned by the caller).  stream==NULL selects the
+ * legacy default stream, which orders with the caller's other default-stream work.  Not re-entrant per ctx
  * (one Julia thread drives a rank: SURVEY.md 8b). */
 int mgb_ctx_create(int device, void* stream, mgb_ctx** out);
 int mgb_ctx_destroy(mgb_ctx* ctx);

@@ -267,8 +267,9 @@ int mgb_ctx_create(int device, void* stream, mgb_ctx** out) {
         auto ctx = std::make_unique<mgb_ctx>();
         ctx->device = device;
         ctx->sm_count = prop.multiProcessorCount;
-        if (stream) ctx->stream = (cudaStream_t)stream;
-        else { CUDA_OK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)); ctx->own_stream = true; }
+        // stream == NULL selects the legacy default stream (0): it orders with the caller's other
+        // default-stream work (CUDA.jl / torch enqueue there unless told otherwise)
+        ctx->stream = (cudaStream_t)stream;
         ctx->flag.alloc(1);
         *out = ctx.release();
         return 0;
