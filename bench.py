@@ -191,35 +191,92 @@ def main():
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    exch = None
+    if world > 1:
+        from mgb_b200 import dist as mdist
+        gplan = capi.Plan(None, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"])   # replicated symbolic pattern
+        grp, gci = gplan.pattern()
+        lrp, lci = plan.pattern()
+        ex = mdist.build_exchange(rank, world, plan.m, grp.astype(np.int64), gci.astype(np.int64),
+                                  lrp.astype(np.int64), lci.astype(np.int64), dev)
+        exch = mdist.Exchanger(ex, dev, ctx=ctx)
+        flush_buf = torch.empty(256 << 17, dtype=f64, device=dev)  # 256 MiB
+
+    def step_multi(nsteps):
+        """per-step CUDA events on the launching stream; interface exchange + scalar all-reduce inside"""
+        tot = 0.0
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for r in range(nsteps):
+            if flush:
+                flush_buf.fill_(float(r))
+            ev0.record()
+            plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
+            exch.exchange(hval_d, grad_d, scal_d)
+            ev1.record()
+            ev1.synchronize()
+            tot += ev0.elapsed_time(ev1)
+        return tot / nsteps
+
     # ---- warm-up
-    plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, args.warmup, flush, split=False)
+    if world == 1:
+        plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, args.warmup, flush, split=False)
+    else:
+        step_multi(args.warmup)
     launches0 = capi.launch_count()
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
     wall0 = time.perf_counter()
-    ms_total, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
-                                                     args.steps, flush, split=False)
+    if world == 1:
+        ms_total, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
+                                                         args.steps, flush, split=False)
+    else:
+        ms_total = step_multi(args.steps)
     launches = capi.launch_count() - launches0
     barrier()
     wall = time.perf_counter() - wall0
     # per-kernel split (separate pass, not part of `value`)
     _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
                                                max(10, args.steps // 2), flush, split=True)
-    # ---- e2e through host buffers
-    s_h = pr["s"].copy()
-    Dz0_h = np.asfortranarray(pr["Dz0"][rows[0]:rows[1]])
-    c_h = np.asfortranarray(pr["c"][rows[0]:rows[1]])
-    plan.assemble_host(s_h, Dz0_h, c_h, args.t, flags, upload_inputs=True)
-    for _ in range(2):
-        plan.assemble_host(s_h, None, None, args.t, flags, upload_inputs=False)
+    # ---- e2e through host buffers (pinned): H2D of the Newton unknown, D2H of gradient + Hessian values
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    s_h = pin(pr["s"])
+    n_h = exch.ex.n_own_h if exch is not None else plan.nnzH
+    n_g = exch.ex.n_own_g if exch is not None else plan.m
+    hval_h = torch.empty(max(n_h, 1), dtype=f64).pin_memory()
+    grad_h = torch.empty(max(n_g, 1), dtype=f64).pin_memory()
+    scal_h = torch.empty(4, dtype=f64).pin_memory()
+
+    def e2e_step():
+        s_d.copy_(s_h, non_blocking=True)
+        plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
+        if exch is not None:
+            ho, go, _ = exch.exchange(hval_d, grad_d, scal_d)
+        else:
+            ho, go = hval_d[:n_h], grad_d[:n_g]
+        hval_h[:n_h].copy_(ho, non_blocking=True)
+        grad_h[:n_g].copy_(go, non_blocking=True)
+        scal_h.copy_(scal_d, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        e2e_step()
     barrier()
     e2e_steps = max(5, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        out = plan.assemble_host(s_h, None, None, args.t, flags, upload_inputs=False)
+        e2e_step()
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    # the same call through the C ABI with plain (pageable) host buffers, as a Julia Array caller sees it
+    if world == 1:
+        plan.assemble_host(pr["s"], np.asfortranarray(pr["Dz0"]), np.asfortranarray(pr["c"]), args.t, flags, True)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            plan.assemble_host(pr["s"], None, None, args.t, flags, upload_inputs=False)
+        e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / 5
+    else:
+        e2e_pageable_ms = None
     clocks = sampler.stop()
 
     vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms], dtype=f64, device=dev)
@@ -246,10 +303,12 @@ def main():
                        "l2": "flushed between steps (256 MiB write)" if flush else "not flushed",
                        "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
                        "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
-                       "rows_per_rank": nloc},
+                       "rows_per_rank": nloc,
+                       "multi_gpu": None if world == 1 else "row-block shards; interface rows via one all_to_all + 4-double all_reduce per assembly"},
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(plan.m * 8),
-                    "d2h_bytes_per_step": int((plan.m + plan.nnzH + 4) * 8)},
+                    "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned",
+                    "c_abi_pageable_ms": e2e_pageable_ms},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "element_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": None, "peak_source": peak_src,

@@ -1,0 +1,185 @@
+"""Row-block sharding of the assembly over the GPUs of one box (one process per GPU).
+
+Partitioning follows the reference's HPCSparseArrays layout: quadrature rows are
+split in contiguous blocks (whole broken elements, so apply_D needs no halo), the outputs - gradient
+entries and rows of R'HR - are split in contiguous blocks of the m unknowns.  Every rank assembles
+the contributions of its own quadrature rows on its local pattern; the contributions to rows owned by
+another rank (the interface between neighbouring row blocks) travel once per assembly in a single
+all-to-all, and are summed at the owner in fixed source-rank order (bit-reproducible).  The scalars
+(objective, <c,Dz>, feasibility) are one 4-double all-reduce.
+
+The index maps are built once per level (symbolic phase) from replicated structural information plus
+one integer all-to-all; the per-assembly work is: pack kernel -> all_to_all_single -> unpack kernels.
+The same code runs on CPU tensors with the gloo backend (tests/test_dist_cpu.py) - there the packing
+uses torch index ops and the local values come from the test, the CUDA kernels are not involved.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .hpc import uniform_partition
+
+
+def owner_of(part: np.ndarray, idx: np.ndarray) -> np.ndarray:
+    """rank owning each 0-based index under the 1-based offset vector ``part``."""
+    return np.searchsorted(part[1:] - 1, idx, side="right")
+
+
+@dataclass
+class ExchangePlan:
+    """Frozen maps of one level's interface exchange (per rank)."""
+    rank: int
+    nranks: int
+    m_part: np.ndarray            # 1-based offsets of the unknowns
+    own_rowptr: np.ndarray        # CSR of the owned rows of the global pattern (0-based, local row ids)
+    own_colidx: np.ndarray
+    # Hessian values
+    h_send_idx: torch.Tensor      # positions in the local value array, grouped by destination rank
+    h_send_splits: List[int]
+    h_recv_pos: torch.Tensor      # positions in the owned value array, grouped by source rank
+    h_recv_splits: List[int]
+    # gradient entries
+    g_send_idx: torch.Tensor
+    g_send_splits: List[int]
+    g_recv_pos: torch.Tensor
+    g_recv_splits: List[int]
+    n_own_h: int = 0
+    n_own_g: int = 0
+
+
+def _exchange_int_lists(lists: List[np.ndarray], device, group=None) -> List[np.ndarray]:
+    """all-to-all of variable-length int64 lists (setup only)."""
+    P = len(lists)
+    send_counts = torch.tensor([len(x) for x in lists], dtype=torch.int64, device=device)
+    recv_counts = torch.empty(P, dtype=torch.int64, device=device)
+    dist.all_to_all_single(recv_counts, send_counts, group=group)
+    rc = [int(v) for v in recv_counts.cpu()]
+    sendbuf = torch.from_numpy(np.concatenate(lists).astype(np.int64) if P else np.zeros(0, np.int64)).to(device)
+    recvbuf = torch.empty(sum(rc), dtype=torch.int64, device=device)
+    dist.all_to_all_single(recvbuf, sendbuf, output_split_sizes=rc, input_split_sizes=[len(x) for x in lists],
+                           group=group)
+    out, o = [], 0
+    rb = recvbuf.cpu().numpy()
+    for c in rc:
+        out.append(rb[o:o + c])
+        o += c
+    return out
+
+
+def build_exchange(rank: int, nranks: int, m: int, glob_rowptr: np.ndarray, glob_colidx: np.ndarray,
+                   loc_rowptr: np.ndarray, loc_colidx: np.ndarray, device, m_part: Optional[np.ndarray] = None,
+                   group=None) -> ExchangePlan:
+    """``glob_*``: global pattern of R'HR (replicated, from a symbolic-only plan over all rows);
+    ``loc_*``: pattern of this rank's local plan (m rows, global column ids)."""
+    m_part = uniform_partition(m, nranks) if m_part is None else m_part
+    lo, hi = int(m_part[rank] - 1), int(m_part[rank + 1] - 1)
+    own_rowptr = (glob_rowptr[lo:hi + 1] - glob_rowptr[lo]).astype(np.int64)
+    own_colidx = glob_colidx[glob_rowptr[lo]:glob_rowptr[hi]].astype(np.int64)
+    # ---- Hessian: every local entry (a,b) -> (owner(a), position inside the owner's block)
+    rows_loc = np.repeat(np.arange(m, dtype=np.int64), np.diff(loc_rowptr))
+    own = owner_of(m_part, rows_loc)
+    # position of (a,b) in the global pattern: search b inside row a of the global CSR
+    gpos = np.empty(rows_loc.size, dtype=np.int64)
+    key_g = np.repeat(np.arange(m, dtype=np.int64), np.diff(glob_rowptr)) * (m + 1) + glob_colidx.astype(np.int64)
+    key_l = rows_loc * (m + 1) + loc_colidx.astype(np.int64)
+    gpos = np.searchsorted(key_g, key_l)
+    if gpos.size and not np.array_equal(key_g[gpos], key_l):
+        raise RuntimeError("local pattern is not contained in the global pattern")
+    blk_start = glob_rowptr[(m_part[:-1] - 1).astype(np.int64)].astype(np.int64)  # first global position of each owner
+    pos_in_owner = gpos - blk_start[own]
+    order = np.argsort(own, kind="stable")
+    h_send_idx = order.astype(np.int64)
+    h_send_splits = [int(c) for c in np.bincount(own, minlength=nranks)]
+    send_lists, o = [], 0
+    for r in range(nranks):
+        send_lists.append(pos_in_owner[order[o:o + h_send_splits[r]]])
+        o += h_send_splits[r]
+    recv_lists = _exchange_int_lists(send_lists, device, group)
+    # ---- gradient: local rows with at least one entry touch dof a
+    touched = np.flatnonzero(np.diff(loc_rowptr) > 0).astype(np.int64)
+    gown = owner_of(m_part, touched)
+    gorder = np.argsort(gown, kind="stable")
+    g_send_splits = [int(c) for c in np.bincount(gown, minlength=nranks)]
+    gsend, o = [], 0
+    for r in range(nranks):
+        sel = touched[gorder[o:o + g_send_splits[r]]]
+        gsend.append(sel - int(m_part[r] - 1))
+        o += g_send_splits[r]
+    grecv = _exchange_int_lists(gsend, device, group)
+    td = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int64)).to(device)
+    return ExchangePlan(rank, nranks, m_part, own_rowptr, own_colidx,
+                        td(h_send_idx), h_send_splits, td(np.concatenate(recv_lists) if recv_lists else np.zeros(0)),
+                        [len(x) for x in recv_lists],
+                        td(touched[gorder]), g_send_splits, td(np.concatenate(grecv) if grecv else np.zeros(0)),
+                        [len(x) for x in grecv], n_own_h=int(own_colidx.size), n_own_g=hi - lo)
+
+
+class Exchanger:
+    """Per-assembly interface exchange.  ``ctx`` (capi.Context) selects the CUDA pack/unpack kernels;
+    ``ctx=None`` uses torch index ops (CPU / gloo tests)."""
+
+    def __init__(self, ex: ExchangePlan, device, ctx=None, group=None):
+        self.ex, self.device, self.ctx, self.group = ex, device, ctx, group
+        f64 = torch.float64
+        self.h_send = torch.empty(int(ex.h_send_idx.numel()), dtype=f64, device=device)
+        self.h_recv = torch.empty(int(ex.h_recv_pos.numel()), dtype=f64, device=device)
+        self.g_send = torch.empty(int(ex.g_send_idx.numel()), dtype=f64, device=device)
+        self.g_recv = torch.empty(int(ex.g_recv_pos.numel()), dtype=f64, device=device)
+        self.h_own = torch.zeros(max(ex.n_own_h, 1), dtype=f64, device=device)
+        self.g_own = torch.zeros(max(ex.n_own_g, 1), dtype=f64, device=device)
+        if ctx is not None:
+            self._h_send_idx32 = ex.h_send_idx.to(torch.int32)
+            self._h_recv_pos32 = ex.h_recv_pos.to(torch.int32)
+            self._g_send_idx32 = ex.g_send_idx.to(torch.int32)
+            self._g_recv_pos32 = ex.g_recv_pos.to(torch.int32)
+
+    def _pack(self, src, idx64, idx32, out):
+        if out.numel() == 0:
+            return
+        if self.ctx is None:
+            torch.index_select(src, 0, idx64, out=out)
+        else:
+            self.ctx.gather_idx(src, idx32, out.numel(), out)
+
+    def _unpack(self, recv, pos64, pos32, splits, dst):
+        o = 0
+        for cnt in splits:  # fixed source-rank order; positions are unique within one source
+            if cnt:
+                if self.ctx is None:
+                    dst.index_add_(0, pos64[o:o + cnt], recv[o:o + cnt])
+                else:
+                    self.ctx.scatter_add_idx(recv[o:o + cnt], pos32[o:o + cnt], cnt, dst)
+            o += cnt
+
+    def exchange(self, hval_loc: Optional[torch.Tensor], grad_loc: Optional[torch.Tensor], scal: Optional[torch.Tensor]):
+        """Returns (H values of the owned rows, owned gradient block, reduced scalars)."""
+        ex = self.ex
+        i32 = self.ctx is not None
+        if hval_loc is not None:
+            self._pack(hval_loc, ex.h_send_idx, self._h_send_idx32 if i32 else None, self.h_send)
+            dist.all_to_all_single(self.h_recv, self.h_send, output_split_sizes=ex.h_recv_splits,
+                                   input_split_sizes=ex.h_send_splits, group=self.group)
+            self.h_own.zero_()
+            self._unpack(self.h_recv, ex.h_recv_pos, self._h_recv_pos32 if i32 else None, ex.h_recv_splits, self.h_own)
+        if grad_loc is not None:
+            self._pack(grad_loc, ex.g_send_idx, self._g_send_idx32 if i32 else None, self.g_send)
+            dist.all_to_all_single(self.g_recv, self.g_send, output_split_sizes=ex.g_recv_splits,
+                                   input_split_sizes=ex.g_send_splits, group=self.group)
+            self.g_own.zero_()
+            self._unpack(self.g_recv, ex.g_recv_pos, self._g_recv_pos32 if i32 else None, ex.g_recv_splits, self.g_own)
+        if scal is not None:
+            # {f0, all_finite, <c,Dz>, nonfinite count}: sums, with all_finite recomputed from the count
+            dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=self.group)
+            scal[1] = (scal[3] == 0).to(scal.dtype)
+        return self.h_own[: ex.n_own_h], self.g_own[: ex.n_own_g], scal
+
+
+def element_rows(n: int, block: int, rank: int, nranks: int):
+    """[row0,row1) of this rank: whole elements, first ranks take the remainder (uniform_partition)."""
+    part = uniform_partition(n, nranks, block)
+    return int(part[rank] - 1), int(part[rank + 1] - 1)
