@@ -12,8 +12,9 @@ apply_D -> barrier F/F1/F2 -> gradient -> Hessian numeric phase -> R'HR values (
             no julia/mpiexec in the image) timed on the host cores.
 
 N > 1 (torchrun): quadrature rows (whole elements) are sharded across ranks, every rank assembles
-the contributions of its own rows (no data-path collective inside the timed region; the owner-side
-sum of the few shared interface rows is part of the solve seam), scaling = "strong".
+the contributions of its own rows, then the interface rows travel to their owners (one NCCL
+all-to-all per output + a 4-double all-reduce, all inside the timed region); the fixed L=8 problem is
+split, so scaling = "strong".
 """
 from __future__ import annotations
 
