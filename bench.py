@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--t", type=float, default=1.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
     ap.add_argument("--cpu-reps", type=int, default=3)
+    ap.add_argument("--two-stage", action="store_true", help="element_kernel + gather_kernel instead of the patch-fused kernel")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -174,7 +175,8 @@ def main():
     stream = torch.cuda.current_stream(dev)
     ctx = capi.Context(local_rank, stream.cuda_stream)
     t_plan = time.perf_counter()
-    plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows)
+    plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows,
+                     force_path=capi.PLAN_TWO_STAGE if args.two_stage else 0)
     t_plan = time.perf_counter() - t_plan
     nloc = rows[1] - rows[0]
     flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
@@ -311,7 +313,7 @@ def main():
                     "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned",
                     "c_abi_pageable_ms": e2e_pageable_ms},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "element_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "element_kernel" if args.two_stage else "patch_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes": int(alg_elem), "kernel_ms": ms_elem,
                          "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all,

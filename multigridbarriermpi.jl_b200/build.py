@@ -9,8 +9,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MGB_B200_LIB") or os.path.join(HERE, "libmgb_b200.so")
-SOURCES = ["mgb_b200.cu", "plan_host.cpp"]
-HEADERS = ["kernels.cuh", "kernels_csr.cuh", "plan_host.h", os.path.join("..", "..", "include", "mgb_b200.h")]
+SOURCES = ["mgb_b200.cu", "plan_host.cpp", "launch.cu", "inst_1d.cu", "inst_2d.cu"]
+HEADERS = ["kernels.cuh", "kernels_csr.cuh", "plan_host.h", "launch.h", "inst_common.cuh", os.path.join("..", "..", "include", "mgb_b200.h")]
 
 
 def _nvcc() -> str:
@@ -32,16 +32,32 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) 
     """``out``/``extra`` build tuning variants (e.g. -DMGB_ELEM_MINBLOCKS=6) next to the default library."""
     if not force and out == LIB and not needs_build():
         return LIB
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "--shared", "-Xcompiler", "-fPIC,-O3", *extra, "-o", out] + [os.path.join(CSRC, s) for s in SOURCES]
+    import concurrent.futures as cf
+    import tempfile
+    objdir = tempfile.mkdtemp(prefix="mgb_b200_obj_")
+    common = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC,-O3", *extra]
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        common[1:1] = ["-Xptxas", "-v"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
+        res = subprocess.run(common + ["-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        return src, obj, res
+
+    objs, logs = [], []
+    with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        for src, obj, res in ex.map(compile_one, SOURCES):
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
+            objs.append(obj)
+            logs.append(res.stderr)
+    res = subprocess.run([_nvcc(), "--shared", "-o", out] + objs, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    shutil.rmtree(objdir, ignore_errors=True)
     if verbose:
-        sys.stderr.write(res.stderr)
+        sys.stderr.write("".join(logs))
     return out
 
 

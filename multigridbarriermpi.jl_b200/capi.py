@@ -18,6 +18,7 @@ from . import build as _build
 WANT_F0, WANT_GRAD, WANT_HESS, STORE_DZ = 1, 2, 4, 8
 PATH_ELEMENT, PATH_CSR = 1, 2
 PLAN_NO_HESSIAN = 16
+PLAN_TWO_STAGE = 32
 BARRIER_EUCLIDIAN_POWER = 1
 
 EXPORTS = [

@@ -111,8 +111,13 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
 }
 
 // FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
+// Per-point work of one element group (LPE lanes).  Writes the element's gradient record to `rel`
+// and its slot record to `sel` (global memory in the two-stage path, shared memory in the patch-
+// fused path; entry r of a butterfly-reduced block is stored at  off + r*LPE + lane).  Returns this
+// thread's objective / <c,Dz> / infeasibility partials.  Every lane of the group must call it.
 template <int B, int D, bool SLACK, bool FINE, int FLAGS>
-__global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
+__device__ __forceinline__ void element_body(const ElemParams& P, const int64_t e, const int l, double* __restrict__ sel,
+                                             double* __restrict__ rel, double& v0, double& v1, double& v2) {
     constexpr int LPE = Pow2Ceil<B>::value;
     constexpr int ND = D + 2 + (SLACK ? 1 : 0);
     constexpr int NU = 2 + (SLACK ? 1 : 0);
@@ -120,9 +125,6 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
     constexpr int NTRI = (B * (B + 1) / 2 + LPE - 1) / LPE * LPE;
     constexpr int NFULL = (B * B + LPE - 1) / LPE * LPE;
 
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t e = tid / LPE;
-    const int l = (int)(tid % LPE);
     const bool act_e = e < P.E;
     const bool act = act_e && (l < B);
     const int64_t i = act ? e * B + l : 0;
@@ -211,34 +213,15 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
         bo.feasible = bo.feasible && (tau1 > 0.0);
     }
 
-    // ---- objective / feasibility partials (fixed-order block reduction)
+    // ---- objective / feasibility partials of this point (reduced by the caller in a fixed order)
     {
         double cd = 0.0;
 #pragma unroll
         for (int k = 0; k < ND; ++k) cd = fma(cc[k], dz[k], cd);
-        double v0 = 0.0, v1 = act ? wi * cd : 0.0;
-        if (WF) v0 = act ? wi * bo.F : 0.0;
-        double v2 = (act && !bo.feasible) ? 1.0 : 0.0;
-#pragma unroll
-        for (int mk = 16; mk >= 1; mk >>= 1) {
-            v0 += shfl_xor_d(v0, mk);
-            v1 += shfl_xor_d(v1, mk);
-            v2 += shfl_xor_d(v2, mk);
-        }
-        __shared__ double red[3][4];
-        const int wid = threadIdx.x >> 5;
-        if ((threadIdx.x & 31) == 0) { red[0][wid] = v0; red[1][wid] = v1; red[2][wid] = v2; }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-            const int nw = blockDim.x >> 5;
-            for (int r = 0; r < nw; ++r) { s0 += red[0][r]; s1 += red[1][r]; s2 += red[2][r]; }
-            P.part[(int64_t)blockIdx.x * 4 + 0] = s0;
-            P.part[(int64_t)blockIdx.x * 4 + 1] = s1;
-            P.part[(int64_t)blockIdx.x * 4 + 2] = s2;
-        }
+        v0 = (WF && act) ? wi * bo.F : 0.0;
+        v1 = act ? wi * cd : 0.0;
+        v2 = (act && !bo.feasible) ? 1.0 : 0.0;
     }
-    if (!(WG || WH)) return;
     // an infeasible point produces NaN/Inf values; they flow to the outputs as data (the caller
     // reads all_finite, like amgb_all_isfinite in the reference, src:121-133)
 
@@ -263,11 +246,11 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
             ru[q] = r;
         }
         group_reduce<LPE, LPE>(ru, l);
-        if (act_e) P.rel[(e * NU + 0) * LPE + l] = ru[0];
+        if (act_e) rel[l] = ru[0];
         if (FINE) {
 #pragma unroll
             for (int v = 1; v < NU; ++v)
-                if (act && oh[v]) P.rel[(e * NU + v) * LPE + olq[v]] = oval[v] * gy[D + v];
+                if (act && oh[v]) rel[v * LPE + olq[v]] = oval[v] * gy[D + v];
         } else {
 #pragma unroll
             for (int v = 1; v < NU; ++v) {
@@ -275,14 +258,12 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
 #pragma unroll
                 for (int q = 0; q < LPE; ++q) rs[q] = (q < B) ? aid[FINE ? 0 : v][FINE ? 0 : (q < B ? q : 0)] * gy[D + v] : 0.0;
                 group_reduce<LPE, LPE>(rs, l);
-                if (act_e) P.rel[(e * NU + v) * LPE + l] = rs[0];
+                if (act_e) rel[v * LPE + l] = rs[0];
             }
         }
     }
-    if (!WH) return;
-
+    if (WH) {
     // ---- Hessian: element-local blocks of sum_jk a_j' (w Y_jk) a_k
-    double* sel = P.sel + e * (int64_t)P.NS;
     // u-u block (derivative operators only: the u.id row of F2 is identically zero)
     {
         double T[D][B];
@@ -310,7 +291,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
         group_reduce<NTRI, LPE>(v, l);
         if (act_e) {
 #pragma unroll
-            for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + l * (NTRI / LPE) + r] = v[r];
+            for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + r * LPE + l] = v[r];
         }
     }
     // u-s (and u-slack) blocks
@@ -351,7 +332,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
             const int off = (v2 == 1) ? P.off_us : P.off_ut;
             if (act_e) {
 #pragma unroll
-                for (int r = 0; r < NFULL / LPE; ++r) sel[off + l * (NFULL / LPE) + r] = v[r];
+                for (int r = 0; r < NFULL / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
         }
 #pragma unroll
@@ -368,7 +349,7 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
             const int off = (v1 == 1) ? P.off_ss : P.off_tt;
             if (act_e) {
 #pragma unroll
-                for (int r = 0; r < NTRI / LPE; ++r) sel[off + l * (NTRI / LPE) + r] = v[r];
+                for (int r = 0; r < NTRI / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
         }
         if (SLACK) {  // s x slack full block
@@ -383,9 +364,161 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
             group_reduce<NFULL, LPE>(v, l);
             if (act_e) {
 #pragma unroll
-                for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + l * (NFULL / LPE) + r] = v[r];
+                for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + r * LPE + l] = v[r];
             }
         }
+    }
+    }  // WH
+}
+
+// fixed-order block reduction of the three scalar partials -> part[blockIdx]
+__device__ __forceinline__ void block_scalars(double v0, double v1, double v2, double* __restrict__ part) {
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) {
+        v0 += shfl_xor_d(v0, mk);
+        v1 += shfl_xor_d(v1, mk);
+        v2 += shfl_xor_d(v2, mk);
+    }
+    __shared__ double red[3][32];
+    const int wid = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][wid] = v0; red[1][wid] = v1; red[2][wid] = v2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        const int nw = (blockDim.x + 31) >> 5;
+        for (int r = 0; r < nw; ++r) { s0 += red[0][r]; s1 += red[1][r]; s2 += red[2][r]; }
+        part[(int64_t)blockIdx.x * 4 + 0] = s0;
+        part[(int64_t)blockIdx.x * 4 + 1] = s1;
+        part[(int64_t)blockIdx.x * 4 + 2] = s2;
+    }
+}
+
+// Two-stage path, stage 1: slot / gradient records to global memory (replayed by gather_kernel).
+template <int B, int D, bool SLACK, bool FINE, int FLAGS>
+__global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr int NU = 2 + (SLACK ? 1 : 0);
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = tid / LPE;
+    const int l = (int)(tid % LPE);
+    double v0, v1, v2;
+    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
+    block_scalars(v0, v1, v2, P.part);
+}
+
+// Patch-fused path: one CTA = PATCH consecutive elements.  Phase A keeps the slot / gradient records
+// in shared memory; phase B replays the patch's frozen lists: entries fed by this patch alone go
+// straight into the CSR value array / gradient, the others leave one partial sum per patch in the
+// export buffers that interface_kernel folds.  No atomics; fixed summation order.
+struct PatchParams {
+    int NSP, RSP;                 // shared-memory strides (doubles) of the slot / gradient records
+    const int32_t* w2_pp;  const int32_t* w2_dest;  const uint32_t* w2_src;
+    const int32_t* lg_pp;  const int32_t* lg_dest;  const int32_t* lg_ptr;  const uint16_t* lg_idx;
+    const int32_t* g_pp;   const int32_t* g_dest;   const int32_t* g_ptr;   const uint16_t* g_idx;
+    double* hval;  double* hexp;  double* grad;  double* gexp;
+};
+
+template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
+__global__ void __launch_bounds__(PATCH * Pow2Ceil<B>::value) patch_kernel(const ElemParams P, const PatchParams Q) {
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr bool WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0;
+    extern __shared__ double smem[];
+    double* sel_s = smem;                          // PATCH * NSP
+    double* rel_s = smem + (size_t)PATCH * Q.NSP;  // PATCH * RSP
+    const int el = threadIdx.x / LPE;
+    const int l = threadIdx.x % LPE;
+    const int64_t e = (int64_t)blockIdx.x * PATCH + el;
+    double v0, v1, v2;
+    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, sel_s + (size_t)el * Q.NSP, rel_s + (size_t)el * Q.RSP, v0, v1, v2);
+    block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes the records
+    if (!(WG || WH)) return;
+    const int p = blockIdx.x;
+    if (WH) {
+        for (int k = Q.w2_pp[p] + threadIdx.x; k < Q.w2_pp[p + 1]; k += blockDim.x) {
+            const int32_t dest = __ldg(&Q.w2_dest[k]);
+            const uint32_t src = __ldg(&Q.w2_src[k]);
+            double v = sel_s[src & 0xFFFFu];
+            const uint32_t s1 = src >> 16;
+            if (s1 != 0xFFFFu) v += sel_s[s1];
+            if (dest >= 0) Q.hval[dest] = v; else Q.hexp[-1 - dest] = v;
+        }
+        for (int k = Q.lg_pp[p] + threadIdx.x; k < Q.lg_pp[p + 1]; k += blockDim.x) {
+            const int32_t dest = __ldg(&Q.lg_dest[k]);
+            double v = 0.0;
+            for (int r = __ldg(&Q.lg_ptr[k]); r < __ldg(&Q.lg_ptr[k + 1]); ++r) v += sel_s[__ldg(&Q.lg_idx[r])];
+            if (dest >= 0) Q.hval[dest] = v; else Q.hexp[-1 - dest] = v;
+        }
+    }
+    if (WG) {
+        for (int k = Q.g_pp[p] + threadIdx.x; k < Q.g_pp[p + 1]; k += blockDim.x) {
+            const int32_t dest = __ldg(&Q.g_dest[k]);
+            double v = 0.0;
+            for (int r = __ldg(&Q.g_ptr[k]); r < __ldg(&Q.g_ptr[k + 1]); ++r) v += rel_s[__ldg(&Q.g_idx[r])];
+            if (dest >= 0) Q.grad[dest] = v; else Q.gexp[-1 - dest] = v;
+        }
+    }
+}
+
+struct InterfaceParams {
+    int64_t n_if, n_gif, nparts;
+    const int32_t* if_t;  const int32_t* if_ptr;  const double* hexp;  double* hval;
+    const int32_t* gif_a; const int32_t* gif_ptr; const double* gexp;  double* grad;
+    const double* part;  double* scal;  double t;
+    int64_t nblk_h, nblk_g;
+    int warp_per_entry;
+};
+
+// Folds the per-patch partial sums of the interface entries (fixed patch order) and the scalar partials.
+static __global__ void __launch_bounds__(256) interface_kernel(const InterfaceParams P) {
+    const int64_t b = blockIdx.x;
+    if (b < P.nblk_h + P.nblk_g) {
+        const bool isg = b >= P.nblk_h;
+        const int64_t nent = isg ? P.n_gif : P.n_if;
+        const int32_t* __restrict__ ptr = isg ? P.gif_ptr : P.if_ptr;
+        const int32_t* __restrict__ idx = isg ? P.gif_a : P.if_t;
+        const double* __restrict__ src = isg ? P.gexp : P.hexp;
+        double* __restrict__ dst = isg ? P.grad : P.hval;
+        const int64_t bb = isg ? b - P.nblk_h : b;
+        if (P.warp_per_entry) {
+            const int64_t j = bb * 8 + (threadIdx.x >> 5);
+            const int lane = threadIdx.x & 31;
+            if (j >= nent) return;
+            double acc = 0.0;
+            for (int r = ptr[j] + lane; r < ptr[j + 1]; r += 32) acc += src[r];
+#pragma unroll
+            for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+            if (lane == 0) dst[idx[j]] = acc;
+        } else {
+            const int64_t j = bb * 256 + threadIdx.x;
+            if (j >= nent) return;
+            double acc = 0.0;
+            for (int r = __ldg(&ptr[j]); r < __ldg(&ptr[j + 1]); ++r) acc += src[r];
+            dst[__ldg(&idx[j])] = acc;
+        }
+        return;
+    }
+    __shared__ double sh[3][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {
+        s0 += P.part[r * 4 + 0];
+        s1 += P.part[r * 4 + 1];
+        s2 += P.part[r * 4 + 2];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && P.scal) {
+        P.scal[0] = sh[0][0] + P.t * sh[1][0];
+        P.scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
+        P.scal[2] = sh[1][0];
+        P.scal[3] = sh[2][0];
     }
 }
 
@@ -414,7 +547,7 @@ constexpr int GATHER_UNROLL = 4;
 // Replays the frozen contribution lists: blocks [0,nblk_h) produce Hessian values (GATHER_UNROLL
 // entries per thread, two-deep dependent loads), blocks [nblk_h, nblk_h+nblk_g) the gradient, the
 // last block folds the scalar partials in a fixed order.
-__global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
+static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
     const int64_t b = blockIdx.x;
     if (b < P.nblk_h) {
         const int64_t base = b * (256 * GATHER_UNROLL) + threadIdx.x;
@@ -482,7 +615,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
 }
 
 // warp per output entry (long contribution lists: coarse multigrid levels)
-__global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, const int64_t* __restrict__ cptr,
+static __global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, const int64_t* __restrict__ cptr,
                                                           const int32_t* __restrict__ cidx,
                                                           const double* __restrict__ src, double* __restrict__ dst) {
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -497,26 +630,26 @@ __global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, co
 }
 
 // ---------------------------------------------------------------- small utilities
-__global__ void isfinite_kernel(const double* __restrict__ v, int64_t len, int* __restrict__ flag) {
+static __global__ void isfinite_kernel(const double* __restrict__ v, int64_t len, int* __restrict__ flag) {
     int bad = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
         bad |= !isfinite(v[i]);
     if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 0;  // idempotent store, not an accumulation
 }
 
-__global__ void diag_scale_kernel(const double* __restrict__ w, const double* __restrict__ y, int64_t n,
+static __global__ void diag_scale_kernel(const double* __restrict__ w, const double* __restrict__ y, int64_t n,
                                   double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = w[i] * y[i];
 }
 
-__global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v) {
+static __global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
         buf[i] = v;
 }
 
 // y = alpha * A x + beta * y0, thread per row (operator / restriction rows are short)
-__global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int64_t* __restrict__ ptr,
+static __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int64_t* __restrict__ ptr,
                                                    const int32_t* __restrict__ idx, const double* __restrict__ val,
                                                    double alpha, const double* __restrict__ x, double beta,
                                                    const double* __restrict__ y0, double* __restrict__ y) {
@@ -527,13 +660,13 @@ __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const int64_t*
     y[i] = alpha * acc + ((y0 && beta != 0.0) ? beta * y0[i] : 0.0);
 }
 
-__global__ void __launch_bounds__(256) gather_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
+static __global__ void __launch_bounds__(256) gather_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
                                                          int64_t count, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < count) out[k] = src[idx[k]];
 }
 
-__global__ void __launch_bounds__(256) scatter_add_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
+static __global__ void __launch_bounds__(256) scatter_add_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
                                                               int64_t count, double* __restrict__ dst) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k < count) dst[idx[k]] += src[k];  // idx unique within a call: plain read-modify-write

@@ -1,0 +1,27 @@
+// Launch entry points of the templated element / patch kernels.  The instantiations live in
+// inst_1d.cu / inst_2d.cu so the translation units compile in parallel.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.cuh"
+
+namespace mgb {
+
+bool element_supported(int B, int dim);
+// canonical flag sets the kernels are instantiated for: 1 (objective), 7 (objective+gradient+Hessian),
+// 8 (apply_D only), 15 (everything + Dz); other requests run the next superset.
+int canonical_flags(int flags);
+
+void launch_element(int B, int dim, bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_patch(int B, int dim, bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags,
+                  int64_t nblk, size_t smem, cudaStream_t st);
+
+void launch_element_1d(bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_element_2d(bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_patch_1d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
+                     size_t smem, cudaStream_t st);
+void launch_patch_2d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
+                     size_t smem, cudaStream_t st);
+
+}  // namespace mgb

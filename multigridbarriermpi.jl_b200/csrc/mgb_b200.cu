@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <stdexcept>
@@ -16,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "kernels_csr.cuh"
+#include "launch.h"
 #include "plan_host.h"
 
 namespace {
@@ -84,6 +86,15 @@ struct mgb_plan {
     DevBuf<double> d_opd, d_idd, d_ownval, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     DevBuf<uint8_t> d_ownlq;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
+    // patch-fused path
+    int patch = 0;  // elements per CTA (0 = two-stage path)
+    int NSP = 0, RSP = 0;
+    int64_t n_if = 0, n_gif = 0, n_hexp = 0, n_gexp = 0;
+    bool if_warp = false;
+    DevBuf<int32_t> p_w2pp, p_w2dest, p_lgpp, p_lgdest, p_lgptr, p_gpp, p_gdest, p_gptr, p_ift, p_ifptr, p_gifa, p_gifptr;
+    DevBuf<uint32_t> p_w2src;
+    DevBuf<uint16_t> p_lgidx, p_gidx;
+    DevBuf<double> d_hexp, d_gexp;
     bool has_hessian = true;
     bool long_lists = false;
     // ---- csr path
@@ -154,51 +165,19 @@ int64_t algorithmic_bytes(int64_t n, int64_t N, int nD, int dim, int64_t nnzD, i
     return b;
 }
 
-template <int B, int D, bool SLACK, bool FINE>
-void launch_elem_flags(const mgb::ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
-    const int f = flags & 15;
-    const dim3 g((unsigned)nblk), b(128);
-#define MGB_CASE(F)                                                            \
-    case F:                                                                    \
-        mgb::element_kernel<B, D, SLACK, FINE, F><<<g, b, 0, st>>>(P);         \
-        break;
-    switch (f) {
-        MGB_CASE(1) MGB_CASE(2) MGB_CASE(3) MGB_CASE(6) MGB_CASE(7) MGB_CASE(8) MGB_CASE(9) MGB_CASE(10)
-        MGB_CASE(11) MGB_CASE(14) MGB_CASE(15)
-        case 4: mgb::element_kernel<B, D, SLACK, FINE, 6><<<g, b, 0, st>>>(P); break;
-        case 5: mgb::element_kernel<B, D, SLACK, FINE, 7><<<g, b, 0, st>>>(P); break;
-        case 12: mgb::element_kernel<B, D, SLACK, FINE, 14><<<g, b, 0, st>>>(P); break;
-        case 13: mgb::element_kernel<B, D, SLACK, FINE, 15><<<g, b, 0, st>>>(P); break;
-        default: throw std::runtime_error("assemble: empty flags");
-    }
-#undef MGB_CASE
-    g_launches++;
-}
+bool want_patch_early(int force_flags) { return (force_flags & MGB_PLAN_TWO_STAGE) == 0; }
 
-template <int B, int D>
-void launch_elem_bd(const mgb::ElemParams& P, bool slack, bool fine, int flags, int64_t nblk, cudaStream_t st) {
-    if (slack) {
-        if (fine) launch_elem_flags<B, D, true, true>(P, flags, nblk, st);
-        else launch_elem_flags<B, D, true, false>(P, flags, nblk, st);
-    } else {
-        if (fine) launch_elem_flags<B, D, false, true>(P, flags, nblk, st);
-        else launch_elem_flags<B, D, false, false>(P, flags, nblk, st);
-    }
-}
-
-bool elem_supported(int B, int dim) { return (B == 2 && dim == 1) || (B == 7 && dim == 2); }
+bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
 void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
-    cudaStream_t st = pl->ctx->stream;
     const auto& ep = pl->ep;
-    if (ep.B == 2 && ep.dim == 1) launch_elem_bd<2, 1>(P, ep.slack, ep.fine, flags, pl->nblocks_elem, st);
-    else if (ep.B == 7 && ep.dim == 2) launch_elem_bd<7, 2>(P, ep.slack, ep.fine, flags, pl->nblocks_elem, st);
-    else throw std::runtime_error("element kernel not instantiated for this element type");
+    mgb::launch_element(ep.B, ep.dim, ep.slack, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
+    g_launches++;
     CUDA_OK(cudaGetLastError());
 }
 
 void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, int flags,
-                      double* scal, double* grad, double* hval, double* Dz) {
+                      double* scal, double* grad, double* hval, double* Dz, cudaEvent_t mid = nullptr) {
     cudaStream_t st = pl->ctx->stream;
     const auto& ep = pl->ep;
     mgb::ElemParams P{};
@@ -212,7 +191,35 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     if ((flags & MGB_STORE_DZ) && !Dz) throw std::runtime_error("MGB_STORE_DZ without Dz buffer");
     if ((flags & MGB_WANT_GRAD) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
     if ((flags & MGB_WANT_HESS) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
+    if (pl->patch > 0) {
+        int f = flags & 15;
+        if ((f & 6) == 4) f |= 2;  // Hessian-only requests also produce the gradient (same kernel instance)
+        if ((f & 2) && !grad) grad = pl->d_rel.p;  // scratch target when the caller did not ask for it
+        mgb::PatchParams Q{};
+        Q.NSP = pl->NSP; Q.RSP = pl->RSP;
+        Q.w2_pp = pl->p_w2pp.p; Q.w2_dest = pl->p_w2dest.p; Q.w2_src = pl->p_w2src.p;
+        Q.lg_pp = pl->p_lgpp.p; Q.lg_dest = pl->p_lgdest.p; Q.lg_ptr = pl->p_lgptr.p; Q.lg_idx = pl->p_lgidx.p;
+        Q.g_pp = pl->p_gpp.p; Q.g_dest = pl->p_gdest.p; Q.g_ptr = pl->p_gptr.p; Q.g_idx = pl->p_gidx.p;
+        Q.hval = hval; Q.hexp = pl->d_hexp.p; Q.grad = grad; Q.gexp = pl->d_gexp.p;
+        const size_t smem = ((size_t)pl->patch * (pl->NSP + pl->RSP)) * sizeof(double);
+        mgb::launch_patch(ep.B, ep.dim, ep.slack, ep.fine, pl->patch, P, Q, f, pl->nblocks_elem, smem, st);
+        g_launches++;
+        if (mid) CUDA_OK(cudaEventRecord(mid, st));
+        mgb::InterfaceParams I{};
+        I.n_if = (f & 4) ? pl->n_if : 0; I.n_gif = (f & 2) ? pl->n_gif : 0; I.nparts = pl->nblocks_elem;
+        I.if_t = pl->p_ift.p; I.if_ptr = pl->p_ifptr.p; I.hexp = pl->d_hexp.p; I.hval = hval;
+        I.gif_a = pl->p_gifa.p; I.gif_ptr = pl->p_gifptr.p; I.gexp = pl->d_gexp.p; I.grad = grad;
+        I.part = pl->d_part.p; I.scal = scal ? scal : pl->d_scal_tmp.p; I.t = t;
+        I.warp_per_entry = pl->if_warp ? 1 : 0;
+        const int64_t per = pl->if_warp ? 8 : 256;
+        I.nblk_h = (I.n_if + per - 1) / per; I.nblk_g = (I.n_gif + per - 1) / per;
+        mgb::interface_kernel<<<(unsigned)(I.nblk_h + I.nblk_g + 1), 256, 0, st>>>(I);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return;
+    }
     launch_elem(pl, P, flags);
+    if (mid) CUDA_OK(cudaEventRecord(mid, st));
 
     mgb::GatherParams G{};
     G.nnzH = pl->nnzH; G.m = pl->m;
@@ -326,6 +333,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         cudaStream_t st = host_only ? nullptr : ctx->stream;
         bool use_elem = false;
         const bool want_hess = (force_path & MGB_PLAN_NO_HESSIAN) == 0;
+        const int force_flags = force_path;
         force_path &= 3;
         pl->has_hessian = want_hess;
         if (force_path != MGB_PATH_CSR) {
@@ -349,7 +357,9 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
                 pl->long_lists = avg > 12.0;
             }
-            if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
+            if (want_patch_early(force_flags)) {
+                // patch-fused path builds its own lists below
+            } else if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
                 pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
             } else {   // two-wide ELL + long list for the thread-per-entry gather
                 std::vector<int2> src2(pl->nnzH);
@@ -372,11 +382,35 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
-            pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);
-            pl->d_rel.alloc((size_t)ep.E * ep.NU * ep.LPE);
-            CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
+            int want_patch = 0;
+            if ((force_flags & MGB_PLAN_TWO_STAGE) == 0) {
+                want_patch = (ep.B == 2) ? 64 : 32;
+                if (const char* ev = getenv("MGB_PATCH")) want_patch = atoi(ev);
+                if (ep.B == 7 && want_patch != 16 && want_patch != 32 && want_patch != 64) want_patch = 32;
+                if (ep.B == 2) want_patch = 64;
+            }
+            if (want_patch > 0) {
+                mgb::build_patch_plan(ep, want_patch);
+                const auto& pp = ep.patch;
+                pl->patch = pp.P; pl->NSP = pp.NSP; pl->RSP = pp.RSP;
+                pl->n_if = (int64_t)pp.if_t.size(); pl->n_gif = (int64_t)pp.gif_a.size();
+                pl->n_hexp = pp.n_hexp; pl->n_gexp = pp.n_gexp;
+                pl->if_warp = pl->n_if > 0 && (double)pp.n_hexp / (double)pl->n_if > 16.0;
+                pl->p_w2pp.upload(pp.w2_pp, st); pl->p_w2dest.upload(pp.w2_dest, st); pl->p_w2src.upload(pp.w2_src, st);
+                pl->p_lgpp.upload(pp.lg_pp, st); pl->p_lgdest.upload(pp.lg_dest, st); pl->p_lgptr.upload(pp.lg_ptr, st);
+                pl->p_lgidx.upload(pp.lg_idx, st);
+                pl->p_gpp.upload(pp.g_pp, st); pl->p_gdest.upload(pp.g_dest, st); pl->p_gptr.upload(pp.g_ptr, st);
+                pl->p_gidx.upload(pp.g_idx, st);
+                pl->p_ift.upload(pp.if_t, st); pl->p_ifptr.upload(pp.if_ptr, st);
+                pl->p_gifa.upload(pp.gif_a, st); pl->p_gifptr.upload(pp.gif_ptr, st);
+                pl->d_hexp.alloc((size_t)std::max<int64_t>(pp.n_hexp, 1)); pl->d_gexp.alloc((size_t)std::max<int64_t>(pp.n_gexp, 1));
+                CUDA_OK(cudaStreamSynchronize(st));
+            }
+            if (pl->patch == 0) pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);
+            pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m));
+            if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
-            const int epb = 128 / ep.LPE;
+            const int epb = pl->patch > 0 ? pl->patch : 128 / ep.LPE;
             pl->nblocks_elem = (ep.E + epb - 1) / epb;
             pl->d_part.alloc((size_t)pl->nblocks_elem * 4);
             pl->d_scal_tmp.alloc(4);
@@ -653,22 +687,16 @@ int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, 
             // second pass with an event between the two kernels (kept out of the totals above)
             for (int r = 0; r < reps; ++r) {
                 if (flush_l2) mgb::l2_flush_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->flush.p, flush_len, (double)r);
-                mgb::ElemParams P{};
-                const auto& ep = pl->ep;
-                P.E = ep.E; P.nloc = ep.nloc; P.lcols = pl->d_lcols.p; P.opd = pl->d_opd.p; P.idd = pl->d_idd.p;
-                P.own_val = pl->d_ownval.p; P.own_lq = pl->d_ownlq.p; P.w = pl->d_w.p; P.s = s_dev; P.Dz0 = Dz0_dev;
-                P.c = c_dev; P.t = t; P.p = pl->bar.p; P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p;
-                P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss; P.off_ut = ep.lay.off_ut;
-                P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
                 CUDA_OK(cudaEventRecord(pl->ev[0], st));
-                launch_elem(pl, P, flags & 7);
+                assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, nullptr, pl->ev[2]);
                 CUDA_OK(cudaEventRecord(pl->ev[1], st));
                 CUDA_OK(cudaEventSynchronize(pl->ev[1]));
-                float ms = 0.f;
-                CUDA_OK(cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[1]));
+                float ms = 0.f, ms2 = 0.f;
+                CUDA_OK(cudaEventElapsedTime(&ms, pl->ev[0], pl->ev[2]));
+                CUDA_OK(cudaEventElapsedTime(&ms2, pl->ev[2], pl->ev[1]));
                 tel += ms;
+                tga += ms2;
             }
-            tga = tot - tel;
         }
         if (ms_total) *ms_total = (float)(tot / reps);
         if (ms_kernel_element) *ms_kernel_element = (float)(tel / reps);

@@ -119,6 +119,8 @@ void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_) {
 }
 
 int SlotLayout::tri(int q, int q2) const { return q * B - q * (q - 1) / 2 + (q2 - q); }
+int SlotLayout::ntri_pad() const { return round_up(B * (B + 1) / 2, LPE); }
+int SlotLayout::nfull_pad() const { return round_up(B * B, LPE); }
 
 namespace {
 struct UF {
@@ -288,14 +290,14 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     auto slot_of = [&](int a1, int a2, const std::vector<int>& own /*[nu][B] local col per point*/) -> int {
         int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
         if (v1 > v2 || (v1 == v2 && q1 > q2)) { std::swap(v1, v2); std::swap(q1, q2); }
-        const int full_stride = lay.fine ? lay.LPE : lay.B;
-        if (v1 == 0 && v2 == 0) return lay.off_uu + lay.tri(q1, q2);
-        if (v1 == 0 && v2 == 1) return lay.off_us + q1 * full_stride + q2;
-        if (v1 == 0 && v2 == 2) return lay.off_ut + q1 * full_stride + q2;
-        if (v1 == 1 && v2 == 1) return lay.fine ? (q1 == q2 ? lay.off_ss + q1 : -1) : lay.off_ss + lay.tri(q1, q2);
-        if (v1 == 2 && v2 == 2) return lay.fine ? (q1 == q2 ? lay.off_tt + q1 : -1) : lay.off_tt + lay.tri(q1, q2);
+        const int NT = lay.ntri_pad(), NF = lay.nfull_pad();
+        if (v1 == 0 && v2 == 0) return lay.packed(lay.off_uu, lay.tri(q1, q2), NT);
+        if (v1 == 0 && v2 == 1) return lay.fine ? lay.off_us + q1 * lay.LPE + q2 : lay.packed(lay.off_us, q1 * lay.B + q2, NF);
+        if (v1 == 0 && v2 == 2) return lay.fine ? lay.off_ut + q1 * lay.LPE + q2 : lay.packed(lay.off_ut, q1 * lay.B + q2, NF);
+        if (v1 == 1 && v2 == 1) return lay.fine ? (q1 == q2 ? lay.off_ss + q1 : -1) : lay.packed(lay.off_ss, lay.tri(q1, q2), NT);
+        if (v1 == 2 && v2 == 2) return lay.fine ? (q1 == q2 ? lay.off_tt + q1 : -1) : lay.packed(lay.off_tt, lay.tri(q1, q2), NT);
         if (v1 == 1 && v2 == 2) {
-            if (!lay.fine) return lay.off_st + q1 * lay.B + q2;
+            if (!lay.fine) return lay.packed(lay.off_st, q1 * lay.B + q2, NF);
             for (int l = 0; l < (int)B; ++l)
                 if (own[1 * B + l] == q1 && own[2 * B + l] == q2) return lay.off_st + l;
             return -1;
@@ -404,6 +406,111 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                 if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
             }
     P.ok = true;
+}
+
+void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
+    PatchPlan& PP = EP.patch;
+    const int NS = EP.lay.NS, LPE = EP.LPE, NU = EP.NU;
+    PP.P = elems_per_patch;
+    PP.npatch = (EP.E + PP.P - 1) / PP.P;
+    int nsp = NS;
+    while (nsp % 16 != LPE % 16) ++nsp;  // consecutive elements land on disjoint shared-memory banks
+    PP.NSP = nsp;
+    PP.RSP = NU * LPE;
+    if ((int64_t)PP.P * PP.NSP > 65534 || (int64_t)PP.P * PP.RSP > 65534) throw std::runtime_error("patch too large for 16-bit local slots");
+    const int64_t nnzH = (int64_t)EP.h_colidx.size(), m = EP.m, np = PP.npatch;
+    auto patch_of = [&](int32_t gslot) { return (int64_t)(gslot / NS) / PP.P; };
+    auto local_of = [&](int32_t gslot) { const int64_t e = gslot / NS; return (uint16_t)((e % PP.P) * PP.NSP + gslot % NS); };
+    // pass 1: count per patch, assign export ranges
+    std::vector<int32_t> w2c(np + 1, 0), lgc(np + 1, 0);
+    PP.if_ptr.assign(1, 0);
+    struct Grp { int64_t t; int64_t c0, c1; int64_t patch; int32_t dest; };
+    std::vector<Grp> groups;
+    groups.reserve((size_t)(nnzH + nnzH / 4));
+    int64_t nexp = 0;
+    for (int64_t t = 0; t < nnzH; ++t) {
+        const int64_t c0 = EP.h_cptr[t], c1 = EP.h_cptr[t + 1];
+        int64_t g0 = c0;
+        const bool single = patch_of(EP.h_cidx[c0]) == patch_of(EP.h_cidx[c1 - 1]);  // lists are sorted by element
+        while (g0 < c1) {
+            const int64_t pa = patch_of(EP.h_cidx[g0]);
+            int64_t g1 = g0;
+            while (g1 < c1 && patch_of(EP.h_cidx[g1]) == pa) ++g1;
+            const int32_t dest = single ? (int32_t)t : (int32_t)(-1 - nexp++);
+            groups.push_back({t, g0, g1, pa, dest});
+            if (g1 - g0 <= 2) w2c[pa + 1]++; else lgc[pa + 1]++;
+            g0 = g1;
+        }
+        if (!single) { PP.if_t.push_back((int32_t)t); PP.if_ptr.push_back((int32_t)nexp); }
+    }
+    if (nexp > INT32_MAX) throw std::runtime_error("export buffer exceeds int32 indexing");
+    PP.n_hexp = nexp;
+    for (int64_t q = 0; q < np; ++q) { w2c[q + 1] += w2c[q]; lgc[q + 1] += lgc[q]; }
+    PP.w2_pp = w2c; PP.lg_pp = lgc;
+    PP.w2_dest.resize(w2c[np]); PP.w2_src.resize(w2c[np]);
+    PP.lg_dest.resize(lgc[np]);
+    std::vector<int32_t> lg_cnt(lgc[np], 0);
+    std::vector<int32_t> w2pos(w2c.begin(), w2c.end() - 1), lgpos(lgc.begin(), lgc.end() - 1);
+    std::vector<int64_t> lg_src0(lgc[np], 0);
+    for (const Grp& g : groups) {
+        const int64_t cnt = g.c1 - g.c0;
+        if (cnt <= 2) {
+            const int32_t k = w2pos[g.patch]++;
+            PP.w2_dest[k] = g.dest;
+            const uint32_t s0 = local_of(EP.h_cidx[g.c0]);
+            const uint32_t s1 = cnt == 2 ? local_of(EP.h_cidx[g.c0 + 1]) : 0xFFFFu;
+            PP.w2_src[k] = s0 | (s1 << 16);
+        } else {
+            const int32_t k = lgpos[g.patch]++;
+            PP.lg_dest[k] = g.dest;
+            lg_cnt[k] = (int32_t)cnt;
+            lg_src0[k] = g.c0;
+        }
+    }
+    PP.lg_ptr.assign(lgc[np] + 1, 0);
+    for (int64_t k = 0; k < lgc[np]; ++k) PP.lg_ptr[k + 1] = PP.lg_ptr[k] + lg_cnt[k];
+    PP.lg_idx.resize(PP.lg_ptr[lgc[np]]);
+    for (int64_t k = 0; k < lgc[np]; ++k)
+        for (int32_t r = 0; r < lg_cnt[k]; ++r) PP.lg_idx[PP.lg_ptr[k] + r] = local_of(EP.h_cidx[lg_src0[k] + r]);
+    // ---- gradient
+    const int RS = PP.RSP;
+    auto gpatch_of = [&](int32_t gi) { return (int64_t)(gi / RS) / PP.P; };
+    auto glocal_of = [&](int32_t gi) { const int64_t e = gi / RS; return (uint16_t)((e % PP.P) * RS + gi % RS); };
+    std::vector<int32_t> gc(np + 1, 0);
+    struct GG { int64_t c0, c1, patch; int32_t dest; };
+    std::vector<GG> gg;
+    PP.gif_ptr.assign(1, 0);
+    int64_t ngexp = 0;
+    for (int64_t a = 0; a < m; ++a) {
+        const int64_t c0 = EP.g_cptr[a], c1 = EP.g_cptr[a + 1];
+        if (c1 == c0) continue;
+        const bool single = gpatch_of(EP.g_cidx[c0]) == gpatch_of(EP.g_cidx[c1 - 1]);
+        int64_t g0 = c0;
+        while (g0 < c1) {
+            const int64_t pa = gpatch_of(EP.g_cidx[g0]);
+            int64_t g1 = g0;
+            while (g1 < c1 && gpatch_of(EP.g_cidx[g1]) == pa) ++g1;
+            gg.push_back({g0, g1, pa, single ? (int32_t)a : (int32_t)(-1 - ngexp++)});
+            gc[pa + 1]++;
+            g0 = g1;
+        }
+        if (!single) { PP.gif_a.push_back((int32_t)a); PP.gif_ptr.push_back((int32_t)ngexp); }
+    }
+    PP.n_gexp = ngexp;
+    for (int64_t q = 0; q < np; ++q) gc[q + 1] += gc[q];
+    PP.g_pp = gc;
+    PP.g_dest.resize(gc[np]);
+    std::vector<int32_t> gcnt(gc[np], 0), gpos(gc.begin(), gc.end() - 1);
+    std::vector<int64_t> gsrc0(gc[np], 0);
+    for (const GG& g : gg) {
+        const int32_t k = gpos[g.patch]++;
+        PP.g_dest[k] = g.dest; gcnt[k] = (int32_t)(g.c1 - g.c0); gsrc0[k] = g.c0;
+    }
+    PP.g_ptr.assign(gc[np] + 1, 0);
+    for (int64_t k = 0; k < gc[np]; ++k) PP.g_ptr[k + 1] = PP.g_ptr[k] + gcnt[k];
+    PP.g_idx.resize(PP.g_ptr[gc[np]]);
+    for (int64_t k = 0; k < gc[np]; ++k)
+        for (int32_t r = 0; r < gcnt[k]; ++r) PP.g_idx[PP.g_ptr[k] + r] = glocal_of(EP.g_cidx[gsrc0[k] + r]);
 }
 
 void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P, bool want_hessian) {

@@ -33,6 +33,39 @@ struct SlotLayout {
     int NS = 0;  // doubles per element
     void build(int B_, int dim_, bool slack_, bool fine_);
     int tri(int q, int q2) const;  // packed upper-triangle index, q <= q2 < B
+    // slot of packed entry pk of a block of padded size npad that went through the transposing
+    // butterfly: lane l ends with entries [l*K,(l+1)*K) and stores entry r at  off + r*LPE + l
+    int packed(int off, int pk, int npad) const { const int K = npad / LPE; return off + (pk % K) * LPE + pk / K; }
+    int ntri_pad() const;
+    int nfull_pad() const;
+};
+
+// Patch-fused replay lists: a CTA owns P consecutive elements, keeps their slot records in shared
+// memory and finishes every output entry whose contributions all come from the patch; the others get
+// one partial sum per patch in an export buffer that a small interface kernel folds.
+struct PatchPlan {
+    int P = 0, NSP = 0, RSP = 0;  // elements per patch, smem strides (doubles) of the slot / gradient records
+    int64_t npatch = 0;
+    // Hessian, per patch
+    std::vector<int32_t> w2_pp;    // npatch+1
+    std::vector<int32_t> w2_dest;  // >=0: index into hval; <0: -1-index into the export buffer
+    std::vector<uint32_t> w2_src;  // lo16 first local slot, hi16 second (0xFFFF none)
+    std::vector<int32_t> lg_pp;    // npatch+1 (entries with > 2 in-patch contributions)
+    std::vector<int32_t> lg_dest;
+    std::vector<int32_t> lg_ptr;   // nlong+1 into lg_idx
+    std::vector<uint16_t> lg_idx;
+    // Hessian interface
+    std::vector<int32_t> if_t;     // hval index
+    std::vector<int32_t> if_ptr;   // n_if+1 into the export buffer (contiguous partials per entry)
+    int64_t n_hexp = 0;
+    // gradient, per patch
+    std::vector<int32_t> g_pp;     // npatch+1
+    std::vector<int32_t> g_dest;
+    std::vector<int32_t> g_ptr;    // +1 into g_idx
+    std::vector<uint16_t> g_idx;
+    std::vector<int32_t> gif_a;
+    std::vector<int32_t> gif_ptr;
+    int64_t n_gexp = 0;
 };
 
 struct ElementPlan {
@@ -53,7 +86,11 @@ struct ElementPlan {
     std::vector<int32_t> h_cidx;              // contribution -> e*NS + slot
     std::vector<int64_t> g_cptr;              // m+1
     std::vector<int32_t> g_cidx;              // contribution -> (e*NU+v)*LPE + q
+    PatchPlan patch;
 };
+
+// Derives the patch-fused lists from the element plan's global contribution lists.
+void build_patch_plan(ElementPlan& P, int elems_per_patch);
 
 struct BarrierDesc {
     int kind = 1, nidx = 0, idx[8] = {0};

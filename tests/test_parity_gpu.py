@@ -39,6 +39,31 @@ def test_feasibility_slack_variant(gpu_ctx, gen, L):
     check_against_oracle(gpu_ctx, getattr(mgb_b200, gen)(L), 2.0, t=0.5, slack=True, level=0)
 
 
+@pytest.mark.parametrize("gen,L,level,slack", [("fem1d", 4, None, False), ("fem2d", 4, None, False), ("fem2d", 4, 1, False),
+                                                  ("fem2d", 3, None, True), ("fem2d", 3, 0, True)])
+def test_two_stage_element_path(gpu_ctx, gen, L, level, slack):
+    """the element_kernel + gather_kernel pair kept for A/B comparison against the patch-fused kernel"""
+    plan, _ = check_against_oracle(gpu_ctx, getattr(mgb_b200, gen)(L), 1.0, t=0.9, level=level, slack=slack,
+                                   force_path=capi.PLAN_TWO_STAGE)
+    assert plan.info["path"] == capi.PATH_ELEMENT
+
+
+@pytest.mark.parametrize("patch", ["16", "64"])
+def test_patch_sizes(gpu_ctx, patch, monkeypatch):
+    monkeypatch.setenv("MGB_PATCH", patch)
+    check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.0, t=0.9)
+    check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.5, t=0.9, level=1)
+
+
+def test_bitwise_reproducible(gpu_ctx):
+    """fixed summation order: two runs give identical bits"""
+    from helpers import problem, cuda_eval
+    pr = problem(mgb_b200.fem2d(5))
+    _, o1, H1 = cuda_eval(gpu_ctx, pr, 0.7)
+    _, o2, H2 = cuda_eval(gpu_ctx, pr, 0.7)
+    assert np.array_equal(H1.data, H2.data) and np.array_equal(o1["grad"], o2["grad"]) and o1["scal"][0] == o2["scal"][0]
+
+
 @pytest.mark.parametrize("gen,L,level", [("fem1d", 4, None), ("fem2d", 3, None), ("fem2d", 3, 1), ("fem3d", 2, None)])
 def test_csr_path(gpu_ctx, gen, L, level):
     geom = mgb_b200.fem3d(L, k=1) if gen == "fem3d" else getattr(mgb_b200, gen)(L)
