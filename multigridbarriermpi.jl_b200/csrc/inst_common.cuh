@@ -37,7 +37,7 @@ void launch_elem_bd(const ElemParams& P, bool slack, bool fine, int flags, int64
 template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
 void launch_patch_one(const ElemParams& P, const PatchParams& Q, int64_t nblk, size_t smem, cudaStream_t st) {
     auto kern = patch_kernel<B, D, SLACK, FINE, FLAGS, PATCH>;
-    if (smem > 48 * 1024) inst_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
+    if (smem > 40 * 1024) inst_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
     kern<<<dim3((unsigned)nblk), dim3(PATCH * Pow2Ceil<B>::value), smem, st>>>(P, Q);
 }
 

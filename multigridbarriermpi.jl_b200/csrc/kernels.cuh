@@ -410,53 +410,78 @@ __global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const 
 // in shared memory; phase B replays the patch's frozen lists: entries fed by this patch alone go
 // straight into the CSR value array / gradient, the others leave one partial sum per patch in the
 // export buffers that interface_kernel folds.  No atomics; fixed summation order.
-struct PatchParams {
-    int NSP, RSP;                 // shared-memory strides (doubles) of the slot / gradient records
-    const int32_t* w2_pp;  const int32_t* w2_dest;  const uint32_t* w2_src;
+struct ReplayDev {
+    const int32_t* pp;  const int2* rec;
     const int32_t* lg_pp;  const int32_t* lg_dest;  const int32_t* lg_ptr;  const uint16_t* lg_idx;
-    const int32_t* g_pp;   const int32_t* g_dest;   const int32_t* g_ptr;   const uint16_t* g_idx;
-    double* hval;  double* hexp;  double* grad;  double* gexp;
+    double* out;  double* exp;
+    int max_rec;
 };
+
+struct PatchParams {
+    int NSP, RSP;  // shared-memory strides (doubles) of the slot / gradient records
+    ReplayDev H, G;
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// replay of one output family from the patch's shared-memory image `img`
+__device__ __forceinline__ void replay(const ReplayDev& R, const int2* __restrict__ rec_s, const double* __restrict__ img,
+                                       const int p) {
+    const int n = R.pp[p + 1] - R.pp[p];
+#pragma unroll 4
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int2 rc = rec_s[k];
+        const uint32_t src = (uint32_t)rc.y;
+        double v = img[src & 0xFFFFu];
+        const uint32_t s1 = src >> 16;
+        if (s1 != 0xFFFFu) v += img[s1];
+        if (rc.x >= 0) R.out[rc.x] = v; else R.exp[-1 - rc.x] = v;
+    }
+    for (int k = R.lg_pp[p] + threadIdx.x; k < R.lg_pp[p + 1]; k += blockDim.x) {
+        const int32_t dest = __ldg(&R.lg_dest[k]);
+        const int r0 = __ldg(&R.lg_ptr[k]), r1 = __ldg(&R.lg_ptr[k + 1]);
+        double v = 0.0;
+        for (int r = r0; r < r1; ++r) v += img[__ldg(&R.lg_idx[r])];
+        if (dest >= 0) R.out[dest] = v; else R.exp[-1 - dest] = v;
+    }
+}
 
 template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
 __global__ void __launch_bounds__(PATCH * Pow2Ceil<B>::value) patch_kernel(const ElemParams P, const PatchParams Q) {
     constexpr int LPE = Pow2Ceil<B>::value;
     constexpr bool WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0;
     extern __shared__ double smem[];
-    double* sel_s = smem;                          // PATCH * NSP
-    double* rel_s = smem + (size_t)PATCH * Q.NSP;  // PATCH * RSP
+    double* img = smem;                                               // PATCH*NSP slot records, then PATCH*RSP gradient records
+    int2* rec_h = reinterpret_cast<int2*>(smem + (size_t)PATCH * (Q.NSP + Q.RSP));
+    int2* rec_g = rec_h + Q.H.max_rec;
+    const int p = blockIdx.x;
+    // stage this patch's replay records with cp.async: their latency hides behind phase A
+    if (WH) {
+        const int n = Q.H.pp[p + 1] - Q.H.pp[p];
+        const int2* src = Q.H.rec + Q.H.pp[p];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_h[k], &src[k]);
+    }
+    if (WG) {
+        const int n = Q.G.pp[p + 1] - Q.G.pp[p];
+        const int2* src = Q.G.rec + Q.G.pp[p];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_g[k], &src[k]);
+    }
     const int el = threadIdx.x / LPE;
     const int l = threadIdx.x % LPE;
     const int64_t e = (int64_t)blockIdx.x * PATCH + el;
     double v0, v1, v2;
-    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, sel_s + (size_t)el * Q.NSP, rel_s + (size_t)el * Q.RSP, v0, v1, v2);
-    block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes the records
-    if (!(WG || WH)) return;
-    const int p = blockIdx.x;
-    if (WH) {
-        for (int k = Q.w2_pp[p] + threadIdx.x; k < Q.w2_pp[p + 1]; k += blockDim.x) {
-            const int32_t dest = __ldg(&Q.w2_dest[k]);
-            const uint32_t src = __ldg(&Q.w2_src[k]);
-            double v = sel_s[src & 0xFFFFu];
-            const uint32_t s1 = src >> 16;
-            if (s1 != 0xFFFFu) v += sel_s[s1];
-            if (dest >= 0) Q.hval[dest] = v; else Q.hexp[-1 - dest] = v;
-        }
-        for (int k = Q.lg_pp[p] + threadIdx.x; k < Q.lg_pp[p + 1]; k += blockDim.x) {
-            const int32_t dest = __ldg(&Q.lg_dest[k]);
-            double v = 0.0;
-            for (int r = __ldg(&Q.lg_ptr[k]); r < __ldg(&Q.lg_ptr[k + 1]); ++r) v += sel_s[__ldg(&Q.lg_idx[r])];
-            if (dest >= 0) Q.hval[dest] = v; else Q.hexp[-1 - dest] = v;
-        }
-    }
-    if (WG) {
-        for (int k = Q.g_pp[p] + threadIdx.x; k < Q.g_pp[p + 1]; k += blockDim.x) {
-            const int32_t dest = __ldg(&Q.g_dest[k]);
-            double v = 0.0;
-            for (int r = __ldg(&Q.g_ptr[k]); r < __ldg(&Q.g_ptr[k + 1]); ++r) v += rel_s[__ldg(&Q.g_idx[r])];
-            if (dest >= 0) Q.grad[dest] = v; else Q.gexp[-1 - dest] = v;
-        }
-    }
+    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, img + (size_t)el * Q.NSP,
+                                           img + (size_t)PATCH * Q.NSP + (size_t)el * Q.RSP, v0, v1, v2);
+    if (WG || WH) cp_async_commit_wait_all();
+    block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes records and staged lists
+    if (WH) replay(Q.H, rec_h, img, p);
+    if (WG) replay(Q.G, rec_g, img, p);
 }
 
 struct InterfaceParams {

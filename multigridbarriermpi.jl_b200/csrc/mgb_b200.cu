@@ -91,10 +91,25 @@ struct mgb_plan {
     int NSP = 0, RSP = 0;
     int64_t n_if = 0, n_gif = 0, n_hexp = 0, n_gexp = 0;
     bool if_warp = false;
-    DevBuf<int32_t> p_w2pp, p_w2dest, p_lgpp, p_lgdest, p_lgptr, p_gpp, p_gdest, p_gptr, p_ift, p_ifptr, p_gifa, p_gifptr;
-    DevBuf<uint32_t> p_w2src;
-    DevBuf<uint16_t> p_lgidx, p_gidx;
-    DevBuf<double> d_hexp, d_gexp;
+    struct ReplayBufs {
+        DevBuf<int32_t> pp, rec, lg_pp, lg_dest, lg_ptr, if_dst, if_ptr;
+        DevBuf<uint16_t> lg_idx;
+        DevBuf<double> exp;
+        int max_rec = 0;
+        void upload(const mgb::ReplayLists& L, cudaStream_t st) {
+            pp.upload(L.pp, st); rec.upload(L.rec, st); lg_pp.upload(L.lg_pp, st); lg_dest.upload(L.lg_dest, st);
+            lg_ptr.upload(L.lg_ptr, st); lg_idx.upload(L.lg_idx, st); if_dst.upload(L.if_dst, st); if_ptr.upload(L.if_ptr, st);
+            exp.alloc((size_t)std::max<int64_t>(L.n_exp, 1));
+            max_rec = L.max_rec;
+        }
+        size_t bytes() const { return pp.bytes() + rec.bytes() + lg_pp.bytes() + lg_dest.bytes() + lg_ptr.bytes() + lg_idx.bytes() + if_dst.bytes() + if_ptr.bytes() + exp.bytes(); }
+        mgb::ReplayDev dev(double* out) const {
+            mgb::ReplayDev r{};
+            r.pp = pp.p; r.rec = reinterpret_cast<const int2*>(rec.p); r.lg_pp = lg_pp.p; r.lg_dest = lg_dest.p;
+            r.lg_ptr = lg_ptr.p; r.lg_idx = lg_idx.p; r.out = out; r.exp = exp.p; r.max_rec = max_rec;
+            return r;
+        }
+    } rp_h, rp_g;
     bool has_hessian = true;
     bool long_lists = false;
     // ---- csr path
@@ -197,18 +212,17 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         if ((f & 2) && !grad) grad = pl->d_rel.p;  // scratch target when the caller did not ask for it
         mgb::PatchParams Q{};
         Q.NSP = pl->NSP; Q.RSP = pl->RSP;
-        Q.w2_pp = pl->p_w2pp.p; Q.w2_dest = pl->p_w2dest.p; Q.w2_src = pl->p_w2src.p;
-        Q.lg_pp = pl->p_lgpp.p; Q.lg_dest = pl->p_lgdest.p; Q.lg_ptr = pl->p_lgptr.p; Q.lg_idx = pl->p_lgidx.p;
-        Q.g_pp = pl->p_gpp.p; Q.g_dest = pl->p_gdest.p; Q.g_ptr = pl->p_gptr.p; Q.g_idx = pl->p_gidx.p;
-        Q.hval = hval; Q.hexp = pl->d_hexp.p; Q.grad = grad; Q.gexp = pl->d_gexp.p;
-        const size_t smem = ((size_t)pl->patch * (pl->NSP + pl->RSP)) * sizeof(double);
+        Q.H = pl->rp_h.dev(hval);
+        Q.G = pl->rp_g.dev(grad);
+        const size_t smem = ((size_t)pl->patch * (pl->NSP + pl->RSP)) * sizeof(double) +
+                            ((size_t)pl->rp_h.max_rec + pl->rp_g.max_rec) * sizeof(int2);
         mgb::launch_patch(ep.B, ep.dim, ep.slack, ep.fine, pl->patch, P, Q, f, pl->nblocks_elem, smem, st);
         g_launches++;
         if (mid) CUDA_OK(cudaEventRecord(mid, st));
         mgb::InterfaceParams I{};
         I.n_if = (f & 4) ? pl->n_if : 0; I.n_gif = (f & 2) ? pl->n_gif : 0; I.nparts = pl->nblocks_elem;
-        I.if_t = pl->p_ift.p; I.if_ptr = pl->p_ifptr.p; I.hexp = pl->d_hexp.p; I.hval = hval;
-        I.gif_a = pl->p_gifa.p; I.gif_ptr = pl->p_gifptr.p; I.gexp = pl->d_gexp.p; I.grad = grad;
+        I.if_t = pl->rp_h.if_dst.p; I.if_ptr = pl->rp_h.if_ptr.p; I.hexp = pl->rp_h.exp.p; I.hval = hval;
+        I.gif_a = pl->rp_g.if_dst.p; I.gif_ptr = pl->rp_g.if_ptr.p; I.gexp = pl->rp_g.exp.p; I.grad = grad;
         I.part = pl->d_part.p; I.scal = scal ? scal : pl->d_scal_tmp.p; I.t = t;
         I.warp_per_entry = pl->if_warp ? 1 : 0;
         const int64_t per = pl->if_warp ? 8 : 256;
@@ -393,17 +407,10 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                 mgb::build_patch_plan(ep, want_patch);
                 const auto& pp = ep.patch;
                 pl->patch = pp.P; pl->NSP = pp.NSP; pl->RSP = pp.RSP;
-                pl->n_if = (int64_t)pp.if_t.size(); pl->n_gif = (int64_t)pp.gif_a.size();
-                pl->n_hexp = pp.n_hexp; pl->n_gexp = pp.n_gexp;
-                pl->if_warp = pl->n_if > 0 && (double)pp.n_hexp / (double)pl->n_if > 16.0;
-                pl->p_w2pp.upload(pp.w2_pp, st); pl->p_w2dest.upload(pp.w2_dest, st); pl->p_w2src.upload(pp.w2_src, st);
-                pl->p_lgpp.upload(pp.lg_pp, st); pl->p_lgdest.upload(pp.lg_dest, st); pl->p_lgptr.upload(pp.lg_ptr, st);
-                pl->p_lgidx.upload(pp.lg_idx, st);
-                pl->p_gpp.upload(pp.g_pp, st); pl->p_gdest.upload(pp.g_dest, st); pl->p_gptr.upload(pp.g_ptr, st);
-                pl->p_gidx.upload(pp.g_idx, st);
-                pl->p_ift.upload(pp.if_t, st); pl->p_ifptr.upload(pp.if_ptr, st);
-                pl->p_gifa.upload(pp.gif_a, st); pl->p_gifptr.upload(pp.gif_ptr, st);
-                pl->d_hexp.alloc((size_t)std::max<int64_t>(pp.n_hexp, 1)); pl->d_gexp.alloc((size_t)std::max<int64_t>(pp.n_gexp, 1));
+                pl->n_if = (int64_t)pp.H.if_dst.size(); pl->n_gif = (int64_t)pp.G.if_dst.size();
+                pl->n_hexp = pp.H.n_exp; pl->n_gexp = pp.G.n_exp;
+                pl->if_warp = pl->n_if > 0 && (double)pp.H.n_exp / (double)pl->n_if > 16.0;
+                pl->rp_h.upload(pp.H, st); pl->rp_g.upload(pp.G, st);
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             if (pl->patch == 0) pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);

@@ -408,6 +408,67 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     P.ok = true;
 }
 
+namespace {
+// cptr/cidx: per output entry the (element-sorted) global contribution slots; patch_of/local_of map a
+// global slot to its patch and to its 16-bit index inside the patch's shared-memory image.
+template <class PatchOf, class LocalOf>
+void build_replay(int64_t nout, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx, int64_t np,
+                  PatchOf patch_of, LocalOf local_of, ReplayLists& L) {
+    struct Grp { int64_t c0, c1, patch; int32_t dest; };
+    std::vector<Grp> groups;
+    groups.reserve((size_t)(nout + nout / 4));
+    std::vector<int32_t> rc(np + 1, 0), lc(np + 1, 0);
+    L.if_ptr.assign(1, 0);
+    int64_t nexp = 0;
+    for (int64_t t = 0; t < nout; ++t) {
+        const int64_t c0 = cptr[t], c1 = cptr[t + 1];
+        if (c1 == c0) continue;
+        const bool single = patch_of(cidx[c0]) == patch_of(cidx[c1 - 1]);  // lists are sorted by element
+        int64_t g0 = c0;
+        while (g0 < c1) {
+            const int64_t pa = patch_of(cidx[g0]);
+            int64_t g1 = g0;
+            while (g1 < c1 && patch_of(cidx[g1]) == pa) ++g1;
+            groups.push_back({g0, g1, pa, single ? (int32_t)t : (int32_t)(-1 - nexp++)});
+            if (g1 - g0 <= 2) rc[pa + 1]++; else lc[pa + 1]++;
+            g0 = g1;
+        }
+        if (!single) { L.if_dst.push_back((int32_t)t); L.if_ptr.push_back((int32_t)nexp); }
+    }
+    if (nexp > INT32_MAX) throw std::runtime_error("export buffer exceeds int32 indexing");
+    L.n_exp = nexp;
+    L.max_rec = 0;
+    for (int64_t q = 0; q < np; ++q) {
+        L.max_rec = std::max(L.max_rec, rc[q + 1]);
+        rc[q + 1] += rc[q];
+        lc[q + 1] += lc[q];
+    }
+    L.pp = rc; L.lg_pp = lc;
+    L.rec.resize((size_t)2 * rc[np]);
+    L.lg_dest.resize(lc[np]);
+    std::vector<int32_t> lcnt(lc[np], 0), rpos(rc.begin(), rc.end() - 1), lpos(lc.begin(), lc.end() - 1);
+    std::vector<int64_t> lsrc0(lc[np], 0);
+    for (const Grp& g : groups) {
+        const int64_t cnt = g.c1 - g.c0;
+        if (cnt <= 2) {
+            const int32_t k = rpos[g.patch]++;
+            const uint32_t s0 = local_of(cidx[g.c0]);
+            const uint32_t s1 = cnt == 2 ? local_of(cidx[g.c0 + 1]) : 0xFFFFu;
+            L.rec[2 * (size_t)k] = g.dest;
+            L.rec[2 * (size_t)k + 1] = (int32_t)(s0 | (s1 << 16));
+        } else {
+            const int32_t k = lpos[g.patch]++;
+            L.lg_dest[k] = g.dest; lcnt[k] = (int32_t)cnt; lsrc0[k] = g.c0;
+        }
+    }
+    L.lg_ptr.assign(lc[np] + 1, 0);
+    for (int64_t k = 0; k < lc[np]; ++k) L.lg_ptr[k + 1] = L.lg_ptr[k] + lcnt[k];
+    L.lg_idx.resize(L.lg_ptr[lc[np]]);
+    for (int64_t k = 0; k < lc[np]; ++k)
+        for (int32_t r = 0; r < lcnt[k]; ++r) L.lg_idx[L.lg_ptr[k] + r] = local_of(cidx[lsrc0[k] + r]);
+}
+}  // namespace
+
 void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
     PatchPlan& PP = EP.patch;
     const int NS = EP.lay.NS, LPE = EP.LPE, NU = EP.NU;
@@ -417,100 +478,15 @@ void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
     while (nsp % 16 != LPE % 16) ++nsp;  // consecutive elements land on disjoint shared-memory banks
     PP.NSP = nsp;
     PP.RSP = NU * LPE;
-    if ((int64_t)PP.P * PP.NSP > 65534 || (int64_t)PP.P * PP.RSP > 65534) throw std::runtime_error("patch too large for 16-bit local slots");
-    const int64_t nnzH = (int64_t)EP.h_colidx.size(), m = EP.m, np = PP.npatch;
-    auto patch_of = [&](int32_t gslot) { return (int64_t)(gslot / NS) / PP.P; };
-    auto local_of = [&](int32_t gslot) { const int64_t e = gslot / NS; return (uint16_t)((e % PP.P) * PP.NSP + gslot % NS); };
-    // pass 1: count per patch, assign export ranges
-    std::vector<int32_t> w2c(np + 1, 0), lgc(np + 1, 0);
-    PP.if_ptr.assign(1, 0);
-    struct Grp { int64_t t; int64_t c0, c1; int64_t patch; int32_t dest; };
-    std::vector<Grp> groups;
-    groups.reserve((size_t)(nnzH + nnzH / 4));
-    int64_t nexp = 0;
-    for (int64_t t = 0; t < nnzH; ++t) {
-        const int64_t c0 = EP.h_cptr[t], c1 = EP.h_cptr[t + 1];
-        int64_t g0 = c0;
-        const bool single = patch_of(EP.h_cidx[c0]) == patch_of(EP.h_cidx[c1 - 1]);  // lists are sorted by element
-        while (g0 < c1) {
-            const int64_t pa = patch_of(EP.h_cidx[g0]);
-            int64_t g1 = g0;
-            while (g1 < c1 && patch_of(EP.h_cidx[g1]) == pa) ++g1;
-            const int32_t dest = single ? (int32_t)t : (int32_t)(-1 - nexp++);
-            groups.push_back({t, g0, g1, pa, dest});
-            if (g1 - g0 <= 2) w2c[pa + 1]++; else lgc[pa + 1]++;
-            g0 = g1;
-        }
-        if (!single) { PP.if_t.push_back((int32_t)t); PP.if_ptr.push_back((int32_t)nexp); }
-    }
-    if (nexp > INT32_MAX) throw std::runtime_error("export buffer exceeds int32 indexing");
-    PP.n_hexp = nexp;
-    for (int64_t q = 0; q < np; ++q) { w2c[q + 1] += w2c[q]; lgc[q + 1] += lgc[q]; }
-    PP.w2_pp = w2c; PP.lg_pp = lgc;
-    PP.w2_dest.resize(w2c[np]); PP.w2_src.resize(w2c[np]);
-    PP.lg_dest.resize(lgc[np]);
-    std::vector<int32_t> lg_cnt(lgc[np], 0);
-    std::vector<int32_t> w2pos(w2c.begin(), w2c.end() - 1), lgpos(lgc.begin(), lgc.end() - 1);
-    std::vector<int64_t> lg_src0(lgc[np], 0);
-    for (const Grp& g : groups) {
-        const int64_t cnt = g.c1 - g.c0;
-        if (cnt <= 2) {
-            const int32_t k = w2pos[g.patch]++;
-            PP.w2_dest[k] = g.dest;
-            const uint32_t s0 = local_of(EP.h_cidx[g.c0]);
-            const uint32_t s1 = cnt == 2 ? local_of(EP.h_cidx[g.c0 + 1]) : 0xFFFFu;
-            PP.w2_src[k] = s0 | (s1 << 16);
-        } else {
-            const int32_t k = lgpos[g.patch]++;
-            PP.lg_dest[k] = g.dest;
-            lg_cnt[k] = (int32_t)cnt;
-            lg_src0[k] = g.c0;
-        }
-    }
-    PP.lg_ptr.assign(lgc[np] + 1, 0);
-    for (int64_t k = 0; k < lgc[np]; ++k) PP.lg_ptr[k + 1] = PP.lg_ptr[k] + lg_cnt[k];
-    PP.lg_idx.resize(PP.lg_ptr[lgc[np]]);
-    for (int64_t k = 0; k < lgc[np]; ++k)
-        for (int32_t r = 0; r < lg_cnt[k]; ++r) PP.lg_idx[PP.lg_ptr[k] + r] = local_of(EP.h_cidx[lg_src0[k] + r]);
-    // ---- gradient
-    const int RS = PP.RSP;
-    auto gpatch_of = [&](int32_t gi) { return (int64_t)(gi / RS) / PP.P; };
-    auto glocal_of = [&](int32_t gi) { const int64_t e = gi / RS; return (uint16_t)((e % PP.P) * RS + gi % RS); };
-    std::vector<int32_t> gc(np + 1, 0);
-    struct GG { int64_t c0, c1, patch; int32_t dest; };
-    std::vector<GG> gg;
-    PP.gif_ptr.assign(1, 0);
-    int64_t ngexp = 0;
-    for (int64_t a = 0; a < m; ++a) {
-        const int64_t c0 = EP.g_cptr[a], c1 = EP.g_cptr[a + 1];
-        if (c1 == c0) continue;
-        const bool single = gpatch_of(EP.g_cidx[c0]) == gpatch_of(EP.g_cidx[c1 - 1]);
-        int64_t g0 = c0;
-        while (g0 < c1) {
-            const int64_t pa = gpatch_of(EP.g_cidx[g0]);
-            int64_t g1 = g0;
-            while (g1 < c1 && gpatch_of(EP.g_cidx[g1]) == pa) ++g1;
-            gg.push_back({g0, g1, pa, single ? (int32_t)a : (int32_t)(-1 - ngexp++)});
-            gc[pa + 1]++;
-            g0 = g1;
-        }
-        if (!single) { PP.gif_a.push_back((int32_t)a); PP.gif_ptr.push_back((int32_t)ngexp); }
-    }
-    PP.n_gexp = ngexp;
-    for (int64_t q = 0; q < np; ++q) gc[q + 1] += gc[q];
-    PP.g_pp = gc;
-    PP.g_dest.resize(gc[np]);
-    std::vector<int32_t> gcnt(gc[np], 0), gpos(gc.begin(), gc.end() - 1);
-    std::vector<int64_t> gsrc0(gc[np], 0);
-    for (const GG& g : gg) {
-        const int32_t k = gpos[g.patch]++;
-        PP.g_dest[k] = g.dest; gcnt[k] = (int32_t)(g.c1 - g.c0); gsrc0[k] = g.c0;
-    }
-    PP.g_ptr.assign(gc[np] + 1, 0);
-    for (int64_t k = 0; k < gc[np]; ++k) PP.g_ptr[k + 1] = PP.g_ptr[k] + gcnt[k];
-    PP.g_idx.resize(PP.g_ptr[gc[np]]);
-    for (int64_t k = 0; k < gc[np]; ++k)
-        for (int32_t r = 0; r < gcnt[k]; ++r) PP.g_idx[PP.g_ptr[k] + r] = glocal_of(EP.g_cidx[gsrc0[k] + r]);
+    const int64_t P = PP.P, NSP = PP.NSP, RS = PP.RSP;
+    if (P * (NSP + RS) > 65534) throw std::runtime_error("patch too large for 16-bit local slots");
+    build_replay((int64_t)EP.h_colidx.size(), EP.h_cptr, EP.h_cidx, PP.npatch,
+                 [&](int32_t gs) { return (int64_t)(gs / NS) / P; },
+                 [&](int32_t gs) { const int64_t e = gs / NS; return (uint32_t)((e % P) * NSP + gs % NS); }, PP.H);
+    // gradient records live after the slot records in the patch's shared-memory image
+    build_replay(EP.m, EP.g_cptr, EP.g_cidx, PP.npatch,
+                 [&](int32_t gi) { return (int64_t)(gi / RS) / P; },
+                 [&](int32_t gi) { const int64_t e = gi / RS; return (uint32_t)(P * NSP + (e % P) * RS + gi % RS); }, PP.G);
 }
 
 void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P, bool want_hessian) {

@@ -43,29 +43,26 @@ struct SlotLayout {
 // Patch-fused replay lists: a CTA owns P consecutive elements, keeps their slot records in shared
 // memory and finishes every output entry whose contributions all come from the patch; the others get
 // one partial sum per patch in an export buffer that a small interface kernel folds.
-struct PatchPlan {
-    int P = 0, NSP = 0, RSP = 0;  // elements per patch, smem strides (doubles) of the slot / gradient records
-    int64_t npatch = 0;
-    // Hessian, per patch
-    std::vector<int32_t> w2_pp;    // npatch+1
-    std::vector<int32_t> w2_dest;  // >=0: index into hval; <0: -1-index into the export buffer
-    std::vector<uint32_t> w2_src;  // lo16 first local slot, hi16 second (0xFFFF none)
-    std::vector<int32_t> lg_pp;    // npatch+1 (entries with > 2 in-patch contributions)
+// One output family (Hessian values or gradient entries) of the patch-fused replay.
+struct ReplayLists {
+    std::vector<int32_t> pp;       // npatch+1: records of patch p are [pp[p], pp[p+1])
+    std::vector<int32_t> rec;      // 2 ints per record: dest, src  (dest >= 0: index into the output array,
+                                   // dest < 0: -1-index into the export buffer; src: lo16 first local slot,
+                                   // hi16 second local slot or 0xFFFF)
+    std::vector<int32_t> lg_pp;    // npatch+1: entries with more than two in-patch contributions
     std::vector<int32_t> lg_dest;
     std::vector<int32_t> lg_ptr;   // nlong+1 into lg_idx
     std::vector<uint16_t> lg_idx;
-    // Hessian interface
-    std::vector<int32_t> if_t;     // hval index
-    std::vector<int32_t> if_ptr;   // n_if+1 into the export buffer (contiguous partials per entry)
-    int64_t n_hexp = 0;
-    // gradient, per patch
-    std::vector<int32_t> g_pp;     // npatch+1
-    std::vector<int32_t> g_dest;
-    std::vector<int32_t> g_ptr;    // +1 into g_idx
-    std::vector<uint16_t> g_idx;
-    std::vector<int32_t> gif_a;
-    std::vector<int32_t> gif_ptr;
-    int64_t n_gexp = 0;
+    std::vector<int32_t> if_dst;   // interface entries: output index
+    std::vector<int32_t> if_ptr;   // n_if+1 into the export buffer (partials of one entry are contiguous)
+    int64_t n_exp = 0;
+    int32_t max_rec = 0;           // longest per-patch record list (sizes the shared-memory staging area)
+};
+
+struct PatchPlan {
+    int P = 0, NSP = 0, RSP = 0;  // elements per patch, smem strides (doubles) of the slot / gradient records
+    int64_t npatch = 0;
+    ReplayLists H, G;              // G's local slots index the gradient records, stored after the slot records
 };
 
 struct ElementPlan {
