@@ -13,7 +13,7 @@ inline void inst_check(cudaError_t e, const char* what) {
 
 template <int B, int D, bool SLACK, bool FINE>
 void launch_elem_flags(const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
-    const dim3 g((unsigned)nblk), b(128);
+    const dim3 g((unsigned)nblk), b(MGB_ELEM_THREADS);
     switch (canonical_flags(flags)) {
         case 1: element_kernel<B, D, SLACK, FINE, 1><<<g, b, 0, st>>>(P); break;
         case 7: element_kernel<B, D, SLACK, FINE, 7><<<g, b, 0, st>>>(P); break;

@@ -16,18 +16,20 @@
 #ifndef MGB_ELEM_MINBLOCKS
 #define MGB_ELEM_MINBLOCKS 5
 #endif
+#ifndef MGB_ELEM_THREADS
+#define MGB_ELEM_THREADS 128
+#endif
 
 namespace mgb {
 
 struct ElemParams {
     // geometry / plan (device)
     int64_t E, nloc;
-    const int32_t* lcols;    // [NU][E][LPE]
-    const double* opd;       // [dim][B][nloc]
-    const double* idd;       // coarse [NU][B][nloc]
-    const double* own_val;   // fine [NU][nloc]
-    const uint8_t* own_lq;   // fine [NU][nloc]
-    const double* w;         // nloc
+    const int32_t* lcols;    // [E][NU][LPE] element -> dof (-1: eliminated)
+    const double* prec;      // [nloc][RW] per-point record: derivative rows (D*B), w, then
+                             //   fine:   own_val[NU], own_lq bytes packed in one 8-byte slot
+                             //   coarse: dense id-like rows [NU][B]
+                             // RW even -> every record is 16-byte aligned (128-bit loads)
     // per call
     const double* s;         // m
     const double* Dz0;       // nloc x ND or null
@@ -130,28 +132,50 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     const int64_t i = act ? e * B + l : 0;
     const int64_t n = P.nloc;
 
+    // ---- loads.  Order matters (in-order issue): first the dof indices (their consumer, the gather
+    // of s, comes last), then every independent stream, so one memory latency covers all of them.
+    int32_t col[NU];
+#pragma unroll
+    for (int v = 0; v < NU; ++v) col[v] = act_e ? __ldg(&P.lcols[(e * NU + v) * LPE + l]) : -1;
+    constexpr int RWF = D * B + 1 + NU + 1, RWC = D * B + 1 + NU * B;
+    constexpr int RW = ((FINE ? RWF : RWC) + 1) / 2 * 2;
+    double rec[RW];
+    {
+        const double2* __restrict__ rp = reinterpret_cast<const double2*>(P.prec + i * RW);
+#pragma unroll
+        for (int j = 0; j < RW / 2; ++j) {
+            const double2 t2 = act ? __ldg(rp + j) : make_double2(0.0, 0.0);
+            rec[2 * j] = t2.x;
+            rec[2 * j + 1] = t2.y;
+        }
+    }
+    double cc[ND], dz[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        cc[k] = act ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
+        dz[k] = (act && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+    }
     // ---- gather the element's unknowns: lane q holds z[var][q]
     double zl[NU];
 #pragma unroll
-    for (int v = 0; v < NU; ++v) {
-        const int32_t col = act_e ? __ldg(&P.lcols[((int64_t)v * P.E + e) * LPE + l]) : -1;
-        zl[v] = (col >= 0) ? __ldg(&P.s[col]) : 0.0;
-    }
-    // ---- operator rows of this point in element-local columns
+    for (int v = 0; v < NU; ++v) zl[v] = (col[v] >= 0) ? __ldg(&P.s[col[v]]) : 0.0;
+    // ---- unpack the record
     double a[D][B];
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int q = 0; q < B; ++q) a[k][q] = act ? __ldg(&P.opd[((int64_t)k * B + q) * n + i]) : 0.0;
+        for (int q = 0; q < B; ++q) a[k][q] = rec[k * B + q];
+    const double wi = rec[D * B];
     double aid[FINE ? 1 : NU][FINE ? 1 : B];
     double oval[NU];
     int olq[NU];
     bool oh[NU];  // this point owns a column of variable v (false: eliminated dof, e.g. Dirichlet)
     if (FINE) {
+        const unsigned long long lqbits = (unsigned long long)__double_as_longlong(rec[FINE ? D * B + 1 + NU : 0]);
 #pragma unroll
         for (int v = 0; v < NU; ++v) {
-            oval[v] = act ? __ldg(&P.own_val[(int64_t)v * n + i]) : 0.0;
-            olq[v] = act ? (int)__ldg(&P.own_lq[(int64_t)v * n + i]) : 255;
+            oval[v] = rec[FINE ? D * B + 1 + v : 0];
+            olq[v] = act ? (int)((lqbits >> (8 * v)) & 0xFFull) : 255;
             oh[v] = olq[v] != 255;
             if (!oh[v]) { oval[v] = 0.0; olq[v] = 0; }
         }
@@ -159,14 +183,7 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
 #pragma unroll
         for (int v = 0; v < NU; ++v)
 #pragma unroll
-            for (int q = 0; q < B; ++q) aid[FINE ? 0 : v][FINE ? 0 : q] = act ? __ldg(&P.idd[((int64_t)v * B + q) * n + i]) : 0.0;
-    }
-    double wi = act ? __ldg(&P.w[i]) : 0.0;
-    double cc[ND], dz[ND];
-#pragma unroll
-    for (int k = 0; k < ND; ++k) {
-        cc[k] = act ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
-        dz[k] = (act && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+            for (int q = 0; q < B; ++q) aid[FINE ? 0 : v][FINE ? 0 : q] = rec[FINE ? 0 : D * B + 1 + v * B + q];
     }
     // ---- apply_D: Dz = Dz0 + (D R) s
 #pragma unroll
@@ -395,7 +412,7 @@ __device__ __forceinline__ void block_scalars(double v0, double v1, double v2, d
 
 // Two-stage path, stage 1: slot / gradient records to global memory (replayed by gather_kernel).
 template <int B, int D, bool SLACK, bool FINE, int FLAGS>
-__global__ void __launch_bounds__(128, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
+__global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
     constexpr int LPE = Pow2Ceil<B>::value;
     constexpr int NU = 2 + (SLACK ? 1 : 0);
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -83,8 +83,7 @@ struct mgb_plan {
     DevBuf<int64_t> d_hcptr, d_gcptr, d_hlptr;
     DevBuf<int2> d_hsrc2;
     DevBuf<int32_t> d_hlidx;
-    DevBuf<double> d_opd, d_idd, d_ownval, d_w, d_sel, d_rel, d_part, d_scal_tmp;
-    DevBuf<uint8_t> d_ownlq;
+    DevBuf<double> d_prec, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
     // patch-fused path
     int patch = 0;  // elements per CTA (0 = two-stage path)
@@ -197,8 +196,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     const auto& ep = pl->ep;
     mgb::ElemParams P{};
     P.E = ep.E; P.nloc = ep.nloc;
-    P.lcols = pl->d_lcols.p; P.opd = pl->d_opd.p; P.idd = pl->d_idd.p;
-    P.own_val = pl->d_ownval.p; P.own_lq = pl->d_ownlq.p; P.w = pl->d_w.p;
+    P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
     P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
     P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
@@ -351,7 +349,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         force_path &= 3;
         pl->has_hessian = want_hess;
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, pl->bar, pl->ep, want_hess);
+            mgb::build_element_plan(Dh, Rh, n, w_host + row0, pl->bar, pl->ep, want_hess);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
                 return fail("mgb_plan_create: element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
@@ -365,8 +363,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             pl->h_rowptr = ep.h_rowptr; pl->h_colidx = ep.h_colidx;
             pl->n_hcontrib = (int64_t)ep.h_cidx.size(); pl->n_gcontrib = (int64_t)ep.g_cidx.size();
           if (!host_only) {
-            pl->d_lcols.upload(ep.lcols, st); pl->d_opd.upload(ep.opd, st);
-            pl->d_idd.upload(ep.idd, st); pl->d_ownval.upload(ep.own_val, st); pl->d_ownlq.upload(ep.own_lq, st);
+            pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
             {
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
                 pl->long_lists = avg > 12.0;
@@ -417,18 +414,17 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
-            const int epb = pl->patch > 0 ? pl->patch : 128 / ep.LPE;
+            const int epb = pl->patch > 0 ? pl->patch : MGB_ELEM_THREADS / ep.LPE;
             pl->nblocks_elem = (ep.E + epb - 1) / epb;
             pl->d_part.alloc((size_t)pl->nblocks_elem * 4);
             pl->d_scal_tmp.alloc(4);
             CUDA_OK(cudaStreamSynchronize(st));
-            pl->dev_bytes = pl->d_lcols.bytes() + pl->d_opd.bytes() + pl->d_idd.bytes() + pl->d_ownval.bytes() +
-                            pl->d_ownlq.bytes() + pl->d_hcptr.bytes() + pl->d_hcidx.bytes() + pl->d_gcptr.bytes() +
+            pl->dev_bytes = pl->d_lcols.bytes() + pl->d_prec.bytes() + pl->d_hcptr.bytes() + pl->d_hcidx.bytes() + pl->d_gcptr.bytes() +
                             pl->d_gcidx.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
           }
             // release host copies that are no longer needed
             std::vector<int32_t>().swap(ep.h_cidx); std::vector<int64_t>().swap(ep.h_cptr);
-            std::vector<double>().swap(ep.opd); std::vector<double>().swap(ep.idd);
+            std::vector<double>().swap(ep.prec);
             std::vector<int32_t>().swap(ep.h_rowptr); std::vector<int32_t>().swap(ep.h_colidx);
         } else {
             pl->path = MGB_PATH_CSR;

@@ -140,7 +140,7 @@ struct UF {
 };
 }  // namespace
 
-void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
+void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
                         const BarrierDesc& bar, ElementPlan& P, bool want_hessian) {
     P.ok = false;
     const int ND = (int)D.size();
@@ -219,10 +219,10 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
             std::sort(tmp.begin(), tmp.end());
             tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
             if ((int64_t)tmp.size() > B) { P.why = "element touches more dofs per variable than it has nodes"; return; }
-            for (size_t q = 0; q < tmp.size(); ++q) P.lcols[((size_t)v * E + e) * LPE + q] = tmp[q];
+            for (size_t q = 0; q < tmp.size(); ++q) P.lcols[((size_t)e * nu + v) * LPE + q] = tmp[q];
         }
     auto local_of = [&](int v, int64_t e, int32_t col) -> int {
-        const int32_t* lc = &P.lcols[((size_t)v * E + e) * LPE];
+        const int32_t* lc = &P.lcols[((size_t)e * nu + v) * LPE];
         for (int q = 0; q < (int)B; ++q)
             if (lc[q] == col) return q;
         return -1;
@@ -249,38 +249,42 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     P.lay.build((int)B, dim, slack, fine);
     const SlotLayout& lay = P.lay;
 
-    // operator rows in element-local columns
-    P.opd.assign((size_t)dim * B * nloc, 0.0);
-    for (int kd = 0; kd < dim; ++kd) {
-        const HostCSR& A = Ek[1 + kd];
-        for (int64_t i = 0; i < nloc; ++i) {
-            const int64_t e = i / B;
-            for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
-                const int q = local_of(0, e, A.idx[p]);
-                P.opd[((size_t)kd * B + q) * nloc + i] = A.val[p];
+    // per-point records in element-local columns (one contiguous, 16-byte aligned record per point)
+    {
+        const int rwf = dim * (int)B + 1 + nu + 1, rwc = dim * (int)B + 1 + nu * (int)B;
+        const int RW = ((fine ? rwf : rwc) + 1) / 2 * 2;
+        P.RW = RW;
+        P.prec.assign((size_t)nloc * RW, 0.0);
+        for (int kd = 0; kd < dim; ++kd) {
+            const HostCSR& A = Ek[1 + kd];
+            for (int64_t i = 0; i < nloc; ++i)
+                for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p)
+                    P.prec[(size_t)i * RW + kd * B + local_of(0, i / B, A.idx[p])] = A.val[p];
+        }
+        for (int64_t i = 0; i < nloc; ++i) P.prec[(size_t)i * RW + dim * B] = w_local[i];
+        if (fine) {
+            for (int64_t i = 0; i < nloc; ++i) {
+                unsigned long long bits = 0;
+                for (int v = 0; v < nu; ++v) {
+                    const HostCSR& A = Ek[idop[v]];
+                    unsigned lq = 255;
+                    if (A.ptr[i + 1] > A.ptr[i]) {
+                        P.prec[(size_t)i * RW + dim * B + 1 + v] = A.val[A.ptr[i]];
+                        lq = (unsigned)local_of(v, i / B, A.idx[A.ptr[i]]);
+                    }
+                    bits |= (unsigned long long)lq << (8 * v);
+                }
+                double packed;
+                std::memcpy(&packed, &bits, sizeof(double));
+                P.prec[(size_t)i * RW + dim * B + 1 + nu] = packed;
             }
-        }
-    }
-    if (fine) {
-        P.own_val.assign((size_t)nu * nloc, 0.0);
-        P.own_lq.assign((size_t)nu * nloc, 255);
-        for (int v = 0; v < nu; ++v) {
-            const HostCSR& A = Ek[idop[v]];
-            for (int64_t i = 0; i < nloc; ++i)
-                if (A.ptr[i + 1] > A.ptr[i]) {
-                    P.own_val[(size_t)v * nloc + i] = A.val[A.ptr[i]];
-                    P.own_lq[(size_t)v * nloc + i] = (uint8_t)local_of(v, i / B, A.idx[A.ptr[i]]);
-                }
-        }
-    } else {
-        P.idd.assign((size_t)nu * B * nloc, 0.0);
-        for (int v = 0; v < nu; ++v) {
-            const HostCSR& A = Ek[idop[v]];
-            for (int64_t i = 0; i < nloc; ++i)
-                for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
-                    const int q = local_of(v, i / B, A.idx[p]);
-                    P.idd[((size_t)v * B + q) * nloc + i] = A.val[p];
-                }
+        } else {
+            for (int v = 0; v < nu; ++v) {
+                const HostCSR& A = Ek[idop[v]];
+                for (int64_t i = 0; i < nloc; ++i)
+                    for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p)
+                        P.prec[(size_t)i * RW + dim * B + 1 + v * B + local_of(v, i / B, A.idx[p])] = A.val[p];
+            }
         }
     }
 
@@ -344,11 +348,11 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                         for (int a2 = 0; a2 < NL; ++a2)
                             if (U[(size_t)l * NL + a2]) pres[(size_t)a1 * NL + a2] = 1;
             for (int a1 = 0; a1 < NL; ++a1) {
-                const int32_t ga = P.lcols[((size_t)(a1 / B) * E + e) * LPE + a1 % B];
+                const int32_t ga = P.lcols[((size_t)e * nu + a1 / B) * LPE + a1 % B];
                 if (ga < 0) continue;
                 for (int a2 = 0; a2 < NL; ++a2) {
                     if (!pres[(size_t)a1 * NL + a2]) continue;
-                    const int32_t gb = P.lcols[((size_t)(a2 / B) * E + e) * LPE + a2 % B];
+                    const int32_t gb = P.lcols[((size_t)e * nu + a2 / B) * LPE + a2 % B];
                     if (gb < 0) continue;
                     if (pass == 0) { rowcnt[ga + 1]++; continue; }
                     const int sl = slot_of(a1, a2, own);
@@ -392,7 +396,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     for (int v = 0; v < nu; ++v)
         for (int64_t e = 0; e < E; ++e)
             for (int q = 0; q < (int)B; ++q) {
-                const int32_t a = P.lcols[((size_t)v * E + e) * LPE + q];
+                const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
                 if (a >= 0) gcnt[a + 1]++;
             }
     for (int64_t a = 0; a < m; ++a) gcnt[a + 1] += gcnt[a];
@@ -402,7 +406,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     for (int64_t e = 0; e < E; ++e)  // element-major so every list is ordered by element
         for (int v = 0; v < nu; ++v)
             for (int q = 0; q < (int)B; ++q) {
-                const int32_t a = P.lcols[((size_t)v * E + e) * LPE + q];
+                const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
                 if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
             }
     P.ok = true;

@@ -72,11 +72,10 @@ struct ElementPlan {
     bool slack = false, fine = false;
     int64_t E = 0, nloc = 0, m = 0;
     SlotLayout lay;
-    std::vector<int32_t> lcols;    // [NU][E][LPE]  global dof or -1
-    std::vector<double> opd;       // dense derivative rows [dim][B][nloc]
-    std::vector<double> idd;       // coarse: dense id-like rows [NU][B][nloc]
-    std::vector<double> own_val;   // fine: [NU][nloc]
-    std::vector<uint8_t> own_lq;   // fine: [NU][nloc]  local column or 255
+    std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1
+    int RW = 0;                    // doubles per point record (even)
+    std::vector<double> prec;      // [nloc][RW]: derivative rows (dim*B), w, then fine: own_val[NU] + packed
+                                   // own_lq bytes (255 = none); coarse: dense id-like rows [NU][B]
     // fixed output pattern + replay lists
     std::vector<int32_t> h_rowptr, h_colidx;  // m+1, nnzH
     std::vector<int64_t> h_cptr;              // nnzH+1
@@ -97,7 +96,7 @@ struct BarrierDesc {
 
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.
 // Tries to detect the broken-element block structure the fused kernels exploit.
-void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global,
+void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
                         const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
 
 struct CsrPlan {
