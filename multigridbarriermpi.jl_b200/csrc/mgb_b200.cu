@@ -82,7 +82,8 @@ struct mgb_plan {
     DevBuf<int32_t> d_lcols, d_hcidx, d_gcidx;
     DevBuf<int64_t> d_hcptr, d_gcptr, d_hlptr;
     DevBuf<int2> d_hsrc2;
-    DevBuf<int32_t> d_hlidx;
+    DevBuf<int32_t> d_hlidx, d_hlt;
+    int64_t n_long = 0;
     DevBuf<double> d_prec, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
     // patch-fused path
@@ -179,7 +180,11 @@ int64_t algorithmic_bytes(int64_t n, int64_t N, int nD, int dim, int64_t nnzD, i
     return b;
 }
 
-bool want_patch_early(int force_flags) { return (force_flags & MGB_PLAN_TWO_STAGE) == 0; }
+// The patch-fused kernel is opt-in (MGB_PATCH=16|32|64): measured slower than the two-stage pair at L=8.
+bool want_patch_early(int force_flags) {
+    const char* ev = getenv("MGB_PATCH");
+    return (force_flags & MGB_PLAN_TWO_STAGE) == 0 && ev && atoi(ev) > 0;
+}
 
 bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
@@ -199,8 +204,9 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
     P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
-    P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
-    P.off_ut = ep.lay.off_ut; P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
+    for (int v1 = 0; v1 < 3; ++v1)
+        for (int v2 = 0; v2 < 3; ++v2) P.off[v1][v2] = ep.lay.off[v1][v2];
+    P.NS = ep.lay.NS;
     if ((flags & MGB_STORE_DZ) && !Dz) throw std::runtime_error("MGB_STORE_DZ without Dz buffer");
     if ((flags & MGB_WANT_GRAD) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
     if ((flags & MGB_WANT_HESS) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
@@ -235,7 +241,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
 
     mgb::GatherParams G{};
     G.nnzH = pl->nnzH; G.m = pl->m;
-    G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p;
+    G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p; G.h_lt = pl->d_hlt.p;
     G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
     G.sel = pl->d_sel.p; G.rel = pl->d_rel.p; G.hval = hval; G.grad = grad;
     G.part = pl->d_part.p; G.nparts = pl->nblocks_elem; G.scal = scal ? scal : pl->d_scal_tmp.p; G.t = t;
@@ -257,7 +263,9 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     }
     G.nblk_h = G.want_h ? (pl->nnzH + 256 * mgb::GATHER_UNROLL - 1) / (256 * mgb::GATHER_UNROLL) : 0;
     G.nblk_g = G.want_g ? (pl->m + 255) / 256 : 0;
-    mgb::gather_kernel<<<(unsigned)(G.nblk_h + G.nblk_g + 1), 256, 0, st>>>(G);
+    G.n_long = G.want_h ? pl->n_long : 0;
+    G.nblk_l = (G.n_long + 255) / 256;
+    mgb::gather_kernel<<<(unsigned)(G.nblk_h + G.nblk_l + G.nblk_g + 1), 256, 0, st>>>(G);
     g_launches++;
     CUDA_OK(cudaGetLastError());
 }
@@ -375,7 +383,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             } else {   // two-wide ELL + long list for the thread-per-entry gather
                 std::vector<int2> src2(pl->nnzH);
                 std::vector<int64_t> lptr(1, 0);
-                std::vector<int32_t> lidx;
+                std::vector<int32_t> lidx, lt;
                 for (int64_t t = 0; t < pl->nnzH; ++t) {
                     const int64_t c0 = ep.h_cptr[t], c1 = ep.h_cptr[t + 1];
                     if (c1 - c0 <= 2) {
@@ -387,17 +395,18 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                         src2[t].y = -1;
                         lidx.insert(lidx.end(), ep.h_cidx.begin() + c0, ep.h_cidx.begin() + c1);
                         lptr.push_back((int64_t)lidx.size());
+                        lt.push_back((int32_t)t);
                     }
                 }
                 pl->d_hsrc2.upload(src2, st); pl->d_hlptr.upload(lptr, st); pl->d_hlidx.upload(lidx, st);
+                pl->d_hlt.upload(lt, st); pl->n_long = (int64_t)lt.size();
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
             int want_patch = 0;
-            if ((force_flags & MGB_PLAN_TWO_STAGE) == 0) {
-                want_patch = (ep.B == 2) ? 64 : 32;
-                if (const char* ev = getenv("MGB_PATCH")) want_patch = atoi(ev);
-                if (ep.B == 7 && want_patch != 16 && want_patch != 32 && want_patch != 64) want_patch = 32;
+            if (want_patch_early(force_flags)) {
+                want_patch = atoi(getenv("MGB_PATCH"));
+                if (ep.B == 7 && want_patch != 16 && want_patch != 32 && want_patch != 64) want_patch = 16;
                 if (ep.B == 2) want_patch = 64;
             }
             if (want_patch > 0) {

@@ -48,11 +48,14 @@ def test_two_stage_element_path(gpu_ctx, gen, L, level, slack):
     assert plan.info["path"] == capi.PATH_ELEMENT
 
 
-@pytest.mark.parametrize("patch", ["16", "64"])
-def test_patch_sizes(gpu_ctx, patch, monkeypatch):
+@pytest.mark.parametrize("patch", ["16", "32", "64"])
+def test_patch_fused_path(gpu_ctx, patch, monkeypatch):
+    """opt-in patch-fused kernel (MGB_PATCH): CTA-local records in shared memory + interface partials"""
     monkeypatch.setenv("MGB_PATCH", patch)
     check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.0, t=0.9)
     check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.5, t=0.9, level=1)
+    check_against_oracle(gpu_ctx, mgb_b200.fem2d(3), 1.0, t=0.9, slack=True)
+    check_against_oracle(gpu_ctx, mgb_b200.fem1d(6), 1.0, t=0.9)
 
 
 def test_bitwise_reproducible(gpu_ctx):
