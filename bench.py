@@ -142,6 +142,7 @@ def main():
     ap.add_argument("--p", type=float, default=1.0)
     ap.add_argument("--t", type=float, default=1.0)
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps")
+    ap.add_argument("--flush-mode", default="read", choices=["read", "write"], help="evict L2 by reading (clean lines) or writing (dirty lines) 256 MiB")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--two-stage", action="store_true", help="element_kernel + gather_kernel instead of the patch-fused kernel")
     args = ap.parse_args()
@@ -187,7 +188,7 @@ def main():
     scal_d = torch.zeros(4, dtype=f64, device=dev)
     grad_d = torch.zeros(plan.m, dtype=f64, device=dev)
     hval_d = torch.zeros(max(plan.nnzH, 1), dtype=f64, device=dev)
-    flush = not args.no_flush
+    flush = 0 if args.no_flush else (2 if args.flush_mode == "read" else 1)
 
     def barrier():
         if world > 1:
@@ -203,14 +204,16 @@ def main():
         ex = mdist.build_exchange(rank, world, plan.m, grp.astype(np.int64), gci.astype(np.int64),
                                   lrp.astype(np.int64), lci.astype(np.int64), dev)
         exch = mdist.Exchanger(ex, dev, ctx=ctx)
-        flush_buf = torch.empty(256 << 17, dtype=f64, device=dev)  # 256 MiB
+        flush_buf = torch.zeros(256 << 17, dtype=f64, device=dev)  # 256 MiB
 
     def step_multi(nsteps):
         """per-step CUDA events on the launching stream; interface exchange + scalar all-reduce inside"""
         tot = 0.0
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for r in range(nsteps):
-            if flush:
+            if flush == 2:
+                flush_sink = flush_buf.sum()  # read-evict: leaves L2 full of clean lines
+            elif flush:
                 flush_buf.fill_(float(r))
             ev0.record()
             plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
@@ -303,7 +306,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly: n={n} quadrature points, "
                                    f"m={info['m']} dofs, nnz(R'HR)={info['nnzH']}",
-                       "l2": "flushed between steps (256 MiB write)" if flush else "not flushed",
+                       "l2": ("flushed between steps (256 MiB %s)" % args.flush_mode) if flush else "not flushed",
                        "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
                        "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
                        "rows_per_rank": nloc,

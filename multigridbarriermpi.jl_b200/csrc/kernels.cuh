@@ -40,8 +40,7 @@ struct ElemParams {
     double* rel;             // E*NU*LPE
     double* part;            // gridDim.x * 4  {f0, cdot, nonfinite count, -}
     double* Dz;              // nloc x ND or null
-    int off[3][3];           // slot-record offset of block (row variable, column variable)
-    int NS;
+    int off_uu, off_us, off_ss, off_ut, off_st, off_tt, NS;
 };
 
 template <int V>
@@ -62,27 +61,6 @@ __device__ __forceinline__ void group_reduce(double (&v)[NV], int lane) {
     int len = NV;
 #pragma unroll
     for (int M = LPE / 2; M >= 1; M >>= 1) {
-        const int half = len / 2;
-        const bool up = (lane & M) != 0;
-#pragma unroll
-        for (int r = 0; r < NV / 2; ++r) {
-            if (r < half) {
-                const double lo = v[r], hi = v[r + half];
-                const double send = up ? lo : hi;
-                const double keep = up ? hi : lo;
-                v[r] = keep + shfl_xor_d(send, M);
-            }
-        }
-        len = half;
-    }
-}
-
-// Same butterfly restricted to the lower W lanes-bits (W = 1 leaves v untouched).
-template <int NV, int W>
-__device__ __forceinline__ void group_reduce_w(double (&v)[NV], int lane) {
-    int len = NV;
-#pragma unroll
-    for (int M = W / 2; M >= 1; M >>= 1) {
         const int half = len / 2;
         const bool up = (lane & M) != 0;
 #pragma unroll
@@ -134,14 +112,6 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
     }
 }
 
-template <int D, int B>
-__device__ __forceinline__ double suu_val(const double (&a)[D][B], const double (&T)[D][B], int q, int q2) {
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) acc = fma(a[j][q], T[j][q2], acc);
-    return acc;
-}
-
 // FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
 // Per-point work of one element group (LPE lanes).  Writes the element's gradient record to `rel`
 // and its slot record to `sel` (global memory in the two-stage path, shared memory in the patch-
@@ -154,6 +124,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     constexpr int ND = D + 2 + (SLACK ? 1 : 0);
     constexpr int NU = 2 + (SLACK ? 1 : 0);
     constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
+    constexpr int NTRI = (B * (B + 1) / 2 + LPE - 1) / LPE * LPE;
+    constexpr int NFULL = (B * B + LPE - 1) / LPE * LPE;
 
     const bool act_e = e < P.E;
     const bool act = act_e && (l < B);
@@ -308,30 +280,7 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
         }
     }
     if (WH) {
-    // ---- Hessian: element-local blocks of sum_jk a_j' (w Y_jk) a_k.  Every block is stored with full
-    // rows (row = local dof of the row variable): lane l ends up with row l, so the gather kernel reads
-    // contiguous runs.  rows_of() folds the first butterfly step into the evaluation of X(q,q2): the
-    // lower and upper half of the rows are formed on the fly, only HALF*B values are ever live.
-    constexpr int HALF = (LPE > 1) ? LPE / 2 : 1;
-    constexpr int NVH = HALF * B;
-    const bool up = (l & HALF) != 0;
-#define MGB_ROWS_OF(VARR, XEXPR)                                                                     \
-    {                                                                                                \
-        _Pragma("unroll") for (int r = 0; r < NVH; ++r) {                                            \
-            const int q = r / B, q2 = r % B;                                                         \
-            double lo, hi = 0.0;                                                                     \
-            { const int qq = q; lo = (XEXPR); }                                                      \
-            if (q + HALF < B) { const int qq = (q + HALF < B) ? q + HALF : 0; hi = (XEXPR); }        \
-            (void)q2;                                                                                \
-            if (LPE > 1) {                                                                           \
-                const double send = up ? lo : hi, keep = up ? hi : lo;                               \
-                VARR[r] = keep + shfl_xor_d(send, HALF);                                             \
-            } else {                                                                                 \
-                VARR[r] = lo;                                                                        \
-            }                                                                                        \
-        }                                                                                            \
-        group_reduce_w<NVH, HALF>(VARR, l);                                                          \
-    }
+    // ---- Hessian: element-local blocks of sum_jk a_j' (w Y_jk) a_k
     // u-u block (derivative operators only: the u.id row of F2 is identically zero)
     {
         double T[D][B];
@@ -344,15 +293,25 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                 for (int j2 = 0; j2 < D; ++j2) tacc = fma(wi * bo.Hqq[j][j2], a[j2][q], tacc);
                 T[j][q] = tacc;
             }
-        double v[NVH];
-#define MGB_SUU(QQ, Q2) suu_val<D, B>(a, T, QQ, Q2)
-        MGB_ROWS_OF(v, MGB_SUU(qq, q2))
-#undef MGB_SUU
-        if (act_e && l < B) {
+        double v[NTRI];
 #pragma unroll
-            for (int q2 = 0; q2 < B; ++q2) sel[P.off[0][0] + l * LPE + q2] = v[q2];
+        for (int r = 0; r < NTRI; ++r) v[r] = 0.0;
+#pragma unroll
+        for (int q = 0; q < B; ++q)
+#pragma unroll
+            for (int q2 = q; q2 < B; ++q2) {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < D; ++j) acc = fma(a[j][q], T[j][q2], acc);
+                v[q * B - q * (q - 1) / 2 + (q2 - q)] = acc;
+            }
+        group_reduce<NTRI, LPE>(v, l);
+        if (act_e) {
+#pragma unroll
+            for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + r * LPE + l] = v[r];
         }
     }
+    // u-s (and u-slack) blocks
     double bs[B];
 #pragma unroll
     for (int q = 0; q < B; ++q) {
@@ -364,54 +323,68 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     const double vss = wi * bo.Hss;
     const double vtt = SLACK ? vss + wi * itau * itau : vss;  // slack-slack curvature incl. -log(1+tau)
     if (FINE) {
+        if (act && oh[1]) {
 #pragma unroll
-        for (int v2 = 1; v2 < NU; ++v2) {
-            if (act && oh[v2]) {
-#pragma unroll
-                for (int q = 0; q < B; ++q) {
-                    const double val = bs[q] * oval[v2];
-                    sel[P.off[0][v2] + q * LPE + olq[v2]] = val;   // column of the u x v2 block
-                    sel[P.off[v2][0] + olq[v2] * LPE + q] = val;   // row of the v2 x u block
-                }
-                sel[P.off[v2][v2] + olq[v2]] = (v2 == 2 ? vtt : vss) * oval[v2] * oval[v2];
-            }
+            for (int q = 0; q < B; ++q) sel[P.off_us + q * LPE + olq[1]] = bs[q] * oval[1];
+            sel[P.off_ss + olq[1]] = vss * oval[1] * oval[1];
         }
-        if (SLACK && act && oh[1] && oh[SLACK ? 2 : 1]) {
-            constexpr int VT = SLACK ? 2 : 1;
-            const double val = vss * oval[1] * oval[VT];
-            sel[P.off[1][VT] + olq[1]] = val;
-            sel[P.off[VT][1] + olq[VT]] = val;
+        if (SLACK && act && oh[SLACK ? 2 : 0]) {
+            constexpr int VT = SLACK ? 2 : 0;
+#pragma unroll
+            for (int q = 0; q < B; ++q) sel[P.off_ut + q * LPE + olq[VT]] = bs[q] * oval[VT];
+            if (oh[1]) sel[P.off_st + l] = vss * oval[1] * oval[VT];
+            sel[P.off_tt + olq[VT]] = vtt * oval[VT] * oval[VT];
         }
     } else {
 #pragma unroll
-        for (int v2 = 1; v2 < NU; ++v2) {  // u x {s, slack} and transposes
-            double v[NVH];
-            MGB_ROWS_OF(v, bs[qq] * aid[FINE ? 0 : v2][FINE ? 0 : q2])
-            if (act_e && l < B) {
+        for (int v2 = 1; v2 < NU; ++v2) {  // u x {s, slack}
+            double v[NFULL];
 #pragma unroll
-                for (int q2 = 0; q2 < B; ++q2) {
-                    sel[P.off[0][v2] + l * LPE + q2] = v[q2];
-                    sel[P.off[v2][0] + q2 * LPE + l] = v[q2];
-                }
+            for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = 0; q2 < B; ++q2) v[q * B + q2] = bs[q] * aid[FINE ? 0 : v2][FINE ? 0 : q2];
+            group_reduce<NFULL, LPE>(v, l);
+            const int off = (v2 == 1) ? P.off_us : P.off_ut;
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NFULL / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
         }
 #pragma unroll
-        for (int v1 = 1; v1 < NU; ++v1)
+        for (int v1 = 1; v1 < NU; ++v1) {  // {s,slack} x {s,slack} symmetric diagonal blocks
+            double v[NTRI];
 #pragma unroll
-            for (int v2 = v1; v2 < NU; ++v2) {  // {s,slack} x {s,slack}
-                const double c12 = (v1 == 2 && v2 == 2) ? vtt : vss;
-                double v[NVH];
-                MGB_ROWS_OF(v, c12 * aid[FINE ? 0 : v1][FINE ? 0 : qq] * aid[FINE ? 0 : v2][FINE ? 0 : q2])
-                if (act_e && l < B) {
+            for (int r = 0; r < NTRI; ++r) v[r] = 0.0;
 #pragma unroll
-                    for (int q2 = 0; q2 < B; ++q2) {
-                        sel[P.off[v1][v2] + l * LPE + q2] = v[q2];
-                        if (v1 != v2) sel[P.off[v2][v1] + q2 * LPE + l] = v[q2];
-                    }
-                }
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = q; q2 < B; ++q2)
+                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = (v1 == 2 ? vtt : vss) * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
+            group_reduce<NTRI, LPE>(v, l);
+            const int off = (v1 == 1) ? P.off_ss : P.off_tt;
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NTRI / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
+        }
+        if (SLACK) {  // s x slack full block
+            double v[NFULL];
+#pragma unroll
+            for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
+#pragma unroll
+            for (int q = 0; q < B; ++q)
+#pragma unroll
+                for (int q2 = 0; q2 < B; ++q2)
+                    v[q * B + q2] = vss * aid[FINE ? 0 : 1][FINE ? 0 : q] * aid[FINE ? 0 : (SLACK ? 2 : 0)][FINE ? 0 : q2];
+            group_reduce<NFULL, LPE>(v, l);
+            if (act_e) {
+#pragma unroll
+                for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + r * LPE + l] = v[r];
+            }
+        }
     }
-#undef MGB_ROWS_OF
     }  // WH
 }
 
@@ -721,9 +694,14 @@ static __global__ void diag_scale_kernel(const double* __restrict__ w, const dou
     if (i < n) out[i] = w[i] * y[i];
 }
 
-static __global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x)
-        buf[i] = v;
+// L2 flush between timed steps: mode 0 writes a buffer larger than L2 (leaves L2 full of DIRTY lines whose
+// write-back then competes with the timed kernels), mode 1 reads it (evicts everything, leaves clean lines).
+static __global__ void l2_flush_kernel(double* __restrict__ buf, int64_t len, double v, int mode) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        if (mode == 0) buf[i] = v; else acc += buf[i];
+    }
+    if (mode != 0 && acc == 1.2345e300) buf[0] = acc;  // keeps the loads alive
 }
 
 // y = alpha * A x + beta * y0, thread per row (operator / restriction rows are short)

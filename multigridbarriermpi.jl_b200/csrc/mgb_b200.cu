@@ -204,9 +204,8 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
     P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
-    for (int v1 = 0; v1 < 3; ++v1)
-        for (int v2 = 0; v2 < 3; ++v2) P.off[v1][v2] = ep.lay.off[v1][v2];
-    P.NS = ep.lay.NS;
+    P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
+    P.off_ut = ep.lay.off_ut; P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
     if ((flags & MGB_STORE_DZ) && !Dz) throw std::runtime_error("MGB_STORE_DZ without Dz buffer");
     if ((flags & MGB_WANT_GRAD) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
     if ((flags & MGB_WANT_HESS) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
@@ -679,12 +678,12 @@ int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, 
         CUDA_OK(cudaSetDevice(ctx->device));
         cudaStream_t st = ctx->stream;
         const int64_t flush_len = (int64_t)256 << 20 >> 3;  // 256 MiB > 126 MB L2
-        if (flush_l2 && !ctx->flush.p) ctx->flush.alloc(flush_len);
+        if (flush_l2 && !ctx->flush.p) { ctx->flush.alloc(flush_len); CUDA_OK(cudaMemsetAsync(ctx->flush.p, 0, flush_len * 8, st)); }
         double tot = 0.0, tel = 0.0, tga = 0.0;
         const bool split = pl->path == MGB_PATH_ELEMENT && (ms_kernel_element || ms_kernel_gather);
         for (int r = 0; r < reps; ++r) {
             if (flush_l2) {
-                mgb::l2_flush_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->flush.p, flush_len, (double)r);
+                mgb::l2_flush_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->flush.p, flush_len, (double)r, flush_l2 == 2 ? 1 : 0);
             }
             CUDA_OK(cudaEventRecord(pl->ev[0], st));
             int rc = mgb_assemble(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, nullptr);
@@ -698,7 +697,7 @@ int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, 
         if (split) {
             // second pass with an event between the two kernels (kept out of the totals above)
             for (int r = 0; r < reps; ++r) {
-                if (flush_l2) mgb::l2_flush_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(ctx->flush.p, flush_len, (double)r);
+                if (flush_l2) mgb::l2_flush_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->flush.p, flush_len, (double)r, flush_l2 == 2 ? 1 : 0);
                 CUDA_OK(cudaEventRecord(pl->ev[0], st));
                 assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, nullptr, pl->ev[2]);
                 CUDA_OK(cudaEventRecord(pl->ev[1], st));

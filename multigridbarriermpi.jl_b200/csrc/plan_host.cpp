@@ -103,14 +103,24 @@ void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_) {
     fine = fine_;
     LPE = pow2ceil(B);
     NU = 2 + (slack ? 1 : 0);
+    const int ntri = round_up(B * (B + 1) / 2, LPE);
+    const int nfull = fine ? B * LPE : round_up(B * B, LPE);
+    const int ndiag = fine ? LPE : ntri;
     int o = 0;
-    for (int v1 = 0; v1 < NU; ++v1)
-        for (int v2 = 0; v2 < NU; ++v2) {
-            off[v1][v2] = o;
-            o += is_full(v1, v2) ? B * LPE : LPE;
-        }
-    NS = round_up(o, 2);
+    off_uu = o, o += ntri;
+    off_us = o, o += nfull;
+    off_ss = o, o += ndiag;
+    if (slack) {
+        off_ut = o, o += nfull;
+        off_st = o, o += fine ? LPE : round_up(B * B, LPE);
+        off_tt = o, o += ndiag;
+    }
+    NS = o;
 }
+
+int SlotLayout::tri(int q, int q2) const { return q * B - q * (q - 1) / 2 + (q2 - q); }
+int SlotLayout::ntri_pad() const { return round_up(B * (B + 1) / 2, LPE); }
+int SlotLayout::nfull_pad() const { return round_up(B * B, LPE); }
 
 namespace {
 struct UF {
@@ -282,11 +292,20 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     // over all operators (products keep structural zeros; see DESIGN.md "explicit-zero policy").
     const int NL = nu * (int)B;  // local index alpha = v*B + q
     auto slot_of = [&](int a1, int a2, const std::vector<int>& own /*[nu][B] local col per point*/) -> int {
-        const int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
-        if (lay.is_full(v1, v2)) return lay.off[v1][v2] + q1 * lay.LPE + q2;
-        if (v1 == v2) return q1 == q2 ? lay.off[v1][v1] + q1 : -1;
-        for (int l = 0; l < (int)B; ++l)
-            if (own[v1 * B + l] == q1 && own[v2 * B + l] == q2) return lay.off[v1][v2] + q1;
+        int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
+        if (v1 > v2 || (v1 == v2 && q1 > q2)) { std::swap(v1, v2); std::swap(q1, q2); }
+        const int NT = lay.ntri_pad(), NF = lay.nfull_pad();
+        if (v1 == 0 && v2 == 0) return lay.packed(lay.off_uu, lay.tri(q1, q2), NT);
+        if (v1 == 0 && v2 == 1) return lay.fine ? lay.off_us + q1 * lay.LPE + q2 : lay.packed(lay.off_us, q1 * lay.B + q2, NF);
+        if (v1 == 0 && v2 == 2) return lay.fine ? lay.off_ut + q1 * lay.LPE + q2 : lay.packed(lay.off_ut, q1 * lay.B + q2, NF);
+        if (v1 == 1 && v2 == 1) return lay.fine ? (q1 == q2 ? lay.off_ss + q1 : -1) : lay.packed(lay.off_ss, lay.tri(q1, q2), NT);
+        if (v1 == 2 && v2 == 2) return lay.fine ? (q1 == q2 ? lay.off_tt + q1 : -1) : lay.packed(lay.off_tt, lay.tri(q1, q2), NT);
+        if (v1 == 1 && v2 == 2) {
+            if (!lay.fine) return lay.packed(lay.off_st, q1 * lay.B + q2, NF);
+            for (int l = 0; l < (int)B; ++l)
+                if (own[1 * B + l] == q1 && own[2 * B + l] == q2) return lay.off_st + l;
+            return -1;
+        }
         return -1;
     };
 

@@ -29,15 +29,20 @@ int64_t count_gram_pattern(const std::vector<HostCSR>& D);
 struct SlotLayout {
     int B = 0, LPE = 0, NU = 0, dim = 0;
     bool slack = false, fine = false;
-    // block (v1,v2) of the element Hessian, rows = local dofs of variable v1:
-    //   full blocks:  off[v1][v2] + q1*LPE + q2
-    //   fine, v1,v2 >= 1 (one owned column per point): LPE entries indexed by q1
-    int off[3][3] = {{0}};
+    int off_uu = 0, off_us = 0, off_ss = 0, off_ut = 0, off_st = 0, off_tt = 0;
     int NS = 0;  // doubles per element
     void build(int B_, int dim_, bool slack_, bool fine_);
-    bool is_full(int v1, int v2) const { return !fine || v1 == 0 || v2 == 0; }
+    int tri(int q, int q2) const;  // packed upper-triangle index, q <= q2 < B
+    // slot of packed entry pk of a block of padded size npad that went through the transposing
+    // butterfly: lane l ends with entries [l*K,(l+1)*K) and stores entry r at  off + r*LPE + l
+    int packed(int off, int pk, int npad) const { const int K = npad / LPE; return off + (pk % K) * LPE + pk / K; }
+    int ntri_pad() const;
+    int nfull_pad() const;
 };
 
+// Patch-fused replay lists: a CTA owns P consecutive elements, keeps their slot records in shared
+// memory and finishes every output entry whose contributions all come from the patch; the others get
+// one partial sum per patch in an export buffer that a small interface kernel folds.
 // One output family (Hessian values or gradient entries) of the patch-fused replay.
 struct ReplayLists {
     std::vector<int32_t> pp;       // npatch+1: records of patch p are [pp[p], pp[p+1])
