@@ -150,6 +150,9 @@ int mgb_spmat_mv(mgb_spmat* A, int32_t trans, double alpha, const double* x_dev,
  * entries: out[k] = src[idx[k]]  and  dst[idx[k]] += src[k] (idx unique per call). */
 int mgb_gather_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* out_dev);
 int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_dev, int64_t count, double* dst_dev);
+/* owner-side reduction: dst[k] = sum of src[idx[r]] for r in [ptr[k], ptr[k+1]) in list order (deterministic) */
+int mgb_segsum_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* ptr_dev, const int32_t* idx_dev, int64_t nout,
+                   double* dst_dev);
 
 /* timing helper: runs `reps` assemblies back to back on the ctx stream, returns average ms measured
  * with CUDA events on that stream (bench.py uses it so the events sit on the launching stream). */

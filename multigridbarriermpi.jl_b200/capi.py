@@ -25,7 +25,7 @@ EXPORTS = [
     "mgb_last_error", "mgb_version", "mgb_ctx_create", "mgb_ctx_destroy", "mgb_ctx_sync", "mgb_plan_create",
     "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
-    "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx",
+    "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
 ]
 
 
@@ -94,6 +94,7 @@ def load(build_if_missing: bool = True):
     lib.mgb_spmat_mv.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]
     lib.mgb_gather_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mgb_scatter_add_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mgb_segsum_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     _lib = lib
     return lib
 
@@ -152,6 +153,9 @@ class Context:
 
     def scatter_add_idx(self, src_dev, idx_dev, count: int, dst_dev):
         _check(load().mgb_scatter_add_idx(self._h, _ptr(src_dev), _ptr(idx_dev), int(count), _ptr(dst_dev)))
+
+    def segsum_idx(self, src_dev, ptr_dev, idx_dev, nout: int, dst_dev):
+        _check(load().mgb_segsum_idx(self._h, _ptr(src_dev), _ptr(ptr_dev), _ptr(idx_dev), int(nout), _ptr(dst_dev)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -728,6 +728,17 @@ static __global__ void __launch_bounds__(256) scatter_add_idx_kernel(const doubl
     if (k < count) dst[idx[k]] += src[k];  // idx unique within a call: plain read-modify-write
 }
 
+// dst[k] = sum_{r in [ptr[k], ptr[k+1])} src[idx[r]]  (fixed order; thread per output)
+static __global__ void __launch_bounds__(256) segsum_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ ptr,
+                                                               const int32_t* __restrict__ idx, int64_t nout,
+                                                               double* __restrict__ dst) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nout) return;
+    double acc = 0.0;
+    for (int r = __ldg(&ptr[k]); r < __ldg(&ptr[k + 1]); ++r) acc += src[__ldg(&idx[r])];
+    dst[k] = acc;
+}
+
 // map_rows of the barrier over Dz rows (separately callable seam; reference src:161-170)
 template <int D>
 __global__ void map_barrier_kernel(const double* __restrict__ Dz, int64_t n, int ND, int slack, double p, int which,

@@ -668,6 +668,20 @@ int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_
     } catch (const std::exception& ex) { return fail(std::string("mgb_scatter_add_idx: ") + ex.what()); }
 }
 
+int mgb_segsum_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* ptr_dev, const int32_t* idx_dev, int64_t nout,
+                   double* dst_dev) {
+    try {
+        if (!ctx) return fail("mgb_segsum_idx: NULL argument");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        if (nout > 0) {
+            mgb::segsum_idx_kernel<<<(unsigned)((nout + 255) / 256), 256, 0, ctx->stream>>>(src_dev, ptr_dev, idx_dev, nout, dst_dev);
+            g_launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_segsum_idx: ") + ex.what()); }
+}
+
 int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                       int32_t flags, double* scal_dev, double* grad_dev, double* hval_dev, int32_t reps,
                       int32_t flush_l2, float* ms_total, float* ms_kernel_element, float* ms_kernel_gather) {

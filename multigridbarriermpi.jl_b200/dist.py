@@ -6,7 +6,8 @@ entries and rows of R'HR - are split in contiguous blocks of the m unknowns.  Ev
 the contributions of its own quadrature rows on its local pattern; the contributions to rows owned by
 another rank (the interface between neighbouring row blocks) travel once per assembly in a single
 all-to-all, and are summed at the owner in fixed source-rank order (bit-reproducible).  The scalars
-(objective, <c,Dz>, feasibility) are one 4-double all-reduce.
+(objective, <c,Dz>, feasibility) ride in the same all-to-all (every rank receives every partial and
+sums them in rank order).
 
 The index maps are built once per level (symbolic phase) from replicated structural information plus
 one integer all-to-all; the per-assembly work is: pack kernel -> all_to_all_single -> unpack kernels.
@@ -120,63 +121,89 @@ def build_exchange(rank: int, nranks: int, m: int, glob_rowptr: np.ndarray, glob
 
 
 class Exchanger:
-    """Per-assembly interface exchange.  ``ctx`` (capi.Context) selects the CUDA pack/unpack kernels;
-    ``ctx=None`` uses torch index ops (CPU / gloo tests)."""
+    """Per-assembly interface exchange in ONE collective.
 
-    def __init__(self, ex: ExchangePlan, device, ctx=None, group=None):
+    The local outputs live in one buffer ``loc = [hval | grad | scal(4)]`` (``views()`` hands the three
+    windows to mgb_assemble).  Per step: one pack kernel (gather_idx) builds the send buffer
+    ``[to rank 0 | to rank 1 | ...]``, each segment = H entries owned by that rank, gradient entries
+    owned by that rank, the 4 scalars; one ``all_to_all_single``; one owner-side kernel (segsum_idx)
+    sums, for every owned output, its contributions in source-rank order (bit-reproducible) into
+    ``own = [H rows owned | gradient block owned | scal(4)]``.
+    ``ctx`` (capi.Context) selects the CUDA kernels; ``ctx=None`` uses torch index ops (CPU / gloo tests)."""
+
+    def __init__(self, ex: ExchangePlan, device, ctx=None, group=None, n_loc_h: int = None, m: int = None):
         self.ex, self.device, self.ctx, self.group = ex, device, ctx, group
+        P = ex.nranks
         f64 = torch.float64
-        self.h_send = torch.empty(int(ex.h_send_idx.numel()), dtype=f64, device=device)
-        self.h_recv = torch.empty(int(ex.h_recv_pos.numel()), dtype=f64, device=device)
-        self.g_send = torch.empty(int(ex.g_send_idx.numel()), dtype=f64, device=device)
-        self.g_recv = torch.empty(int(ex.g_recv_pos.numel()), dtype=f64, device=device)
-        self.h_own = torch.zeros(max(ex.n_own_h, 1), dtype=f64, device=device)
-        self.g_own = torch.zeros(max(ex.n_own_g, 1), dtype=f64, device=device)
+        self.n_loc_h = int(n_loc_h if n_loc_h is not None else ex.h_send_idx.numel())
+        self.m = int(m if m is not None else ex.m_part[-1] - 1)
+        self.loc = torch.zeros(self.n_loc_h + self.m + 4, dtype=f64, device=device)
+        hs, gs = ex.h_send_idx.cpu().numpy(), ex.g_send_idx.cpu().numpy()
+        hr, gr = ex.h_recv_pos.cpu().numpy(), ex.g_recv_pos.cpu().numpy()
+        scal_pos = np.arange(4, dtype=np.int64) + self.n_loc_h + self.m
+        send_idx, self.send_splits, self.recv_splits = [], [], []
+        oh = og = 0
+        for r in range(P):
+            send_idx += [hs[oh:oh + ex.h_send_splits[r]], self.n_loc_h + gs[og:og + ex.g_send_splits[r]], scal_pos]
+            self.send_splits.append(ex.h_send_splits[r] + ex.g_send_splits[r] + 4)
+            oh += ex.h_send_splits[r]
+            og += ex.g_send_splits[r]
+        send_idx = np.concatenate(send_idx).astype(np.int64)
+        # owner side: destination (in `own`) of every received value, then CSR by destination
+        dest, oh, og = [], 0, 0
+        for r in range(P):
+            dest += [hr[oh:oh + ex.h_recv_splits[r]], ex.n_own_h + gr[og:og + ex.g_recv_splits[r]],
+                     ex.n_own_h + ex.n_own_g + np.arange(4, dtype=np.int64)]
+            self.recv_splits.append(ex.h_recv_splits[r] + ex.g_recv_splits[r] + 4)
+            oh += ex.h_recv_splits[r]
+            og += ex.g_recv_splits[r]
+        dest = np.concatenate(dest).astype(np.int64)
+        n_out = ex.n_own_h + ex.n_own_g + 4
+        order = np.argsort(dest, kind="stable")          # stable: contributions stay in source-rank order
+        ptr = np.zeros(n_out + 1, dtype=np.int64)
+        np.add.at(ptr, dest + 1, 1)
+        ptr = np.cumsum(ptr)
+        self.n_out = n_out
+        self.send = torch.empty(send_idx.size, dtype=f64, device=device)
+        self.recv = torch.empty(dest.size, dtype=f64, device=device)
+        self.own = torch.zeros(n_out, dtype=f64, device=device)
+        td = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(device)
+        self.send_idx64 = td(send_idx, torch.int64)
+        self.red_idx64 = td(order, torch.int64)
+        self.red_ptr64 = td(ptr, torch.int64)
         if ctx is not None:
-            self._h_send_idx32 = ex.h_send_idx.to(torch.int32)
-            self._h_recv_pos32 = ex.h_recv_pos.to(torch.int32)
-            self._g_send_idx32 = ex.g_send_idx.to(torch.int32)
-            self._g_recv_pos32 = ex.g_recv_pos.to(torch.int32)
+            assert self.loc.numel() < 2 ** 31 and dest.size < 2 ** 31
+            self.send_idx32 = td(send_idx, torch.int32)
+            self.red_idx32 = td(order, torch.int32)
+            self.red_ptr32 = td(ptr, torch.int32)
+        else:  # CPU: segment ids for index_add
+            self.red_seg = td(np.repeat(np.arange(n_out), np.diff(ptr)), torch.int64)
 
-    def _pack(self, src, idx64, idx32, out):
-        if out.numel() == 0:
-            return
-        if self.ctx is None:
-            torch.index_select(src, 0, idx64, out=out)
-        else:
-            self.ctx.gather_idx(src, idx32, out.numel(), out)
+    def views(self):
+        """(hval, grad, scal) windows of the local output buffer, to be passed to mgb_assemble."""
+        h, m = self.n_loc_h, self.m
+        return self.loc[:h], self.loc[h:h + m], self.loc[h + m:h + m + 4]
 
-    def _unpack(self, recv, pos64, pos32, splits, dst):
-        o = 0
-        for cnt in splits:  # fixed source-rank order; positions are unique within one source
-            if cnt:
-                if self.ctx is None:
-                    dst.index_add_(0, pos64[o:o + cnt], recv[o:o + cnt])
-                else:
-                    self.ctx.scatter_add_idx(recv[o:o + cnt], pos32[o:o + cnt], cnt, dst)
-            o += cnt
-
-    def exchange(self, hval_loc: Optional[torch.Tensor], grad_loc: Optional[torch.Tensor], scal: Optional[torch.Tensor]):
-        """Returns (H values of the owned rows, owned gradient block, reduced scalars)."""
+    def exchange(self):
+        """pack -> all_to_all -> owner-side sum.  Returns (H values of the owned rows, owned gradient
+        block, reduced scalars {f0, all_finite, <c,Dz>, nonfinite count})."""
         ex = self.ex
-        i32 = self.ctx is not None
-        if hval_loc is not None:
-            self._pack(hval_loc, ex.h_send_idx, self._h_send_idx32 if i32 else None, self.h_send)
-            dist.all_to_all_single(self.h_recv, self.h_send, output_split_sizes=ex.h_recv_splits,
-                                   input_split_sizes=ex.h_send_splits, group=self.group)
-            self.h_own.zero_()
-            self._unpack(self.h_recv, ex.h_recv_pos, self._h_recv_pos32 if i32 else None, ex.h_recv_splits, self.h_own)
-        if grad_loc is not None:
-            self._pack(grad_loc, ex.g_send_idx, self._g_send_idx32 if i32 else None, self.g_send)
-            dist.all_to_all_single(self.g_recv, self.g_send, output_split_sizes=ex.g_recv_splits,
-                                   input_split_sizes=ex.g_send_splits, group=self.group)
-            self.g_own.zero_()
-            self._unpack(self.g_recv, ex.g_recv_pos, self._g_recv_pos32 if i32 else None, ex.g_recv_splits, self.g_own)
-        if scal is not None:
-            # {f0, all_finite, <c,Dz>, nonfinite count}: sums, with all_finite recomputed from the count
-            dist.all_reduce(scal, op=dist.ReduceOp.SUM, group=self.group)
-            scal[1] = (scal[3] == 0).to(scal.dtype)
-        return self.h_own[: ex.n_own_h], self.g_own[: ex.n_own_g], scal
+        if self.ctx is None:
+            torch.index_select(self.loc, 0, self.send_idx64, out=self.send)
+        else:
+            self.ctx.gather_idx(self.loc, self.send_idx32, self.send.numel(), self.send)
+        dist.all_to_all_single(self.recv, self.send, output_split_sizes=self.recv_splits,
+                               input_split_sizes=self.send_splits, group=self.group)
+        if self.ctx is None:
+            self.own.zero_()
+            self.own.index_add_(0, self.red_seg, self.recv.index_select(0, self.red_idx64))
+        else:
+            self.ctx.segsum_idx(self.recv, self.red_ptr32, self.red_idx32, self.n_out, self.own)
+        h_own = self.own[: ex.n_own_h]
+        g_own = self.own[ex.n_own_h: ex.n_own_h + ex.n_own_g]
+        scal = self.own[ex.n_own_h + ex.n_own_g:]
+        scal[1] = (scal[3] == 0).to(scal.dtype)
+        return h_own, g_own, scal
 
 
 def element_rows(n: int, block: int, rank: int, nranks: int):

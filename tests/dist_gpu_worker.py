@@ -30,16 +30,14 @@ for gen, L, level in (("fem2d", 4, None), ("fem2d", 3, 1), ("fem1d", 5, None)):
     lrp, lci = plan.pattern()
     ex = mdist.build_exchange(rank, world, m, grp.astype(np.int64), gci.astype(np.int64), lrp.astype(np.int64),
                               lci.astype(np.int64), dev)
-    exch = mdist.Exchanger(ex, dev, ctx=ctx)
+    exch = mdist.Exchanger(ex, dev, ctx=ctx, n_loc_h=plan.nnzH, m=m)
     t = 0.8
     Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)[rows[0]:rows[1]]
     cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
     s_d = torch.from_numpy(pr["s"]).to(dev)
-    scal = torch.zeros(4, dtype=torch.float64, device=dev)
-    grad = torch.zeros(m, dtype=torch.float64, device=dev)
-    hval = torch.zeros(max(plan.nnzH, 1), dtype=torch.float64, device=dev)
+    hval, grad, scal = exch.views()
     plan.assemble(s_d, cm(Dz0), cm(pr["c"][rows[0]:rows[1]]), t, 7, scal, grad, hval)
-    h_own, g_own, scal = exch.exchange(hval, grad, scal)
+    h_own, g_own, scal = exch.exchange()
     Q = O.EuclidianPower(idx=pr["idx"], p=1.0)
     argsg = (pr["s"], pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
     Hg, gg, f0g = O.f2(*argsg).tocsr(), O.f1(*argsg), O.f0(*argsg)

@@ -45,10 +45,12 @@ def _worker(rank, world, port, gen, L, level, q):
         gl = O.f1(*args)
         f0l = O.f0(*args)
         rows = np.repeat(np.arange(m), np.diff(lrp))
-        hval_loc = torch.from_numpy(np.asarray(Hl[rows, lci]).ravel().copy())
-        scal = torch.tensor([f0l, 1.0, 0.0, 0.0], dtype=torch.float64)
-        exch = mdist.Exchanger(ex, torch.device("cpu"))
-        h_own, g_own, scal = exch.exchange(hval_loc, torch.from_numpy(gl.copy()), scal)
+        exch = mdist.Exchanger(ex, torch.device("cpu"), n_loc_h=lplan.nnzH, m=m)
+        hv, gv, sv = exch.views()
+        hv.copy_(torch.from_numpy(np.asarray(Hl[rows, lci]).ravel().copy()))
+        gv.copy_(torch.from_numpy(gl.copy()))
+        sv.copy_(torch.tensor([f0l, 1.0, 0.0, 0.0], dtype=torch.float64))
+        h_own, g_own, scal = exch.exchange()
         # global oracle
         argsg = (pr["s"], pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
         Hg = O.f2(*argsg).tocsr()
@@ -59,6 +61,7 @@ def _worker(rank, world, port, gen, L, level, q):
         errg = np.abs(g_own.numpy() - gg[lo:hi]).max() / np.abs(gg).max()
         errf = abs(float(scal[0]) - O.f0(*argsg)) / abs(O.f0(*argsg))
         cover = int(sum(ex.h_recv_splits))
+        assert float(scal[1]) == 1.0
         q.put((rank, float(errH), float(errg), float(errf), cover, (row0, row1), (lo, hi)))
         dist.destroy_process_group()
     except Exception as exc:  # pragma: no cover
