@@ -96,6 +96,17 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic(kernel: str, L: int):
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as fh:
+            d = json.load(fh)
+        return d.get(f"L{L}", {}).get(kernel)
+    except Exception:
+        return None
+
+
 def cpu_assembly_sample(pr, t, reps):
     """CPU oracle restatement of one assembly (f1 + f2 + f0), `reps` times, one core; ms per assembly."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -370,8 +381,8 @@ def main():
                     "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned",
                     "c_abi_pageable_ms": e2e_pageable_ms},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "element_kernel" if args.two_stage else "patch_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "patch_kernel" if (os.environ.get("MGB_PATCH") and not args.two_stage) else "element_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": ncu_traffic("element_kernel", args.L), "peak_source": peak_src,
                          "algorithmic_bytes": int(alg_elem), "kernel_ms": ms_elem,
                          "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all,
                                       "frac": ach_all / peak, "gather_ms": ms_gather}},
