@@ -3,8 +3,8 @@
 //   csr_apply_kernel    Dz = Dz0 + E_k s            (apply_D, reference test/test_apply_d.jl:44)
 //   csr_barrier_kernel  w.*F1, w.*F2, objective    (map_rows src:161-170 + amgb_diag src:137-147)
 //   csr_grad_kernel     g = sum_k E_k' (w.*(y1_k + t c_k))   (gather over the stored transpose)
-//   csr_hess_kernel     warp per output row: numeric-only replay of sum_jk E_j' diag E_k on the
-//                       frozen pattern, accumulators in shared memory, no atomics
+//   csr_hess_kernel     thread per output entry: numeric-only replay of sum_jk E_j' diag E_k on the
+//                       frozen pattern from precomputed (coefficient, V index) product lists, no atomics
 //                       (test/test_map_rows_compare.jl:102-123 with R folded in: E_k = D_k R)
 #pragma once
 #include <cuda_runtime.h>
@@ -34,12 +34,9 @@ struct CsrDev {
     std::vector<void*> owned;  // device allocations
     CsrOpDev E[8], Et[8];
     const int32_t* h_rowptr = nullptr;
-    const int64_t* seg_ptr = nullptr;
-    const int32_t* seg_i = nullptr;
-    const int32_t* seg_pair = nullptr;
-    const double* seg_alpha = nullptr;
-    const int64_t* seg_dst = nullptr;
-    const int32_t* dst = nullptr;
+    const int64_t* prod_ptr = nullptr;
+    const double* prod_coef = nullptr;
+    const int32_t* prod_v = nullptr;
     double* Dz = nullptr;    // nloc x ND
     double* gy = nullptr;    // nloc x ND
     double* V = nullptr;     // nloc x ND^2
@@ -63,18 +60,15 @@ static const T* csr_up(CsrDev& d, const std::vector<T>& h, cudaStream_t st, size
 static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, cudaStream_t st) {
     size_t bytes = 0;
     d.ND = cp.ND; d.nloc = cp.nloc; d.m = cp.m; d.nnzH = (int64_t)cp.h_colidx.size();
-    d.nprod = (int64_t)cp.dst.size(); d.max_row = cp.max_row; d.bar = bar;
+    d.nprod = (int64_t)cp.prod_coef.size(); d.max_row = cp.max_row; d.bar = bar;
     for (int k = 0; k < cp.ND; ++k) {
         d.E[k] = {csr_up(d, cp.E[k].ptr, st, bytes), csr_up(d, cp.E[k].idx, st, bytes), csr_up(d, cp.E[k].val, st, bytes)};
         d.Et[k] = {csr_up(d, cp.Et[k].ptr, st, bytes), csr_up(d, cp.Et[k].idx, st, bytes), csr_up(d, cp.Et[k].val, st, bytes)};
     }
     d.h_rowptr = csr_up(d, cp.h_rowptr, st, bytes);
-    d.seg_ptr = csr_up(d, cp.seg_ptr, st, bytes);
-    d.seg_i = csr_up(d, cp.seg_i, st, bytes);
-    d.seg_pair = csr_up(d, cp.seg_pair, st, bytes);
-    d.seg_alpha = csr_up(d, cp.seg_alpha, st, bytes);
-    d.seg_dst = csr_up(d, cp.seg_dst, st, bytes);
-    d.dst = csr_up(d, cp.dst, st, bytes);
+    d.prod_ptr = csr_up(d, cp.prod_ptr, st, bytes);
+    d.prod_coef = csr_up(d, cp.prod_coef, st, bytes);
+    d.prod_v = csr_up(d, cp.prod_v, st, bytes);
     auto scratch = [&](size_t count) {
         double* p = nullptr;
         if (cudaMalloc(&p, std::max<size_t>(count, 1) * 8) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (csr scratch)");
@@ -87,7 +81,6 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     d.V = scratch((size_t)cp.nloc * cp.ND * cp.ND);
     d.nblk = (cp.nloc + 255) / 256;
     d.part = scratch((size_t)d.nblk * 4);
-    if ((size_t)cp.max_row * 8 * 4 > 200 * 1024) throw std::runtime_error("csr path: Hessian row too long for shared-memory accumulation");
     return bytes;
 }
 
@@ -210,48 +203,21 @@ __global__ void __launch_bounds__(256) csr_grad_kernel(const CsrGradParams P) {
     P.grad[a] = acc;
 }
 
-struct CsrHessParams {
-    CsrOpDev E[8];
-    int ND, max_row;
-    int64_t n, m;
-    const int32_t* h_rowptr;
-    const int64_t* seg_ptr;
-    const int32_t* seg_i;
-    const int32_t* seg_pair;
-    const double* seg_alpha;
-    const int64_t* seg_dst;
-    const int32_t* dst;
-    const double* V;
-    double* hval;
-};
-
-// one warp per output row; lanes run over the entries of one E_kb row at a time (distinct
-// destinations inside a segment), segments are serialised -> fixed summation order, no atomics
-__global__ void __launch_bounds__(128) csr_hess_kernel(const CsrHessParams P) {
-    extern __shared__ double acc_all[];
-    const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t a = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    if (a >= P.m) return;
-    double* acc = acc_all + (size_t)wib * P.max_row;
-    const int h0 = P.h_rowptr[a], hl = P.h_rowptr[a + 1] - h0;
-    for (int j = lane; j < hl; j += 32) acc[j] = 0.0;
-    __syncwarp();
-    const int64_t g0 = P.seg_ptr[a], g1 = P.seg_ptr[a + 1];
-    for (int64_t g = g0; g < g1; ++g) {
-        const int32_t i = P.seg_i[g];
-        const int pair = P.seg_pair[g];
-        const int kb = pair % P.ND;
-        const double coef = P.seg_alpha[g] * P.V[(int64_t)pair * P.n + i];
-        const int64_t r0 = P.E[kb].ptr[i];
-        const int len = (int)(P.E[kb].ptr[i + 1] - r0);
-        const int64_t d0 = P.seg_dst[g];
-        for (int r = lane; r < len; r += 32) acc[P.dst[d0 + r]] = fma(coef, P.E[kb].val[r0 + r], acc[P.dst[d0 + r]]);
-        __syncwarp();
-    }
-    for (int j = lane; j < hl; j += 32) P.hval[h0 + j] = acc[j];
+// numeric-only triple product on the frozen pattern: one lane per output entry, eight entries per
+// warp-iteration group; every entry sums its precomputed products coef * V in list order (no atomics,
+// bit-reproducible).  coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
+__global__ void __launch_bounds__(256) csr_hess_kernel(int64_t nnzH, const int64_t* __restrict__ prod_ptr,
+                                                       const double* __restrict__ coef, const int32_t* __restrict__ vsrc,
+                                                       const double* __restrict__ V, double* __restrict__ hval) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nnzH) return;
+    const int64_t r0 = __ldg(&prod_ptr[t]), r1 = __ldg(&prod_ptr[t + 1]);
+    double acc = 0.0;
+    for (int64_t r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), V[__ldg(&vsrc[r])], acc);
+    hval[t] = acc;
 }
 
-__global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
+static __global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
                                                             double* __restrict__ scal) {
     __shared__ double sh[3][256];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
@@ -313,16 +279,8 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         csr_grad_kernel<<<(unsigned)((d.m + 255) / 256), 256, 0, st>>>(P);
         ++launches;
     }
-    if (flags & 4) {
-        CsrHessParams P{};
-        for (int k = 0; k < d.ND; ++k) P.E[k] = d.E[k];
-        P.ND = d.ND; P.max_row = d.max_row; P.n = n; P.m = d.m; P.h_rowptr = d.h_rowptr; P.seg_ptr = d.seg_ptr;
-        P.seg_i = d.seg_i; P.seg_pair = d.seg_pair; P.seg_alpha = d.seg_alpha; P.seg_dst = d.seg_dst; P.dst = d.dst;
-        P.V = d.V; P.hval = hval;
-        const size_t smem = (size_t)4 * d.max_row * sizeof(double);
-        if (smem > 48 * 1024)
-            csr_check(cudaFuncSetAttribute(csr_hess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
-        csr_hess_kernel<<<(unsigned)((d.m + 3) / 4), 128, smem, st>>>(P);
+    if ((flags & 4) && d.nnzH > 0) {
+        csr_hess_kernel<<<(unsigned)((d.nnzH + 255) / 256), 256, 0, st>>>(d.nnzH, d.prod_ptr, d.prod_coef, d.prod_v, d.V, hval);
         ++launches;
     }
     scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);

@@ -440,7 +440,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             mgb::build_csr_plan(Dh, Rh, cp, want_hess);
             pl->nnzH = (int64_t)cp.h_colidx.size();
             pl->h_rowptr = cp.h_rowptr; pl->h_colidx = cp.h_colidx;
-            pl->n_hcontrib = (int64_t)cp.dst.size();
+            pl->n_hcontrib = (int64_t)cp.prod_coef.size();
             if (!host_only) {
                 pl->dev_bytes = mgb::csr_upload(cp, pl->bar, pl->csr, st) + pl->d_w.bytes();
                 pl->d_scal_tmp.alloc(4);

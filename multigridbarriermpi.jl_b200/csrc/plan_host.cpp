@@ -507,8 +507,10 @@ void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P,
     }
     // pattern: row a = union over (ka, i in column a of E_ka) of union_kb supp(E_kb[i,:])
     P.h_rowptr.assign(m + 1, 0);
-    P.seg_ptr.assign(m + 1, 0);
+    P.prod_ptr.assign(1, 0);
+    if ((int64_t)ND * ND * P.nloc > INT32_MAX) throw std::runtime_error("csr path: V index exceeds int32");
     std::vector<int32_t> mark(m, -1), pos(m, 0), cols;
+    std::vector<std::vector<std::pair<double, int32_t>>> rowprod;
     for (int64_t a = 0; a < m && want_hessian; ++a) {
         cols.clear();
         for (int ka = 0; ka < ND; ++ka)
@@ -524,20 +526,21 @@ void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P,
         for (size_t t = 0; t < cols.size(); ++t) { pos[cols[t]] = (int32_t)t; P.h_colidx.push_back(cols[t]); }
         P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
         P.max_row = std::max<int32_t>(P.max_row, (int32_t)cols.size());
+        if (rowprod.size() < cols.size()) rowprod.resize(cols.size());
+        for (size_t t = 0; t < cols.size(); ++t) rowprod[t].clear();
         for (int ka = 0; ka < ND; ++ka)
             for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {
                 const int32_t i = P.Et[ka].idx[p];
-                for (int kb = 0; kb < ND; ++kb) {
-                    const int64_t r0 = P.E[kb].ptr[i], r1 = P.E[kb].ptr[i + 1];
-                    if (r1 == r0) continue;
-                    P.seg_i.push_back(i);
-                    P.seg_pair.push_back(ka * ND + kb);
-                    P.seg_alpha.push_back(P.Et[ka].val[p]);
-                    P.seg_dst.push_back((int64_t)P.dst.size());
-                    for (int64_t r = r0; r < r1; ++r) P.dst.push_back(pos[P.E[kb].idx[r]]);
-                }
+                const double alpha = P.Et[ka].val[p];
+                for (int kb = 0; kb < ND; ++kb)
+                    for (int64_t r = P.E[kb].ptr[i]; r < P.E[kb].ptr[i + 1]; ++r)
+                        rowprod[pos[P.E[kb].idx[r]]].emplace_back(alpha * P.E[kb].val[r],
+                                                                  (int32_t)(((int64_t)ka * ND + kb) * P.nloc + i));
             }
-        P.seg_ptr[a + 1] = (int64_t)P.seg_i.size();
+        for (size_t t = 0; t < cols.size(); ++t) {
+            for (auto& pr : rowprod[t]) { P.prod_coef.push_back(pr.first); P.prod_v.push_back(pr.second); }
+            P.prod_ptr.push_back((int64_t)P.prod_coef.size());
+        }
     }
 }
 

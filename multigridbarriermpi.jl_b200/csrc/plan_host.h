@@ -105,13 +105,12 @@ struct CsrPlan {
     std::vector<HostCSR> E;   // E_k = D_k R   (nloc x m)
     std::vector<HostCSR> Et;  // transposes   (m x nloc)
     std::vector<int32_t> h_rowptr, h_colidx;
-    // warp-per-row replay: for output row a, segments (k_a, entry in column a of E_ka) x k_b
-    std::vector<int64_t> seg_ptr;   // m+1 -> segments of row a
-    std::vector<int32_t> seg_i;     // quadrature row i
-    std::vector<int32_t> seg_pair;  // ka*ND+kb
-    std::vector<double> seg_alpha;  // E_ka[i,a]
-    std::vector<int64_t> seg_dst;   // start into dst (length = nnz of row i of E_kb)
-    std::vector<int32_t> dst;       // position inside H row a
+    // numeric-only replay of sum_jk E_j' diag(V_jk) E_k on the frozen pattern: for output entry t the
+    // products  coef[r] * V[vsrc[r]],  r in [prod_ptr[t], prod_ptr[t+1]),  coef = E_ka[i,a]*E_kb[i,b],
+    // vsrc = (ka*ND+kb)*nloc + i, listed in the fixed order (ka, i, kb)
+    std::vector<int64_t> prod_ptr;
+    std::vector<double> prod_coef;
+    std::vector<int32_t> prod_v;
     int32_t max_row = 0;
 };
 
