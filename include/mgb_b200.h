@@ -48,6 +48,11 @@ typedef struct {
     int32_t idx[8];
     double p;
     int32_t slack;
+    /* optional second cone (intersection of two convex sets, e.g. upstream parabolic_solve:
+     * {s1 >= u^2} with idx2 = (u.id, s1.id), p2 = 2, next to {s2 >= |grad u|^p}); nidx2 = 0: none */
+    int32_t nidx2;
+    int32_t idx2[8];
+    double p2;
 } mgb_barrier;
 
 #define MGB_BARRIER_EUCLIDIAN_POWER 1

@@ -283,6 +283,17 @@ def amgb(g: Geometry, **kwargs) -> solver.AMGBSOL:
     return solver.AMGBSOL(z, sol.SOL_feasibility, sol.SOL_main, sol.log, g, sol.stats)
 
 
+def parabolic_solve(g: Geometry, **kwargs) -> solver.ParabolicSOL:
+    """parabolic_solve on an HPC-typed geometry (reference test/test_parabolic.jl:48): h, t1, p as upstream;
+    snapshots come back as HPCMatrix (n x 3: u, s1, s2)."""
+    be = g.x.backend if isinstance(g.x, HPCMatrix) else backend_cuda()
+    g_native = mpi_to_native(g) if isinstance(g.x, HPCMatrix) else g
+    sol = solver.parabolic_solve(g_native, device=be.index, **kwargs)
+    if isinstance(g.x, HPCMatrix):
+        return solver.ParabolicSOL(g, sol.ts, [HPCMatrix(u, be, g.x.row_partition) for u in sol.u])
+    return sol
+
+
 def fem1d_mpi_solve(T=np.float64, **kwargs):
     return amgb(fem1d_mpi(T, **kwargs), **kwargs)
 

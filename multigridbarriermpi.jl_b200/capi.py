@@ -41,7 +41,7 @@ class _Csr(C.Structure):
 
 class _Barrier(C.Structure):
     _fields_ = [("kind", C.c_int32), ("nidx", C.c_int32), ("idx", C.c_int32 * 8), ("p", C.c_double),
-                ("slack", C.c_int32)]
+                ("slack", C.c_int32), ("nidx2", C.c_int32), ("idx2", C.c_int32 * 8), ("p2", C.c_double)]
 
 
 _lib = None
@@ -189,7 +189,8 @@ class Plan:
             "slots_per_element", "hess_contribs", "grad_contribs", "plan_bytes", "N", "nu", "alg_bytes"]
 
     def __init__(self, ctx: Context, D: Sequence[sp.spmatrix], R: sp.spmatrix, x: np.ndarray, w: np.ndarray,
-                 idx: Sequence[int], p: float, slack: bool = False, rows=None, force_path: int = 0):
+                 idx: Sequence[int], p: float, slack: bool = False, rows=None, force_path: int = 0,
+                 idx2: Optional[Sequence[int]] = None, p2: float = 2.0):
         lib = load()
         self.ctx = ctx
         n = D[0].shape[0]
@@ -200,6 +201,10 @@ class Plan:
         bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
         for j, v in enumerate(idx):
             bar.idx[j] = int(v)
+        if idx2:
+            bar.nidx2, bar.p2 = len(idx2), float(p2)
+            for j, v in enumerate(idx2):
+                bar.idx2[j] = int(v)
         x = np.asfortranarray(x, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
         row0, row1 = (0, n) if rows is None else rows

@@ -107,6 +107,9 @@ __global__ void __launch_bounds__(256) csr_apply_kernel(const CsrApplyParams P) 
 struct CsrBarrierParams {
     int ND, nq, slack;
     int idx[8];
+    int nq2;       // second cone: number of q columns (-1: no second cone)
+    int idx2[8];
+    double p2;
     int64_t n;
     double p, t;
     const double* Dz;
@@ -124,46 +127,59 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
     const int64_t n = P.n;
     double v0 = 0.0, v1 = 0.0, v2 = 0.0;
     if (act) {
-        double q[3] = {0.0, 0.0, 0.0};
-        for (int j = 0; j < P.nq; ++j) q[j] = P.Dz[(int64_t)P.idx[j] * n + i];
-        const int scol = P.idx[P.nq];
-        double s = P.Dz[(int64_t)scol * n + i];
-        if (P.slack) s += P.Dz[(int64_t)(P.ND - 1) * n + i];
-        BarrierOut bo;
-        barrier_eval<3, true, true>(q, s, P.p, bo);
-        double tau1 = 1.0;
-        if (P.slack) {  // slack bounded below by -log(1 + tau)
-            tau1 = 1.0 + P.Dz[(int64_t)(P.ND - 1) * n + i];
-            bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
-            bo.feasible = bo.feasible && (tau1 > 0.0);
-        }
         const double wi = P.w[i];
+        const int ND = P.ND;
         double cd = 0.0;
-        for (int k = 0; k < P.ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
-        v0 = P.want_f ? wi * bo.F : 0.0;
+        for (int k = 0; k < ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
         v1 = wi * cd;
-        v2 = bo.feasible ? 0.0 : 1.0;
-        const int ns = P.slack ? 2 : 1;
-        const int scols[2] = {scol, P.ND - 1};
-        if (P.want_g) {
-            for (int k = 0; k < P.ND; ++k) P.gy[(int64_t)k * n + i] = wi * (P.t * P.c[(int64_t)k * n + i]);
-            for (int j = 0; j < P.nq; ++j) P.gy[(int64_t)P.idx[j] * n + i] += wi * bo.gq[j];
-            for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * (bo.gs - (r == 1 ? 1.0 / tau1 : 0.0));
-        }
-        if (P.want_h) {
-            const int ND = P.ND;
+        if (P.want_g)
+            for (int k = 0; k < ND; ++k) P.gy[(int64_t)k * n + i] = wi * (P.t * P.c[(int64_t)k * n + i]);
+        if (P.want_h)
             for (int cidx = 0; cidx < ND * ND; ++cidx) P.V[(int64_t)cidx * n + i] = 0.0;
-            for (int j = 0; j < P.nq; ++j) {
-                for (int j2 = 0; j2 < P.nq; ++j2) P.V[(int64_t)(P.idx[j] * ND + P.idx[j2]) * n + i] = wi * bo.Hqq[j][j2];
-                for (int r = 0; r < ns; ++r) {
-                    P.V[(int64_t)(P.idx[j] * ND + scols[r]) * n + i] = wi * bo.Hqs[j];
-                    P.V[(int64_t)(scols[r] * ND + P.idx[j]) * n + i] = wi * bo.Hqs[j];
-                }
+        double Fsum = 0.0;
+        bool feas = true;
+        const int ncones = (P.nq2 >= 0) ? 2 : 1;
+        for (int cone = 0; cone < ncones; ++cone) {
+            const int nq = cone ? P.nq2 : P.nq;
+            const int* idx = cone ? P.idx2 : P.idx;
+            const double pp = cone ? P.p2 : P.p;
+            double q[3] = {0.0, 0.0, 0.0};
+            for (int j = 0; j < nq; ++j) q[j] = P.Dz[(int64_t)idx[j] * n + i];
+            const int scol = idx[nq];
+            double s = P.Dz[(int64_t)scol * n + i];
+            const bool sl = P.slack && cone == 0;
+            if (sl) s += P.Dz[(int64_t)(ND - 1) * n + i];
+            BarrierOut bo;
+            barrier_eval<3, true, true>(q, s, pp, bo);
+            double tau1 = 1.0;
+            if (sl) {  // slack bounded below by -log(1 + tau)
+                tau1 = 1.0 + P.Dz[(int64_t)(ND - 1) * n + i];
+                bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
+                bo.feasible = bo.feasible && (tau1 > 0.0);
             }
-            for (int r = 0; r < ns; ++r)
-                for (int r2 = 0; r2 < ns; ++r2)
-                    P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] = wi * (bo.Hss + ((r == 1 && r2 == 1) ? 1.0 / (tau1 * tau1) : 0.0));
+            Fsum += bo.F;
+            feas = feas && bo.feasible;
+            const int ns = sl ? 2 : 1;
+            const int scols[2] = {scol, ND - 1};
+            if (P.want_g) {
+                for (int j = 0; j < nq; ++j) P.gy[(int64_t)idx[j] * n + i] += wi * bo.gq[j];
+                for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * (bo.gs - (r == 1 ? 1.0 / tau1 : 0.0));
+            }
+            if (P.want_h) {
+                for (int j = 0; j < nq; ++j) {
+                    for (int j2 = 0; j2 < nq; ++j2) P.V[(int64_t)(idx[j] * ND + idx[j2]) * n + i] += wi * bo.Hqq[j][j2];
+                    for (int r = 0; r < ns; ++r) {
+                        P.V[(int64_t)(idx[j] * ND + scols[r]) * n + i] += wi * bo.Hqs[j];
+                        P.V[(int64_t)(scols[r] * ND + idx[j]) * n + i] += wi * bo.Hqs[j];
+                    }
+                }
+                for (int r = 0; r < ns; ++r)
+                    for (int r2 = 0; r2 < ns; ++r2)
+                        P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] += wi * (bo.Hss + ((r == 1 && r2 == 1) ? 1.0 / (tau1 * tau1) : 0.0));
+            }
         }
+        v0 = P.want_f ? wi * Fsum : 0.0;
+        v2 = feas ? 0.0 : 1.0;
     }
 #pragma unroll
     for (int mk = 16; mk >= 1; mk >>= 1) {
@@ -267,6 +283,8 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         CsrBarrierParams P{};
         P.ND = d.ND; P.nq = d.bar.nidx - 1; P.slack = d.bar.slack;
         for (int j = 0; j < d.bar.nidx; ++j) P.idx[j] = d.bar.idx[j];
+        P.nq2 = d.bar.nidx2 > 0 ? d.bar.nidx2 - 1 : -1; P.p2 = d.bar.p2;
+        for (int j = 0; j < d.bar.nidx2; ++j) P.idx2[j] = d.bar.idx2[j];
         P.n = n; P.p = d.bar.p; P.t = t; P.Dz = Dz; P.c = c; P.w = w; P.gy = d.gy; P.V = d.V; P.part = d.part;
         P.want_f = (flags & 1) ? 1 : 0; P.want_g = (flags & 2) ? 1 : 0; P.want_h = (flags & 4) ? 1 : 0;
         csr_barrier_kernel<<<(unsigned)d.nblk, 256, 0, st>>>(P);

@@ -340,6 +340,16 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             if (barrier->idx[j] < 0 || barrier->idx[j] >= nD) return fail("mgb_plan_create: barrier idx outside 0..nD-1");
             pl->bar.idx[j] = barrier->idx[j];
         }
+        if (barrier->nidx2 < 0 || barrier->nidx2 > 4) return fail("mgb_plan_create: second cone needs 0 or 2..4 idx entries");
+        if (barrier->nidx2 > 0) {
+            if (barrier->nidx2 < 2 || !(barrier->p2 >= 1.0)) return fail("mgb_plan_create: bad second cone");
+            if (barrier->slack) return fail("mgb_plan_create: slack variant supports a single cone");
+            pl->bar.nidx2 = barrier->nidx2; pl->bar.p2 = barrier->p2;
+            for (int j = 0; j < barrier->nidx2; ++j) {
+                if (barrier->idx2[j] < 0 || barrier->idx2[j] >= nD) return fail("mgb_plan_create: barrier idx2 outside 0..nD-1");
+                pl->bar.idx2[j] = barrier->idx2[j];
+            }
+        }
         std::vector<mgb::HostCSR> Dh(nD);
         int64_t nnzD = 0;
         for (int k = 0; k < nD; ++k) {

@@ -149,6 +149,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     const int nu = (int)(N / n_global);
     const bool slack = bar.slack != 0;
     const int dim = ND - 2 - (slack ? 1 : 0);
+    if (bar.nidx2 > 0) { P.why = "two-cone barrier: general CSR kernels"; return; }
     if (bar.kind != 1 || dim < 1 || dim > 3 || nu != 2 + (slack ? 1 : 0)) { P.why = "not the p-Laplace operator table"; return; }
     if (bar.nidx != dim + 1) { P.why = "barrier idx does not select (derivatives, s)"; return; }
     for (int j = 0; j <= dim; ++j)

@@ -92,6 +92,8 @@ struct BarrierDesc {
     int kind = 1, nidx = 0, idx[8] = {0};
     double p = 1.0;
     int slack = 0;
+    int nidx2 = 0, idx2[8] = {0};  // optional second cone (intersection)
+    double p2 = 2.0;
 };
 
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.

@@ -40,7 +40,7 @@ class LevelState:
 
     def __init__(self, prob: "DeviceProblem", J: int):
         self.plan = capi.Plan(prob.ctx, prob.M.D, prob.M.R_fine[J], prob.M.x, prob.M.w, prob.idx, prob.p,
-                              slack=prob.slack)
+                              slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
         dev = prob.device
         m, nnz = self.plan.m, self.plan.nnzH
         f64 = torch.float64
@@ -63,8 +63,9 @@ class DeviceProblem:
     """One AMG hierarchy resident on one GPU."""
 
     def __init__(self, M: AMG, idx: Sequence[int], p: float, slack: bool = False, device: int = 0,
-                 ctx: Optional[capi.Context] = None):
+                 ctx: Optional[capi.Context] = None, idx2: Optional[Sequence[int]] = None, p2: float = 2.0):
         self.M, self.idx, self.p, self.slack = M, list(idx), float(p), bool(slack)
+        self.idx2, self.p2 = (list(idx2) if idx2 else None), float(p2)
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.current_stream(self.device)
@@ -74,7 +75,7 @@ class DeviceProblem:
         self.levels: Dict[int, LevelState] = {}
         # operator-only plan with R = I: Dz0 = D z for any fine-space z
         self.op_plan = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
-                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN)
+                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2)
         self.Dz0 = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)  # column-major n x nD
         self.stats = dict(assemblies=0, f0_evals=0, solve_s=0.0, assemble_s=0.0)
 
@@ -281,3 +282,60 @@ def feasibility_phase(geom, prob: DeviceProblem, z, cmat, state_variables, D, to
         t *= kappa
         if t > 1.0 / tol:
             raise RuntimeError("feasibility phase failed")
+
+
+# --------------------------------------------------------------------------------------------------
+# parabolic_solve (upstream; reference test/test_parabolic.jl:48, docs/src/guide.md:358-380): implicit
+# Euler for the p-Laplace gradient flow; every step is a barrier solve on the same geometry, so the
+# level plans (symbolic phase) are built once and reused for all steps - the "pattern reuse" config.
+# --------------------------------------------------------------------------------------------------
+PARABOLIC_STATE = (("u", "dirichlet"), ("s1", "full"), ("s2", "full"))
+
+
+def parabolic_tables(dim: int):
+    D = [("u", "id")] + [("u", "d" + "xyz"[k]) for k in range(dim)] + [("s1", "id"), ("s2", "id")]
+    return D, [0, dim + 1], list(range(1, dim + 1)) + [dim + 2]
+
+
+def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float = 1.0, p: float = 1.0, f1=None, g=None,
+                    tol: float = math.sqrt(EPS), t: float = 0.1, kappa: float = 10.0, maxit: int = 50,
+                    verbose: bool = False, device: int = 0, solve_fn: Callable = solve, **_ignored) -> ParabolicSOL:
+    dim = geom.dim
+    f1 = (lambda x: 0.5) if f1 is None else f1
+    g = (lambda tt, x: x[0]) if g is None else g
+    Dt, idxA, idxB = parabolic_tables(dim)
+    M = amg_helper(geom, PARABOLIC_STATE, Dt)
+    n = geom.x.shape[0]
+    # cone 1 of the plan = (grad u, s2) with p, cone 2 = (u, s1) with p = 2
+    prob = DeviceProblem(M, idxB, p, slack=False, device=device, idx2=idxA, p2=2.0)
+    dev = prob.device
+    ts = np.arange(t0, t1 + 1e-12 * max(1.0, abs(t1)), h)
+    S = geom.subspaces["dirichlet"][-1].tocsr()
+    bnd = np.flatnonzero(np.diff(S.indptr) == 0)
+    f1v = np.array([f1(geom.x[i]) for i in range(n)], dtype=float)
+    max_newton = int(math.ceil(math.log2(1.0 / tol) + 2))
+    z = torch.zeros(3 * n, dtype=torch.float64, device=dev)
+    Dz = torch.zeros((len(Dt), n), dtype=torch.float64, device=dev)
+
+    def feasible_start(u_host):
+        z.zero_()
+        z[:n] = torch.from_numpy(u_host).to(dev)
+        prob.apply_D(z, Dz)
+        z[n:2 * n] = Dz[0] ** 2 + 1.0
+        z[2 * n:] = (Dz[1:dim + 1] ** 2).sum(dim=0) ** (p / 2.0) + 1.0
+
+    u = np.array([g(ts[0], geom.x[i]) for i in range(n)], dtype=float)
+    feasible_start(u)
+    snaps = [z.cpu().numpy().reshape(n, 3, order="F").copy()]
+    for k in range(len(ts) - 1):
+        uk = snaps[-1][:, 0]
+        u0 = uk.copy()
+        u0[bnd] = np.array([g(ts[k + 1], geom.x[i]) for i in bnd], dtype=float)
+        feasible_start(u0)
+        c = np.zeros((n, len(Dt)))
+        c[:, 0] = h * f1v - uk
+        c[:, dim + 1] = 0.5
+        c[:, dim + 2] = h / p
+        amgb_core(prob, z, _cm(c, dev), tol, t, kappa, maxit, max_newton, verbose, solve_fn)
+        snaps.append(z.cpu().numpy().reshape(n, 3, order="F").copy())
+    return ParabolicSOL(geom, ts, snaps)

@@ -135,6 +135,22 @@ class EuclidianPower:
         return H
 
 
+@dataclass
+class Intersection:
+    """Intersection of convex sets: the barriers add (upstream ``intersect`` / the parabolic problem's
+    {s1 >= u^2} with {s2 >= |grad u|^p})."""
+    sets: Sequence
+
+    def F(self, x, y):
+        return sum(Q.F(x, y) for Q in self.sets)
+
+    def F1(self, x, y):
+        return sum(Q.F1(x, y) for Q in self.sets)
+
+    def F2(self, x, y):
+        return sum(Q.F2(x, y) for Q in self.sets)
+
+
 # --------------------------------------------------------------------------------------
 # f0 / f1 / f2 : the Newton-step assembly.  Loop order follows the reference's restatement of
 # the upstream ``barrier`` body: test/test_map_rows_compare.jl:102-123 (Hessian),
@@ -408,3 +424,74 @@ def feasibility_phase(geom, M, Q, z, c, state_variables, D, tol, t0, kappa, maxi
         t *= kappa
         if t > 1.0 / tol:
             raise RuntimeError("feasibility phase failed")
+
+
+# --------------------------------------------------------------------------------------
+# parabolic_solve (upstream; reached through test/test_parabolic.jl:48 and docs/src/guide.md:358-380):
+# implicit Euler for the p-Laplace gradient flow  u_t - div(|grad u|^(p-2) grad u) = -f1.
+# Each step minimises  int (1/2) s1 + (h/p) s2 + (h f1 - u_k) u   s.t.  s1 >= u^2, s2 >= |grad u|^p
+# with the barrier method on the same geometry (identical sparsity every step).  Body not in the
+# reference: restated.  The start of every step is made strictly feasible by construction
+# (s1 = u^2 + 1, s2 = |grad u|^p + 1), so no feasibility phase is needed.
+# --------------------------------------------------------------------------------------
+
+PARABOLIC_STATE = (("u", "dirichlet"), ("s1", "full"), ("s2", "full"))
+
+
+def parabolic_tables(dim):
+    D = [("u", "id")] + [("u", "d" + "xyz"[k]) for k in range(dim)] + [("s1", "id"), ("s2", "id")]
+    idxA = [0, dim + 1]                              # (u, s1), p = 2
+    idxB = list(range(1, dim + 1)) + [dim + 2]       # (grad u, s2), p
+    return D, idxA, idxB
+
+
+def boundary_mask(geom):
+    """broken nodes whose Dirichlet row is empty = boundary nodes"""
+    S = geom.subspaces["dirichlet"][-1].tocsr()
+    return np.diff(S.indptr) == 0
+
+
+@dataclass
+class ParabolicSOL:
+    geometry: object
+    ts: np.ndarray
+    u: list
+
+
+def parabolic_feasible_start(M, u, dim, p):
+    n = M.x.shape[0]
+    z = np.concatenate([u, np.zeros(2 * n)])
+    Dz = apply_D(M.D, z)
+    s1 = Dz[:, 0] ** 2 + 1.0
+    s2 = np.sum(Dz[:, 1:dim + 1] ** 2, axis=1) ** (p / 2.0) + 1.0
+    return np.concatenate([u, s1, s2])
+
+
+def parabolic_solve(geom, h=0.2, t0=0.0, t1=1.0, p=1.0, f1=None, g=None, tol=math.sqrt(EPS), t=0.1, kappa=10.0,
+                    maxit=50, verbose=False, solve_fn=solve):
+    dim = geom.x.shape[1]
+    f1 = (lambda x: 0.5) if f1 is None else f1
+    g = (lambda tt, x: x[0]) if g is None else g
+    Dt, idxA, idxB = parabolic_tables(dim)
+    M = amg_helper(geom, PARABOLIC_STATE, Dt)
+    Q = Intersection([EuclidianPower(idx=idxA, p=2.0), EuclidianPower(idx=idxB, p=float(p))])
+    n = geom.x.shape[0]
+    ts = np.arange(t0, t1 + 1e-12 * max(1.0, abs(t1)), h)
+    bnd = boundary_mask(geom)
+    f1v = np.array([f1(geom.x[i]) for i in range(n)], dtype=float)
+    u = np.array([g(ts[0], geom.x[i]) for i in range(n)], dtype=float)
+    z = parabolic_feasible_start(M, u, dim, p)
+    snaps = [z.reshape(n, 3, order="F").copy()]
+    max_newton = int(math.ceil(math.log2(1.0 / tol) + 2))
+    for k in range(len(ts) - 1):
+        uk = snaps[-1][:, 0]
+        u0 = uk.copy()
+        u0[bnd] = np.array([g(ts[k + 1], geom.x[i]) for i in np.flatnonzero(bnd)], dtype=float)
+        z = parabolic_feasible_start(M, u0, dim, p)
+        c = np.zeros((n, len(Dt)))
+        c[:, 0] = h * f1v - uk
+        c[:, dim + 1] = 0.5
+        c[:, dim + 2] = h / p
+        z, _ = amgb_core(M, Q, z, c, tol, t, kappa, maxit, max_newton, verbose, solve_fn)
+        snaps.append(z.reshape(n, 3, order="F").copy())
+    return ParabolicSOL(geom, ts, snaps)
