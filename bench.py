@@ -209,6 +209,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes for the CPU restatement (0 = all cores)")
     ap.add_argument("--two-stage", action="store_true", help="element_kernel + gather_kernel instead of the patch-fused kernel")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N>1: fused peer-memory exchange (stores into the owner's window over NVLink) or the NCCL all_to_all path")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -235,13 +237,18 @@ def main():
     n = geom.x.shape[0]
     B = geom.block
     E = n // B
-    e0, e1 = (E * rank) // world, (E * (rank + 1)) // world
-    rows = (e0 * B, e1 * B)
+    from mgb_b200 import dist as mdist
+    rows = mdist.element_rows(n, B, rank, world)
     stream = torch.cuda.current_stream(dev)
     ctx = capi.Context(local_rank, stream.cuda_stream)
+    peer = world > 1 and args.exchange == "peer"
     t_plan = time.perf_counter()
-    plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows,
-                     force_path=capi.PLAN_TWO_STAGE if args.two_stage else 0)
+    if peer:
+        plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], B, rank, world)
+        assert (plan.dinfo["row0"], plan.dinfo["row1"]) == rows
+    else:
+        plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows,
+                         force_path=capi.PLAN_TWO_STAGE if args.two_stage else 0)
     t_plan = time.perf_counter() - t_plan
     nloc = rows[1] - rows[0]
     flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
@@ -261,7 +268,8 @@ def main():
 
     exch = None
     if world > 1:
-        from mgb_b200 import dist as mdist
+        flush_buf = torch.zeros(256 << 17, dtype=f64, device=dev)  # 256 MiB
+    if world > 1 and not peer:
         gplan = capi.Plan(None, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"])   # replicated symbolic pattern
         grp, gci = gplan.pattern()
         lrp, lci = plan.pattern()
@@ -269,24 +277,28 @@ def main():
                                   lrp.astype(np.int64), lci.astype(np.int64), dev)
         exch = mdist.Exchanger(ex, dev, ctx=ctx, n_loc_h=plan.nnzH, m=plan.m)
         hval_d, grad_d, scal_d = exch.views()   # local outputs live inside the exchange buffer
-        flush_buf = torch.zeros(256 << 17, dtype=f64, device=dev)  # 256 MiB
 
     def step_multi(nsteps):
-        """per-step CUDA events on the launching stream; interface exchange + scalar all-reduce inside"""
-        tot = 0.0
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        """per-step CUDA events on the launching stream, exchange inside the timed bracket.  All steps are
+        enqueued before the host waits, so the ranks are paced by their GPUs (the finish kernel / collective
+        couples them every step) and not by host launch jitter."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
         for r in range(nsteps):
             if flush == 2:
-                flush_sink = flush_buf.sum()  # read-evict: leaves L2 full of clean lines
+                flush_buf.sum()  # read-evict: leaves L2 full of clean lines
             elif flush:
                 flush_buf.fill_(float(r))
-            ev0.record()
-            plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
-            exch.exchange()
-            ev1.record()
-            ev1.synchronize()
-            tot += ev0.elapsed_time(ev1)
-        return tot / nsteps
+            evs[r][0].record()
+            if peer:
+                plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags)
+            else:
+                plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
+                exch.exchange()
+            evs[r][1].record()
+        torch.cuda.synchronize(dev)
+        if peer and plan.dist_info()["err"]:
+            raise SystemExit("bench.py: a peer's epoch flag timed out (exchange window protocol error)")
+        return sum(a.elapsed_time(b) for a, b in evs) / nsteps
 
     # ---- warm-up
     if world == 1:
@@ -312,16 +324,30 @@ def main():
     # ---- e2e through host buffers (pinned): H2D of the Newton unknown, D2H of gradient + Hessian values
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     s_h = pin(pr["s"])
-    n_h = exch.ex.n_own_h if exch is not None else plan.nnzH
-    n_g = exch.ex.n_own_g if exch is not None else plan.m
+    n_h = plan.dinfo["n_own_h"] if peer else (exch.ex.n_own_h if exch is not None else plan.nnzH)
+    n_g = plan.dinfo["n_own_g"] if peer else (exch.ex.n_own_g if exch is not None else plan.m)
+    views = {}
+
+    def window_views(ptrs):
+        """zero-copy tensors over the owned results inside this rank's exchange window (two parities)"""
+        if ptrs not in views:
+            views[ptrs] = tuple(torch.as_tensor(capi.DeviceView(p_, cnt), device=dev)
+                                for p_, cnt in zip(ptrs, (max(n_h, 1), max(n_g, 1), 4)))
+        return views[ptrs]
+
     hval_h = torch.empty(max(n_h, 1), dtype=f64).pin_memory()
     grad_h = torch.empty(max(n_g, 1), dtype=f64).pin_memory()
     scal_h = torch.empty(4, dtype=f64).pin_memory()
 
     def e2e_step():
         s_d.copy_(s_h, non_blocking=True)
-        plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
-        if exch is not None:
+        if peer:
+            ho, go, so = window_views(plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags))
+        else:
+            plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
+        if peer:
+            ho, go = ho[:n_h], go[:n_g]
+        elif exch is not None:
             ho, go, so = exch.exchange()
         else:
             ho, go, so = hval_d[:n_h], grad_d[:n_g], scal_d
@@ -375,7 +401,11 @@ def main():
                        "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
                        "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
                        "rows_per_rank": nloc,
-                       "multi_gpu": None if world == 1 else "row-block shards; interface rows + scalars in one all_to_all per assembly, owner-side sum in rank order"},
+                       "multi_gpu": None if world == 1 else (
+                           "row-block shards; push_kernel stores every result into the owner's window over NVLink peer memory "
+                           "(CUDA IPC), epoch flags, owner-side finish kernel sums interface entries in rank order; no NCCL on the data path"
+                           if peer else
+                           "row-block shards; interface rows + scalars in one NCCL all_to_all per assembly, owner-side sum in rank order")},
             "clocks": clocks,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(plan.m * 8),
                     "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned",
@@ -401,6 +431,9 @@ def main():
                 line["cpu_baseline_error"] = str(exc)
         print(json.dumps(line))
     if world > 1:
+        if peer:
+            views.clear()
+            mdist.destroy_peer_plan(plan)
         dist.destroy_process_group()
 
 

@@ -159,6 +159,62 @@ int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_
 int mgb_segsum_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* ptr_dev, const int32_t* idx_dev, int64_t nout,
                    double* dst_dev);
 
+/* stream-ordered device -> host copy on the ctx stream, then synchronise (results that live in library-owned
+ * device memory, e.g. the exchange window of mgb_dist_end) */
+int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
+
+/* ---- multi-GPU: one process per GPU, fused peer-memory exchange -----------------------
+ * Replaces, for the sharded assembly, the distributed SpGEMM/transpose exchanges HPCSparseArrays runs
+ * inside D_j' * diag * D_k and R' * H * R (reference test/test_map_rows_compare.jl:102-123,165-171 on
+ * HPC types; collectives listed in SURVEY.md 2.2).  Quadrature rows are split by `row_part` (whole broken
+ * elements: apply_D needs no halo), outputs (gradient entries, rows of R'HR) by `out_part`
+ * (HPCSparseArrays row partition, a13; offsets here are 0-based, length nranks+1).  Every rank stores its
+ * results directly into the owner's exchange window over NVLink peer memory; interface entries are summed
+ * by the owner in rank order.  No NCCL call on the data path.
+ *
+ *   1. mgb_dist_plan_create on every rank (same arguments except `rank`; ctx==NULL: maps only)
+ *   2. mgb_dist_export -> exchange the 64-byte handles between processes (MPI/NCCL/any) -> mgb_dist_attach
+ *      (or mgb_dist_attach_local with raw device pointers when all ranks live in one process)
+ *   3. per Newton step, collectively and in the same order on every rank: mgb_dist_assemble
+ *      (= mgb_dist_begin + mgb_dist_end).  Results stay valid until the second-next assemble call.
+ */
+typedef struct { unsigned char bytes[64]; } mgb_ipc_handle;
+
+int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R,
+                         int32_t dim, const double* x_host, const double* w_host,
+                         const mgb_barrier* barrier, int32_t rank, int32_t nranks,
+                         const int64_t* row_part, const int64_t* out_part, mgb_plan** out);
+/* info[0]=rank, [1]=nranks, [2]=owned Hessian entries, [3]=owned unknowns, [4],[5]=owned unknown range,
+ * [6]=local Hessian entries, [7],[8]=staged Hessian/gradient values received, [9],[10]=owned interface
+ * Hessian/gradient entries, [11]=window doubles per parity, [12]=epoch, [13]=error flag (1: a peer's
+ * epoch flag timed out), [14],[15]=local quadrature row range */
+int mgb_dist_info(const mgb_plan* plan, int64_t* info, int32_t ninfo);
+/* window layout of any rank: {n_own_h, n_own_g, n_stg_h, n_stg_g, off_h, off_g, off_scal, off_stg_h,
+ * off_stg_g, off_stg_scal, size} (doubles) */
+int mgb_dist_layout(const mgb_plan* plan, int32_t rank, int64_t* lay11);
+/* owned rows of the global pattern: rowptr (owned rows + 1, 0-based, relative), colidx (global ids) */
+int mgb_dist_pattern(const mgb_plan* plan, int32_t* rowptr_host, int32_t* colidx_host);
+/* host copies of the frozen maps (any pointer may be NULL): destination of every local Hessian entry
+ * ((owner << 27) | window offset) and unknown (-1: none); owner-side interface sums (position, staging
+ * ranges).  Used by the CPU tests of the host logic. */
+int mgb_dist_maps(const mgb_plan* plan, int32_t* h_dest, int32_t* g_dest, int32_t* fh_pos, int32_t* fh_ptr,
+                  int32_t* fg_pos, int32_t* fg_ptr);
+int mgb_dist_window(mgb_plan* plan, void** window_dev, int64_t* bytes);
+int mgb_dist_export(mgb_plan* plan, mgb_ipc_handle* handle);
+int mgb_dist_attach(mgb_plan* plan, const mgb_ipc_handle* handles /* nranks */);
+int mgb_dist_attach_local(mgb_plan* plan, void* const* windows_dev /* nranks */);
+/* element kernel + fused gather/push kernel (asynchronous on the ctx stream) */
+int mgb_dist_begin(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
+                   int32_t flags);
+/* owner-side finish kernel: waits for every rank's epoch flag, sums interface entries, folds the scalars.
+ * Returns device pointers into this rank's window: Hessian values of the owned rows (mgb_dist_pattern
+ * order), owned gradient block, scalars {f0, all_finite, <c,Dz>_w, infeasible count} (global sums). */
+int mgb_dist_end(mgb_plan* plan, double t, int32_t flags, const double** hval_own_dev,
+                 const double** grad_own_dev, const double** scal_dev);
+int mgb_dist_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
+                      int32_t flags, const double** hval_own_dev, const double** grad_own_dev,
+                      const double** scal_dev);
+
 /* timing helper: runs `reps` assemblies back to back on the ctx stream, returns average ms measured
  * with CUDA events on that stream (bench.py uses it so the events sit on the launching stream). */
 int mgb_time_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev,

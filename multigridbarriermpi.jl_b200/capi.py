@@ -26,6 +26,8 @@ EXPORTS = [
     "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
+    "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
+    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host",
 ]
 
 
@@ -95,6 +97,23 @@ def load(build_if_missing: bool = True):
     lib.mgb_gather_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mgb_scatter_add_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.mgb_segsum_idx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.mgb_dist_plan_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_Csr), C.POINTER(_Csr), C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.mgb_dist_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+    lib.mgb_dist_layout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.mgb_dist_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.mgb_dist_maps.argtypes = [C.c_void_p] + [C.c_void_p] * 6
+    lib.mgb_dist_window.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
+    lib.mgb_dist_export.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mgb_dist_attach.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mgb_dist_attach_local.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mgb_dist_begin.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32]
+    lib.mgb_dist_end.argtypes = [C.c_void_p, C.c_double, C.c_int32, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                 C.POINTER(C.c_void_p)]
+    lib.mgb_dist_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
+                                      C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     _lib = lib
     return lib
 
@@ -113,6 +132,16 @@ def _ptr(a) -> Optional[int]:
     if isinstance(a, int):
         return a
     return a.data_ptr()
+
+
+class DeviceView:
+    """``count`` float64 items at device address ``ptr`` as a __cuda_array_interface__ object
+    (``torch.as_tensor(DeviceView(...), device=...)`` gives a zero-copy tensor over library-owned memory,
+    e.g. the exchange window results of DistPlan.end)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
 
 
 def launch_count() -> int:
@@ -156,6 +185,12 @@ class Context:
 
     def segsum_idx(self, src_dev, ptr_dev, idx_dev, nout: int, dst_dev):
         _check(load().mgb_segsum_idx(self._h, _ptr(src_dev), _ptr(ptr_dev), _ptr(idx_dev), int(nout), _ptr(dst_dev)))
+
+    def to_host(self, src_dev: int, count: int, dtype=np.float64) -> np.ndarray:
+        """stream-ordered copy of ``count`` items at device address ``src_dev`` to a new numpy array"""
+        out = np.empty(int(count), dtype=dtype)
+        _check(load().mgb_copy_to_host(self._h, out.ctypes.data, C.c_void_p(int(src_dev)), out.nbytes))
+        return out
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -269,6 +304,119 @@ class Plan:
             self.close()
         except Exception:
             pass
+
+
+DIST_RANK_SHIFT = 27
+DIST_OFF_MASK = (1 << DIST_RANK_SHIFT) - 1
+
+
+class DistPlan(Plan):
+    """Sharded plan with the fused peer-memory exchange (mgb_dist_*): one instance per rank.
+
+    ``row_part`` / ``out_part``: 0-based offsets (length nranks+1) of the quadrature rows (whole elements)
+    and of the unknowns.  ``ctx=None`` builds the maps only (CPU tests of the host logic)."""
+
+    DINFO = ["rank", "nranks", "n_own_h", "n_own_g", "own0", "own1", "n_local_h", "n_stg_h", "n_stg_g", "n_fh", "n_fg",
+             "window_doubles", "epoch", "err", "row0", "row1"]
+    LAYOUT = ["n_own_h", "n_own_g", "n_stg_h", "n_stg_g", "off_h", "off_g", "off_scal", "off_stg_h", "off_stg_g",
+              "off_stg_scal", "size"]
+
+    def __init__(self, ctx: Optional[Context], D, R, x, w, idx, p: float, rank: int, nranks: int, row_part, out_part,
+                 slack: bool = False):
+        lib = load()
+        self.ctx = ctx
+        n = D[0].shape[0]
+        keep: list = []
+        Ds = (_Csr * len(D))(*[_csr_struct(d, keep) for d in D])
+        Rs = _csr_struct(R, keep)
+        bar = _Barrier()
+        bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
+        for j, v in enumerate(idx):
+            bar.idx[j] = int(v)
+        x = np.asfortranarray(x, dtype=np.float64)
+        w = np.ascontiguousarray(w, dtype=np.float64)
+        rp = np.ascontiguousarray(row_part, dtype=np.int64)
+        op = np.ascontiguousarray(out_part, dtype=np.int64)
+        assert rp.size == nranks + 1 and op.size == nranks + 1
+        h = C.c_void_p()
+        _check(lib.mgb_dist_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1],
+                                        x.ctypes.data, w.ctypes.data, C.byref(bar), int(rank), int(nranks),
+                                        rp.ctypes.data, op.ctypes.data, C.byref(h)))
+        self._h = h
+        info = np.zeros(15, dtype=np.int64)
+        _check(lib.mgb_plan_info(h, info.ctypes.data, 15))
+        self.info = dict(zip(self.INFO, (int(v) for v in info)))
+        self.n_local, self.nD, self.m, self.nnzH = (self.info[k] for k in ("n_local", "nD", "m", "nnzH"))
+        self._pattern = None
+        self.rank, self.nranks = int(rank), int(nranks)
+        self.dinfo = self.dist_info()
+        self._own_pattern = None
+
+    def dist_info(self) -> dict:
+        v = np.zeros(16, dtype=np.int64)
+        _check(load().mgb_dist_info(self._h, v.ctypes.data, 16))
+        return dict(zip(self.DINFO, (int(a) for a in v)))
+
+    def layout(self, rank: int) -> dict:
+        v = np.zeros(11, dtype=np.int64)
+        _check(load().mgb_dist_layout(self._h, int(rank), v.ctypes.data))
+        return dict(zip(self.LAYOUT, (int(a) for a in v)))
+
+    def own_pattern(self):
+        """(rowptr, colidx) of the owned rows of R'HR (rowptr relative to the block, global column ids)."""
+        if self._own_pattern is None:
+            d = self.dinfo
+            rp = np.zeros(d["own1"] - d["own0"] + 1, dtype=np.int32)
+            ci = np.zeros(max(d["n_own_h"], 1), dtype=np.int32)
+            _check(load().mgb_dist_pattern(self._h, rp.ctypes.data, ci.ctypes.data))
+            self._own_pattern = (rp, ci[: d["n_own_h"]])
+        return self._own_pattern
+
+    def maps(self) -> dict:
+        d = self.dinfo
+        out = dict(h_dest=np.zeros(max(d["n_local_h"], 1), np.int32), g_dest=np.zeros(max(self.m, 1), np.int32),
+                   fh_pos=np.zeros(max(d["n_fh"], 1), np.int32), fh_ptr=np.zeros(d["n_fh"] + 1, np.int32),
+                   fg_pos=np.zeros(max(d["n_fg"], 1), np.int32), fg_ptr=np.zeros(d["n_fg"] + 1, np.int32))
+        _check(load().mgb_dist_maps(self._h, *[out[k].ctypes.data for k in ("h_dest", "g_dest", "fh_pos", "fh_ptr", "fg_pos", "fg_ptr")]))
+        out["h_dest"] = out["h_dest"][: d["n_local_h"]]
+        out["g_dest"] = out["g_dest"][: self.m]
+        out["fh_pos"] = out["fh_pos"][: d["n_fh"]]
+        out["fg_pos"] = out["fg_pos"][: d["n_fg"]]
+        return out
+
+    def window(self):
+        p, b = C.c_void_p(), C.c_int64(0)
+        _check(load().mgb_dist_window(self._h, C.byref(p), C.byref(b)))
+        return int(p.value), int(b.value)
+
+    def export_handle(self) -> bytes:
+        buf = (C.c_ubyte * 64)()
+        _check(load().mgb_dist_export(self._h, buf))
+        return bytes(buf)
+
+    def attach(self, handles: Sequence[bytes]):
+        assert len(handles) == self.nranks and all(len(h) == 64 for h in handles)
+        buf = (C.c_ubyte * (64 * self.nranks)).from_buffer_copy(b"".join(handles))
+        _check(load().mgb_dist_attach(self._h, buf))
+
+    def attach_local(self, windows: Sequence[int]):
+        arr = (C.c_void_p * self.nranks)(*[C.c_void_p(int(w)) for w in windows])
+        _check(load().mgb_dist_attach_local(self._h, arr))
+
+    def begin(self, s_dev, Dz0_dev, c_dev, t: float, flags: int):
+        _check(load().mgb_dist_begin(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags)))
+
+    def end(self, t: float, flags: int):
+        """-> device pointers (hval_own, grad_own, scal) into this rank's window"""
+        hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(load().mgb_dist_end(self._h, float(t), int(flags), C.byref(hp), C.byref(gp), C.byref(sp_)))
+        return int(hp.value), int(gp.value), int(sp_.value)
+
+    def dist_assemble(self, s_dev, Dz0_dev, c_dev, t: float, flags: int):
+        hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(load().mgb_dist_assemble(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags),
+                                        C.byref(hp), C.byref(gp), C.byref(sp_)))
+        return int(hp.value), int(gp.value), int(sp_.value)
 
 
 class SpMat:

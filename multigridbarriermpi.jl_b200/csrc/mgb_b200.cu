@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "kernels_csr.cuh"
+#include "kernels_dist.cuh"
 #include "launch.h"
 #include "plan_host.h"
 
@@ -117,6 +118,26 @@ struct mgb_plan {
     // ---- host staging for the *_host entry point
     DevBuf<double> st_s, st_dz0, st_c, st_scal, st_grad, st_hval, st_dz;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // ---- multi-GPU peer exchange (mgb_dist_*)
+    struct Dist {
+        mgb::DistMaps maps;
+        DevBuf<int32_t> h_dest, g_dest, fh_pos, fh_ptr, fg_pos, fg_ptr;
+        DevBuf<unsigned int> counter;
+        DevBuf<int> err;
+        void* window = nullptr;        // [parity 0 | parity 1 | flags]; cudaMalloc'ed, exported by IPC handle
+        size_t window_bytes = 0;
+        void* peer[mgb::DIST_MAX_RANKS] = {nullptr};
+        bool peer_ipc[mgb::DIST_MAX_RANKS] = {false};
+        bool attached = false;
+        unsigned long long epoch = 0;
+        double timeout_s = 2.0;
+        ~Dist() {
+            for (int p = 0; p < mgb::DIST_MAX_RANKS; ++p)
+                if (peer_ipc[p] && peer[p]) cudaIpcCloseMemHandle(peer[p]);
+            if (window) cudaFree(window);
+        }
+    };
+    std::unique_ptr<Dist> dist;
 };
 
 struct mgb_spmat {
@@ -195,9 +216,7 @@ void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     CUDA_OK(cudaGetLastError());
 }
 
-void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, int flags,
-                      double* scal, double* grad, double* hval, double* Dz, cudaEvent_t mid = nullptr) {
-    cudaStream_t st = pl->ctx->stream;
+mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, double* Dz) {
     const auto& ep = pl->ep;
     mgb::ElemParams P{};
     P.E = ep.E; P.nloc = ep.nloc;
@@ -206,6 +225,34 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
     P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
     P.off_ut = ep.lay.off_ut; P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
+    return P;
+}
+
+// two-wide ELL + long-list replay parameters of the thread-per-entry gather (fine levels)
+mgb::GatherParams make_gather_params(mgb_plan* pl, int flags, double t, double* scal, double* grad, double* hval) {
+    mgb::GatherParams G{};
+    G.nnzH = pl->nnzH; G.m = pl->m;
+    G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p; G.h_lt = pl->d_hlt.p;
+    G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
+    G.sel = pl->d_sel.p; G.rel = pl->d_rel.p; G.hval = hval; G.grad = grad;
+    G.part = pl->d_part.p; G.nparts = pl->nblocks_elem; G.scal = scal; G.t = t;
+    G.want_h = (flags & MGB_WANT_HESS) ? 1 : 0;
+    G.want_g = (flags & MGB_WANT_GRAD) ? 1 : 0;
+    return G;
+}
+
+void size_gather_grid(mgb_plan* pl, mgb::GatherParams& G) {
+    G.nblk_h = G.want_h ? (pl->nnzH + 256 * mgb::GATHER_UNROLL - 1) / (256 * mgb::GATHER_UNROLL) : 0;
+    G.nblk_g = G.want_g ? (pl->m + 255) / 256 : 0;
+    G.n_long = G.want_h ? pl->n_long : 0;
+    G.nblk_l = (G.n_long + 255) / 256;
+}
+
+void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, int flags,
+                      double* scal, double* grad, double* hval, double* Dz, cudaEvent_t mid = nullptr) {
+    cudaStream_t st = pl->ctx->stream;
+    const auto& ep = pl->ep;
+    mgb::ElemParams P = make_elem_params(pl, s, Dz0, c, t, Dz);
     if ((flags & MGB_STORE_DZ) && !Dz) throw std::runtime_error("MGB_STORE_DZ without Dz buffer");
     if ((flags & MGB_WANT_GRAD) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
     if ((flags & MGB_WANT_HESS) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
@@ -238,14 +285,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     launch_elem(pl, P, flags);
     if (mid) CUDA_OK(cudaEventRecord(mid, st));
 
-    mgb::GatherParams G{};
-    G.nnzH = pl->nnzH; G.m = pl->m;
-    G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p; G.h_lt = pl->d_hlt.p;
-    G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
-    G.sel = pl->d_sel.p; G.rel = pl->d_rel.p; G.hval = hval; G.grad = grad;
-    G.part = pl->d_part.p; G.nparts = pl->nblocks_elem; G.scal = scal ? scal : pl->d_scal_tmp.p; G.t = t;
-    G.want_h = (flags & MGB_WANT_HESS) ? 1 : 0;
-    G.want_g = (flags & MGB_WANT_GRAD) ? 1 : 0;
+    mgb::GatherParams G = make_gather_params(pl, flags, t, scal ? scal : pl->d_scal_tmp.p, grad, hval);
     if (pl->long_lists) {
         // coarse levels: few output entries with long lists -> warp per entry
         if (G.want_h) {
@@ -260,10 +300,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         }
         G.want_h = G.want_g = 0;
     }
-    G.nblk_h = G.want_h ? (pl->nnzH + 256 * mgb::GATHER_UNROLL - 1) / (256 * mgb::GATHER_UNROLL) : 0;
-    G.nblk_g = G.want_g ? (pl->m + 255) / 256 : 0;
-    G.n_long = G.want_h ? pl->n_long : 0;
-    G.nblk_l = (G.n_long + 255) / 256;
+    size_gather_grid(pl, G);
     mgb::gather_kernel<<<(unsigned)(G.nblk_h + G.nblk_l + G.nblk_g + 1), 256, 0, st>>>(G);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -738,6 +775,222 @@ int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, 
         if (ms_kernel_gather) *ms_kernel_gather = (float)(tga / reps);
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_time_assemble: ") + ex.what()); }
+}
+
+int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
+    try {
+        if (!ctx || (bytes > 0 && (!dst_host || !src_dev))) return fail("mgb_copy_to_host: NULL argument");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        if (bytes > 0) CUDA_OK(cudaMemcpyAsync(dst_host, src_dev, (size_t)bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_copy_to_host: ") + ex.what()); }
+}
+
+// ------------------------------------------------------------------ multi-GPU peer exchange
+int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
+                         const double* x_host, const double* w_host, const mgb_barrier* barrier, int32_t rank,
+                         int32_t nranks, const int64_t* row_part, const int64_t* out_part, mgb_plan** out) {
+    try {
+        if (!D || !R || !w_host || !barrier || !row_part || !out_part || !out) return fail("mgb_dist_plan_create: NULL argument");
+        if (nranks < 1 || nranks > mgb::DIST_MAX_RANKS || rank < 0 || rank >= nranks) return fail("mgb_dist_plan_create: bad rank / nranks (1..16)");
+        mgb_plan* plraw = nullptr;
+        int rc = mgb_plan_create(ctx, n, nD, D, R, dim, x_host, w_host, barrier, row_part[rank], row_part[rank + 1],
+                                 MGB_PATH_ELEMENT | MGB_PLAN_TWO_STAGE, &plraw);
+        if (rc) return rc;
+        std::unique_ptr<mgb_plan, int (*)(mgb_plan*)> pl(plraw, mgb_plan_destroy);
+        if (pl->patch > 0 || pl->long_lists)
+            return fail("mgb_dist_plan_create: peer exchange is implemented for the thread-per-entry gather (fine levels)");
+        // replicated global symbolic plan (host only) -> exchange maps
+        std::vector<mgb::HostCSR> Dh(nD);
+        for (int k = 0; k < nD; ++k) Dh[k] = to_host_csr(D[k], 0, n);
+        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+        mgb::ElementPlan gp;
+        mgb::build_element_plan(Dh, Rh, n, w_host, pl->bar, gp, true);
+        auto dd = std::make_unique<mgb_plan::Dist>();
+        mgb::build_dist_maps(gp, rank, nranks, row_part, out_part, dd->maps);
+        const auto& M = dd->maps;
+        if ((int64_t)M.h_dest.size() != pl->nnzH) return fail("mgb_dist_plan_create: internal: local pattern differs from the global plan's view");
+        if (ctx) {
+            CUDA_OK(cudaSetDevice(ctx->device));
+            cudaStream_t st = ctx->stream;
+            dd->h_dest.upload(M.h_dest, st); dd->g_dest.upload(M.g_dest, st);
+            dd->fh_pos.upload(M.fh_pos, st); dd->fh_ptr.upload(M.fh_ptr, st);
+            dd->fg_pos.upload(M.fg_pos, st); dd->fg_ptr.upload(M.fg_ptr, st);
+            dd->counter.alloc(1); dd->err.alloc(1);
+            CUDA_OK(cudaMemsetAsync(dd->counter.p, 0, sizeof(unsigned int), st));
+            CUDA_OK(cudaMemsetAsync(dd->err.p, 0, sizeof(int), st));
+            dd->window_bytes = (size_t)2 * M.lay[rank].size * 8 + mgb::DIST_MAX_RANKS * sizeof(unsigned long long);
+            CUDA_OK(cudaMalloc(&dd->window, dd->window_bytes));
+            CUDA_OK(cudaMemsetAsync(dd->window, 0, dd->window_bytes, st));
+            CUDA_OK(cudaStreamSynchronize(st));
+            pl->dev_bytes += dd->window_bytes + dd->h_dest.bytes() + dd->g_dest.bytes();
+            if (const char* ev = getenv("MGB_DIST_TIMEOUT_S")) dd->timeout_s = atof(ev) > 0 ? atof(ev) : dd->timeout_s;
+        }
+        pl->dist = std::move(dd);
+        *out = pl.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_plan_create: ") + ex.what()); }
+}
+
+int mgb_dist_info(const mgb_plan* pl, int64_t* info, int32_t ninfo) {
+    if (!pl || !pl->dist || !info) return fail("mgb_dist_info: not a distributed plan");
+    const auto& M = pl->dist->maps;
+    const auto& L = M.lay[M.rank];
+    int err = 0;
+    if (pl->ctx && pl->dist->err.p) {
+        cudaSetDevice(pl->ctx->device);
+        cudaMemcpy(&err, pl->dist->err.p, sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    int64_t v[16] = {M.rank, M.nranks, L.n_own_h, L.n_own_g, M.out_part[M.rank], M.out_part[M.rank + 1],
+                     (int64_t)M.h_dest.size(), L.n_stg_h, L.n_stg_g, (int64_t)M.fh_pos.size(), (int64_t)M.fg_pos.size(),
+                     L.size, (int64_t)pl->dist->epoch, err, M.row_part[M.rank], M.row_part[M.rank + 1]};
+    for (int i = 0; i < ninfo && i < 16; ++i) info[i] = v[i];
+    return 0;
+}
+
+int mgb_dist_layout(const mgb_plan* pl, int32_t rank, int64_t* lay11) {
+    if (!pl || !pl->dist || !lay11) return fail("mgb_dist_layout: not a distributed plan");
+    if (rank < 0 || rank >= pl->dist->maps.nranks) return fail("mgb_dist_layout: bad rank");
+    const auto& L = pl->dist->maps.lay[rank];
+    const int64_t v[11] = {L.n_own_h, L.n_own_g, L.n_stg_h, L.n_stg_g, L.off_h, L.off_g, L.off_scal, L.off_stg_h,
+                           L.off_stg_g, L.off_stg_scal, L.size};
+    std::memcpy(lay11, v, sizeof(v));
+    return 0;
+}
+
+int mgb_dist_pattern(const mgb_plan* pl, int32_t* rowptr_host, int32_t* colidx_host) {
+    if (!pl || !pl->dist || !rowptr_host || !colidx_host) return fail("mgb_dist_pattern: not a distributed plan");
+    const auto& M = pl->dist->maps;
+    std::memcpy(rowptr_host, M.own_rowptr.data(), M.own_rowptr.size() * sizeof(int32_t));
+    std::memcpy(colidx_host, M.own_colidx.data(), M.own_colidx.size() * sizeof(int32_t));
+    return 0;
+}
+
+int mgb_dist_maps(const mgb_plan* pl, int32_t* h_dest, int32_t* g_dest, int32_t* fh_pos, int32_t* fh_ptr,
+                  int32_t* fg_pos, int32_t* fg_ptr) {
+    if (!pl || !pl->dist) return fail("mgb_dist_maps: not a distributed plan");
+    const auto& M = pl->dist->maps;
+    auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
+    cp(h_dest, M.h_dest); cp(g_dest, M.g_dest); cp(fh_pos, M.fh_pos); cp(fh_ptr, M.fh_ptr); cp(fg_pos, M.fg_pos); cp(fg_ptr, M.fg_ptr);
+    return 0;
+}
+
+int mgb_dist_window(mgb_plan* pl, void** window_dev, int64_t* bytes) {
+    if (!pl || !pl->dist || !pl->dist->window) return fail("mgb_dist_window: plan has no exchange window (symbolic-only or not distributed)");
+    if (window_dev) *window_dev = pl->dist->window;
+    if (bytes) *bytes = (int64_t)pl->dist->window_bytes;
+    return 0;
+}
+
+int mgb_dist_export(mgb_plan* pl, mgb_ipc_handle* handle) {
+    try {
+        if (!pl || !pl->dist || !pl->dist->window || !handle) return fail("mgb_dist_export: plan has no exchange window");
+        static_assert(sizeof(cudaIpcMemHandle_t) == sizeof(mgb_ipc_handle), "IPC handle size");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        cudaIpcMemHandle_t h;
+        CUDA_OK(cudaIpcGetMemHandle(&h, pl->dist->window));
+        std::memcpy(handle->bytes, &h, sizeof(h));
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_export: ") + ex.what()); }
+}
+
+int mgb_dist_attach(mgb_plan* pl, const mgb_ipc_handle* handles) {
+    try {
+        if (!pl || !pl->dist || !pl->dist->window || !handles) return fail("mgb_dist_attach: plan has no exchange window");
+        auto& dd = *pl->dist;
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        for (int p = 0; p < dd.maps.nranks; ++p) {
+            if (p == dd.maps.rank) { dd.peer[p] = dd.window; continue; }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, handles[p].bytes, sizeof(h));
+            void* ptr = nullptr;
+            CUDA_OK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+            dd.peer[p] = ptr; dd.peer_ipc[p] = true;
+        }
+        dd.attached = true;
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_attach: ") + ex.what()); }
+}
+
+int mgb_dist_attach_local(mgb_plan* pl, void* const* windows_dev) {
+    if (!pl || !pl->dist || !pl->dist->window || !windows_dev) return fail("mgb_dist_attach_local: plan has no exchange window");
+    auto& dd = *pl->dist;
+    for (int p = 0; p < dd.maps.nranks; ++p) {
+        if (!windows_dev[p]) return fail("mgb_dist_attach_local: NULL window");
+        dd.peer[p] = (p == dd.maps.rank) ? dd.window : windows_dev[p];
+    }
+    dd.attached = true;
+    return 0;
+}
+
+int mgb_dist_begin(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags) {
+    try {
+        if (!pl || !pl->dist || !s_dev || !c_dev) return fail("mgb_dist_begin: NULL argument / not a distributed plan");
+        if (!pl->ctx) return fail("mgb_dist_begin: symbolic-only plan; no CPU path exists");
+        auto& dd = *pl->dist;
+        if (!dd.attached) return fail("mgb_dist_begin: peers not attached (mgb_dist_attach)");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        cudaStream_t st = pl->ctx->stream;
+        const auto& M = dd.maps;
+        dd.epoch++;
+        const int par = (int)(dd.epoch & 1ull);
+        mgb::ElemParams E = make_elem_params(pl, s_dev, Dz0_dev, c_dev, t, nullptr);
+        launch_elem(pl, E, flags & 7);
+        mgb::PushParams P{};
+        P.G = make_gather_params(pl, flags, t, nullptr, nullptr, nullptr);
+        size_gather_grid(pl, P.G);
+        P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p;
+        for (int p = 0; p < M.nranks; ++p) {
+            char* base = static_cast<char*>(dd.peer[p]);
+            P.win[p] = reinterpret_cast<double*>(base) + (size_t)par * M.lay[p].size;
+            P.flag[p] = reinterpret_cast<unsigned long long*>(base + (size_t)2 * M.lay[p].size * 8);
+            P.scal_off[p] = M.lay[p].off_stg_scal + 4 * (int64_t)M.rank;
+        }
+        P.rank = M.rank; P.nranks = M.nranks; P.epoch = dd.epoch; P.counter = dd.counter.p;
+        mgb::push_kernel<<<(unsigned)(P.G.nblk_h + P.G.nblk_l + P.G.nblk_g + 1), 256, 0, st>>>(P);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_begin: ") + ex.what()); }
+}
+
+int mgb_dist_end(mgb_plan* pl, double t, int32_t flags, const double** hval_own_dev, const double** grad_own_dev,
+                 const double** scal_dev) {
+    try {
+        if (!pl || !pl->dist || !pl->ctx) return fail("mgb_dist_end: not a distributed device plan");
+        auto& dd = *pl->dist;
+        if (dd.epoch == 0) return fail("mgb_dist_end: no mgb_dist_begin in flight");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        const auto& M = dd.maps;
+        const auto& L = M.lay[M.rank];
+        const int par = (int)(dd.epoch & 1ull);
+        mgb::FinishParams F{};
+        char* base = static_cast<char*>(dd.window);
+        F.win = reinterpret_cast<double*>(base) + (size_t)par * L.size;
+        F.flag = reinterpret_cast<const unsigned long long*>(base + (size_t)2 * L.size * 8);
+        F.nranks = M.nranks; F.epoch = dd.epoch; F.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9);
+        F.n_fh = (flags & MGB_WANT_HESS) ? (int64_t)M.fh_pos.size() : 0;
+        F.n_fg = (flags & MGB_WANT_GRAD) ? (int64_t)M.fg_pos.size() : 0;
+        F.fh_pos = dd.fh_pos.p; F.fh_ptr = dd.fh_ptr.p; F.fg_pos = dd.fg_pos.p; F.fg_ptr = dd.fg_ptr.p;
+        F.off_h = L.off_h; F.off_g = L.off_g; F.off_scal = L.off_scal; F.off_stg_h = L.off_stg_h;
+        F.off_stg_g = L.off_stg_g; F.off_stg_scal = L.off_stg_scal; F.t = t;
+        F.nblk_h = (F.n_fh + 255) / 256; F.nblk_g = (F.n_fg + 255) / 256; F.err = dd.err.p;
+        mgb::finish_kernel<<<(unsigned)(F.nblk_h + F.nblk_g + 1), 256, 0, pl->ctx->stream>>>(F);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        if (hval_own_dev) *hval_own_dev = F.win + L.off_h;
+        if (grad_own_dev) *grad_own_dev = F.win + L.off_g;
+        if (scal_dev) *scal_dev = F.win + L.off_scal;
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_end: ") + ex.what()); }
+}
+
+int mgb_dist_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
+                      int32_t flags, const double** hval_own_dev, const double** grad_own_dev, const double** scal_dev) {
+    int rc = mgb_dist_begin(pl, s_dev, Dz0_dev, c_dev, t, flags);
+    if (rc) return rc;
+    return mgb_dist_end(pl, t, flags, hval_own_dev, grad_own_dev, scal_dev);
 }
 
 }  // extern "C"

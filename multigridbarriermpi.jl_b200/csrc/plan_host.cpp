@@ -494,6 +494,125 @@ void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
                  [&](int32_t gi) { const int64_t e = gi / RS; return (uint32_t)(P * NSP + (e % P) * RS + gi % RS); }, PP.G);
 }
 
+namespace {
+int64_t pad16(int64_t v) { return (v + 15) / 16 * 16; }
+
+// one output family (Hessian entries or gradient entries).  cptr/cidx: global contribution lists sorted by
+// element; elem_of(contribution) -> element; owner_of_entry(t) -> owning rank; pos_in_owner(t) -> index
+// inside the owner's block.  Fills dest (for entries this rank contributes to, in entry order) and the
+// owner-side lists of this rank; counts staged values per owner.
+template <class ElemOf, class OwnerOf, class PosOf, class Sink>
+void dist_family(int64_t nout, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx, int rank, int nranks,
+                 const std::vector<int64_t>& elem_part, ElemOf elem_of, OwnerOf owner_of, PosOf pos_of,
+                 std::vector<int64_t>& n_stg /*per owner*/, Sink sink /* (t, owner, pos, staged, stg_index) for my entries */,
+                 std::vector<int32_t>& f_pos, std::vector<int32_t>& f_ptr) {
+    n_stg.assign(nranks, 0);
+    f_pos.clear();
+    f_ptr.assign(1, 0);
+    for (int64_t t = 0; t < nout; ++t) {
+        const int64_t c0 = cptr[t], c1 = cptr[t + 1];
+        if (c1 == c0) continue;
+        // contributing ranks in ascending order (lists are sorted by element)
+        int nsrc = 0, mine = -1, last = -1;
+        for (int64_t c = c0; c < c1; ++c) {
+            const int64_t e = elem_of(cidx[c]);
+            const int r = (int)(std::upper_bound(elem_part.begin(), elem_part.end(), e) - elem_part.begin()) - 1;
+            if (r < last) throw std::runtime_error("internal: contribution list not sorted by element");
+            if (r != last) {
+                if (r == rank) mine = nsrc;
+                ++nsrc;
+                last = r;
+            }
+        }
+        const int owner = owner_of(t);
+        const int64_t pos = pos_of(t, owner);
+        if (nsrc == 1) {
+            if (mine >= 0) sink(t, owner, pos, false, (int64_t)0);
+        } else {
+            const int64_t base = n_stg[owner];
+            n_stg[owner] += nsrc;
+            if (mine >= 0) sink(t, owner, pos, true, base + mine);
+            if (owner == rank) {
+                if (pos > INT32_MAX || base + nsrc > INT32_MAX) throw std::runtime_error("exchange window exceeds int32 indexing");
+                f_pos.push_back((int32_t)pos);
+                f_ptr.push_back((int32_t)(base + nsrc));
+            }
+        }
+    }
+}
+}  // namespace
+
+void build_dist_maps(const ElementPlan& G, int rank, int nranks, const int64_t* row_part, const int64_t* out_part,
+                     DistMaps& M) {
+    if (nranks < 1 || nranks > DIST_MAX_RANKS) throw std::runtime_error("number of ranks must be 1..16");
+    if (rank < 0 || rank >= nranks) throw std::runtime_error("rank outside 0..nranks-1");
+    if (!G.ok) throw std::runtime_error("peer exchange needs the element path: " + G.why);
+    M.rank = rank; M.nranks = nranks;
+    M.row_part.assign(row_part, row_part + nranks + 1);
+    M.out_part.assign(out_part, out_part + nranks + 1);
+    const int64_t m = G.m, B = G.B, nnzH = (int64_t)G.h_colidx.size();
+    if (M.row_part[0] != 0 || M.row_part[nranks] != G.nloc) throw std::runtime_error("row partition must cover [0,n)");
+    if (M.out_part[0] != 0 || M.out_part[nranks] != m) throw std::runtime_error("output partition must cover [0,m)");
+    std::vector<int64_t> elem_part(nranks + 1);
+    for (int r = 0; r <= nranks; ++r) {
+        if (M.row_part[r] % B) throw std::runtime_error("row partition splits a broken element");
+        if (r && (M.row_part[r] < M.row_part[r - 1] || M.out_part[r] < M.out_part[r - 1])) throw std::runtime_error("partition offsets must be non-decreasing");
+        elem_part[r] = M.row_part[r] / B;
+    }
+    auto owner_of_row = [&](int64_t a) { return (int)(std::upper_bound(M.out_part.begin(), M.out_part.end(), a) - M.out_part.begin()) - 1; };
+    // row of every global Hessian entry
+    std::vector<int32_t> row_of(nnzH);
+    for (int64_t a = 0; a < m; ++a)
+        for (int64_t t = G.h_rowptr[a]; t < G.h_rowptr[a + 1]; ++t) row_of[t] = (int32_t)a;
+    const int NS = G.lay.NS, RS = G.NU * G.LPE;
+    struct Rec { int owner; int64_t pos; bool staged; int64_t sidx; };
+    std::vector<Rec> hrec, grec;
+    std::vector<int32_t> g_entry;  // unknown of each gradient record
+    std::vector<int64_t> nstg_h, nstg_g;
+    dist_family(nnzH, G.h_cptr, G.h_cidx, rank, nranks, elem_part,
+                [&](int32_t gs) { return (int64_t)(gs / NS); },
+                [&](int64_t t) { return owner_of_row(row_of[t]); },
+                [&](int64_t t, int owner) { return t - (int64_t)G.h_rowptr[M.out_part[owner]]; }, nstg_h,
+                [&](int64_t, int owner, int64_t pos, bool staged, int64_t sidx) { hrec.push_back({owner, pos, staged, sidx}); },
+                M.fh_pos, M.fh_ptr);
+    dist_family(m, G.g_cptr, G.g_cidx, rank, nranks, elem_part,
+                [&](int32_t gi) { return (int64_t)(gi / RS); },
+                [&](int64_t a) { return owner_of_row(a); },
+                [&](int64_t a, int owner) { return a - M.out_part[owner]; }, nstg_g,
+                [&](int64_t a, int owner, int64_t pos, bool staged, int64_t sidx) { grec.push_back({owner, pos, staged, sidx}); g_entry.push_back((int32_t)a); },
+                M.fg_pos, M.fg_ptr);
+    // window layouts of every rank
+    M.lay.assign(nranks, DistLayout());
+    for (int r = 0; r < nranks; ++r) {
+        DistLayout& L = M.lay[r];
+        L.n_own_h = (int64_t)G.h_rowptr[M.out_part[r + 1]] - (int64_t)G.h_rowptr[M.out_part[r]];
+        L.n_own_g = M.out_part[r + 1] - M.out_part[r];
+        L.n_stg_h = nstg_h[r]; L.n_stg_g = nstg_g[r];
+        int64_t o = 0;
+        L.off_h = o; o += pad16(L.n_own_h);
+        L.off_g = o; o += pad16(L.n_own_g);
+        L.off_scal = o; o += 16;
+        L.off_stg_h = o; o += pad16(L.n_stg_h);
+        L.off_stg_g = o; o += pad16(L.n_stg_g);
+        L.off_stg_scal = o; o += pad16(4 * (int64_t)nranks);
+        L.size = o;
+        if (L.size > DIST_OFF_MASK) throw std::runtime_error("exchange window exceeds 2^27 doubles; use more ranks");
+    }
+    auto encode = [&](const Rec& r, bool hess) -> int32_t {
+        const DistLayout& L = M.lay[r.owner];
+        const int64_t off = r.staged ? (hess ? L.off_stg_h : L.off_stg_g) + r.sidx : (hess ? L.off_h : L.off_g) + r.pos;
+        return (int32_t)(((int64_t)r.owner << DIST_RANK_SHIFT) | off);
+    };
+    M.h_dest.resize(hrec.size());
+    for (size_t k = 0; k < hrec.size(); ++k) M.h_dest[k] = encode(hrec[k], true);
+    M.g_dest.assign(m, -1);
+    for (size_t k = 0; k < grec.size(); ++k) M.g_dest[g_entry[k]] = encode(grec[k], false);
+    const int64_t lo = M.out_part[rank], hi = M.out_part[rank + 1];
+    M.own_rowptr.resize(hi - lo + 1);
+    for (int64_t a = lo; a <= hi; ++a) M.own_rowptr[a - lo] = G.h_rowptr[a] - G.h_rowptr[lo];
+    M.own_colidx.assign(G.h_colidx.begin() + G.h_rowptr[lo], G.h_colidx.begin() + G.h_rowptr[hi]);
+}
+
 void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P, bool want_hessian) {
     const int ND = (int)D.size();
     P.ND = ND;

@@ -101,6 +101,38 @@ struct BarrierDesc {
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
                         const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
 
+
+// ---- multi-GPU (one process per GPU): fused peer-memory exchange maps --------------------------------
+// Every rank assembles the contributions of its own quadrature rows (whole elements) and stores each
+// local result straight into the memory of the rank that OWNS the output row (HPCSparseArrays row
+// partition of R'HR and of the gradient): entries fed by one rank only go to their final
+// position in the owner's value array, entries fed by several ranks (element-partition interface) go to
+// a staging area and are summed by the owner in source-rank order.  All maps derive from the replicated
+// global symbolic plan, so no integer exchange is needed.
+constexpr int DIST_MAX_RANKS = 16;
+constexpr int DIST_RANK_SHIFT = 27;                         // dest = (rank << 27) | offset (doubles)
+constexpr int32_t DIST_OFF_MASK = (1 << DIST_RANK_SHIFT) - 1;
+
+struct DistLayout {  // one rank's exchange window (offsets in doubles; one copy per epoch parity)
+    int64_t n_own_h = 0, n_own_g = 0, n_stg_h = 0, n_stg_g = 0;
+    int64_t off_h = 0, off_g = 0, off_scal = 0, off_stg_h = 0, off_stg_g = 0, off_stg_scal = 0, size = 0;
+};
+
+struct DistMaps {
+    int rank = 0, nranks = 1;
+    std::vector<int64_t> row_part, out_part;   // 0-based offsets, nranks+1 (quadrature rows / unknowns)
+    std::vector<DistLayout> lay;               // every rank's window layout
+    std::vector<int32_t> h_dest;               // per LOCAL Hessian entry (local pattern order)
+    std::vector<int32_t> g_dest;               // per unknown (m); -1: no local contribution
+    std::vector<int32_t> fh_pos, fh_ptr;       // owned multi-source Hessian entries: position, staging range
+    std::vector<int32_t> fg_pos, fg_ptr;       // same for the gradient
+    std::vector<int32_t> own_rowptr, own_colidx;  // owned rows of the global pattern (global column ids)
+};
+
+// `global`: element plan over ALL quadrature rows (host arrays still present).
+void build_dist_maps(const ElementPlan& global, int rank, int nranks, const int64_t* row_part,
+                     const int64_t* out_part, DistMaps& out);
+
 struct CsrPlan {
     int ND = 0, NU = 0;
     int64_t nloc = 0, m = 0;

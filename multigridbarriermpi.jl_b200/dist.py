@@ -210,3 +210,39 @@ def element_rows(n: int, block: int, rank: int, nranks: int):
     """[row0,row1) of this rank: whole elements, first ranks take the remainder (uniform_partition)."""
     part = uniform_partition(n, nranks, block)
     return int(part[rank] - 1), int(part[rank + 1] - 1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Fused peer-memory exchange (mgb_dist_*): no collective on the data path.  torch.distributed is used
+# once, at setup, to pass the 64-byte CUDA IPC handles of the exchange windows between the processes.
+
+def peer_partitions(n: int, m: int, block: int, nranks: int):
+    """0-based offsets (length nranks+1): quadrature rows in whole elements, unknowns uniformly
+    (uniform_partition: the HPCSparseArrays-style split, first ``units mod P`` ranks take one extra unit)."""
+    return uniform_partition(n, nranks, block) - 1, uniform_partition(m, nranks) - 1
+
+
+def create_peer_plan(ctx, D, R, x, w, idx, p: float, block: int, rank: int, nranks: int, group=None, slack: bool = False):
+    """Collective: every rank builds its DistPlan, the windows are cross-mapped over CUDA IPC, and a
+    barrier makes sure every window is mapped (and zero-initialised) before the first assembly."""
+    from . import capi
+    n, m = D[0].shape[0], R.shape[1]
+    row_part, out_part = peer_partitions(n, m, block, nranks)
+    plan = capi.DistPlan(ctx, D, R, x, w, idx, p, rank, nranks, row_part, out_part, slack=slack)
+    handles: List[Optional[bytes]] = [None] * nranks
+    if nranks > 1:
+        dist.all_gather_object(handles, plan.export_handle(), group=group)
+    else:
+        handles = [plan.export_handle()]
+    plan.attach(handles)
+    if nranks > 1:
+        dist.barrier(group=group)
+    return plan
+
+
+def destroy_peer_plan(plan, group=None):
+    """Collective: nobody unmaps/frees a window while a peer may still store into it."""
+    plan.ctx.sync()
+    if plan.nranks > 1:
+        dist.barrier(group=group)
+    plan.close()
