@@ -239,7 +239,8 @@ def main():
     E = n // B
     from mgb_b200 import dist as mdist
     rows = mdist.element_rows(n, B, rank, world)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)      # a real (non-legacy) stream: programmatic dependent launch needs one
+    torch.cuda.set_stream(stream)
     ctx = capi.Context(local_rank, stream.cuda_stream)
     peer = world > 1 and args.exchange == "peer"
     t_plan = time.perf_counter()

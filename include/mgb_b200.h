@@ -203,6 +203,10 @@ int mgb_dist_window(mgb_plan* plan, void** window_dev, int64_t* bytes);
 int mgb_dist_export(mgb_plan* plan, mgb_ipc_handle* handle);
 int mgb_dist_attach(mgb_plan* plan, const mgb_ipc_handle* handles /* nranks */);
 int mgb_dist_attach_local(mgb_plan* plan, void* const* windows_dev /* nranks */);
+/* developer timeline (plan created with MGB_DIST_DEBUG=1 in the environment): ring of 512 epochs x 8
+ * globaltimer stamps {push start, stores issued, last ticket, flags published, flags seen, finish done,
+ * before element kernel, -} */
+int mgb_dist_debug(mgb_plan* plan, uint64_t* out512x8);
 /* element kernel + fused gather/push kernel (asynchronous on the ctx stream) */
 int mgb_dist_begin(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                    int32_t flags);

@@ -27,7 +27,7 @@ EXPORTS = [
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
-    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host",
+    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_dist_debug",
 ]
 
 
@@ -101,6 +101,7 @@ def load(build_if_missing: bool = True):
                                          C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.mgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.mgb_dist_debug.argtypes = [C.c_void_p, C.c_void_p]
     lib.mgb_dist_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.mgb_dist_layout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
     lib.mgb_dist_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -411,6 +412,11 @@ class DistPlan(Plan):
         hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(load().mgb_dist_end(self._h, float(t), int(flags), C.byref(hp), C.byref(gp), C.byref(sp_)))
         return int(hp.value), int(gp.value), int(sp_.value)
+
+    def debug_timeline(self) -> np.ndarray:
+        out = np.zeros((512, 8), dtype=np.uint64)
+        _check(load().mgb_dist_debug(self._h, out.ctypes.data))
+        return out
 
     def dist_assemble(self, s_dev, Dz0_dev, c_dev, t: float, flags: int):
         hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -46,6 +46,12 @@ struct ElemParams {
 template <int V>
 struct Pow2Ceil { static constexpr int value = (V <= 1) ? 1 : 2 * Pow2Ceil<(V + 1) / 2>::value; };
 
+// Programmatic dependent launch (PDL): the element kernel lets its dependent (gather / push) start while its
+// last wave drains; the dependent loads its index lists, then waits for the element records.  Both are
+// no-ops when the kernel is launched without the programmatic-serialization attribute.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait_primary() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ double shfl_d(double v, int src, int width) {
     return __shfl_sync(0xffffffffu, v, src, width);
 }
@@ -415,6 +421,7 @@ template <int B, int D, bool SLACK, bool FINE, int FLAGS>
 __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
     constexpr int LPE = Pow2Ceil<B>::value;
     constexpr int NU = 2 + (SLACK ? 1 : 0);
+    pdl_launch_dependents();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = tid / LPE;
     const int l = (int)(tid % LPE);
@@ -604,6 +611,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
             const int64_t t = base + (int64_t)j * 256;
             src[j] = (t < P.nnzH) ? __ldg(&P.h_src2[t]) : make_int2(0, -1);
         }
+        pdl_wait_primary();
         double v0[GATHER_UNROLL], v1[GATHER_UNROLL];
 #pragma unroll
         for (int j = 0; j < GATHER_UNROLL; ++j) {
@@ -621,6 +629,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
     if (b < P.nblk_h + P.nblk_l) {
         // entries with more than two contributions (vertex diagonals ...): thread per entry
         const int64_t li = (b - P.nblk_h) * 256 + threadIdx.x;
+        pdl_wait_primary();
         if (li < P.n_long) {
             const int64_t c0 = __ldg(&P.h_lptr[li]), c1 = __ldg(&P.h_lptr[li + 1]);
             double acc = 0.0;
@@ -631,6 +640,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
     }
     if (b < P.nblk_h + P.nblk_l + P.nblk_g) {
         const int64_t a = (b - P.nblk_h - P.nblk_l) * 256 + threadIdx.x;
+        pdl_wait_primary();
         if (a < P.m) {
             const int64_t c0 = __ldg(&P.g_cptr[a]), c1 = __ldg(&P.g_cptr[a + 1]);
             double acc = 0.0;
@@ -640,6 +650,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
         return;
     }
     // scalar block
+    pdl_wait_primary();
     __shared__ double sh[3][256];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {

@@ -6,8 +6,10 @@
 // (HPCSparseArrays row partition), through NVLink peer-mapped memory: entries fed by this
 // rank alone land in their final position of the owner's CSR value array / gradient block, entries on the
 // element-partition interface land in the owner's staging area.  The last CTA to retire publishes an epoch
-// flag in every peer's window (release, system scope).  finish_kernel on the owner waits for all peers'
-// flags (acquire), sums the staged values in source-rank order (bit-reproducible) and folds the scalars.
+// flag in every peer's window (release, system scope), then - fused mode, mgb_dist_assemble - acts as the
+// owner: waits for all peers' flags (acquire), sums the staged values in source-rank order
+// (bit-reproducible) and folds the scalars.  Split mode (mgb_dist_begin / mgb_dist_end) runs that owner
+// step as finish_kernel instead, so several ranks can share one stream (tests on a single GPU).
 // No NCCL on the data path; no atomics on values.  Windows are double-buffered by epoch parity: a rank can
 // only reach epoch k+2 after every peer finished reading epoch k.
 #pragma once
@@ -27,10 +29,94 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
+}
+
+struct FinishParams {
+    double* win;                        // this rank's window (this epoch's parity)
+    const unsigned long long* flag;     // this rank's flag array (written by the peers)
+    int nranks;
+    unsigned long long epoch, timeout_ns;
+    int64_t n_fh, n_fg;
+    const int32_t* fh_pos; const int32_t* fh_ptr;
+    const int32_t* fg_pos; const int32_t* fg_ptr;
+    int64_t off_h, off_g, off_scal, off_stg_h, off_stg_g, off_stg_scal;
+    double t;
+    int* err;                           // set to 1 when a peer's flag did not arrive in time
+};
+
+// out[pos[j]] = sum of stg[ptr[j] .. ptr[j+1]) in list (= source-rank) order.  FIN_U entries per thread with all
+// index loads, then all value loads, issued together: the fused finish runs in ONE CTA, so memory-level
+// parallelism per thread is what bounds it.
+constexpr int FIN_U = 4;
+__device__ __forceinline__ void finish_family(const double* stg, double* out, const int32_t* __restrict__ pos,
+                                              const int32_t* __restrict__ ptr, const int64_t n, const int bid, const int nb) {
+    for (int64_t base = (int64_t)bid * blockDim.x * FIN_U; base < n; base += (int64_t)nb * blockDim.x * FIN_U) {
+        int r0[FIN_U], r1[FIN_U], ps[FIN_U];
+#pragma unroll
+        for (int u = 0; u < FIN_U; ++u) {
+            const int64_t j = base + (int64_t)u * blockDim.x + threadIdx.x;
+            const bool ok = j < n;
+            r0[u] = ok ? __ldg(&ptr[j]) : 0;
+            r1[u] = ok ? __ldg(&ptr[j + 1]) : 0;
+            ps[u] = ok ? __ldg(&pos[j]) : -1;
+        }
+        double a[FIN_U], b[FIN_U];
+#pragma unroll
+        for (int u = 0; u < FIN_U; ++u) {
+            a[u] = (r0[u] < r1[u]) ? __ldcg(&stg[r0[u]]) : 0.0;
+            b[u] = (r0[u] + 1 < r1[u]) ? __ldcg(&stg[r0[u] + 1]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < FIN_U; ++u) {
+            if (ps[u] < 0) continue;
+            double acc = a[u] + b[u];
+            for (int r = r0[u] + 2; r < r1[u]; ++r) acc += __ldcg(&stg[r]);  // more than two source ranks: mesh corners
+            out[ps[u]] = acc;
+        }
+    }
+}
+
+// Owner side.  CTA `bid` of `nb`: wait until every rank (this one included) has published `epoch`, then sum
+// the staged interface values in source-rank order and fold the scalars.
+__device__ __forceinline__ void finish_body(const FinishParams& P, const int bid, const int nb, unsigned long long* dbg = nullptr) {
+    // the index lists are level data: pull them into L2 while the peers' flags are still on their way
+    for (int64_t j = ((int64_t)bid * blockDim.x + threadIdx.x) * 32; j < P.n_fh; j += (int64_t)nb * blockDim.x * 32) {
+        prefetch_l2(P.fh_ptr + j); prefetch_l2(P.fh_pos + j);
+    }
+    for (int64_t j = ((int64_t)bid * blockDim.x + threadIdx.x) * 32; j < P.n_fg; j += (int64_t)nb * blockDim.x * 32) {
+        prefetch_l2(P.fg_ptr + j); prefetch_l2(P.fg_pos + j);
+    }
+    if ((int)threadIdx.x < P.nranks) {
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(P.flag + threadIdx.x) < P.epoch) {
+            if (global_timer_ns() - t0 > P.timeout_ns) { atomicExch(P.err, 1); break; }
+        }
+    }
+    __syncthreads();
+    if (dbg && threadIdx.x == 0) dbg[4] = global_timer_ns();
+    // staged values were written by peers: L2-coherent loads, never the read-only (nc) path
+    finish_family(P.win + P.off_stg_h, P.win + P.off_h, P.fh_pos, P.fh_ptr, P.n_fh, bid, nb);
+    finish_family(P.win + P.off_stg_g, P.win + P.off_g, P.fg_pos, P.fg_ptr, P.n_fg, bid, nb);
+    if (bid == nb - 1 && threadIdx.x == 0) {
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+        for (int r = 0; r < P.nranks; ++r) {  // rank order: identical result on every rank
+            const double* d = P.win + P.off_stg_scal + 4 * r;
+            s0 += __ldcg(d + 0); s1 += __ldcg(d + 1); s2 += __ldcg(d + 2);
+        }
+        double* scal = P.win + P.off_scal;
+        scal[0] = s0 + P.t * s1;
+        scal[1] = (s2 == 0.0) ? 1.0 : 0.0;
+        scal[2] = s1;
+        scal[3] = s2;
+    }
 }
 
 struct PushParams {
@@ -43,17 +129,27 @@ struct PushParams {
     int rank, nranks;
     unsigned long long epoch;
     unsigned int* counter;                 // CTA retirement counter (zero between launches)
+    int64_t h_rot;                         // rotation of the Hessian block order (remote destinations first)
+    int fused;                             // the last CTA also runs the owner-side finish (F)
+    FinishParams F;
+    unsigned long long* dbg;               // optional timeline slots of this epoch (MGB_DIST_DEBUG), else null
 };
+
+// timeline slots (globaltimer ns): 0 first CTA start (min), 1 last CTA's stores issued (max), 2 last ticket taken,
+// 3 flags published, 4 all flags seen, 5 finish done, 6 stamp before the element kernel
+static __global__ void stamp_kernel(unsigned long long* slot) { *slot = global_timer_ns(); }
 
 __device__ __forceinline__ double* dist_dst(const PushParams& P, int32_t d) {
     return P.win[d >> DIST_RANK_SHIFT] + (d & DIST_OFF_MASK);
 }
 
-static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant__ PushParams P) {
+static __global__ void __launch_bounds__(256, 6) push_kernel(const __grid_constant__ PushParams P) {
     const GatherParams& G = P.G;
     const int64_t b = blockIdx.x;
+    if (P.dbg && threadIdx.x == 0) atomicMin(&P.dbg[0], global_timer_ns());
     if (b < G.nblk_h) {
-        const int64_t base = b * (256 * GATHER_UNROLL) + threadIdx.x;
+        const int64_t bb = (b + P.h_rot < G.nblk_h) ? b + P.h_rot : b + P.h_rot - G.nblk_h;
+        const int64_t base = bb * (256 * GATHER_UNROLL) + threadIdx.x;
         int2 src[GATHER_UNROLL];
         int32_t dst[GATHER_UNROLL];
 #pragma unroll
@@ -62,6 +158,7 @@ static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant_
             src[j] = (t < G.nnzH) ? __ldg(&G.h_src2[t]) : make_int2(-1, -1);
             dst[j] = (t < G.nnzH) ? __ldg(&P.h_dest[t]) : 0;
         }
+        pdl_wait_primary();
         double v0[GATHER_UNROLL], v1[GATHER_UNROLL];
 #pragma unroll
         for (int j = 0; j < GATHER_UNROLL; ++j) {
@@ -75,6 +172,7 @@ static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant_
         }
     } else if (b < G.nblk_h + G.nblk_l) {
         const int64_t li = (b - G.nblk_h) * 256 + threadIdx.x;
+        pdl_wait_primary();
         if (li < G.n_long) {
             const int64_t c0 = __ldg(&G.h_lptr[li]), c1 = __ldg(&G.h_lptr[li + 1]);
             double acc = 0.0;
@@ -83,6 +181,7 @@ static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant_
         }
     } else if (b < G.nblk_h + G.nblk_l + G.nblk_g) {
         const int64_t a = (b - G.nblk_h - G.nblk_l) * 256 + threadIdx.x;
+        pdl_wait_primary();
         if (a < G.m) {
             const int32_t d = __ldg(&P.g_dest[a]);
             if (d >= 0) {
@@ -94,6 +193,7 @@ static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant_
         }
     } else {
         // this rank's scalar partials {sum w F, <c,Dz>_w, infeasible count} -> every rank's staging row
+        pdl_wait_primary();
         __shared__ double sh[3][256];
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int64_t r = threadIdx.x; r < G.nparts; r += blockDim.x) {
@@ -117,75 +217,33 @@ static __global__ void __launch_bounds__(256) push_kernel(const __grid_constant_
         }
     }
     // ---- publish: the last CTA to retire raises this rank's epoch flag in every peer's window
+    __shared__ int s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
+        if (P.dbg) atomicMax(&P.dbg[1], global_timer_ns());
         __threadfence_system();
         const unsigned int prev = atomicAdd(P.counter, 1u);
-        if (prev == gridDim.x - 1) {
+        const int last = (prev == gridDim.x - 1) ? 1 : 0;
+        if (last) {
+            if (P.dbg) P.dbg[2] = global_timer_ns();
             atomicExch(P.counter, 0u);
-            __threadfence_system();
-            for (int p = 0; p < P.nranks; ++p) st_release_sys(P.flag[p] + P.rank, P.epoch);
+            __threadfence_system();  // one fence orders everything the grid stored before ALL flag stores below
+            for (int p = 0; p < P.nranks; ++p) st_relaxed_sys(P.flag[p] + P.rank, P.epoch);
+            if (P.dbg) P.dbg[3] = global_timer_ns();
         }
+        s_last = last;
+    }
+    __syncthreads();
+    // fused owner-side finish: the interface is a few thousand entries, one CTA folds it while the grid drains
+    if (s_last && P.fused) {
+        finish_body(P.F, 0, 1, P.dbg);
+        __syncthreads();
+        if (P.dbg && threadIdx.x == 0) P.dbg[5] = global_timer_ns();
     }
 }
 
-struct FinishParams {
-    double* win;                        // this rank's window (this epoch's parity)
-    const unsigned long long* flag;     // this rank's flag array (written by the peers)
-    int nranks;
-    unsigned long long epoch, timeout_ns;
-    int64_t n_fh, n_fg;
-    const int32_t* fh_pos; const int32_t* fh_ptr;
-    const int32_t* fg_pos; const int32_t* fg_ptr;
-    int64_t off_h, off_g, off_scal, off_stg_h, off_stg_g, off_stg_scal;
-    double t;
-    int64_t nblk_h, nblk_g;
-    int* err;                           // set to 1 when a peer's flag did not arrive in time
-};
-
 static __global__ void __launch_bounds__(256) finish_kernel(const FinishParams P) {
-    // every CTA waits until all ranks (this one included) have published epoch `epoch`
-    if ((int)threadIdx.x < P.nranks) {
-        const unsigned long long t0 = global_timer_ns();
-        while (ld_acquire_sys(P.flag + threadIdx.x) < P.epoch) {
-            if (global_timer_ns() - t0 > P.timeout_ns) { atomicExch(P.err, 1); break; }
-        }
-    }
-    __syncthreads();
-    const int64_t b = blockIdx.x;
-    // staged values were written by peers: plain (coherent) loads, never the read-only path
-    if (b < P.nblk_h) {
-        const int64_t j = b * 256 + threadIdx.x;
-        if (j < P.n_fh) {
-            const double* __restrict__ stg = P.win + P.off_stg_h;
-            double acc = 0.0;
-            for (int r = __ldg(&P.fh_ptr[j]); r < __ldg(&P.fh_ptr[j + 1]); ++r) acc += __ldcg(&stg[r]);
-            P.win[P.off_h + __ldg(&P.fh_pos[j])] = acc;
-        }
-        return;
-    }
-    if (b < P.nblk_h + P.nblk_g) {
-        const int64_t j = (b - P.nblk_h) * 256 + threadIdx.x;
-        if (j < P.n_fg) {
-            const double* __restrict__ stg = P.win + P.off_stg_g;
-            double acc = 0.0;
-            for (int r = __ldg(&P.fg_ptr[j]); r < __ldg(&P.fg_ptr[j + 1]); ++r) acc += __ldcg(&stg[r]);
-            P.win[P.off_g + __ldg(&P.fg_pos[j])] = acc;
-        }
-        return;
-    }
-    if (threadIdx.x == 0) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int r = 0; r < P.nranks; ++r) {  // rank order: identical result on every rank
-            const double* d = P.win + P.off_stg_scal + 4 * r;
-            s0 += __ldcg(d + 0); s1 += __ldcg(d + 1); s2 += __ldcg(d + 2);
-        }
-        double* scal = P.win + P.off_scal;
-        scal[0] = s0 + P.t * s1;
-        scal[1] = (s2 == 0.0) ? 1.0 : 0.0;
-        scal[2] = s1;
-        scal[3] = s2;
-    }
+    finish_body(P, (int)blockIdx.x, (int)gridDim.x);
 }
 
 }  // namespace mgb

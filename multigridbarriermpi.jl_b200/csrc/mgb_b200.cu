@@ -124,12 +124,15 @@ struct mgb_plan {
         DevBuf<int32_t> h_dest, g_dest, fh_pos, fh_ptr, fg_pos, fg_ptr;
         DevBuf<unsigned int> counter;
         DevBuf<int> err;
+        DevBuf<unsigned long long> dbg;  // MGB_DIST_DEBUG: ring of 512 epochs x 8 timeline slots
         void* window = nullptr;        // [parity 0 | parity 1 | flags]; cudaMalloc'ed, exported by IPC handle
         size_t window_bytes = 0;
         void* peer[mgb::DIST_MAX_RANKS] = {nullptr};
         bool peer_ipc[mgb::DIST_MAX_RANKS] = {false};
         bool attached = false;
         unsigned long long epoch = 0;
+        bool finish_pending = false;
+        int64_t h_rot = 0;             // first push block whose entries belong to a higher rank (remote stores first)
         double timeout_s = 2.0;
         ~Dist() {
             for (int p = 0; p < mgb::DIST_MAX_RANKS; ++p)
@@ -214,6 +217,27 @@ void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     mgb::launch_element(ep.B, ep.dim, ep.slack, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
     g_launches++;
     CUDA_OK(cudaGetLastError());
+}
+
+// Launch as a programmatic dependent of the previous kernel in the stream (PDL): the kernel may start while
+// the element kernel's last wave drains and blocks at griddepcontrol.wait until its records are complete.
+// Falls back to a plain launch when the attribute is rejected (MGB_NO_PDL=1 disables it for A/B runs).
+bool g_pdl_ok = getenv("MGB_NO_PDL") == nullptr;
+
+template <class Params>
+void launch_dependent(void (*kernel)(Params), unsigned grid, unsigned block, cudaStream_t st, const Params& params, bool allow_pdl) {
+    if (allow_pdl && g_pdl_ok) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kernel, params) == cudaSuccess) return;
+        cudaGetLastError();
+        g_pdl_ok = false;
+    }
+    kernel<<<grid, block, 0, st>>>(params);
 }
 
 mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, double* Dz) {
@@ -301,7 +325,8 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         G.want_h = G.want_g = 0;
     }
     size_gather_grid(pl, G);
-    mgb::gather_kernel<<<(unsigned)(G.nblk_h + G.nblk_l + G.nblk_g + 1), 256, 0, st>>>(G);
+    launch_dependent(mgb::gather_kernel, (unsigned)(G.nblk_h + G.nblk_l + G.nblk_g + 1), 256u, st, G,
+                     /*allow_pdl=*/mid == nullptr && !pl->long_lists);
     g_launches++;
     CUDA_OK(cudaGetLastError());
 }
@@ -826,6 +851,18 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
             CUDA_OK(cudaStreamSynchronize(st));
             pl->dev_bytes += dd->window_bytes + dd->h_dest.bytes() + dd->g_dest.bytes();
             if (const char* ev = getenv("MGB_DIST_TIMEOUT_S")) dd->timeout_s = atof(ev) > 0 ? atof(ev) : dd->timeout_s;
+            if (getenv("MGB_DIST_DEBUG")) {
+                std::vector<unsigned long long> init(512 * 8, 0ull);
+                for (int k = 0; k < 512; ++k) init[k * 8] = ~0ull;
+                dd->dbg.upload(init, st);
+                CUDA_OK(cudaStreamSynchronize(st));
+            }
+            // block order of the push kernel: entries of higher ranks first, then lower ranks, own entries last,
+            // so the NVLink stores are in flight while the local part runs
+            int64_t first_after = (int64_t)M.h_dest.size();
+            for (int64_t k = 0; k < (int64_t)M.h_dest.size(); ++k)
+                if ((M.h_dest[k] >> mgb::DIST_RANK_SHIFT) > rank) { first_after = k; break; }
+            dd->h_rot = getenv("MGB_DIST_NOROT") ? 0 : first_after / (256 * mgb::GATHER_UNROLL);
         }
         pl->dist = std::move(dd);
         *out = pl.release();
@@ -924,33 +961,85 @@ int mgb_dist_attach_local(mgb_plan* pl, void* const* windows_dev) {
     return 0;
 }
 
+namespace {
+mgb::FinishParams make_finish_params(mgb_plan* pl, double t, int flags) {
+    auto& dd = *pl->dist;
+    const auto& M = dd.maps;
+    const auto& L = M.lay[M.rank];
+    const int par = (int)(dd.epoch & 1ull);
+    mgb::FinishParams F{};
+    char* base = static_cast<char*>(dd.window);
+    F.win = reinterpret_cast<double*>(base) + (size_t)par * L.size;
+    F.flag = reinterpret_cast<const unsigned long long*>(base + (size_t)2 * L.size * 8);
+    F.nranks = M.nranks; F.epoch = dd.epoch; F.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9);
+    F.n_fh = (flags & MGB_WANT_HESS) ? (int64_t)M.fh_pos.size() : 0;
+    F.n_fg = (flags & MGB_WANT_GRAD) ? (int64_t)M.fg_pos.size() : 0;
+    F.fh_pos = dd.fh_pos.p; F.fh_ptr = dd.fh_ptr.p; F.fg_pos = dd.fg_pos.p; F.fg_ptr = dd.fg_ptr.p;
+    F.off_h = L.off_h; F.off_g = L.off_g; F.off_scal = L.off_scal; F.off_stg_h = L.off_stg_h;
+    F.off_stg_g = L.off_stg_g; F.off_stg_scal = L.off_stg_scal; F.t = t;
+    F.err = dd.err.p;
+    return F;
+}
+
+void dist_outputs(mgb_plan* pl, const double** hval_own_dev, const double** grad_own_dev, const double** scal_dev) {
+    auto& dd = *pl->dist;
+    const auto& L = dd.maps.lay[dd.maps.rank];
+    const double* win = static_cast<const double*>(dd.window) + (size_t)(dd.epoch & 1ull) * L.size;
+    if (hval_own_dev) *hval_own_dev = win + L.off_h;
+    if (grad_own_dev) *grad_own_dev = win + L.off_g;
+    if (scal_dev) *scal_dev = win + L.off_scal;
+}
+
+// element kernel + push kernel of a new epoch; fused: the push kernel's last CTA also runs the owner-side finish
+void dist_launch(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int flags, bool fused) {
+    auto& dd = *pl->dist;
+    if (!dd.attached) throw std::runtime_error("peers not attached (mgb_dist_attach)");
+    CUDA_OK(cudaSetDevice(pl->ctx->device));
+    cudaStream_t st = pl->ctx->stream;
+    const auto& M = dd.maps;
+    dd.epoch++;
+    dd.finish_pending = !fused;
+    const int par = (int)(dd.epoch & 1ull);
+    unsigned long long* dbg = dd.dbg.p ? dd.dbg.p + (dd.epoch % 512) * 8 : nullptr;
+    if (dbg) mgb::stamp_kernel<<<1, 1, 0, st>>>(dbg + 6);
+    mgb::ElemParams E = make_elem_params(pl, s_dev, Dz0_dev, c_dev, t, nullptr);
+    launch_elem(pl, E, flags & 7);
+    mgb::PushParams P{};
+    P.dbg = dbg;
+    P.G = make_gather_params(pl, flags, t, nullptr, nullptr, nullptr);
+    size_gather_grid(pl, P.G);
+    P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p;
+    for (int p = 0; p < M.nranks; ++p) {
+        char* base = static_cast<char*>(dd.peer[p]);
+        P.win[p] = reinterpret_cast<double*>(base) + (size_t)par * M.lay[p].size;
+        P.flag[p] = reinterpret_cast<unsigned long long*>(base + (size_t)2 * M.lay[p].size * 8);
+        P.scal_off[p] = M.lay[p].off_stg_scal + 4 * (int64_t)M.rank;
+    }
+    P.rank = M.rank; P.nranks = M.nranks; P.epoch = dd.epoch; P.counter = dd.counter.p;
+    P.h_rot = P.G.nblk_h > 0 ? dd.h_rot % P.G.nblk_h : 0;
+    P.fused = fused ? 1 : 0;
+    P.F = make_finish_params(pl, t, flags);
+    launch_dependent(mgb::push_kernel, (unsigned)(P.G.nblk_h + P.G.nblk_l + P.G.nblk_g + 1), 256u, st, P, true);
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+}
+}  // namespace
+
+int mgb_dist_debug(mgb_plan* pl, uint64_t* out512x8) {
+    try {
+        if (!pl || !pl->dist || !pl->dist->dbg.p || !out512x8) return fail("mgb_dist_debug: timeline not enabled (MGB_DIST_DEBUG=1 at plan creation)");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        CUDA_OK(cudaStreamSynchronize(pl->ctx->stream));
+        CUDA_OK(cudaMemcpy(out512x8, pl->dist->dbg.p, 512 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_debug: ") + ex.what()); }
+}
+
 int mgb_dist_begin(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags) {
     try {
         if (!pl || !pl->dist || !s_dev || !c_dev) return fail("mgb_dist_begin: NULL argument / not a distributed plan");
         if (!pl->ctx) return fail("mgb_dist_begin: symbolic-only plan; no CPU path exists");
-        auto& dd = *pl->dist;
-        if (!dd.attached) return fail("mgb_dist_begin: peers not attached (mgb_dist_attach)");
-        CUDA_OK(cudaSetDevice(pl->ctx->device));
-        cudaStream_t st = pl->ctx->stream;
-        const auto& M = dd.maps;
-        dd.epoch++;
-        const int par = (int)(dd.epoch & 1ull);
-        mgb::ElemParams E = make_elem_params(pl, s_dev, Dz0_dev, c_dev, t, nullptr);
-        launch_elem(pl, E, flags & 7);
-        mgb::PushParams P{};
-        P.G = make_gather_params(pl, flags, t, nullptr, nullptr, nullptr);
-        size_gather_grid(pl, P.G);
-        P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p;
-        for (int p = 0; p < M.nranks; ++p) {
-            char* base = static_cast<char*>(dd.peer[p]);
-            P.win[p] = reinterpret_cast<double*>(base) + (size_t)par * M.lay[p].size;
-            P.flag[p] = reinterpret_cast<unsigned long long*>(base + (size_t)2 * M.lay[p].size * 8);
-            P.scal_off[p] = M.lay[p].off_stg_scal + 4 * (int64_t)M.rank;
-        }
-        P.rank = M.rank; P.nranks = M.nranks; P.epoch = dd.epoch; P.counter = dd.counter.p;
-        mgb::push_kernel<<<(unsigned)(P.G.nblk_h + P.G.nblk_l + P.G.nblk_g + 1), 256, 0, st>>>(P);
-        g_launches++;
-        CUDA_OK(cudaGetLastError());
+        dist_launch(pl, s_dev, Dz0_dev, c_dev, t, flags, /*fused=*/false);
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_dist_begin: ") + ex.what()); }
 }
@@ -960,37 +1049,29 @@ int mgb_dist_end(mgb_plan* pl, double t, int32_t flags, const double** hval_own_
     try {
         if (!pl || !pl->dist || !pl->ctx) return fail("mgb_dist_end: not a distributed device plan");
         auto& dd = *pl->dist;
-        if (dd.epoch == 0) return fail("mgb_dist_end: no mgb_dist_begin in flight");
+        if (!dd.finish_pending) return fail("mgb_dist_end: no mgb_dist_begin in flight");
         CUDA_OK(cudaSetDevice(pl->ctx->device));
-        const auto& M = dd.maps;
-        const auto& L = M.lay[M.rank];
-        const int par = (int)(dd.epoch & 1ull);
-        mgb::FinishParams F{};
-        char* base = static_cast<char*>(dd.window);
-        F.win = reinterpret_cast<double*>(base) + (size_t)par * L.size;
-        F.flag = reinterpret_cast<const unsigned long long*>(base + (size_t)2 * L.size * 8);
-        F.nranks = M.nranks; F.epoch = dd.epoch; F.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9);
-        F.n_fh = (flags & MGB_WANT_HESS) ? (int64_t)M.fh_pos.size() : 0;
-        F.n_fg = (flags & MGB_WANT_GRAD) ? (int64_t)M.fg_pos.size() : 0;
-        F.fh_pos = dd.fh_pos.p; F.fh_ptr = dd.fh_ptr.p; F.fg_pos = dd.fg_pos.p; F.fg_ptr = dd.fg_ptr.p;
-        F.off_h = L.off_h; F.off_g = L.off_g; F.off_scal = L.off_scal; F.off_stg_h = L.off_stg_h;
-        F.off_stg_g = L.off_stg_g; F.off_stg_scal = L.off_stg_scal; F.t = t;
-        F.nblk_h = (F.n_fh + 255) / 256; F.nblk_g = (F.n_fg + 255) / 256; F.err = dd.err.p;
-        mgb::finish_kernel<<<(unsigned)(F.nblk_h + F.nblk_g + 1), 256, 0, pl->ctx->stream>>>(F);
+        mgb::FinishParams F = make_finish_params(pl, t, flags);
+        const int64_t work = std::max<int64_t>(F.n_fh, F.n_fg);
+        const unsigned nb = (unsigned)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 64);
+        mgb::finish_kernel<<<nb, 256, 0, pl->ctx->stream>>>(F);
         g_launches++;
         CUDA_OK(cudaGetLastError());
-        if (hval_own_dev) *hval_own_dev = F.win + L.off_h;
-        if (grad_own_dev) *grad_own_dev = F.win + L.off_g;
-        if (scal_dev) *scal_dev = F.win + L.off_scal;
+        dd.finish_pending = false;
+        dist_outputs(pl, hval_own_dev, grad_own_dev, scal_dev);
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_dist_end: ") + ex.what()); }
 }
 
 int mgb_dist_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                       int32_t flags, const double** hval_own_dev, const double** grad_own_dev, const double** scal_dev) {
-    int rc = mgb_dist_begin(pl, s_dev, Dz0_dev, c_dev, t, flags);
-    if (rc) return rc;
-    return mgb_dist_end(pl, t, flags, hval_own_dev, grad_own_dev, scal_dev);
+    try {
+        if (!pl || !pl->dist || !s_dev || !c_dev) return fail("mgb_dist_assemble: NULL argument / not a distributed plan");
+        if (!pl->ctx) return fail("mgb_dist_assemble: symbolic-only plan; no CPU path exists");
+        dist_launch(pl, s_dev, Dz0_dev, c_dev, t, flags, /*fused=*/true);
+        dist_outputs(pl, hval_own_dev, grad_own_dev, scal_dev);
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_assemble: ") + ex.what()); }
 }
 
 }  // extern "C"

@@ -112,6 +112,54 @@ def test_missing_peer_times_out_without_hanging(gpu_ctx):
         pl.close()
 
 
+def test_fused_finish_two_streams(gpu_ctx):
+    """mgb_dist_assemble (finish fused into the push kernel's last CTA): two ranks on two streams of one GPU,
+    each waiting in-kernel for the other's epoch flag."""
+    import torch
+    import mgb_b200
+    from mgb_b200 import capi
+    from mgb_b200.hpc import uniform_partition
+    from helpers import problem, oracle_eval
+    geom = mgb_b200.fem2d(4)
+    pr = problem(geom)
+    n, m = geom.x.shape[0], pr["R"].shape[1]
+    rp, op = uniform_partition(n, 2, geom.block) - 1, uniform_partition(m, 2) - 1
+    dev = torch.device("cuda", gpu_ctx.device)
+    streams = [torch.cuda.Stream(dev) for _ in range(2)]
+    ctxs = [capi.Context(gpu_ctx.device, st.cuda_stream) for st in streams]
+    plans = [capi.DistPlan(ctxs[r], pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, r, 2, rp, op) for r in range(2)]
+    wins = [pl.window()[0] for pl in plans]
+    for pl in plans:
+        pl.attach_local(wins)
+    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
+    cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
+    ins = [(cm(Dz0[rp[r]:rp[r + 1]]), cm(pr["c"][rp[r]:rp[r + 1]])) for r in range(2)]
+    s_d = torch.from_numpy(pr["s"]).to(dev)
+    torch.cuda.synchronize(dev)
+    t = 0.9
+    f0_o, g_o, H_o = oracle_eval(pr, t)
+    for rep in range(6):   # repeated epochs, alternating which rank launches first
+        order = (0, 1) if rep % 2 == 0 else (1, 0)
+        ptrs = {}
+        for r in order:
+            ptrs[r] = plans[r].dist_assemble(s_d, ins[r][0], ins[r][1], t, 7)
+        for r in range(2):
+            d = plans[r].dinfo
+            hp, gp, sp_ = ptrs[r]
+            h_own, g_own, scal = ctxs[r].to_host(hp, d["n_own_h"]), ctxs[r].to_host(gp, d["n_own_g"]), ctxs[r].to_host(sp_, 4)
+            orp, oci = plans[r].own_pattern()
+            lo, hi = d["own0"], d["own1"]
+            Hown = sp.csr_matrix((h_own, oci.astype(np.int64), orp.astype(np.int64)), shape=(hi - lo, m))
+            assert abs(Hown - H_o[lo:hi]).max() <= 1e-12 * abs(H_o).max()
+            assert np.abs(g_own - g_o[lo:hi]).max() <= 1e-12 * np.abs(g_o).max()
+            assert abs(scal[0] - f0_o) <= 1e-12 * abs(f0_o) and scal[1] == 1.0
+            assert plans[r].dist_info()["err"] == 0
+    for pl in plans:
+        pl.close()
+    for c in ctxs:
+        c.close()
+
+
 def test_two_gpu_peer_exchange_matches_oracle():
     import torch
     if torch.cuda.device_count() < 2:
