@@ -159,6 +159,11 @@ int mgb_scatter_add_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* idx_
 int mgb_segsum_idx(mgb_ctx* ctx, const double* src_dev, const int32_t* ptr_dev, const int32_t* idx_dev, int64_t nout,
                    double* dst_dev);
 
+/* Page-lock caller-owned host arrays (e.g. the Julia Vector that receives nzval) once, so the D2H copies of
+ * mgb_assemble_host run at PCIe DMA rate instead of the pageable-memory rate; undo before the array is freed. */
+int mgb_host_register(void* ptr_host, int64_t bytes);
+int mgb_host_unregister(void* ptr_host);
+
 /* stream-ordered device -> host copy on the ctx stream, then synchronise (results that live in library-owned
  * device memory, e.g. the exchange window of mgb_dist_end) */
 int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);

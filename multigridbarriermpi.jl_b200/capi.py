@@ -27,7 +27,7 @@ EXPORTS = [
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
-    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_dist_debug",
+    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_dist_debug", "mgb_host_register", "mgb_host_unregister",
 ]
 
 
@@ -101,6 +101,8 @@ def load(build_if_missing: bool = True):
                                          C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.c_int32,
                                          C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]
     lib.mgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.mgb_host_register.argtypes = [C.c_void_p, C.c_int64]
+    lib.mgb_host_unregister.argtypes = [C.c_void_p]
     lib.mgb_dist_debug.argtypes = [C.c_void_p, C.c_void_p]
     lib.mgb_dist_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.mgb_dist_layout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
@@ -143,6 +145,15 @@ class DeviceView:
     def __init__(self, ptr: int, count: int):
         self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
                                          "version": 2, "strides": None}
+
+
+def host_register(a: np.ndarray):
+    """page-lock a caller-owned numpy array in place (mgb_host_register)"""
+    _check(load().mgb_host_register(a.ctypes.data, a.nbytes))
+
+
+def host_unregister(a: np.ndarray):
+    _check(load().mgb_host_unregister(a.ctypes.data))
 
 
 def launch_count() -> int:
@@ -268,17 +279,21 @@ class Plan:
         _check(load().mgb_assemble(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags),
                                    _ptr(scal_dev), _ptr(grad_dev), _ptr(hval_dev), _ptr(Dz_dev)))
 
-    def assemble_host(self, s, Dz0, c, t: float, flags: int, upload_inputs: bool = True):
-        """Host-buffer call; returns dict(scal, grad, hval, Dz) of numpy arrays (only requested ones)."""
+    def assemble_host(self, s, Dz0, c, t: float, flags: int, upload_inputs: bool = True, out: Optional[dict] = None):
+        """Host-buffer call; returns dict(scal, grad, hval, Dz) of numpy arrays (only requested ones).
+        ``out``: reuse the arrays of a previous call (e.g. page-locked with host_register)."""
         s = np.ascontiguousarray(s, dtype=np.float64)
         assert s.shape == (self.m,)
         nd = self.n_local * self.nD
         Dz0 = None if Dz0 is None else np.asfortranarray(Dz0, dtype=np.float64)
         c = None if c is None else np.asfortranarray(c, dtype=np.float64)
-        scal = np.zeros(4)
-        grad = np.zeros(self.m) if flags & WANT_GRAD else None
-        hval = np.zeros(self.nnzH) if flags & WANT_HESS else None
-        Dz = np.zeros((self.n_local, self.nD), order="F") if flags & STORE_DZ else None
+        if out is not None:
+            scal, grad, hval, Dz = out["scal"], out["grad"], out["hval"], out["Dz"]
+        else:
+            scal = np.zeros(4)
+            grad = np.zeros(self.m) if flags & WANT_GRAD else None
+            hval = np.zeros(self.nnzH) if flags & WANT_HESS else None
+            Dz = np.zeros((self.n_local, self.nD), order="F") if flags & STORE_DZ else None
         _check(load().mgb_assemble_host(self._h, _ptr(s), _ptr(Dz0), _ptr(c), int(upload_inputs), float(t), int(flags),
                                         _ptr(scal), _ptr(grad), _ptr(hval), _ptr(Dz)))
         assert nd >= 0

@@ -56,6 +56,7 @@ struct FinishParams {
 // index loads, then all value loads, issued together: the fused finish runs in ONE CTA, so memory-level
 // parallelism per thread is what bounds it.
 constexpr int FIN_U = 4;
+constexpr int FIN_CTAS = 8;   // CTAs that share the fused owner-side finish
 __device__ __forceinline__ void finish_family(const double* stg, double* out, const int32_t* __restrict__ pos,
                                               const int32_t* __restrict__ ptr, const int64_t n, const int bid, const int nb) {
     for (int64_t base = (int64_t)bid * blockDim.x * FIN_U; base < n; base += (int64_t)nb * blockDim.x * FIN_U) {
@@ -105,7 +106,7 @@ __device__ __forceinline__ void finish_body(const FinishParams& P, const int bid
     // staged values were written by peers: L2-coherent loads, never the read-only (nc) path
     finish_family(P.win + P.off_stg_h, P.win + P.off_h, P.fh_pos, P.fh_ptr, P.n_fh, bid, nb);
     finish_family(P.win + P.off_stg_g, P.win + P.off_g, P.fg_pos, P.fg_ptr, P.n_fg, bid, nb);
-    if (bid == nb - 1 && threadIdx.x == 0) {
+    if (bid == 0 && threadIdx.x == 0) {
         double s0 = 0.0, s1 = 0.0, s2 = 0.0;
         for (int r = 0; r < P.nranks; ++r) {  // rank order: identical result on every rank
             const double* d = P.win + P.off_stg_scal + 4 * r;
@@ -217,28 +218,30 @@ static __global__ void __launch_bounds__(256, 6) push_kernel(const __grid_consta
         }
     }
     // ---- publish: the last CTA to retire raises this rank's epoch flag in every peer's window
-    __shared__ int s_last;
+    __shared__ int s_slot;
     __syncthreads();
     if (threadIdx.x == 0) {
         if (P.dbg) atomicMax(&P.dbg[1], global_timer_ns());
         __threadfence_system();
         const unsigned int prev = atomicAdd(P.counter, 1u);
-        const int last = (prev == gridDim.x - 1) ? 1 : 0;
-        if (last) {
+        const int slot = (int)(gridDim.x - 1 - prev);      // 0 for the last CTA to retire
+        if (slot == 0) {
             if (P.dbg) P.dbg[2] = global_timer_ns();
             atomicExch(P.counter, 0u);
             __threadfence_system();  // one fence orders everything the grid stored before ALL flag stores below
             for (int p = 0; p < P.nranks; ++p) st_relaxed_sys(P.flag[p] + P.rank, P.epoch);
             if (P.dbg) P.dbg[3] = global_timer_ns();
         }
-        s_last = last;
+        s_slot = slot;
     }
     __syncthreads();
-    // fused owner-side finish: the interface is a few thousand entries, one CTA folds it while the grid drains
-    if (s_last && P.fused) {
-        finish_body(P.F, 0, 1, P.dbg);
+    // fused owner-side finish: the interface is a few thousand entries; the last FIN_CTAS CTAs to retire fold it
+    // (they spin on this rank's flag array until every rank, this one included, has published the epoch)
+    const int nfin = (int)min((unsigned)FIN_CTAS, gridDim.x);
+    if (P.fused && s_slot < nfin) {
+        finish_body(P.F, s_slot, nfin, s_slot == 0 ? P.dbg : nullptr);
         __syncthreads();
-        if (P.dbg && threadIdx.x == 0) P.dbg[5] = global_timer_ns();
+        if (P.dbg && s_slot == 0 && threadIdx.x == 0) P.dbg[5] = global_timer_ns();
     }
 }
 

@@ -802,6 +802,22 @@ int mgb_time_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, 
     } catch (const std::exception& ex) { return fail(std::string("mgb_time_assemble: ") + ex.what()); }
 }
 
+int mgb_host_register(void* ptr_host, int64_t bytes) {
+    try {
+        if (!ptr_host || bytes <= 0) return fail("mgb_host_register: bad argument");
+        CUDA_OK(cudaHostRegister(ptr_host, (size_t)bytes, cudaHostRegisterDefault));
+        return 0;
+    } catch (const std::exception& ex) { cudaGetLastError(); return fail(std::string("mgb_host_register: ") + ex.what()); }
+}
+
+int mgb_host_unregister(void* ptr_host) {
+    try {
+        if (!ptr_host) return fail("mgb_host_unregister: NULL argument");
+        CUDA_OK(cudaHostUnregister(ptr_host));
+        return 0;
+    } catch (const std::exception& ex) { cudaGetLastError(); return fail(std::string("mgb_host_unregister: ") + ex.what()); }
+}
+
 int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes) {
     try {
         if (!ctx || (bytes > 0 && (!dst_host || !src_dev))) return fail("mgb_copy_to_host: NULL argument");
