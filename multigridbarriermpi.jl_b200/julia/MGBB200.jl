@@ -14,6 +14,7 @@ module MGBB200
 using SparseArrays, LinearAlgebra
 using CUDA                      # device arrays only; no CUDA.jl kernels on the hot path
 using HPCSparseArrays: HPCVector, HPCMatrix, HPCSparseMatrix
+import MPI                      # already a dependency of the reference (Project.toml: MPI = "0.20")
 import MultiGridBarrier
 import MultiGridBarrier: Barrier
 
@@ -24,9 +25,13 @@ struct MgbCsr
     rowptr::Ptr{Int32}; colidx::Ptr{Int32}; vals::Ptr{Float64}
     index_base::Int32
 end
-struct MgbBarrier
+struct MgbBarrier          # field-for-field the C struct mgb_barrier (include/mgb_b200.h)
     kind::Int32; nidx::Int32; idx::NTuple{8,Int32}; p::Float64; slack::Int32
+    nidx2::Int32; idx2::NTuple{8,Int32}; p2::Float64          # optional second cone (parabolic_solve); nidx2 = 0: none
 end
+MgbBarrier(idx::Vector{Int}, p::Float64, slack::Bool; idx2::Vector{Int} = Int[], p2::Float64 = 2.0) =
+    MgbBarrier(1, length(idx), ntuple(i -> i <= length(idx) ? Int32(idx[i] - 1) : Int32(0), 8), p, slack,
+               length(idx2), ntuple(i -> i <= length(idx2) ? Int32(idx2[i] - 1) : Int32(0), 8), p2)
 
 lasterr() = unsafe_string(ccall((:mgb_last_error, LIB), Cstring, ()))
 check(rc) = rc == 0 ? nothing : error("libmgb_b200: " * lasterr())
@@ -49,7 +54,7 @@ mutable struct Plan; h::Ptr{Cvoid}; m::Int; nnzH::Int; rowptr::Vector{Int32}; co
 function Plan(ctx::Ctx, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::Matrix{Float64}, w::Vector{Float64};
               idx::Vector{Int}, p::Float64, slack::Bool = false, rows = (0, size(D[1], 1)))
     Ds = [csr(d) for d in D]; Rs = Ref(csr(R))
-    bar = Ref(MgbBarrier(1, length(idx), ntuple(i -> i <= length(idx) ? Int32(idx[i] - 1) : Int32(0), 8), p, slack))
+    bar = Ref(MgbBarrier(idx, p, slack))
     r = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve D R x w begin
         check(ccall((:mgb_plan_create, LIB), Cint,
@@ -100,19 +105,91 @@ pair (symbolic phase once per level) and return an HPCVector / HPCSparseMatrix o
 pattern, so `MultiGridBarrier.solve(H, g)` (MUMPS, test/test_newton_matrix_compare.jl:51) is unchanged.
 """
 function b200_barrier(; idx::Vector{Int}, p::Float64, ctx::Ctx = Ctx())
-    plans = IdDict{Any,Plan}()
-    getplan(x, w, R, D) = get!(plans, (R, D)) do
-        Plan(ctx, D, R, Matrix(x), Vector(w); idx = idx, p = p)
+    plans = IdDict{Any,Any}()
+    # per (R, D): the plan plus its device buffers.  Dz0 = D*z0 is refreshed when z0 changes (once per Newton
+    # solve: the operator-only plan built with R = I and MGB_PLAN_NO_HESSIAN gives D*z0 through mgb_apply_D).
+    function state(x, w, R, D)
+        get!(plans, (R, D)) do
+            pl = Plan(ctx, D, R, Matrix(x), Vector(w); idx = idx, p = p)
+            n, nD = size(D[1], 1), length(D)
+            (pl = pl, s = CUDA.zeros(Float64, pl.m), Dz0 = CUDA.zeros(Float64, n, nD), c = CUDA.zeros(Float64, n, nD),
+             scal = CUDA.zeros(Float64, 4), grad = CUDA.zeros(Float64, pl.m), hval = CUDA.zeros(Float64, pl.nnzH),
+             z0id = Ref{UInt}(0), cid = Ref{UInt}(0))
+        end
     end
     function run(flags, s, x, w, c, R, D, z0)
-        pl = getplan(x, w, R, D)
-        # Dz0 = D*z0 is recomputed by the caller once per Newton solve (operator-only plan, R = I)
-        error("wire Dz0 / device buffers of your HPCVector backend here; see INTEGRATION.md section 3")
+        st = state(x, w, R, D)
+        if objectid(z0) != st.z0id[]                       # new Newton solve: Dz0 = hcat([D_k*z0]...) (test/test_apply_d.jl:44)
+            copyto!(st.Dz0, reduce(hcat, [Vector(Dk * z0) for Dk in D])); st.z0id[] = objectid(z0)
+        end
+        if objectid(c) != st.cid[]
+            copyto!(st.c, Matrix(c)); st.cid[] = objectid(c)
+        end
+        copyto!(st.s, MultiGridBarrier._raw_array(s))      # src/MultiGridBarrierMPI.jl:175-176
+        assemble!(st.pl, st.s, st.Dz0, st.c, 1.0, flags; scal = st.scal, grad = st.grad, hval = st.hval)
+        st
     end
-    f0(s, x, w, c, R, D, z0) = run(WANT_F0, s, x, w, c, R, D, z0)
-    f1(s, x, w, c, R, D, z0) = run(WANT_GRAD, s, x, w, c, R, D, z0)
-    f2(s, x, w, c, R, D, z0) = run(WANT_HESS, s, x, w, c, R, D, z0)
+    backend(s) = s.backend
+    f0(s, x, w, c, R, D, z0) = (st = run(WANT_F0, s, x, w, c, R, D, z0); sc = Array(st.scal); sc[2] == 1.0 ? sc[1] : Inf)
+    f1(s, x, w, c, R, D, z0) = (st = run(WANT_GRAD, s, x, w, c, R, D, z0); HPCVector(Array(st.grad), backend(s)))
+    function f2(s, x, w, c, R, D, z0)
+        st = run(WANT_HESS, s, x, w, c, R, D, z0)
+        pl = st.pl                                          # frozen CSR pattern (0-based -> 1-based), values of this step
+        At = SparseMatrixCSC(pl.m, pl.m, Int32.(pl.rowptr .+ 1), Int32.(pl.colidx .+ 1), Array(st.hval))   # CSC of H' = CSR of H
+        HPCSparseMatrix(SparseMatrixCSC(transpose(At)), backend(s))
+    end
     Barrier(f0 = f0, f1 = f1, f2 = f2)
 end
+
+# ---- multi-GPU: one MPI rank per GPU (test/test_2d.jl:17-20), fused peer-memory exchange (mgb_dist_*) ----
+struct MgbIpcHandle; bytes::NTuple{64,UInt8}; end
+
+mutable struct DistPlan; h::Ptr{Cvoid}; rank::Int; nranks::Int; info::Vector{Int64}; rowptr::Vector{Int32}; colidx::Vector{Int32}; end
+
+"""
+    DistPlan(ctx, comm, D, R, x, w; idx, p, row_part, out_part)
+
+Collective over `comm` (MPI.Comm): every rank passes the SAME replicated operators (exactly what the reference
+holds: fem2d builds the full native mesh on every rank, src:239-240) and the 0-based partition offsets of the
+quadrature rows (whole elements) and of the unknowns (HPCSparseArrays row partition).  The 64-byte CUDA IPC
+handles of the exchange windows travel through one MPI.Allgather; afterwards no MPI/NCCL call is made per step.
+"""
+function DistPlan(ctx::Ctx, comm, D, R, x::Matrix{Float64}, w::Vector{Float64}; idx::Vector{Int}, p::Float64,
+                  row_part::Vector{Int64}, out_part::Vector{Int64}, slack::Bool = false)
+    rank, nranks = MPI.Comm_rank(comm), MPI.Comm_size(comm)
+    Ds = [csr(d) for d in D]; Rs = Ref(csr(R)); bar = Ref(MgbBarrier(idx, p, slack)); r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve D R x w row_part out_part begin
+        check(ccall((:mgb_dist_plan_create, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Int32, Ptr{MgbCsr}, Ref{MgbCsr}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{MgbBarrier},
+                     Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
+                    ctx.h, size(D[1], 1), length(D), Ds, Rs, size(x, 2), x, w, bar, rank, nranks, row_part, out_part, r))
+    end
+    mine = Ref(MgbIpcHandle(ntuple(_ -> 0x00, 64)))
+    check(ccall((:mgb_dist_export, LIB), Cint, (Ptr{Cvoid}, Ref{MgbIpcHandle}), r[], mine))
+    all = MPI.Allgather(mine[], comm)                       # Vector{MgbIpcHandle}, one per rank
+    check(ccall((:mgb_dist_attach, LIB), Cint, (Ptr{Cvoid}, Ptr{MgbIpcHandle}), r[], all))
+    MPI.Barrier(comm)                                       # every window mapped before the first store
+    info = zeros(Int64, 16)
+    check(ccall((:mgb_dist_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32), r[], info, 16))
+    rp = zeros(Int32, info[6] - info[5] + 1); ci = zeros(Int32, info[3])
+    check(ccall((:mgb_dist_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), r[], rp, ci))
+    DistPlan(r[], rank, nranks, info, rp, ci)               # destroy collectively: MPI.Barrier, then mgb_plan_destroy
+end
+
+"collective, same order on every rank; returns device pointers (owned H values, owned gradient block, 4 scalars)"
+function dist_assemble!(pl::DistPlan, s::CuVector{Float64}, Dz0::CuMatrix{Float64}, c::CuMatrix{Float64}, t::Float64, flags)
+    hp, gp, sp = Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}()
+    GC.@preserve s Dz0 c begin
+        check(ccall((:mgb_dist_assemble, LIB), Cint,
+                    (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Float64, Int32,
+                     Ref{CuPtr{Float64}}, Ref{CuPtr{Float64}}, Ref{CuPtr{Float64}}),
+                    pl.h, pointer(s), pointer(Dz0), pointer(c), t, flags, hp, gp, sp))
+    end
+    (unsafe_wrap(CuArray, hp[], pl.info[3]), unsafe_wrap(CuArray, gp[], pl.info[4]), unsafe_wrap(CuArray, sp[], 4))
+end
+
+"page-lock a Julia Array once so mgb_assemble_host copies into it at DMA rate"
+pin!(a::Array) = (check(ccall((:mgb_host_register, LIB), Cint, (Ptr{Cvoid}, Int64), a, sizeof(a))); a)
+unpin!(a::Array) = check(ccall((:mgb_host_unregister, LIB), Cint, (Ptr{Cvoid},), a))
 
 end # module
