@@ -133,6 +133,7 @@ struct mgb_plan {
         unsigned long long epoch = 0;
         bool finish_pending = false;
         int64_t h_rot = 0;             // first push block whose entries belong to a higher rank (remote stores first)
+        int64_t h_own = 0;             // local Hessian entries owned by this rank
         double timeout_s = 2.0;
         ~Dist() {
             for (int p = 0; p < mgb::DIST_MAX_RANKS; ++p)
@@ -879,6 +880,8 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
             for (int64_t k = 0; k < (int64_t)M.h_dest.size(); ++k)
                 if ((M.h_dest[k] >> mgb::DIST_RANK_SHIFT) > rank) { first_after = k; break; }
             dd->h_rot = getenv("MGB_DIST_NOROT") ? 0 : first_after / (256 * mgb::GATHER_UNROLL);
+            for (int32_t d : M.h_dest) dd->h_own += ((d >> mgb::DIST_RANK_SHIFT) == rank) ? 1 : 0;
+            if (getenv("MGB_DIST_NOROT")) dd->h_own = 0;
         }
         pl->dist = std::move(dd);
         *out = pl.release();
@@ -1033,6 +1036,7 @@ void dist_launch(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const
     }
     P.rank = M.rank; P.nranks = M.nranks; P.epoch = dd.epoch; P.counter = dd.counter.p;
     P.h_rot = P.G.nblk_h > 0 ? dd.h_rot % P.G.nblk_h : 0;
+    P.h_loc_blk = std::min<int64_t>(dd.h_own / (256 * mgb::GATHER_UNROLL), P.G.nblk_h);
     P.fused = fused ? 1 : 0;
     P.F = make_finish_params(pl, t, flags);
     launch_dependent(mgb::push_kernel, (unsigned)(P.G.nblk_h + P.G.nblk_l + P.G.nblk_g + 1), 256u, st, P, true);
