@@ -27,19 +27,24 @@ struct CsrOpDev {
 };
 
 struct CsrDev {
-    int ND = 0;
-    int64_t nloc = 0, m = 0, nnzH = 0, nprod = 0;
+    int ND = 0, npair = 0;
+    int pair_a[36] = {0}, pair_b[36] = {0};
+    int64_t nloc = 0, m = 0, nnzH = 0, nprod = 0, nup = 0;
     int max_row = 0;
     BarrierDesc bar;
     std::vector<void*> owned;  // device allocations
-    CsrOpDev E[8], Et[8];
-    const int32_t* h_rowptr = nullptr;
-    const int64_t* prod_ptr = nullptr;
+    CsrOpDev E[8];
+    const int32_t* gt_ptr = nullptr;
+    const double* gt_coef = nullptr;
+    const int32_t* gt_src = nullptr;
+    const int32_t* up_t = nullptr;
+    const int32_t* up_m = nullptr;
+    const int32_t* prod_ptr = nullptr;
     const double* prod_coef = nullptr;
     const int32_t* prod_v = nullptr;
     double* Dz = nullptr;    // nloc x ND
     double* gy = nullptr;    // nloc x ND
-    double* V = nullptr;     // nloc x ND^2
+    double* V = nullptr;     // nloc x npair
     double* part = nullptr;  // nblk x 4
     int64_t nblk = 0;
     ~CsrDev() { for (void* p : owned) cudaFree(p); }
@@ -60,12 +65,16 @@ static const T* csr_up(CsrDev& d, const std::vector<T>& h, cudaStream_t st, size
 static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, cudaStream_t st) {
     size_t bytes = 0;
     d.ND = cp.ND; d.nloc = cp.nloc; d.m = cp.m; d.nnzH = (int64_t)cp.h_colidx.size();
-    d.nprod = (int64_t)cp.prod_coef.size(); d.max_row = cp.max_row; d.bar = bar;
-    for (int k = 0; k < cp.ND; ++k) {
+    d.nprod = (int64_t)cp.prod_coef.size(); d.nup = (int64_t)cp.up_t.size(); d.max_row = cp.max_row; d.bar = bar;
+    d.npair = cp.npair;
+    for (int c = 0; c < cp.npair; ++c) { d.pair_a[c] = cp.pair_a[c]; d.pair_b[c] = cp.pair_b[c]; }
+    for (int k = 0; k < cp.ND; ++k)
         d.E[k] = {csr_up(d, cp.E[k].ptr, st, bytes), csr_up(d, cp.E[k].idx, st, bytes), csr_up(d, cp.E[k].val, st, bytes)};
-        d.Et[k] = {csr_up(d, cp.Et[k].ptr, st, bytes), csr_up(d, cp.Et[k].idx, st, bytes), csr_up(d, cp.Et[k].val, st, bytes)};
-    }
-    d.h_rowptr = csr_up(d, cp.h_rowptr, st, bytes);
+    d.gt_ptr = csr_up(d, cp.gt_ptr, st, bytes);
+    d.gt_coef = csr_up(d, cp.gt_coef, st, bytes);
+    d.gt_src = csr_up(d, cp.gt_src, st, bytes);
+    d.up_t = csr_up(d, cp.up_t, st, bytes);
+    d.up_m = csr_up(d, cp.up_m, st, bytes);
     d.prod_ptr = csr_up(d, cp.prod_ptr, st, bytes);
     d.prod_coef = csr_up(d, cp.prod_coef, st, bytes);
     d.prod_v = csr_up(d, cp.prod_v, st, bytes);
@@ -78,7 +87,7 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     };
     d.Dz = scratch((size_t)cp.nloc * cp.ND);
     d.gy = scratch((size_t)cp.nloc * cp.ND);
-    d.V = scratch((size_t)cp.nloc * cp.ND * cp.ND);
+    d.V = scratch((size_t)cp.nloc * std::max(cp.npair, 1));
     d.nblk = (cp.nloc + 255) / 256;
     d.part = scratch((size_t)d.nblk * 4);
     return bytes;
@@ -110,6 +119,9 @@ struct CsrBarrierParams {
     int nq2;       // second cone: number of q columns (-1: no second cone)
     int idx2[8];
     double p2;
+    int npair;
+    signed char pair_a[36], pair_b[36];   // operator pair of every V column (unique pairs coupled by a cone)
+    signed char loc[2][8];                // per cone: operator column -> local slot (0..2 q, 3 s, 4 slack) or -1
     int64_t n;
     double p, t;
     const double* Dz;
@@ -121,7 +133,32 @@ struct CsrBarrierParams {
     int want_f, want_g, want_h;
 };
 
-__global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams P) {
+// entry (la, lb) of the 5x5 local Hessian of one cone over (q0, q1, q2, s, slack); la, lb are warp-uniform,
+// every index below is a compile-time constant, so the barrier derivatives stay in registers
+__device__ __forceinline__ double cone_hess_pick(const BarrierOut& bo, const double tt, const int la, const int lb) {
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int b = 0; b < 3; ++b) v = (la == a && lb == b) ? bo.Hqq[a][b] : v;
+        v = ((la == a && lb >= 3) || (lb == a && la >= 3)) ? bo.Hqs[a] : v;
+    }
+    v = (la >= 3 && lb >= 3) ? bo.Hss : v;
+    v = (la == 4 && lb == 4) ? bo.Hss + tt : v;
+    return v;
+}
+__device__ __forceinline__ double cone_grad_pick(const BarrierOut& bo, const double itau, const int la) {
+    double v = 0.0;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) v = (la == a) ? bo.gq[a] : v;
+    v = (la == 3) ? bo.gs : v;
+    v = (la == 4) ? bo.gs - itau : v;
+    return v;
+}
+
+// map_rows of F / F1 / F2 over the Dz rows for one or two cones: everything of a point stays in registers, every
+// output column (w.*F1: ND columns, w.*F2: one column per coupled operator pair) is stored exactly once.
+__global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant__ CsrBarrierParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < P.n;
     const int64_t n = P.n;
@@ -132,50 +169,48 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
         double cd = 0.0;
         for (int k = 0; k < ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
         v1 = wi * cd;
-        if (P.want_g)
-            for (int k = 0; k < ND; ++k) P.gy[(int64_t)k * n + i] = wi * (P.t * P.c[(int64_t)k * n + i]);
-        if (P.want_h)
-            for (int cidx = 0; cidx < ND * ND; ++cidx) P.V[(int64_t)cidx * n + i] = 0.0;
-        double Fsum = 0.0;
+        BarrierOut bo[2];
+        double itau = 0.0, tt = 0.0, Fsum = 0.0;
         bool feas = true;
         const int ncones = (P.nq2 >= 0) ? 2 : 1;
-        for (int cone = 0; cone < ncones; ++cone) {
+#pragma unroll
+        for (int cone = 0; cone < 2; ++cone) {
+            if (cone >= ncones) break;
             const int nq = cone ? P.nq2 : P.nq;
             const int* idx = cone ? P.idx2 : P.idx;
             const double pp = cone ? P.p2 : P.p;
             double q[3] = {0.0, 0.0, 0.0};
-            for (int j = 0; j < nq; ++j) q[j] = P.Dz[(int64_t)idx[j] * n + i];
-            const int scol = idx[nq];
-            double s = P.Dz[(int64_t)scol * n + i];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (j < nq) q[j] = P.Dz[(int64_t)idx[j] * n + i];
+            double s = P.Dz[(int64_t)idx[nq] * n + i];
             const bool sl = P.slack && cone == 0;
             if (sl) s += P.Dz[(int64_t)(ND - 1) * n + i];
-            BarrierOut bo;
-            barrier_eval<3, true, true>(q, s, pp, bo);
-            double tau1 = 1.0;
+            barrier_eval<3, true, true>(q, s, pp, bo[cone]);
             if (sl) {  // slack bounded below by -log(1 + tau)
-                tau1 = 1.0 + P.Dz[(int64_t)(ND - 1) * n + i];
-                bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
-                bo.feasible = bo.feasible && (tau1 > 0.0);
+                const double tau1 = 1.0 + P.Dz[(int64_t)(ND - 1) * n + i];
+                bo[cone].F = (tau1 > 0.0) ? bo[cone].F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
+                bo[cone].feasible = bo[cone].feasible && (tau1 > 0.0);
+                itau = 1.0 / tau1;
+                tt = itau * itau;
             }
-            Fsum += bo.F;
-            feas = feas && bo.feasible;
-            const int ns = sl ? 2 : 1;
-            const int scols[2] = {scol, ND - 1};
-            if (P.want_g) {
-                for (int j = 0; j < nq; ++j) P.gy[(int64_t)idx[j] * n + i] += wi * bo.gq[j];
-                for (int r = 0; r < ns; ++r) P.gy[(int64_t)scols[r] * n + i] += wi * (bo.gs - (r == 1 ? 1.0 / tau1 : 0.0));
+            Fsum += bo[cone].F;
+            feas = feas && bo[cone].feasible;
+        }
+        if (P.want_g) {
+            for (int k = 0; k < ND; ++k) {
+                double g = cone_grad_pick(bo[0], itau, P.loc[0][k]);
+                if (ncones == 2) g += cone_grad_pick(bo[1], 0.0, P.loc[1][k]);
+                P.gy[(int64_t)k * n + i] = wi * (g + P.t * P.c[(int64_t)k * n + i]);
             }
-            if (P.want_h) {
-                for (int j = 0; j < nq; ++j) {
-                    for (int j2 = 0; j2 < nq; ++j2) P.V[(int64_t)(idx[j] * ND + idx[j2]) * n + i] += wi * bo.Hqq[j][j2];
-                    for (int r = 0; r < ns; ++r) {
-                        P.V[(int64_t)(idx[j] * ND + scols[r]) * n + i] += wi * bo.Hqs[j];
-                        P.V[(int64_t)(scols[r] * ND + idx[j]) * n + i] += wi * bo.Hqs[j];
-                    }
-                }
-                for (int r = 0; r < ns; ++r)
-                    for (int r2 = 0; r2 < ns; ++r2)
-                        P.V[(int64_t)(scols[r] * ND + scols[r2]) * n + i] += wi * (bo.Hss + ((r == 1 && r2 == 1) ? 1.0 / (tau1 * tau1) : 0.0));
+        }
+        if (P.want_h) {
+            for (int cidx = 0; cidx < P.npair; ++cidx) {
+                const int ka = P.pair_a[cidx], kb = P.pair_b[cidx];
+                double h = 0.0;
+                if (P.loc[0][ka] >= 0 && P.loc[0][kb] >= 0) h = cone_hess_pick(bo[0], tt, P.loc[0][ka], P.loc[0][kb]);
+                if (ncones == 2 && P.loc[1][ka] >= 0 && P.loc[1][kb] >= 0) h += cone_hess_pick(bo[1], 0.0, P.loc[1][ka], P.loc[1][kb]);
+                P.V[(int64_t)cidx * n + i] = wi * h;
             }
         }
         v0 = P.want_f ? wi * Fsum : 0.0;
@@ -200,37 +235,37 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const CsrBarrierParams
     }
 }
 
-struct CsrGradParams {
-    CsrOpDev Et[8];
-    int ND;
-    int64_t n, m;
-    const double* gy;
-    double* grad;
-};
-
-__global__ void __launch_bounds__(256) csr_grad_kernel(const CsrGradParams P) {
+// g[a] = sum_r gt_coef[r] * gy[gt_src[r]]: the transposed operators merged into one list per unknown
+// (gather, no atomics, fixed order)
+__global__ void __launch_bounds__(256) csr_grad_kernel(int64_t m, const int32_t* __restrict__ ptr, const double* __restrict__ coef,
+                                                       const int32_t* __restrict__ src, const double* __restrict__ gy,
+                                                       double* __restrict__ grad) {
     const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= P.m) return;
+    if (a >= m) return;
+    const int r0 = __ldg(&ptr[a]), r1 = __ldg(&ptr[a + 1]);
     double acc = 0.0;
-    for (int k = 0; k < P.ND; ++k) {
-        const int64_t p0 = P.Et[k].ptr[a], p1 = P.Et[k].ptr[a + 1];
-        for (int64_t p = p0; p < p1; ++p) acc = fma(P.Et[k].val[p], P.gy[(int64_t)k * P.n + P.Et[k].idx[p]], acc);
-    }
-    P.grad[a] = acc;
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), gy[__ldg(&src[r])], acc);
+    grad[a] = acc;
 }
 
-// numeric-only triple product on the frozen pattern: one lane per output entry, eight entries per
-// warp-iteration group; every entry sums its precomputed products coef * V in list order (no atomics,
-// bit-reproducible).  coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
-__global__ void __launch_bounds__(256) csr_hess_kernel(int64_t nnzH, const int64_t* __restrict__ prod_ptr,
-                                                       const double* __restrict__ coef, const int32_t* __restrict__ vsrc,
-                                                       const double* __restrict__ V, double* __restrict__ hval) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= nnzH) return;
-    const int64_t r0 = __ldg(&prod_ptr[t]), r1 = __ldg(&prod_ptr[t + 1]);
+// numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry; it sums its
+// precomputed products coef * V in list order (no atomics, bit-reproducible) and stores the value at (a,b) and
+// at the mirror (b,a) - R'HR is symmetric, so half of the product lists never has to be read.
+// coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
+__global__ void __launch_bounds__(256) csr_hess_kernel(int64_t nup, const int32_t* __restrict__ up_t, const int32_t* __restrict__ up_m,
+                                                       const int32_t* __restrict__ prod_ptr, const double* __restrict__ coef,
+                                                       const int32_t* __restrict__ vsrc, const double* __restrict__ V,
+                                                       double* __restrict__ hval) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= nup) return;
+    const int r0 = __ldg(&prod_ptr[j]), r1 = __ldg(&prod_ptr[j + 1]);
+    const int32_t t = __ldg(&up_t[j]), tm = __ldg(&up_m[j]);
     double acc = 0.0;
-    for (int64_t r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), V[__ldg(&vsrc[r])], acc);
+#pragma unroll 4
+    for (int r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), V[__ldg(&vsrc[r])], acc);
     hval[t] = acc;
+    if (tm >= 0) hval[tm] = acc;
 }
 
 static __global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
@@ -285,20 +320,28 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         for (int j = 0; j < d.bar.nidx; ++j) P.idx[j] = d.bar.idx[j];
         P.nq2 = d.bar.nidx2 > 0 ? d.bar.nidx2 - 1 : -1; P.p2 = d.bar.p2;
         for (int j = 0; j < d.bar.nidx2; ++j) P.idx2[j] = d.bar.idx2[j];
+        P.npair = d.npair;
+        for (int c2 = 0; c2 < d.npair; ++c2) { P.pair_a[c2] = (signed char)d.pair_a[c2]; P.pair_b[c2] = (signed char)d.pair_b[c2]; }
+        for (int cone = 0; cone < 2; ++cone)
+            for (int k = 0; k < 8; ++k) P.loc[cone][k] = -1;
+        for (int j = 0; j < P.nq; ++j) P.loc[0][P.idx[j]] = (signed char)j;
+        P.loc[0][P.idx[P.nq]] = 3;
+        if (P.slack) P.loc[0][d.ND - 1] = 4;
+        if (P.nq2 >= 0) {
+            for (int j = 0; j < P.nq2; ++j) P.loc[1][P.idx2[j]] = (signed char)j;
+            P.loc[1][P.idx2[P.nq2]] = 3;
+        }
         P.n = n; P.p = d.bar.p; P.t = t; P.Dz = Dz; P.c = c; P.w = w; P.gy = d.gy; P.V = d.V; P.part = d.part;
         P.want_f = (flags & 1) ? 1 : 0; P.want_g = (flags & 2) ? 1 : 0; P.want_h = (flags & 4) ? 1 : 0;
         csr_barrier_kernel<<<(unsigned)d.nblk, 256, 0, st>>>(P);
         ++launches;
     }
     if (flags & 2) {
-        CsrGradParams P{};
-        for (int k = 0; k < d.ND; ++k) P.Et[k] = d.Et[k];
-        P.ND = d.ND; P.n = n; P.m = d.m; P.gy = d.gy; P.grad = grad;
-        csr_grad_kernel<<<(unsigned)((d.m + 255) / 256), 256, 0, st>>>(P);
+        csr_grad_kernel<<<(unsigned)((d.m + 255) / 256), 256, 0, st>>>(d.m, d.gt_ptr, d.gt_coef, d.gt_src, d.gy, grad);
         ++launches;
     }
-    if ((flags & 4) && d.nnzH > 0) {
-        csr_hess_kernel<<<(unsigned)((d.nnzH + 255) / 256), 256, 0, st>>>(d.nnzH, d.prod_ptr, d.prod_coef, d.prod_v, d.V, hval);
+    if ((flags & 4) && d.nup > 0) {
+        csr_hess_kernel<<<(unsigned)((d.nup + 255) / 256), 256, 0, st>>>(d.nup, d.up_t, d.up_m, d.prod_ptr, d.prod_coef, d.prod_v, d.V, hval);
         ++launches;
     }
     scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);

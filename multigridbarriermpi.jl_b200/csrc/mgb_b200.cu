@@ -510,7 +510,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         } else {
             pl->path = MGB_PATH_CSR;
             mgb::CsrPlan cp;
-            mgb::build_csr_plan(Dh, Rh, cp, want_hess);
+            mgb::build_csr_plan(Dh, Rh, pl->bar, cp, want_hess);
             pl->nnzH = (int64_t)cp.h_colidx.size();
             pl->h_rowptr = cp.h_rowptr; pl->h_colidx = cp.h_colidx;
             pl->n_hcontrib = (int64_t)cp.prod_coef.size();

@@ -613,29 +613,64 @@ void build_dist_maps(const ElementPlan& G, int rank, int nranks, const int64_t* 
     M.own_colidx.assign(G.h_colidx.begin() + G.h_rowptr[lo], G.h_colidx.begin() + G.h_rowptr[hi]);
 }
 
-void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P, bool want_hessian) {
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, const BarrierDesc& bar, CsrPlan& P,
+                    bool want_hessian) {
     const int ND = (int)D.size();
     P.ND = ND;
     P.nloc = D[0].nrows;
     P.m = R.ncols;
     const int64_t m = P.m;
     P.E.resize(ND);
-    P.Et.resize(ND);
+    std::vector<HostCSR> Et(ND);
     for (int k = 0; k < ND; ++k) {
         P.E[k] = spgemm(D[k], R);
-        P.Et[k] = transpose(P.E[k]);
+        Et[k] = transpose(P.E[k]);
     }
-    // pattern: row a = union over (ka, i in column a of E_ka) of union_kb supp(E_kb[i,:])
+    if ((int64_t)ND * P.nloc > INT32_MAX) throw std::runtime_error("csr path: gradient source index exceeds int32");
+    // merged transposed lists (gradient)
+    P.gt_ptr.assign(m + 1, 0);
+    for (int64_t a = 0; a < m; ++a) {
+        for (int k = 0; k < ND; ++k)
+            for (int64_t p = Et[k].ptr[a]; p < Et[k].ptr[a + 1]; ++p) {
+                P.gt_coef.push_back(Et[k].val[p]);
+                P.gt_src.push_back((int32_t)((int64_t)k * P.nloc + Et[k].idx[p]));
+            }
+        if ((int64_t)P.gt_coef.size() > INT32_MAX) throw std::runtime_error("csr path: gradient list exceeds int32");
+        P.gt_ptr[a + 1] = (int32_t)P.gt_coef.size();
+    }
+    // V columns: unique operator pairs coupled by at least one cone
+    bool act[8][8] = {{false}};
+    auto mark_cone = [&](const int* idx, int cnt, bool with_slack) {
+        int cols[10], nc = 0;
+        for (int j = 0; j < cnt; ++j) cols[nc++] = idx[j];
+        if (with_slack) cols[nc++] = ND - 1;
+        for (int x = 0; x < nc; ++x)
+            for (int y = 0; y < nc; ++y) act[cols[x]][cols[y]] = true;
+    };
+    mark_cone(bar.idx, bar.nidx, bar.slack != 0);
+    if (bar.nidx2 > 0) mark_cone(bar.idx2, bar.nidx2, false);
+    P.npair = 0;
+    for (int a = 0; a < 8; ++a)
+        for (int b = 0; b < 8; ++b) P.pair_col[a][b] = -1;
+    for (int a = 0; a < ND; ++a)
+        for (int b = a; b < ND; ++b)
+            if (act[a][b]) {
+                P.pair_a[P.npair] = a; P.pair_b[P.npair] = b;
+                P.pair_col[a][b] = P.pair_col[b][a] = P.npair++;
+            }
+    if ((int64_t)std::max(P.npair, 1) * P.nloc > INT32_MAX) throw std::runtime_error("csr path: V index exceeds int32");
+    // pattern: row a = union over (ka, i in column a of E_ka) of union_kb supp(E_kb[i,:])  (structural: every
+    // operator pair, also the ones whose F2 block is identically zero - Julia products keep structural zeros)
     P.h_rowptr.assign(m + 1, 0);
     P.prod_ptr.assign(1, 0);
-    if ((int64_t)ND * ND * P.nloc > INT32_MAX) throw std::runtime_error("csr path: V index exceeds int32");
     std::vector<int32_t> mark(m, -1), pos(m, 0), cols;
     std::vector<std::vector<std::pair<double, int32_t>>> rowprod;
+    std::vector<int32_t> ent_row;   // row of every pattern entry (for the mirror lookup)
     for (int64_t a = 0; a < m && want_hessian; ++a) {
         cols.clear();
         for (int ka = 0; ka < ND; ++ka)
-            for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {
-                const int32_t i = P.Et[ka].idx[p];
+            for (int64_t p = Et[ka].ptr[a]; p < Et[ka].ptr[a + 1]; ++p) {
+                const int32_t i = Et[ka].idx[p];
                 for (int kb = 0; kb < ND; ++kb)
                     for (int64_t r = P.E[kb].ptr[i]; r < P.E[kb].ptr[i + 1]; ++r) {
                         const int32_t b = P.E[kb].idx[r];
@@ -643,24 +678,46 @@ void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& P,
                     }
             }
         std::sort(cols.begin(), cols.end());
+        const int64_t row0 = (int64_t)P.h_colidx.size();
         for (size_t t = 0; t < cols.size(); ++t) { pos[cols[t]] = (int32_t)t; P.h_colidx.push_back(cols[t]); }
+        if ((int64_t)P.h_colidx.size() > INT32_MAX) throw std::runtime_error("nnz(H) exceeds int32 indexing");
         P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
         P.max_row = std::max<int32_t>(P.max_row, (int32_t)cols.size());
         if (rowprod.size() < cols.size()) rowprod.resize(cols.size());
         for (size_t t = 0; t < cols.size(); ++t) rowprod[t].clear();
         for (int ka = 0; ka < ND; ++ka)
-            for (int64_t p = P.Et[ka].ptr[a]; p < P.Et[ka].ptr[a + 1]; ++p) {
-                const int32_t i = P.Et[ka].idx[p];
-                const double alpha = P.Et[ka].val[p];
-                for (int kb = 0; kb < ND; ++kb)
-                    for (int64_t r = P.E[kb].ptr[i]; r < P.E[kb].ptr[i + 1]; ++r)
-                        rowprod[pos[P.E[kb].idx[r]]].emplace_back(alpha * P.E[kb].val[r],
-                                                                  (int32_t)(((int64_t)ka * ND + kb) * P.nloc + i));
+            for (int64_t p = Et[ka].ptr[a]; p < Et[ka].ptr[a + 1]; ++p) {
+                const int32_t i = Et[ka].idx[p];
+                const double alpha = Et[ka].val[p];
+                for (int kb = 0; kb < ND; ++kb) {
+                    const int col = P.pair_col[ka][kb];
+                    if (col < 0) continue;   // F2 block identically zero for this operator pair
+                    for (int64_t r = P.E[kb].ptr[i]; r < P.E[kb].ptr[i + 1]; ++r) {
+                        const int32_t b = P.E[kb].idx[r];
+                        if (b < (int32_t)a) continue;   // lower triangle: filled from the mirror entry
+                        rowprod[pos[b]].emplace_back(alpha * P.E[kb].val[r], (int32_t)((int64_t)col * P.nloc + i));
+                    }
+                }
             }
         for (size_t t = 0; t < cols.size(); ++t) {
+            if (cols[t] < (int32_t)a) continue;
+            P.up_t.push_back((int32_t)(row0 + (int64_t)t));
+            P.up_m.push_back(cols[t] == (int32_t)a ? -1 : -2 - cols[t]);   // resolved below: -2-b = "row b, column a"
+            ent_row.push_back((int32_t)a);
             for (auto& pr : rowprod[t]) { P.prod_coef.push_back(pr.first); P.prod_v.push_back(pr.second); }
-            P.prod_ptr.push_back((int64_t)P.prod_coef.size());
+            if ((int64_t)P.prod_coef.size() > INT32_MAX) throw std::runtime_error("csr path: product list exceeds int32");
+            P.prod_ptr.push_back((int32_t)P.prod_coef.size());
         }
+    }
+    // mirror positions: entry (b, a) of the (structurally symmetric) pattern
+    for (size_t j = 0; j < P.up_t.size(); ++j) {
+        if (P.up_m[j] == -1) continue;
+        const int32_t b = -2 - P.up_m[j], a = ent_row[j];
+        const int32_t* lo = P.h_colidx.data() + P.h_rowptr[b];
+        const int32_t* hi = P.h_colidx.data() + P.h_rowptr[b + 1];
+        const int32_t* it = std::lower_bound(lo, hi, a);
+        if (it == hi || *it != a) throw std::runtime_error("internal: pattern of sum_jk E_j' diag E_k is not symmetric");
+        P.up_m[j] = (int32_t)(it - P.h_colidx.data());
     }
 }
 

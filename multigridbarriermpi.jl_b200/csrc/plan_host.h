@@ -137,17 +137,27 @@ struct CsrPlan {
     int ND = 0, NU = 0;
     int64_t nloc = 0, m = 0;
     std::vector<HostCSR> E;   // E_k = D_k R   (nloc x m)
-    std::vector<HostCSR> Et;  // transposes   (m x nloc)
+    // gradient: all E_k' merged into one list per unknown a:  g[a] = sum_r gt_coef[r] * gy[gt_src[r]],
+    // gt_src = k*nloc + i, listed in the fixed order (k, i)
+    std::vector<int32_t> gt_ptr, gt_src;
+    std::vector<double> gt_coef;
     std::vector<int32_t> h_rowptr, h_colidx;
-    // numeric-only replay of sum_jk E_j' diag(V_jk) E_k on the frozen pattern: for output entry t the
-    // products  coef[r] * V[vsrc[r]],  r in [prod_ptr[t], prod_ptr[t+1]),  coef = E_ka[i,a]*E_kb[i,b],
-    // vsrc = (ka*ND+kb)*nloc + i, listed in the fixed order (ka, i, kb)
-    std::vector<int64_t> prod_ptr;
+    // V = w .* F2 is symmetric and structurally zero outside the cones' index sets: only the unique pairs
+    // (ka <= kb) that some cone couples get a column; pair_col[ka][kb] = column or -1
+    int npair = 0;
+    int pair_a[36] = {0}, pair_b[36] = {0};
+    int pair_col[8][8];
+    // numeric-only replay of sum_jk E_j' diag(V_jk) E_k on the frozen (symmetric) pattern, upper triangle only:
+    // upper entry j (row a <= column b) sums  coef[r] * V[vsrc[r]],  r in [prod_ptr[j], prod_ptr[j+1]),
+    // coef = E_ka[i,a]*E_kb[i,b], vsrc = pair_col[ka][kb]*nloc + i, in the fixed order (ka, i, kb); the value
+    // goes to position up_t[j] and to its mirror up_m[j] (-1 on the diagonal)
+    std::vector<int32_t> up_t, up_m, prod_ptr;
     std::vector<double> prod_coef;
     std::vector<int32_t> prod_v;
     int32_t max_row = 0;
 };
 
-void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, CsrPlan& out, bool want_hessian = true);
+void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, const BarrierDesc& bar, CsrPlan& out,
+                    bool want_hessian = true);
 
 }  // namespace mgb
