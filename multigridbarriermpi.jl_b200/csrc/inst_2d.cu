@@ -2,8 +2,8 @@
 #include "inst_common.cuh"
 
 namespace mgb {
-void launch_element_2d(bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
-    launch_elem_bd<7, 2>(P, slack, fine, flags, nblk, st);
+void launch_element_2d(int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
+    launch_elem_bd<7, 2>(P, mode, fine, flags, nblk, st);
 }
 void launch_patch_2d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
                      size_t smem, cudaStream_t st) {

@@ -34,7 +34,7 @@ struct ElemParams {
     const double* s;         // m
     const double* Dz0;       // nloc x ND or null
     const double* c;         // nloc x ND
-    double t, p;
+    double t, p, p2;         // p2: exponent of the second cone (MODE 2)
     // outputs
     double* sel;             // E*NS
     double* rel;             // E*NU*LPE
@@ -123,12 +123,16 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
 // and its slot record to `sel` (global memory in the two-stage path, shared memory in the patch-
 // fused path; entry r of a butterfly-reduced block is stored at  off + r*LPE + lane).  Returns this
 // thread's objective / <c,Dz> / infeasibility partials.  Every lane of the group must call it.
-template <int B, int D, bool SLACK, bool FINE, int FLAGS>
+// MODE: 0 = one cone on (grad u, s); 1 = feasibility phase, cone on (grad u, s + tau) plus -log(1 + tau);
+//       2 = two cones (upstream parabolic_solve): A on (u, s1) with exponent p2, B on (grad u, s2) with p.
+//       Modes 1 and 2 share the three-variable operator table [u.id; u.d*; v1.id; v2.id] and slot layout.
+template <int B, int D, int MODE, bool FINE, int FLAGS>
 __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t e, const int l, double* __restrict__ sel,
                                              double* __restrict__ rel, double& v0, double& v1, double& v2) {
+    constexpr bool SLACK = MODE == 1, TWO = MODE == 2, THREE = MODE != 0;
     constexpr int LPE = Pow2Ceil<B>::value;
-    constexpr int ND = D + 2 + (SLACK ? 1 : 0);
-    constexpr int NU = 2 + (SLACK ? 1 : 0);
+    constexpr int ND = D + 2 + (THREE ? 1 : 0);
+    constexpr int NU = 2 + (THREE ? 1 : 0);
     constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
     constexpr int NTRI = (B * (B + 1) / 2 + LPE - 1) / LPE * LPE;
     constexpr int NFULL = (B * B + LPE - 1) / LPE * LPE;
@@ -220,8 +224,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     double qv[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) qv[j] = dz[1 + j];
-    double sv = dz[D + 1];
-    if (SLACK) sv += dz[D + 2];
+    double sv = TWO ? dz[D + (THREE ? 2 : 1)] : dz[D + 1];
+    if (SLACK) sv += dz[D + (THREE ? 2 : 1)];
     if (!act) { sv = 1.0;
 #pragma unroll
         for (int j = 0; j < D; ++j) qv[j] = 0.0; }
@@ -230,10 +234,19 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     // feasibility phase: the slack tau is bounded below by the extra barrier -log(1 + tau)
     double tau1 = 1.0, itau = 1.0;
     if (SLACK) {
-        tau1 = act ? 1.0 + dz[D + 2] : 1.0;
+        tau1 = act ? 1.0 + dz[D + (THREE ? 2 : 1)] : 1.0;
         itau = 1.0 / tau1;
         if (WF) bo.F = (tau1 > 0.0) ? bo.F - log(tau1) : __longlong_as_double(0x7ff0000000000000LL);
         bo.feasible = bo.feasible && (tau1 > 0.0);
+    }
+    // second cone A on (u, s1)
+    BarrierOut ba;
+    if (TWO) {
+        double qa[1] = {act ? dz[0] : 0.0};
+        const double sa = act ? dz[D + 1] : 1.0;
+        barrier_eval<1, WF, (WG || WH)>(qa, sa, P.p2, ba);
+        if (WF) bo.F += ba.F;
+        bo.feasible = bo.feasible && ba.feasible;
     }
 
     // ---- objective / feasibility partials of this point (reduced by the caller in a fixed order)
@@ -251,11 +264,12 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
     // ---- gradient: r[var][q] = sum_points sum_k a_k[q] * w (F1_k + t c_k)
     if (WG) {
         double gy[ND];
-        gy[0] = wi * (P.t * cc[0]);
+        gy[0] = wi * ((TWO ? ba.gq[0] : 0.0) + P.t * cc[0]);
 #pragma unroll
         for (int j = 0; j < D; ++j) gy[1 + j] = wi * (bo.gq[j] + P.t * cc[1 + j]);
-        gy[D + 1] = wi * (bo.gs + P.t * cc[D + 1]);
-        if (SLACK) gy[D + 2] = wi * (bo.gs - itau + P.t * cc[D + 2]);
+        gy[D + 1] = wi * ((TWO ? ba.gs : bo.gs) + P.t * cc[D + 1]);
+        if (SLACK) gy[D + (THREE ? 2 : 1)] = wi * (bo.gs - itau + P.t * cc[D + (THREE ? 2 : 1)]);
+        if (TWO) gy[D + (THREE ? 2 : 1)] = wi * (bo.gs + P.t * cc[D + (THREE ? 2 : 1)]);
         double ru[LPE];
 #pragma unroll
         for (int q = 0; q < LPE; ++q) {
@@ -311,6 +325,19 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                 for (int j = 0; j < D; ++j) acc = fma(a[j][q], T[j][q2], acc);
                 v[q * B - q * (q - 1) / 2 + (q2 - q)] = acc;
             }
+        if (TWO) {  // cone A couples u with itself through u.id
+            const double huu = wi * ba.Hqq[0][0];
+#pragma unroll
+            for (int q = 0; q < B; ++q) {
+                if (FINE) {
+                    v[q * B - q * (q - 1) / 2] += (oh[0] && q == olq[0]) ? huu * oval[0] * oval[0] : 0.0;
+                } else {
+#pragma unroll
+                    for (int q2 = q; q2 < B; ++q2)
+                        v[q * B - q * (q - 1) / 2 + (q2 - q)] += huu * aid[0][FINE ? 0 : q] * aid[0][FINE ? 0 : q2];
+                }
+            }
+        }
         group_reduce<NTRI, LPE>(v, l);
         if (act_e) {
 #pragma unroll
@@ -327,30 +354,34 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
         bs[q] = acc;
     }
     const double vss = wi * bo.Hss;
-    const double vtt = SLACK ? vss + wi * itau * itau : vss;  // slack-slack curvature incl. -log(1+tau)
+    const double vtt = SLACK ? vss + wi * itau * itau : vss;  // last variable's own curvature (slack: incl. -log(1+tau))
+    const double haus = TWO ? wi * ba.Hqs[0] : 0.0;           // cone A: u x s1 and s1 x s1
+    const double hass = TWO ? wi * ba.Hss : 0.0;
+    constexpr int VT = THREE ? 2 : 0;
     if (FINE) {
         if (act && oh[1]) {
 #pragma unroll
-            for (int q = 0; q < B; ++q) sel[P.off_us + q * LPE + olq[1]] = bs[q] * oval[1];
-            sel[P.off_ss + olq[1]] = vss * oval[1] * oval[1];
+            for (int q = 0; q < B; ++q)
+                sel[P.off_us + q * LPE + olq[1]] = TWO ? ((oh[0] && q == olq[0]) ? haus * oval[0] * oval[1] : 0.0) : bs[q] * oval[1];
+            sel[P.off_ss + olq[1]] = (TWO ? hass : vss) * oval[1] * oval[1];
         }
-        if (SLACK && act && oh[SLACK ? 2 : 0]) {
-            constexpr int VT = SLACK ? 2 : 0;
+        if (THREE && act && oh[VT]) {
 #pragma unroll
             for (int q = 0; q < B; ++q) sel[P.off_ut + q * LPE + olq[VT]] = bs[q] * oval[VT];
-            if (oh[1]) sel[P.off_st + l] = vss * oval[1] * oval[VT];
+            if (oh[1]) sel[P.off_st + l] = TWO ? 0.0 : vss * oval[1] * oval[VT];
             sel[P.off_tt + olq[VT]] = vtt * oval[VT] * oval[VT];
         }
     } else {
 #pragma unroll
-        for (int v2 = 1; v2 < NU; ++v2) {  // u x {s, slack}
+        for (int v2 = 1; v2 < NU; ++v2) {  // u x {v1, v2}
             double v[NFULL];
 #pragma unroll
             for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
 #pragma unroll
             for (int q = 0; q < B; ++q)
 #pragma unroll
-                for (int q2 = 0; q2 < B; ++q2) v[q * B + q2] = bs[q] * aid[FINE ? 0 : v2][FINE ? 0 : q2];
+                for (int q2 = 0; q2 < B; ++q2)
+                    v[q * B + q2] = ((TWO && v2 == 1) ? haus * aid[0][FINE ? 0 : q] : bs[q]) * aid[FINE ? 0 : v2][FINE ? 0 : q2];
             group_reduce<NFULL, LPE>(v, l);
             const int off = (v2 == 1) ? P.off_us : P.off_ut;
             if (act_e) {
@@ -359,15 +390,16 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
             }
         }
 #pragma unroll
-        for (int v1 = 1; v1 < NU; ++v1) {  // {s,slack} x {s,slack} symmetric diagonal blocks
+        for (int v1 = 1; v1 < NU; ++v1) {  // symmetric diagonal blocks of v1, v2
             double v[NTRI];
 #pragma unroll
             for (int r = 0; r < NTRI; ++r) v[r] = 0.0;
+            const double hd = (v1 == 2) ? vtt : (TWO ? hass : vss);
 #pragma unroll
             for (int q = 0; q < B; ++q)
 #pragma unroll
                 for (int q2 = q; q2 < B; ++q2)
-                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = (v1 == 2 ? vtt : vss) * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
+                    v[q * B - q * (q - 1) / 2 + (q2 - q)] = hd * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
             group_reduce<NTRI, LPE>(v, l);
             const int off = (v1 == 1) ? P.off_ss : P.off_tt;
             if (act_e) {
@@ -375,16 +407,18 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                 for (int r = 0; r < NTRI / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
         }
-        if (SLACK) {  // s x slack full block
+        if (THREE) {  // v1 x v2 full block (two cones: structurally present, identically zero)
             double v[NFULL];
 #pragma unroll
             for (int r = 0; r < NFULL; ++r) v[r] = 0.0;
+            if (!TWO) {
 #pragma unroll
-            for (int q = 0; q < B; ++q)
+                for (int q = 0; q < B; ++q)
 #pragma unroll
-                for (int q2 = 0; q2 < B; ++q2)
-                    v[q * B + q2] = vss * aid[FINE ? 0 : 1][FINE ? 0 : q] * aid[FINE ? 0 : (SLACK ? 2 : 0)][FINE ? 0 : q2];
-            group_reduce<NFULL, LPE>(v, l);
+                    for (int q2 = 0; q2 < B; ++q2)
+                        v[q * B + q2] = vss * aid[FINE ? 0 : 1][FINE ? 0 : q] * aid[FINE ? 0 : VT][FINE ? 0 : q2];
+                group_reduce<NFULL, LPE>(v, l);
+            }
             if (act_e) {
 #pragma unroll
                 for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + r * LPE + l] = v[r];
@@ -417,16 +451,16 @@ __device__ __forceinline__ void block_scalars(double v0, double v1, double v2, d
 }
 
 // Two-stage path, stage 1: slot / gradient records to global memory (replayed by gather_kernel).
-template <int B, int D, bool SLACK, bool FINE, int FLAGS>
+template <int B, int D, int MODE, bool FINE, int FLAGS>
 __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
     constexpr int LPE = Pow2Ceil<B>::value;
-    constexpr int NU = 2 + (SLACK ? 1 : 0);
+    constexpr int NU = 2 + (MODE != 0 ? 1 : 0);
     pdl_launch_dependents();
     const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t e = tid / LPE;
     const int l = (int)(tid % LPE);
     double v0, v1, v2;
-    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
+    element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
     block_scalars(v0, v1, v2, P.part);
 }
 
@@ -500,7 +534,7 @@ __global__ void __launch_bounds__(PATCH * Pow2Ceil<B>::value) patch_kernel(const
     const int l = threadIdx.x % LPE;
     const int64_t e = (int64_t)blockIdx.x * PATCH + el;
     double v0, v1, v2;
-    element_body<B, D, SLACK, FINE, FLAGS>(P, e, l, img + (size_t)el * Q.NSP,
+    element_body<B, D, SLACK ? 1 : 0, FINE, FLAGS>(P, e, l, img + (size_t)el * Q.NSP,
                                            img + (size_t)PATCH * Q.NSP + (size_t)el * Q.RSP, v0, v1, v2);
     if (WG || WH) cp_async_commit_wait_all();
     block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes records and staged lists

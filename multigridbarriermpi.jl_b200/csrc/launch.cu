@@ -14,9 +14,9 @@ int canonical_flags(int flags) {
     return (f & 8) ? 15 : 7;
 }
 
-void launch_element(int B, int dim, bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
-    if (B == 2 && dim == 1) launch_element_1d(slack, fine, P, flags, nblk, st);
-    else if (B == 7 && dim == 2) launch_element_2d(slack, fine, P, flags, nblk, st);
+void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
+    if (B == 2 && dim == 1) launch_element_1d(mode, fine, P, flags, nblk, st);
+    else if (B == 7 && dim == 2) launch_element_2d(mode, fine, P, flags, nblk, st);
     else throw std::runtime_error("element kernel not instantiated for this element type");
 }
 

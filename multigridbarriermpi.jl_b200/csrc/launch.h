@@ -13,12 +13,12 @@ bool element_supported(int B, int dim);
 // 8 (apply_D only), 15 (everything + Dz); other requests run the next superset.
 int canonical_flags(int flags);
 
-void launch_element(int B, int dim, bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
 void launch_patch(int B, int dim, bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags,
                   int64_t nblk, size_t smem, cudaStream_t st);
 
-void launch_element_1d(bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
-void launch_element_2d(bool slack, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_element_1d(int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+void launch_element_2d(int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
 void launch_patch_1d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
                      size_t smem, cudaStream_t st);
 void launch_patch_2d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,

@@ -210,12 +210,13 @@ bool want_patch_early(int force_flags) {
     const char* ev = getenv("MGB_PATCH");
     return (force_flags & MGB_PLAN_TWO_STAGE) == 0 && ev && atoi(ev) > 0;
 }
+bool patch_requested(int force_flags, const mgb::ElementPlan& ep) { return want_patch_early(force_flags) && ep.mode != 2; }
 
 bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
 void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     const auto& ep = pl->ep;
-    mgb::launch_element(ep.B, ep.dim, ep.slack, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
+    mgb::launch_element(ep.B, ep.dim, ep.mode, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
     g_launches++;
     CUDA_OK(cudaGetLastError());
 }
@@ -246,7 +247,7 @@ mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz
     mgb::ElemParams P{};
     P.E = ep.E; P.nloc = ep.nloc;
     P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
-    P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p;
+    P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p; P.p2 = pl->bar.p2;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
     P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
     P.off_ut = ep.lay.off_ut; P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
@@ -448,7 +449,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
                 pl->long_lists = avg > 12.0;
             }
-            if (want_patch_early(force_flags)) {
+            if (patch_requested(force_flags, ep)) {
                 // patch-fused path builds its own lists below
             } else if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
                 pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
@@ -476,7 +477,7 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
             }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
             int want_patch = 0;
-            if (want_patch_early(force_flags)) {
+            if (patch_requested(force_flags, ep)) {
                 want_patch = atoi(getenv("MGB_PATCH"));
                 if (ep.B == 7 && want_patch != 16 && want_patch != 32 && want_patch != 64) want_patch = 16;
                 if (ep.B == 2) want_patch = 64;

@@ -147,13 +147,19 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
     if (N % n_global) { P.why = "N is not a multiple of n"; return; }
     const int nu = (int)(N / n_global);
-    const bool slack = bar.slack != 0;
+    const bool two = bar.nidx2 > 0;
+    const bool slack = bar.slack != 0 || two;   // three state variables
     const int dim = ND - 2 - (slack ? 1 : 0);
-    if (bar.nidx2 > 0) { P.why = "two-cone barrier: general CSR kernels"; return; }
     if (bar.kind != 1 || dim < 1 || dim > 3 || nu != 2 + (slack ? 1 : 0)) { P.why = "not the p-Laplace operator table"; return; }
     if (bar.nidx != dim + 1) { P.why = "barrier idx does not select (derivatives, s)"; return; }
-    for (int j = 0; j <= dim; ++j)
+    for (int j = 0; j < dim; ++j)
         if (bar.idx[j] != 1 + j) { P.why = "barrier idx does not select (derivatives, s)"; return; }
+    if (bar.idx[dim] != (two ? dim + 2 : dim + 1)) { P.why = "barrier idx does not select (derivatives, s)"; return; }
+    if (two && (bar.slack != 0 || bar.nidx2 != 2 || bar.idx2[0] != 0 || bar.idx2[1] != dim + 1)) {
+        P.why = "second cone is not (u.id, s1.id): general CSR kernels";
+        return;
+    }
+    P.mode = two ? 2 : (bar.slack != 0 ? 1 : 0);
     // operator -> state variable
     std::vector<int> var(ND, 0);
     for (int k = 0; k < ND; ++k) {

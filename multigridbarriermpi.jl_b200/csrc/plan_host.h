@@ -69,7 +69,8 @@ struct ElementPlan {
     bool ok = false;       // element-block structure detected and supported by the fused kernels
     std::string why;       // reason when !ok
     int B = 0, LPE = 0, dim = 0, NU = 0, ND = 0;
-    bool slack = false, fine = false;
+    bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
+    int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
     SlotLayout lay;
     std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1

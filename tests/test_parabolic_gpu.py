@@ -13,7 +13,7 @@ from helpers import rel
 pytestmark = pytest.mark.gpu
 
 
-def _two_cone_problem(geom, p, seed=5):
+def _two_cone_problem(geom, p, seed=5, level=-1):
     dim = geom.dim
     Dt, idxA, idxB = O.parabolic_tables(dim)
     M = O.amg_helper(geom, O.PARABOLIC_STATE, Dt)
@@ -21,22 +21,25 @@ def _two_cone_problem(geom, p, seed=5):
     rng = np.random.default_rng(seed)
     u = np.sin(geom.x[:, 0]) + (geom.x[:, 1] ** 2 if dim > 1 else 0.0)
     z0 = O.parabolic_feasible_start(M, u, dim, p)
-    R = M.R_fine[-1]
+    R = M.R_fine[level]
     s = 1e-3 * rng.uniform(-1, 1, size=R.shape[1])
     c = rng.normal(size=(n, len(Dt)))
     return M, R, z0, s, c, idxA, idxB
 
 
-@pytest.mark.parametrize("gen,L,p", [("fem1d", 3, 2.0), ("fem2d", 2, 1.0), ("fem2d", 3, 1.5)])
-def test_two_cone_assembly_matches_oracle(gpu_ctx, gen, L, p):
+@pytest.mark.parametrize("path", [capi.PATH_ELEMENT, capi.PATH_CSR])
+@pytest.mark.parametrize("gen,L,p", [("fem1d", 3, 2.0), ("fem2d", 2, 1.0), ("fem2d", 3, 1.5), ("fem2d", 4, 1.0)])
+def test_two_cone_assembly_matches_oracle(gpu_ctx, gen, L, p, path):
+    """both numeric paths: the fused element kernels (MODE 2) and the general CSR kernels"""
     geom = getattr(mgb_b200, gen)(L)
     M, R, z0, s, c, idxA, idxB = _two_cone_problem(geom, p)
     Q = O.Intersection([O.EuclidianPower(idx=idxA, p=2.0), O.EuclidianPower(idx=idxB, p=p)])
     t = 0.6
     args = (s, geom.x, geom.w, t * c, R, M.D, z0, Q)
     f0, g, H = O.f0(*args), O.f1(*args), O.f2(*args).tocsr()
-    plan = capi.Plan(gpu_ctx, M.D, R, geom.x, geom.w, idxB, p, idx2=idxA, p2=2.0)
-    assert plan.info["path"] == capi.PATH_CSR
+    plan = capi.Plan(gpu_ctx, M.D, R, geom.x, geom.w, idxB, p, idx2=idxA, p2=2.0, force_path=path)
+    assert plan.info["path"] == path
+    assert capi.Plan(None, M.D, R, geom.x, geom.w, idxB, p, idx2=idxA, p2=2.0).info["path"] == capi.PATH_ELEMENT  # default
     Dz0 = np.stack([Dk @ z0 for Dk in M.D], axis=1)
     out = plan.assemble_host(s, Dz0, c, t, 7)
     rp, ci = plan.pattern()
@@ -45,6 +48,32 @@ def test_two_cone_assembly_matches_oracle(gpu_ctx, gen, L, p):
     assert abs(out["scal"][0] - f0) <= 1e-12 * abs(f0)
     assert rel(out["grad"], g) <= 1e-12
     assert abs(Hc - H).max() <= 1e-12 * abs(H).max()
+
+
+@pytest.mark.parametrize("path", [capi.PATH_ELEMENT, capi.PATH_CSR])
+@pytest.mark.parametrize("gen,L,level,p", [("fem2d", 3, 1, 1.0), ("fem2d", 3, 0, 2.0), ("fem1d", 4, 1, 1.5)])
+def test_two_cone_coarse_levels(gpu_ctx, gen, L, level, p, path):
+    """coarse multigrid levels: the id-like operators become dense element rows (the !FINE kernel instances)"""
+    geom = getattr(mgb_b200, gen)(L)
+    M, R, z0, s, c, idxA, idxB = _two_cone_problem(geom, p, level=level)
+    Q = O.Intersection([O.EuclidianPower(idx=idxA, p=2.0), O.EuclidianPower(idx=idxB, p=p)])
+    t = 0.6
+    args = (s, geom.x, geom.w, t * c, R, M.D, z0, Q)
+    f0, g, H = O.f0(*args), O.f1(*args), O.f2(*args).tocsr()
+    plan = capi.Plan(gpu_ctx, M.D, R, geom.x, geom.w, idxB, p, idx2=idxA, p2=2.0, force_path=path)
+    assert plan.info["path"] == path
+    Dz0 = np.stack([Dk @ z0 for Dk in M.D], axis=1)
+    out = plan.assemble_host(s, Dz0, c, t, 7)
+    rp, ci = plan.pattern()
+    Hc = sp.csr_matrix((out["hval"], ci, rp), shape=(plan.m, plan.m))
+    assert out["scal"][1] == 1.0
+    assert abs(out["scal"][0] - f0) <= 1e-12 * abs(f0)
+    assert rel(out["grad"], g) <= 1e-12
+    assert abs(Hc - H).max() <= 1e-12 * abs(H).max()
+    Ho = H.copy(); Ho.eliminate_zeros()
+    Pc = sp.csr_matrix((np.ones(Hc.nnz), Hc.indices, Hc.indptr), shape=Hc.shape)
+    Po = sp.csr_matrix((np.ones(Ho.nnz), Ho.indices, Ho.indptr), shape=Ho.shape)
+    assert (Po - Po.multiply(Pc)).nnz == 0, "oracle pattern not contained in plan pattern"
 
 
 def test_parabolic_1d_reference_case():
