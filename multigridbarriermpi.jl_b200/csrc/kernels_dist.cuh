@@ -123,7 +123,8 @@ __device__ __forceinline__ void finish_body(const FinishParams& P, const int bid
 struct PushParams {
     GatherParams G;                        // local replay lists (hval / grad / scal members unused)
     const int32_t* h_dest;                 // per local Hessian entry: (owner << 27) | offset in the owner's window
-    const int32_t* g_dest;                 // per unknown: same, -1 = this rank has no contribution
+    const int2* g_dest;                    // per unknown this rank contributes to: {unknown, destination}
+    int64_t n_gtouch;
     double* win[DIST_MAX_RANKS];           // peers' windows (this epoch's parity), win[rank] = own
     unsigned long long* flag[DIST_MAX_RANKS];  // peers' flag arrays; this rank writes flag[p][rank]
     int64_t scal_off[DIST_MAX_RANKS];      // offset of this rank's 4 staged scalars inside window p
@@ -187,14 +188,12 @@ static __global__ void __launch_bounds__(256, 6) push_kernel(const __grid_consta
     } else if (b < G.nblk_h + G.nblk_l + G.nblk_g) {
         const int64_t a = (b - G.nblk_h - G.nblk_l) * 256 + threadIdx.x;
         pdl_wait_primary();
-        if (a < G.m) {
-            const int32_t d = __ldg(&P.g_dest[a]);
-            if (d >= 0) {
-                const int64_t c0 = __ldg(&G.g_cptr[a]), c1 = __ldg(&G.g_cptr[a + 1]);
-                double acc = 0.0;
-                for (int64_t cix = c0; cix < c1; ++cix) acc += G.rel[__ldg(&G.g_cidx[cix])];
-                *dist_dst(P, d) = acc;
-            }
+        if (a < P.n_gtouch) {
+            const int2 ad = __ldg(&P.g_dest[a]);
+            const int64_t c0 = __ldg(&G.g_cptr[ad.x]), c1 = __ldg(&G.g_cptr[ad.x + 1]);
+            double acc = 0.0;
+            for (int64_t cix = c0; cix < c1; ++cix) acc += G.rel[__ldg(&G.g_cidx[cix])];
+            *dist_dst(P, ad.y) = acc;
         }
     } else {
         // this rank's scalar partials {sum w F, <c,Dz>_w, infeasible count} -> every rank's staging row

@@ -121,7 +121,9 @@ struct mgb_plan {
     // ---- multi-GPU peer exchange (mgb_dist_*)
     struct Dist {
         mgb::DistMaps maps;
-        DevBuf<int32_t> h_dest, g_dest, fh_pos, fh_ptr, fg_pos, fg_ptr;
+        DevBuf<int32_t> h_dest, fh_pos, fh_ptr, fg_pos, fg_ptr;
+        DevBuf<int2> g_dest;             // {unknown, destination} of the unknowns this rank contributes to
+        int64_t n_gtouch = 0;
         DevBuf<unsigned int> counter;
         DevBuf<int> err;
         DevBuf<unsigned long long> dbg;  // MGB_DIST_DEBUG: ring of 512 epochs x 8 timeline slots
@@ -857,7 +859,14 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
         if (ctx) {
             CUDA_OK(cudaSetDevice(ctx->device));
             cudaStream_t st = ctx->stream;
-            dd->h_dest.upload(M.h_dest, st); dd->g_dest.upload(M.g_dest, st);
+            dd->h_dest.upload(M.h_dest, st);
+            {
+                std::vector<int2> gd;
+                for (int64_t a = 0; a < (int64_t)M.g_dest.size(); ++a)
+                    if (M.g_dest[a] >= 0) gd.push_back(make_int2((int)a, M.g_dest[a]));
+                dd->n_gtouch = (int64_t)gd.size();
+                dd->g_dest.upload(gd, st);
+            }
             dd->fh_pos.upload(M.fh_pos, st); dd->fh_ptr.upload(M.fh_ptr, st);
             dd->fg_pos.upload(M.fg_pos, st); dd->fg_ptr.upload(M.fg_ptr, st);
             dd->counter.alloc(1); dd->err.alloc(1);
@@ -1028,7 +1037,8 @@ void dist_launch(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const
     P.dbg = dbg;
     P.G = make_gather_params(pl, flags, t, nullptr, nullptr, nullptr);
     size_gather_grid(pl, P.G);
-    P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p;
+    P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p; P.n_gtouch = dd.n_gtouch;
+    if (P.G.want_g) P.G.nblk_g = (dd.n_gtouch + 255) / 256;
     for (int p = 0; p < M.nranks; ++p) {
         char* base = static_cast<char*>(dd.peer[p]);
         P.win[p] = reinterpret_cast<double*>(base) + (size_t)par * M.lay[p].size;
