@@ -97,6 +97,26 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
                     int32_t dim, const double* x_host, const double* w_host,
                     const mgb_barrier* barrier, int64_t row0, int64_t row1, int32_t force_path,
                     mgb_plan** out);
+/* The same symbolic phase fed with this rank's HPCSparseMatrix blocks exactly as the reference stores them
+ * (constructor argument order src/MultiGridBarrierMPI.jl:216-221; older field names
+ * test/test_dump_matrices.jl:62-71): the local rows as CSC-of-the-transpose, i.e. `colptr` indexes the
+ * LOCAL rows, `rowval` holds COMPRESSED local column ids and `col_indices[c]` is the global column of
+ * compressed column c.  All four arrays can be passed zero-copy from Julia (index_base = 1).
+ *   row0          : first global quadrature row of the block (0-based; row_partition[rank]-1, a13)
+ *   x_local/w_local: the rank's rows of x and w (HPCMatrix.A / HPCVector.v local storage, src:176)
+ *   R             : replicated N x m (every rank builds the same native geometry, src:239-240)
+ * The plan is identical to mgb_plan_create(..., row0, row0 + nrows_local, ...) on the global operators. */
+typedef struct {
+    int64_t nrows_local, ncols_compressed, ncols_global, row0;
+    const int32_t* colptr;      /* nrows_local + 1 */
+    const int32_t* rowval;      /* nnz, compressed column ids */
+    const double* nzval;        /* nnz */
+    const int32_t* col_indices; /* ncols_compressed, global column ids */
+    int32_t index_base;         /* 0 (C) or 1 (Julia) */
+} mgb_hpc_block;
+int mgb_plan_create_local(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_hpc_block* D, const mgb_csr* R,
+                          int32_t dim, const double* x_local_host, const double* w_local_host,
+                          const mgb_barrier* barrier, int32_t force_path, mgb_plan** out);
 int mgb_plan_destroy(mgb_plan* plan);
 
 /* sizes: info[0]=path, [1]=n_local, [2]=nD, [3]=m, [4]=nnzH, [5]=elements, [6]=nodes/element,

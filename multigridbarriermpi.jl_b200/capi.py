@@ -23,7 +23,7 @@ BARRIER_EUCLIDIAN_POWER = 1
 
 EXPORTS = [
     "mgb_last_error", "mgb_version", "mgb_ctx_create", "mgb_ctx_destroy", "mgb_ctx_sync", "mgb_plan_create",
-    "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
+    "mgb_plan_create_local", "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
@@ -39,6 +39,13 @@ class _Csr(C.Structure):
     _fields_ = [("nrows", C.c_int64), ("ncols", C.c_int64), ("nnz", C.c_int64),
                 ("rowptr", C.c_void_p), ("colidx", C.c_void_p), ("vals", C.c_void_p),
                 ("index_base", C.c_int32)]
+
+
+class _HpcBlock(C.Structure):
+    """mgb_hpc_block: one rank's HPCSparseMatrix storage in the reference's field layout (src:216-221)."""
+    _fields_ = [("nrows_local", C.c_int64), ("ncols_compressed", C.c_int64), ("ncols_global", C.c_int64),
+                ("row0", C.c_int64), ("colptr", C.c_void_p), ("rowval", C.c_void_p), ("nzval", C.c_void_p),
+                ("col_indices", C.c_void_p), ("index_base", C.c_int32)]
 
 
 class _Barrier(C.Structure):
@@ -77,6 +84,8 @@ def load(build_if_missing: bool = True):
     lib.mgb_plan_create.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_Csr), C.POINTER(_Csr), C.c_int32,
                                     C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int64, C.c_int64, C.c_int32,
                                     C.POINTER(C.c_void_p)]
+    lib.mgb_plan_create_local.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_HpcBlock), C.POINTER(_Csr), C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.POINTER(C.c_void_p)]
     lib.mgb_plan_destroy.argtypes = [C.c_void_p]
     lib.mgb_plan_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
     lib.mgb_plan_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -258,6 +267,48 @@ class Plan:
         h = C.c_void_p()
         _check(lib.mgb_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1], x.ctypes.data, w.ctypes.data,
                                    C.byref(bar), int(row0), int(row1), int(force_path), C.byref(h)))
+        self._finish_init(h)
+
+    @classmethod
+    def from_local_blocks(cls, ctx: Optional["Context"], blocks: Sequence[dict], R: sp.spmatrix, n: int, x_local: np.ndarray,
+                          w_local: np.ndarray, idx: Sequence[int], p: float, slack: bool = False, force_path: int = 0,
+                          idx2: Optional[Sequence[int]] = None, p2: float = 2.0) -> "Plan":
+        """Plan from this rank's HPCSparseMatrix storage (mgb_plan_create_local): every entry of ``blocks`` is the
+        dict ``HPCSparseMatrix.local_storage()`` returns (reference field names colptr / rowval / nzval /
+        col_indices, 1-based)."""
+        lib = load()
+        self = cls.__new__(cls)
+        self.ctx = ctx
+        keep: list = []
+        arr = (_HpcBlock * len(blocks))()
+        for k, b in enumerate(blocks):
+            cp = np.ascontiguousarray(b["colptr"], dtype=np.int32)
+            rv = np.ascontiguousarray(b["rowval"], dtype=np.int32)
+            nz = np.ascontiguousarray(b["nzval"], dtype=np.float64)
+            ci = np.ascontiguousarray(b["col_indices"], dtype=np.int32)
+            keep.extend([cp, rv, nz, ci])
+            arr[k] = _HpcBlock(int(b["nrows_local"]), int(b["ncols_compressed"]), int(b["ncols_global"]), int(b["row0"]),
+                               cp.ctypes.data, rv.ctypes.data, nz.ctypes.data, ci.ctypes.data, int(b.get("index_base", 1)))
+        Rs = _csr_struct(R, keep)
+        bar = _Barrier()
+        bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
+        for j, v in enumerate(idx):
+            bar.idx[j] = int(v)
+        if idx2:
+            bar.nidx2, bar.p2 = len(idx2), float(p2)
+            for j, v in enumerate(idx2):
+                bar.idx2[j] = int(v)
+        x_local = np.asfortranarray(x_local, dtype=np.float64)
+        w_local = np.ascontiguousarray(w_local, dtype=np.float64)
+        h = C.c_void_p()
+        _check(lib.mgb_plan_create_local(ctx._h if ctx is not None else None, int(n), len(blocks), arr, C.byref(Rs),
+                                         x_local.shape[1], x_local.ctypes.data, w_local.ctypes.data, C.byref(bar),
+                                         int(force_path), C.byref(h)))
+        self._finish_init(h)
+        return self
+
+    def _finish_init(self, h):
+        lib = load()
         self._h = h
         info = np.zeros(15, dtype=np.int64)
         _check(lib.mgb_plan_info(h, info.ctypes.data, 15))

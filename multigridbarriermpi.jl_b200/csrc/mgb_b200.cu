@@ -156,6 +156,24 @@ struct mgb_spmat {
 
 namespace {
 
+// sort columns inside each row (HPCSparseMatrix has_sorted_rows may be false)
+void sort_rows(mgb::HostCSR& H) {
+    std::vector<std::pair<int32_t, double>> tmp;
+    for (int64_t i = 0; i < H.nrows; ++i) {
+        bool sorted = true;
+        for (int64_t p = H.ptr[i] + 1; p < H.ptr[i + 1]; ++p)
+            if (H.idx[p] < H.idx[p - 1]) { sorted = false; break; }
+        if (sorted) continue;
+        tmp.clear();
+        for (int64_t p = H.ptr[i]; p < H.ptr[i + 1]; ++p) tmp.emplace_back(H.idx[p], H.val[p]);
+        std::sort(tmp.begin(), tmp.end());
+        for (int64_t p = H.ptr[i]; p < H.ptr[i + 1]; ++p) {
+            H.idx[p] = tmp[p - H.ptr[i]].first;
+            H.val[p] = tmp[p - H.ptr[i]].second;
+        }
+    }
+}
+
 mgb::HostCSR to_host_csr(const mgb_csr& A, int64_t row0, int64_t row1) {
     mgb::HostCSR H;
     const int base = A.index_base;
@@ -174,21 +192,7 @@ mgb::HostCSR to_host_csr(const mgb_csr& A, int64_t row0, int64_t row1) {
         H.idx[p] = j;
         H.val[p] = A.vals[p0 + p];
     }
-    // sort columns inside each row (HPCSparseMatrix has_sorted_rows may be false)
-    std::vector<std::pair<int32_t, double>> tmp;
-    for (int64_t i = 0; i < H.nrows; ++i) {
-        bool sorted = true;
-        for (int64_t p = H.ptr[i] + 1; p < H.ptr[i + 1]; ++p)
-            if (H.idx[p] < H.idx[p - 1]) { sorted = false; break; }
-        if (sorted) continue;
-        tmp.clear();
-        for (int64_t p = H.ptr[i]; p < H.ptr[i + 1]; ++p) tmp.emplace_back(H.idx[p], H.val[p]);
-        std::sort(tmp.begin(), tmp.end());
-        for (int64_t p = H.ptr[i]; p < H.ptr[i + 1]; ++p) {
-            H.idx[p] = tmp[p - H.ptr[i]].first;
-            H.val[p] = tmp[p - H.ptr[i]].second;
-        }
-    }
+    sort_rows(H);
     return H;
 }
 
@@ -337,93 +341,13 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
 
 }  // namespace
 
-extern "C" {
-
-const char* mgb_last_error(void) { return g_err.c_str(); }
-int mgb_version(void) { return 100; }
-int64_t mgb_launch_count(void) { return g_launches.load(); }
-
-int mgb_ctx_create(int device, void* stream, mgb_ctx** out) {
-    try {
-        if (!out) return fail("mgb_ctx_create: out is NULL");
-        int count = 0;
-        cudaError_t e = cudaGetDeviceCount(&count);
-        if (e != cudaSuccess || count == 0)
-            return fail(std::string("mgb_ctx_create: no CUDA device available (") + cudaGetErrorString(e) +
-                        "); this library has no CPU path");
-        if (device < 0 || device >= count) return fail("mgb_ctx_create: bad device index");
-        CUDA_OK(cudaSetDevice(device));
-        cudaDeviceProp prop{};
-        CUDA_OK(cudaGetDeviceProperties(&prop, device));
-        if (prop.major < 10) return fail("mgb_ctx_create: device is not sm_100 class; kernels are built for sm_100a only");
-        auto ctx = std::make_unique<mgb_ctx>();
-        ctx->device = device;
-        ctx->sm_count = prop.multiProcessorCount;
-        // stream == NULL selects the legacy default stream (0): it orders with the caller's other
-        // default-stream work (CUDA.jl / torch enqueue there unless told otherwise)
-        ctx->stream = (cudaStream_t)stream;
-        ctx->flag.alloc(1);
-        *out = ctx.release();
-        return 0;
-    } catch (const std::exception& ex) { return fail(ex.what()); }
-}
-
-int mgb_ctx_destroy(mgb_ctx* ctx) {
-    if (!ctx) return 0;
-    cudaSetDevice(ctx->device);
-    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
-    delete ctx;
-    return 0;
-}
-
-int mgb_ctx_sync(mgb_ctx* ctx) {
-    try {
-        if (!ctx) return fail("mgb_ctx_sync: ctx is NULL");
-        CUDA_OK(cudaStreamSynchronize(ctx->stream));
-        return 0;
-    } catch (const std::exception& ex) { return fail(ex.what()); }
-}
-
-int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
-                    const double* x_host, const double* w_host, const mgb_barrier* barrier, int64_t row0,
-                    int64_t row1, int32_t force_path, mgb_plan** out) {
-    try {
-        if (!D || !R || !w_host || !barrier || !out) return fail("mgb_plan_create: NULL argument");
-        const bool host_only = (ctx == nullptr);  // symbolic-only plan: pattern/info queries, no numeric calls
-        if (nD < 1 || nD > 8) return fail("mgb_plan_create: nD must be 1..8");
-        if (barrier->kind != MGB_BARRIER_EUCLIDIAN_POWER) return fail("mgb_plan_create: unknown barrier kind");
-        if (barrier->nidx < 1 || barrier->nidx > 4) return fail("mgb_plan_create: barrier needs 1..4 idx entries (<=3 derivatives + s)");
-        if (!(barrier->p >= 1.0)) return fail("mgb_plan_create: p must be >= 1");
-        (void)x_host;  // the Euclidian power barrier does not depend on x (p is constant); kept for the f(x,.) signature
-        if (!host_only) CUDA_OK(cudaSetDevice(ctx->device));
-        auto pl = std::make_unique<mgb_plan>();
-        pl->ctx = ctx;
-        pl->n = n; pl->ND = nD; pl->dim = dim;
-        pl->N = D[0].ncols; pl->m = R->ncols; pl->nloc = row1 - row0;
-        if (R->nrows != pl->N) return fail("mgb_plan_create: R rows must equal D columns");
-        pl->bar.kind = barrier->kind; pl->bar.nidx = barrier->nidx; pl->bar.p = barrier->p; pl->bar.slack = barrier->slack;
-        for (int j = 0; j < barrier->nidx; ++j) {
-            if (barrier->idx[j] < 0 || barrier->idx[j] >= nD) return fail("mgb_plan_create: barrier idx outside 0..nD-1");
-            pl->bar.idx[j] = barrier->idx[j];
-        }
-        if (barrier->nidx2 < 0 || barrier->nidx2 > 4) return fail("mgb_plan_create: second cone needs 0 or 2..4 idx entries");
-        if (barrier->nidx2 > 0) {
-            if (barrier->nidx2 < 2 || !(barrier->p2 >= 1.0)) return fail("mgb_plan_create: bad second cone");
-            if (barrier->slack) return fail("mgb_plan_create: slack variant supports a single cone");
-            pl->bar.nidx2 = barrier->nidx2; pl->bar.p2 = barrier->p2;
-            for (int j = 0; j < barrier->nidx2; ++j) {
-                if (barrier->idx2[j] < 0 || barrier->idx2[j] >= nD) return fail("mgb_plan_create: barrier idx2 outside 0..nD-1");
-                pl->bar.idx2[j] = barrier->idx2[j];
-            }
-        }
-        std::vector<mgb::HostCSR> Dh(nD);
-        int64_t nnzD = 0;
-        for (int k = 0; k < nD; ++k) {
-            if (D[k].nrows != n || D[k].ncols != pl->N) return fail("mgb_plan_create: operator shapes differ");
-            Dh[k] = to_host_csr(D[k], row0, row1);
-            nnzD += Dh[k].nnz();
-        }
-        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+namespace {
+// Everything after the inputs are on the host in canonical form: symbolic phase, uploads, replay lists.
+// Dh: the operators restricted to this plan's quadrature rows (nloc x N), wloc: their weights.
+void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, mgb::HostCSR& Rh, std::vector<double>& wloc,
+                 int64_t n, int nD, int dim, int force_path, int64_t nnzD) {
+        mgb_ctx* ctx = pl->ctx;
+        const bool host_only = (ctx == nullptr);
         pl->NU = (int)(pl->N / n);
         cudaStream_t st = host_only ? nullptr : ctx->stream;
         bool use_elem = false;
@@ -432,12 +356,11 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         force_path &= 3;
         pl->has_hessian = want_hess;
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, w_host + row0, pl->bar, pl->ep, want_hess);
+            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
-                return fail("mgb_plan_create: element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
+                throw std::runtime_error("element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
         }
-        std::vector<double> wloc(w_host + row0, w_host + row1);
         if (!host_only) pl->d_w.upload(wloc, st);
         if (use_elem) {
             auto& ep = pl->ep;
@@ -527,9 +450,165 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
         const int64_t nnzS = mgb::count_gram_pattern(Dh);
         pl->alg_bytes = algorithmic_bytes(pl->nloc, pl->N, nD, dim, nnzD, nnzS, Rh.nnz(), pl->nnzH);
         if (!host_only) for (auto& e : pl->ev) CUDA_OK(cudaEventCreate(&e));
+}
+}  // namespace
+
+namespace {
+// argument checks + the fields every plan needs; returns an error text or nullptr
+const char* init_plan(mgb_plan& pl, mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
+                      const mgb_barrier* barrier) {
+    if (nD < 1 || nD > 8) return "nD must be 1..8";
+    if (barrier->kind != MGB_BARRIER_EUCLIDIAN_POWER) return "unknown barrier kind";
+    if (barrier->nidx < 1 || barrier->nidx > 4) return "barrier needs 1..4 idx entries (<=3 derivatives + s)";
+    if (!(barrier->p >= 1.0)) return "p must be >= 1";
+    pl.ctx = ctx;
+    pl.n = n; pl.ND = nD; pl.dim = dim;
+    pl.N = D[0].ncols; pl.m = R->ncols;
+    if (R->nrows != pl.N) return "R rows must equal D columns";
+    if (n <= 0 || pl.N % n) return "operator columns are not a multiple of n";
+    pl.bar.kind = barrier->kind; pl.bar.nidx = barrier->nidx; pl.bar.p = barrier->p; pl.bar.slack = barrier->slack;
+    for (int j = 0; j < barrier->nidx; ++j) {
+        if (barrier->idx[j] < 0 || barrier->idx[j] >= nD) return "barrier idx outside 0..nD-1";
+        pl.bar.idx[j] = barrier->idx[j];
+    }
+    if (barrier->nidx2 < 0 || barrier->nidx2 > 4) return "second cone needs 0 or 2..4 idx entries";
+    if (barrier->nidx2 > 0) {
+        if (barrier->nidx2 < 2 || !(barrier->p2 >= 1.0)) return "bad second cone";
+        if (barrier->slack) return "slack variant supports a single cone";
+        pl.bar.nidx2 = barrier->nidx2; pl.bar.p2 = barrier->p2;
+        for (int j = 0; j < barrier->nidx2; ++j) {
+            if (barrier->idx2[j] < 0 || barrier->idx2[j] >= nD) return "barrier idx2 outside 0..nD-1";
+            pl.bar.idx2[j] = barrier->idx2[j];
+        }
+    }
+    for (int k = 0; k < nD; ++k)
+        if (D[k].nrows != n || D[k].ncols != pl.N) return "operator shapes differ";
+    return nullptr;
+}
+}  // namespace
+
+extern "C" {
+
+const char* mgb_last_error(void) { return g_err.c_str(); }
+int mgb_version(void) { return 100; }
+int64_t mgb_launch_count(void) { return g_launches.load(); }
+
+int mgb_ctx_create(int device, void* stream, mgb_ctx** out) {
+    try {
+        if (!out) return fail("mgb_ctx_create: out is NULL");
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            return fail(std::string("mgb_ctx_create: no CUDA device available (") + cudaGetErrorString(e) +
+                        "); this library has no CPU path");
+        if (device < 0 || device >= count) return fail("mgb_ctx_create: bad device index");
+        CUDA_OK(cudaSetDevice(device));
+        cudaDeviceProp prop{};
+        CUDA_OK(cudaGetDeviceProperties(&prop, device));
+        if (prop.major < 10) return fail("mgb_ctx_create: device is not sm_100 class; kernels are built for sm_100a only");
+        auto ctx = std::make_unique<mgb_ctx>();
+        ctx->device = device;
+        ctx->sm_count = prop.multiProcessorCount;
+        // stream == NULL selects the legacy default stream (0): it orders with the caller's other
+        // default-stream work (CUDA.jl / torch enqueue there unless told otherwise)
+        ctx->stream = (cudaStream_t)stream;
+        ctx->flag.alloc(1);
+        *out = ctx.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(ex.what()); }
+}
+
+int mgb_ctx_destroy(mgb_ctx* ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+int mgb_ctx_sync(mgb_ctx* ctx) {
+    try {
+        if (!ctx) return fail("mgb_ctx_sync: ctx is NULL");
+        CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        return 0;
+    } catch (const std::exception& ex) { return fail(ex.what()); }
+}
+
+int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
+                    const double* x_host, const double* w_host, const mgb_barrier* barrier, int64_t row0,
+                    int64_t row1, int32_t force_path, mgb_plan** out) {
+    try {
+        if (!D || !R || !w_host || !barrier || !out) return fail("mgb_plan_create: NULL argument");
+        const bool host_only = (ctx == nullptr);  // symbolic-only plan: pattern/info queries, no numeric calls
+        auto pl = std::make_unique<mgb_plan>();
+        if (const char* why = init_plan(*pl, ctx, n, nD, D, R, dim, barrier)) return fail(std::string("mgb_plan_create: ") + why);
+        pl->nloc = row1 - row0;
+        (void)x_host;  // the Euclidian power barrier does not depend on x (p is constant); kept for the f(x,.) signature
+        if (!host_only) CUDA_OK(cudaSetDevice(ctx->device));
+        std::vector<mgb::HostCSR> Dh(nD);
+        int64_t nnzD = 0;
+        for (int k = 0; k < nD; ++k) {
+            Dh[k] = to_host_csr(D[k], row0, row1);
+            nnzD += Dh[k].nnz();
+        }
+        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+        std::vector<double> wloc(w_host + row0, w_host + row1);
+        finish_plan(pl, Dh, Rh, wloc, n, nD, dim, force_path, nnzD);
         *out = pl.release();
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_plan_create: ") + ex.what()); }
+}
+
+int mgb_plan_create_local(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_hpc_block* D, const mgb_csr* R, int32_t dim,
+                          const double* x_local_host, const double* w_local_host, const mgb_barrier* barrier,
+                          int32_t force_path, mgb_plan** out) {
+    try {
+        if (!D || !R || !w_local_host || !barrier || !out) return fail("mgb_plan_create_local: NULL argument");
+        const bool host_only = (ctx == nullptr);
+        const int64_t nloc = D[0].nrows_local;
+        std::vector<mgb_csr> shape(nD > 0 && nD <= 8 ? nD : 0);
+        for (auto& c : shape) { c = mgb_csr{}; c.nrows = n; c.ncols = D[0].ncols_global; }
+        for (int k = 0; k < (int)shape.size(); ++k) {
+            if (D[k].nrows_local != nloc || D[k].row0 != D[0].row0) return fail("mgb_plan_create_local: operator row blocks differ");
+            shape[k].ncols = D[k].ncols_global;
+        }
+        if (D[0].row0 < 0 || D[0].row0 + nloc > n) return fail("mgb_plan_create_local: row block outside 0..n");
+        auto pl = std::make_unique<mgb_plan>();
+        if (const char* why = init_plan(*pl, ctx, n, nD, shape.data(), R, dim, barrier)) return fail(std::string("mgb_plan_create_local: ") + why);
+        pl->nloc = nloc;
+        (void)x_local_host;
+        if (!host_only) CUDA_OK(cudaSetDevice(ctx->device));
+        // expand the compressed column ids (rowval -> col_indices[rowval]) to global ids; rows stay local
+        std::vector<mgb::HostCSR> Dh(nD);
+        int64_t nnzD = 0;
+        for (int k = 0; k < nD; ++k) {
+            const mgb_hpc_block& b = D[k];
+            const int base = b.index_base;
+            if (!b.colptr || (!b.rowval && nloc > 0 && b.colptr[nloc] - base > 0) || !b.nzval || (!b.col_indices && b.ncols_compressed > 0))
+                return fail("mgb_plan_create_local: NULL array in operator block");
+            mgb::HostCSR& H = Dh[k];
+            H.nrows = nloc; H.ncols = b.ncols_global;
+            H.ptr.resize(nloc + 1);
+            for (int64_t i = 0; i <= nloc; ++i) H.ptr[i] = (int64_t)b.colptr[i] - base;
+            if (H.ptr[0] != 0) return fail("mgb_plan_create_local: colptr must start at index_base");
+            const int64_t cnt = H.ptr[nloc];
+            H.idx.resize(cnt); H.val.assign(b.nzval, b.nzval + cnt);
+            for (int64_t q = 0; q < cnt; ++q) {
+                const int64_t cc = (int64_t)b.rowval[q] - base;
+                if (cc < 0 || cc >= b.ncols_compressed) return fail("mgb_plan_create_local: compressed column id outside 0..ncols_compressed-1");
+                const int64_t gc = (int64_t)b.col_indices[cc] - base;
+                if (gc < 0 || gc >= b.ncols_global) return fail("mgb_plan_create_local: col_indices entry outside the matrix");
+                H.idx[q] = (int32_t)gc;
+            }
+            sort_rows(H);
+            nnzD += H.nnz();
+        }
+        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+        std::vector<double> wloc(w_local_host, w_local_host + nloc);
+        finish_plan(pl, Dh, Rh, wloc, n, nD, dim, force_path, nnzD);
+        *out = pl.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_plan_create_local: ") + ex.what()); }
 }
 
 int mgb_plan_destroy(mgb_plan* plan) {

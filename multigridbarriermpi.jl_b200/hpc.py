@@ -133,3 +133,17 @@ class HPCSparseMatrix:
     @property
     def nnz(self):
         return self.host.nnz
+
+    def local_storage(self) -> dict:
+        """This rank's block in the reference's own field layout (constructor order
+        src/MultiGridBarrierMPI.jl:216-221; older names test/test_dump_matrices.jl:62-71): the local rows stored
+        as CSC of the transpose - ``colptr`` indexes local rows, ``rowval`` holds COMPRESSED column ids,
+        ``col_indices[c]`` is the global column of compressed column c; everything 1-based in ``Ti``."""
+        loc = self.local
+        lo = int(self.row_partition[self.backend.rank] - 1)
+        cols = np.unique(loc.indices)                       # sorted global columns this block touches
+        comp = np.searchsorted(cols, loc.indices)
+        return dict(nrows_local=loc.shape[0], ncols_compressed=len(cols), ncols_global=loc.shape[1], row0=lo,
+                    colptr=(loc.indptr + 1).astype(self.Ti), rowval=(comp + 1).astype(self.Ti),
+                    nzval=np.ascontiguousarray(loc.data, dtype=np.float64), col_indices=(cols + 1).astype(self.Ti),
+                    index_base=1, has_sorted_rows=True)

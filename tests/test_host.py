@@ -108,3 +108,41 @@ def test_one_based_csr_input_accepted():
     ref = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
     assert info[4] == ref.nnzH and info[3] == ref.m
     lib.mgb_plan_destroy(h)
+
+
+@pytest.mark.parametrize("gen,L,nranks", [("fem1d", 4, 3), ("fem2d", 3, 2), ("fem2d", 3, 4)])
+def test_plan_from_hpc_local_blocks_matches_global_plan(gen, L, nranks):
+    """mgb_plan_create_local takes a rank's HPCSparseMatrix storage as the reference lays it out (compressed
+    column ids + col_indices, 1-based; src/MultiGridBarrierMPI.jl:216-221) and must give the plan that
+    mgb_plan_create builds from the global operators restricted to the same rows."""
+    from mgb_b200.hpc import Backend, HPCSparseMatrix, uniform_partition
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom)
+    n = pr["x"].shape[0]
+    part = uniform_partition(n, nranks, block=geom.block)
+    for rank in range(nranks):
+        be = Backend(device="cpu", rank=rank, nranks=nranks)
+        blocks = [HPCSparseMatrix(Dk, be, row_partition=part).local_storage() for Dk in pr["D"]]
+        lo, hi = int(part[rank] - 1), int(part[rank + 1] - 1)
+        assert blocks[0]["row0"] == lo and blocks[0]["nrows_local"] == hi - lo
+        # compressed ids really are compressed: dx touches only this block's element columns
+        assert blocks[1]["ncols_compressed"] < blocks[1]["ncols_global"]
+        loc = capi.Plan.from_local_blocks(None, blocks, pr["R"], n, pr["x"][lo:hi], pr["w"][lo:hi], pr["idx"], 1.0)
+        ref = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, rows=(lo, hi))
+        assert loc.info == ref.info
+        for a, b in zip(loc.pattern(), ref.pattern()):
+            assert np.array_equal(a, b)
+
+
+def test_plan_from_hpc_local_blocks_rejects_bad_ids():
+    from mgb_b200.hpc import Backend, HPCSparseMatrix
+    pr = problem(mgb_b200.fem1d(3))
+    n = pr["x"].shape[0]
+    be = Backend(device="cpu")
+    blocks = [HPCSparseMatrix(Dk, be).local_storage() for Dk in pr["D"]]
+    bad = dict(blocks[1]); bad["rowval"] = blocks[1]["rowval"].copy(); bad["rowval"][0] = bad["ncols_compressed"] + 1
+    with pytest.raises(capi.MgbError, match="compressed column id"):
+        capi.Plan.from_local_blocks(None, [blocks[0], bad, blocks[2]], pr["R"], n, pr["x"], pr["w"], pr["idx"], 1.0)
+    bad = dict(blocks[1]); bad["col_indices"] = blocks[1]["col_indices"].copy(); bad["col_indices"][0] = 0
+    with pytest.raises(capi.MgbError, match="col_indices"):
+        capi.Plan.from_local_blocks(None, [blocks[0], bad, blocks[2]], pr["R"], n, pr["x"], pr["w"], pr["idx"], 1.0)

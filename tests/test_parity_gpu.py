@@ -72,3 +72,38 @@ def test_csr_path(gpu_ctx, gen, L, level):
     geom = mgb_b200.fem3d(L, k=1) if gen == "fem3d" else getattr(mgb_b200, gen)(L)
     plan, _ = check_against_oracle(gpu_ctx, geom, 1.0, t=0.9, level=level, force_path=capi.PATH_CSR)
     assert plan.info["path"] == capi.PATH_CSR
+
+
+def test_fem3d_q3_default_table(gpu_ctx):
+    """config C4 at a size the oracle finishes in seconds: fem3d k=3 (64-node elements, nD=5), reference
+    problem data src/MultiGridBarrierMPI.jl:736-738"""
+    check_against_oracle(gpu_ctx, mgb_b200.fem3d(2), 1.0, t=0.9)
+    check_against_oracle(gpu_ctx, mgb_b200.fem3d(2), 1.5, t=0.9, level=0)
+
+
+@pytest.mark.parametrize("gen,L,nranks", [("fem2d", 3, 2), ("fem1d", 5, 3)])
+def test_plans_from_hpc_local_blocks_sum_to_the_oracle(gpu_ctx, gen, L, nranks):
+    """every rank builds its plan from its own HPCSparseMatrix storage (mgb_plan_create_local: compressed column
+    ids + col_indices, 1-based); the rank contributions add up to the oracle's gradient and Hessian"""
+    import scipy.sparse as sp
+    from helpers import problem, oracle_eval, rel
+    from mgb_b200.hpc import Backend, HPCSparseMatrix, uniform_partition
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom)
+    n = pr["x"].shape[0]
+    part = uniform_partition(n, nranks, block=geom.block)
+    f0_o, g_o, H_o = oracle_eval(pr, 0.8)
+    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
+    f0 = 0.0; g = 0.0; H = None
+    for rank in range(nranks):
+        be = Backend(device="cpu", rank=rank, nranks=nranks)
+        lo, hi = int(part[rank] - 1), int(part[rank + 1] - 1)
+        blocks = [HPCSparseMatrix(Dk, be, row_partition=part).local_storage() for Dk in pr["D"]]
+        plan = capi.Plan.from_local_blocks(gpu_ctx, blocks, pr["R"], n, pr["x"][lo:hi], pr["w"][lo:hi], pr["idx"], 1.0)
+        out = plan.assemble_host(pr["s"], Dz0[lo:hi], pr["c"][lo:hi], 0.8, capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS)
+        rp, ci = plan.pattern()   # the rows this rank's quadrature points touch: differs per rank
+        Hr = sp.csr_matrix((out["hval"], ci.astype(np.int64), rp.astype(np.int64)), shape=(plan.m, plan.m))
+        f0 += out["scal"][0]; g = g + out["grad"]; H = Hr if H is None else H + Hr
+    assert abs(f0 - f0_o) <= 1e-12 * max(1.0, abs(f0_o))
+    assert rel(g, g_o) <= 1e-12
+    assert abs(H - H_o).max() <= 1e-12 * abs(H_o).max()
