@@ -121,7 +121,8 @@ int mgb_plan_destroy(mgb_plan* plan);
 
 /* sizes: info[0]=path, [1]=n_local, [2]=nD, [3]=m, [4]=nnzH, [5]=elements, [6]=nodes/element,
  * [7]=local cols/var, [8]=slots/element, [9]=Hessian contributions, [10]=gradient contributions,
- * [11]=plan device bytes, [12]=N, [13]=nu, [14]=algorithmic bytes per assembly (SURVEY 8d formula) */
+ * [11]=plan device bytes, [12]=N, [13]=nu, [14]=algorithmic bytes per assembly (SURVEY 8d formula),
+ * [15]=Hessian contributions stored incl. slice padding (CSR path) */
 int mgb_plan_info(const mgb_plan* plan, int64_t* info, int32_t ninfo);
 
 /* Fixed sparsity pattern of R' H R (CSR, 0-based, sorted columns) -> host buffers. */

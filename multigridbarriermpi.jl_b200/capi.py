@@ -242,7 +242,8 @@ class Plan:
     ``ctx=None`` builds a symbolic-only plan (pattern/info queries; numeric calls raise)."""
 
     INFO = ["path", "n_local", "nD", "m", "nnzH", "elements", "nodes_per_element", "cols_per_var",
-            "slots_per_element", "hess_contribs", "grad_contribs", "plan_bytes", "N", "nu", "alg_bytes"]
+            "slots_per_element", "hess_contribs", "grad_contribs", "plan_bytes", "N", "nu", "alg_bytes",
+            "hess_stored"]
 
     def __init__(self, ctx: Context, D: Sequence[sp.spmatrix], R: sp.spmatrix, x: np.ndarray, w: np.ndarray,
                  idx: Sequence[int], p: float, slack: bool = False, rows=None, force_path: int = 0,
@@ -310,8 +311,8 @@ class Plan:
     def _finish_init(self, h):
         lib = load()
         self._h = h
-        info = np.zeros(15, dtype=np.int64)
-        _check(lib.mgb_plan_info(h, info.ctypes.data, 15))
+        info = np.zeros(16, dtype=np.int64)
+        _check(lib.mgb_plan_info(h, info.ctypes.data, 16))
         self.info = dict(zip(self.INFO, (int(v) for v in info)))
         self.n_local, self.nD, self.m, self.nnzH = (self.info[k] for k in ("n_local", "nD", "m", "nnzH"))
         self._pattern = None
@@ -410,8 +411,8 @@ class DistPlan(Plan):
                                         x.ctypes.data, w.ctypes.data, C.byref(bar), int(rank), int(nranks),
                                         rp.ctypes.data, op.ctypes.data, C.byref(h)))
         self._h = h
-        info = np.zeros(15, dtype=np.int64)
-        _check(lib.mgb_plan_info(h, info.ctypes.data, 15))
+        info = np.zeros(16, dtype=np.int64)
+        _check(lib.mgb_plan_info(h, info.ctypes.data, 16))
         self.info = dict(zip(self.INFO, (int(v) for v in info)))
         self.n_local, self.nD, self.m, self.nnzH = (self.info[k] for k in ("n_local", "nD", "m", "nnzH"))
         self._pattern = None

@@ -11,6 +11,7 @@
 #include <stdint.h>
 
 #include <algorithm>
+#include <functional>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -18,30 +19,121 @@
 #include "kernels.cuh"
 #include "plan_host.h"
 
+#include <cstdlib>
+
 namespace mgb {
 
-struct CsrOpDev {
-    const int64_t* ptr;
-    const int32_t* idx;
-    const double* val;
+// sorting window of the SELL lists (outputs); MGB_SELL_SIGMA in the environment overrides it (tuning runs)
+static int sell_sigma() {
+    const char* e = std::getenv("MGB_SELL_SIGMA");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 ? v : 4096;
+}
+// apply_D lists are nearly uniform on fine levels: a short window keeps the Dz0 reads / Dz stores local
+static int sell_sigma_apply() { return std::min(sell_sigma(), 256); }
+// Hessian stores: 1 = stage a window's results in shared memory and store them in CSR order (coalesced),
+// 0 = every slot stores its own result (scattered inside the window); MGB_HESS_STAGE overrides
+static bool hess_staged(int sigma) {
+    const char* e = std::getenv("MGB_HESS_STAGE");
+    const bool want = e ? std::atoi(e) != 0 : true;
+    return want && sigma % 32 == 0 && sigma >= 256 && sigma <= 8192;
+}
+
+// Sliced-ELL replay list (SELL-32-sigma).  Every output value (a Dz entry, a gradient entry, an upper-triangle
+// Hessian entry) owns a list of (coefficient, source index) contributions that is fixed per level.  Outputs are
+// grouped in slices of 32 = one warp; contribution r of lane l of slice s sits at (off[s] + r) * 32 + l, so every
+// warp load of coefficients / source ids is one contiguous, fully used run (the thread-per-list CSR walk touched
+// 32 different sectors per step and idled the warp on its longest list).  Inside every window of `sigma`
+// consecutive outputs the outputs are sorted by list length first (stable), which removes the padding and the
+// divergence; perm[slot] is the output a slot stands for (-1: padding slot).  Padding contributions carry
+// src = -1 and are skipped by a predicate - a 0 * Inf of a non-finite iterate must not leak into other entries.
+// The order of a list is unchanged, so results are bit-identical to the sequential replay.
+struct SellHost {
+    std::vector<uint32_t> off;   // nslices + 1, in units of 32 contributions
+    std::vector<int32_t> perm;   // nslices * 32
+    std::vector<int32_t> src;
+    std::vector<double> coef;
 };
+
+template <class PtrT>
+static void build_sell(int64_t nent, const PtrT* ptr, const double* coef, const int32_t* src, int sigma, SellHost& out) {
+    const int64_t nsl = (nent + 31) / 32;
+    out.perm.assign((size_t)nsl * 32, -1);
+    std::vector<int32_t> win;
+    for (int64_t w0 = 0; w0 < nent; w0 += sigma) {
+        const int64_t w1 = std::min<int64_t>(nent, w0 + sigma);
+        win.resize((size_t)(w1 - w0));
+        for (int64_t j = w0; j < w1; ++j) win[(size_t)(j - w0)] = (int32_t)j;
+        if (sigma > 1)
+            std::stable_sort(win.begin(), win.end(), [&](int32_t a, int32_t b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
+        for (int64_t j = w0; j < w1; ++j) out.perm[(size_t)j] = win[(size_t)(j - w0)];
+    }
+    out.off.assign((size_t)nsl + 1, 0);
+    for (int64_t sl = 0; sl < nsl; ++sl) {
+        int64_t len = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int32_t e = out.perm[(size_t)sl * 32 + l];
+            if (e >= 0) len = std::max<int64_t>(len, (int64_t)(ptr[e + 1] - ptr[e]));
+        }
+        const int64_t nxt = (int64_t)out.off[(size_t)sl] + len;
+        if (nxt > (int64_t)UINT32_MAX) throw std::runtime_error("csr path: replay list too long for 32-bit slice offsets");
+        out.off[(size_t)sl + 1] = (uint32_t)nxt;
+    }
+    const size_t tot = (size_t)out.off[(size_t)nsl] * 32;
+    out.coef.assign(tot, 0.0);
+    out.src.assign(tot, -1);
+    for (int64_t sl = 0; sl < nsl; ++sl)
+        for (int l = 0; l < 32; ++l) {
+            const int32_t e = out.perm[(size_t)sl * 32 + l];
+            if (e < 0) continue;
+            size_t q = (size_t)out.off[(size_t)sl] * 32 + l;
+            for (int64_t r = (int64_t)ptr[e]; r < (int64_t)ptr[e + 1]; ++r, q += 32) { out.coef[q] = coef[r]; out.src[q] = src[r]; }
+        }
+}
+
+// contributions a SELL list stores, padding included (plan statistics; no arrays are built)
+template <class PtrT>
+static int64_t sell_stored(int64_t nent, const PtrT* ptr, int sigma) {
+    std::vector<int64_t> len;
+    int64_t tot = 0;
+    for (int64_t w0 = 0; w0 < nent; w0 += std::max(sigma, 32)) {
+        const int64_t w1 = std::min<int64_t>(nent, w0 + std::max(sigma, 32));
+        len.clear();
+        for (int64_t j = w0; j < w1; ++j) len.push_back((int64_t)(ptr[j + 1] - ptr[j]));
+        if (sigma > 1) std::sort(len.begin(), len.end(), std::greater<int64_t>());
+        for (size_t q = 0; q < len.size(); q += 32) tot += 32 * *std::max_element(len.begin() + q, len.begin() + std::min(len.size(), q + 32));
+    }
+    return tot;
+}
+
+struct SellDev {
+    const uint32_t* off = nullptr;
+    const int32_t* perm = nullptr;
+    const int32_t* src = nullptr;
+    const double* coef = nullptr;
+    int64_t nslot = 0;   // slices * 32
+};
+
+__global__ void csr_hess_staged_kernel(const __grid_constant__ SellDev L, const int sigma, const int64_t nup, const int32_t* __restrict__ nat_t,
+                                       const int32_t* __restrict__ nat_m, const double* __restrict__ V, double* __restrict__ hval);
 
 struct CsrDev {
     int ND = 0, npair = 0;
     int pair_a[36] = {0}, pair_b[36] = {0};
     int64_t nloc = 0, m = 0, nnzH = 0, nprod = 0, nup = 0;
+    int64_t pad_apply = 0, pad_grad = 0, pad_hess = 0;   // stored contributions incl. padding (diagnostics)
     int max_row = 0;
     BarrierDesc bar;
     std::vector<void*> owned;  // device allocations
-    CsrOpDev E[8];
-    const int32_t* gt_ptr = nullptr;
-    const double* gt_coef = nullptr;
-    const int32_t* gt_src = nullptr;
-    const int32_t* up_t = nullptr;
-    const int32_t* up_m = nullptr;
-    const int32_t* prod_ptr = nullptr;
-    const double* prod_coef = nullptr;
-    const int32_t* prod_v = nullptr;
+    SellDev E[8];              // apply_D: outputs = local rows of E_k = D_k R, sources = unknowns
+    SellDev G;                 // gradient: outputs = unknowns, sources = gy entries (k * nloc + i)
+    SellDev Hs;                // Hessian: outputs = upper-triangle entries, sources = V entries (pair * nloc + i)
+    const int32_t* up_t = nullptr;   // per slot: position of the entry in the CSR value array (-1: padding slot)
+    const int32_t* up_m = nullptr;   // per slot: position of the mirror entry (-1: diagonal / padding)
+    const int32_t* nat_t = nullptr;  // the same two maps per upper entry in CSR order (staged stores)
+    const int32_t* nat_m = nullptr;
+    int hess_sigma = 0;              // sorting window of Hs
+    bool staged = false;
     double* Dz = nullptr;    // nloc x ND
     double* gy = nullptr;    // nloc x ND
     double* V = nullptr;     // nloc x npair
@@ -56,10 +148,22 @@ static const T* csr_up(CsrDev& d, const std::vector<T>& h, cudaStream_t st, size
     const size_t nb = std::max<size_t>(h.size(), 1) * sizeof(T);
     if (cudaMalloc(&p, nb) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (csr plan)");
     d.owned.push_back(p);
-    if (!h.empty() && cudaMemcpyAsync(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess)
-        throw std::runtime_error("cudaMemcpyAsync failed (csr plan)");
+    // the host vectors die before the stream is synchronised by the caller: copy synchronously
+    if (!h.empty() && cudaMemcpy(p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess)
+        throw std::runtime_error("cudaMemcpy failed (csr plan)");
+    (void)st;
     bytes += nb;
     return p;
+}
+
+static SellDev sell_upload(CsrDev& d, const SellHost& h, cudaStream_t st, size_t& bytes) {
+    SellDev o;
+    o.off = csr_up(d, h.off, st, bytes);
+    o.perm = csr_up(d, h.perm, st, bytes);
+    o.src = csr_up(d, h.src, st, bytes);
+    o.coef = csr_up(d, h.coef, st, bytes);
+    o.nslot = (int64_t)h.perm.size();
+    return o;
 }
 
 static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, cudaStream_t st) {
@@ -68,16 +172,36 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     d.nprod = (int64_t)cp.prod_coef.size(); d.nup = (int64_t)cp.up_t.size(); d.max_row = cp.max_row; d.bar = bar;
     d.npair = cp.npair;
     for (int c = 0; c < cp.npair; ++c) { d.pair_a[c] = cp.pair_a[c]; d.pair_b[c] = cp.pair_b[c]; }
-    for (int k = 0; k < cp.ND; ++k)
-        d.E[k] = {csr_up(d, cp.E[k].ptr, st, bytes), csr_up(d, cp.E[k].idx, st, bytes), csr_up(d, cp.E[k].val, st, bytes)};
-    d.gt_ptr = csr_up(d, cp.gt_ptr, st, bytes);
-    d.gt_coef = csr_up(d, cp.gt_coef, st, bytes);
-    d.gt_src = csr_up(d, cp.gt_src, st, bytes);
-    d.up_t = csr_up(d, cp.up_t, st, bytes);
-    d.up_m = csr_up(d, cp.up_m, st, bytes);
-    d.prod_ptr = csr_up(d, cp.prod_ptr, st, bytes);
-    d.prod_coef = csr_up(d, cp.prod_coef, st, bytes);
-    d.prod_v = csr_up(d, cp.prod_v, st, bytes);
+    for (int k = 0; k < cp.ND; ++k) {
+        SellHost h;
+        build_sell(cp.nloc, cp.E[k].ptr.data(), cp.E[k].val.data(), cp.E[k].idx.data(), sell_sigma_apply(), h);
+        d.E[k] = sell_upload(d, h, st, bytes);
+        d.pad_apply += (int64_t)h.coef.size();
+    }
+    {
+        SellHost h;
+        build_sell(cp.m, cp.gt_ptr.data(), cp.gt_coef.data(), cp.gt_src.data(), sell_sigma(), h);
+        d.G = sell_upload(d, h, st, bytes);
+        d.pad_grad = (int64_t)h.coef.size();
+    }
+    {
+        SellHost h;
+        d.hess_sigma = sell_sigma();
+        d.staged = hess_staged(d.hess_sigma);
+        build_sell(d.nup, cp.prod_ptr.data(), cp.prod_coef.data(), cp.prod_v.data(), d.hess_sigma, h);
+        d.Hs = sell_upload(d, h, st, bytes);
+        d.nat_t = csr_up(d, cp.up_t, st, bytes);
+        d.nat_m = csr_up(d, cp.up_m, st, bytes);
+        if (d.staged && d.hess_sigma * 8 > 48 * 1024 &&
+            cudaFuncSetAttribute(csr_hess_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.hess_sigma * 8) != cudaSuccess)
+            throw std::runtime_error("cudaFuncSetAttribute failed (csr_hess_staged_kernel)");
+        d.pad_hess = (int64_t)h.coef.size();
+        std::vector<int32_t> t(h.perm.size(), -1), mm(h.perm.size(), -1);
+        for (size_t q = 0; q < h.perm.size(); ++q)
+            if (h.perm[q] >= 0) { t[q] = cp.up_t[(size_t)h.perm[q]]; mm[q] = cp.up_m[(size_t)h.perm[q]]; }
+        d.up_t = csr_up(d, t, st, bytes);
+        d.up_m = csr_up(d, mm, st, bytes);
+    }
     auto scratch = [&](size_t count) {
         double* p = nullptr;
         if (cudaMalloc(&p, std::max<size_t>(count, 1) * 8) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (csr scratch)");
@@ -93,8 +217,23 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     return bytes;
 }
 
+// one slot's replay: sum of coef * x[src] over the slice's rows, in list order
+__device__ __forceinline__ double sell_replay(const SellDev& L, const double* __restrict__ x, const int64_t slot) {
+    const int64_t sl = slot >> 5;
+    const uint32_t o0 = __ldg(&L.off[sl]), o1 = __ldg(&L.off[sl + 1]);
+    int64_t q = (int64_t)o0 * 32 + (slot & 31);
+    double acc = 0.0;
+#pragma unroll 4
+    for (uint32_t r = o0; r < o1; ++r, q += 32) {
+        const int32_t v = __ldg(&L.src[q]);
+        const double c = __ldg(&L.coef[q]);
+        if (v >= 0) acc = fma(c, x[v], acc);
+    }
+    return acc;
+}
+
 struct CsrApplyParams {
-    CsrOpDev E[8];
+    SellDev E[8];
     int ND;
     int64_t n;
     const double* s;
@@ -102,15 +241,16 @@ struct CsrApplyParams {
     double* Dz;
 };
 
-__global__ void __launch_bounds__(256) csr_apply_kernel(const CsrApplyParams P) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= P.n) return;
-    for (int k = 0; k < P.ND; ++k) {
-        double acc = P.Dz0 ? P.Dz0[(int64_t)k * P.n + i] : 0.0;
-        const int64_t p0 = P.E[k].ptr[i], p1 = P.E[k].ptr[i + 1];
-        for (int64_t p = p0; p < p1; ++p) acc = fma(P.E[k].val[p], __ldg(&P.s[P.E[k].idx[p]]), acc);
-        P.Dz[(int64_t)k * P.n + i] = acc;
-    }
+// apply_D: blockIdx.y = operator, one slot per local row (rows sorted by length inside windows of sigma)
+__global__ void __launch_bounds__(256) csr_apply_kernel(const __grid_constant__ CsrApplyParams P) {
+    const int k = blockIdx.y;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= P.E[k].nslot) return;
+    const double dot = sell_replay(P.E[k], P.s, slot);
+    const int32_t i = __ldg(&P.E[k].perm[slot]);
+    if (i < 0) return;
+    const int64_t o = (int64_t)k * P.n + i;
+    P.Dz[o] = P.Dz0 ? P.Dz0[o] + dot : dot;
 }
 
 struct CsrBarrierParams {
@@ -235,37 +375,58 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant_
     }
 }
 
-// g[a] = sum_r gt_coef[r] * gy[gt_src[r]]: the transposed operators merged into one list per unknown
+// g[a] = sum_r coef[r] * gy[src[r]]: the transposed operators merged into one list per unknown
 // (gather, no atomics, fixed order)
-__global__ void __launch_bounds__(256) csr_grad_kernel(int64_t m, const int32_t* __restrict__ ptr, const double* __restrict__ coef,
-                                                       const int32_t* __restrict__ src, const double* __restrict__ gy,
+__global__ void __launch_bounds__(256) csr_grad_kernel(const __grid_constant__ SellDev L, const double* __restrict__ gy,
                                                        double* __restrict__ grad) {
-    const int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= m) return;
-    const int r0 = __ldg(&ptr[a]), r1 = __ldg(&ptr[a + 1]);
-    double acc = 0.0;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), gy[__ldg(&src[r])], acc);
-    grad[a] = acc;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= L.nslot) return;
+    const double acc = sell_replay(L, gy, slot);
+    const int32_t a = __ldg(&L.perm[slot]);
+    if (a >= 0) grad[a] = acc;
 }
 
 // numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry; it sums its
 // precomputed products coef * V in list order (no atomics, bit-reproducible) and stores the value at (a,b) and
 // at the mirror (b,a) - R'HR is symmetric, so half of the product lists never has to be read.
 // coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
-__global__ void __launch_bounds__(256) csr_hess_kernel(int64_t nup, const int32_t* __restrict__ up_t, const int32_t* __restrict__ up_m,
-                                                       const int32_t* __restrict__ prod_ptr, const double* __restrict__ coef,
-                                                       const int32_t* __restrict__ vsrc, const double* __restrict__ V,
+__global__ void __launch_bounds__(256) csr_hess_kernel(const __grid_constant__ SellDev L, const int32_t* __restrict__ up_t,
+                                                       const int32_t* __restrict__ up_m, const double* __restrict__ V,
                                                        double* __restrict__ hval) {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= nup) return;
-    const int r0 = __ldg(&prod_ptr[j]), r1 = __ldg(&prod_ptr[j + 1]);
-    const int32_t t = __ldg(&up_t[j]), tm = __ldg(&up_m[j]);
-    double acc = 0.0;
-#pragma unroll 4
-    for (int r = r0; r < r1; ++r) acc = fma(__ldg(&coef[r]), V[__ldg(&vsrc[r])], acc);
-    hval[t] = acc;
+    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (slot >= L.nslot) return;
+    const int32_t t = __ldg(&up_t[slot]), tm = __ldg(&up_m[slot]);
+    const double acc = sell_replay(L, V, slot);
+    if (t >= 0) hval[t] = acc;
     if (tm >= 0) hval[tm] = acc;
+}
+
+// the same replay with coalesced stores: one CTA per sorting window of `sigma` upper entries.  Warps take the
+// window's slices round-robin (slices are sorted by length, so the warps stay balanced), every slot drops its sum
+// into shared memory at the entry's position inside the window, and after one barrier the CTA stores the window
+// in CSR order (the upper entries of a window are nearly contiguous in the value array; only the mirror stores
+// scatter).
+__global__ void __launch_bounds__(256) csr_hess_staged_kernel(const __grid_constant__ SellDev L, const int sigma, const int64_t nup,
+                                                              const int32_t* __restrict__ nat_t, const int32_t* __restrict__ nat_m,
+                                                              const double* __restrict__ V, double* __restrict__ hval) {
+    extern __shared__ double win[];
+    const int64_t w0 = (int64_t)blockIdx.x * sigma;
+    const int cnt = (int)min((int64_t)sigma, nup - w0);
+    const int nsl = (cnt + 31) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int sl = threadIdx.x >> 5; sl < nsl; sl += 8) {
+        const int64_t slot = w0 + (int64_t)sl * 32 + lane;
+        const double acc = sell_replay(L, V, slot);
+        const int32_t e = __ldg(&L.perm[slot]);
+        if (e >= 0) win[e - w0] = acc;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += 256) {
+        const double v = win[j];
+        hval[__ldg(&nat_t[w0 + j])] = v;
+        const int32_t tm = __ldg(&nat_m[w0 + j]);
+        if (tm >= 0) hval[tm] = v;
+    }
 }
 
 static __global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
@@ -309,10 +470,13 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
     if ((flags & 4) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
     {
         CsrApplyParams P{};
-        for (int k = 0; k < d.ND; ++k) P.E[k] = d.E[k];
+        int64_t nslot = 0;
+        for (int k = 0; k < d.ND; ++k) { P.E[k] = d.E[k]; nslot = std::max(nslot, d.E[k].nslot); }
         P.ND = d.ND; P.n = n; P.s = s; P.Dz0 = Dz0; P.Dz = Dz;
-        csr_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(P);
-        ++launches;
+        if (nslot > 0) {
+            csr_apply_kernel<<<dim3((unsigned)((nslot + 255) / 256), (unsigned)d.ND), 256, 0, st>>>(P);
+            ++launches;
+        }
     }
     {
         CsrBarrierParams P{};
@@ -336,12 +500,16 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         csr_barrier_kernel<<<(unsigned)d.nblk, 256, 0, st>>>(P);
         ++launches;
     }
-    if (flags & 2) {
-        csr_grad_kernel<<<(unsigned)((d.m + 255) / 256), 256, 0, st>>>(d.m, d.gt_ptr, d.gt_coef, d.gt_src, d.gy, grad);
+    if ((flags & 2) && d.G.nslot > 0) {
+        csr_grad_kernel<<<(unsigned)((d.G.nslot + 255) / 256), 256, 0, st>>>(d.G, d.gy, grad);
         ++launches;
     }
     if ((flags & 4) && d.nup > 0) {
-        csr_hess_kernel<<<(unsigned)((d.nup + 255) / 256), 256, 0, st>>>(d.nup, d.up_t, d.up_m, d.prod_ptr, d.prod_coef, d.prod_v, d.V, hval);
+        if (d.staged)
+            csr_hess_staged_kernel<<<(unsigned)((d.nup + d.hess_sigma - 1) / d.hess_sigma), 256, (size_t)d.hess_sigma * 8, st>>>(
+                d.Hs, d.hess_sigma, d.nup, d.nat_t, d.nat_m, d.V, hval);
+        else
+            csr_hess_kernel<<<(unsigned)((d.Hs.nslot + 255) / 256), 256, 0, st>>>(d.Hs, d.up_t, d.up_m, d.V, hval);
         ++launches;
     }
     scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);

@@ -86,7 +86,7 @@ struct mgb_plan {
     DevBuf<int32_t> d_hlidx, d_hlt;
     int64_t n_long = 0;
     DevBuf<double> d_prec, d_w, d_sel, d_rel, d_part, d_scal_tmp;
-    int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0;
+    int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0, n_hstored = 0;
     // patch-fused path
     int patch = 0;  // elements per CTA (0 = two-stage path)
     int NSP = 0, RSP = 0;
@@ -440,6 +440,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->nnzH = (int64_t)cp.h_colidx.size();
             pl->h_rowptr = cp.h_rowptr; pl->h_colidx = cp.h_colidx;
             pl->n_hcontrib = (int64_t)cp.prod_coef.size();
+            pl->n_hstored = mgb::sell_stored(cp.up_t.size(), cp.prod_ptr.data(), mgb::sell_sigma());
             if (!host_only) {
                 pl->dev_bytes = mgb::csr_upload(cp, pl->bar, pl->csr, st) + pl->d_w.bytes();
                 pl->d_scal_tmp.alloc(4);
@@ -624,10 +625,10 @@ int mgb_plan_destroy(mgb_plan* plan) {
 
 int mgb_plan_info(const mgb_plan* pl, int64_t* info, int32_t ninfo) {
     if (!pl || !info) return fail("mgb_plan_info: NULL argument");
-    int64_t v[15] = {pl->path, pl->nloc, pl->ND, pl->m, pl->nnzH, pl->ep.E, pl->ep.B, pl->ep.B, pl->ep.lay.NS,
-                     pl->n_hcontrib, pl->n_gcontrib, (int64_t)pl->dev_bytes, pl->N, pl->NU, pl->alg_bytes};
+    int64_t v[16] = {pl->path, pl->nloc, pl->ND, pl->m, pl->nnzH, pl->ep.E, pl->ep.B, pl->ep.B, pl->ep.lay.NS,
+                     pl->n_hcontrib, pl->n_gcontrib, (int64_t)pl->dev_bytes, pl->N, pl->NU, pl->alg_bytes, pl->n_hstored};
     if (pl->path == MGB_PATH_CSR) { v[5] = 0; v[6] = 0; v[7] = 0; v[8] = 0; v[10] = 0; }
-    for (int i = 0; i < ninfo && i < 15; ++i) info[i] = v[i];
+    for (int i = 0; i < ninfo && i < 16; ++i) info[i] = v[i];
     return 0;
 }
 

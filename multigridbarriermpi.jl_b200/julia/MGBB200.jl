@@ -71,6 +71,41 @@ function Plan(ctx::Ctx, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::Mat
     finalizer(p -> ccall((:mgb_plan_destroy, LIB), Cint, (Ptr{Cvoid},), p.h), pl); pl
 end
 
+# The rank's own storage of a row-partitioned HPCSparseMatrix, field for field (constructor order
+# src/MultiGridBarrierMPI.jl:216-221): colptr indexes LOCAL rows, rowval holds COMPRESSED column ids,
+# col_indices maps them to global columns.  Passed zero-copy to mgb_plan_create_local (struct mgb_hpc_block).
+struct MgbHpcBlock
+    nrows_local::Int64; ncols_compressed::Int64; ncols_global::Int64; row0::Int64
+    colptr::Ptr{Int32}; rowval::Ptr{Int32}; nzval::Ptr{Float64}; col_indices::Ptr{Int32}
+    index_base::Int32
+end
+hpc_block(A::HPCSparseMatrix, rank::Integer) =
+    MgbHpcBlock(A.nrows_local, A.ncols_compressed, size(A, 2), A.row_partition[rank + 1] - 1,
+                pointer(A.colptr), pointer(A.rowval), pointer(A.nzval), pointer(A.col_indices), Int32(1))
+
+# Plan from the local blocks: no rank ever needs the global operators (only R is replicated, src:239-240).
+function LocalPlan(ctx::Ctx, comm, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::HPCMatrix, w::HPCVector;
+                   idx::Vector{Int}, p::Float64, slack::Bool = false)
+    rank = MPI.Comm_rank(comm)
+    Ds = [hpc_block(d, rank) for d in D]; Rs = Ref(csr(R))
+    bar = Ref(MgbBarrier(idx, p, slack))
+    r = Ref{Ptr{Cvoid}}(C_NULL)
+    xl = Array(x.A); wl = Array(w.v)          # local rows (HPCMatrix.A / HPCVector.v, src:176)
+    GC.@preserve D R xl wl begin
+        check(ccall((:mgb_plan_create_local, LIB), Cint,
+                    (Ptr{Cvoid}, Int64, Int32, Ptr{MgbHpcBlock}, Ref{MgbCsr}, Int32, Ptr{Float64}, Ptr{Float64},
+                     Ref{MgbBarrier}, Int32, Ref{Ptr{Cvoid}}),
+                    ctx.h, size(D[1], 1), length(D), Ds, Rs, size(xl, 2), xl, wl, bar, 0, r))
+    end
+    info = zeros(Int64, 16)
+    check(ccall((:mgb_plan_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32), r[], info, 16))
+    m, nnzH = info[4], info[5]
+    rp = zeros(Int32, m + 1); ci = zeros(Int32, nnzH)
+    check(ccall((:mgb_plan_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), r[], rp, ci))
+    pl = Plan(r[], m, nnzH, rp, ci)
+    finalizer(p -> ccall((:mgb_plan_destroy, LIB), Cint, (Ptr{Cvoid},), p.h), pl); pl
+end
+
 const WANT_F0, WANT_GRAD, WANT_HESS, STORE_DZ = 1, 2, 4, 8
 
 "numeric phase: everything stays on the device (CuArray pointers are borrowed for the call)"
