@@ -27,53 +27,85 @@ namespace mgb {
 static int sell_sigma() {
     const char* e = std::getenv("MGB_SELL_SIGMA");
     const int v = e ? std::atoi(e) : 0;
-    return v >= 1 ? v : 4096;
+    return v >= 1 ? v : 16384;
 }
 // apply_D lists are nearly uniform on fine levels: a short window keeps the Dz0 reads / Dz stores local
 static int sell_sigma_apply() { return std::min(sell_sigma(), 256); }
-// Hessian stores: 1 = stage a window's results in shared memory and store them in CSR order (coalesced),
-// 0 = every slot stores its own result (scattered inside the window); MGB_HESS_STAGE overrides
-static bool hess_staged(int sigma) {
-    const char* e = std::getenv("MGB_HESS_STAGE");
-    const bool want = e ? std::atoi(e) != 0 : true;
-    return want && sigma % 32 == 0 && sigma >= 256 && sigma <= 8192;
+static int sell_sigma_grad() {
+    const char* e = std::getenv("MGB_SELL_SIGMA_GRAD");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 ? v : 1024;
+}
+// longest run one lane replays (MGB_SELL_CHUNK); longer lists are cut into chunks, see below
+static int sell_chunk() {
+    const char* e = std::getenv("MGB_SELL_CHUNK");
+    const int v = e ? std::atoi(e) : 0;
+    return v >= 1 ? v : 16;
 }
 
 // Sliced-ELL replay list (SELL-32-sigma).  Every output value (a Dz entry, a gradient entry, an upper-triangle
 // Hessian entry) owns a list of (coefficient, source index) contributions that is fixed per level.  Outputs are
-// grouped in slices of 32 = one warp; contribution r of lane l of slice s sits at (off[s] + r) * 32 + l, so every
-// warp load of coefficients / source ids is one contiguous, fully used run (the thread-per-list CSR walk touched
-// 32 different sectors per step and idled the warp on its longest list).  Inside every window of `sigma`
+// grouped in slices of 32 lanes = one warp; contribution r of lane l of slice s sits at (off[s] + r) * 32 + l, so
+// every warp load of coefficients / source ids is one contiguous, fully used run (the thread-per-list CSR walk
+// touched 32 different sectors per step and idled the warp on its longest list).  Inside every window of `sigma`
 // consecutive outputs the outputs are sorted by list length first (stable), which removes the padding and the
-// divergence; perm[slot] is the output a slot stands for (-1: padding slot).  Padding contributions carry
-// src = -1 and are skipped by a predicate - a 0 * Inf of a non-finite iterate must not leak into other entries.
-// The order of a list is unchanged, so results are bit-identical to the sequential replay.
+// divergence.  Padding contributions carry src = -1 and are skipped by a predicate - a 0 * Inf of a non-finite
+// iterate must not leak into other entries.
+//
+// Chunks.  A replay is a chain of dependent loads (source id -> value -> fma), and the kernel cannot end before its
+// longest chain does: on the fem3d mesh the mean Hessian list has 3.8 products, the longest 144 (a vertex shared by
+// eight elements), and that one lane set the kernel time (113 us at 36 % of the DRAM peak, ncu long-scoreboard
+// stalls).  Lists longer than `chunk` are therefore cut into runs of `chunk` contributions that different lanes
+// replay; each run drops its partial sum into `part`, and a small second kernel adds the partials of an output in
+// list order.  code[slot] says what a slot stands for: >= 0 the output itself, -1 padding, <= -2 partial slot
+// -(code + 2).  Lists that fit one chunk keep their order and value bit for bit; chunked lists are the fixed-order
+// sum of their runs (deterministic, differs by rounding only).
 struct SellHost {
     std::vector<uint32_t> off;   // nslices + 1, in units of 32 contributions
-    std::vector<int32_t> perm;   // nslices * 32
+    std::vector<int32_t> code;   // nslices * 32
     std::vector<int32_t> src;
     std::vector<double> coef;
+    std::vector<int32_t> comb_ptr, comb_out;   // chunked outputs: partial range, output id
 };
 
 template <class PtrT>
-static void build_sell(int64_t nent, const PtrT* ptr, const double* coef, const int32_t* src, int sigma, SellHost& out) {
-    const int64_t nsl = (nent + 31) / 32;
-    out.perm.assign((size_t)nsl * 32, -1);
-    std::vector<int32_t> win;
-    for (int64_t w0 = 0; w0 < nent; w0 += sigma) {
-        const int64_t w1 = std::min<int64_t>(nent, w0 + sigma);
+static void build_sell(int64_t nent, const PtrT* ptr, const double* coef, const int32_t* src, int sigma, int chunk, SellHost& out) {
+    // virtual entries: (first contribution, length, code)
+    std::vector<int64_t> vbeg;
+    std::vector<int32_t> vlen, vcode;
+    vbeg.reserve((size_t)nent); vlen.reserve((size_t)nent); vcode.reserve((size_t)nent);
+    out.comb_ptr.assign(1, 0);
+    int64_t npart = 0;
+    for (int64_t e = 0; e < nent; ++e) {
+        const int64_t b0 = (int64_t)ptr[e], len = (int64_t)ptr[e + 1] - b0;
+        if (len <= chunk) { vbeg.push_back(b0); vlen.push_back((int32_t)len); vcode.push_back((int32_t)e); continue; }
+        for (int64_t c0 = 0; c0 < len; c0 += chunk) {
+            vbeg.push_back(b0 + c0); vlen.push_back((int32_t)std::min<int64_t>(chunk, len - c0));
+            vcode.push_back((int32_t)(-2 - npart)); ++npart;
+            if (npart > INT32_MAX - 4) throw std::runtime_error("csr path: partial slots exceed int32");
+        }
+        out.comb_ptr.push_back((int32_t)npart);
+        out.comb_out.push_back((int32_t)e);
+    }
+    const int64_t nv = (int64_t)vbeg.size();
+    const int64_t nsl = (nv + 31) / 32;
+    std::vector<int32_t> order((size_t)nsl * 32, -1), win;
+    for (int64_t w0 = 0; w0 < nv; w0 += sigma) {
+        const int64_t w1 = std::min<int64_t>(nv, w0 + sigma);
         win.resize((size_t)(w1 - w0));
         for (int64_t j = w0; j < w1; ++j) win[(size_t)(j - w0)] = (int32_t)j;
-        if (sigma > 1)
-            std::stable_sort(win.begin(), win.end(), [&](int32_t a, int32_t b) { return ptr[a + 1] - ptr[a] > ptr[b + 1] - ptr[b]; });
-        for (int64_t j = w0; j < w1; ++j) out.perm[(size_t)j] = win[(size_t)(j - w0)];
+        if (sigma > 1) std::stable_sort(win.begin(), win.end(), [&](int32_t a, int32_t b) { return vlen[(size_t)a] > vlen[(size_t)b]; });
+        for (int64_t j = w0; j < w1; ++j) order[(size_t)j] = win[(size_t)(j - w0)];
     }
+    out.code.assign((size_t)nsl * 32, -1);
     out.off.assign((size_t)nsl + 1, 0);
     for (int64_t sl = 0; sl < nsl; ++sl) {
         int64_t len = 0;
         for (int l = 0; l < 32; ++l) {
-            const int32_t e = out.perm[(size_t)sl * 32 + l];
-            if (e >= 0) len = std::max<int64_t>(len, (int64_t)(ptr[e + 1] - ptr[e]));
+            const int32_t v = order[(size_t)sl * 32 + l];
+            if (v < 0) continue;
+            out.code[(size_t)sl * 32 + l] = vcode[(size_t)v];
+            len = std::max<int64_t>(len, vlen[(size_t)v]);
         }
         const int64_t nxt = (int64_t)out.off[(size_t)sl] + len;
         if (nxt > (int64_t)UINT32_MAX) throw std::runtime_error("csr path: replay list too long for 32-bit slice offsets");
@@ -84,10 +116,10 @@ static void build_sell(int64_t nent, const PtrT* ptr, const double* coef, const 
     out.src.assign(tot, -1);
     for (int64_t sl = 0; sl < nsl; ++sl)
         for (int l = 0; l < 32; ++l) {
-            const int32_t e = out.perm[(size_t)sl * 32 + l];
-            if (e < 0) continue;
+            const int32_t v = order[(size_t)sl * 32 + l];
+            if (v < 0) continue;
             size_t q = (size_t)out.off[(size_t)sl] * 32 + l;
-            for (int64_t r = (int64_t)ptr[e]; r < (int64_t)ptr[e + 1]; ++r, q += 32) { out.coef[q] = coef[r]; out.src[q] = src[r]; }
+            for (int64_t r = vbeg[(size_t)v]; r < vbeg[(size_t)v] + vlen[(size_t)v]; ++r, q += 32) { out.coef[q] = coef[r]; out.src[q] = src[r]; }
         }
 }
 
@@ -108,14 +140,15 @@ static int64_t sell_stored(int64_t nent, const PtrT* ptr, int sigma) {
 
 struct SellDev {
     const uint32_t* off = nullptr;
-    const int32_t* perm = nullptr;
+    const int32_t* code = nullptr;
     const int32_t* src = nullptr;
     const double* coef = nullptr;
     int64_t nslot = 0;   // slices * 32
+    const int32_t* comb_ptr = nullptr;   // chunked outputs (ncomb + 1)
+    const int32_t* comb_out = nullptr;
+    int64_t ncomb = 0;
+    double* part = nullptr;
 };
-
-__global__ void csr_hess_staged_kernel(const __grid_constant__ SellDev L, const int sigma, const int64_t nup, const int32_t* __restrict__ nat_t,
-                                       const int32_t* __restrict__ nat_m, const double* __restrict__ V, double* __restrict__ hval);
 
 struct CsrDev {
     int ND = 0, npair = 0;
@@ -128,12 +161,11 @@ struct CsrDev {
     SellDev E[8];              // apply_D: outputs = local rows of E_k = D_k R, sources = unknowns
     SellDev G;                 // gradient: outputs = unknowns, sources = gy entries (k * nloc + i)
     SellDev Hs;                // Hessian: outputs = upper-triangle entries, sources = V entries (pair * nloc + i)
-    const int32_t* up_t = nullptr;   // per slot: position of the entry in the CSR value array (-1: padding slot)
-    const int32_t* up_m = nullptr;   // per slot: position of the mirror entry (-1: diagonal / padding)
-    const int32_t* nat_t = nullptr;  // the same two maps per upper entry in CSR order (staged stores)
+    const int32_t* up_t = nullptr;   // per slot: position of the entry in the CSR value array (-1: padding slot,
+                                     // <= -2: partial slot of a chunked entry)
+    const int32_t* up_m = nullptr;   // per slot: position of the mirror entry (-1: diagonal / padding / partial)
+    const int32_t* nat_t = nullptr;  // the two positions per upper entry in CSR order (chunked entries)
     const int32_t* nat_m = nullptr;
-    int hess_sigma = 0;              // sorting window of Hs
-    bool staged = false;
     double* Dz = nullptr;    // nloc x ND
     double* gy = nullptr;    // nloc x ND
     double* V = nullptr;     // nloc x npair
@@ -159,10 +191,19 @@ static const T* csr_up(CsrDev& d, const std::vector<T>& h, cudaStream_t st, size
 static SellDev sell_upload(CsrDev& d, const SellHost& h, cudaStream_t st, size_t& bytes) {
     SellDev o;
     o.off = csr_up(d, h.off, st, bytes);
-    o.perm = csr_up(d, h.perm, st, bytes);
+    o.code = csr_up(d, h.code, st, bytes);
     o.src = csr_up(d, h.src, st, bytes);
     o.coef = csr_up(d, h.coef, st, bytes);
-    o.nslot = (int64_t)h.perm.size();
+    o.nslot = (int64_t)h.code.size();
+    o.comb_ptr = csr_up(d, h.comb_ptr, st, bytes);
+    o.comb_out = csr_up(d, h.comb_out, st, bytes);
+    o.ncomb = (int64_t)h.comb_out.size();
+    double* p = nullptr;
+    const size_t np = (size_t)std::max<int32_t>(h.comb_ptr.back(), 1);
+    if (cudaMalloc(&p, np * 8) != cudaSuccess) throw std::runtime_error("cudaMalloc failed (replay partials)");
+    d.owned.push_back(p);
+    bytes += np * 8;
+    o.part = p;
     return o;
 }
 
@@ -174,33 +215,30 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     for (int c = 0; c < cp.npair; ++c) { d.pair_a[c] = cp.pair_a[c]; d.pair_b[c] = cp.pair_b[c]; }
     for (int k = 0; k < cp.ND; ++k) {
         SellHost h;
-        build_sell(cp.nloc, cp.E[k].ptr.data(), cp.E[k].val.data(), cp.E[k].idx.data(), sell_sigma_apply(), h);
+        build_sell(cp.nloc, cp.E[k].ptr.data(), cp.E[k].val.data(), cp.E[k].idx.data(), sell_sigma_apply(), sell_chunk(), h);
         d.E[k] = sell_upload(d, h, st, bytes);
         d.pad_apply += (int64_t)h.coef.size();
     }
     {
         SellHost h;
-        build_sell(cp.m, cp.gt_ptr.data(), cp.gt_coef.data(), cp.gt_src.data(), sell_sigma(), h);
+        build_sell(cp.m, cp.gt_ptr.data(), cp.gt_coef.data(), cp.gt_src.data(), sell_sigma_grad(), sell_chunk(), h);
         d.G = sell_upload(d, h, st, bytes);
         d.pad_grad = (int64_t)h.coef.size();
     }
     {
         SellHost h;
-        d.hess_sigma = sell_sigma();
-        d.staged = hess_staged(d.hess_sigma);
-        build_sell(d.nup, cp.prod_ptr.data(), cp.prod_coef.data(), cp.prod_v.data(), d.hess_sigma, h);
+        build_sell(d.nup, cp.prod_ptr.data(), cp.prod_coef.data(), cp.prod_v.data(), sell_sigma(), sell_chunk(), h);
         d.Hs = sell_upload(d, h, st, bytes);
-        d.nat_t = csr_up(d, cp.up_t, st, bytes);
-        d.nat_m = csr_up(d, cp.up_m, st, bytes);
-        if (d.staged && d.hess_sigma * 8 > 48 * 1024 &&
-            cudaFuncSetAttribute(csr_hess_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, d.hess_sigma * 8) != cudaSuccess)
-            throw std::runtime_error("cudaFuncSetAttribute failed (csr_hess_staged_kernel)");
         d.pad_hess = (int64_t)h.coef.size();
-        std::vector<int32_t> t(h.perm.size(), -1), mm(h.perm.size(), -1);
-        for (size_t q = 0; q < h.perm.size(); ++q)
-            if (h.perm[q] >= 0) { t[q] = cp.up_t[(size_t)h.perm[q]]; mm[q] = cp.up_m[(size_t)h.perm[q]]; }
+        std::vector<int32_t> t(h.code.size(), -1), mm(h.code.size(), -1);
+        for (size_t q = 0; q < h.code.size(); ++q) {
+            if (h.code[q] >= 0) { t[q] = cp.up_t[(size_t)h.code[q]]; mm[q] = cp.up_m[(size_t)h.code[q]]; }
+            else t[q] = h.code[q];
+        }
         d.up_t = csr_up(d, t, st, bytes);
         d.up_m = csr_up(d, mm, st, bytes);
+        d.nat_t = csr_up(d, cp.up_t, st, bytes);
+        d.nat_m = csr_up(d, cp.up_m, st, bytes);
     }
     auto scratch = [&](size_t count) {
         double* p = nullptr;
@@ -217,7 +255,7 @@ static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, c
     return bytes;
 }
 
-// one slot's replay: sum of coef * x[src] over the slice's rows, in list order
+// one slot's replay: sum of coef * x[src] over the slice's rows, in list order.  
 __device__ __forceinline__ double sell_replay(const SellDev& L, const double* __restrict__ x, const int64_t slot) {
     const int64_t sl = slot >> 5;
     const uint32_t o0 = __ldg(&L.off[sl]), o1 = __ldg(&L.off[sl + 1]);
@@ -231,6 +269,14 @@ __device__ __forceinline__ double sell_replay(const SellDev& L, const double* __
     }
     return acc;
 }
+// partials of chunked output q, added in list order
+__device__ __forceinline__ double sell_combine(const SellDev& L, const int64_t q) {
+    const int32_t r0 = __ldg(&L.comb_ptr[q]), r1 = __ldg(&L.comb_ptr[q + 1]);
+    double acc = 0.0;
+#pragma unroll 4
+    for (int32_t r = r0; r < r1; ++r) acc += __ldcs(&L.part[r]);
+    return acc;
+}
 
 struct CsrApplyParams {
     SellDev E[8];
@@ -241,15 +287,24 @@ struct CsrApplyParams {
     double* Dz;
 };
 
-// apply_D: blockIdx.y = operator, one slot per local row (rows sorted by length inside windows of sigma)
+// apply_D: blockIdx.y = operator, one slot per local row or chunk of a row
 __global__ void __launch_bounds__(256) csr_apply_kernel(const __grid_constant__ CsrApplyParams P) {
     const int k = blockIdx.y;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= P.E[k].nslot) return;
     const double dot = sell_replay(P.E[k], P.s, slot);
-    const int32_t i = __ldg(&P.E[k].perm[slot]);
-    if (i < 0) return;
-    const int64_t o = (int64_t)k * P.n + i;
+    const int32_t i = __ldg(&P.E[k].code[slot]);
+    if (i >= 0) {
+        const int64_t o = (int64_t)k * P.n + i;
+        P.Dz[o] = P.Dz0 ? P.Dz0[o] + dot : dot;
+    } else if (i <= -2) P.E[k].part[-(i + 2)] = dot;
+}
+__global__ void __launch_bounds__(256) csr_apply_combine_kernel(const __grid_constant__ CsrApplyParams P) {
+    const int k = blockIdx.y;
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= P.E[k].ncomb) return;
+    const double dot = sell_combine(P.E[k], q);
+    const int64_t o = (int64_t)k * P.n + __ldg(&P.E[k].comb_out[q]);
     P.Dz[o] = P.Dz0 ? P.Dz0[o] + dot : dot;
 }
 
@@ -298,6 +353,7 @@ __device__ __forceinline__ double cone_grad_pick(const BarrierOut& bo, const dou
 
 // map_rows of F / F1 / F2 over the Dz rows for one or two cones: everything of a point stays in registers, every
 // output column (w.*F1: ND columns, w.*F2: one column per coupled operator pair) is stored exactly once.
+template <int NCONES>
 __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant__ CsrBarrierParams P) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < P.n;
@@ -309,13 +365,12 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant_
         double cd = 0.0;
         for (int k = 0; k < ND; ++k) cd = fma(P.c[(int64_t)k * n + i], P.Dz[(int64_t)k * n + i], cd);
         v1 = wi * cd;
-        BarrierOut bo[2];
+        BarrierOut bo[NCONES];
         double itau = 0.0, tt = 0.0, Fsum = 0.0;
         bool feas = true;
-        const int ncones = (P.nq2 >= 0) ? 2 : 1;
+        constexpr int ncones = NCONES;
 #pragma unroll
-        for (int cone = 0; cone < 2; ++cone) {
-            if (cone >= ncones) break;
+        for (int cone = 0; cone < NCONES; ++cone) {
             const int nq = cone ? P.nq2 : P.nq;
             const int* idx = cone ? P.idx2 : P.idx;
             const double pp = cone ? P.p2 : P.p;
@@ -340,7 +395,7 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant_
         if (P.want_g) {
             for (int k = 0; k < ND; ++k) {
                 double g = cone_grad_pick(bo[0], itau, P.loc[0][k]);
-                if (ncones == 2) g += cone_grad_pick(bo[1], 0.0, P.loc[1][k]);
+                if (NCONES == 2) g += cone_grad_pick(bo[NCONES - 1], 0.0, P.loc[1][k]);
                 P.gy[(int64_t)k * n + i] = wi * (g + P.t * P.c[(int64_t)k * n + i]);
             }
         }
@@ -349,7 +404,7 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant_
                 const int ka = P.pair_a[cidx], kb = P.pair_b[cidx];
                 double h = 0.0;
                 if (P.loc[0][ka] >= 0 && P.loc[0][kb] >= 0) h = cone_hess_pick(bo[0], tt, P.loc[0][ka], P.loc[0][kb]);
-                if (ncones == 2 && P.loc[1][ka] >= 0 && P.loc[1][kb] >= 0) h += cone_hess_pick(bo[1], 0.0, P.loc[1][ka], P.loc[1][kb]);
+                if (NCONES == 2 && P.loc[1][ka] >= 0 && P.loc[1][kb] >= 0) h += cone_hess_pick(bo[NCONES - 1], 0.0, P.loc[1][ka], P.loc[1][kb]);
                 P.V[(int64_t)cidx * n + i] = wi * h;
             }
         }
@@ -382,13 +437,19 @@ __global__ void __launch_bounds__(256) csr_grad_kernel(const __grid_constant__ S
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= L.nslot) return;
     const double acc = sell_replay(L, gy, slot);
-    const int32_t a = __ldg(&L.perm[slot]);
+    const int32_t a = __ldg(&L.code[slot]);
     if (a >= 0) grad[a] = acc;
+    else if (a <= -2) L.part[-(a + 2)] = acc;
+}
+__global__ void __launch_bounds__(256) csr_grad_combine_kernel(const __grid_constant__ SellDev L, double* __restrict__ grad) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= L.ncomb) return;
+    grad[__ldg(&L.comb_out[q])] = sell_combine(L, q);
 }
 
-// numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry; it sums its
-// precomputed products coef * V in list order (no atomics, bit-reproducible) and stores the value at (a,b) and
-// at the mirror (b,a) - R'HR is symmetric, so half of the product lists never has to be read.
+// numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry (or chunk of one); it
+// sums its precomputed products coef * V in list order (no atomics, bit-reproducible) and stores the value at (a,b)
+// and at the mirror (b,a) - R'HR is symmetric, so half of the product lists never has to be read.
 // coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
 __global__ void __launch_bounds__(256) csr_hess_kernel(const __grid_constant__ SellDev L, const int32_t* __restrict__ up_t,
                                                        const int32_t* __restrict__ up_m, const double* __restrict__ V,
@@ -397,36 +458,20 @@ __global__ void __launch_bounds__(256) csr_hess_kernel(const __grid_constant__ S
     if (slot >= L.nslot) return;
     const int32_t t = __ldg(&up_t[slot]), tm = __ldg(&up_m[slot]);
     const double acc = sell_replay(L, V, slot);
-    if (t >= 0) hval[t] = acc;
-    if (tm >= 0) hval[tm] = acc;
+    if (t >= 0) {
+        hval[t] = acc;
+        if (tm >= 0) hval[tm] = acc;
+    } else if (t <= -2) L.part[-(t + 2)] = acc;
 }
-
-// the same replay with coalesced stores: one CTA per sorting window of `sigma` upper entries.  Warps take the
-// window's slices round-robin (slices are sorted by length, so the warps stay balanced), every slot drops its sum
-// into shared memory at the entry's position inside the window, and after one barrier the CTA stores the window
-// in CSR order (the upper entries of a window are nearly contiguous in the value array; only the mirror stores
-// scatter).
-__global__ void __launch_bounds__(256) csr_hess_staged_kernel(const __grid_constant__ SellDev L, const int sigma, const int64_t nup,
-                                                              const int32_t* __restrict__ nat_t, const int32_t* __restrict__ nat_m,
-                                                              const double* __restrict__ V, double* __restrict__ hval) {
-    extern __shared__ double win[];
-    const int64_t w0 = (int64_t)blockIdx.x * sigma;
-    const int cnt = (int)min((int64_t)sigma, nup - w0);
-    const int nsl = (cnt + 31) >> 5;
-    const int lane = threadIdx.x & 31;
-    for (int sl = threadIdx.x >> 5; sl < nsl; sl += 8) {
-        const int64_t slot = w0 + (int64_t)sl * 32 + lane;
-        const double acc = sell_replay(L, V, slot);
-        const int32_t e = __ldg(&L.perm[slot]);
-        if (e >= 0) win[e - w0] = acc;
-    }
-    __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += 256) {
-        const double v = win[j];
-        hval[__ldg(&nat_t[w0 + j])] = v;
-        const int32_t tm = __ldg(&nat_m[w0 + j]);
-        if (tm >= 0) hval[tm] = v;
-    }
+__global__ void __launch_bounds__(256) csr_hess_combine_kernel(const __grid_constant__ SellDev L, const int32_t* __restrict__ nat_t,
+                                                               const int32_t* __restrict__ nat_m, double* __restrict__ hval) {
+    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= L.ncomb) return;
+    const int32_t e = __ldg(&L.comb_out[q]);
+    const int32_t t = __ldg(&nat_t[e]), tm = __ldg(&nat_m[e]);
+    const double acc = sell_combine(L, q);
+    hval[t] = acc;
+    if (tm >= 0) hval[tm] = acc;
 }
 
 static __global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
@@ -460,6 +505,8 @@ static void csr_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+static unsigned sell_grid(int64_t count) { return (unsigned)((count + 255) / 256); }
+
 // returns the number of kernels launched
 static int csr_assemble(CsrDev& d, const double* w, const double* s, const double* Dz0, const double* c, double t,
                         int flags, double* scal, double* grad, double* hval, double* Dz_out, cudaStream_t st) {
@@ -470,11 +517,15 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
     if ((flags & 4) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
     {
         CsrApplyParams P{};
-        int64_t nslot = 0;
-        for (int k = 0; k < d.ND; ++k) { P.E[k] = d.E[k]; nslot = std::max(nslot, d.E[k].nslot); }
+        int64_t nslot = 0, ncomb = 0;
+        for (int k = 0; k < d.ND; ++k) { P.E[k] = d.E[k]; nslot = std::max(nslot, d.E[k].nslot); ncomb = std::max(ncomb, d.E[k].ncomb); }
         P.ND = d.ND; P.n = n; P.s = s; P.Dz0 = Dz0; P.Dz = Dz;
         if (nslot > 0) {
-            csr_apply_kernel<<<dim3((unsigned)((nslot + 255) / 256), (unsigned)d.ND), 256, 0, st>>>(P);
+            csr_apply_kernel<<<dim3(sell_grid(nslot), (unsigned)d.ND), 256, 0, st>>>(P);
+            ++launches;
+        }
+        if (ncomb > 0) {
+            csr_apply_combine_kernel<<<dim3(sell_grid(ncomb), (unsigned)d.ND), 256, 0, st>>>(P);
             ++launches;
         }
     }
@@ -497,19 +548,24 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         }
         P.n = n; P.p = d.bar.p; P.t = t; P.Dz = Dz; P.c = c; P.w = w; P.gy = d.gy; P.V = d.V; P.part = d.part;
         P.want_f = (flags & 1) ? 1 : 0; P.want_g = (flags & 2) ? 1 : 0; P.want_h = (flags & 4) ? 1 : 0;
-        csr_barrier_kernel<<<(unsigned)d.nblk, 256, 0, st>>>(P);
+        if (P.nq2 >= 0) csr_barrier_kernel<2><<<(unsigned)d.nblk, 256, 0, st>>>(P);
+        else csr_barrier_kernel<1><<<(unsigned)d.nblk, 256, 0, st>>>(P);
         ++launches;
     }
     if ((flags & 2) && d.G.nslot > 0) {
-        csr_grad_kernel<<<(unsigned)((d.G.nslot + 255) / 256), 256, 0, st>>>(d.G, d.gy, grad);
+        csr_grad_kernel<<<sell_grid(d.G.nslot), 256, 0, st>>>(d.G, d.gy, grad);
+        if (d.G.ncomb > 0) {
+            csr_grad_combine_kernel<<<sell_grid(d.G.ncomb), 256, 0, st>>>(d.G, grad);
+            ++launches;
+        }
         ++launches;
     }
     if ((flags & 4) && d.nup > 0) {
-        if (d.staged)
-            csr_hess_staged_kernel<<<(unsigned)((d.nup + d.hess_sigma - 1) / d.hess_sigma), 256, (size_t)d.hess_sigma * 8, st>>>(
-                d.Hs, d.hess_sigma, d.nup, d.nat_t, d.nat_m, d.V, hval);
-        else
-            csr_hess_kernel<<<(unsigned)((d.Hs.nslot + 255) / 256), 256, 0, st>>>(d.Hs, d.up_t, d.up_m, d.V, hval);
+        csr_hess_kernel<<<sell_grid(d.Hs.nslot), 256, 0, st>>>(d.Hs, d.up_t, d.up_m, d.V, hval);
+        if (d.Hs.ncomb > 0) {
+            csr_hess_combine_kernel<<<sell_grid(d.Hs.ncomb), 256, 0, st>>>(d.Hs, d.nat_t, d.nat_m, hval);
+            ++launches;
+        }
         ++launches;
     }
     scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);
