@@ -12,9 +12,9 @@ apply_D -> barrier F/F1/F2 -> gradient -> Hessian numeric phase -> R'HR values (
             no julia/mpiexec in the image) timed on the host cores.
 
 N > 1 (torchrun): quadrature rows (whole elements) are sharded across ranks, every rank assembles
-the contributions of its own rows, then the interface rows travel to their owners (one NCCL
-all-to-all per output + a 4-double all-reduce, all inside the timed region); the fixed L=8 problem is
-split, so scaling = "strong".
+the contributions of its own rows and stores them straight into the owner's exchange window over NVLink
+peer memory (push_kernel + epoch flags, all inside the timed region; `--exchange nccl` selects the
+pack -> all_to_all -> owner-side sum path instead); the fixed L=8 problem is split, so scaling = "strong".
 """
 from __future__ import annotations
 
@@ -343,6 +343,9 @@ def main():
     # per-kernel split (separate pass, not part of `value`)
     _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
                                                max(10, args.steps // 2), flush, split=True)
+    # line-search point: objective only (reported as a separate line, ms per f0)
+    ms_f0, _, _ = plan.time_assemble(s_d, Dz0_d, c_d, args.t, capi.WANT_F0, scal_d, grad_d, hval_d,
+                                     max(10, args.steps // 2), flush, split=False) if world == 1 else (None, 0, 0)
     # ---- e2e through host buffers (pinned): H2D of the Newton unknown, D2H of gradient + Hessian values
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
     s_h = pin(pr["s"])
@@ -449,7 +452,7 @@ def main():
                          "frac": ach / peak, "traffic": ncu_traffic("element_kernel", args.L), "peak_source": peak_src,
                          "algorithmic_bytes": int(alg_elem), "kernel_ms": ms_elem,
                          "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all,
-                                      "frac": ach_all / peak, "gather_ms": ms_gather}},
+                                      "frac": ach_all / peak, "gather_ms": ms_gather, "f0_ms": ms_f0}},
             "wall_s_timed_region": wall,
         }
         if world == 1 and args.cpu_reps > 0:

@@ -107,3 +107,17 @@ def test_plans_from_hpc_local_blocks_sum_to_the_oracle(gpu_ctx, gen, L, nranks):
     assert abs(f0 - f0_o) <= 1e-12 * max(1.0, abs(f0_o))
     assert rel(g, g_o) <= 1e-12
     assert abs(H - H_o).max() <= 1e-12 * abs(H_o).max()
+
+
+@pytest.mark.parametrize("chunk,sigma", [("2", "64"), ("5", "1"), ("1000000", "16384")])
+def test_csr_replay_chunking_and_windows(gpu_ctx, chunk, sigma, monkeypatch):
+    """CSR path replay lists: chunk = 2 cuts nearly every list of apply_D, gradient and Hessian into runs whose
+    partial sums a second kernel adds (all three combine kernels run); chunk = 10^6 never cuts.  The sorting
+    window changes which lanes sit in a slice, never a value."""
+    monkeypatch.setenv("MGB_SELL_CHUNK", chunk)
+    monkeypatch.setenv("MGB_SELL_SIGMA", sigma)
+    monkeypatch.setenv("MGB_SELL_SIGMA_GRAD", sigma)
+    check_against_oracle(gpu_ctx, mgb_b200.fem3d(2), 1.0, t=0.9)
+    check_against_oracle(gpu_ctx, mgb_b200.fem2d(3), 1.5, t=0.9, level=1, force_path=capi.PATH_CSR)
+    check_against_oracle(gpu_ctx, mgb_b200.fem2d(2), 1.0, t=0.5, slack=True, force_path=capi.PATH_CSR)
+    check_against_oracle(gpu_ctx, mgb_b200.fem1d(5), 2.0, t=0.9, level=0, force_path=capi.PATH_CSR)
