@@ -126,7 +126,44 @@ def cpu_assembly_sample(pr, t, reps):
 _W = {}
 
 
+def available_cores() -> int:
+    """host cores this process may really use: the smallest of cpu_count, the affinity mask and the cgroup CPU quota
+    (a container can see 16 CPUs and be allowed 2: forking 16 ranks there measures the scheduler, not the code)"""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            quota, period = fh.read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(float(quota) / float(period))))
+    except Exception:
+        pass
+    try:  # cgroup v1
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us") as fh:
+            quota = int(fh.read())
+        with open("/sys/fs/cgroup/cpu/cpu.cfs_period_us") as fh:
+            period = int(fh.read())
+        if quota > 0 and period > 0:
+            n = min(n, max(1, quota // period))
+    except Exception:
+        pass
+    return max(1, n)
+
+
+def _single_thread():
+    """one thread per rank, like an MPI rank of the reference (BLAS threads via env, docs/src/guide.md:221-230)"""
+    try:
+        from threadpoolctl import threadpool_limits
+        _W["tp"] = threadpool_limits(limits=1)
+    except Exception:
+        pass
+
+
 def _worker_init(pr, t, blocks):
+    _single_thread()
     _W.update(pr=pr, t=t, blocks=blocks)
 
 
@@ -193,8 +230,12 @@ def run_reference(args, rank, world):
     restatement (oracle/mgb_oracle.py) is timed on the host cores, sharded by row blocks like MPI ranks."""
     if rank != 0:
         return
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ.setdefault(var, "1")
+    _single_thread()
     pr = build_problem(args.L, args.p)
-    cores = max(1, min(os.cpu_count() or 1, args.cpu_procs if args.cpu_procs > 0 else (os.cpu_count() or 1)))
+    avail = available_cores()
+    cores = max(1, min(avail, args.cpu_procs if args.cpu_procs > 0 else avail))
     steps = max(1, args.steps)
     if cores > 1:
         ms, ms_slowest = cpu_assembly_parallel(pr, args.t, steps, cores)
@@ -208,7 +249,8 @@ def run_reference(args, rank, world):
         "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly (n={pr['geom'].x.shape[0]})",
                    "note": "CPU restatement (oracle/mgb_oracle.py, scipy CSC), NOT the Julia reference: julia/mpiexec are "
                            "absent from this image; sharded over processes by row blocks like `mpiexec -n cores`",
-                   "one_core_ms": ms_1, "slowest_rank_compute_ms": ms_slowest},
+                   "one_core_ms": ms_1, "slowest_rank_compute_ms": ms_slowest,
+                   "host_cpus_visible": os.cpu_count(), "host_cpus_usable": avail},
         "cpu_baseline": {"value": ms, "unit": "ms", "cores": cores, "kind": "port",
                          "sample": f"{steps} full assemblies (f0+f1+f2) at L={args.L}"},
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
