@@ -50,8 +50,17 @@ class Backend:
         return torch.device("cuda", self.index) if self.device == "cuda" else torch.device("cpu")
 
 
-def backend_cuda(index: int = 0, rank: int = 0, nranks: int = 1) -> Backend:
-    return Backend(index=index, rank=rank, nranks=nranks)
+def backend_cuda(index: Optional[int] = None, rank: Optional[int] = None, nranks: Optional[int] = None) -> Backend:
+    """Without arguments: the running job's layout - under an initialised torch.distributed job (one process per
+    GPU, the reference's `mpiexec -n P` with one rank per GPU, test/test_2d.jl:17-20) the rank / world size of the
+    default group and this process's current CUDA device; otherwise one rank on device 0."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        rank = dist.get_rank() if rank is None else rank
+        nranks = dist.get_world_size() if nranks is None else nranks
+        if index is None:
+            index = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    return Backend(index=index or 0, rank=rank or 0, nranks=nranks or 1)
 
 
 class HPCVector:

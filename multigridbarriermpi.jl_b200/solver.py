@@ -31,52 +31,123 @@ NEWTON_NOISE = 1024.0
 
 
 def solve(H: sp.spmatrix, g: np.ndarray) -> np.ndarray:
-    """MultiGridBarrier.solve(A, b) = A \\ b.  Host sparse LU stands in for MUMPS (outside the graft)."""
-    return spla.splu(sp.csc_matrix(H)).solve(g)
+    """MultiGridBarrier.solve(A, b) = A \\ b.  Host sparse LU stands in for MUMPS (outside the graft).
+    The barrier Hessian is symmetric positive definite: minimum-degree ordering on A'+A with diagonal pivots
+    halves SuperLU's fill against the default COLAMD (fem2d L=6: 1.28 M vs 2.37 M factor entries)."""
+    A = sp.csc_matrix(H)
+    try:
+        return spla.splu(A, permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True)).solve(g)
+    except RuntimeError:   # exactly singular pivot without partial pivoting: fall back to the general ordering
+        return spla.splu(A).solve(g)
 
 
 class LevelState:
-    """Plan + preallocated device buffers of one multigrid level."""
+    """Plan + preallocated device buffers of one multigrid level.  ``assemble`` leaves the objective scalars in
+    ``scal``, the gradient in ``grad`` and the CSR values of R'HR in ``hval`` - complete on every rank."""
 
     def __init__(self, prob: "DeviceProblem", J: int):
-        self.plan = capi.Plan(prob.ctx, prob.M.D, prob.M.R_fine[J], prob.M.x, prob.M.w, prob.idx, prob.p,
-                              slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
+        M = prob.M
         dev = prob.device
-        m, nnz = self.plan.m, self.plan.nnzH
+        if prob.nranks > 1:
+            from . import dist as mdist
+            if prob.idx2:
+                raise NotImplementedError("two-cone plans are single-rank for now")
+            self.plan = mdist.create_peer_plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, prob.block,
+                                               prob.rank, prob.nranks, group=prob.group, slack=prob.slack)
+            # the replicated symbolic plan gives the global pattern the solve seam needs (owned row blocks are
+            # contiguous, so the global value array is the concatenation of the ranks' owned values)
+            sym = capi.Plan(None, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, slack=prob.slack)
+            rp, ci = sym.pattern()
+            m, nnz = sym.m, sym.nnzH
+            d = self.plan.dinfo
+            self.own_h = (int(rp[d["own0"]]), d["n_own_h"])
+            self.own_g = (d["own0"], d["n_own_g"])
+            assert self.own_h[0] + self.own_h[1] == int(rp[d["own1"]])
+            self._views = {}
+        else:
+            self.plan = capi.Plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p,
+                                  slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
+            m, nnz = self.plan.m, self.plan.nnzH
+            rp, ci = self.plan.pattern()
+        # no back-reference to `prob`: a reference cycle would hand destruction order (plans before their context)
+        # to the cyclic garbage collector
+        self.nranks, self.group, self.device = prob.nranks, prob.group, dev
+        self.m, self.nnzH = m, nnz
         f64 = torch.float64
         self.s = torch.zeros(m, dtype=f64, device=dev)
         self.trial = torch.zeros(m, dtype=f64, device=dev)
         self.step = torch.zeros(m, dtype=f64, device=dev)
-        self.grad = torch.zeros(m, dtype=f64, device=dev)
-        self.hval = torch.zeros(max(nnz, 1), dtype=f64, device=dev)
+        # one buffer [hval | grad]: on several ranks a single all-reduce completes both
+        self.hg = torch.zeros(max(nnz, 1) + m, dtype=f64, device=dev)
+        self.hval, self.grad = self.hg[: max(nnz, 1)], self.hg[max(nnz, 1):]
         self.scal = torch.zeros(4, dtype=f64, device=dev)
-        self.R = capi.SpMat(prob.ctx, prob.M.R_fine[J])
-        rp, ci = self.plan.pattern()
+        self.R = capi.SpMat(prob.ctx, M.R_fine[J])
         self.rowptr, self.colidx = rp.astype(np.int64), ci.astype(np.int64)
         # pinned host mirrors for the solve seam
         self.h_hval = torch.zeros(max(nnz, 1), dtype=f64).pin_memory()
         self.h_grad = torch.zeros(m, dtype=f64).pin_memory()
         self.h_step = torch.zeros(m, dtype=f64).pin_memory()
 
+    def assemble(self, s: torch.Tensor, Dz0: torch.Tensor, c: torch.Tensor, t: float, flags: int):
+        if self.nranks == 1:
+            self.plan.assemble(s, Dz0, c, t, flags, self.scal, self.grad, self.hval)
+            return
+        # sharded: every rank assembles its quadrature rows; the fused peer exchange leaves each rank with its
+        # own rows of R'HR / block of the gradient and the globally summed scalars (mgb_dist_assemble); the
+        # host solve below needs the whole system, so the owned blocks are then replicated (solve seam only).
+        import torch.distributed as dist
+        ptrs = self.plan.dist_assemble(s, Dz0, c, t, flags)
+        if ptrs not in self._views:
+            cnt = (max(self.own_h[1], 1), max(self.own_g[1], 1), 4)
+            self._views[ptrs] = tuple(torch.as_tensor(capi.DeviceView(p_, n_), device=self.device) for p_, n_ in zip(ptrs, cnt))
+        vh, vg, vs = self._views[ptrs]
+        self.scal.copy_(vs)
+        if flags & (capi.WANT_GRAD | capi.WANT_HESS):
+            self.hg.zero_()
+            if flags & capi.WANT_HESS:
+                self.hval[self.own_h[0]: self.own_h[0] + self.own_h[1]] = vh[: self.own_h[1]]
+            if flags & capi.WANT_GRAD:
+                self.grad[self.own_g[0]: self.own_g[0] + self.own_g[1]] = vg[: self.own_g[1]]
+            dist.all_reduce(self.hg, group=self.group)   # every entry has exactly one non-zero contributor: exact
+
+    def close(self):
+        if self.nranks > 1:
+            from . import dist as mdist
+            self._views.clear()
+            mdist.destroy_peer_plan(self.plan, group=self.group)
+        else:
+            self.plan.close()
+
 
 class DeviceProblem:
-    """One AMG hierarchy resident on one GPU."""
+    """One AMG hierarchy resident on one GPU - or, with ``nranks > 1`` (one process per GPU, torch.distributed
+    initialised), this rank's shard of it: quadrature rows split on element boundaries as HPCSparseArrays
+    splits them (hpc.uniform_partition), the unknown ``z`` replicated, every level plan a DistPlan."""
 
     def __init__(self, M: AMG, idx: Sequence[int], p: float, slack: bool = False, device: int = 0,
-                 ctx: Optional[capi.Context] = None, idx2: Optional[Sequence[int]] = None, p2: float = 2.0):
+                 ctx: Optional[capi.Context] = None, idx2: Optional[Sequence[int]] = None, p2: float = 2.0,
+                 rank: int = 0, nranks: int = 1, block: int = 1, group=None):
         self.M, self.idx, self.p, self.slack = M, list(idx), float(p), bool(slack)
         self.idx2, self.p2 = (list(idx2) if idx2 else None), float(p2)
+        self.rank, self.nranks, self.block, self.group = int(rank), int(nranks), int(block), group
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.current_stream(self.device)
         self.ctx = ctx or capi.Context(device, self.stream.cuda_stream)
         self.n = M.x.shape[0]
         self.N = M.nu * self.n
+        if self.nranks > 1:
+            from . import dist as mdist
+            self.rows = mdist.element_rows(self.n, self.block, self.rank, self.nranks)
+        else:
+            self.rows = (0, self.n)
+        self.nloc = self.rows[1] - self.rows[0]
         self.levels: Dict[int, LevelState] = {}
-        # operator-only plan with R = I: Dz0 = D z for any fine-space z
+        # operator-only plan with R = I: Dz0 = D z for any fine-space z (this rank's rows)
         self.op_plan = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
-                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2)
-        self.Dz0 = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)  # column-major n x nD
+                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2,
+                                 rows=self.rows)
+        self.Dz0 = torch.zeros((M.nD, self.nloc), dtype=torch.float64, device=self.device)  # column-major nloc x nD
         self.stats = dict(assemblies=0, f0_evals=0, solve_s=0.0, assemble_s=0.0)
 
     def level(self, J: int) -> LevelState:
@@ -89,17 +160,28 @@ class DeviceProblem:
         self.op_plan.apply_D(z_dev, None, out)
         return out
 
+    def local_rows(self, a: torch.Tensor) -> torch.Tensor:
+        """this rank's quadrature rows of a column-major (k, n) device block"""
+        if self.nranks == 1:
+            return a
+        return a[:, self.rows[0]: self.rows[1]].contiguous()
+
+    def close(self):
+        """collective on several ranks: nobody unmaps an exchange window a peer may still store into"""
+        for J in sorted(self.levels):
+            self.levels[J].close()
+        self.levels.clear()
+
 
 def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor, t: float, maxit: int,
                   alpha: float = 0.1, beta: float = 0.25, solve_fn: Callable = solve):
     """Damped Newton on level J for s -> f(z + R_J s); same decisions as the oracle's ``newton``."""
     lv = prob.level(J)
-    plan = lv.plan
     Dz0 = prob.apply_D(z)
     lv.s.zero_()
     F0, FG, FH = capi.WANT_F0, capi.WANT_GRAD, capi.WANT_HESS
     t0 = time.perf_counter()
-    plan.assemble(lv.s, Dz0, c, t, F0 | FG | FH, lv.scal, lv.grad, lv.hval)
+    lv.assemble(lv.s, Dz0, c, t, F0 | FG | FH)
     sc = lv.scal.cpu()
     prob.stats["assemblies"] += 1
     y = float(sc[0])
@@ -112,7 +194,7 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
         torch.cuda.current_stream().synchronize()
         prob.stats["assemble_s"] += time.perf_counter() - t0
         ts = time.perf_counter()
-        H = sp.csr_matrix((lv.h_hval.numpy()[: plan.nnzH], lv.colidx, lv.rowptr), shape=(plan.m, plan.m))
+        H = sp.csr_matrix((lv.h_hval.numpy()[: lv.nnzH], lv.colidx, lv.rowptr), shape=(lv.m, lv.m))
         g = lv.h_grad.numpy()
         nstep = solve_fn(H, g)
         inc = float(np.dot(g, nstep))
@@ -127,7 +209,7 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
         sstep, ok = 1.0, False
         while sstep > 1e-12:
             torch.add(lv.s, lv.step, alpha=-sstep, out=lv.trial)
-            plan.assemble(lv.trial, Dz0, c, t, F0, lv.scal)
+            lv.assemble(lv.trial, Dz0, c, t, F0)
             sc = lv.scal.cpu()
             prob.stats["f0_evals"] += 1
             yn = float(sc[0])
@@ -141,7 +223,7 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
             break
         lv.s.copy_(lv.trial)
         y = yn
-        plan.assemble(lv.s, Dz0, c, t, FG | FH, lv.scal, lv.grad, lv.hval)
+        lv.assemble(lv.s, Dz0, c, t, FG | FH)
         prob.stats["assemblies"] += 1
     prob.stats["assemble_s"] += time.perf_counter() - t0
     # z <- z + R s
@@ -176,7 +258,6 @@ def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, ka
     ts, its, cdots = [], [], []
     t_begin = time.time()
     kk = 0
-    scal = torch.zeros(4, dtype=torch.float64, device=prob.device)
     while t <= 1.0 / tol:
         kk += 1
         ts.append(t)
@@ -198,8 +279,8 @@ def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, ka
         # <c, Dz>_w through the objective kernel on the finest plan (s = 0)
         lv = prob.level(L - 1)
         lv.s.zero_()
-        lv.plan.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0, scal)
-        cdots.append(float(scal.cpu()[2]))
+        lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
+        cdots.append(float(lv.scal.cpu()[2]))
         if verbose:
             print(f"t={t:.3e} its={row} c.Dz={cdots[-1]:.12e}", file=logfile)
         t *= kappa
@@ -229,20 +310,35 @@ def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float =
     cmat = np.array([f(geom.x[i]) for i in range(n)], dtype=float)
     if max_newton is None:
         max_newton = int(math.ceil(math.log2(1.0 / tol) + 2))
-    prob = DeviceProblem(M, idx, p, slack=False, device=device)
+    rank, nranks, group = _dist_layout()
+    prob = DeviceProblem(M, idx, p, slack=False, device=device, rank=rank, nranks=nranks, block=geom.block, group=group)
     z = torch.from_numpy(z0.reshape(-1, order="F").copy()).to(prob.device)
-    c = _cm(cmat, prob.device)
+    c = prob.local_rows(_cm(cmat, prob.device))
     # strict feasibility of the start (upstream skips the feasibility phase when it holds)
     lv = prob.level(len(M.R_fine) - 1)
     Dz0 = prob.apply_D(z)
     lv.s.zero_()
-    lv.plan.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0, lv.scal)
+    lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
     sol_feas = None
     if float(lv.scal.cpu()[1]) != 1.0:
+        if nranks > 1:
+            raise NotImplementedError("the feasibility phase runs on one rank only for now")
         z, sol_feas = feasibility_phase(geom, prob, z, cmat, state_variables, D, tol, t, kappa, maxit, solve_fn, device)
     sol_main = amgb_core(prob, z, c, tol, t, kappa, maxit, max_newton, verbose, solve_fn, logfile)
     zz = z.cpu().numpy().reshape(n, M.nu, order="F")
-    return AMGBSOL(zz, sol_feas, sol_main, "", geom, dict(prob.stats))
+    stats = dict(prob.stats, nranks=nranks)
+    if nranks > 1:
+        prob.close()
+    return AMGBSOL(zz, sol_feas, sol_main, "", geom, stats)
+
+
+def _dist_layout():
+    """(rank, nranks, group) of the running job: one process per GPU when torch.distributed is initialised with
+    more than one rank (the reference's `mpiexec -n P`, one rank per GPU: test/test_2d.jl:17-20), else (0, 1, None)"""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        return dist.get_rank(), dist.get_world_size(), None
+    return 0, 1, None
 
 
 SLACK_COST = 10.0

@@ -169,3 +169,15 @@ def test_two_gpu_peer_exchange_matches_oracle():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     assert "PEER_OK" in res.stdout
+
+
+def test_two_gpu_sharded_solve_matches_oracle():
+    """configs[0] of BASELINE.json: fem2d_mpi_solve(L=3, p=1.0) on 2 ranks, one GPU each (+ a 1-D and a p=1.5 case)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29643", os.path.join(ROOT, "tests", "dist_solve_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "SOLVE_OK" in res.stdout

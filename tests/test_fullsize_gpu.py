@@ -1,4 +1,4 @@
-"""Full-size checks at BASELINE.json's sizes (fem2d L=8: n=229,376; fem1d L=16: n=131,072), where the oracle is
+"""Full-size checks at BASELINE.json's sizes (fem2d L=8: n=229,376; fem1d L=16: n=131,072; fem3d L=5: n=262,144), where the oracle is
 too slow to run inside the suite: size-independent properties of the assembled objects.
 
   * R'HR is symmetric on its (symmetric) frozen pattern;
@@ -19,13 +19,13 @@ def _setup(gpu_ctx, gen, L, p=1.0):
     from mgb_b200 import capi
     from helpers import problem
     geom = getattr(mgb_b200, gen)(L)
-    pr = problem(geom, p=p, pert=1e-3 if gen == "fem2d" else 1e-8)
+    pr = problem(geom, p=p, pert=1e-8 if gen == "fem1d" else 1e-3)
     plan = capi.Plan(gpu_ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], p)
     Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
     return geom, pr, plan, Dz0
 
 
-@pytest.mark.parametrize("gen,L", [("fem2d", 8), ("fem1d", 16)])
+@pytest.mark.parametrize("gen,L", [("fem2d", 8), ("fem1d", 16), ("fem3d", 5)])
 def test_derivative_identities_at_full_size(gpu_ctx, gen, L):
     from mgb_b200 import capi
     geom, pr, plan, Dz0 = _setup(gpu_ctx, gen, L)
@@ -41,7 +41,7 @@ def test_derivative_identities_at_full_size(gpu_ctx, gen, L):
     # derivative below the rounding noise of the objective)
     g = out["grad"]
     v = g / np.linalg.norm(g)
-    eps = 1e-4 if gen == "fem2d" else 1e-8   # the 1-D feasible set is thin at L=16 (element size 2^-16)
+    eps = 1e-8 if gen == "fem1d" else 1e-4   # the 1-D feasible set is thin at L=16 (element size 2^-16)
     op = plan.assemble_host(s + eps * v, None, None, t, 1, upload_inputs=False)
     om = plan.assemble_host(s - eps * v, None, None, t, 1, upload_inputs=False)
     assert op["scal"][1] == 1.0 and om["scal"][1] == 1.0
@@ -51,7 +51,7 @@ def test_derivative_identities_at_full_size(gpu_ctx, gen, L):
     rng = np.random.default_rng(3)
     v = rng.standard_normal(plan.m)
     v /= np.linalg.norm(v)
-    eps = 1e-6 if gen == "fem2d" else 1e-9
+    eps = 1e-9 if gen == "fem1d" else 1e-6
     op = plan.assemble_host(s + eps * v, None, None, t, 3, upload_inputs=False)
     om = plan.assemble_host(s - eps * v, None, None, t, 3, upload_inputs=False)
     hv_fd = (op["grad"] - om["grad"]) / (2 * eps)
@@ -97,10 +97,12 @@ def test_sharded_equals_single_at_full_size(gpu_ctx):
         p.close()
 
 
-def test_nonfinite_and_infeasible_iterates_are_data(gpu_ctx):
-    """amgb_all_isfinite semantics (reference src/MultiGridBarrierMPI.jl:121-133): rc = 0, all_finite = 0"""
+@pytest.mark.parametrize("gen,L", [("fem2d", 3), ("fem3d", 2)])
+def test_nonfinite_and_infeasible_iterates_are_data(gpu_ctx, gen, L):
+    """amgb_all_isfinite semantics (reference src/MultiGridBarrierMPI.jl:121-133): rc = 0, all_finite = 0
+    (element path and CSR path)"""
     from mgb_b200 import capi
-    geom, pr, plan, Dz0 = _setup(gpu_ctx, "fem2d", 3)
+    geom, pr, plan, Dz0 = _setup(gpu_ctx, gen, L)
     s = pr["s"].copy()
     s[7] = np.nan
     out = plan.assemble_host(s, Dz0, pr["c"], 1.0, 7)
