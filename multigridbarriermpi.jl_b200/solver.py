@@ -48,12 +48,23 @@ class LevelState:
     def __init__(self, prob: "DeviceProblem", J: int):
         M = prob.M
         dev = prob.device
+        self.sharded = False
         if prob.nranks > 1:
             from . import dist as mdist
             if prob.idx2:
                 raise NotImplementedError("two-cone plans are single-rank for now")
-            self.plan = mdist.create_peer_plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, prob.block,
-                                               prob.rank, prob.nranks, group=prob.group, slack=prob.slack)
+            try:
+                self.plan = mdist.create_peer_plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, prob.block,
+                                                   prob.rank, prob.nranks, group=prob.group, slack=prob.slack)
+                self.sharded = True
+            except capi.MgbError as exc:
+                # the fused peer exchange covers the levels whose gather runs thread-per-entry (the fine ones, where
+                # the work is); a coarse level is assembled redundantly by every rank instead - same inputs, same
+                # kernels, hence bit-identical results on all ranks and no communication.  Every rank takes this
+                # branch together: the refusal depends on the (replicated) operators only.
+                if "peer exchange is implemented" not in str(exc):
+                    raise
+        if self.sharded:
             # the replicated symbolic plan gives the global pattern the solve seam needs (owned row blocks are
             # contiguous, so the global value array is the concatenation of the ranks' owned values)
             sym = capi.Plan(None, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, slack=prob.slack)
@@ -89,7 +100,7 @@ class LevelState:
         self.h_step = torch.zeros(m, dtype=f64).pin_memory()
 
     def assemble(self, s: torch.Tensor, Dz0: torch.Tensor, c: torch.Tensor, t: float, flags: int):
-        if self.nranks == 1:
+        if not self.sharded:
             self.plan.assemble(s, Dz0, c, t, flags, self.scal, self.grad, self.hval)
             return
         # sharded: every rank assembles its quadrature rows; the fused peer exchange leaves each rank with its
@@ -111,7 +122,7 @@ class LevelState:
             dist.all_reduce(self.hg, group=self.group)   # every entry has exactly one non-zero contributor: exact
 
     def close(self):
-        if self.nranks > 1:
+        if self.sharded:
             from . import dist as mdist
             self._views.clear()
             mdist.destroy_peer_plan(self.plan, group=self.group)
@@ -148,6 +159,8 @@ class DeviceProblem:
                                  slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2,
                                  rows=self.rows)
         self.Dz0 = torch.zeros((M.nD, self.nloc), dtype=torch.float64, device=self.device)  # column-major nloc x nD
+        self.op_plan_full, self.Dz0_full = self.op_plan, self.Dz0     # all rows: levels assembled redundantly
+        self._loc_cache = {}
         self.stats = dict(assemblies=0, f0_evals=0, solve_s=0.0, assemble_s=0.0)
 
     def level(self, J: int) -> LevelState:
@@ -155,16 +168,30 @@ class DeviceProblem:
             self.levels[J] = LevelState(self, J)
         return self.levels[J]
 
-    def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None, full: bool = False) -> torch.Tensor:
+        """Dz0 = D z on this rank's quadrature rows (``full``: on all rows)"""
+        if full and self.nranks > 1:
+            if self.op_plan_full is self.op_plan:
+                M = self.M
+                self.op_plan_full = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
+                                              slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2)
+                self.Dz0_full = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)
+            out = self.Dz0_full if out is None else out
+            self.op_plan_full.apply_D(z_dev, None, out)
+            return out
         out = self.Dz0 if out is None else out
         self.op_plan.apply_D(z_dev, None, out)
         return out
 
     def local_rows(self, a: torch.Tensor) -> torch.Tensor:
-        """this rank's quadrature rows of a column-major (k, n) device block"""
+        """this rank's quadrature rows of a column-major (k, n) device block (cached per block)"""
         if self.nranks == 1:
             return a
-        return a[:, self.rows[0]: self.rows[1]].contiguous()
+        hit = self._loc_cache.get(id(a))
+        if hit is None or hit[0] is not a:
+            hit = (a, a[:, self.rows[0]: self.rows[1]].contiguous())
+            self._loc_cache[id(a)] = hit
+        return hit[1]
 
     def close(self):
         """collective on several ranks: nobody unmaps an exchange window a peer may still store into"""
@@ -177,7 +204,9 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
                   alpha: float = 0.1, beta: float = 0.25, solve_fn: Callable = solve):
     """Damped Newton on level J for s -> f(z + R_J s); same decisions as the oracle's ``newton``."""
     lv = prob.level(J)
-    Dz0 = prob.apply_D(z)
+    Dz0 = prob.apply_D(z, full=not lv.sharded)
+    if lv.sharded:
+        c = prob.local_rows(c)
     lv.s.zero_()
     F0, FG, FH = capi.WANT_F0, capi.WANT_GRAD, capi.WANT_HESS
     t0 = time.perf_counter()
@@ -275,11 +304,11 @@ def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, ka
             for J in range(L):
                 ok = level(J, maxit)
         its.append(row)
-        Dz0 = prob.apply_D(z)
         # <c, Dz>_w through the objective kernel on the finest plan (s = 0)
         lv = prob.level(L - 1)
+        Dz0 = prob.apply_D(z, full=not lv.sharded)
         lv.s.zero_()
-        lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
+        lv.assemble(lv.s, Dz0, prob.local_rows(c) if lv.sharded else c, 0.0, capi.WANT_F0)
         cdots.append(float(lv.scal.cpu()[2]))
         if verbose:
             print(f"t={t:.3e} its={row} c.Dz={cdots[-1]:.12e}", file=logfile)
@@ -313,12 +342,12 @@ def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float =
     rank, nranks, group = _dist_layout()
     prob = DeviceProblem(M, idx, p, slack=False, device=device, rank=rank, nranks=nranks, block=geom.block, group=group)
     z = torch.from_numpy(z0.reshape(-1, order="F").copy()).to(prob.device)
-    c = prob.local_rows(_cm(cmat, prob.device))
+    c = _cm(cmat, prob.device)
     # strict feasibility of the start (upstream skips the feasibility phase when it holds)
     lv = prob.level(len(M.R_fine) - 1)
-    Dz0 = prob.apply_D(z)
+    Dz0 = prob.apply_D(z, full=not lv.sharded)
     lv.s.zero_()
-    lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
+    lv.assemble(lv.s, Dz0, prob.local_rows(c) if lv.sharded else c, 0.0, capi.WANT_F0)
     sol_feas = None
     if float(lv.scal.cpu()[1]) != 1.0:
         if nranks > 1:
