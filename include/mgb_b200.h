@@ -158,6 +158,17 @@ int mgb_map_barrier(mgb_ctx* ctx, const mgb_barrier* barrier, int32_t nD, int64_
                     int32_t which, double* out_dev);
 /* amgb_all_isfinite (src:121-133): *flag_host = 1 if every entry finite. */
 int mgb_all_isfinite(mgb_ctx* ctx, const double* v_dev, int64_t len, int32_t* flag_host);
+/* Local part of the HPCVector reductions the Newton loop and the line search use (dot, sum, norm: reference
+ * tools/profile_scaling.jl:89-109, tools/profile_barrier.jl:95-118): out = <x,y>, sum(x), |x|_2^2 or
+ * max|x| over `len` device entries.  Deterministic (fixed grid, fixed fold order).  The result goes to out_dev
+ * (1 double, may be NULL) and/or out_host (may be NULL; non-NULL synchronises the stream).  Across ranks the caller
+ * all-reduces the scalar (MPI/NCCL), as HPCSparseArrays does. */
+#define MGB_REDUCE_DOT 0
+#define MGB_REDUCE_SUM 1
+#define MGB_REDUCE_NORM2SQ 2
+#define MGB_REDUCE_MAXABS 3
+int mgb_reduce(mgb_ctx* ctx, int32_t op, const double* x_dev, const double* y_dev, int64_t len, double* out_dev,
+               double* out_host);
 /* amgb_diag (src:137-147) as a device map: out = w .* y[:,col] (the diagonal the reference wraps in a sparse matrix) */
 int mgb_diag_scale(mgb_ctx* ctx, const double* w_dev, const double* y_dev, int64_t n, int64_t ld,
                    int32_t col, double* out_dev);

@@ -60,6 +60,40 @@ def amgb_all_isfinite(z) -> bool:
     return ok
 
 
+# ------------------------------------------------------------------ dot / sum / norm (HPCVector reductions)
+def _reduce(op: str, x, y=None) -> float:
+    """local deterministic device reduction (mgb_reduce) + all-reduce of the scalar over the ranks
+    (reference: local reduce + Allreduce, tools/profile_scaling.jl:89-109)"""
+    bx = x.v if isinstance(x, HPCVector) else x.A
+    by = None if y is None else (y.v if isinstance(y, HPCVector) else y.A)
+    if by is not None and by.numel() != bx.numel():
+        raise ValueError("dot: vectors of different local length (partitions differ)")
+    val = _ctx(x.backend).reduce(op, bx, bx.numel(), by)
+    if _dist_ready():
+        import torch.distributed as dist
+        t = torch.tensor([val], device=bx.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "maxabs" else dist.ReduceOp.SUM)
+        val = float(t.item())
+    return val
+
+
+def dot(x, y) -> float:
+    return _reduce("dot", x, y)
+
+
+def vsum(x) -> float:
+    return _reduce("sum", x)
+
+
+def norm(x, ord=2) -> float:
+    """2-norm (default) or max-norm (ord=inf) of an HPCVector / HPCMatrix"""
+    if ord in (np.inf, float("inf"), "inf"):
+        return _reduce("maxabs", x)
+    if ord != 2:
+        raise ValueError("norm: only the 2-norm and the max-norm are implemented")
+    return float(np.sqrt(_reduce("norm2sq", x)))
+
+
 # ------------------------------------------------------------------ amgb_diag (src:137-147)
 def amgb_diag(proto, z, m: Optional[int] = None, n: Optional[int] = None) -> HPCSparseMatrix:
     """spdiagm(m, n, 0 => z) as an HPCSparseMatrix with the prototype's index type (Int32 for a dense

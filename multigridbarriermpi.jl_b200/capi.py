@@ -24,7 +24,7 @@ BARRIER_EUCLIDIAN_POWER = 1
 EXPORTS = [
     "mgb_last_error", "mgb_version", "mgb_ctx_create", "mgb_ctx_destroy", "mgb_ctx_sync", "mgb_plan_create",
     "mgb_plan_create_local", "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
-    "mgb_map_barrier", "mgb_all_isfinite", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
+    "mgb_map_barrier", "mgb_all_isfinite", "mgb_reduce", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
     "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_dist_debug", "mgb_host_register", "mgb_host_unregister",
@@ -96,6 +96,7 @@ def load(build_if_missing: bool = True):
     lib.mgb_apply_D.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.mgb_map_barrier.argtypes = [C.c_void_p, C.POINTER(_Barrier), C.c_int32, C.c_int64, C.c_void_p, C.c_int32, C.c_void_p]
     lib.mgb_all_isfinite.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int32)]
+    lib.mgb_reduce.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.POINTER(C.c_double)]
     lib.mgb_diag_scale.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_void_p]
     lib.mgb_time_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32,
@@ -186,6 +187,14 @@ class Context:
         flag = C.c_int32(0)
         _check(load().mgb_all_isfinite(self._h, _ptr(v_dev), int(length), C.byref(flag)))
         return bool(flag.value)
+
+    REDUCE = {"dot": 0, "sum": 1, "norm2sq": 2, "maxabs": 3}
+
+    def reduce(self, op: str, x_dev, length: int, y_dev=None) -> float:
+        """dot / sum / squared 2-norm / max-abs of device vectors (mgb_reduce), result on the host"""
+        out = C.c_double(0.0)
+        _check(load().mgb_reduce(self._h, self.REDUCE[op], _ptr(x_dev), _ptr(y_dev), int(length), None, C.byref(out)))
+        return out.value
 
     def diag_scale(self, w_dev, y_dev, n: int, ld: int, col: int, out_dev):
         _check(load().mgb_diag_scale(self._h, _ptr(w_dev), _ptr(y_dev), int(n), int(ld), int(col), _ptr(out_dev)))

@@ -733,6 +733,51 @@ static __global__ void isfinite_kernel(const double* __restrict__ v, int64_t len
     if (__syncthreads_or(bad) && threadIdx.x == 0) *flag = 0;  // idempotent store, not an accumulation
 }
 
+// dot / sum / squared 2-norm / max |.| of device vectors (HPCVector dot, sum, norm: reference
+// tools/profile_scaling.jl:89-109).  Deterministic: a fixed grid of REDUCE_BLOCKS blocks, each thread
+// strides the vector in a fixed pattern, shuffle tree inside the block, and the block that retires last folds the
+// REDUCE_BLOCKS partials in index order - the same bits on every run and for every launch configuration.
+constexpr int REDUCE_BLOCKS = 296;   // 2 per SM on B200
+static __global__ void __launch_bounds__(256) reduce_kernel(const double* __restrict__ x, const double* __restrict__ y, int64_t len,
+                                                            int op, double* __restrict__ part, unsigned* __restrict__ ticket,
+                                                            double* __restrict__ out) {
+    double acc = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < len; i += (int64_t)gridDim.x * blockDim.x) {
+        const double a = x[i];
+        if (op == 0) acc = fma(a, y[i], acc);          // dot
+        else if (op == 1) acc += a;                     // sum
+        else if (op == 2) acc = fma(a, a, acc);         // |x|^2
+        else acc = fmax(acc, fabs(a));                  // max |x|
+    }
+    __shared__ double sh[8];
+    __shared__ bool last;
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, acc, mk);
+        acc = (op == 3) ? fmax(acc, o) : acc + o;
+    }
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = sh[0];
+        for (int r = 1; r < 8; ++r) v = (op == 3) ? fmax(v, sh[r]) : v + sh[r];
+        part[blockIdx.x] = v;
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);   // a ticket, not an accumulation of values
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence();
+        double v = 0.0;
+        for (unsigned b = 0; b < gridDim.x; ++b) {
+            const double pb = *((volatile double*)&part[b]);
+            v = (op == 3) ? fmax(v, pb) : v + pb;
+        }
+        out[0] = v;
+        *ticket = 0u;
+    }
+}
+
 static __global__ void diag_scale_kernel(const double* __restrict__ w, const double* __restrict__ y, int64_t n,
                                   double* __restrict__ out) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

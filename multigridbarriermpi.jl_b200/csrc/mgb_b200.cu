@@ -67,6 +67,8 @@ struct mgb_ctx {
     int sm_count = 148;
     DevBuf<double> flush;  // L2 flush scratch (lazy)
     DevBuf<int> flag;
+    DevBuf<double> red;       // reduce_kernel: REDUCE_BLOCKS partials + result (lazy)
+    DevBuf<unsigned> ticket;
 };
 
 struct mgb_plan {
@@ -739,6 +741,31 @@ int mgb_all_isfinite(mgb_ctx* ctx, const double* v_dev, int64_t len, int32_t* fl
         *flag_host = res;
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_all_isfinite: ") + ex.what()); }
+}
+
+int mgb_reduce(mgb_ctx* ctx, int32_t op, const double* x_dev, const double* y_dev, int64_t len, double* out_dev,
+               double* out_host) {
+    try {
+        if (!ctx || (!x_dev && len > 0)) return fail("mgb_reduce: NULL argument");
+        if (op < MGB_REDUCE_DOT || op > MGB_REDUCE_MAXABS) return fail("mgb_reduce: unknown operation");
+        if (op == MGB_REDUCE_DOT && !y_dev && len > 0) return fail("mgb_reduce: dot needs two vectors");
+        if (len < 0) return fail("mgb_reduce: negative length");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        if (!ctx->red.p) {
+            ctx->red.alloc(mgb::REDUCE_BLOCKS + 1);
+            ctx->ticket.alloc(1);
+            CUDA_OK(cudaMemsetAsync(ctx->ticket.p, 0, sizeof(unsigned), ctx->stream));
+        }
+        double* out = out_dev ? out_dev : ctx->red.p + mgb::REDUCE_BLOCKS;
+        mgb::reduce_kernel<<<mgb::REDUCE_BLOCKS, 256, 0, ctx->stream>>>(x_dev, y_dev, len, op, ctx->red.p, ctx->ticket.p, out);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        if (out_host) {
+            CUDA_OK(cudaMemcpyAsync(out_host, out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        }
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_reduce: ") + ex.what()); }
 }
 
 int mgb_diag_scale(mgb_ctx* ctx, const double* w_dev, const double* y_dev, int64_t n, int64_t ld, int32_t col,

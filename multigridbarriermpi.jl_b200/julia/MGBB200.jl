@@ -71,6 +71,17 @@ function Plan(ctx::Ctx, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::Mat
     finalizer(p -> ccall((:mgb_plan_destroy, LIB), Cint, (Ptr{Cvoid},), p.h), pl); pl
 end
 
+# local part of dot / sum / norm^2 / max|.| on device vectors (deterministic); the caller all-reduces the scalar
+function reduce_local(ctx::Ctx, op::Integer, x::CuVector{Float64}, y::Union{CuVector{Float64},Nothing} = nothing)
+    out = Ref{Float64}(0.0)
+    GC.@preserve x y begin
+        check(ccall((:mgb_reduce, LIB), Cint, (Ptr{Cvoid}, Int32, CuPtr{Float64}, CuPtr{Float64}, Int64, CuPtr{Float64}, Ref{Float64}),
+                    ctx.h, op, pointer(x), y === nothing ? CU_NULL : pointer(y), length(x), CU_NULL, out))
+    end
+    out[]
+end
+LinearAlgebra.dot(ctx::Ctx, x::HPCVector, y::HPCVector, comm) = MPI.Allreduce(reduce_local(ctx, 0, x.v, y.v), +, comm)
+
 # The rank's own storage of a row-partitioned HPCSparseMatrix, field for field (constructor order
 # src/MultiGridBarrierMPI.jl:216-221): colptr indexes LOCAL rows, rowval holds COMPRESSED column ids,
 # col_indices maps them to global columns.  Passed zero-copy to mgb_plan_create_local (struct mgb_hpc_block).

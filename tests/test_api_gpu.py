@@ -48,6 +48,23 @@ def test_amgb_all_isfinite(api, be):
     assert api.amgb_all_isfinite(HPCVector(np.zeros(0), be)) is True   # empty
 
 
+def test_vector_reductions(api, be, gpu_ctx):
+    """dot / sum / norm of HPCVectors (reference tools/profile_scaling.jl:89-109): deterministic device reductions"""
+    from mgb_b200.hpc import HPCVector
+    rng = np.random.default_rng(5)
+    for n in (1, 7, 256, 1000, 300001):
+        a, b = rng.standard_normal(n), rng.standard_normal(n)
+        x, y = HPCVector(a, be), HPCVector(b, be)
+        assert abs(api.dot(x, y) - a @ b) <= 1e-13 * (np.abs(a) @ np.abs(b))
+        assert abs(api.vsum(x) - a.sum()) <= 1e-13 * np.abs(a).sum()
+        assert abs(api.norm(x) - np.linalg.norm(a)) <= 1e-14 * np.linalg.norm(a)
+        assert api.norm(x, np.inf) == np.abs(a).max()
+        assert api.dot(x, y) == api.dot(x, y)            # same bits on every call
+    a = np.array([1.0, np.nan, 2.0])
+    assert np.isnan(api.vsum(HPCVector(a, be)))          # non-finite entries are data, not errors
+    assert gpu_ctx.reduce("sum", None, 0) == 0.0         # empty local block (more ranks than rows)
+
+
 def test_map_rows_kats(api, be):
     from mgb_b200.hpc import HPCVector, HPCMatrix
     x = HPCMatrix(np.array([[1.0, 2], [3, 4], [5, 6]]), be)
