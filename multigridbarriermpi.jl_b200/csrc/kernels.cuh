@@ -730,16 +730,35 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
     }
 }
 
-// warp per output entry (long contribution lists: coarse multigrid levels)
+// LPE lanes per output entry (long contribution lists: coarse multigrid levels).  LPE = 32 for lists of hundreds of
+// contributions, 8 when a list has a few dozen (a full warp per entry would leave most lanes idle and quadruple
+// the number of warps that have to cycle through the SMs).
+template <int LPE>
 static __global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, const int64_t* __restrict__ cptr,
                                                           const int32_t* __restrict__ cidx,
                                                           const double* __restrict__ src, double* __restrict__ dst) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+    const int lane = threadIdx.x % LPE;
+    const bool act = wid < nout;   // whole groups: every lane of a warp reaches the shuffles
+    double acc = 0.0;
+    if (act) {
+        const int64_t c0 = cptr[wid], c1 = cptr[wid + 1];
+        for (int64_t cix = c0 + lane; cix < c1; cix += LPE) acc += src[cidx[cix]];
+    }
+#pragma unroll
+    for (int mk = LPE / 2; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+    if (act && lane == 0) dst[wid] = acc;
+}
+
+// stage 2 of the chunked coarse-level gather: dst[e] = sum of the contiguous partials [pptr[e], pptr[e+1]) in order
+static __global__ void __launch_bounds__(256) gather_warp_contig_kernel(const int64_t nout, const int64_t* __restrict__ pptr,
+                                                                 const double* __restrict__ part, double* __restrict__ dst) {
     const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nout) return;
-    const int64_t c0 = cptr[wid], c1 = cptr[wid + 1];
+    const int64_t c0 = pptr[wid], c1 = pptr[wid + 1];
     double acc = 0.0;
-    for (int64_t cix = c0 + lane; cix < c1; cix += 32) acc += src[cidx[cix]];
+    for (int64_t cix = c0 + lane; cix < c1; cix += 32) acc += part[cix];
 #pragma unroll
     for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
     if (lane == 0) dst[wid] = acc;

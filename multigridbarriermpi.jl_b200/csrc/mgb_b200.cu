@@ -58,6 +58,37 @@ struct DevBuf {
     size_t bytes() const { return n * sizeof(T); }
 };
 
+// Coarse multigrid levels have few outputs with very long contribution lists (level 0 of fem2d L=8: 25 entries fed
+// by all 32,768 elements).  One warp per output walks such a list in hundreds of dependent steps and sets the kernel
+// time alone; instead every list is cut into chunks of GATHER_CHUNK contributions (one warp each, stage 1) whose
+// partial sums a second launch adds per output in list order (stage 2).  Deterministic; the chunking depends on the
+// plan only.
+struct ChunkedList {
+    DevBuf<int64_t> kptr;   // nchunks + 1: contribution range of every chunk
+    DevBuf<int64_t> pptr;   // nout + 1: partial range of every output
+    DevBuf<double> part;    // nchunks
+    int64_t nchunks = 0;
+    void build(const std::vector<int64_t>& cptr, int64_t chunk, cudaStream_t st) {
+        const int64_t nout = (int64_t)cptr.size() - 1;
+        std::vector<int64_t> k(1, 0), pp((size_t)nout + 1, 0);
+        for (int64_t e = 0; e < nout; ++e) {
+            for (int64_t c0 = cptr[e]; c0 < cptr[e + 1]; c0 += chunk) k.push_back(std::min(cptr[e + 1], c0 + chunk));
+            pp[(size_t)e + 1] = (int64_t)k.size() - 1;
+        }
+        nchunks = (int64_t)k.size() - 1;
+        kptr.upload(k, st); pptr.upload(pp, st);
+        part.alloc((size_t)std::max<int64_t>(nchunks, 1));
+        CUDA_OK(cudaStreamSynchronize(st));   // k / pp die with this scope
+    }
+    size_t bytes() const { return kptr.bytes() + pptr.bytes() + part.bytes(); }
+};
+
+static int64_t gather_chunk() {
+    const char* e = std::getenv("MGB_GATHER_CHUNK");
+    const long v = e ? std::atol(e) : 128;
+    return v > 0 ? v : 0;   // 0: one warp per output (no chunking)
+}
+
 }  // namespace
 
 struct mgb_ctx {
@@ -84,6 +115,8 @@ struct mgb_plan {
     mgb::ElementPlan ep;  // host arrays are released after upload except the pattern
     DevBuf<int32_t> d_lcols, d_hcidx, d_gcidx;
     DevBuf<int64_t> d_hcptr, d_gcptr, d_hlptr;
+    // coarse levels: contribution lists cut into chunks (one warp each) + partial sums (see ChunkedList)
+    ChunkedList ck_h, ck_g;
     DevBuf<int2> d_hsrc2;
     DevBuf<int32_t> d_hlidx, d_hlt;
     int64_t n_long = 0;
@@ -321,17 +354,24 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
 
     mgb::GatherParams G = make_gather_params(pl, flags, t, scal ? scal : pl->d_scal_tmp.p, grad, hval);
     if (pl->long_lists) {
-        // coarse levels: few output entries with long lists -> warp per entry
-        if (G.want_h) {
-            const int64_t nb = (pl->nnzH * 32 + 255) / 256;
-            mgb::gather_warp_kernel<<<(unsigned)nb, 256, 0, st>>>(pl->nnzH, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval);
-            g_launches++;
-        }
-        if (G.want_g) {
-            const int64_t nb = (pl->m * 32 + 255) / 256;
-            mgb::gather_warp_kernel<<<(unsigned)nb, 256, 0, st>>>(pl->m, G.g_cptr, G.g_cidx, G.rel, grad);
-            g_launches++;
-        }
+        // coarse levels: few output entries with long lists -> warp per chunk of a list, then warp per entry over
+        // the partial sums
+        auto warp_gather = [&](ChunkedList& ck, int64_t nout, int64_t ncontrib, const int64_t* cptr, const int32_t* cidx, const double* src,
+                               double* dst) {
+            if (ck.nchunks > 0) {
+                mgb::gather_warp_kernel<32><<<(unsigned)((ck.nchunks * 32 + 255) / 256), 256, 0, st>>>(ck.nchunks, ck.kptr.p, cidx, src, ck.part.p);
+                mgb::gather_warp_contig_kernel<<<(unsigned)((nout * 32 + 255) / 256), 256, 0, st>>>(nout, ck.pptr.p, ck.part.p, dst);
+                g_launches += 2;
+            } else if (ncontrib < 48 * nout) {
+                mgb::gather_warp_kernel<8><<<(unsigned)((nout * 8 + 255) / 256), 256, 0, st>>>(nout, cptr, cidx, src, dst);
+                g_launches++;
+            } else {
+                mgb::gather_warp_kernel<32><<<(unsigned)((nout * 32 + 255) / 256), 256, 0, st>>>(nout, cptr, cidx, src, dst);
+                g_launches++;
+            }
+        };
+        if (G.want_h) warp_gather(pl->ck_h, pl->nnzH, pl->n_hcontrib, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval);
+        if (G.want_g) warp_gather(pl->ck_g, pl->m, pl->n_gcontrib, G.g_cptr, G.g_cidx, G.rel, grad);
         G.want_h = G.want_g = 0;
     }
     size_gather_grid(pl, G);
@@ -380,6 +420,10 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 // patch-fused path builds its own lists below
             } else if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
                 pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
+                // chunk only where it pays: lists of a thousand contributions and more (coarsest levels)
+                const int64_t ch = gather_chunk();
+                if (ch > 0 && (int64_t)ep.h_cidx.size() >= 1024 * std::max<int64_t>(pl->nnzH, 1)) pl->ck_h.build(ep.h_cptr, ch, st);
+                if (ch > 0 && (int64_t)ep.g_cidx.size() >= 1024 * std::max<int64_t>(pl->m, 1)) pl->ck_g.build(ep.g_cptr, ch, st);
             } else {   // two-wide ELL + long list for the thread-per-entry gather
                 std::vector<int2> src2(pl->nnzH);
                 std::vector<int64_t> lptr(1, 0);
@@ -429,7 +473,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->d_scal_tmp.alloc(4);
             CUDA_OK(cudaStreamSynchronize(st));
             pl->dev_bytes = pl->d_lcols.bytes() + pl->d_prec.bytes() + pl->d_hcptr.bytes() + pl->d_hcidx.bytes() + pl->d_gcptr.bytes() +
-                            pl->d_gcidx.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
+                            pl->d_gcidx.bytes() + pl->ck_h.bytes() + pl->ck_g.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
           }
             // release host copies that are no longer needed
             std::vector<int32_t>().swap(ep.h_cidx); std::vector<int64_t>().swap(ep.h_cptr);
