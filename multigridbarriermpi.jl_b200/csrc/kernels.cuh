@@ -845,6 +845,35 @@ static __global__ void __launch_bounds__(256) spmv_kernel(int64_t nrows, const i
     y[i] = alpha * acc + ((y0 && beta != 0.0) ? beta * y0[i] : 0.0);
 }
 
+// rows of hundreds of entries and more (the restriction R' of a coarse level: a few rows fed by every fine unknown):
+// one warp per chunk of a row (stage 1), then one warp per row over the partial sums (stage 2, with alpha / beta)
+static __global__ void __launch_bounds__(256) spmv_chunk_kernel(int64_t nchunks, const int64_t* __restrict__ kptr,
+                                                         const int32_t* __restrict__ idx, const double* __restrict__ val,
+                                                         const double* __restrict__ x, double* __restrict__ part) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool act = wid < nchunks;
+    double acc = 0.0;
+    if (act)
+        for (int64_t p = kptr[wid] + lane; p < kptr[wid + 1]; p += 32) acc = fma(val[p], __ldg(&x[idx[p]]), acc);
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+    if (act && lane == 0) part[wid] = acc;
+}
+static __global__ void __launch_bounds__(256) spmv_fold_kernel(int64_t nrows, const int64_t* __restrict__ pptr,
+                                                        const double* __restrict__ part, double alpha, double beta,
+                                                        const double* __restrict__ y0, double* __restrict__ y) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool act = wid < nrows;
+    double acc = 0.0;
+    if (act)
+        for (int64_t p = pptr[wid] + lane; p < pptr[wid + 1]; p += 32) acc += part[p];
+#pragma unroll
+    for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+    if (act && lane == 0) y[wid] = alpha * acc + ((y0 && beta != 0.0) ? beta * y0[wid] : 0.0);
+}
+
 static __global__ void __launch_bounds__(256) gather_idx_kernel(const double* __restrict__ src, const int32_t* __restrict__ idx,
                                                          int64_t count, double* __restrict__ out) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -187,6 +187,7 @@ struct mgb_spmat {
     DevBuf<int64_t> ptr, tptr;
     DevBuf<int32_t> idx, tidx;
     DevBuf<double> val, tval;
+    ChunkedList ck, tck;   // built when an orientation has rows of >= 1024 entries (thread-per-row would crawl)
 };
 
 namespace {
@@ -837,6 +838,9 @@ int mgb_spmat_create(mgb_ctx* ctx, const mgb_csr* A, mgb_spmat** out) {
         cudaStream_t st = ctx->stream;
         M->ptr.upload(H.ptr, st); M->idx.upload(H.idx, st); M->val.upload(H.val, st);
         M->tptr.upload(T.ptr, st); M->tidx.upload(T.idx, st); M->tval.upload(T.val, st);
+        auto longest = [](const mgb::HostCSR& C) { int64_t mx = 0; for (int64_t i = 0; i < C.nrows; ++i) mx = std::max(mx, C.ptr[i + 1] - C.ptr[i]); return mx; };
+        if (longest(H) >= 1024) M->ck.build(H.ptr, 256, st);
+        if (longest(T) >= 1024) M->tck.build(T.ptr, 256, st);
         CUDA_OK(cudaStreamSynchronize(st));
         *out = M.release();
         return 0;
@@ -858,10 +862,17 @@ int mgb_spmat_mv(mgb_spmat* A, int32_t trans, double alpha, const double* x_dev,
         CUDA_OK(cudaSetDevice(A->ctx->device));
         const int64_t nr = trans ? A->ncols : A->nrows;
         if (nr > 0) {
-            if (trans)
-                mgb::spmv_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, A->ctx->stream>>>(nr, A->tptr.p, A->tidx.p, A->tval.p, alpha, x_dev, beta, y0_dev, y_dev);
-            else
-                mgb::spmv_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, A->ctx->stream>>>(nr, A->ptr.p, A->idx.p, A->val.p, alpha, x_dev, beta, y0_dev, y_dev);
+            cudaStream_t st = A->ctx->stream;
+            ChunkedList& ck = trans ? A->tck : A->ck;
+            const int64_t* ptr = trans ? A->tptr.p : A->ptr.p;
+            const int32_t* idx = trans ? A->tidx.p : A->idx.p;
+            const double* val = trans ? A->tval.p : A->val.p;
+            if (ck.nchunks > 0) {
+                mgb::spmv_chunk_kernel<<<(unsigned)((ck.nchunks * 32 + 255) / 256), 256, 0, st>>>(ck.nchunks, ck.kptr.p, idx, val, x_dev, ck.part.p);
+                mgb::spmv_fold_kernel<<<(unsigned)((nr * 32 + 255) / 256), 256, 0, st>>>(nr, ck.pptr.p, ck.part.p, alpha, beta, y0_dev, y_dev);
+                g_launches++;
+            } else
+                mgb::spmv_kernel<<<(unsigned)((nr + 255) / 256), 256, 0, st>>>(nr, ptr, idx, val, alpha, x_dev, beta, y0_dev, y_dev);
             g_launches++;
         }
         CUDA_OK(cudaGetLastError());

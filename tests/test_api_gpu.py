@@ -125,3 +125,32 @@ def test_fem2d_mpi_solve_wrapper(api):
     sol_ref = O.amgb(mgb_b200.fem2d(2), p=2.0)
     assert np.linalg.norm(soln.z - sol_ref.z) / np.linalg.norm(sol_ref.z) < 1e-9
     assert np.array_equal(soln.SOL_main["its"], sol_ref.SOL_main["its"])
+
+
+def test_spmat_products_both_orientations(gpu_ctx):
+    """HPCSparseMatrix * HPCVector and A' * v (reference test/test_nonsquare.jl:45-72) through mgb_spmat_mv:
+    short rows (thread per row) and the restriction of a coarse level, whose transposed rows hold thousands of
+    entries (chunked two-stage path); alpha / beta / in-place update as the Newton driver uses them."""
+    import torch
+    from mgb_b200 import capi
+    from helpers import problem
+    dev = torch.device("cuda", gpu_ctx.device)
+    rng = np.random.default_rng(9)
+    mats = [sp.random(300, 120, density=0.05, random_state=3, format="csr"),
+            problem(mgb_b200.fem2d(5), level=0)["R"], problem(mgb_b200.fem1d(12), level=1)["R"]]
+    for A in mats:
+        A = sp.csr_matrix(A)
+        M = capi.SpMat(gpu_ctx, A)
+        assert max(np.diff(A.tocsc().indptr)) >= 1024 or A.shape[0] == 300
+        for trans in (False, True):
+            op = A.T if trans else A
+            x = rng.standard_normal(op.shape[1]); y0 = rng.standard_normal(op.shape[0])
+            x_d, y0_d = torch.from_numpy(x).to(dev), torch.from_numpy(y0).to(dev)
+            y_d = torch.empty(op.shape[0], dtype=torch.float64, device=dev)
+            M.mv(x_d, y_d, trans=trans)
+            ref = op @ x
+            assert np.abs(y_d.cpu().numpy() - ref).max() <= 1e-13 * (abs(op) @ np.abs(x)).max()
+            M.mv(x_d, y0_d, trans=trans, alpha=-0.5, beta=2.0, y0_dev=y0_d)      # in place: y0 <- 2 y0 - A x / 2
+            ref2 = 2.0 * y0 - 0.5 * ref
+            assert np.abs(y0_d.cpu().numpy() - ref2).max() <= 1e-13 * ((abs(op) @ np.abs(x)).max() + np.abs(y0).max())
+        M.close()
