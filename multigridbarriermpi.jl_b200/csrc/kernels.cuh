@@ -41,9 +41,6 @@ struct ElemParams {
     double* part;            // gridDim.x * 4  {f0, cdot, nonfinite count, -}
     double* Dz;              // nloc x ND or null
     int off_uu, off_us, off_ss, off_ut, off_st, off_tt, NS;
-    // objective-only calls (line search): the block that retires last folds the partials itself - no second launch
-    double* scal_out;        // {f0, all_finite, <c,Dz>_w, infeasible count} or null
-    unsigned* ticket;
 };
 
 template <int V>
@@ -453,48 +450,6 @@ __device__ __forceinline__ void block_scalars(double v0, double v1, double v2, d
     }
 }
 
-// Objective-only calls: the last block to retire folds the per-block scalars in exactly the order gather_kernel's
-// scalar block uses (256 strided partial sums, then a binary tree), so f0 has the same bits whichever kernel
-// finishes it.  The ticket counts blocks, it does not accumulate values.
-__device__ __forceinline__ void fold_scalars_last_block(const double* __restrict__ part, double t, double* __restrict__ scal,
-                                                        unsigned* __restrict__ ticket) {
-    __shared__ bool last;
-    __shared__ double sh[3][256];
-    if (threadIdx.x == 0) {
-        __threadfence();
-        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return;
-    __threadfence();
-    const int64_t nparts = gridDim.x;
-    for (int v = threadIdx.x; v < 256; v += blockDim.x) {
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-        for (int64_t r = v; r < nparts; r += 256) {
-            s0 += __ldcg(&part[r * 4 + 0]);
-            s1 += __ldcg(&part[r * 4 + 1]);
-            s2 += __ldcg(&part[r * 4 + 2]);
-        }
-        sh[0][v] = s0; sh[1][v] = s1; sh[2][v] = s2;
-    }
-    __syncthreads();
-    for (int st = 128; st >= 1; st >>= 1) {
-        for (int v = threadIdx.x; v < st; v += blockDim.x) {
-            sh[0][v] += sh[0][v + st];
-            sh[1][v] += sh[1][v + st];
-            sh[2][v] += sh[2][v + st];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        scal[0] = sh[0][0] + t * sh[1][0];
-        scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
-        scal[2] = sh[1][0];
-        scal[3] = sh[2][0];
-        *ticket = 0u;
-    }
-}
-
 // Two-stage path, stage 1: slot / gradient records to global memory (replayed by gather_kernel).
 template <int B, int D, int MODE, bool FINE, int FLAGS>
 __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
@@ -507,9 +462,6 @@ __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_
     double v0, v1, v2;
     element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
     block_scalars(v0, v1, v2, P.part);
-    if constexpr (FLAGS == 1) {
-        if (P.scal_out) fold_scalars_last_block(P.part, P.t, P.scal_out, P.ticket);
-    }
 }
 
 // Patch-fused path: one CTA = PATCH consecutive elements.  Phase A keeps the slot / gradient records

@@ -117,7 +117,6 @@ struct mgb_plan {
     DevBuf<int64_t> d_hcptr, d_gcptr, d_hlptr;
     // coarse levels: contribution lists cut into chunks (one warp each) + partial sums (see ChunkedList)
     ChunkedList ck_h, ck_g;
-    DevBuf<unsigned> d_ticket;   // objective-only calls: last-block fold in the element kernel
     DevBuf<int2> d_hsrc2;
     DevBuf<int32_t> d_hlidx, d_hlt;
     int64_t n_long = 0;
@@ -351,15 +350,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         CUDA_OK(cudaGetLastError());
         return;
     }
-    // objective only (line-search points): the element kernel's last block folds the scalars, no second launch
-    const bool f0_only = mgb::canonical_flags(flags) == 1 && mid == nullptr && getenv("MGB_F0_TWO_LAUNCHES") == nullptr;
-    if (f0_only) {
-        if (!pl->d_ticket.p) { pl->d_ticket.alloc(1); CUDA_OK(cudaMemsetAsync(pl->d_ticket.p, 0, sizeof(unsigned), st)); }
-        P.scal_out = scal ? scal : pl->d_scal_tmp.p;
-        P.ticket = pl->d_ticket.p;
-    }
     launch_elem(pl, P, flags);
-    if (f0_only) return;
     if (mid) CUDA_OK(cudaEventRecord(mid, st));
 
     mgb::GatherParams G = make_gather_params(pl, flags, t, scal ? scal : pl->d_scal_tmp.p, grad, hval);

@@ -124,24 +124,6 @@ def test_csr_replay_chunking_and_windows(gpu_ctx, chunk, sigma, monkeypatch):
 
 
 @pytest.mark.parametrize("gen,L,level", [("fem2d", 5, None), ("fem2d", 4, 1), ("fem1d", 9, None), ("fem1d", 6, 0)])
-def test_objective_only_call_has_the_bits_of_the_full_assembly(gpu_ctx, gen, L, level, monkeypatch):
-    """line-search points (flags = WANT_F0) fold the scalars in the element kernel's last block; the fold order is
-    the one of the gather kernel's scalar block, so f0 is bit-identical to the f0 of a full assembly and to the
-    two-launch variant (MGB_F0_TWO_LAUNCHES)"""
-    from helpers import problem
-    pr = problem(getattr(mgb_b200, gen)(L), level=level)
-    plan = capi.Plan(gpu_ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
-    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
-    full = plan.assemble_host(pr["s"], Dz0, pr["c"], 0.7, 7)["scal"].copy()
-    for rep in range(3):   # the ticket must re-arm itself
-        one = plan.assemble_host(pr["s"], Dz0, pr["c"], 0.7, 1)["scal"].copy()
-        assert np.array_equal(one, full), (one, full)
-    monkeypatch.setenv("MGB_F0_TWO_LAUNCHES", "1")
-    two = plan.assemble_host(pr["s"], Dz0, pr["c"], 0.7, 1)["scal"].copy()
-    assert np.array_equal(two, full)
-
-
-@pytest.mark.parametrize("gen,L,level", [("fem2d", 5, None), ("fem2d", 4, 1), ("fem1d", 9, None), ("fem1d", 6, 0)])
 def test_objective_only_call_has_the_bits_of_the_full_assembly(gpu_ctx, gen, L, level):
     """line-search points (flags = WANT_F0) run other kernel instances than a full assembly; the objective they
     return must be the same number bit for bit (the Newton driver compares one against the other)"""
