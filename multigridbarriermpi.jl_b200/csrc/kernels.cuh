@@ -605,6 +605,33 @@ static __global__ void __launch_bounds__(256) interface_kernel(const InterfacePa
     }
 }
 
+// one block of 256 threads folds the per-block scalar partials in a fixed order -> {f0, all_finite, <c,Dz>_w, count}
+__device__ __forceinline__ void fold_scalars_block(const double* __restrict__ part, int64_t nparts, double t, double* __restrict__ scal) {
+    __shared__ double sh[3][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = threadIdx.x; r < nparts; r += blockDim.x) {
+        s0 += part[r * 4 + 0];
+        s1 += part[r * 4 + 1];
+        s2 += part[r * 4 + 2];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && scal) {
+        scal[0] = sh[0][0] + t * sh[1][0];
+        scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
+        scal[2] = sh[1][0];
+        scal[3] = sh[2][0];
+    }
+}
+
 struct GatherParams {
     int64_t nnzH, m;
     const int2* h_src2;       // per entry: {first, second} contribution slot; second = -1 if none;
@@ -705,63 +732,57 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
     }
     // scalar block
     pdl_wait_primary();
-    __shared__ double sh[3][256];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {
-        s0 += P.part[r * 4 + 0];
-        s1 += P.part[r * 4 + 1];
-        s2 += P.part[r * 4 + 2];
-    }
-    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
-    __syncthreads();
-    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
-        if ((int)threadIdx.x < st) {
-            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
-            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
-            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && P.scal) {
-        P.scal[0] = sh[0][0] + P.t * sh[1][0];
-        P.scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
-        P.scal[2] = sh[1][0];
-        P.scal[3] = sh[2][0];
-    }
+    fold_scalars_block(P.part, P.nparts, P.t, P.scal);
 }
 
-// LPE lanes per output entry (long contribution lists: coarse multigrid levels).  LPE = 32 for lists of hundreds of
-// contributions, 8 when a list has a few dozen (a full warp per entry would leave most lanes idle and quadruple
-// the number of warps that have to cycle through the SMs).
+// Coarse multigrid levels: few outputs with long contribution lists.  One launch serves up to two lists (Hessian
+// values and gradient) plus the scalar fold, so a coarse assembly is element kernel + one or two of these launches
+// instead of five small ones.  Per list: LPE lanes per output - 32 for lists of hundreds of contributions, 8 when a
+// list has a few dozen (a full warp per entry would leave most lanes idle and quadruple the number of warps that
+// cycle through the SMs); idx == nullptr sums the contiguous range src[ptr[o] .. ptr[o+1]) (stage 2 of a chunked
+// list, see ChunkedList in mgb_b200.cu).
+struct WarpList {
+    int64_t nout;          // 0: unused
+    const int64_t* ptr;
+    const int32_t* idx;    // nullptr: contiguous
+    const double* src;
+    double* dst;
+    int lpe;               // 8 or 32
+    int64_t nblk;          // blocks of 256 threads
+};
+struct WarpGatherParams {
+    WarpList a, b;
+    const double* part;    // scalar partials (folded by the last block when scal != nullptr)
+    int64_t nparts;
+    double t;
+    double* scal;
+};
+
 template <int LPE>
-static __global__ void __launch_bounds__(256) gather_warp_kernel(const int64_t nout, const int64_t* __restrict__ cptr,
-                                                          const int32_t* __restrict__ cidx,
-                                                          const double* __restrict__ src, double* __restrict__ dst) {
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / LPE;
+__device__ __forceinline__ void warp_list_sum(const WarpList& W, const int64_t blk) {
+    const int64_t o = (blk * 256 + threadIdx.x) / LPE;
     const int lane = threadIdx.x % LPE;
-    const bool act = wid < nout;   // whole groups: every lane of a warp reaches the shuffles
+    const bool act = o < W.nout;   // whole groups: every lane of a warp reaches the shuffles
     double acc = 0.0;
     if (act) {
-        const int64_t c0 = cptr[wid], c1 = cptr[wid + 1];
-        for (int64_t cix = c0 + lane; cix < c1; cix += LPE) acc += src[cidx[cix]];
+        const int64_t c0 = W.ptr[o], c1 = W.ptr[o + 1];
+        if (W.idx) for (int64_t c = c0 + lane; c < c1; c += LPE) acc += W.src[W.idx[c]];
+        else for (int64_t c = c0 + lane; c < c1; c += LPE) acc += W.src[c];
     }
 #pragma unroll
     for (int mk = LPE / 2; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
-    if (act && lane == 0) dst[wid] = acc;
+    if (act && lane == 0) W.dst[o] = acc;
 }
 
-// stage 2 of the chunked coarse-level gather: dst[e] = sum of the contiguous partials [pptr[e], pptr[e+1]) in order
-static __global__ void __launch_bounds__(256) gather_warp_contig_kernel(const int64_t nout, const int64_t* __restrict__ pptr,
-                                                                 const double* __restrict__ part, double* __restrict__ dst) {
-    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= nout) return;
-    const int64_t c0 = pptr[wid], c1 = pptr[wid + 1];
-    double acc = 0.0;
-    for (int64_t cix = c0 + lane; cix < c1; cix += 32) acc += part[cix];
-#pragma unroll
-    for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
-    if (lane == 0) dst[wid] = acc;
+static __global__ void __launch_bounds__(256) warp_gather_kernel(const WarpGatherParams P) {
+    const int64_t b = blockIdx.x;
+    if (b < P.a.nblk) {
+        if (P.a.lpe == 8) warp_list_sum<8>(P.a, b); else warp_list_sum<32>(P.a, b);
+    } else if (b < P.a.nblk + P.b.nblk) {
+        if (P.b.lpe == 8) warp_list_sum<8>(P.b, b - P.a.nblk); else warp_list_sum<32>(P.b, b - P.a.nblk);
+    } else {
+        fold_scalars_block(P.part, P.nparts, P.t, P.scal);
+    }
 }
 
 // ---------------------------------------------------------------- small utilities

@@ -355,25 +355,36 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
 
     mgb::GatherParams G = make_gather_params(pl, flags, t, scal ? scal : pl->d_scal_tmp.p, grad, hval);
     if (pl->long_lists) {
-        // coarse levels: few output entries with long lists -> warp per chunk of a list, then warp per entry over
-        // the partial sums
-        auto warp_gather = [&](ChunkedList& ck, int64_t nout, int64_t ncontrib, const int64_t* cptr, const int32_t* cidx, const double* src,
-                               double* dst) {
-            if (ck.nchunks > 0) {
-                mgb::gather_warp_kernel<32><<<(unsigned)((ck.nchunks * 32 + 255) / 256), 256, 0, st>>>(ck.nchunks, ck.kptr.p, cidx, src, ck.part.p);
-                mgb::gather_warp_contig_kernel<<<(unsigned)((nout * 32 + 255) / 256), 256, 0, st>>>(nout, ck.pptr.p, ck.part.p, dst);
-                g_launches += 2;
-            } else if (ncontrib < 48 * nout) {
-                mgb::gather_warp_kernel<8><<<(unsigned)((nout * 8 + 255) / 256), 256, 0, st>>>(nout, cptr, cidx, src, dst);
-                g_launches++;
-            } else {
-                mgb::gather_warp_kernel<32><<<(unsigned)((nout * 32 + 255) / 256), 256, 0, st>>>(nout, cptr, cidx, src, dst);
-                g_launches++;
-            }
+        // coarse levels: few output entries with long lists.  Stage 1: one warp (or 8 lanes) per output, or per chunk
+        // of a chunked list; stage 2 (only with chunked lists): the partial sums of every output.  The scalar fold
+        // rides in the last launch.
+        auto stage1 = [&](ChunkedList& ck, int64_t nout, int64_t ncontrib, const int64_t* cptr, const int32_t* cidx, const double* src,
+                          double* dst) {
+            mgb::WarpList w{};
+            if (ck.nchunks > 0) { w.nout = ck.nchunks; w.ptr = ck.kptr.p; w.idx = cidx; w.src = src; w.dst = ck.part.p; w.lpe = 32; }
+            else { w.nout = nout; w.ptr = cptr; w.idx = cidx; w.src = src; w.dst = dst; w.lpe = (ncontrib < 48 * nout) ? 8 : 32; }
+            w.nblk = (w.nout * w.lpe + 255) / 256;
+            return w;
         };
-        if (G.want_h) warp_gather(pl->ck_h, pl->nnzH, pl->n_hcontrib, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval);
-        if (G.want_g) warp_gather(pl->ck_g, pl->m, pl->n_gcontrib, G.g_cptr, G.g_cidx, G.rel, grad);
-        G.want_h = G.want_g = 0;
+        auto stage2 = [&](ChunkedList& ck, int64_t nout, double* dst) {
+            mgb::WarpList w{};
+            if (ck.nchunks > 0) { w.nout = nout; w.ptr = ck.pptr.p; w.idx = nullptr; w.src = ck.part.p; w.dst = dst; w.lpe = 32; w.nblk = (nout * 32 + 255) / 256; }
+            return w;
+        };
+        mgb::WarpGatherParams W1{}, W2{};
+        if (G.want_h) { W1.a = stage1(pl->ck_h, pl->nnzH, pl->n_hcontrib, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval); W2.a = stage2(pl->ck_h, pl->nnzH, hval); }
+        if (G.want_g) { W1.b = stage1(pl->ck_g, pl->m, pl->n_gcontrib, G.g_cptr, G.g_cidx, G.rel, grad); W2.b = stage2(pl->ck_g, pl->m, grad); }
+        const bool two = W2.a.nblk + W2.b.nblk > 0;
+        mgb::WarpGatherParams& last = two ? W2 : W1;
+        last.part = G.part; last.nparts = G.nparts; last.t = G.t; last.scal = G.scal;
+        mgb::warp_gather_kernel<<<(unsigned)(W1.a.nblk + W1.b.nblk + (two ? 0 : 1)), 256, 0, st>>>(W1);
+        g_launches++;
+        if (two) {
+            mgb::warp_gather_kernel<<<(unsigned)(W2.a.nblk + W2.b.nblk + 1), 256, 0, st>>>(W2);
+            g_launches++;
+        }
+        CUDA_OK(cudaGetLastError());
+        return;
     }
     size_gather_grid(pl, G);
     launch_dependent(mgb::gather_kernel, (unsigned)(G.nblk_h + G.nblk_l + G.nblk_g + 1), 256u, st, G,
