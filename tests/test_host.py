@@ -146,3 +146,22 @@ def test_plan_from_hpc_local_blocks_rejects_bad_ids():
     bad = dict(blocks[1]); bad["col_indices"] = blocks[1]["col_indices"].copy(); bad["col_indices"][0] = 0
     with pytest.raises(capi.MgbError, match="col_indices"):
         capi.Plan.from_local_blocks(None, [blocks[0], bad, blocks[2]], pr["R"], n, pr["x"], pr["w"], pr["idx"], 1.0)
+
+
+def test_sell_chunk_layout_replays_every_list(tmp_path):
+    """the SELL-32-sigma / chunk layout of the CSR path (host C++ in csrc/kernels_csr.cuh) replayed on the CPU exactly
+    as the kernels walk it: unchunked lists bit-identical to the sequential sum, chunked ones to rounding, every
+    output written exactly once, no lane longer than one chunk"""
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    exe = tmp_path / "sell_layout_check"
+    csrc = os.path.join(ROOT, "multigridbarriermpi.jl_b200", "csrc")
+    cmd = [nvcc, "-std=c++17", "-O1", "-gencode", "arch=compute_100a,code=sm_100a", "-I", csrc, "-I", os.path.join(ROOT, "include"),
+           "-o", str(exe), os.path.join(ROOT, "tests", "native", "sell_layout_check.cu"), os.path.join(csrc, "plan_host.cpp")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "bad 0" in run.stdout, run.stdout[-2000:]
