@@ -165,3 +165,21 @@ def test_sell_chunk_layout_replays_every_list(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=300)
     assert run.returncode == 0 and "bad 0" in run.stdout, run.stdout[-2000:]
+
+
+def test_host_sparse_algebra_known_answers(tmp_path):
+    """spgemm / transpose of the symbolic phase (csrc/plan_host.cpp) on the literals of the reference's own test
+    (test/test_basic_ops.jl:27-66: A*B and A'A of a 3x2 and a 2x3 matrix) + the keep-structural-zeros convention"""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    if not gxx:
+        pytest.skip("g++ not available")
+    exe = tmp_path / "host_algebra_check"
+    csrc = os.path.join(ROOT, "multigridbarriermpi.jl_b200", "csrc")
+    res = subprocess.run([gxx, "-std=c++17", "-O1", "-I", csrc, "-I", os.path.join(ROOT, "include"), "-o", str(exe),
+                          os.path.join(ROOT, "tests", "native", "host_algebra_check.cpp"), os.path.join(csrc, "plan_host.cpp")],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
+    assert run.returncode == 0 and "bad 0" in run.stdout, run.stdout[-2000:]

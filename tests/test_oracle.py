@@ -109,3 +109,19 @@ def test_oracle_solves_quick_cases():
     M = O.amg_helper(mgb_b200.fem2d(2), (("u", "dirichlet"), ("s", "full")), O.DEFAULT_D[2])
     Dz = O.apply_D(M.D, sol.z.reshape(-1, order="F"))
     assert np.all(Dz[:, 3] >= (Dz[:, 1] ** 2 + Dz[:, 2] ** 2) ** (2.0 / 2.0) - 1e-12)
+
+
+def test_sparse_product_and_solve_kats():
+    # reference test/test_basic_ops.jl:27-110: literal A (3x2), B (2x3); A*B, A'A and (A'A + 0.01 I) \ ones
+    import scipy.sparse as sp
+    A = sp.csc_matrix(np.array([[1.0, 0.0], [2.0, 3.0], [0.0, 4.0]]))
+    B = sp.csc_matrix(np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]]))
+    assert np.array_equal((A @ B).toarray(), [[1, 2, 3], [14, 19, 24], [16, 20, 24]])
+    AtA = (A.T @ A)
+    assert np.array_equal(AtA.toarray(), [[5, 6], [6, 25]])
+    x = O.solve(AtA + 0.01 * sp.identity(2, format="csc"), np.ones(2))
+    xe = np.linalg.solve(np.array([[5.01, 6.0], [6.0, 25.01]]), np.ones(2))
+    assert np.linalg.norm(x - xe) < 1e-10          # the reference's own tolerance (test_basic_ops.jl:93)
+    # the product's solve seam stand-in gives the same answer
+    from mgb_b200 import solver
+    assert np.linalg.norm(solver.solve(AtA + 0.01 * sp.identity(2, format="csc"), np.ones(2)) - xe) < 1e-10
