@@ -3,14 +3,17 @@
 //   csr_apply_kernel    Dz = Dz0 + E_k s            (apply_D, reference test/test_apply_d.jl:44)
 //   csr_barrier_kernel  w.*F1, w.*F2, objective    (map_rows src:161-170 + amgb_diag src:137-147)
 //   csr_grad_kernel     g = sum_k E_k' (w.*(y1_k + t c_k))   (gather over the stored transpose)
-//   csr_hess_kernel     thread per output entry: numeric-only replay of sum_jk E_j' diag E_k on the
+//   csr_hess_kernel     lane per upper-triangle output entry: numeric-only replay of sum_jk E_j' diag E_k on the
 //                       frozen pattern from precomputed (coefficient, V index) product lists, no atomics
 //                       (test/test_map_rows_compare.jl:102-123 with R folded in: E_k = D_k R)
+// The three sparse steps share one list layout (sliced ELL with sorting windows and chunks, see SellHost) and one
+// replay routine; *_combine_kernel adds the partial sums of the lists that were cut into chunks.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <stdexcept>
 #include <string>
@@ -18,8 +21,6 @@
 
 #include "kernels.cuh"
 #include "plan_host.h"
-
-#include <cstdlib>
 
 namespace mgb {
 
@@ -153,9 +154,7 @@ struct SellDev {
 struct CsrDev {
     int ND = 0, npair = 0;
     int pair_a[36] = {0}, pair_b[36] = {0};
-    int64_t nloc = 0, m = 0, nnzH = 0, nprod = 0, nup = 0;
-    int64_t pad_apply = 0, pad_grad = 0, pad_hess = 0;   // stored contributions incl. padding (diagnostics)
-    int max_row = 0;
+    int64_t nloc = 0, m = 0, nnzH = 0, nup = 0;
     BarrierDesc bar;
     std::vector<void*> owned;  // device allocations
     SellDev E[8];              // apply_D: outputs = local rows of E_k = D_k R, sources = unknowns
@@ -210,26 +209,23 @@ static SellDev sell_upload(CsrDev& d, const SellHost& h, cudaStream_t st, size_t
 static size_t csr_upload(const CsrPlan& cp, const BarrierDesc& bar, CsrDev& d, cudaStream_t st) {
     size_t bytes = 0;
     d.ND = cp.ND; d.nloc = cp.nloc; d.m = cp.m; d.nnzH = (int64_t)cp.h_colidx.size();
-    d.nprod = (int64_t)cp.prod_coef.size(); d.nup = (int64_t)cp.up_t.size(); d.max_row = cp.max_row; d.bar = bar;
+    d.nup = (int64_t)cp.up_t.size(); d.bar = bar;
     d.npair = cp.npair;
     for (int c = 0; c < cp.npair; ++c) { d.pair_a[c] = cp.pair_a[c]; d.pair_b[c] = cp.pair_b[c]; }
     for (int k = 0; k < cp.ND; ++k) {
         SellHost h;
         build_sell(cp.nloc, cp.E[k].ptr.data(), cp.E[k].val.data(), cp.E[k].idx.data(), sell_sigma_apply(), sell_chunk(), h);
         d.E[k] = sell_upload(d, h, st, bytes);
-        d.pad_apply += (int64_t)h.coef.size();
     }
     {
         SellHost h;
         build_sell(cp.m, cp.gt_ptr.data(), cp.gt_coef.data(), cp.gt_src.data(), sell_sigma_grad(), sell_chunk(), h);
         d.G = sell_upload(d, h, st, bytes);
-        d.pad_grad = (int64_t)h.coef.size();
     }
     {
         SellHost h;
         build_sell(d.nup, cp.prod_ptr.data(), cp.prod_coef.data(), cp.prod_v.data(), sell_sigma(), sell_chunk(), h);
         d.Hs = sell_upload(d, h, st, bytes);
-        d.pad_hess = (int64_t)h.coef.size();
         std::vector<int32_t> t(h.code.size(), -1), mm(h.code.size(), -1);
         for (size_t q = 0; q < h.code.size(); ++q) {
             if (h.code[q] >= 0) { t[q] = cp.up_t[(size_t)h.code[q]]; mm[q] = cp.up_m[(size_t)h.code[q]]; }
