@@ -2,12 +2,13 @@
 // (or operator tables other than [u.id; u.d*; s.id]).  One kernel per seam of the reference:
 //   csr_apply_kernel    Dz = Dz0 + E_k s            (apply_D, reference test/test_apply_d.jl:44)
 //   csr_barrier_kernel  w.*F1, w.*F2, objective    (map_rows src:161-170 + amgb_diag src:137-147)
-//   csr_grad_kernel     g = sum_k E_k' (w.*(y1_k + t c_k))   (gather over the stored transpose)
-//   csr_hess_kernel     lane per upper-triangle output entry: numeric-only replay of sum_jk E_j' diag E_k on the
-//                       frozen pattern from precomputed (coefficient, V index) product lists, no atomics
-//                       (test/test_map_rows_compare.jl:102-123 with R folded in: E_k = D_k R)
+//   csr_replay_kernel   gradient g = sum_k E_k' (w.*(y1_k + t c_k)) (gather over the stored transpose) and, in the
+//                       same launch, the Hessian: lane per upper-triangle output entry, numeric-only replay of
+//                       sum_jk E_j' diag E_k on the frozen pattern from precomputed (coefficient, V index) product
+//                       lists, no atomics (test/test_map_rows_compare.jl:102-123 with R folded in: E_k = D_k R)
+//   csr_finish_kernel   partial sums of the lists that were cut into chunks + the scalar fold
 // The three sparse steps share one list layout (sliced ELL with sorting windows and chunks, see SellHost) and one
-// replay routine; *_combine_kernel adds the partial sums of the lists that were cut into chunks.
+// replay routine.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -285,6 +286,7 @@ struct CsrApplyParams {
 
 // apply_D: blockIdx.y = operator, one slot per local row or chunk of a row
 __global__ void __launch_bounds__(256) csr_apply_kernel(const __grid_constant__ CsrApplyParams P) {
+    pdl_launch_dependents();
     const int k = blockIdx.y;
     const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (slot >= P.E[k].nslot) return;
@@ -351,6 +353,8 @@ __device__ __forceinline__ double cone_grad_pick(const BarrierOut& bo, const dou
 // output column (w.*F1: ND columns, w.*F2: one column per coupled operator pair) is stored exactly once.
 template <int NCONES>
 __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant__ CsrBarrierParams P) {
+    pdl_launch_dependents();   // the replay kernel may stage its list metadata while this grid drains
+    pdl_wait_primary();        // Dz comes from the apply kernel
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const bool act = i < P.n;
     const int64_t n = P.n;
@@ -426,79 +430,110 @@ __global__ void __launch_bounds__(256) csr_barrier_kernel(const __grid_constant_
     }
 }
 
-// g[a] = sum_r coef[r] * gy[src[r]]: the transposed operators merged into one list per unknown
-// (gather, no atomics, fixed order)
-__global__ void __launch_bounds__(256) csr_grad_kernel(const __grid_constant__ SellDev L, const double* __restrict__ gy,
-                                                       double* __restrict__ grad) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= L.nslot) return;
-    const double acc = sell_replay(L, gy, slot);
-    const int32_t a = __ldg(&L.code[slot]);
-    if (a >= 0) grad[a] = acc;
-    else if (a <= -2) L.part[-(a + 2)] = acc;
-}
-__global__ void __launch_bounds__(256) csr_grad_combine_kernel(const __grid_constant__ SellDev L, double* __restrict__ grad) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= L.ncomb) return;
-    grad[__ldg(&L.comb_out[q])] = sell_combine(L, q);
-}
+// Gradient and Hessian replays share one launch (both depend on the barrier kernel only): the gradient blocks come
+// first - their lists are longer - and their latency hides inside the Hessian replay, which is most of the step.
+//   gradient: g[a] = sum_r coef[r] * gy[src[r]], the transposed operators merged into one list per unknown
+//             (gather, no atomics, fixed order)
+//   Hessian : numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry (or chunk
+//             of one); it sums its precomputed products coef * V in list order (no atomics, bit-reproducible) and
+//             stores the value at (a,b) and at the mirror (b,a) - R'HR is symmetric, so half of the product lists
+//             never has to be read.  coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
+struct CsrReplayParams {
+    SellDev G;
+    const double* gy;
+    double* grad;
+    int64_t nblk_g;       // 0: no gradient
+    SellDev H;
+    const int32_t* up_t;
+    const int32_t* up_m;
+    const double* V;
+    double* hval;
+};
 
-// numeric-only triple product on the frozen pattern: one lane per UPPER-triangle output entry (or chunk of one); it
-// sums its precomputed products coef * V in list order (no atomics, bit-reproducible) and stores the value at (a,b)
-// and at the mirror (b,a) - R'HR is symmetric, so half of the product lists never has to be read.
-// coef = E_ka[i,a]*E_kb[i,b] is level data, V = w.*F2 changes every Newton step.
-__global__ void __launch_bounds__(256) csr_hess_kernel(const __grid_constant__ SellDev L, const int32_t* __restrict__ up_t,
-                                                       const int32_t* __restrict__ up_m, const double* __restrict__ V,
-                                                       double* __restrict__ hval) {
-    const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (slot >= L.nslot) return;
-    const int32_t t = __ldg(&up_t[slot]), tm = __ldg(&up_m[slot]);
-    const double acc = sell_replay(L, V, slot);
+__global__ void __launch_bounds__(256) csr_replay_kernel(const __grid_constant__ CsrReplayParams P) {
+    // programmatic dependent launch: this grid may start while the barrier kernel drains; everything loaded before
+    // pdl_wait_primary() is level data (plan arrays), gy / V are read after it.  Every thread reaches the wait.
+    pdl_launch_dependents();
+    if ((int64_t)blockIdx.x < P.nblk_g) {
+        const int64_t slot = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+        const bool act = slot < P.G.nslot;
+        const int32_t a = act ? __ldg(&P.G.code[slot]) : -1;
+        pdl_wait_primary();
+        if (!act) return;
+        const double acc = sell_replay(P.G, P.gy, slot);
+        if (a >= 0) P.grad[a] = acc;
+        else if (a <= -2) P.G.part[-(a + 2)] = acc;
+        return;
+    }
+    const int64_t slot = ((int64_t)blockIdx.x - P.nblk_g) * blockDim.x + threadIdx.x;
+    const bool act = slot < P.H.nslot;
+    const int32_t t = act ? __ldg(&P.up_t[slot]) : -1, tm = act ? __ldg(&P.up_m[slot]) : -1;
+    pdl_wait_primary();
+    if (!act) return;
+    const double acc = sell_replay(P.H, P.V, slot);
     if (t >= 0) {
-        hval[t] = acc;
-        if (tm >= 0) hval[tm] = acc;
-    } else if (t <= -2) L.part[-(t + 2)] = acc;
-}
-__global__ void __launch_bounds__(256) csr_hess_combine_kernel(const __grid_constant__ SellDev L, const int32_t* __restrict__ nat_t,
-                                                               const int32_t* __restrict__ nat_m, double* __restrict__ hval) {
-    const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= L.ncomb) return;
-    const int32_t e = __ldg(&L.comb_out[q]);
-    const int32_t t = __ldg(&nat_t[e]), tm = __ldg(&nat_m[e]);
-    const double acc = sell_combine(L, q);
-    hval[t] = acc;
-    if (tm >= 0) hval[tm] = acc;
+        P.hval[t] = acc;
+        if (tm >= 0) P.hval[tm] = acc;
+    } else if (t <= -2) P.H.part[-(t + 2)] = acc;
 }
 
-static __global__ void __launch_bounds__(256) scalar_finish_kernel(const double* __restrict__ part, int64_t nparts, double t,
-                                                            double* __restrict__ scal) {
-    __shared__ double sh[3][256];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int64_t r = threadIdx.x; r < nparts; r += blockDim.x) {
-        s0 += part[r * 4 + 0];
-        s1 += part[r * 4 + 1];
-        s2 += part[r * 4 + 2];
-    }
-    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
-    __syncthreads();
-    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
-        if ((int)threadIdx.x < st) {
-            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
-            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
-            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        scal[0] = sh[0][0] + t * sh[1][0];
-        scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
-        scal[2] = sh[1][0];
-        scal[3] = sh[2][0];
+// Last launch of an assembly: partial sums of the chunked gradient lists, of the chunked Hessian lists, and the
+// fold of the per-block scalars (last block) - one launch instead of three small ones.
+struct CsrFinishParams {
+    SellDev G;
+    double* grad;
+    int64_t nblk_g;
+    SellDev H;
+    const int32_t* nat_t;
+    const int32_t* nat_m;
+    double* hval;
+    int64_t nblk_h;
+    const double* part;
+    int64_t nparts;
+    double t;
+    double* scal;
+};
+
+__global__ void __launch_bounds__(256) csr_finish_kernel(const __grid_constant__ CsrFinishParams P) {
+    pdl_wait_primary();   // partial sums and scalar partials come from the replay / barrier kernels
+    const int64_t b = blockIdx.x;
+    if (b < P.nblk_g) {
+        const int64_t q = b * blockDim.x + threadIdx.x;
+        if (q < P.G.ncomb) P.grad[__ldg(&P.G.comb_out[q])] = sell_combine(P.G, q);
+    } else if (b < P.nblk_g + P.nblk_h) {
+        const int64_t q = (b - P.nblk_g) * blockDim.x + threadIdx.x;
+        if (q >= P.H.ncomb) return;
+        const int32_t e = __ldg(&P.H.comb_out[q]);
+        const int32_t t = __ldg(&P.nat_t[e]), tm = __ldg(&P.nat_m[e]);
+        const double acc = sell_combine(P.H, q);
+        P.hval[t] = acc;
+        if (tm >= 0) P.hval[tm] = acc;
+    } else {
+        fold_scalars_block(P.part, P.nparts, P.t, P.scal);
     }
 }
 
 static void csr_check(cudaError_t e, const char* what) {
     if (e != cudaSuccess) throw std::runtime_error(std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+// launch as a programmatic dependent of the previous kernel in the stream (its blocks may be scheduled while the
+// previous grid drains and block at griddepcontrol.wait); plain launch when the attribute is refused or MGB_NO_PDL is set
+template <class Params>
+static void csr_launch(void (*kernel)(Params), unsigned grid, cudaStream_t st, const Params& params, bool pdl) {
+    static bool pdl_ok = std::getenv("MGB_NO_PDL") == nullptr;
+    if (pdl && pdl_ok) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        if (cudaLaunchKernelEx(&cfg, kernel, params) == cudaSuccess) return;
+        cudaGetLastError();
+        pdl_ok = false;
+    }
+    kernel<<<grid, 256, 0, st>>>(params);
 }
 
 static unsigned sell_grid(int64_t count) { return (unsigned)((count + 255) / 256); }
@@ -544,28 +579,27 @@ static int csr_assemble(CsrDev& d, const double* w, const double* s, const doubl
         }
         P.n = n; P.p = d.bar.p; P.t = t; P.Dz = Dz; P.c = c; P.w = w; P.gy = d.gy; P.V = d.V; P.part = d.part;
         P.want_f = (flags & 1) ? 1 : 0; P.want_g = (flags & 2) ? 1 : 0; P.want_h = (flags & 4) ? 1 : 0;
-        if (P.nq2 >= 0) csr_barrier_kernel<2><<<(unsigned)d.nblk, 256, 0, st>>>(P);
-        else csr_barrier_kernel<1><<<(unsigned)d.nblk, 256, 0, st>>>(P);
+        if (P.nq2 >= 0) csr_launch(csr_barrier_kernel<2>, (unsigned)d.nblk, st, P, true);
+        else csr_launch(csr_barrier_kernel<1>, (unsigned)d.nblk, st, P, true);
         ++launches;
     }
-    if ((flags & 2) && d.G.nslot > 0) {
-        csr_grad_kernel<<<sell_grid(d.G.nslot), 256, 0, st>>>(d.G, d.gy, grad);
-        if (d.G.ncomb > 0) {
-            csr_grad_combine_kernel<<<sell_grid(d.G.ncomb), 256, 0, st>>>(d.G, grad);
-            ++launches;
-        }
+    const bool want_g = (flags & 2) && d.G.nslot > 0, want_h = (flags & 4) && d.nup > 0;
+    if (want_g || want_h) {
+        CsrReplayParams P{};
+        if (want_g) { P.G = d.G; P.gy = d.gy; P.grad = grad; P.nblk_g = sell_grid(d.G.nslot); }
+        if (want_h) { P.H = d.Hs; P.up_t = d.up_t; P.up_m = d.up_m; P.V = d.V; P.hval = hval; }
+        const int64_t nblk_h = want_h ? sell_grid(d.Hs.nslot) : 0;
+        csr_launch(csr_replay_kernel, (unsigned)(P.nblk_g + nblk_h), st, P, true);
         ++launches;
     }
-    if ((flags & 4) && d.nup > 0) {
-        csr_hess_kernel<<<sell_grid(d.Hs.nslot), 256, 0, st>>>(d.Hs, d.up_t, d.up_m, d.V, hval);
-        if (d.Hs.ncomb > 0) {
-            csr_hess_combine_kernel<<<sell_grid(d.Hs.ncomb), 256, 0, st>>>(d.Hs, d.nat_t, d.nat_m, hval);
-            ++launches;
-        }
+    {
+        CsrFinishParams P{};
+        if (want_g && d.G.ncomb > 0) { P.G = d.G; P.grad = grad; P.nblk_g = sell_grid(d.G.ncomb); }
+        if (want_h && d.Hs.ncomb > 0) { P.H = d.Hs; P.nat_t = d.nat_t; P.nat_m = d.nat_m; P.hval = hval; P.nblk_h = sell_grid(d.Hs.ncomb); }
+        P.part = d.part; P.nparts = d.nblk; P.t = t; P.scal = scal;
+        csr_launch(csr_finish_kernel, (unsigned)(P.nblk_g + P.nblk_h + 1), st, P, true);
         ++launches;
     }
-    scalar_finish_kernel<<<1, 256, 0, st>>>(d.part, d.nblk, t, scal);
-    ++launches;
     csr_check(cudaGetLastError(), "csr_assemble launch");
     return launches;
 }
