@@ -775,6 +775,8 @@ __device__ __forceinline__ void warp_list_sum(const WarpList& W, const int64_t b
 }
 
 static __global__ void __launch_bounds__(256) warp_gather_kernel(const WarpGatherParams P) {
+    pdl_launch_dependents();   // a second stage may be scheduled while this grid drains
+    pdl_wait_primary();        // records / partial sums of the previous kernel (no-op without the PDL attribute)
     const int64_t b = blockIdx.x;
     if (b < P.a.nblk) {
         if (P.a.lpe == 8) warp_list_sum<8>(P.a, b); else warp_list_sum<32>(P.a, b);

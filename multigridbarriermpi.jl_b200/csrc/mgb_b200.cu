@@ -377,10 +377,10 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         const bool two = W2.a.nblk + W2.b.nblk > 0;
         mgb::WarpGatherParams& last = two ? W2 : W1;
         last.part = G.part; last.nparts = G.nparts; last.t = G.t; last.scal = G.scal;
-        mgb::warp_gather_kernel<<<(unsigned)(W1.a.nblk + W1.b.nblk + (two ? 0 : 1)), 256, 0, st>>>(W1);
+        launch_dependent(mgb::warp_gather_kernel, (unsigned)(W1.a.nblk + W1.b.nblk + (two ? 0 : 1)), 256u, st, W1, /*allow_pdl=*/mid == nullptr);
         g_launches++;
         if (two) {
-            mgb::warp_gather_kernel<<<(unsigned)(W2.a.nblk + W2.b.nblk + 1), 256, 0, st>>>(W2);
+            launch_dependent(mgb::warp_gather_kernel, (unsigned)(W2.a.nblk + W2.b.nblk + 1), 256u, st, W2, /*allow_pdl=*/true);
             g_launches++;
         }
         CUDA_OK(cudaGetLastError());
