@@ -14,7 +14,9 @@ import mgb_b200  # noqa: E402
 from helpers import problem, oracle_eval  # noqa: E402
 
 CASES = [("fem1d", 3, 1.0, False, None, 1.3), ("fem2d", 2, 2.0, False, None, 0.7), ("fem2d", 3, 1.0, False, None, 0.7),
-         ("fem2d", 3, 1.5, False, 1, 2.0), ("fem2d", 2, 1.0, True, None, 0.5)]
+         ("fem2d", 3, 1.5, False, 1, 2.0), ("fem2d", 2, 1.0, True, None, 0.5),
+         # 64-node hexahedra (fem3d k=3, operator table u.id u.dx u.dy u.dz s.id): the CSR path, fine and coarse level
+         ("fem3d", 2, 1.0, False, None, 0.9), ("fem3d", 2, 1.5, False, 0, 0.9)]
 
 
 def name(gen, L, p, slack, level, t):
@@ -23,6 +25,8 @@ def name(gen, L, p, slack, level, t):
 
 if __name__ == "__main__":
     for gen, L, p, slack, level, t in CASES:
+        if os.path.exists(os.path.join(HERE, name(gen, L, p, slack, level, t))) and "--force" not in sys.argv:
+            continue   # committed fixtures stay as they are
         pr = problem(getattr(mgb_b200, gen)(L), p=p, slack=slack, level=level)
         f0, g, H = oracle_eval(pr, t)
         H.sort_indices()
