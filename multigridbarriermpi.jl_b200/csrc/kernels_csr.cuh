@@ -326,27 +326,35 @@ struct CsrBarrierParams {
     int want_f, want_g, want_h;
 };
 
-// entry (la, lb) of the 5x5 local Hessian of one cone over (q0, q1, q2, s, slack); la, lb are warp-uniform,
-// every index below is a compile-time constant, so the barrier derivatives stay in registers
-__device__ __forceinline__ double cone_hess_pick(const BarrierOut& bo, const double tt, const int la, const int lb) {
-    double v = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int b = 0; b < 3; ++b) v = (la == a && lb == b) ? bo.Hqq[a][b] : v;
-        v = ((la == a && lb >= 3) || (lb == a && la >= 3)) ? bo.Hqs[a] : v;
+// entry (la, lb) of the 5x5 local Hessian of one cone over (q0, q1, q2, s, slack); la, lb are warp-uniform (they come
+// from the kernel parameters), so the switch is a short tree of uniform branches and the barrier derivatives stay
+// in registers (a chain of selects over all 25 combinations made this kernel instruction bound)
+__device__ __forceinline__ double cone_hess_pick(const BarrierOut& bo, const double tt, int la, int lb) {
+    if (la > lb) { const int x = la; la = lb; lb = x; }
+    switch (la * 5 + lb) {
+        case 0: return bo.Hqq[0][0];
+        case 1: return bo.Hqq[0][1];
+        case 2: return bo.Hqq[0][2];
+        case 3: case 4: return bo.Hqs[0];
+        case 6: return bo.Hqq[1][1];
+        case 7: return bo.Hqq[1][2];
+        case 8: case 9: return bo.Hqs[1];
+        case 12: return bo.Hqq[2][2];
+        case 13: case 14: return bo.Hqs[2];
+        case 18: case 19: return bo.Hss;
+        case 24: return bo.Hss + tt;
+        default: return 0.0;
     }
-    v = (la >= 3 && lb >= 3) ? bo.Hss : v;
-    v = (la == 4 && lb == 4) ? bo.Hss + tt : v;
-    return v;
 }
 __device__ __forceinline__ double cone_grad_pick(const BarrierOut& bo, const double itau, const int la) {
-    double v = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) v = (la == a) ? bo.gq[a] : v;
-    v = (la == 3) ? bo.gs : v;
-    v = (la == 4) ? bo.gs - itau : v;
-    return v;
+    switch (la) {
+        case 0: return bo.gq[0];
+        case 1: return bo.gq[1];
+        case 2: return bo.gq[2];
+        case 3: return bo.gs;
+        case 4: return bo.gs - itau;
+        default: return 0.0;
+    }
 }
 
 // map_rows of F / F1 / F2 over the Dz rows for one or two cones: everything of a point stays in registers, every
