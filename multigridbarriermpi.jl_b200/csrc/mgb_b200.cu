@@ -426,7 +426,11 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
             {
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
-                pl->long_lists = avg > 12.0;
+                // lists averaging more than six contributions go to the lanes-per-output gather (fem1d L=16 level 12,
+                // 10.7 per entry: 36.5 -> 21.5 us; at 5.4 per entry the thread-per-entry gather still wins: 69 vs 105 us;
+                // MGB_LONG_AVG overrides for tuning runs)
+                const char* ev = getenv("MGB_LONG_AVG");
+                pl->long_lists = avg > (ev ? atof(ev) : 6.0);
             }
             if (patch_requested(force_flags, ep)) {
                 // patch-fused path builds its own lists below
