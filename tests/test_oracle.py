@@ -125,3 +125,48 @@ def test_sparse_product_and_solve_kats():
     # the product's solve seam stand-in gives the same answer
     from mgb_b200 import solver
     assert np.linalg.norm(solver.solve(AtA + 0.01 * sp.identity(2, format="csc"), np.ones(2)) - xe) < 1e-10
+
+
+@pytest.mark.parametrize("p", [1.0, 1.3, 2.0, 2.7])
+@pytest.mark.parametrize("variant", ["main3d", "main2d", "slack", "two_cones"])
+def test_barrier_derivatives_match_automatic_differentiation(p, variant):
+    """Upstream obtains F1 / F2 by automatic differentiation of the pointwise F (ForwardDiff); the oracle and the
+    CUDA kernels use hand-derived formulas.  Pin them to autodiff of the same F (torch.autograd, float64) to
+    rounding - a check by the reference's own method rather than by finite differences."""
+    import torch
+    rng = np.random.default_rng(7)
+    if variant == "main3d":
+        nD, sets = 5, [dict(idx=[1, 2, 3, 4], p=p, slack=False)]
+    elif variant == "main2d":
+        nD, sets = 4, [dict(idx=[1, 2, 3], p=p, slack=False)]
+    elif variant == "slack":
+        nD, sets = 5, [dict(idx=[1, 2, 3], p=p, slack=True)]
+    else:  # parabolic: {s1 >= u^2} (p = 2) and {s2 >= |grad u|^p} on [u.id u.dx u.dy s1.id s2.id]
+        nD, sets = 5, [dict(idx=[1, 2, 4], p=p, slack=False), dict(idx=[0, 3], p=2.0, slack=False)]
+    Q = O.Intersection([O.EuclidianPower(**kw) for kw in sets])
+    y = rng.normal(size=(8, nD)) * 0.3
+    for kw in sets:
+        y[:, kw["idx"][-1]] = 2.5 + rng.uniform(size=8)         # s well inside the cone
+    if variant == "slack":
+        y[:, -1] = rng.uniform(-0.5, 0.5, size=8)
+
+    def F_torch(row):
+        tot = row.new_zeros(())
+        for kw in sets:
+            q = row[kw["idx"][:-1]]
+            s = row[kw["idx"][-1]] + (row[-1] if kw["slack"] else 0.0)
+            a = 2.0 / kw["p"]
+            tot = tot - torch.log(s ** a - (q * q).sum()) - O._mu(kw["p"]) * torch.log(s)
+            if kw["slack"]:
+                tot = tot - torch.log(1.0 + row[-1])
+        return tot
+
+    g, H = Q.F1(None, y), Q.F2(None, y)
+    for r in range(y.shape[0]):
+        row = torch.tensor(y[r], dtype=torch.float64, requires_grad=True)
+        f_ad = float(F_torch(row).detach())
+        assert abs(f_ad - float(Q.F(None, y[r:r + 1])[0])) <= 1e-13 * max(1.0, abs(f_ad))
+        g_ad = torch.autograd.functional.jacobian(F_torch, row).numpy()
+        H_ad = torch.autograd.functional.hessian(F_torch, row).numpy()
+        assert np.abs(g[r] - g_ad).max() <= 1e-12 * max(1.0, np.abs(g_ad).max())
+        assert np.abs(H[r] - H_ad).max() <= 1e-11 * max(1.0, np.abs(H_ad).max())
