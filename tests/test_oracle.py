@@ -170,3 +170,36 @@ def test_barrier_derivatives_match_automatic_differentiation(p, variant):
         H_ad = torch.autograd.functional.hessian(F_torch, row).numpy()
         assert np.abs(g[r] - g_ad).max() <= 1e-12 * max(1.0, np.abs(g_ad).max())
         assert np.abs(H[r] - H_ad).max() <= 1e-11 * max(1.0, np.abs(H_ad).max())
+
+
+@pytest.mark.parametrize("gen,L,p,level", [("fem2d", 2, 1.0, None), ("fem2d", 2, 1.5, 0), ("fem1d", 3, 2.0, None), ("fem3d", 1, 1.0, None)])
+def test_assembly_is_the_autodiff_gradient_and_hessian_of_the_objective(gen, L, p, level):
+    """The whole assembly (apply_D, barrier map, w-scaling, the Hessian double loop, R'.R) against automatic
+    differentiation of the objective s -> f0(s) written densely in torch float64: g = grad f0 and R'HR = hess f0 to
+    rounding.  Exact (no finite-difference step), and independent of the sparse algebra the oracle uses."""
+    import torch
+    from helpers import problem
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom, p=p, level=level, pert=1e-2)
+    Q = O.EuclidianPower(idx=pr["idx"], p=pr["p"])
+    t = 0.7
+    args = (pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
+    g, H = O.f1(pr["s"], *args), O.f2(pr["s"], *args).toarray()
+    T = lambda a: torch.tensor(np.asarray(a), dtype=torch.float64)
+    Dd = [T(Dk.toarray()) for Dk in pr["D"]]
+    Rd, z0, w, c = T(pr["R"].toarray()), T(pr["z0"]), T(pr["w"]), T(t * pr["c"])
+    idx, a, mu = pr["idx"], 2.0 / p, O._mu(p)
+
+    def f0_torch(s):
+        z = z0 + Rd @ s
+        Dz = torch.stack([Dk @ z for Dk in Dd], dim=1)
+        q, ss = Dz[:, idx[:-1]], Dz[:, idx[-1]]
+        F = -torch.log(ss ** a - (q * q).sum(dim=1)) - mu * torch.log(ss)
+        return (w * F).sum() + (w[:, None] * c * Dz).sum()
+
+    s = T(pr["s"]).requires_grad_(True)
+    assert abs(float(f0_torch(s).detach()) - O.f0(pr["s"], *args)) <= 1e-12 * abs(O.f0(pr["s"], *args))
+    g_ad = torch.autograd.functional.jacobian(f0_torch, s).numpy()
+    H_ad = torch.autograd.functional.hessian(f0_torch, s).numpy()
+    assert np.abs(g - g_ad).max() <= 1e-11 * np.abs(g_ad).max()
+    assert np.abs(H - H_ad).max() <= 1e-11 * np.abs(H_ad).max()
