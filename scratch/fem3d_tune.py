@@ -16,10 +16,9 @@ cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
 s_d = torch.from_numpy(pr["s"]).to(dev); Dz0_d = cm(Dz0); c_d = cm(pr["c"])
 ref = None
 rows = []
-G = 2**31 - 1
-variants = [(G, 16, 1), (G, 8, 1), (G, 12, 1), (G, 24, 1), (16384, 16, 1), (G, 16, 2), (G, 8, 2)]
-for sigma, stage, sg in variants:
-    os.environ["MGB_SELL_SIGMA"] = str(sigma); os.environ["MGB_SELL_CHUNK"] = str(stage); os.environ["MGB_SELL_K"] = str(sg)
+variants = [(16384, 16, 1024), (16384, 8, 1024), (16384, 32, 1024), (4096, 16, 1024), (65536, 16, 1024), (16384, 16, 256), (16384, 1000000, 1024)]
+for sigma, stage, sg in variants:   # (Hessian sorting window, chunk length, gradient sorting window)
+    os.environ["MGB_SELL_SIGMA"] = str(sigma); os.environ["MGB_SELL_CHUNK"] = str(stage); os.environ["MGB_SELL_SIGMA_GRAD"] = str(sg)
     t0 = time.time()
     plan = capi.Plan(ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], pr["p"])
     tp = time.time() - t0
@@ -32,7 +31,7 @@ for sigma, stage, sg in variants:
     if ref is None:
         ref = cur
     same = all(np.allclose(a, b, rtol=1e-13, atol=1e-13 * np.abs(b).max()) for a, b in zip(cur, ref))
-    row = dict(L=L, sigma=sigma, chunk=stage, K=sg, ms=ms, ms_f0=ms0, plan_s=tp, identical=bool(same), finite=bool(np.isfinite(cur[0]).all()),
+    row = dict(L=L, sigma=sigma, chunk=stage, sigma_grad=sg, ms=ms, ms_f0=ms0, plan_s=tp, identical=bool(same), finite=bool(np.isfinite(cur[0]).all()),
                stored=plan.info["hess_stored"], contribs=plan.info["hess_contribs"], alg_bytes=plan.info["alg_bytes"],
                frac=plan.info["alg_bytes"] / (ms * 1e-3) / 1e9 / 6545.6)
     print(json.dumps(row), flush=True)
