@@ -143,6 +143,38 @@ class HPCSparseMatrix:
     def nnz(self):
         return self.host.nnz
 
+    # ---- the sparse algebra the reference's f2 loop is written in (HPCSparseArrays methods `*`, `'`, `+`:
+    # test/test_map_rows_compare.jl:102-123).  Host-side structural operations with Julia's conventions; the
+    # hot path never calls them (it replays the frozen pattern on the device) - they exist so that code written
+    # against the reference's operator surface runs, and so that the conventions are stated in one place.
+    def __matmul__(self, other):
+        """A * B keeps structural zeros (Julia spmatmul does not drop cancelled entries)."""
+        if isinstance(other, HPCSparseMatrix):
+            a, b = self.host.tocsr(), other.host.tocsr()
+            pat = (sp.csr_matrix((np.ones(a.nnz), a.indices, a.indptr), shape=a.shape) @
+                   sp.csr_matrix((np.ones(b.nnz), b.indices, b.indptr), shape=b.shape)).tocsr()   # structural pattern
+            val = (a @ b).tocsr()              # scipy prunes cancelled entries: put the values on the structural pattern
+            pat.sort_indices()
+            rows = np.repeat(np.arange(pat.shape[0]), np.diff(pat.indptr))
+            data = np.asarray(val[rows, pat.indices]).ravel() if pat.nnz else np.zeros(0)
+            out = sp.csr_matrix((data, pat.indices, pat.indptr), shape=pat.shape)
+            return HPCSparseMatrix(out, self.backend, row_partition=self.row_partition, Ti=self.Ti)
+        return NotImplemented
+
+    def __add__(self, other):
+        """A + B drops entries that cancel to exactly 0.0, like Julia's SparseMatrixCSC `+` - which makes the
+        structure of a sum value-dependent (reference test/test_matrix_addition.jl:22-24)."""
+        if isinstance(other, HPCSparseMatrix):
+            c = (self.host + other.host).tocsr()
+            c.eliminate_zeros()
+            return HPCSparseMatrix(c, self.backend, row_partition=self.row_partition, Ti=self.Ti)
+        return NotImplemented
+
+    @property
+    def T(self):
+        """A' (reference test/test_transpose_only.jl): rows of the transpose are partitioned like A's columns"""
+        return HPCSparseMatrix(self.host.T.tocsr(), self.backend, row_partition=self.col_partition, Ti=self.Ti)
+
     def local_storage(self) -> dict:
         """This rank's block in the reference's own field layout (constructor order
         src/MultiGridBarrierMPI.jl:216-221; older names test/test_dump_matrices.jl:62-71): the local rows stored

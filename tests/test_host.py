@@ -183,3 +183,39 @@ def test_host_sparse_algebra_known_answers(tmp_path):
     assert res.returncode == 0, res.stderr[-2000:]
     run = subprocess.run([str(exe)], capture_output=True, text=True, timeout=60)
     assert run.returncode == 0 and "bad 0" in run.stdout, run.stdout[-2000:]
+
+
+def test_hpc_sparse_algebra_conventions():
+    """`*`, `'`, `+` on the HPCSparseMatrix mirror with the reference's conventions: the literals of
+    test/test_basic_ops.jl:27-66, structural zeros kept by products, exact cancellations dropped by sums
+    (test/test_matrix_addition.jl:22-24), and the f2 accumulation of test/test_matrix_addition.jl:38-80 equal to the oracle"""
+    from mgb_b200.hpc import Backend, HPCSparseMatrix
+    be = Backend(device="cpu")
+    A = HPCSparseMatrix(sp.csr_matrix(np.array([[1.0, 0.0], [2.0, 3.0], [0.0, 4.0]])), be)
+    B = HPCSparseMatrix(sp.csr_matrix(np.array([[1.0, 2.0, 3.0], [4.0, 5.0, 6.0]])), be)
+    assert np.array_equal((A @ B).host.toarray(), [[1, 2, 3], [14, 19, 24], [16, 20, 24]])
+    assert np.array_equal((A.T @ A).host.toarray(), [[5, 6], [6, 25]])
+    # a product keeps the structural entry of a cancellation, a sum drops it
+    R1 = HPCSparseMatrix(sp.csr_matrix(np.array([[1.0, -1.0]])), be)
+    C1 = HPCSparseMatrix(sp.csr_matrix(np.array([[1.0], [1.0]])), be)
+    assert (R1 @ C1).host.nnz == 1 and (R1 @ C1).host.data[0] == 0.0
+    P = HPCSparseMatrix(sp.csr_matrix(np.array([[1.0, 2.0]])), be)
+    M = HPCSparseMatrix(sp.csr_matrix(np.array([[-1.0, 2.0]])), be)
+    assert (P + M).host.nnz == 1 and (P + M).host.toarray().tolist() == [[0.0, 4.0]]
+    # the f2 accumulation written with these operators = the oracle's Hessian (fem1d L=2, literal weights)
+    g = mgb_b200.fem1d(2)
+    n = g.x.shape[0]
+    D = [HPCSparseMatrix(g.operators["dx"], be), HPCSparseMatrix(g.operators["id"], be)]
+    y = np.zeros((n, 4)); y[:, 0] = 0.5; y[:, 1] = 0.1; y[:, 2] = 0.1; y[:, 3] = 0.3
+    diag = lambda v: HPCSparseMatrix(sp.diags(g.w * v).tocsr(), be)
+    ret = None
+    for j in range(2):
+        bar = D[j].T @ diag(y[:, j * 2 + j]) @ D[j]
+        ret = bar if ret is None else ret + bar
+        for k in range(j):
+            t1 = D[j].T @ diag(y[:, j * 2 + k]) @ D[k]
+            ret = ret + t1 + t1.T
+    Ho = O.hessian_fine(y, g.w, [g.operators["dx"], g.operators["id"]])
+    assert abs(ret.host - Ho).max() < 1e-13
+    Hd = ret.host.copy(); Hd.eliminate_zeros(); Hoz = Ho.copy(); Hoz.eliminate_zeros()
+    assert Hd.nnz == Hoz.nnz
