@@ -87,11 +87,17 @@ struct BarrierOut {
     bool feasible;
 };
 
+// mu(p): weight of the extra -log s term.  [U] (upstream convex_Euclidian_power is not vendored): 0 for p = 1
+// (-log(s^2 - |q|^2), the Lorentz-cone barrier) and for p = 2 (-log(s - |q|^2), the paraboloid epigraph - both are
+// self-concordant as they stand), 1 for 1 < p < 2, 2 for p > 2.  The ONE place the kernels define it; the oracle's
+// _mu (oracle/mgb_oracle.py) is its twin.
+__device__ __forceinline__ double barrier_mu(double p) { return (p == 1.0 || p == 2.0) ? 0.0 : ((p < 2.0) ? 1.0 : 2.0); }
+
 // Euclidian power cone barrier on (q_0..q_{D-1}, s): F = -log(s^a - |q|^2) - mu log s, a = 2/p.
 template <int D, bool WANT_F, bool WANT_D>
 __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, double p, BarrierOut& o) {
     const double a = 2.0 / p;
-    const double mu = (p == 1.0) ? 0.0 : ((p < 2.0) ? 1.0 : 2.0);
+    const double mu = barrier_mu(p);
     double sa, sa1, sa2;  // s^a, s^(a-1), s^(a-2)
     const double is = 1.0 / s;
     if (p == 1.0) { sa = s * s; sa1 = s; sa2 = 1.0; }

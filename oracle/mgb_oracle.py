@@ -63,7 +63,11 @@ def map_rows(f: Callable, *args):
 # --------------------------------------------------------------------------------------
 
 def _mu(p: float) -> float:
-    return 0.0 if p == 1.0 else (1.0 if p < 2.0 else 2.0)
+    """weight of the extra -log(s) term of the power-cone barrier.  [U]: upstream ``convex_Euclidian_power`` is not
+    under /root/reference.  p = 1 (-log(s^2 - |q|^2), Lorentz cone) and p = 2 (-log(s - |q|^2), paraboloid epigraph)
+    are self-concordant without it -> 0; 1 < p < 2 -> 1; p > 2 -> 2.  (Round 1 used 2 at p = 2; changed on review:
+    the p = 2 set s - |q|^2 > 0 already implies s > 0.)"""
+    return 0.0 if (p == 1.0 or p == 2.0) else (1.0 if p < 2.0 else 2.0)
 
 
 @dataclass

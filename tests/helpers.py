@@ -52,11 +52,11 @@ def rel(a, b):
     return np.linalg.norm((np.asarray(a) - np.asarray(b)).ravel()) / (na if na > 0 else 1.0)
 
 
-def check_against_oracle(ctx, geom, p, t, slack=False, level=None, force_path=0, tol=1e-12):
+def check_against_oracle(ctx, geom, p, t, slack=False, level=None, force_path=0, tol=1e-12, pert=1e-3):
     """north_star tolerance: gradient and Hessian within 1e-12 relative; pattern: oracle's
     (cancellation-dependent) pattern is contained in the plan's structural pattern and every extra
     entry is numerically zero."""
-    pr = problem(geom, p=p, slack=slack, level=level)
+    pr = problem(geom, p=p, slack=slack, level=level, pert=pert)
     f0_o, g_o, H_o = oracle_eval(pr, t)
     plan, out, H_c = cuda_eval(ctx, pr, t, force_path=force_path)
     assert out["scal"][1] == 1.0, "iterate reported non-finite"
