@@ -71,3 +71,19 @@ wavefronts(srcA, 'round-1 packed layout (96/elem)')
 wavefronts(srcB, 'row-major full layout (154/elem)')
 wavefronts(srcA, 'packed, 32B sectors', line=4)
 wavefronts(srcB, 'row-major, 32B sectors', line=4)
+def variant(RU, RS, NSX, name):
+    def slot(v1, q1, v2, q2):
+        if v1 == 0: return q1*RU + (q2 if v2 == 0 else 7 + q2)
+        if v2 == 0: return 7*RU + q1*RS + q2
+        return 7*RU + q1*RS + 7 if q1 == q2 else -1
+    src = []
+    for e in range(E):
+        loc = [(0, q, cu[e, q]) for q in range(B) if cu[e, q] >= 0] + [(1, q, cs[e, q]) for q in range(B) if cs[e, q] >= 0]
+        for (v1, q1, g1) in loc:
+            for (v2, q2, g2) in loc:
+                if slotA(v1, q1, v2, q2) < 0: continue
+                src.append(e*NSX + slot(v1, q1, v2, q2))
+    src = np.array(src)[order]
+    wavefronts(src, name)
+variant(16, 8, 168, 'u-run 16 s-run 8 (168)')
+variant(16, 8, 176, 'u-run 16 s-run 8, record 176 (line aligned)')
