@@ -23,4 +23,8 @@ void launch_element_2d(int mode, bool fine, const ElemParams& P, int flags, int6
 int element_ctas_per_sm_1d(int mode, bool fine, size_t smem);
 int element_ctas_per_sm_2d(int mode, bool fine, size_t smem);
 
+// thread-per-element kernel (kernels_te.cuh; fine levels, one cone): grid = nblk CTAs of one warp
+void launch_element_te(int B, int dim, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
+int element_te_ctas_per_sm(int B, int dim);
+
 }  // namespace mgb

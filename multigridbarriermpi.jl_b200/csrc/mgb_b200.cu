@@ -228,8 +228,9 @@ bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
 void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     const auto& ep = pl->ep;
-    mgb::launch_element(ep.B, ep.dim, ep.mode, ep.fine, P, flags, pl->nblocks_elem,
-                        (size_t)pl->smem_warp * (MGB_ELEM_THREADS / 32), pl->ctx->stream);
+    if (ep.te) mgb::launch_element_te(ep.B, ep.dim, P, flags, pl->nblocks_elem, pl->ctx->stream);
+    else mgb::launch_element(ep.B, ep.dim, ep.mode, ep.fine, P, flags, pl->nblocks_elem,
+                             (size_t)pl->smem_warp * (MGB_ELEM_THREADS / 32), pl->ctx->stream);
     g_launches++;
     CUDA_OK(cudaGetLastError());
 }
@@ -352,10 +353,12 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         cudaStream_t st = host_only ? nullptr : ctx->stream;
         bool use_elem = false;
         const bool want_hess = (force_path & MGB_PLAN_NO_HESSIAN) == 0;
-            force_path &= 3;
+        const int force_flags = force_path;
+        force_path &= 3;
         pl->has_hessian = want_hess;
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess);
+            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess,
+                                    /*allow_te=*/(force_flags & MGB_PLAN_TWO_STAGE) == 0 && getenv("MGB_NO_TE") == nullptr);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
                 throw std::runtime_error("element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
@@ -406,11 +409,18 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
-            pl->d_sel.alloc((size_t)ep.ntiles * ep.EPW * ep.lay.NS);   // whole warp tiles: the bulk stores write full tiles
-            pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m));
+            // whole warp tiles: the bulk stores write full tiles
+            pl->d_sel.alloc(ep.te ? (size_t)ep.ntiles * ep.te_TS : (size_t)ep.ntiles * ep.EPW * ep.lay.NS);
+            pl->d_rel.alloc((size_t)std::max<int64_t>(ep.te ? ep.ntiles * ep.NU * ep.B * 32 : (int64_t)ep.E * ep.NU * ep.LPE, pl->m));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
-            {   // persistent element kernel: shared memory per warp = two record stages + the tile's slot records +
+            if (ep.te) {   // thread-per-element kernel: one warp per CTA, persistent over tiles of 32 elements
+                const int per_sm = mgb::element_te_ctas_per_sm(ep.B, ep.dim);
+                if (per_sm < 1) throw std::runtime_error("thread-per-element kernel does not fit one CTA per SM (shared memory)");
+                const char* ev = getenv("MGB_ELEM_CTAS_PER_SM");
+                const int use = ev && atoi(ev) > 0 ? std::min(atoi(ev), per_sm) : per_sm;
+                pl->nblocks_elem = std::max<int64_t>(1, std::min<int64_t>(ep.ntiles, (int64_t)ctx->sm_count * use));
+            } else {   // persistent element kernel: shared memory per warp = two record stages + the tile's slot records +
                 // two mbarriers; grid = as many CTAs as are resident, capped by the number of warp tiles
                 const int in_bytes = (ep.RW / 2) * ep.PTS * 16;
                 pl->in_stride = (in_bytes + 127) / 128 * 128;
@@ -966,7 +976,7 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
         for (int k = 0; k < nD; ++k) Dh[k] = to_host_csr(D[k], 0, n);
         mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
         mgb::ElementPlan gp;
-        mgb::build_element_plan(Dh, Rh, n, w_host, pl->bar, gp, true);
+        mgb::build_element_plan(Dh, Rh, n, w_host, pl->bar, gp, true, /*allow_te=*/false);
         auto dd = std::make_unique<mgb_plan::Dist>();
         mgb::build_dist_maps(gp, rank, nranks, row_part, out_part, dd->maps);
         const auto& M = dd->maps;

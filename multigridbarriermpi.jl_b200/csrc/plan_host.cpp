@@ -152,8 +152,13 @@ struct UF {
 };
 }  // namespace
 
+namespace {
+// kernels_te.cuh te_swz: swizzled position of 16-byte chunk c inside a lane's cell of NC chunks
+int te_swz_host(int lane, int c, int NC) { return NC >= 8 ? (c ^ (lane & 7)) : NC == 4 ? (c ^ ((lane >> 1) & 3)) : NC == 2 ? (c ^ ((lane >> 2) & 1)) : c; }
+}  // namespace
+
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian) {
+                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian, bool allow_te) {
     P.ok = false;
     const int ND = (int)D.size();
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
@@ -265,7 +270,13 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         }
     }
     P.fine = fine;
+    P.te = allow_te && fine && P.mode == 0 && ((B == 2 && dim == 1) || (B == 7 && dim == 2));
     P.lay.build((int)B, dim, slack, fine);
+    if (P.te) {   // must match kernels_te.cuh TeShape
+        P.te_RU = (B >= 4) ? (2 * (int)B + 7) / 8 * 8 : (2 * (int)B + 1) / 2 * 2;
+        P.te_RS = (B >= 4) ? ((int)B + 1 + 7) / 8 * 8 : ((int)B + 1 + 1) / 2 * 2;
+        P.te_TS = (int64_t)B * 32 * P.te_RU + (int64_t)B * 32 * P.te_RS;
+    }
     const SlotLayout& lay = P.lay;
 
     // per-point records in element-local columns, stored per warp tile of EPW elements as 16-byte chunks in
@@ -274,12 +285,15 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         const int rwf = dim * (int)B + 1 + nu + 1, rwc = dim * (int)B + 1 + nu * (int)B;
         const int RW = ((fine ? rwf : rwc) + 1) / 2 * 2;
         P.RW = RW;
-        P.EPW = 32 / LPE; P.PTS = P.EPW * (int)B;
+        P.EPW = P.te ? 32 : 32 / LPE; P.PTS = P.EPW * (int)B;
         P.ntiles = (E + P.EPW - 1) / P.EPW;
         const int CH = RW / 2, PTS = P.PTS, EPW = P.EPW;
         P.prec.assign((size_t)P.ntiles * CH * PTS * 2, 0.0);
+        const bool te = P.te;
         auto at = [&](int64_t i, int c) -> double& {
             const int64_t e = i / B, T = e / EPW;
+            if (te)   // [tile][point l][chunk][lane = element in tile][2]
+                return P.prec[((((size_t)T * B + i % B) * CH + c / 2) * 32 + e % 32) * 2 + c % 2];
             const int ps = (int)(e % EPW) * (int)B + (int)(i % B);
             return P.prec[(((size_t)T * CH + c / 2) * PTS + ps) * 2 + c % 2];
         };
@@ -314,12 +328,19 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                         at(i, dim * (int)B + 1 + v * (int)B + local_of(v, i / B, A.idx[p])) = A.val[p];
             }
         }
-        // dof ids per lane of a warp tile: lane = (element in tile) * LPE + local node
-        P.lcols_tile.assign((size_t)P.ntiles * nu * 32, -1);
-        for (int64_t e = 0; e < E; ++e)
-            for (int v = 0; v < nu; ++v)
-                for (int q = 0; q < LPE; ++q)
-                    P.lcols_tile[((size_t)(e / EPW) * nu + v) * 32 + (e % EPW) * LPE + q] = P.lcols[((size_t)e * nu + v) * LPE + q];
+        if (te) {   // [tile][variable][local node][lane = element in tile]
+            P.lcols_tile.assign((size_t)P.ntiles * nu * B * 32, -1);
+            for (int64_t e = 0; e < E; ++e)
+                for (int v = 0; v < nu; ++v)
+                    for (int q = 0; q < (int)B; ++q)
+                        P.lcols_tile[(((size_t)(e / 32) * nu + v) * B + q) * 32 + e % 32] = P.lcols[((size_t)e * nu + v) * LPE + q];
+        } else {    // dof ids per lane of a warp tile: lane = (element in tile) * LPE + local node
+            P.lcols_tile.assign((size_t)P.ntiles * nu * 32, -1);
+            for (int64_t e = 0; e < E; ++e)
+                for (int v = 0; v < nu; ++v)
+                    for (int q = 0; q < LPE; ++q)
+                        P.lcols_tile[((size_t)(e / EPW) * nu + v) * 32 + (e % EPW) * LPE + q] = P.lcols[((size_t)e * nu + v) * LPE + q];
+        }
     }
 
     // structural pattern of R'(sum_jk D_j' diag D_k)R = union_i U_i x U_i, U_i = support of point i
@@ -394,11 +415,33 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                     const int32_t gb = P.lcols[((size_t)e * nu + a2 / B) * LPE + a2 % B];
                     if (gb < 0) continue;
                     if (pass == 0) { rowcnt[ga + 1]++; continue; }
-                    const int sl = slot_of(a1, a2, own);
-                    if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
+                    int64_t abs_slot;
+                    if (P.te) {
+                        // slot records of the thread-per-element kernel: [tile][u-row q | s-row of point l][lane][cell],
+                        // 16-byte chunks of a cell swizzled (te_swz); s-row q' is stored at the point that owns column q'
+                        const int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
+                        const int64_t tb0 = (e / 32) * P.te_TS;
+                        const int ln = (int)(e % 32);
+                        if (v1 == 0) {
+                            const int col = (v2 == 0) ? q2 : (int)B + q2;
+                            abs_slot = tb0 + (int64_t)q1 * 32 * P.te_RU + ln * P.te_RU + te_swz_host(ln, col / 2, P.te_RU / 2) * 2 + col % 2;
+                        } else {
+                            int lp = -1;
+                            for (int l = 0; l < (int)B; ++l) if (own[1 * B + l] == q1) lp = l;
+                            if (lp < 0 || (v2 == 1 && q1 != q2)) throw std::runtime_error("internal: s-row without an owning point");
+                            const int col = (v2 == 0) ? q2 : (int)B;
+                            abs_slot = tb0 + (int64_t)B * 32 * P.te_RU + (int64_t)lp * 32 * P.te_RS + ln * P.te_RS +
+                                       te_swz_host(ln, col / 2, P.te_RS / 2) * 2 + col % 2;
+                        }
+                    } else {
+                        const int sl = slot_of(a1, a2, own);
+                        if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
+                        abs_slot = e * lay.NS + sl;
+                    }
+                    if (abs_slot > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
                     const int64_t d = fillpos[ga]++;
                     tb[d] = gb;
-                    ts[d] = (int32_t)(e * lay.NS + sl);
+                    ts[d] = (int32_t)abs_slot;
                 }
             }
         }
@@ -446,7 +489,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         for (int v = 0; v < nu; ++v)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
-                if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
+                if (a >= 0) P.g_cidx[gpos[a]++] = P.te ? (int32_t)((((e / 32) * nu + v) * B + q) * 32 + e % 32) : (int32_t)((e * nu + v) * LPE + q);
             }
     P.ok = true;
 }

@@ -52,6 +52,10 @@ struct ElementPlan {
     std::string why;       // reason when !ok
     int B = 0, LPE = 0, dim = 0, NU = 0, ND = 0;
     bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
+    bool te = false;                    // thread-per-element kernel (kernels_te.cuh): fine level, one cone.  Tiles of 32
+                                        // elements; records / dof ids / slot records in the [tile][..][lane] layouts below
+    int te_RU = 0, te_RS = 0;           // doubles per u-row / s-row cell of the slot records
+    int64_t te_TS = 0;                  // doubles of slot records per tile
     int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
     SlotLayout lay;
@@ -82,7 +86,7 @@ struct BarrierDesc {
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.
 // Tries to detect the broken-element block structure the fused kernels exploit.
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
+                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true, bool allow_te = true);
 
 
 // ---- multi-GPU (one process per GPU): fused peer-memory exchange maps --------------------------------
