@@ -14,7 +14,7 @@
 #include <stdint.h>
 
 #ifndef MGB_ELEM_MINBLOCKS
-#define MGB_ELEM_MINBLOCKS 4
+#define MGB_ELEM_MINBLOCKS 5
 #endif
 #ifndef MGB_ELEM_THREADS
 #define MGB_ELEM_THREADS 128
@@ -24,25 +24,23 @@ namespace mgb {
 
 struct ElemParams {
     // geometry / plan (device)
-    int64_t E, nloc, ntiles;
-    const int32_t* lcols;    // [ntiles][NU][32] element -> dof of every lane of a warp tile (-1: eliminated / idle lane)
-    const double* prec;      // [ntiles][CH][PTS] 16-byte chunks of the per-point records (see ElemShape):
-                             //   derivative rows (D*B), w, then
+    int64_t E, nloc;
+    const int32_t* lcols;    // [E][NU][LPE] element -> dof (-1: eliminated)
+    const double* prec;      // [nloc][RW] per-point record: derivative rows (D*B), w, then
                              //   fine:   own_val[NU], own_lq bytes packed in one 8-byte slot
                              //   coarse: dense id-like rows [NU][B]
+                             // RW even -> every record is 16-byte aligned (128-bit loads)
     // per call
     const double* s;         // m
     const double* Dz0;       // nloc x ND or null
     const double* c;         // nloc x ND
     double t, p, p2;         // p2: exponent of the second cone (MODE 2)
     // outputs
-    double* sel;             // ntiles*EPW*NS slot records (bulk-stored per warp tile)
+    double* sel;             // E*NS
     double* rel;             // E*NU*LPE
     double* part;            // gridDim.x * 4  {f0, cdot, nonfinite count, -}
     double* Dz;              // nloc x ND or null
     int off_uu, off_us, off_ss, off_ut, off_st, off_tt, NS;
-    int RU, RS;              // row-major records (fine, two variables): doubles per u-row / s-row
-    int in_stride, smem_warp;  // shared memory: bytes per record stage (128-byte multiple) / per warp
 };
 
 template <int V>
@@ -126,91 +124,64 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
     }
 }
 
-// ---------------------------------------------------------------- TMA (1-D bulk copy) + mbarrier helpers
-// The element kernel streams its per-point operator records HBM -> shared memory with cp.async.bulk (the 1-D TMA
-// path: SASS UBLKCP), double-buffered per warp behind an mbarrier, and writes every element's slot record back with
-// one bulk store per warp tile - so the load/store units only see shared-memory traffic.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, unsigned parity) {
-    unsigned ok;
-    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) { while (!mbar_try_wait(bar, parity)) {} }
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-}
-__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-
-// Compile-time shape of one element-kernel instance.  A warp owns tiles of EPW consecutive elements (one LPE-lane
-// group each); the per-point records of a tile are stored chunk-major ([chunk of 16 bytes][point]), so a tile is one
-// contiguous block in HBM (one bulk copy) and lane-consecutive 16-byte shared-memory loads are conflict free.
-template <int B, int D, int MODE, bool FINE>
-struct ElemShape {
-    static constexpr bool THREE = MODE != 0;
-    static constexpr int LPE = Pow2Ceil<B>::value;
-    static constexpr int EPW = 32 / LPE;             // elements per warp tile
-    static constexpr int PTS = EPW * B;              // quadrature points per tile
-    static constexpr int ND = D + 2 + (THREE ? 1 : 0);
-    static constexpr int NU = 2 + (THREE ? 1 : 0);
-    static constexpr int RWF = D * B + 1 + NU + 1, RWC = D * B + 1 + NU * B;
-    static constexpr int RW = ((FINE ? RWF : RWC) + 1) / 2 * 2;   // doubles per point record (even)
-    static constexpr int CH = RW / 2;                // 16-byte chunks per point
-    static constexpr int IN_BYTES = CH * PTS * 16;   // one tile of records
-    static constexpr bool ROWMAJOR = FINE && !THREE; // slot record laid out by (row, column): see SlotLayout
-};
-
 // FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
-// Work of one element group (LPE lanes, one quadrature point per lane) on one element.
-//   rec2  : this point's operator record in shared memory, chunk c at rec2[c * PTS]
-//   sel   : the element's slot record (shared memory, bulk-stored by the caller), `rel` its gradient record (global)
-//   col/zl/cc/dz: element -> dof ids, gathered unknowns, cost row and Dz0 row of this point (prefetched by the caller)
-// Returns this thread's objective / <c,Dz> / infeasibility partials.  Every lane of the warp must call it.
+// Per-point work of one element group (LPE lanes).  Writes the element's gradient record to `rel`
+// and its slot record to `sel` (global memory in the two-stage path, shared memory in the patch-
+// fused path; entry r of a butterfly-reduced block is stored at  off + r*LPE + lane).  Returns this
+// thread's objective / <c,Dz> / infeasibility partials.  Every lane of the group must call it.
 // MODE: 0 = one cone on (grad u, s); 1 = feasibility phase, cone on (grad u, s + tau) plus -log(1 + tau);
 //       2 = two cones (upstream parabolic_solve): A on (u, s1) with exponent p2, B on (grad u, s2) with p.
 //       Modes 1 and 2 share the three-variable operator table [u.id; u.d*; v1.id; v2.id] and slot layout.
 template <int B, int D, int MODE, bool FINE, int FLAGS>
-__device__ __forceinline__ void element_body(const ElemParams& P, const bool act_e, const bool act, const int l, const int64_t i,
-                                             const double2* __restrict__ rec2, const double (&zl)[2 + (MODE != 0 ? 1 : 0)],
-                                             const double (&cc)[D + 2 + (MODE != 0 ? 1 : 0)], double (&dz)[D + 2 + (MODE != 0 ? 1 : 0)],
-                                             double* __restrict__ sel, double* __restrict__ rel, double& v0, double& v1, double& v2) {
-    using S = ElemShape<B, D, MODE, FINE>;
+__device__ __forceinline__ void element_body(const ElemParams& P, const int64_t e, const int l, double* __restrict__ sel,
+                                             double* __restrict__ rel, double& v0, double& v1, double& v2) {
     constexpr bool SLACK = MODE == 1, TWO = MODE == 2, THREE = MODE != 0;
-    constexpr int LPE = S::LPE, ND = S::ND, NU = S::NU, RW = S::RW, PTS = S::PTS;
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr int ND = D + 2 + (THREE ? 1 : 0);
+    constexpr int NU = 2 + (THREE ? 1 : 0);
     constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
     constexpr int NTRI = (B * (B + 1) / 2 + LPE - 1) / LPE * LPE;
     constexpr int NFULL = (B * B + LPE - 1) / LPE * LPE;
+
+    const bool act_e = e < P.E;
+    const bool act = act_e && (l < B);
+    const int64_t i = act ? e * B + l : 0;
     const int64_t n = P.nloc;
 
-    // ---- unpack the record (shared memory, 16-byte loads; consecutive points are consecutive 16-byte words)
-    double rec[RW];
+    // ---- loads.  Order matters (in-order issue): first the dof indices (their consumer, the gather
+    // of s, comes last), then every independent stream, so one memory latency covers all of them.
+    int32_t col[NU];
 #pragma unroll
-    for (int j = 0; j < RW / 2; ++j) {
-        const double2 t2 = rec2[j * PTS];
-        rec[2 * j] = t2.x;
-        rec[2 * j + 1] = t2.y;
+    for (int v = 0; v < NU; ++v) col[v] = act_e ? __ldg(&P.lcols[(e * NU + v) * LPE + l]) : -1;
+    constexpr int RWF = D * B + 1 + NU + 1, RWC = D * B + 1 + NU * B;
+    constexpr int RW = ((FINE ? RWF : RWC) + 1) / 2 * 2;
+    double rec[RW];
+    {
+        const double2* __restrict__ rp = reinterpret_cast<const double2*>(P.prec + i * RW);
+#pragma unroll
+        for (int j = 0; j < RW / 2; ++j) {
+            const double2 t2 = act ? __ldg(rp + j) : make_double2(0.0, 0.0);
+            rec[2 * j] = t2.x;
+            rec[2 * j + 1] = t2.y;
+        }
     }
+    double cc[ND], dz[ND];
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+        cc[k] = act ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
+        dz[k] = (act && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+    }
+    // ---- gather the element's unknowns: lane q holds z[var][q]
+    double zl[NU];
+#pragma unroll
+    for (int v = 0; v < NU; ++v) zl[v] = (col[v] >= 0) ? __ldg(&P.s[col[v]]) : 0.0;
+    // ---- unpack the record
     double a[D][B];
 #pragma unroll
     for (int k = 0; k < D; ++k)
 #pragma unroll
-        for (int q = 0; q < B; ++q) a[k][q] = act ? rec[k * B + q] : 0.0;
-    const double wi = act ? rec[D * B] : 0.0;
+        for (int q = 0; q < B; ++q) a[k][q] = rec[k * B + q];
+    const double wi = rec[D * B];
     double aid[FINE ? 1 : NU][FINE ? 1 : B];
     double oval[NU];
     int olq[NU];
@@ -228,7 +199,7 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const bool act
 #pragma unroll
         for (int v = 0; v < NU; ++v)
 #pragma unroll
-            for (int q = 0; q < B; ++q) aid[FINE ? 0 : v][FINE ? 0 : q] = act ? rec[FINE ? 0 : D * B + 1 + v * B + q] : 0.0;
+            for (int q = 0; q < B; ++q) aid[FINE ? 0 : v][FINE ? 0 : q] = rec[FINE ? 0 : D * B + 1 + v * B + q];
     }
     // ---- apply_D: Dz = Dz0 + (D R) s
 #pragma unroll
@@ -374,22 +345,7 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const bool act
             }
         }
         group_reduce<NTRI, LPE>(v, l);
-        if (S::ROWMAJOR) {
-            // lane l holds packed upper-triangle entries pk = l*K + r: store (q1,q2) and its mirror in the two u-rows
-            constexpr int K = NTRI / LPE;
-#pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const int pk = l * K + r;
-                int q1 = 0;
-#pragma unroll
-                for (int q = 1; q < B; ++q) q1 += (pk >= q * B - q * (q - 1) / 2) ? 1 : 0;
-                const int q2 = pk - (q1 * B - q1 * (q1 - 1) / 2) + q1;
-                if (act_e && pk < B * (B + 1) / 2) {
-                    sel[q1 * P.RU + q2] = v[r];
-                    sel[q2 * P.RU + q1] = v[r];
-                }
-            }
-        } else if (act_e) {
+        if (act_e) {
 #pragma unroll
             for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + r * LPE + l] = v[r];
         }
@@ -408,19 +364,7 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const bool act
     const double haus = TWO ? wi * ba.Hqs[0] : 0.0;           // cone A: u x s1 and s1 x s1
     const double hass = TWO ? wi * ba.Hss : 0.0;
     constexpr int VT = THREE ? 2 : 0;
-    if (S::ROWMAJOR) {
-        // row-major record: u-row q = [uu(q,.) | us(q,.)], s-row q' = [su(q',.) | ss(q')]; this point owns s column olq[1]
-        if (act && oh[1]) {
-            double* srow = sel + B * P.RU + olq[1] * P.RS;
-#pragma unroll
-            for (int q = 0; q < B; ++q) {
-                const double val = bs[q] * oval[1];
-                sel[q * P.RU + B + olq[1]] = val;
-                srow[q] = val;
-            }
-            srow[B] = vss * oval[1] * oval[1];
-        }
-    } else if (FINE) {
+    if (FINE) {
         if (act && oh[1]) {
 #pragma unroll
             for (int q = 0; q < B; ++q)
@@ -512,107 +456,159 @@ __device__ __forceinline__ void block_scalars(double v0, double v1, double v2, d
     }
 }
 
-// Stage 1 of an assembly: persistent warps, each walking the tiles  gw, gw + GW, gw + 2 GW, ...  (gw = global warp
-// id, GW = warps in the grid; static schedule -> the scalar partial sums have a fixed order for a given launch shape).
-// Per tile a warp
-//   * has the tile's operator records arriving in shared memory by a bulk copy issued one tile ahead (mbarrier),
-//   * holds the next tile's dof ids / gathered unknowns / c / Dz0 rows in registers, loaded one tile ahead (ids two),
-//   * computes apply_D -> barrier -> element-local gradient and Hessian blocks in registers (element_body),
-//   * assembles the EPW slot records in shared memory and writes them to `sel` with one bulk store.
-// Shared memory per warp (P.smem_warp bytes): [2 x IN_BYTES records | EPW * NS doubles of slot records | 2 mbarriers].
+// Two-stage path, stage 1: slot / gradient records to global memory (replayed by gather_kernel).
 template <int B, int D, int MODE, bool FINE, int FLAGS>
-__global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const __grid_constant__ ElemParams P) {
-    using S = ElemShape<B, D, MODE, FINE>;
-    constexpr int LPE = S::LPE, EPW = S::EPW, NU = S::NU, ND = S::ND, PTS = S::PTS;
-    constexpr bool WH = (FLAGS & 4) != 0;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+__global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_kernel(const ElemParams P) {
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr int NU = 2 + (MODE != 0 ? 1 : 0);
     pdl_launch_dependents();
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    unsigned char* wbase = smem_raw + (size_t)wib * P.smem_warp;
-    double* out_buf = reinterpret_cast<double*>(wbase + 2 * (size_t)P.in_stride);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(wbase + P.smem_warp - 16);
-    const int el = lane / LPE, l = lane % LPE;
-    const int ps = min(el * B + l, PTS - 1);  // this lane's point slot inside a tile (idle lanes alias a valid one)
-    const int64_t gw = (int64_t)blockIdx.x * (blockDim.x >> 5) + wib;
-    const int64_t GW = (int64_t)gridDim.x * (blockDim.x >> 5);
-    const int64_t n = P.nloc;
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t e = tid / LPE;
+    const int l = (int)(tid % LPE);
+    double v0, v1, v2;
+    element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
+    block_scalars(v0, v1, v2, P.part);
+}
 
-    if (lane == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init_fence(); }
-    if (WH) for (int k = lane; k < EPW * P.NS; k += 32) out_buf[k] = 0.0;
-    __syncwarp();
+// Patch-fused path: one CTA = PATCH consecutive elements.  Phase A keeps the slot / gradient records
+// in shared memory; phase B replays the patch's frozen lists: entries fed by this patch alone go
+// straight into the CSR value array / gradient, the others leave one partial sum per patch in the
+// export buffers that interface_kernel folds.  No atomics; fixed summation order.
+struct ReplayDev {
+    const int32_t* pp;  const int2* rec;
+    const int32_t* lg_pp;  const int32_t* lg_dest;  const int32_t* lg_ptr;  const uint16_t* lg_idx;
+    double* out;  double* exp;
+    int max_rec;
+};
 
-    auto issue = [&](int64_t tile, int stage) {
-        if (lane == 0) {
-            mbar_expect_tx(bars + stage, (unsigned)S::IN_BYTES);
-            bulk_g2s(wbase + stage * P.in_stride, reinterpret_cast<const unsigned char*>(P.prec) + tile * (int64_t)S::IN_BYTES, (unsigned)S::IN_BYTES, bars + stage);
-        }
-    };
-    auto load_cols = [&](int64_t tile, int32_t (&col)[NU]) {
-#pragma unroll
-        for (int v = 0; v < NU; ++v) col[v] = (tile < P.ntiles) ? __ldg(&P.lcols[(tile * NU + v) * 32 + lane]) : -1;
-    };
-    auto load_z = [&](const int32_t (&col)[NU], double (&z)[NU]) {
-#pragma unroll
-        for (int v = 0; v < NU; ++v) z[v] = (col[v] >= 0) ? __ldg(&P.s[col[v]]) : 0.0;
-    };
-    auto load_rows = [&](int64_t tile, double (&cc)[ND], double (&dz)[ND]) {
-        const int64_t e = tile * EPW + el;
-        const bool act = tile < P.ntiles && e < P.E && l < B;
-        const int64_t i = act ? e * B + l : 0;
-#pragma unroll
-        for (int k = 0; k < ND; ++k) {
-            cc[k] = act ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
-            dz[k] = (act && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
-        }
-    };
+struct PatchParams {
+    int NSP, RSP;  // shared-memory strides (doubles) of the slot / gradient records
+    ReplayDev H, G;
+};
 
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
-    int64_t tile = gw;
-    int32_t col_n[NU], col_nn[NU];
-    double zl_n[NU], cc_n[ND], dz_n[ND];
-    if (tile < P.ntiles) issue(tile, 0);
-    load_cols(tile, col_n);
-    load_cols(tile + GW, col_nn);
-    load_rows(tile, cc_n, dz_n);
-    load_z(col_n, zl_n);
-    unsigned phase = 0u;   // bit s: parity the next wait on stage s expects
-    int stage = 0;
-    for (; tile < P.ntiles; tile += GW, stage ^= 1) {
-        double zl[NU], cc[ND], dz[ND];
-#pragma unroll
-        for (int v = 0; v < NU; ++v) zl[v] = zl_n[v];
-#pragma unroll
-        for (int k = 0; k < ND; ++k) { cc[k] = cc_n[k]; dz[k] = dz_n[k]; }
-        // ---- one tile ahead: records by bulk copy into the other stage (its readers finished last iteration),
-        //      dof ids / unknowns / c / Dz0 rows into registers
-        const int64_t nxt = tile + GW;
-        __syncwarp();
-        if (nxt < P.ntiles) issue(nxt, stage ^ 1);
-        load_z(col_nn, zl_n);
-        load_rows(nxt, cc_n, dz_n);
-        load_cols(nxt + GW, col_nn);
-        // ---- this tile
-        const int64_t e = tile * EPW + el;
-        const bool act_e = e < P.E, act = act_e && l < B;
-        const int64_t i = act ? e * B + l : 0;
-        mbar_wait(bars + stage, (phase >> stage) & 1u);
-        phase ^= 1u << stage;
-        if (WH) {   // the previous tile's bulk store must have read the staging buffer before it is overwritten
-            if (lane == 0) bulk_wait_read();
-            __syncwarp();
-        }
-        double v0, v1, v2;
-        element_body<B, D, MODE, FINE, FLAGS>(P, act_e, act, l, i, reinterpret_cast<const double2*>(wbase + stage * P.in_stride) + ps, zl, cc, dz,
-                                              out_buf + (size_t)el * P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
-        acc0 += v0; acc1 += v1; acc2 += v2;
-        if (WH) {
-            fence_async_smem();   // generic-proxy writes of the slot records -> visible to the bulk-copy engine
-            __syncwarp();
-            if (lane == 0) bulk_s2g(P.sel + tile * (int64_t)(EPW * P.NS), out_buf, (unsigned)(EPW * P.NS * 8));
-        }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+
+// replay of one output family from the patch's shared-memory image `img`
+__device__ __forceinline__ void replay(const ReplayDev& R, const int2* __restrict__ rec_s, const double* __restrict__ img,
+                                       const int p) {
+    const int n = R.pp[p + 1] - R.pp[p];
+#pragma unroll 4
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+        const int2 rc = rec_s[k];
+        const uint32_t src = (uint32_t)rc.y;
+        double v = img[src & 0xFFFFu];
+        const uint32_t s1 = src >> 16;
+        if (s1 != 0xFFFFu) v += img[s1];
+        if (rc.x >= 0) R.out[rc.x] = v; else R.exp[-1 - rc.x] = v;
     }
-    if (WH && lane == 0) bulk_wait_all();
-    block_scalars(acc0, acc1, acc2, P.part);
+    for (int k = R.lg_pp[p] + threadIdx.x; k < R.lg_pp[p + 1]; k += blockDim.x) {
+        const int32_t dest = __ldg(&R.lg_dest[k]);
+        const int r0 = __ldg(&R.lg_ptr[k]), r1 = __ldg(&R.lg_ptr[k + 1]);
+        double v = 0.0;
+        for (int r = r0; r < r1; ++r) v += img[__ldg(&R.lg_idx[r])];
+        if (dest >= 0) R.out[dest] = v; else R.exp[-1 - dest] = v;
+    }
+}
+
+template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
+__global__ void __launch_bounds__(PATCH * Pow2Ceil<B>::value) patch_kernel(const ElemParams P, const PatchParams Q) {
+    constexpr int LPE = Pow2Ceil<B>::value;
+    constexpr bool WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0;
+    extern __shared__ double smem[];
+    double* img = smem;                                               // PATCH*NSP slot records, then PATCH*RSP gradient records
+    int2* rec_h = reinterpret_cast<int2*>(smem + (size_t)PATCH * (Q.NSP + Q.RSP));
+    int2* rec_g = rec_h + Q.H.max_rec;
+    const int p = blockIdx.x;
+    // stage this patch's replay records with cp.async: their latency hides behind phase A
+    if (WH) {
+        const int n = Q.H.pp[p + 1] - Q.H.pp[p];
+        const int2* src = Q.H.rec + Q.H.pp[p];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_h[k], &src[k]);
+    }
+    if (WG) {
+        const int n = Q.G.pp[p + 1] - Q.G.pp[p];
+        const int2* src = Q.G.rec + Q.G.pp[p];
+        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_g[k], &src[k]);
+    }
+    const int el = threadIdx.x / LPE;
+    const int l = threadIdx.x % LPE;
+    const int64_t e = (int64_t)blockIdx.x * PATCH + el;
+    double v0, v1, v2;
+    element_body<B, D, SLACK ? 1 : 0, FINE, FLAGS>(P, e, l, img + (size_t)el * Q.NSP,
+                                           img + (size_t)PATCH * Q.NSP + (size_t)el * Q.RSP, v0, v1, v2);
+    if (WG || WH) cp_async_commit_wait_all();
+    block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes records and staged lists
+    if (WH) replay(Q.H, rec_h, img, p);
+    if (WG) replay(Q.G, rec_g, img, p);
+}
+
+struct InterfaceParams {
+    int64_t n_if, n_gif, nparts;
+    const int32_t* if_t;  const int32_t* if_ptr;  const double* hexp;  double* hval;
+    const int32_t* gif_a; const int32_t* gif_ptr; const double* gexp;  double* grad;
+    const double* part;  double* scal;  double t;
+    int64_t nblk_h, nblk_g;
+    int warp_per_entry;
+};
+
+// Folds the per-patch partial sums of the interface entries (fixed patch order) and the scalar partials.
+static __global__ void __launch_bounds__(256) interface_kernel(const InterfaceParams P) {
+    const int64_t b = blockIdx.x;
+    if (b < P.nblk_h + P.nblk_g) {
+        const bool isg = b >= P.nblk_h;
+        const int64_t nent = isg ? P.n_gif : P.n_if;
+        const int32_t* __restrict__ ptr = isg ? P.gif_ptr : P.if_ptr;
+        const int32_t* __restrict__ idx = isg ? P.gif_a : P.if_t;
+        const double* __restrict__ src = isg ? P.gexp : P.hexp;
+        double* __restrict__ dst = isg ? P.grad : P.hval;
+        const int64_t bb = isg ? b - P.nblk_h : b;
+        if (P.warp_per_entry) {
+            const int64_t j = bb * 8 + (threadIdx.x >> 5);
+            const int lane = threadIdx.x & 31;
+            if (j >= nent) return;
+            double acc = 0.0;
+            for (int r = ptr[j] + lane; r < ptr[j + 1]; r += 32) acc += src[r];
+#pragma unroll
+            for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
+            if (lane == 0) dst[idx[j]] = acc;
+        } else {
+            const int64_t j = bb * 256 + threadIdx.x;
+            if (j >= nent) return;
+            double acc = 0.0;
+            for (int r = __ldg(&ptr[j]); r < __ldg(&ptr[j + 1]); ++r) acc += src[r];
+            dst[__ldg(&idx[j])] = acc;
+        }
+        return;
+    }
+    __shared__ double sh[3][256];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {
+        s0 += P.part[r * 4 + 0];
+        s1 += P.part[r * 4 + 1];
+        s2 += P.part[r * 4 + 2];
+    }
+    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
+    __syncthreads();
+    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
+        if ((int)threadIdx.x < st) {
+            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
+            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
+            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && P.scal) {
+        P.scal[0] = sh[0][0] + P.t * sh[1][0];
+        P.scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
+        P.scal[2] = sh[1][0];
+        P.scal[3] = sh[2][0];
+    }
 }
 
 // one block of 256 threads folds the per-block scalar partials in a fixed order -> {f0, all_finite, <c,Dz>_w, count}

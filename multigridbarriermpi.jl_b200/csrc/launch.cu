@@ -14,16 +14,17 @@ int canonical_flags(int flags) {
     return (f & 8) ? 15 : 7;
 }
 
-void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, size_t smem, cudaStream_t st) {
-    if (B == 2 && dim == 1) launch_element_1d(mode, fine, P, flags, nblk, smem, st);
-    else if (B == 7 && dim == 2) launch_element_2d(mode, fine, P, flags, nblk, smem, st);
+void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st) {
+    if (B == 2 && dim == 1) launch_element_1d(mode, fine, P, flags, nblk, st);
+    else if (B == 7 && dim == 2) launch_element_2d(mode, fine, P, flags, nblk, st);
     else throw std::runtime_error("element kernel not instantiated for this element type");
 }
 
-int element_ctas_per_sm(int B, int dim, int mode, bool fine, size_t smem) {
-    if (B == 2 && dim == 1) return element_ctas_per_sm_1d(mode, fine, smem);
-    if (B == 7 && dim == 2) return element_ctas_per_sm_2d(mode, fine, smem);
-    throw std::runtime_error("element kernel not instantiated for this element type");
+void launch_patch(int B, int dim, bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags,
+                  int64_t nblk, size_t smem, cudaStream_t st) {
+    if (B == 2 && dim == 1) launch_patch_1d(slack, fine, patch, P, Q, flags, nblk, smem, st);
+    else if (B == 7 && dim == 2) launch_patch_2d(slack, fine, patch, P, Q, flags, nblk, smem, st);
+    else throw std::runtime_error("patch kernel not instantiated for this element type");
 }
 
 }  // namespace mgb

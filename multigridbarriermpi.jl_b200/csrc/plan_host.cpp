@@ -103,18 +103,6 @@ void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_) {
     fine = fine_;
     LPE = pow2ceil(B);
     NU = 2 + (slack ? 1 : 0);
-    rowmajor = fine && !slack;
-    if (rowmajor) {
-        // runs padded so that a u-row of a 7-node element is exactly one 128-byte line and the record a whole
-        // number of lines (fem2d: RU = 16, RS = 8, NS = 176); small elements stay unpadded (fem1d: 4, 3, 14)
-        RU = (B >= 4) ? round_up(2 * B, 8) : 2 * B;
-        RS = (B >= 4) ? round_up(B + 1, 8) : B + 1;
-        NS = B * RU + B * RS;
-        if (B >= 4) NS = round_up(NS, 16);
-        NS = round_up(NS, 2);
-        off_uu = 0; off_us = B; off_ss = B * RU;
-        return;
-    }
     const int ntri = round_up(B * (B + 1) / 2, LPE);
     const int nfull = fine ? B * LPE : round_up(B * B, LPE);
     const int ndiag = fine ? LPE : ntri;
@@ -152,13 +140,8 @@ struct UF {
 };
 }  // namespace
 
-namespace {
-// kernels_te.cuh te_swz: swizzled position of 16-byte chunk c inside a lane's cell of NC chunks
-int te_swz_host(int lane, int c, int NC) { return NC >= 8 ? (c ^ (lane & 7)) : NC == 4 ? (c ^ ((lane >> 1) & 3)) : NC == 2 ? (c ^ ((lane >> 2) & 1)) : c; }
-}  // namespace
-
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian, bool allow_te) {
+                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian) {
     P.ok = false;
     const int ND = (int)D.size();
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
@@ -270,40 +253,22 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         }
     }
     P.fine = fine;
-    P.te = allow_te && fine && P.mode == 0 && ((B == 2 && dim == 1) || (B == 7 && dim == 2));
     P.lay.build((int)B, dim, slack, fine);
-    if (P.te) {   // must match kernels_te.cuh TeShape
-        P.te_RU = (B >= 4) ? (2 * (int)B + 7) / 8 * 8 : (2 * (int)B + 1) / 2 * 2;
-        P.te_RS = (B >= 4) ? ((int)B + 1 + 7) / 8 * 8 : ((int)B + 1 + 1) / 2 * 2;
-        P.te_TS = (int64_t)B * 32 * P.te_RU + (int64_t)B * 32 * P.te_RS;
-    }
     const SlotLayout& lay = P.lay;
 
-    // per-point records in element-local columns, stored per warp tile of EPW elements as 16-byte chunks in
-    // chunk-major order: double c of point slot ps of tile T sits at ((T*CH + c/2)*PTS + ps)*2 + c%2
+    // per-point records in element-local columns (one contiguous, 16-byte aligned record per point)
     {
         const int rwf = dim * (int)B + 1 + nu + 1, rwc = dim * (int)B + 1 + nu * (int)B;
         const int RW = ((fine ? rwf : rwc) + 1) / 2 * 2;
         P.RW = RW;
-        P.EPW = P.te ? 32 : 32 / LPE; P.PTS = P.EPW * (int)B;
-        P.ntiles = (E + P.EPW - 1) / P.EPW;
-        const int CH = RW / 2, PTS = P.PTS, EPW = P.EPW;
-        P.prec.assign((size_t)P.ntiles * CH * PTS * 2, 0.0);
-        const bool te = P.te;
-        auto at = [&](int64_t i, int c) -> double& {
-            const int64_t e = i / B, T = e / EPW;
-            if (te)   // [tile][point l][chunk][lane = element in tile][2]
-                return P.prec[((((size_t)T * B + i % B) * CH + c / 2) * 32 + e % 32) * 2 + c % 2];
-            const int ps = (int)(e % EPW) * (int)B + (int)(i % B);
-            return P.prec[(((size_t)T * CH + c / 2) * PTS + ps) * 2 + c % 2];
-        };
+        P.prec.assign((size_t)nloc * RW, 0.0);
         for (int kd = 0; kd < dim; ++kd) {
             const HostCSR& A = Ek[1 + kd];
             for (int64_t i = 0; i < nloc; ++i)
                 for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p)
-                    at(i, kd * (int)B + local_of(0, i / B, A.idx[p])) = A.val[p];
+                    P.prec[(size_t)i * RW + kd * B + local_of(0, i / B, A.idx[p])] = A.val[p];
         }
-        for (int64_t i = 0; i < nloc; ++i) at(i, dim * (int)B) = w_local[i];
+        for (int64_t i = 0; i < nloc; ++i) P.prec[(size_t)i * RW + dim * B] = w_local[i];
         if (fine) {
             for (int64_t i = 0; i < nloc; ++i) {
                 unsigned long long bits = 0;
@@ -311,35 +276,22 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                     const HostCSR& A = Ek[idop[v]];
                     unsigned lq = 255;
                     if (A.ptr[i + 1] > A.ptr[i]) {
-                        at(i, dim * (int)B + 1 + v) = A.val[A.ptr[i]];
+                        P.prec[(size_t)i * RW + dim * B + 1 + v] = A.val[A.ptr[i]];
                         lq = (unsigned)local_of(v, i / B, A.idx[A.ptr[i]]);
                     }
                     bits |= (unsigned long long)lq << (8 * v);
                 }
                 double packed;
                 std::memcpy(&packed, &bits, sizeof(double));
-                at(i, dim * (int)B + 1 + nu) = packed;
+                P.prec[(size_t)i * RW + dim * B + 1 + nu] = packed;
             }
         } else {
             for (int v = 0; v < nu; ++v) {
                 const HostCSR& A = Ek[idop[v]];
                 for (int64_t i = 0; i < nloc; ++i)
                     for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p)
-                        at(i, dim * (int)B + 1 + v * (int)B + local_of(v, i / B, A.idx[p])) = A.val[p];
+                        P.prec[(size_t)i * RW + dim * B + 1 + v * B + local_of(v, i / B, A.idx[p])] = A.val[p];
             }
-        }
-        if (te) {   // [tile][variable][local node][lane = element in tile]
-            P.lcols_tile.assign((size_t)P.ntiles * nu * B * 32, -1);
-            for (int64_t e = 0; e < E; ++e)
-                for (int v = 0; v < nu; ++v)
-                    for (int q = 0; q < (int)B; ++q)
-                        P.lcols_tile[(((size_t)(e / 32) * nu + v) * B + q) * 32 + e % 32] = P.lcols[((size_t)e * nu + v) * LPE + q];
-        } else {    // dof ids per lane of a warp tile: lane = (element in tile) * LPE + local node
-            P.lcols_tile.assign((size_t)P.ntiles * nu * 32, -1);
-            for (int64_t e = 0; e < E; ++e)
-                for (int v = 0; v < nu; ++v)
-                    for (int q = 0; q < LPE; ++q)
-                        P.lcols_tile[((size_t)(e / EPW) * nu + v) * 32 + (e % EPW) * LPE + q] = P.lcols[((size_t)e * nu + v) * LPE + q];
         }
     }
 
@@ -348,11 +300,6 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     const int NL = nu * (int)B;  // local index alpha = v*B + q
     auto slot_of = [&](int a1, int a2, const std::vector<int>& own /*[nu][B] local col per point*/) -> int {
         int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
-        if (lay.rowmajor) {   // (row a1, column a2) as stored: no symmetric sharing
-            if (v1 == 0) return q1 * lay.RU + (v2 == 0 ? q2 : (int)B + q2);
-            if (v2 == 0) return (int)B * lay.RU + q1 * lay.RS + q2;
-            return q1 == q2 ? (int)B * lay.RU + q1 * lay.RS + (int)B : -1;
-        }
         if (v1 > v2 || (v1 == v2 && q1 > q2)) { std::swap(v1, v2); std::swap(q1, q2); }
         const int NT = lay.ntri_pad(), NF = lay.nfull_pad();
         if (v1 == 0 && v2 == 0) return lay.packed(lay.off_uu, lay.tri(q1, q2), NT);
@@ -415,33 +362,11 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                     const int32_t gb = P.lcols[((size_t)e * nu + a2 / B) * LPE + a2 % B];
                     if (gb < 0) continue;
                     if (pass == 0) { rowcnt[ga + 1]++; continue; }
-                    int64_t abs_slot;
-                    if (P.te) {
-                        // slot records of the thread-per-element kernel: [tile][u-row q | s-row of point l][lane][cell],
-                        // 16-byte chunks of a cell swizzled (te_swz); s-row q' is stored at the point that owns column q'
-                        const int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
-                        const int64_t tb0 = (e / 32) * P.te_TS;
-                        const int ln = (int)(e % 32);
-                        if (v1 == 0) {
-                            const int col = (v2 == 0) ? q2 : (int)B + q2;
-                            abs_slot = tb0 + (int64_t)q1 * 32 * P.te_RU + ln * P.te_RU + te_swz_host(ln, col / 2, P.te_RU / 2) * 2 + col % 2;
-                        } else {
-                            int lp = -1;
-                            for (int l = 0; l < (int)B; ++l) if (own[1 * B + l] == q1) lp = l;
-                            if (lp < 0 || (v2 == 1 && q1 != q2)) throw std::runtime_error("internal: s-row without an owning point");
-                            const int col = (v2 == 0) ? q2 : (int)B;
-                            abs_slot = tb0 + (int64_t)B * 32 * P.te_RU + (int64_t)lp * 32 * P.te_RS + ln * P.te_RS +
-                                       te_swz_host(ln, col / 2, P.te_RS / 2) * 2 + col % 2;
-                        }
-                    } else {
-                        const int sl = slot_of(a1, a2, own);
-                        if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
-                        abs_slot = e * lay.NS + sl;
-                    }
-                    if (abs_slot > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
+                    const int sl = slot_of(a1, a2, own);
+                    if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
                     const int64_t d = fillpos[ga]++;
                     tb[d] = gb;
-                    ts[d] = (int32_t)abs_slot;
+                    ts[d] = (int32_t)(e * lay.NS + sl);
                 }
             }
         }
@@ -489,9 +414,90 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         for (int v = 0; v < nu; ++v)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
-                if (a >= 0) P.g_cidx[gpos[a]++] = P.te ? (int32_t)((((e / 32) * nu + v) * B + q) * 32 + e % 32) : (int32_t)((e * nu + v) * LPE + q);
+                if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
             }
     P.ok = true;
+}
+
+namespace {
+// cptr/cidx: per output entry the (element-sorted) global contribution slots; patch_of/local_of map a
+// global slot to its patch and to its 16-bit index inside the patch's shared-memory image.
+template <class PatchOf, class LocalOf>
+void build_replay(int64_t nout, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx, int64_t np,
+                  PatchOf patch_of, LocalOf local_of, ReplayLists& L) {
+    struct Grp { int64_t c0, c1, patch; int32_t dest; };
+    std::vector<Grp> groups;
+    groups.reserve((size_t)(nout + nout / 4));
+    std::vector<int32_t> rc(np + 1, 0), lc(np + 1, 0);
+    L.if_ptr.assign(1, 0);
+    int64_t nexp = 0;
+    for (int64_t t = 0; t < nout; ++t) {
+        const int64_t c0 = cptr[t], c1 = cptr[t + 1];
+        if (c1 == c0) continue;
+        const bool single = patch_of(cidx[c0]) == patch_of(cidx[c1 - 1]);  // lists are sorted by element
+        int64_t g0 = c0;
+        while (g0 < c1) {
+            const int64_t pa = patch_of(cidx[g0]);
+            int64_t g1 = g0;
+            while (g1 < c1 && patch_of(cidx[g1]) == pa) ++g1;
+            groups.push_back({g0, g1, pa, single ? (int32_t)t : (int32_t)(-1 - nexp++)});
+            if (g1 - g0 <= 2) rc[pa + 1]++; else lc[pa + 1]++;
+            g0 = g1;
+        }
+        if (!single) { L.if_dst.push_back((int32_t)t); L.if_ptr.push_back((int32_t)nexp); }
+    }
+    if (nexp > INT32_MAX) throw std::runtime_error("export buffer exceeds int32 indexing");
+    L.n_exp = nexp;
+    L.max_rec = 0;
+    for (int64_t q = 0; q < np; ++q) {
+        L.max_rec = std::max(L.max_rec, rc[q + 1]);
+        rc[q + 1] += rc[q];
+        lc[q + 1] += lc[q];
+    }
+    L.pp = rc; L.lg_pp = lc;
+    L.rec.resize((size_t)2 * rc[np]);
+    L.lg_dest.resize(lc[np]);
+    std::vector<int32_t> lcnt(lc[np], 0), rpos(rc.begin(), rc.end() - 1), lpos(lc.begin(), lc.end() - 1);
+    std::vector<int64_t> lsrc0(lc[np], 0);
+    for (const Grp& g : groups) {
+        const int64_t cnt = g.c1 - g.c0;
+        if (cnt <= 2) {
+            const int32_t k = rpos[g.patch]++;
+            const uint32_t s0 = local_of(cidx[g.c0]);
+            const uint32_t s1 = cnt == 2 ? local_of(cidx[g.c0 + 1]) : 0xFFFFu;
+            L.rec[2 * (size_t)k] = g.dest;
+            L.rec[2 * (size_t)k + 1] = (int32_t)(s0 | (s1 << 16));
+        } else {
+            const int32_t k = lpos[g.patch]++;
+            L.lg_dest[k] = g.dest; lcnt[k] = (int32_t)cnt; lsrc0[k] = g.c0;
+        }
+    }
+    L.lg_ptr.assign(lc[np] + 1, 0);
+    for (int64_t k = 0; k < lc[np]; ++k) L.lg_ptr[k + 1] = L.lg_ptr[k] + lcnt[k];
+    L.lg_idx.resize(L.lg_ptr[lc[np]]);
+    for (int64_t k = 0; k < lc[np]; ++k)
+        for (int32_t r = 0; r < lcnt[k]; ++r) L.lg_idx[L.lg_ptr[k] + r] = local_of(cidx[lsrc0[k] + r]);
+}
+}  // namespace
+
+void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
+    PatchPlan& PP = EP.patch;
+    const int NS = EP.lay.NS, LPE = EP.LPE, NU = EP.NU;
+    PP.P = elems_per_patch;
+    PP.npatch = (EP.E + PP.P - 1) / PP.P;
+    int nsp = NS;
+    while (nsp % 16 != LPE % 16) ++nsp;  // consecutive elements land on disjoint shared-memory banks
+    PP.NSP = nsp;
+    PP.RSP = NU * LPE;
+    const int64_t P = PP.P, NSP = PP.NSP, RS = PP.RSP;
+    if (P * (NSP + RS) > 65534) throw std::runtime_error("patch too large for 16-bit local slots");
+    build_replay((int64_t)EP.h_colidx.size(), EP.h_cptr, EP.h_cidx, PP.npatch,
+                 [&](int32_t gs) { return (int64_t)(gs / NS) / P; },
+                 [&](int32_t gs) { const int64_t e = gs / NS; return (uint32_t)((e % P) * NSP + gs % NS); }, PP.H);
+    // gradient records live after the slot records in the patch's shared-memory image
+    build_replay(EP.m, EP.g_cptr, EP.g_cidx, PP.npatch,
+                 [&](int32_t gi) { return (int64_t)(gi / RS) / P; },
+                 [&](int32_t gi) { const int64_t e = gi / RS; return (uint32_t)(P * NSP + (e % P) * RS + gi % RS); }, PP.G);
 }
 
 namespace {

@@ -29,13 +29,6 @@ int64_t count_gram_pattern(const std::vector<HostCSR>& D);
 struct SlotLayout {
     int B = 0, LPE = 0, NU = 0, dim = 0;
     bool slack = false, fine = false;
-    // rowmajor (fine levels, two state variables): the record is laid out by (local row, local column) -
-    // u-row q = [uu(q,0..B) | us(q,0..B)] (RU doubles), then s-row q' = [su(q',0..B) | ss(q')] (RS doubles) - so
-    // the entries of one CSR row of R'HR that come from one element are one contiguous run: the gather kernel's
-    // scattered 8-byte reads of a warp fall into a few 128-byte lines instead of one per entry.  The symmetric
-    // halves are both stored (no packed triangle).  Otherwise: packed blocks at off_*.
-    bool rowmajor = false;
-    int RU = 0, RS = 0;
     int off_uu = 0, off_us = 0, off_ss = 0, off_ut = 0, off_st = 0, off_tt = 0;
     int NS = 0;  // doubles per element
     void build(int B_, int dim_, bool slack_, bool fine_);
@@ -47,33 +40,54 @@ struct SlotLayout {
     int nfull_pad() const;
 };
 
+// Patch-fused replay lists: a CTA owns P consecutive elements, keeps their slot records in shared
+// memory and finishes every output entry whose contributions all come from the patch; the others get
+// one partial sum per patch in an export buffer that a small interface kernel folds.
+// One output family (Hessian values or gradient entries) of the patch-fused replay.
+struct ReplayLists {
+    std::vector<int32_t> pp;       // npatch+1: records of patch p are [pp[p], pp[p+1])
+    std::vector<int32_t> rec;      // 2 ints per record: dest, src  (dest >= 0: index into the output array,
+                                   // dest < 0: -1-index into the export buffer; src: lo16 first local slot,
+                                   // hi16 second local slot or 0xFFFF)
+    std::vector<int32_t> lg_pp;    // npatch+1: entries with more than two in-patch contributions
+    std::vector<int32_t> lg_dest;
+    std::vector<int32_t> lg_ptr;   // nlong+1 into lg_idx
+    std::vector<uint16_t> lg_idx;
+    std::vector<int32_t> if_dst;   // interface entries: output index
+    std::vector<int32_t> if_ptr;   // n_if+1 into the export buffer (partials of one entry are contiguous)
+    int64_t n_exp = 0;
+    int32_t max_rec = 0;           // longest per-patch record list (sizes the shared-memory staging area)
+};
+
+struct PatchPlan {
+    int P = 0, NSP = 0, RSP = 0;  // elements per patch, smem strides (doubles) of the slot / gradient records
+    int64_t npatch = 0;
+    ReplayLists H, G;              // G's local slots index the gradient records, stored after the slot records
+};
+
 struct ElementPlan {
     bool ok = false;       // element-block structure detected and supported by the fused kernels
     std::string why;       // reason when !ok
     int B = 0, LPE = 0, dim = 0, NU = 0, ND = 0;
     bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
-    bool te = false;                    // thread-per-element kernel (kernels_te.cuh): fine level, one cone.  Tiles of 32
-                                        // elements; records / dof ids / slot records in the [tile][..][lane] layouts below
-    int te_RU = 0, te_RS = 0;           // doubles per u-row / s-row cell of the slot records
-    int64_t te_TS = 0;                  // doubles of slot records per tile
     int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
     SlotLayout lay;
     std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1
     int RW = 0;                    // doubles per point record (even)
-    int EPW = 0, PTS = 0;          // elements / points per warp tile (32 / LPE elements)
-    int64_t ntiles = 0;
-    std::vector<double> prec;      // [ntiles][RW/2][PTS][2] (16-byte chunks, chunk-major inside a tile; see kernels.cuh
-                                   // ElemShape): derivative rows (dim*B), w, then fine: own_val[NU] + packed
+    std::vector<double> prec;      // [nloc][RW]: derivative rows (dim*B), w, then fine: own_val[NU] + packed
                                    // own_lq bytes (255 = none); coarse: dense id-like rows [NU][B]
-    std::vector<int32_t> lcols_tile;  // [ntiles][NU][32]: lcols of every lane of a warp tile (-1: none / idle lane)
     // fixed output pattern + replay lists
     std::vector<int32_t> h_rowptr, h_colidx;  // m+1, nnzH
     std::vector<int64_t> h_cptr;              // nnzH+1
     std::vector<int32_t> h_cidx;              // contribution -> e*NS + slot
     std::vector<int64_t> g_cptr;              // m+1
     std::vector<int32_t> g_cidx;              // contribution -> (e*NU+v)*LPE + q
+    PatchPlan patch;
 };
+
+// Derives the patch-fused lists from the element plan's global contribution lists.
+void build_patch_plan(ElementPlan& P, int elems_per_patch);
 
 struct BarrierDesc {
     int kind = 1, nidx = 0, idx[8] = {0};
@@ -86,7 +100,7 @@ struct BarrierDesc {
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.
 // Tries to detect the broken-element block structure the fused kernels exploit.
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true, bool allow_te = true);
+                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
 
 
 // ---- multi-GPU (one process per GPU): fused peer-memory exchange maps --------------------------------
