@@ -7,14 +7,16 @@ apply_D -> barrier F/F1/F2 -> gradient -> Hessian numeric phase -> R'HR values (
   value     device-resident inputs, CUDA events on the launching stream, L2 flushed between steps
   e2e       the same step through the C ABI with HOST buffers (mgb_assemble_host): H2D of the
             Newton unknown, D2H of gradient + Hessian values + scalars inside the timed region
-  roofline  dominant kernel (element_kernel): algorithmic bytes / event time vs measured HBM peak
+  roofline  dominant (= longest) kernel: algorithmic bytes / event time vs measured HBM peak, next to the
+            fraction by ncu DRAM traffic and by the bytes this two-kernel design has to move
   cpu_baseline / --impl reference: the CPU oracle restatement (the Julia reference cannot run here:
             no julia/mpiexec in the image) timed on the host cores.
 
-N > 1 (torchrun): quadrature rows (whole elements) are sharded across ranks, every rank assembles
-the contributions of its own rows and stores them straight into the owner's exchange window over NVLink
-peer memory (push_kernel + epoch flags, all inside the timed region; `--exchange nccl` selects the
-pack -> all_to_all -> owner-side sum path instead); the fixed L=8 problem is split, so scaling = "strong".
+N > 1 (torchrun): owner-computes sharding - the rows of R'HR and the gradient entries are split over the ranks
+(HPCSparseArrays row partition), a rank evaluates every element touching its rows and completes them locally; only
+the objective scalars cross NVLink (peer-memory words, written and awaited inside the gather kernel, all inside the
+timed region).  The fixed L=8 problem is split, so scaling = "strong"; `sub_records` adds L=9 on the same GPUs.
+Every line carries `parity`: the buffers that were just timed against the CPU oracle (max over ranks).
 """
 from __future__ import annotations
 
@@ -97,8 +99,11 @@ def peak_hbm():
 
 
 def ncu_traffic(kernel: str, L: int):
-    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture (profiles/), or None."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """DRAM bytes per launch of `kernel` from the committed `ncu --set full` capture of this bench command at N = 1
+    (profiles/), or None."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r1_traffic.json")
     try:
         with open(path) as fh:
             d = json.load(fh)
@@ -246,7 +251,7 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly (n={pr['geom'].x.shape[0]})",
+        "config": {"workload": workload_name(args.L, args.p, pr['geom'].x.shape[0]),
                    "note": "CPU restatement (oracle/mgb_oracle.py, scipy CSC), NOT the Julia reference: julia/mpiexec are "
                            "absent from this image; sharded over processes by row blocks like `mpiexec -n cores`",
                    "one_core_ms": ms_1, "slowest_rank_compute_ms": ms_slowest,
@@ -256,6 +261,264 @@ def run_reference(args, rank, world):
         "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def workload_name(L, p, n):
+    return f"fem2d L={L} p={p} finest-level assembly (n={n})"
+
+
+def oracle_outputs(pr, t):
+    """CPU oracle (checker, never timed here): objective, gradient, R'HR of the bench problem"""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import mgb_oracle as O
+    Q = O.EuclidianPower(idx=pr["idx"], p=pr["p"])
+    args = (pr["s"], pr["geom"].x, pr["geom"].w, t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
+    return O.f0(*args), O.f1(*args), O.f2(*args).tocsr()
+
+
+def parity_block(pr, t, f0, grad_own, hval_own, rowptr, colidx, lo, hi):
+    """relative errors of the buffers that were just timed against the oracle's rows [lo, hi)"""
+    import scipy.sparse as sp
+    f0_o, g_o, H_o = oracle_outputs(pr, t)
+    m = H_o.shape[0]
+    Hc = sp.csr_matrix((hval_own, colidx.astype(np.int64), rowptr.astype(np.int64)), shape=(hi - lo, m))
+    hn, gn = abs(H_o).max(), np.abs(g_o).max()
+    return {"f0_rel": float(abs(f0 - f0_o) / abs(f0_o)), "grad_rel": float(np.abs(grad_own - g_o[lo:hi]).max() / gn),
+            "hess_rel": float(abs(Hc - H_o[lo:hi]).max() / hn)}
+
+
+def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup, want_cpu=False):
+    """one timed configuration (fem2d level L on `world` GPUs); returns the record (rank 0) or None"""
+    import torch
+    import torch.distributed as dist
+    from mgb_b200 import capi
+    from mgb_b200 import dist as mdist
+
+    pr = build_problem(L, args.p)
+    geom = pr["geom"]
+    n = geom.x.shape[0]
+    B = geom.block
+    sharded = world > 1
+    t_plan = time.perf_counter()
+    if sharded:
+        plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], B, rank, world)
+        rows = plan.rows
+    else:
+        plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"])
+        rows = np.arange(n)
+    t_plan = time.perf_counter() - t_plan
+    flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
+    f64 = torch.float64
+    s_d = torch.from_numpy(pr["s"]).to(dev)
+    Dz0_d = torch.from_numpy(np.ascontiguousarray(pr["Dz0"][rows].T)).to(dev)   # (nD, n_local) = column-major n_local x nD
+    c_d = torch.from_numpy(np.ascontiguousarray(pr["c"][rows].T)).to(dev)
+    n_h = plan.dinfo["n_own_h"] if sharded else plan.nnzH
+    n_g = plan.dinfo["n_own_g"] if sharded else plan.m
+    scal_d = torch.zeros(4, dtype=f64, device=dev)
+    grad_d = torch.zeros(max(n_g, 1), dtype=f64, device=dev)
+    hval_d = torch.zeros(max(n_h, 1), dtype=f64, device=dev)
+    flush = 0 if args.no_flush else (2 if args.flush_mode == "read" else 1)
+    flush_buf = torch.zeros(256 << 17, dtype=f64, device=dev) if sharded else None  # 256 MiB
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    views = {}
+
+    def window_views(ptrs):
+        """zero-copy tensors over the owned results (library-owned device memory)"""
+        if ptrs not in views:
+            views[ptrs] = tuple(torch.as_tensor(capi.DeviceView(p_, cnt), device=dev)
+                                for p_, cnt in zip(ptrs, (max(n_h, 1), max(n_g, 1), 4)))
+        return views[ptrs]
+
+    def step_multi(nsteps):
+        """per-step CUDA events on the launching stream, the cross-rank sum of the scalars inside the timed bracket
+        (the gather kernel of every rank waits for its peers' words).  All steps are enqueued before the host waits,
+        so the ranks are paced by their GPUs and not by host launch jitter."""
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        for r in range(nsteps):
+            if flush == 2:
+                flush_buf.sum()  # read-evict: leaves L2 full of clean lines
+            elif flush:
+                flush_buf.fill_(float(r))
+            evs[r][0].record()
+            plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags)
+            evs[r][1].record()
+        torch.cuda.synchronize(dev)
+        if plan.dist_info()["err"]:
+            raise SystemExit("bench.py: a peer's objective partials timed out (scalar exchange protocol error)")
+        return sum(a.elapsed_time(b) for a, b in evs) / nsteps
+
+    # ---- warm-up
+    if not sharded:
+        plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, warmup, flush, split=False)
+    else:
+        step_multi(warmup)
+    launches0 = capi.launch_count()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    wall0 = time.perf_counter()
+    if not sharded:
+        ms_total, _, _ = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, steps, flush, split=False)
+    else:
+        ms_total = step_multi(steps)
+    launches = capi.launch_count() - launches0
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    # ---- parity of the buffers that were just timed (every rank: its owned rows against the oracle's)
+    if sharded:
+        ho, go, so = window_views(plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags))
+        torch.cuda.synchronize(dev)
+        lo, hi = plan.dinfo["own0"], plan.dinfo["own1"]
+        scal_now, g_now, h_now = so.cpu().numpy(), go[:n_g].cpu().numpy(), ho[:n_h].cpu().numpy()
+    else:
+        lo, hi = 0, plan.m
+        scal_now, g_now, h_now = scal_d.cpu().numpy(), grad_d.cpu().numpy(), hval_d[:n_h].cpu().numpy()
+    rp, ci = plan.pattern()
+    parity = parity_block(pr, args.t, scal_now[0], g_now, h_now, rp, ci, lo, hi) if not args.no_parity else None
+    # per-kernel split (separate pass, not part of `value`): this rank's element / gather kernels
+    # (N > 1: the rank's own two kernels without the cross-rank scalar exchange)
+    _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
+                                               max(10, steps // 2), flush, split=True)
+    ms_f0 = None
+    if not sharded:   # line-search point: objective only (SURVEY 8d: reported as a separate line, ms per f0)
+        plan.time_assemble(s_d, Dz0_d, c_d, args.t, capi.WANT_F0, scal_d, grad_d, hval_d, 3, flush, split=False)
+        ms_f0, _, _ = plan.time_assemble(s_d, Dz0_d, c_d, args.t, capi.WANT_F0, scal_d, grad_d, hval_d,
+                                         max(10, steps // 2), flush, split=False)
+    # ---- e2e: the same step through HOST buffers.  N = 1: the C-ABI host call (mgb_assemble_host) on the caller's
+    # page-locked arrays - H2D of the Newton unknown, D2H of gradient + Hessian values + scalars inside the call.
+    # N > 1: pinned torch buffers around mgb_dist_assemble (the owned blocks come back).
+    e2e_steps = max(5, min(steps, 20))
+    e2e_extra = {}
+    if not sharded:
+        plan.assemble_host(pr["s"], np.asfortranarray(pr["Dz0"]), np.asfortranarray(pr["c"]), args.t, flags, True)
+        t0 = time.perf_counter()
+        for _ in range(5):
+            plan.assemble_host(pr["s"], None, None, args.t, flags, upload_inputs=False)
+        e2e_extra["c_abi_pageable_ms"] = (time.perf_counter() - t0) * 1e3 / 5
+        s_reg = pr["s"].copy()
+        outb = plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False)
+        regs = (s_reg, outb["hval"], outb["grad"], outb["scal"])
+        for a in regs:
+            capi.host_register(a)
+        for _ in range(3):
+            plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False, out=outb)
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False, out=outb)
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        for a in regs:
+            capi.host_unregister(a)
+        e2e_extra["path"] = "mgb_assemble_host on arrays page-locked once with mgb_host_register"
+    else:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        s_h = pin(pr["s"])
+        hval_h = torch.empty(max(n_h, 1), dtype=f64).pin_memory()
+        grad_h = torch.empty(max(n_g, 1), dtype=f64).pin_memory()
+        scal_h = torch.empty(4, dtype=f64).pin_memory()
+
+        def e2e_step():
+            s_d.copy_(s_h, non_blocking=True)
+            ho, go, so = window_views(plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags))
+            hval_h[:n_h].copy_(ho[:n_h], non_blocking=True)
+            grad_h[:n_g].copy_(go[:n_g], non_blocking=True)
+            scal_h.copy_(so, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        e2e_extra["path"] = "pinned host buffers around mgb_dist_assemble (owned blocks)"
+
+    par = [parity[k] if parity else 0.0 for k in ("f0_rel", "grad_rel", "hess_rel")]
+    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms] + par + [float(rows.size), float(n_h)], dtype=f64, device=dev)
+    mx = vals.clone()
+    if world > 1:
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    ms_total, ms_elem, ms_gather, e2e_ms = (float(v) for v in mx[:4].cpu())
+    rec = None
+    if rank == 0:
+        peak, peak_src = peak_hbm()
+        info = plan.info
+        nD, dim, nu = info["nD"], 2, info["nu"]
+        nnzD = int(sum(d.nnz for d in pr["D"]))
+        nnzR = int(pr["R"].nnz)
+        if sharded:   # algorithmic bytes are a property of the whole level: take them from a symbolic global plan
+            ginfo = capi.Plan(None, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"]).info
+        else:
+            ginfo = info
+        alg, nnzH, N, E = ginfo["alg_bytes"], ginfo["nnzH"], ginfo["N"], ginfo["elements"]
+        # SURVEY 8(d): B = apply_D + barrier + y1 + y2 + gradient + Hessian numeric + restriction; the fine-space
+        # pattern size nnz(sum_jk D_j' D_k) is recovered from the library's total (it enters twice, 8 bytes each)
+        y2u = nD * (nD + 1) // 2
+        other = (N * 8 + nnzD * 12 + nD * (n + 1) * 4 + n * nD * 8) + n * (nD + dim + 1 + nD) * 8 + n * nD * 8 + n * y2u * 8 \
+            + (nnzD * 12 + n * nD * 8 + N * 8) + (n * y2u * 8 + nnzD * 8) + (nnzR * 24 + nnzH * 8)
+        nnzS = (alg - other) // 16
+        restr = nnzS * 8 + nnzR * 24 + nnzH * 8
+        shares = {"element_kernel": alg - restr, "gather_kernel": restr}
+        # bytes the two-kernel design itself has to move (compulsory traffic of THIS implementation, for the honest
+        # fraction next to the SURVEY formula): element kernel reads records / ids / c / Dz0 / s and writes the slot
+        # and gradient records, the gather kernel reads them back with the index lists and writes R'HR and g
+        RW = (dim * B + 1 + nu + 1 + 1) // 2 * 2
+        NS = ginfo["slots_per_element"]
+        design = {"element_kernel": n * RW * 8 + E * nu * 8 * 4 + 2 * n * nD * 8 + ginfo["m"] * 8 + E * NS * 8 + E * nu * 8 * 8,
+                  "gather_kernel": nnzH * 8 + E * NS * 8 + nnzH * 8 + ginfo["grad_contribs"] * 12 + ginfo["m"] * 8}
+        kms = {"element_kernel": ms_elem, "gather_kernel": ms_gather}
+        dom = max(kms, key=kms.get) if not sharded else None
+        traffic = ncu_traffic(dom, L) if dom else None
+        ach_all = alg / (ms_total * 1e-3) / 1e9
+        roof = {"bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+                "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all, "frac": ach_all / peak,
+                             "design_bytes": int(sum(design.values())),
+                             "design_frac": sum(design.values()) / (ms_total * 1e-3) / 1e9 / peak,
+                             "element_ms": ms_elem, "gather_ms": ms_gather, "f0_ms": ms_f0}}
+        if dom:
+            ach = shares[dom] / (kms[dom] * 1e-3) / 1e9
+            roof.update({"kernel": dom, "kernel_ms": kms[dom], "algorithmic_bytes": int(shares[dom]), "achieved": ach,
+                         "frac": ach / peak, "traffic": traffic,
+                         "traffic_frac": (traffic / (kms[dom] * 1e-3) / 1e9 / peak) if traffic else None,
+                         "design_bytes": int(design[dom]), "design_frac": design[dom] / (kms[dom] * 1e-3) / 1e9 / peak})
+        else:   # N > 1: per-kernel split and ncu traffic are single-GPU measurements; the whole assembly stands in
+            roof.update({"kernel": "element_kernel+gather_kernel (whole assembly, max over ranks)", "achieved": ach_all,
+                         "frac": ach_all / peak, "traffic": None})
+        rec = {
+            "value": ms_total, "ms_per_step": ms_total,
+            "config": {"workload": workload_name(L, args.p, n), "m": ginfo["m"], "nnzH": nnzH,
+                       "l2": ("flushed between steps (256 MiB %s)" % args.flush_mode) if flush else "not flushed",
+                       "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
+                       "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
+                       "rows_evaluated_max_rank": int(mx[7].cpu()), "rows_total": n, "owned_hessian_entries_max_rank": int(mx[8].cpu()),
+                       "multi_gpu": None if not sharded else (
+                           "owner-computes: a rank evaluates every element touching its output rows (each element on about "
+                           "two ranks) and completes its rows of R'HR / block of g locally; only the 3 objective scalars cross "
+                           "NVLink, as epoch-tagged peer-memory words written and awaited inside the gather kernel; no NCCL on "
+                           "the data path")},
+            "clocks": clocks,
+            "e2e": dict({"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(ginfo["m"] * 8),
+                         "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned / page-locked"}, **e2e_extra),
+            "gpu_launches": int(launches),
+            "parity": None if parity is None else {"f0_rel": float(mx[4].cpu()), "grad_rel": float(mx[5].cpu()), "hess_rel": float(mx[6].cpu()),
+                                                    "against": "CPU oracle on the same inputs; max over ranks of each rank's owned rows",
+                                                    "tolerance": 1e-12},
+            "roofline": roof,
+            "wall_s_timed_region": wall,
+        }
+    views.clear()
+    if sharded:
+        mdist.destroy_peer_plan(plan)
+    else:
+        plan.close()
+    return rec
 
 
 def main():
@@ -271,9 +534,8 @@ def main():
     ap.add_argument("--flush-mode", default="read", choices=["read", "write"], help="evict L2 by reading (clean lines) or writing (dirty lines) 256 MiB")
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes for the CPU restatement (0 = all cores)")
-    ap.add_argument("--two-stage", action="store_true", help="element_kernel + gather_kernel instead of the patch-fused kernel")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
-                    help="N>1: fused peer-memory exchange (stores into the owner's window over NVLink) or the NCCL all_to_all path")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed buffers")
+    ap.add_argument("--sub", default=None, help="comma-separated extra levels timed as sub-records (default: 9 when N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -294,209 +556,26 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    pr = build_problem(args.L, args.p)
-    geom = pr["geom"]
-    n = geom.x.shape[0]
-    B = geom.block
-    E = n // B
-    from mgb_b200 import dist as mdist
-    rows = mdist.element_rows(n, B, rank, world)
     stream = torch.cuda.Stream(dev)      # a real (non-legacy) stream: programmatic dependent launch needs one
     torch.cuda.set_stream(stream)
     ctx = capi.Context(local_rank, stream.cuda_stream)
-    peer = world > 1 and args.exchange == "peer"
-    t_plan = time.perf_counter()
-    if peer:
-        plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], B, rank, world)
-        assert (plan.dinfo["row0"], plan.dinfo["row1"]) == rows
-    else:
-        plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], rows=rows,
-                         force_path=capi.PLAN_TWO_STAGE if args.two_stage else 0)
-    t_plan = time.perf_counter() - t_plan
-    nloc = rows[1] - rows[0]
-    flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
-    f64 = torch.float64
-    s_d = torch.from_numpy(pr["s"]).to(dev)
-    Dz0_d = torch.from_numpy(np.asfortranarray(pr["Dz0"][rows[0]:rows[1]]).T.copy()).to(dev)  # (nD, nloc) = column-major
-    c_d = torch.from_numpy(np.asfortranarray(pr["c"][rows[0]:rows[1]]).T.copy()).to(dev)
-    scal_d = torch.zeros(4, dtype=f64, device=dev)
-    grad_d = torch.zeros(plan.m, dtype=f64, device=dev)
-    hval_d = torch.zeros(max(plan.nnzH, 1), dtype=f64, device=dev)
-    flush = 0 if args.no_flush else (2 if args.flush_mode == "read" else 1)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize(dev)
-
-    exch = None
-    if world > 1:
-        flush_buf = torch.zeros(256 << 17, dtype=f64, device=dev)  # 256 MiB
-    if world > 1 and not peer:
-        gplan = capi.Plan(None, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"])   # replicated symbolic pattern
-        grp, gci = gplan.pattern()
-        lrp, lci = plan.pattern()
-        ex = mdist.build_exchange(rank, world, plan.m, grp.astype(np.int64), gci.astype(np.int64),
-                                  lrp.astype(np.int64), lci.astype(np.int64), dev)
-        exch = mdist.Exchanger(ex, dev, ctx=ctx, n_loc_h=plan.nnzH, m=plan.m)
-        hval_d, grad_d, scal_d = exch.views()   # local outputs live inside the exchange buffer
-
-    def step_multi(nsteps):
-        """per-step CUDA events on the launching stream, exchange inside the timed bracket.  All steps are
-        enqueued before the host waits, so the ranks are paced by their GPUs (the finish kernel / collective
-        couples them every step) and not by host launch jitter."""
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
-        for r in range(nsteps):
-            if flush == 2:
-                flush_buf.sum()  # read-evict: leaves L2 full of clean lines
-            elif flush:
-                flush_buf.fill_(float(r))
-            evs[r][0].record()
-            if peer:
-                plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags)
-            else:
-                plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
-                exch.exchange()
-            evs[r][1].record()
-        torch.cuda.synchronize(dev)
-        if peer and plan.dist_info()["err"]:
-            raise SystemExit("bench.py: a peer's epoch flag timed out (exchange window protocol error)")
-        return sum(a.elapsed_time(b) for a, b in evs) / nsteps
-
-    # ---- warm-up
-    if world == 1:
-        plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, args.warmup, flush, split=False)
-    else:
-        step_multi(args.warmup)
-    launches0 = capi.launch_count()
-    sampler = ClockSampler(local_rank)
-    barrier()
-    sampler.start()
-    wall0 = time.perf_counter()
-    if world == 1:
-        ms_total, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
-                                                         args.steps, flush, split=False)
-    else:
-        ms_total = step_multi(args.steps)
-    launches = capi.launch_count() - launches0
-    barrier()
-    wall = time.perf_counter() - wall0
-    # per-kernel split (separate pass, not part of `value`)
-    _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
-                                               max(10, args.steps // 2), flush, split=True)
-    # line-search point: objective only (SURVEY 8d: reported as a separate line, ms per f0)
-    ms_f0, _, _ = plan.time_assemble(s_d, Dz0_d, c_d, args.t, capi.WANT_F0, scal_d, grad_d, hval_d,
-                                     max(10, args.steps // 2), flush, split=False) if world == 1 else (None, 0, 0)
-    # ---- e2e through host buffers (pinned): H2D of the Newton unknown, D2H of gradient + Hessian values
-    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-    s_h = pin(pr["s"])
-    n_h = plan.dinfo["n_own_h"] if peer else (exch.ex.n_own_h if exch is not None else plan.nnzH)
-    n_g = plan.dinfo["n_own_g"] if peer else (exch.ex.n_own_g if exch is not None else plan.m)
-    views = {}
-
-    def window_views(ptrs):
-        """zero-copy tensors over the owned results inside this rank's exchange window (two parities)"""
-        if ptrs not in views:
-            views[ptrs] = tuple(torch.as_tensor(capi.DeviceView(p_, cnt), device=dev)
-                                for p_, cnt in zip(ptrs, (max(n_h, 1), max(n_g, 1), 4)))
-        return views[ptrs]
-
-    hval_h = torch.empty(max(n_h, 1), dtype=f64).pin_memory()
-    grad_h = torch.empty(max(n_g, 1), dtype=f64).pin_memory()
-    scal_h = torch.empty(4, dtype=f64).pin_memory()
-
-    def e2e_step():
-        s_d.copy_(s_h, non_blocking=True)
-        if peer:
-            ho, go, so = window_views(plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags))
-        else:
-            plan.assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d)
-        if peer:
-            ho, go = ho[:n_h], go[:n_g]
-        elif exch is not None:
-            ho, go, so = exch.exchange()
-        else:
-            ho, go, so = hval_d[:n_h], grad_d[:n_g], scal_d
-        hval_h[:n_h].copy_(ho, non_blocking=True)
-        grad_h[:n_g].copy_(go, non_blocking=True)
-        scal_h.copy_(so, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-
-    for _ in range(3):
-        e2e_step()
-    barrier()
-    e2e_steps = max(5, min(args.steps, 20))
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-    # the same call through the C ABI with plain (pageable) host buffers, as a Julia Array caller sees it
-    if world == 1:
-        plan.assemble_host(pr["s"], np.asfortranarray(pr["Dz0"]), np.asfortranarray(pr["c"]), args.t, flags, True)
-        t0 = time.perf_counter()
-        for _ in range(5):
-            plan.assemble_host(pr["s"], None, None, args.t, flags, upload_inputs=False)
-        e2e_pageable_ms = (time.perf_counter() - t0) * 1e3 / 5
-        # ... and with the caller's arrays page-locked once (mgb_host_register), reused every step
-        s_reg = pr["s"].copy()
-        outb = plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False)
-        for a in (s_reg, outb["hval"], outb["grad"], outb["scal"]):
-            capi.host_register(a)
-        plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False, out=outb)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            plan.assemble_host(s_reg, None, None, args.t, flags, upload_inputs=False, out=outb)
-        e2e_registered_ms = (time.perf_counter() - t0) * 1e3 / 10
-        for a in (s_reg, outb["hval"], outb["grad"], outb["scal"]):
-            capi.host_unregister(a)
-    else:
-        e2e_pageable_ms = e2e_registered_ms = None
-    clocks = sampler.stop()
-
-    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms], dtype=f64, device=dev)
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
-    ms_total, ms_elem, ms_gather, e2e_ms = (float(v) for v in vals.cpu())
-
+    rec = run_config(args, args.L, rank, world, local_rank, dev, ctx, stream, args.steps, args.warmup)
+    subs = []
+    sub_levels = [int(v) for v in (args.sub.split(",") if args.sub else (["9"] if world > 1 and args.sub is None else [])) if v]
+    for Ls in sub_levels:   # larger meshes on the same GPUs: where sharding has work to split
+        r = run_config(args, Ls, rank, world, local_rank, dev, ctx, stream, max(5, args.steps // 5), 3)
+        if rank == 0:
+            subs.append({"workload": r["config"]["workload"], "ms_per_step": r["value"], "parity": r["parity"],
+                         "rows_evaluated_max_rank": r["config"]["rows_evaluated_max_rank"], "rows_total": r["config"]["rows_total"],
+                         "assembly_frac_of_peak": r["roofline"]["assembly"]["frac"]})
     if rank == 0:
-        peak, peak_src = peak_hbm()
-        info = plan.info
-        alg = info["alg_bytes"]
-        # element kernel share of the algorithmic bytes: everything except the restriction line
-        nnzS = 154 * info["elements"] if info["nodes_per_element"] == 7 else 0
-        restr = nnzS * 8 + pr["R"].nnz * 24 + info["nnzH"] * 8
-        alg_elem = alg - restr
-        ach = alg_elem / (ms_elem * 1e-3) / 1e9 if ms_elem > 0 else 0.0
-        ach_all = alg / (ms_total * 1e-3) / 1e9
-        line = {
-            "metric": METRIC, "value": ms_total, "unit": "ms", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_total, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"fem2d L={args.L} p={args.p} finest-level assembly: n={n} quadrature points, "
-                                   f"m={info['m']} dofs, nnz(R'HR)={info['nnzH']}",
-                       "l2": ("flushed between steps (256 MiB %s)" % args.flush_mode) if flush else "not flushed",
-                       "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
-                       "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
-                       "rows_per_rank": nloc,
-                       "multi_gpu": None if world == 1 else (
-                           "row-block shards; push_kernel stores every result into the owner's window over NVLink peer memory "
-                           "(CUDA IPC), epoch flags, owner-side finish kernel sums interface entries in rank order; no NCCL on the data path"
-                           if peer else
-                           "row-block shards; interface rows + scalars in one NCCL all_to_all per assembly, owner-side sum in rank order")},
-            "clocks": clocks,
-            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(plan.m * 8),
-                    "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned",
-                    "c_abi_pageable_ms": e2e_pageable_ms, "c_abi_registered_ms": e2e_registered_ms},
-            "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "patch_kernel" if (os.environ.get("MGB_PATCH") and not args.two_stage) else "element_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": ncu_traffic("element_kernel", args.L), "peak_source": peak_src,
-                         "algorithmic_bytes": int(alg_elem), "kernel_ms": ms_elem,
-                         "assembly": {"algorithmic_bytes": int(alg), "ms": ms_total, "achieved": ach_all,
-                                      "frac": ach_all / peak, "gather_ms": ms_gather, "f0_ms": ms_f0}},
-            "wall_s_timed_region": wall,
-        }
+        line = {"metric": METRIC, "value": rec["value"], "unit": "ms", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": False, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
+        line.update({k: rec[k] for k in ("config", "clocks", "e2e", "gpu_launches", "parity", "roofline", "wall_s_timed_region")})
+        if subs:
+            line["sub_records"] = subs
         if world == 1 and args.cpu_reps > 0:
             try:
                 out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--L", str(args.L),
@@ -509,10 +588,8 @@ def main():
             except Exception as exc:  # pragma: no cover
                 line["cpu_baseline_error"] = str(exc)
         print(json.dumps(line))
+    ctx.close()
     if world > 1:
-        if peer:
-            views.clear()
-            mdist.destroy_peer_plan(plan)
         dist.destroy_process_group()
 
 

@@ -200,58 +200,61 @@ int mgb_host_unregister(void* ptr_host);
  * device memory, e.g. the exchange window of mgb_dist_end) */
 int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t bytes);
 
-/* ---- multi-GPU: one process per GPU, fused peer-memory exchange -----------------------
- * Replaces, for the sharded assembly, the distributed SpGEMM/transpose exchanges HPCSparseArrays runs
- * inside D_j' * diag * D_k and R' * H * R (reference test/test_map_rows_compare.jl:102-123,165-171 on
- * HPC types; collectives listed in SURVEY.md 2.2).  Quadrature rows are split by `row_part` (whole broken
- * elements: apply_D needs no halo), outputs (gradient entries, rows of R'HR) by `out_part`
- * (HPCSparseArrays row partition, a13; offsets here are 0-based, length nranks+1).  Every rank stores its
- * results directly into the owner's exchange window over NVLink peer memory; interface entries are summed
- * by the owner in rank order.  No NCCL call on the data path.
+/* ---- multi-GPU: one process per GPU, owner-computes sharding -----------------------------
+ * Replaces, for the sharded assembly, the distributed SpGEMM / transpose exchanges HPCSparseArrays runs inside
+ * D_j' * diag * D_k and R' * H * R (reference test/test_map_rows_compare.jl:102-123,165-171 on HPC types;
+ * collectives listed in SURVEY.md 2.2).  The outputs - gradient entries and rows of R'HR - are split by
+ * `out_part` (HPCSparseArrays row partition, a13; offsets 0-based, length nranks+1).  Every rank evaluates the
+ * quadrature rows of ITS block of `row_part` (whole broken elements; the reference's partition of x / w) plus the
+ * halo elements that touch one of its output rows, so every owned row is completed locally and no Hessian or
+ * gradient value crosses NVLink; only the objective scalars are summed across ranks, by peer-memory words with
+ * embedded epoch tags written from inside the gather kernel (no NCCL call, no fence, no host round trip).
  *
- *   1. mgb_dist_plan_create on every rank (same arguments except `rank`; ctx==NULL: maps only)
+ *   1. mgb_dist_plan_create on every rank (same arguments except `rank`; ctx==NULL: symbolic only)
  *   2. mgb_dist_export -> exchange the 64-byte handles between processes (MPI/NCCL/any) -> mgb_dist_attach
  *      (or mgb_dist_attach_local with raw device pointers when all ranks live in one process)
  *   3. per Newton step, collectively and in the same order on every rank: mgb_dist_assemble
- *      (= mgb_dist_begin + mgb_dist_end).  Results stay valid until the second-next assemble call.
+ *      (= mgb_dist_begin + mgb_dist_end).  Dz0 / c are n_local x nD blocks over the plan's rows (mgb_dist_rows
+ *      order); s is the replicated Newton unknown (m).  Results stay valid until the next assemble call.
+ * A peer that never delivers its scalars makes the call return NaN scalars with all_finite = 0 after
+ * MGB_DIST_TIMEOUT_S seconds (default 30) and sets the error flag of mgb_dist_info - never a silent partial sum.
  */
 typedef struct { unsigned char bytes[64]; } mgb_ipc_handle;
 
+/* General form of mgb_plan_create: the plan covers the quadrature rows rows_sel[0..nrows_sel) (global 0-based ids,
+ * whole broken elements, any order) and the output rows (unknowns) [out0, out1); only the first n_primary listed
+ * rows count in the objective scalars.  mgb_plan_create(.., row0, row1, ..) = rows row0..row1-1, all outputs. */
+int mgb_plan_create_rows(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
+                         const double* x_host, const double* w_host, const mgb_barrier* barrier, int64_t nrows_sel,
+                         const int64_t* rows_sel, int64_t n_primary, int64_t out0, int64_t out1, int32_t force_path,
+                         mgb_plan** out);
+/* Fails with "sharded plans need the element path: ..." when the level cannot be sharded (operators without
+ * broken-element structure, element type not instantiated, coarse level): assemble such a level redundantly. */
 int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R,
                          int32_t dim, const double* x_host, const double* w_host,
                          const mgb_barrier* barrier, int32_t rank, int32_t nranks,
                          const int64_t* row_part, const int64_t* out_part, mgb_plan** out);
 /* info[0]=rank, [1]=nranks, [2]=owned Hessian entries, [3]=owned unknowns, [4],[5]=owned unknown range,
- * [6]=local Hessian entries, [7],[8]=staged Hessian/gradient values received, [9],[10]=owned interface
- * Hessian/gradient entries, [11]=window doubles per parity, [12]=epoch, [13]=error flag (1: a peer's
- * epoch flag timed out), [14],[15]=local quadrature row range */
+ * [6]=local quadrature rows (primary block + halo), [7]=primary rows, [8]=local elements, [11]=window words,
+ * [12]=epoch, [13]=error flag (1: a peer's scalars timed out) */
 int mgb_dist_info(const mgb_plan* plan, int64_t* info, int32_t ninfo);
-/* window layout of any rank: {n_own_h, n_own_g, n_stg_h, n_stg_g, off_h, off_g, off_scal, off_stg_h,
- * off_stg_g, off_stg_scal, size} (doubles) */
-int mgb_dist_layout(const mgb_plan* plan, int32_t rank, int64_t* lay11);
+/* global ids of the plan's quadrature rows, in plan order (info[6] entries): row k of the Dz0 / c blocks */
+int mgb_dist_rows(const mgb_plan* plan, int64_t* rows_host);
 /* owned rows of the global pattern: rowptr (owned rows + 1, 0-based, relative), colidx (global ids) */
 int mgb_dist_pattern(const mgb_plan* plan, int32_t* rowptr_host, int32_t* colidx_host);
-/* host copies of the frozen maps (any pointer may be NULL): destination of every local Hessian entry
- * ((owner << 27) | window offset) and unknown (-1: none); owner-side interface sums (position, staging
- * ranges).  Used by the CPU tests of the host logic. */
-int mgb_dist_maps(const mgb_plan* plan, int32_t* h_dest, int32_t* g_dest, int32_t* fh_pos, int32_t* fh_ptr,
-                  int32_t* fg_pos, int32_t* fg_ptr);
 int mgb_dist_window(mgb_plan* plan, void** window_dev, int64_t* bytes);
 int mgb_dist_export(mgb_plan* plan, mgb_ipc_handle* handle);
 int mgb_dist_attach(mgb_plan* plan, const mgb_ipc_handle* handles /* nranks */);
 int mgb_dist_attach_local(mgb_plan* plan, void* const* windows_dev /* nranks */);
-/* developer timeline (plan created with MGB_DIST_DEBUG=1 in the environment): ring of 512 epochs x 8
- * globaltimer stamps {push start, stores issued, last ticket, flags published, flags seen, finish done,
- * before element kernel, -} */
-int mgb_dist_debug(mgb_plan* plan, uint64_t* out512x8);
-/* element kernel + fused gather/push kernel (asynchronous on the ctx stream) */
+/* element kernel + gather kernel; the gather's scalar block publishes this rank's partial sums (asynchronous) */
 int mgb_dist_begin(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                    int32_t flags);
-/* owner-side finish kernel: waits for every rank's epoch flag, sums interface entries, folds the scalars.
- * Returns device pointers into this rank's window: Hessian values of the owned rows (mgb_dist_pattern
- * order), owned gradient block, scalars {f0, all_finite, <c,Dz>_w, infeasible count} (global sums). */
+/* collects every rank's partial sums (small kernel).  Returns device pointers (library-owned): Hessian values of
+ * the owned rows (mgb_dist_pattern order), owned gradient block, scalars {f0, all_finite, <c,Dz>_w, infeasible
+ * count} (global sums, identical bits on every rank). */
 int mgb_dist_end(mgb_plan* plan, double t, int32_t flags, const double** hval_own_dev,
                  const double** grad_own_dev, const double** scal_dev);
+/* the same in one call; the gather kernel itself waits for the peers' words (one process per GPU only) */
 int mgb_dist_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                       int32_t flags, const double** hval_own_dev, const double** grad_own_dev,
                       const double** scal_dev);

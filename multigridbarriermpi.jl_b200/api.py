@@ -304,7 +304,7 @@ def fem3d_mpi(T=np.float64, Ti=np.int32, backend=None, **kwargs) -> Geometry:
     return native_to_mpi(geom_mod.fem3d(**_split_kwargs("fem3d", kwargs)), Ti=Ti, backend=backend)
 
 
-def amgb(g: Geometry, **kwargs) -> solver.AMGBSOL:
+def amgb(g: Geometry, /, **kwargs) -> solver.AMGBSOL:
     """amgb on an HPC-typed geometry (re-exported by the reference, src:752).  Geometry keys that
     femNd_mpi_solve forwards to both calls (src:594-600) are ignored here."""
     for k in ("L", "K", "k", "Ti", "backend", "T"):
@@ -317,7 +317,7 @@ def amgb(g: Geometry, **kwargs) -> solver.AMGBSOL:
     return solver.AMGBSOL(z, sol.SOL_feasibility, sol.SOL_main, sol.log, g, sol.stats)
 
 
-def parabolic_solve(g: Geometry, **kwargs) -> solver.ParabolicSOL:
+def parabolic_solve(g: Geometry, /, **kwargs) -> solver.ParabolicSOL:
     """parabolic_solve on an HPC-typed geometry (reference test/test_parabolic.jl:48): h, t1, p as upstream;
     snapshots come back as HPCMatrix (n x 3: u, s1, s2)."""
     be = g.x.backend if isinstance(g.x, HPCMatrix) else backend_cuda()

@@ -29,9 +29,22 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) -> str:
-    """``out``/``extra`` build tuning variants (e.g. -DMGB_ELEM_MINBLOCKS=6) next to the default library."""
+    """``out``/``extra`` build tuning variants (e.g. -DMGB_ELEM_MINBLOCKS=6) next to the default library.
+    Serialised across processes by a lock file: the ranks of one job do not compile the same library at once."""
     if not force and out == LIB and not needs_build():
         return LIB
+    import fcntl
+    with open(out + ".lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and out == LIB and not needs_build():   # another process built it while we waited
+                return LIB
+            return _build_locked(verbose, out, extra)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose: bool, out: str, extra) -> str:
     import concurrent.futures as cf
     import tempfile
     objdir = tempfile.mkdtemp(prefix="mgb_b200_obj_")
@@ -52,9 +65,13 @@ def build(force: bool = False, verbose: bool = False, out: str = LIB, extra=()) 
                 raise RuntimeError(f"nvcc failed on {src}:\n" + res.stdout + res.stderr)
             objs.append(obj)
             logs.append(res.stderr)
-    res = subprocess.run([_nvcc(), "--shared", "-o", out] + objs, capture_output=True, text=True)
+    # link next to the target and rename into place: a process that dlopens `out` concurrently (every rank of a
+    # torchrun job calls load()) sees either the old or the new complete file, never a half-written one
+    tmp_out = f"{out}.tmp.{os.getpid()}"
+    res = subprocess.run([_nvcc(), "--shared", "-o", tmp_out] + objs, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp_out, out)
     shutil.rmtree(objdir, ignore_errors=True)
     if verbose:
         sys.stderr.write("".join(logs))

@@ -26,8 +26,8 @@ EXPORTS = [
     "mgb_plan_create_local", "mgb_plan_destroy", "mgb_plan_info", "mgb_plan_pattern", "mgb_assemble", "mgb_assemble_host", "mgb_apply_D",
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_reduce", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
-    "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_layout", "mgb_dist_pattern", "mgb_dist_maps", "mgb_dist_window",
-    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_dist_debug", "mgb_host_register", "mgb_host_unregister",
+    "mgb_plan_create_rows", "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_rows", "mgb_dist_pattern", "mgb_dist_window",
+    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_host_register", "mgb_host_unregister",
 ]
 
 
@@ -68,10 +68,18 @@ def load(build_if_missing: bool = True):
     path = _build.LIB
     if build_if_missing and _build.needs_build():
         try:
-            _build.build()
-        except Exception as exc:  # no nvcc on this box: fall through to the existence check
+            nvcc = _build._nvcc()
+        except RuntimeError as exc:   # no compiler on this box: an existing (possibly older) library is all there is
+            nvcc = None
             if not os.path.exists(path):
                 raise MgbError(f"libmgb_b200.so is not built and cannot be built here: {exc}") from exc
+            import warnings
+            warnings.warn("libmgb_b200.so is older than its sources and nvcc is not available: loading the stale library")
+        if nvcc is not None:
+            try:
+                _build.build()
+            except Exception as exc:   # a failed rebuild must not silently fall back to stale kernels
+                raise MgbError(f"libmgb_b200.so is out of date and the rebuild failed: {exc}") from exc
     if not os.path.exists(path):
         raise MgbError("libmgb_b200.so missing: run __graft_entry__.build() (there is no CPU fallback)")
     lib = C.CDLL(path)
@@ -113,11 +121,12 @@ def load(build_if_missing: bool = True):
     lib.mgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.mgb_host_register.argtypes = [C.c_void_p, C.c_int64]
     lib.mgb_host_unregister.argtypes = [C.c_void_p]
-    lib.mgb_dist_debug.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mgb_plan_create_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_Csr), C.POINTER(_Csr), C.c_int32,
+                                         C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int64, C.c_void_p, C.c_int64,
+                                         C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
     lib.mgb_dist_info.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
-    lib.mgb_dist_layout.argtypes = [C.c_void_p, C.c_int32, C.c_void_p]
+    lib.mgb_dist_rows.argtypes = [C.c_void_p, C.c_void_p]
     lib.mgb_dist_pattern.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.mgb_dist_maps.argtypes = [C.c_void_p] + [C.c_void_p] * 6
     lib.mgb_dist_window.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]
     lib.mgb_dist_export.argtypes = [C.c_void_p, C.c_void_p]
     lib.mgb_dist_attach.argtypes = [C.c_void_p, C.c_void_p]
@@ -273,10 +282,17 @@ class Plan:
                 bar.idx2[j] = int(v)
         x = np.asfortranarray(x, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
-        row0, row1 = (0, n) if rows is None else rows
         h = C.c_void_p()
-        _check(lib.mgb_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1], x.ctypes.data, w.ctypes.data,
-                                   C.byref(bar), int(row0), int(row1), int(force_path), C.byref(h)))
+        if rows is not None and not (isinstance(rows, tuple) and len(rows) == 2):
+            # explicit list of quadrature rows (whole elements, any order): mgb_plan_create_rows, all outputs
+            ridx = np.ascontiguousarray(rows, dtype=np.int64)
+            _check(lib.mgb_plan_create_rows(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1], x.ctypes.data,
+                                            w.ctypes.data, C.byref(bar), int(ridx.size), ridx.ctypes.data, int(ridx.size), 0, -1,
+                                            int(force_path), C.byref(h)))
+        else:
+            row0, row1 = (0, n) if rows is None else rows
+            _check(lib.mgb_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1], x.ctypes.data, w.ctypes.data,
+                                       C.byref(bar), int(row0), int(row1), int(force_path), C.byref(h)))
         self._finish_init(h)
 
     @classmethod
@@ -383,23 +399,20 @@ class Plan:
             pass
 
 
-DIST_RANK_SHIFT = 27
-DIST_OFF_MASK = (1 << DIST_RANK_SHIFT) - 1
-
-
 class DistPlan(Plan):
-    """Sharded plan with the fused peer-memory exchange (mgb_dist_*): one instance per rank.
+    """Sharded plan, owner-computes (mgb_dist_*): one instance per rank.
 
-    ``row_part`` / ``out_part``: 0-based offsets (length nranks+1) of the quadrature rows (whole elements)
-    and of the unknowns.  ``ctx=None`` builds the maps only (CPU tests of the host logic)."""
+    ``row_part`` / ``out_part``: 0-based offsets (length nranks+1) of the quadrature rows (whole elements) and of
+    the unknowns.  The plan evaluates this rank's block of quadrature rows plus the halo elements touching its
+    output rows (``rows``: their global ids, in the order of the Dz0 / c blocks the numeric calls take) and
+    completes the owned rows of R'HR / block of the gradient locally; only the objective scalars cross the ranks.
+    ``ctx=None`` builds the symbolic part only (CPU tests of the host logic)."""
 
-    DINFO = ["rank", "nranks", "n_own_h", "n_own_g", "own0", "own1", "n_local_h", "n_stg_h", "n_stg_g", "n_fh", "n_fg",
-             "window_doubles", "epoch", "err", "row0", "row1"]
-    LAYOUT = ["n_own_h", "n_own_g", "n_stg_h", "n_stg_g", "off_h", "off_g", "off_scal", "off_stg_h", "off_stg_g",
-              "off_stg_scal", "size"]
+    DINFO = ["rank", "nranks", "n_own_h", "n_own_g", "own0", "own1", "n_rows", "n_primary", "elements", "_9", "_10",
+             "window_words", "epoch", "err", "_14", "_15"]
 
     def __init__(self, ctx: Optional[Context], D, R, x, w, idx, p: float, rank: int, nranks: int, row_part, out_part,
-                 slack: bool = False):
+                 slack: bool = False, idx2: Optional[Sequence[int]] = None, p2: float = 2.0):
         lib = load()
         self.ctx = ctx
         n = D[0].shape[0]
@@ -410,6 +423,10 @@ class DistPlan(Plan):
         bar.kind, bar.nidx, bar.p, bar.slack = BARRIER_EUCLIDIAN_POWER, len(idx), float(p), int(bool(slack))
         for j, v in enumerate(idx):
             bar.idx[j] = int(v)
+        if idx2:
+            bar.nidx2, bar.p2 = len(idx2), float(p2)
+            for j, v in enumerate(idx2):
+                bar.idx2[j] = int(v)
         x = np.asfortranarray(x, dtype=np.float64)
         w = np.ascontiguousarray(w, dtype=np.float64)
         rp = np.ascontiguousarray(row_part, dtype=np.int64)
@@ -419,47 +436,29 @@ class DistPlan(Plan):
         _check(lib.mgb_dist_plan_create(ctx._h if ctx is not None else None, n, len(D), Ds, C.byref(Rs), x.shape[1],
                                         x.ctypes.data, w.ctypes.data, C.byref(bar), int(rank), int(nranks),
                                         rp.ctypes.data, op.ctypes.data, C.byref(h)))
-        self._h = h
-        info = np.zeros(16, dtype=np.int64)
-        _check(lib.mgb_plan_info(h, info.ctypes.data, 16))
-        self.info = dict(zip(self.INFO, (int(v) for v in info)))
-        self.n_local, self.nD, self.m, self.nnzH = (self.info[k] for k in ("n_local", "nD", "m", "nnzH"))
-        self._pattern = None
+        self._finish_init(h)
         self.rank, self.nranks = int(rank), int(nranks)
         self.dinfo = self.dist_info()
-        self._own_pattern = None
+        self.rows = np.zeros(self.dinfo["n_rows"], dtype=np.int64)
+        _check(lib.mgb_dist_rows(h, self.rows.ctypes.data))
 
     def dist_info(self) -> dict:
         v = np.zeros(16, dtype=np.int64)
         _check(load().mgb_dist_info(self._h, v.ctypes.data, 16))
-        return dict(zip(self.DINFO, (int(a) for a in v)))
-
-    def layout(self, rank: int) -> dict:
-        v = np.zeros(11, dtype=np.int64)
-        _check(load().mgb_dist_layout(self._h, int(rank), v.ctypes.data))
-        return dict(zip(self.LAYOUT, (int(a) for a in v)))
+        return {k: int(a) for k, a in zip(self.DINFO, v) if not k.startswith("_")}
 
     def own_pattern(self):
         """(rowptr, colidx) of the owned rows of R'HR (rowptr relative to the block, global column ids)."""
-        if self._own_pattern is None:
+        if self._pattern is None:
             d = self.dinfo
             rp = np.zeros(d["own1"] - d["own0"] + 1, dtype=np.int32)
             ci = np.zeros(max(d["n_own_h"], 1), dtype=np.int32)
             _check(load().mgb_dist_pattern(self._h, rp.ctypes.data, ci.ctypes.data))
-            self._own_pattern = (rp, ci[: d["n_own_h"]])
-        return self._own_pattern
+            self._pattern = (rp, ci[: d["n_own_h"]])
+        return self._pattern
 
-    def maps(self) -> dict:
-        d = self.dinfo
-        out = dict(h_dest=np.zeros(max(d["n_local_h"], 1), np.int32), g_dest=np.zeros(max(self.m, 1), np.int32),
-                   fh_pos=np.zeros(max(d["n_fh"], 1), np.int32), fh_ptr=np.zeros(d["n_fh"] + 1, np.int32),
-                   fg_pos=np.zeros(max(d["n_fg"], 1), np.int32), fg_ptr=np.zeros(d["n_fg"] + 1, np.int32))
-        _check(load().mgb_dist_maps(self._h, *[out[k].ctypes.data for k in ("h_dest", "g_dest", "fh_pos", "fh_ptr", "fg_pos", "fg_ptr")]))
-        out["h_dest"] = out["h_dest"][: d["n_local_h"]]
-        out["g_dest"] = out["g_dest"][: self.m]
-        out["fh_pos"] = out["fh_pos"][: d["n_fh"]]
-        out["fg_pos"] = out["fg_pos"][: d["n_fg"]]
-        return out
+    def pattern(self):
+        return self.own_pattern()
 
     def window(self):
         p, b = C.c_void_p(), C.c_int64(0)
@@ -484,15 +483,10 @@ class DistPlan(Plan):
         _check(load().mgb_dist_begin(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags)))
 
     def end(self, t: float, flags: int):
-        """-> device pointers (hval_own, grad_own, scal) into this rank's window"""
+        """-> device pointers (hval_own, grad_own, scal), library-owned"""
         hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(load().mgb_dist_end(self._h, float(t), int(flags), C.byref(hp), C.byref(gp), C.byref(sp_)))
         return int(hp.value), int(gp.value), int(sp_.value)
-
-    def debug_timeline(self) -> np.ndarray:
-        out = np.zeros((512, 8), dtype=np.uint64)
-        _check(load().mgb_dist_debug(self._h, out.ctypes.data))
-        return out
 
     def dist_assemble(self, s_dev, Dz0_dev, c_dev, t: float, flags: int):
         hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()

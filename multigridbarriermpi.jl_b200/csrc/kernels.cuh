@@ -25,6 +25,8 @@ namespace mgb {
 struct ElemParams {
     // geometry / plan (device)
     int64_t E, nloc;
+    int64_t Eprim;           // elements [0, Eprim) count in the objective / <c,Dz> / feasibility scalars (a sharded plan
+                             // also evaluates halo elements whose scalars another rank owns); E unless sharded
     const int32_t* lcols;    // [E][NU][LPE] element -> dof (-1: eliminated)
     const double* prec;      // [nloc][RW] per-point record: derivative rows (D*B), w, then
                              //   fine:   own_val[NU], own_lq bytes packed in one 8-byte slot
@@ -260,9 +262,10 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
         double cd = 0.0;
 #pragma unroll
         for (int k = 0; k < ND; ++k) cd = fma(cc[k], dz[k], cd);
-        v0 = (WF && act) ? wi * bo.F : 0.0;
-        v1 = act ? wi * cd : 0.0;
-        v2 = (act && !bo.feasible) ? 1.0 : 0.0;
+        const bool act_s = act && e < P.Eprim;
+        v0 = (WF && act_s) ? wi * bo.F : 0.0;
+        v1 = act_s ? wi * cd : 0.0;
+        v2 = (act_s && !bo.feasible) ? 1.0 : 0.0;
     }
     // an infeasible point produces NaN/Inf values; they flow to the outputs as data (the caller
     // reads all_finite, like amgb_all_isfinite in the reference, src:121-133)
@@ -611,8 +614,91 @@ static __global__ void __launch_bounds__(256) interface_kernel(const InterfacePa
     }
 }
 
-// one block of 256 threads folds the per-block scalar partials in a fixed order -> {f0, all_finite, <c,Dz>_w, count}
-__device__ __forceinline__ void fold_scalars_block(const double* __restrict__ part, int64_t nparts, double t, double* __restrict__ scal) {
+// Cross-rank sum of the three objective scalars without a fence or a collective: every 64-bit word that crosses
+// NVLink carries half a double and the 32-bit epoch of the assembly it belongs to, so a single relaxed system-scope
+// store is self-validating (the protocol idea of NCCL's LL mode).  Word w of source rank q of epoch parity par sits at
+// win[(par * DIST_LL_RANKS + q) * 8 + w] in every rank's window.  Two parities: a rank can run at most one epoch
+// ahead of a peer (it cannot finish epoch k+1 without the peer's k+1 words, which the peer sends after reading k).
+constexpr int DIST_LL_RANKS = 16;
+struct DistScal {
+    int rank, nranks;                           // nranks <= 1: single rank, nothing crosses
+    unsigned epoch;                             // never 0
+    unsigned long long* win[DIST_LL_RANKS];     // every rank's window (own included), peer-mapped
+    int publish_only;                           // split mode (mgb_dist_begin): store the partials, do not wait
+    unsigned long long timeout_ns;
+    int* err;                                   // set to 1 when a peer's words did not arrive in time
+};
+
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// this rank's three partial sums -> every rank's window (threads 0 .. 6*nranks-1 of the block; one word each)
+__device__ __forceinline__ void dist_publish(const DistScal& D, const double* __restrict__ tot /* 3, shared */) {
+    const int tid = threadIdx.x;
+    if (tid < 6 * D.nranks) {
+        const int p = tid / 6, w = tid % 6;
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(tot[w >> 1]);
+        const unsigned long long half = (w & 1) ? (bits >> 32) : (bits & 0xFFFFFFFFull);
+        st_relaxed_sys(D.win[p] + (((D.epoch & 1u) * DIST_LL_RANKS + D.rank) * 8 + w), ((unsigned long long)D.epoch << 32) | half);
+    }
+}
+// every rank's partial sums of this epoch -> sums in rank order (identical on every rank).  Returns false on time-out.
+__device__ __forceinline__ bool dist_collect(const DistScal& D, double* __restrict__ sum /* 3, thread 0 only */) {
+    __shared__ unsigned int half_s[DIST_LL_RANKS * 6];
+    __shared__ int bad_s;
+    const int tid = threadIdx.x;
+    if (tid == 0) bad_s = 0;
+    __syncthreads();
+    if (tid < 6 * D.nranks) {
+        const int q = tid / 6, w = tid % 6;
+        const unsigned long long* src = D.win[D.rank] + (((D.epoch & 1u) * DIST_LL_RANKS + q) * 8 + w);
+        const unsigned long long t0 = global_timer_ns();
+        unsigned long long word = ld_relaxed_sys(src);
+        while ((unsigned)(word >> 32) != D.epoch) {
+            if (global_timer_ns() - t0 > D.timeout_ns) { bad_s = 1; break; }
+            word = ld_relaxed_sys(src);
+        }
+        half_s[tid] = (unsigned)(word & 0xFFFFFFFFull);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        sum[0] = sum[1] = sum[2] = 0.0;
+        for (int q = 0; q < D.nranks; ++q)
+            for (int k = 0; k < 3; ++k)
+                sum[k] += __longlong_as_double((long long)(((unsigned long long)half_s[q * 6 + 2 * k + 1] << 32) | half_s[q * 6 + 2 * k]));
+        if (bad_s && D.err) atomicExch(D.err, 1);
+    }
+    return bad_s == 0;   // valid on thread 0 (it wrote and read bad_s around barriers); others do not use it
+}
+
+__device__ __forceinline__ void write_scalars(double s0, double s1, double s2, double t, bool ok, double* __restrict__ scal) {
+    if (!scal) return;
+    if (ok) {
+        scal[0] = s0 + t * s1;
+        scal[1] = (s2 == 0.0) ? 1.0 : 0.0;
+        scal[2] = s1;
+        scal[3] = s2;
+    } else {   // a peer never delivered: poison the result instead of returning a partial sum as if it were the objective
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        scal[0] = nan; scal[1] = 0.0; scal[2] = nan; scal[3] = -1.0;
+    }
+}
+
+// one block of 256 threads folds the per-block scalar partials in a fixed order -> {f0, all_finite, <c,Dz>_w, count};
+// with several ranks (dist.nranks > 1) the three sums first cross the ranks (dist_publish / dist_collect)
+__device__ __forceinline__ void fold_scalars_block(const double* __restrict__ part, int64_t nparts, double t, double* __restrict__ scal,
+                                                   const DistScal* dist = nullptr) {
     __shared__ double sh[3][256];
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     for (int64_t r = threadIdx.x; r < nparts; r += blockDim.x) {
@@ -630,15 +716,22 @@ __device__ __forceinline__ void fold_scalars_block(const double* __restrict__ pa
         }
         __syncthreads();
     }
-    if (threadIdx.x == 0 && scal) {
-        scal[0] = sh[0][0] + t * sh[1][0];
-        scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
-        scal[2] = sh[1][0];
-        scal[3] = sh[2][0];
+    if (dist && dist->nranks > 1) {
+        __shared__ double tot[3];
+        if (threadIdx.x == 0) { tot[0] = sh[0][0]; tot[1] = sh[1][0]; tot[2] = sh[2][0]; }
+        __syncthreads();
+        dist_publish(*dist, tot);
+        if (dist->publish_only) return;
+        double sum[3];
+        const bool ok = dist_collect(*dist, sum);
+        if (threadIdx.x == 0) write_scalars(sum[0], sum[1], sum[2], t, ok, scal);
+        return;
     }
+    if (threadIdx.x == 0) write_scalars(sh[0][0], sh[1][0], sh[2][0], t, true, scal);
 }
 
 struct GatherParams {
+    DistScal dist;           // cross-rank sum of the scalars (nranks <= 1: none)
     int64_t nnzH, m;
     const int2* h_src2;       // per entry: {first, second} contribution slot; second = -1 if none;
                               // first < 0 : entry -1-first of the long list (more than two contributions)
@@ -738,7 +831,7 @@ static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P
     }
     // scalar block
     pdl_wait_primary();
-    fold_scalars_block(P.part, P.nparts, P.t, P.scal);
+    fold_scalars_block(P.part, P.nparts, P.t, P.scal, &P.dist);
 }
 
 // Coarse multigrid levels: few outputs with long contribution lists.  One launch serves up to two lists (Hessian

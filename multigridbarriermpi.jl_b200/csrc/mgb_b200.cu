@@ -106,6 +106,8 @@ struct mgb_plan {
     mgb_ctx* ctx = nullptr;
     int path = 0;
     int64_t n = 0, nloc = 0, N = 0, m = 0, nnzH = 0;
+    int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (all of them unless sharded)
+    int64_t n_primary = 0;         // leading local quadrature rows that count in the scalars (nloc unless sharded)
     int ND = 0, NU = 0, dim = 0;
     mgb::BarrierDesc bar;
     std::vector<int32_t> h_rowptr, h_colidx;
@@ -153,27 +155,22 @@ struct mgb_plan {
     // ---- host staging for the *_host entry point
     DevBuf<double> st_s, st_dz0, st_c, st_scal, st_grad, st_hval, st_dz;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    // ---- multi-GPU peer exchange (mgb_dist_*)
+    // ---- multi-GPU, owner-computes sharding (mgb_dist_*)
     struct Dist {
-        mgb::DistMaps maps;
-        DevBuf<int32_t> h_dest, fh_pos, fh_ptr, fg_pos, fg_ptr;
-        DevBuf<int2> g_dest;             // {unknown, destination} of the unknowns this rank contributes to
-        int64_t n_gtouch = 0;
-        DevBuf<unsigned int> counter;
+        int rank = 0, nranks = 1;
+        std::vector<int64_t> rows;        // global quadrature rows of this plan, in plan order (primary block first)
+        DevBuf<double> hval, grad, scal;  // owned rows of R'HR (mgb_dist_pattern order), owned gradient block, scalars
         DevBuf<int> err;
-        DevBuf<unsigned long long> dbg;  // MGB_DIST_DEBUG: ring of 512 epochs x 8 timeline slots
-        void* window = nullptr;        // [parity 0 | parity 1 | flags]; cudaMalloc'ed, exported by IPC handle
+        void* window = nullptr;           // scalar exchange words [2 parities][DIST_LL_RANKS][8]; cudaMalloc'ed, IPC-exported
         size_t window_bytes = 0;
-        void* peer[mgb::DIST_MAX_RANKS] = {nullptr};
-        bool peer_ipc[mgb::DIST_MAX_RANKS] = {false};
+        void* peer[mgb::DIST_LL_RANKS] = {nullptr};
+        bool peer_ipc[mgb::DIST_LL_RANKS] = {false};
         bool attached = false;
-        unsigned long long epoch = 0;
+        unsigned epoch = 0;
         bool finish_pending = false;
-        int64_t h_rot = 0;             // first push block whose entries belong to a higher rank (remote stores first)
-        int64_t h_own = 0;             // local Hessian entries owned by this rank
-        double timeout_s = 2.0;
+        double timeout_s = 30.0;
         ~Dist() {
-            for (int p = 0; p < mgb::DIST_MAX_RANKS; ++p)
+            for (int p = 0; p < mgb::DIST_LL_RANKS; ++p)
                 if (peer_ipc[p] && peer[p]) cudaIpcCloseMemHandle(peer[p]);
             if (window) cudaFree(window);
         }
@@ -227,6 +224,29 @@ mgb::HostCSR to_host_csr(const mgb_csr& A, int64_t row0, int64_t row1) {
         if (j < 0 || j >= A.ncols) throw std::runtime_error("column index outside matrix");
         H.idx[p] = j;
         H.val[p] = A.vals[p0 + p];
+    }
+    sort_rows(H);
+    return H;
+}
+
+// rows `rows[0..cnt)` of A (global 0-based row ids, any order) as a host CSR block
+mgb::HostCSR to_host_csr_rows(const mgb_csr& A, const int64_t* rows, int64_t cnt) {
+    mgb::HostCSR H;
+    const int base = A.index_base;
+    H.nrows = cnt; H.ncols = A.ncols;
+    H.ptr.assign(cnt + 1, 0);
+    for (int64_t i = 0; i < cnt; ++i) {
+        if (rows[i] < 0 || rows[i] >= A.nrows) throw std::runtime_error("row id outside matrix");
+        H.ptr[i + 1] = H.ptr[i] + (A.rowptr[rows[i] + 1] - A.rowptr[rows[i]]);
+    }
+    H.idx.resize(H.ptr[cnt]); H.val.resize(H.ptr[cnt]);
+    for (int64_t i = 0; i < cnt; ++i) {
+        const int64_t p0 = A.rowptr[rows[i]] - base;
+        for (int64_t q = H.ptr[i]; q < H.ptr[i + 1]; ++q) {
+            const int32_t j = A.colidx[p0 + (q - H.ptr[i])] - base;
+            if (j < 0 || j >= A.ncols) throw std::runtime_error("column index outside matrix");
+            H.idx[q] = j; H.val[q] = A.vals[p0 + (q - H.ptr[i])];
+        }
     }
     sort_rows(H);
     return H;
@@ -287,7 +307,7 @@ void launch_dependent(void (*kernel)(Params), unsigned grid, unsigned block, cud
 mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, double* Dz) {
     const auto& ep = pl->ep;
     mgb::ElemParams P{};
-    P.E = ep.E; P.nloc = ep.nloc;
+    P.E = ep.E; P.nloc = ep.nloc; P.Eprim = pl->n_primary / std::max(ep.B, 1);
     P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
     P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p; P.p2 = pl->bar.p2;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
@@ -299,7 +319,7 @@ mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz
 // two-wide ELL + long-list replay parameters of the thread-per-entry gather (fine levels)
 mgb::GatherParams make_gather_params(mgb_plan* pl, int flags, double t, double* scal, double* grad, double* hval) {
     mgb::GatherParams G{};
-    G.nnzH = pl->nnzH; G.m = pl->m;
+    G.nnzH = pl->nnzH; G.m = pl->m_out;
     G.h_src2 = pl->d_hsrc2.p; G.h_lptr = pl->d_hlptr.p; G.h_lidx = pl->d_hlidx.p; G.h_lt = pl->d_hlt.p;
     G.g_cptr = pl->d_gcptr.p; G.g_cidx = pl->d_gcidx.p;
     G.sel = pl->d_sel.p; G.rel = pl->d_rel.p; G.hval = hval; G.grad = grad;
@@ -311,13 +331,14 @@ mgb::GatherParams make_gather_params(mgb_plan* pl, int flags, double t, double* 
 
 void size_gather_grid(mgb_plan* pl, mgb::GatherParams& G) {
     G.nblk_h = G.want_h ? (pl->nnzH + 256 * mgb::GATHER_UNROLL - 1) / (256 * mgb::GATHER_UNROLL) : 0;
-    G.nblk_g = G.want_g ? (pl->m + 255) / 256 : 0;
+    G.nblk_g = G.want_g ? (pl->m_out + 255) / 256 : 0;
     G.n_long = G.want_h ? pl->n_long : 0;
     G.nblk_l = (G.n_long + 255) / 256;
 }
 
 void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, int flags,
-                      double* scal, double* grad, double* hval, double* Dz, cudaEvent_t mid = nullptr) {
+                      double* scal, double* grad, double* hval, double* Dz, cudaEvent_t mid = nullptr,
+                      const mgb::DistScal* dscal = nullptr) {
     cudaStream_t st = pl->ctx->stream;
     const auto& ep = pl->ep;
     mgb::ElemParams P = make_elem_params(pl, s, Dz0, c, t, Dz);
@@ -354,7 +375,9 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     if (mid) CUDA_OK(cudaEventRecord(mid, st));
 
     mgb::GatherParams G = make_gather_params(pl, flags, t, scal ? scal : pl->d_scal_tmp.p, grad, hval);
+    if (dscal) G.dist = *dscal;
     if (pl->long_lists) {
+        if (dscal) throw std::runtime_error("sharded plans use the thread-per-entry gather (fine levels)");
         // coarse levels: few output entries with long lists.  Stage 1: one warp (or 8 lanes) per output, or per chunk
         // of a chunked list; stage 2 (only with chunked lists): the partial sums of every output.  The scalar fold
         // rides in the last launch.
@@ -373,7 +396,7 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
         };
         mgb::WarpGatherParams W1{}, W2{};
         if (G.want_h) { W1.a = stage1(pl->ck_h, pl->nnzH, pl->n_hcontrib, pl->d_hcptr.p, pl->d_hcidx.p, G.sel, hval); W2.a = stage2(pl->ck_h, pl->nnzH, hval); }
-        if (G.want_g) { W1.b = stage1(pl->ck_g, pl->m, pl->n_gcontrib, G.g_cptr, G.g_cidx, G.rel, grad); W2.b = stage2(pl->ck_g, pl->m, grad); }
+        if (G.want_g) { W1.b = stage1(pl->ck_g, pl->m_out, pl->n_gcontrib, G.g_cptr, G.g_cidx, G.rel, grad); W2.b = stage2(pl->ck_g, pl->m_out, grad); }
         const bool two = W2.a.nblk + W2.b.nblk > 0;
         mgb::WarpGatherParams& last = two ? W2 : W1;
         last.part = G.part; last.nparts = G.nparts; last.t = G.t; last.scal = G.scal;
@@ -399,7 +422,7 @@ namespace {
 // Everything after the inputs are on the host in canonical form: symbolic phase, uploads, replay lists.
 // Dh: the operators restricted to this plan's quadrature rows (nloc x N), wloc: their weights.
 void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, mgb::HostCSR& Rh, std::vector<double>& wloc,
-                 int64_t n, int nD, int dim, int force_path, int64_t nnzD) {
+                 int64_t n, int nD, int dim, int force_path, int64_t nnzD, int64_t out0 = 0, int64_t out1 = -1, int64_t n_primary = -1) {
         mgb_ctx* ctx = pl->ctx;
         const bool host_only = (ctx == nullptr);
         pl->NU = (int)(pl->N / n);
@@ -409,9 +432,15 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         const int force_flags = force_path;
         force_path &= 3;
         pl->has_hessian = want_hess;
+        if (out1 < 0) out1 = pl->m;
+        pl->out0 = out0; pl->m_out = out1 - out0;
+        pl->n_primary = n_primary < 0 ? pl->nloc : n_primary;
+        const bool sharded = out0 != 0 || out1 != pl->m || pl->n_primary != pl->nloc;
+        if (sharded && force_path == MGB_PATH_CSR) throw std::runtime_error("sharded plans need the element path");
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess);
+            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess, out0, out1);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
+            if (!use_elem && sharded) throw std::runtime_error(std::string("sharded plans need the element path: ") + (pl->ep.ok ? "element type not instantiated" : pl->ep.why));
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
                 throw std::runtime_error("element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
         }
@@ -422,8 +451,6 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->nnzH = (int64_t)ep.h_colidx.size();
             pl->h_rowptr = ep.h_rowptr; pl->h_colidx = ep.h_colidx;
             pl->n_hcontrib = (int64_t)ep.h_cidx.size(); pl->n_gcontrib = (int64_t)ep.g_cidx.size();
-          if (!host_only) {
-            pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
             {
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
                 // lists averaging more than six contributions go to the lanes-per-output gather (fem1d L=16 level 12,
@@ -432,6 +459,8 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 const char* ev = getenv("MGB_LONG_AVG");
                 pl->long_lists = avg > (ev ? atof(ev) : 6.0);
             }
+          if (!host_only) {
+            pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
             if (patch_requested(force_flags, ep)) {
                 // patch-fused path builds its own lists below
             } else if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
@@ -439,7 +468,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 // chunk only where it pays: lists of a thousand contributions and more (coarsest levels)
                 const int64_t ch = gather_chunk();
                 if (ch > 0 && (int64_t)ep.h_cidx.size() >= 1024 * std::max<int64_t>(pl->nnzH, 1)) pl->ck_h.build(ep.h_cptr, ch, st);
-                if (ch > 0 && (int64_t)ep.g_cidx.size() >= 1024 * std::max<int64_t>(pl->m, 1)) pl->ck_g.build(ep.g_cptr, ch, st);
+                if (ch > 0 && (int64_t)ep.g_cidx.size() >= 1024 * std::max<int64_t>(pl->m_out, 1)) pl->ck_g.build(ep.g_cptr, ch, st);
             } else {   // two-wide ELL + long list for the thread-per-entry gather
                 std::vector<int2> src2(pl->nnzH);
                 std::vector<int64_t> lptr(1, 0);
@@ -480,7 +509,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             if (pl->patch == 0) pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);
-            pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m));
+            pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m_out));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
             const int epb = pl->patch > 0 ? pl->patch : MGB_ELEM_THREADS / ep.LPE;
@@ -622,6 +651,31 @@ int mgb_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const
     } catch (const std::exception& ex) { return fail(std::string("mgb_plan_create: ") + ex.what()); }
 }
 
+int mgb_plan_create_rows(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
+                         const double* x_host, const double* w_host, const mgb_barrier* barrier, int64_t nrows_sel,
+                         const int64_t* rows_sel, int64_t n_primary, int64_t out0, int64_t out1, int32_t force_path,
+                         mgb_plan** out) {
+    try {
+        if (!D || !R || !w_host || !barrier || !out || (!rows_sel && nrows_sel > 0)) return fail("mgb_plan_create_rows: NULL argument");
+        if (nrows_sel < 0 || n_primary < 0 || n_primary > nrows_sel) return fail("mgb_plan_create_rows: bad row counts");
+        const bool host_only = (ctx == nullptr);
+        auto pl = std::make_unique<mgb_plan>();
+        if (const char* why = init_plan(*pl, ctx, n, nD, D, R, dim, barrier)) return fail(std::string("mgb_plan_create_rows: ") + why);
+        pl->nloc = nrows_sel;
+        (void)x_host;
+        if (!host_only) CUDA_OK(cudaSetDevice(ctx->device));
+        std::vector<mgb::HostCSR> Dh(nD);
+        int64_t nnzD = 0;
+        for (int k = 0; k < nD; ++k) { Dh[k] = to_host_csr_rows(D[k], rows_sel, nrows_sel); nnzD += Dh[k].nnz(); }
+        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+        std::vector<double> wloc((size_t)nrows_sel);
+        for (int64_t i = 0; i < nrows_sel; ++i) wloc[i] = w_host[rows_sel[i]];
+        finish_plan(pl, Dh, Rh, wloc, n, nD, dim, force_path, nnzD, out0, out1, n_primary);
+        *out = pl.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_plan_create_rows: ") + ex.what()); }
+}
+
 int mgb_plan_create_local(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_hpc_block* D, const mgb_csr* R, int32_t dim,
                           const double* x_local_host, const double* w_local_host, const mgb_barrier* barrier,
                           int32_t force_path, mgb_plan** out) {
@@ -729,7 +783,7 @@ int mgb_assemble_host(mgb_plan* pl, const double* s_host, const double* Dz0_host
         const size_t nd = (size_t)pl->nloc * pl->ND;
         if (!pl->st_s.p) {
             pl->st_s.alloc(pl->m); pl->st_dz0.alloc(nd); pl->st_c.alloc(nd); pl->st_scal.alloc(4);
-            pl->st_grad.alloc(pl->m); pl->st_hval.alloc(pl->nnzH); pl->st_dz.alloc(nd);
+            pl->st_grad.alloc(std::max<int64_t>(pl->m_out, 1)); pl->st_hval.alloc(pl->nnzH); pl->st_dz.alloc(nd);
             CUDA_OK(cudaMemsetAsync(pl->st_dz0.p, 0, nd * 8, st));
             CUDA_OK(cudaMemsetAsync(pl->st_c.p, 0, nd * 8, st));
             upload_inputs = 1;
@@ -744,7 +798,7 @@ int mgb_assemble_host(mgb_plan* pl, const double* s_host, const double* Dz0_host
         if (rc) return rc;
         if (scal_host) CUDA_OK(cudaMemcpyAsync(scal_host, pl->st_scal.p, 32, cudaMemcpyDeviceToHost, st));
         if ((flags & MGB_WANT_GRAD) && grad_host)
-            CUDA_OK(cudaMemcpyAsync(grad_host, pl->st_grad.p, pl->m * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_OK(cudaMemcpyAsync(grad_host, pl->st_grad.p, pl->m_out * 8, cudaMemcpyDeviceToHost, st));
         if ((flags & MGB_WANT_HESS) && hval_host)
             CUDA_OK(cudaMemcpyAsync(hval_host, pl->st_hval.p, pl->nnzH * 8, cudaMemcpyDeviceToHost, st));
         if ((flags & MGB_STORE_DZ) && Dz_host)
@@ -1009,66 +1063,59 @@ int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t 
     } catch (const std::exception& ex) { return fail(std::string("mgb_copy_to_host: ") + ex.what()); }
 }
 
-// ------------------------------------------------------------------ multi-GPU peer exchange
+// ------------------------------------------------------------------ multi-GPU: owner-computes sharding
 int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, const mgb_csr* R, int32_t dim,
                          const double* x_host, const double* w_host, const mgb_barrier* barrier, int32_t rank,
                          int32_t nranks, const int64_t* row_part, const int64_t* out_part, mgb_plan** out) {
     try {
         if (!D || !R || !w_host || !barrier || !row_part || !out_part || !out) return fail("mgb_dist_plan_create: NULL argument");
-        if (nranks < 1 || nranks > mgb::DIST_MAX_RANKS || rank < 0 || rank >= nranks) return fail("mgb_dist_plan_create: bad rank / nranks (1..16)");
+        if (nranks < 1 || nranks > mgb::DIST_LL_RANKS || rank < 0 || rank >= nranks) return fail("mgb_dist_plan_create: bad rank / nranks (1..16)");
+        if (nD < 1 || nD > 8) return fail("mgb_dist_plan_create: nD must be 1..8");
+        if (row_part[0] != 0 || row_part[nranks] != n || out_part[0] != 0 || out_part[nranks] != R->ncols)
+            return fail("mgb_dist_plan_create: partitions must cover [0,n) and [0,m)");
+        for (int r = 0; r < nranks; ++r)
+            if (row_part[r + 1] < row_part[r] || out_part[r + 1] < out_part[r]) return fail("mgb_dist_plan_create: partition offsets must be non-decreasing");
+        // replicated element structure (host only, no Hessian lists): which elements touch this rank's output rows
+        std::vector<int64_t> rows;
+        int64_t n_primary = 0;
+        {
+            mgb_plan tmp;
+            if (const char* why = init_plan(tmp, nullptr, n, nD, D, R, dim, barrier)) return fail(std::string("mgb_dist_plan_create: ") + why);
+            std::vector<mgb::HostCSR> Dh(nD);
+            for (int k = 0; k < nD; ++k) Dh[k] = to_host_csr(D[k], 0, n);
+            mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
+            mgb::ElementPlan gp;
+            mgb::build_element_plan(Dh, Rh, n, w_host, tmp.bar, gp, /*want_hessian=*/false);
+            if (!gp.ok) return fail("mgb_dist_plan_create: sharded plans need the element path: " + gp.why);
+            if (!elem_supported(gp.B, gp.dim)) return fail("mgb_dist_plan_create: sharded plans need the element path: element type not instantiated");
+            // decided from the replicated (global) structure so that every rank takes the same branch: only levels whose
+            // id-like operators own one column per row (the fine ones, where the work is) are sharded
+            if (!gp.fine) return fail("mgb_dist_plan_create: sharded plans need the element path with thread-per-entry gather: coarse level");
+            for (int r = 0; r <= nranks; ++r)
+                if (row_part[r] % gp.B) return fail("mgb_dist_plan_create: row partition splits a broken element");
+            mgb::dist_select_elements(gp.lcols, gp.E, gp.NU, gp.LPE, gp.B, rank, nranks, out_part, rows, n_primary);
+        }
         mgb_plan* plraw = nullptr;
-        int rc = mgb_plan_create(ctx, n, nD, D, R, dim, x_host, w_host, barrier, row_part[rank], row_part[rank + 1],
-                                 MGB_PATH_ELEMENT | MGB_PLAN_TWO_STAGE, &plraw);
+        int rc = mgb_plan_create_rows(ctx, n, nD, D, R, dim, x_host, w_host, barrier, (int64_t)rows.size(), rows.data(), n_primary,
+                                      out_part[rank], out_part[rank + 1], MGB_PATH_ELEMENT | MGB_PLAN_TWO_STAGE, &plraw);
         if (rc) return rc;
         std::unique_ptr<mgb_plan, int (*)(mgb_plan*)> pl(plraw, mgb_plan_destroy);
         if (pl->patch > 0 || pl->long_lists)
-            return fail("mgb_dist_plan_create: peer exchange is implemented for the thread-per-entry gather (fine levels)");
-        // replicated global symbolic plan (host only) -> exchange maps
-        std::vector<mgb::HostCSR> Dh(nD);
-        for (int k = 0; k < nD; ++k) Dh[k] = to_host_csr(D[k], 0, n);
-        mgb::HostCSR Rh = to_host_csr(*R, 0, R->nrows);
-        mgb::ElementPlan gp;
-        mgb::build_element_plan(Dh, Rh, n, w_host, pl->bar, gp, true);
+            return fail("mgb_dist_plan_create: sharded plans need the element path: this level's gather runs lanes-per-entry (coarse level)");
         auto dd = std::make_unique<mgb_plan::Dist>();
-        mgb::build_dist_maps(gp, rank, nranks, row_part, out_part, dd->maps);
-        const auto& M = dd->maps;
-        if ((int64_t)M.h_dest.size() != pl->nnzH) return fail("mgb_dist_plan_create: internal: local pattern differs from the global plan's view");
+        dd->rank = rank; dd->nranks = nranks; dd->rows = std::move(rows);
         if (ctx) {
             CUDA_OK(cudaSetDevice(ctx->device));
             cudaStream_t st = ctx->stream;
-            dd->h_dest.upload(M.h_dest, st);
-            {
-                std::vector<int2> gd;
-                for (int64_t a = 0; a < (int64_t)M.g_dest.size(); ++a)
-                    if (M.g_dest[a] >= 0) gd.push_back(make_int2((int)a, M.g_dest[a]));
-                dd->n_gtouch = (int64_t)gd.size();
-                dd->g_dest.upload(gd, st);
-            }
-            dd->fh_pos.upload(M.fh_pos, st); dd->fh_ptr.upload(M.fh_ptr, st);
-            dd->fg_pos.upload(M.fg_pos, st); dd->fg_ptr.upload(M.fg_ptr, st);
-            dd->counter.alloc(1); dd->err.alloc(1);
-            CUDA_OK(cudaMemsetAsync(dd->counter.p, 0, sizeof(unsigned int), st));
+            dd->hval.alloc((size_t)std::max<int64_t>(pl->nnzH, 1)); dd->grad.alloc((size_t)std::max<int64_t>(pl->m_out, 1));
+            dd->scal.alloc(4); dd->err.alloc(1);
             CUDA_OK(cudaMemsetAsync(dd->err.p, 0, sizeof(int), st));
-            dd->window_bytes = (size_t)2 * M.lay[rank].size * 8 + mgb::DIST_MAX_RANKS * sizeof(unsigned long long);
+            dd->window_bytes = (size_t)2 * mgb::DIST_LL_RANKS * 8 * sizeof(unsigned long long);
             CUDA_OK(cudaMalloc(&dd->window, dd->window_bytes));
-            CUDA_OK(cudaMemsetAsync(dd->window, 0, dd->window_bytes, st));
+            CUDA_OK(cudaMemsetAsync(dd->window, 0, dd->window_bytes, st));   // epoch tag 0 never matches a live epoch
             CUDA_OK(cudaStreamSynchronize(st));
-            pl->dev_bytes += dd->window_bytes + dd->h_dest.bytes() + dd->g_dest.bytes();
+            pl->dev_bytes += dd->window_bytes + dd->hval.bytes() + dd->grad.bytes();
             if (const char* ev = getenv("MGB_DIST_TIMEOUT_S")) dd->timeout_s = atof(ev) > 0 ? atof(ev) : dd->timeout_s;
-            if (getenv("MGB_DIST_DEBUG")) {
-                std::vector<unsigned long long> init(512 * 8, 0ull);
-                for (int k = 0; k < 512; ++k) init[k * 8] = ~0ull;
-                dd->dbg.upload(init, st);
-                CUDA_OK(cudaStreamSynchronize(st));
-            }
-            // block order of the push kernel: entries of higher ranks first, then lower ranks, own entries last,
-            // so the NVLink stores are in flight while the local part runs
-            int64_t first_after = (int64_t)M.h_dest.size();
-            for (int64_t k = 0; k < (int64_t)M.h_dest.size(); ++k)
-                if ((M.h_dest[k] >> mgb::DIST_RANK_SHIFT) > rank) { first_after = k; break; }
-            dd->h_rot = getenv("MGB_DIST_NOROT") ? 0 : first_after / (256 * mgb::GATHER_UNROLL);
-            for (int32_t d : M.h_dest) dd->h_own += ((d >> mgb::DIST_RANK_SHIFT) == rank) ? 1 : 0;
-            if (getenv("MGB_DIST_NOROT")) dd->h_own = 0;
         }
         pl->dist = std::move(dd);
         *out = pl.release();
@@ -1077,46 +1124,30 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
 }
 
 int mgb_dist_info(const mgb_plan* pl, int64_t* info, int32_t ninfo) {
-    if (!pl || !pl->dist || !info) return fail("mgb_dist_info: not a distributed plan");
-    const auto& M = pl->dist->maps;
-    const auto& L = M.lay[M.rank];
-    int err = 0;
-    if (pl->ctx && pl->dist->err.p) {
-        cudaSetDevice(pl->ctx->device);
-        cudaMemcpy(&err, pl->dist->err.p, sizeof(int), cudaMemcpyDeviceToHost);
-    }
-    int64_t v[16] = {M.rank, M.nranks, L.n_own_h, L.n_own_g, M.out_part[M.rank], M.out_part[M.rank + 1],
-                     (int64_t)M.h_dest.size(), L.n_stg_h, L.n_stg_g, (int64_t)M.fh_pos.size(), (int64_t)M.fg_pos.size(),
-                     L.size, (int64_t)pl->dist->epoch, err, M.row_part[M.rank], M.row_part[M.rank + 1]};
-    for (int i = 0; i < ninfo && i < 16; ++i) info[i] = v[i];
-    return 0;
+    try {
+        if (!pl || !pl->dist || !info) return fail("mgb_dist_info: not a distributed plan");
+        const auto& dd = *pl->dist;
+        int err = 0;
+        if (pl->ctx && dd.err.p) {
+            CUDA_OK(cudaSetDevice(pl->ctx->device));
+            CUDA_OK(cudaMemcpy(&err, dd.err.p, sizeof(int), cudaMemcpyDeviceToHost));
+        }
+        int64_t v[16] = {dd.rank, dd.nranks, pl->nnzH, pl->m_out, pl->out0, pl->out0 + pl->m_out, pl->nloc, pl->n_primary,
+                         pl->ep.E, 0, 0, (int64_t)(dd.window_bytes / 8), (int64_t)dd.epoch, err, 0, 0};
+        for (int i = 0; i < ninfo && i < 16; ++i) info[i] = v[i];
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_info: ") + ex.what()); }
 }
 
-int mgb_dist_layout(const mgb_plan* pl, int32_t rank, int64_t* lay11) {
-    if (!pl || !pl->dist || !lay11) return fail("mgb_dist_layout: not a distributed plan");
-    if (rank < 0 || rank >= pl->dist->maps.nranks) return fail("mgb_dist_layout: bad rank");
-    const auto& L = pl->dist->maps.lay[rank];
-    const int64_t v[11] = {L.n_own_h, L.n_own_g, L.n_stg_h, L.n_stg_g, L.off_h, L.off_g, L.off_scal, L.off_stg_h,
-                           L.off_stg_g, L.off_stg_scal, L.size};
-    std::memcpy(lay11, v, sizeof(v));
+int mgb_dist_rows(const mgb_plan* pl, int64_t* rows_host) {
+    if (!pl || !pl->dist || !rows_host) return fail("mgb_dist_rows: not a distributed plan");
+    std::memcpy(rows_host, pl->dist->rows.data(), pl->dist->rows.size() * sizeof(int64_t));
     return 0;
 }
 
 int mgb_dist_pattern(const mgb_plan* pl, int32_t* rowptr_host, int32_t* colidx_host) {
-    if (!pl || !pl->dist || !rowptr_host || !colidx_host) return fail("mgb_dist_pattern: not a distributed plan");
-    const auto& M = pl->dist->maps;
-    std::memcpy(rowptr_host, M.own_rowptr.data(), M.own_rowptr.size() * sizeof(int32_t));
-    std::memcpy(colidx_host, M.own_colidx.data(), M.own_colidx.size() * sizeof(int32_t));
-    return 0;
-}
-
-int mgb_dist_maps(const mgb_plan* pl, int32_t* h_dest, int32_t* g_dest, int32_t* fh_pos, int32_t* fh_ptr,
-                  int32_t* fg_pos, int32_t* fg_ptr) {
-    if (!pl || !pl->dist) return fail("mgb_dist_maps: not a distributed plan");
-    const auto& M = pl->dist->maps;
-    auto cp = [](int32_t* dst, const std::vector<int32_t>& v) { if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(int32_t)); };
-    cp(h_dest, M.h_dest); cp(g_dest, M.g_dest); cp(fh_pos, M.fh_pos); cp(fh_ptr, M.fh_ptr); cp(fg_pos, M.fg_pos); cp(fg_ptr, M.fg_ptr);
-    return 0;
+    if (!pl || !pl->dist) return fail("mgb_dist_pattern: not a distributed plan");
+    return mgb_plan_pattern(pl, rowptr_host, colidx_host);
 }
 
 int mgb_dist_window(mgb_plan* pl, void** window_dev, int64_t* bytes) {
@@ -1143,8 +1174,8 @@ int mgb_dist_attach(mgb_plan* pl, const mgb_ipc_handle* handles) {
         if (!pl || !pl->dist || !pl->dist->window || !handles) return fail("mgb_dist_attach: plan has no exchange window");
         auto& dd = *pl->dist;
         CUDA_OK(cudaSetDevice(pl->ctx->device));
-        for (int p = 0; p < dd.maps.nranks; ++p) {
-            if (p == dd.maps.rank) { dd.peer[p] = dd.window; continue; }
+        for (int p = 0; p < dd.nranks; ++p) {
+            if (p == dd.rank) { dd.peer[p] = dd.window; continue; }
             cudaIpcMemHandle_t h;
             std::memcpy(&h, handles[p].bytes, sizeof(h));
             void* ptr = nullptr;
@@ -1159,89 +1190,46 @@ int mgb_dist_attach(mgb_plan* pl, const mgb_ipc_handle* handles) {
 int mgb_dist_attach_local(mgb_plan* pl, void* const* windows_dev) {
     if (!pl || !pl->dist || !pl->dist->window || !windows_dev) return fail("mgb_dist_attach_local: plan has no exchange window");
     auto& dd = *pl->dist;
-    for (int p = 0; p < dd.maps.nranks; ++p) {
+    for (int p = 0; p < dd.nranks; ++p) {
         if (!windows_dev[p]) return fail("mgb_dist_attach_local: NULL window");
-        dd.peer[p] = (p == dd.maps.rank) ? dd.window : windows_dev[p];
+        dd.peer[p] = (p == dd.rank) ? dd.window : windows_dev[p];
     }
     dd.attached = true;
     return 0;
 }
 
 namespace {
-mgb::FinishParams make_finish_params(mgb_plan* pl, double t, int flags) {
+mgb::DistScal make_dist_scal(mgb_plan* pl, bool publish_only) {
     auto& dd = *pl->dist;
-    const auto& M = dd.maps;
-    const auto& L = M.lay[M.rank];
-    const int par = (int)(dd.epoch & 1ull);
-    mgb::FinishParams F{};
-    char* base = static_cast<char*>(dd.window);
-    F.win = reinterpret_cast<double*>(base) + (size_t)par * L.size;
-    F.flag = reinterpret_cast<const unsigned long long*>(base + (size_t)2 * L.size * 8);
-    F.nranks = M.nranks; F.epoch = dd.epoch; F.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9);
-    F.n_fh = (flags & MGB_WANT_HESS) ? (int64_t)M.fh_pos.size() : 0;
-    F.n_fg = (flags & MGB_WANT_GRAD) ? (int64_t)M.fg_pos.size() : 0;
-    F.fh_pos = dd.fh_pos.p; F.fh_ptr = dd.fh_ptr.p; F.fg_pos = dd.fg_pos.p; F.fg_ptr = dd.fg_ptr.p;
-    F.off_h = L.off_h; F.off_g = L.off_g; F.off_scal = L.off_scal; F.off_stg_h = L.off_stg_h;
-    F.off_stg_g = L.off_stg_g; F.off_stg_scal = L.off_stg_scal; F.t = t;
-    F.err = dd.err.p;
-    return F;
+    mgb::DistScal S{};
+    S.rank = dd.rank; S.nranks = dd.nranks; S.epoch = dd.epoch; S.publish_only = publish_only ? 1 : 0;
+    for (int p = 0; p < dd.nranks; ++p) S.win[p] = static_cast<unsigned long long*>(dd.peer[p]);
+    S.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9);
+    S.err = dd.err.p;
+    return S;
 }
 
 void dist_outputs(mgb_plan* pl, const double** hval_own_dev, const double** grad_own_dev, const double** scal_dev) {
     auto& dd = *pl->dist;
-    const auto& L = dd.maps.lay[dd.maps.rank];
-    const double* win = static_cast<const double*>(dd.window) + (size_t)(dd.epoch & 1ull) * L.size;
-    if (hval_own_dev) *hval_own_dev = win + L.off_h;
-    if (grad_own_dev) *grad_own_dev = win + L.off_g;
-    if (scal_dev) *scal_dev = win + L.off_scal;
+    if (hval_own_dev) *hval_own_dev = dd.hval.p;
+    if (grad_own_dev) *grad_own_dev = dd.grad.p;
+    if (scal_dev) *scal_dev = dd.scal.p;
 }
 
-// element kernel + push kernel of a new epoch; fused: the push kernel's last CTA also runs the owner-side finish
+// element kernel + gather kernel of a new epoch on this rank's elements; the gather's scalar block publishes the
+// partial sums to every rank and - fused mode - collects the peers' words and sums them in rank order
 void dist_launch(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int flags, bool fused) {
     auto& dd = *pl->dist;
-    if (!dd.attached) throw std::runtime_error("peers not attached (mgb_dist_attach)");
+    if (dd.nranks > 1 && !dd.attached) throw std::runtime_error("peers not attached (mgb_dist_attach)");
+    if ((flags & MGB_WANT_HESS) && !pl->has_hessian) throw std::runtime_error("plan was created without a Hessian");
     CUDA_OK(cudaSetDevice(pl->ctx->device));
-    cudaStream_t st = pl->ctx->stream;
-    const auto& M = dd.maps;
     dd.epoch++;
+    if (dd.epoch == 0) dd.epoch = 2;   // tag 0 marks "never written"; keep the parity sequence (…, 0xFFFFFFFF, 2, 3, …)
     dd.finish_pending = !fused;
-    const int par = (int)(dd.epoch & 1ull);
-    unsigned long long* dbg = dd.dbg.p ? dd.dbg.p + (dd.epoch % 512) * 8 : nullptr;
-    if (dbg) mgb::stamp_kernel<<<1, 1, 0, st>>>(dbg + 6);
-    mgb::ElemParams E = make_elem_params(pl, s_dev, Dz0_dev, c_dev, t, nullptr);
-    launch_elem(pl, E, flags & 7);
-    mgb::PushParams P{};
-    P.dbg = dbg;
-    P.G = make_gather_params(pl, flags, t, nullptr, nullptr, nullptr);
-    size_gather_grid(pl, P.G);
-    P.h_dest = dd.h_dest.p; P.g_dest = dd.g_dest.p; P.n_gtouch = dd.n_gtouch;
-    if (P.G.want_g) P.G.nblk_g = (dd.n_gtouch + 255) / 256;
-    for (int p = 0; p < M.nranks; ++p) {
-        char* base = static_cast<char*>(dd.peer[p]);
-        P.win[p] = reinterpret_cast<double*>(base) + (size_t)par * M.lay[p].size;
-        P.flag[p] = reinterpret_cast<unsigned long long*>(base + (size_t)2 * M.lay[p].size * 8);
-        P.scal_off[p] = M.lay[p].off_stg_scal + 4 * (int64_t)M.rank;
-    }
-    P.rank = M.rank; P.nranks = M.nranks; P.epoch = dd.epoch; P.counter = dd.counter.p;
-    P.h_rot = P.G.nblk_h > 0 ? dd.h_rot % P.G.nblk_h : 0;
-    P.h_loc_blk = std::min<int64_t>(dd.h_own / (256 * mgb::GATHER_UNROLL), P.G.nblk_h);
-    P.fused = fused ? 1 : 0;
-    P.F = make_finish_params(pl, t, flags);
-    launch_dependent(mgb::push_kernel, (unsigned)(P.G.nblk_h + P.G.nblk_l + P.G.nblk_g + 1), 256u, st, P, true);
-    g_launches++;
-    CUDA_OK(cudaGetLastError());
+    const mgb::DistScal S = make_dist_scal(pl, !fused);
+    assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags & 7, dd.scal.p, dd.grad.p, dd.hval.p, nullptr, nullptr, &S);
 }
 }  // namespace
-
-int mgb_dist_debug(mgb_plan* pl, uint64_t* out512x8) {
-    try {
-        if (!pl || !pl->dist || !pl->dist->dbg.p || !out512x8) return fail("mgb_dist_debug: timeline not enabled (MGB_DIST_DEBUG=1 at plan creation)");
-        CUDA_OK(cudaSetDevice(pl->ctx->device));
-        CUDA_OK(cudaStreamSynchronize(pl->ctx->stream));
-        CUDA_OK(cudaMemcpy(out512x8, pl->dist->dbg.p, 512 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        return 0;
-    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_debug: ") + ex.what()); }
-}
 
 int mgb_dist_begin(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags) {
     try {
@@ -1258,13 +1246,13 @@ int mgb_dist_end(mgb_plan* pl, double t, int32_t flags, const double** hval_own_
         if (!pl || !pl->dist || !pl->ctx) return fail("mgb_dist_end: not a distributed device plan");
         auto& dd = *pl->dist;
         if (!dd.finish_pending) return fail("mgb_dist_end: no mgb_dist_begin in flight");
+        (void)flags;
         CUDA_OK(cudaSetDevice(pl->ctx->device));
-        mgb::FinishParams F = make_finish_params(pl, t, flags);
-        const int64_t work = std::max<int64_t>(F.n_fh, F.n_fg);
-        const unsigned nb = (unsigned)std::min<int64_t>(std::max<int64_t>((work + 255) / 256, 1), 64);
-        mgb::finish_kernel<<<nb, 256, 0, pl->ctx->stream>>>(F);
-        g_launches++;
-        CUDA_OK(cudaGetLastError());
+        if (dd.nranks > 1) {
+            mgb::dist_finish_kernel<<<1, 128, 0, pl->ctx->stream>>>(make_dist_scal(pl, false), t, dd.scal.p);
+            g_launches++;
+            CUDA_OK(cudaGetLastError());
+        }
         dd.finish_pending = false;
         dist_outputs(pl, hval_own_dev, grad_own_dev, scal_dev);
         return 0;

@@ -141,10 +141,14 @@ struct UF {
 }  // namespace
 
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian) {
+                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian, int64_t out0, int64_t out1) {
     P.ok = false;
     const int ND = (int)D.size();
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
+    if (out1 < 0) out1 = m;
+    if (out0 < 0 || out0 > out1 || out1 > m) { P.why = "output row range outside 0..m"; return; }
+    const int64_t mo = out1 - out0;
+    P.out0 = out0; P.m_out = mo;
     if (N % n_global) { P.why = "N is not a multiple of n"; return; }
     const int nu = (int)(N / n_global);
     const bool two = bar.nidx2 > 0;
@@ -316,10 +320,10 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         return -1;
     };
 
-    P.h_rowptr.assign(m + 1, 0);
+    P.h_rowptr.assign(mo + 1, 0);
     P.h_cptr.assign(1, 0);
     if (want_hessian) {
-    std::vector<int64_t> rowcnt(m + 1, 0);
+    std::vector<int64_t> rowcnt(mo + 1, 0);
     std::vector<uint8_t> pres((size_t)NL * NL);
     std::vector<uint8_t> U((size_t)B * NL);
     std::vector<int> own((size_t)nu * B, -1);
@@ -328,9 +332,9 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     std::vector<int64_t> fillpos;
     for (int pass = 0; pass < 2; ++pass) {
         if (pass == 1) {
-            for (int64_t a = 0; a < m; ++a) rowcnt[a + 1] += rowcnt[a];
-            tb.resize(rowcnt[m]);
-            ts.resize(rowcnt[m]);
+            for (int64_t a = 0; a < mo; ++a) rowcnt[a + 1] += rowcnt[a];
+            tb.resize(rowcnt[mo]);
+            ts.resize(rowcnt[mo]);
             fillpos.assign(rowcnt.begin(), rowcnt.end() - 1);
         }
         for (int64_t e = 0; e < E; ++e) {
@@ -356,15 +360,15 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                             if (U[(size_t)l * NL + a2]) pres[(size_t)a1 * NL + a2] = 1;
             for (int a1 = 0; a1 < NL; ++a1) {
                 const int32_t ga = P.lcols[((size_t)e * nu + a1 / B) * LPE + a1 % B];
-                if (ga < 0) continue;
+                if (ga < out0 || ga >= out1) continue;   // eliminated dof (-1) or a row another rank owns
                 for (int a2 = 0; a2 < NL; ++a2) {
                     if (!pres[(size_t)a1 * NL + a2]) continue;
                     const int32_t gb = P.lcols[((size_t)e * nu + a2 / B) * LPE + a2 % B];
                     if (gb < 0) continue;
-                    if (pass == 0) { rowcnt[ga + 1]++; continue; }
+                    if (pass == 0) { rowcnt[ga - out0 + 1]++; continue; }
                     const int sl = slot_of(a1, a2, own);
                     if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
-                    const int64_t d = fillpos[ga]++;
+                    const int64_t d = fillpos[ga - out0]++;
                     tb[d] = gb;
                     ts[d] = (int32_t)(e * lay.NS + sl);
                 }
@@ -373,13 +377,13 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     }
     if ((int64_t)E * lay.NS > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
     // sort each row by (column, source) and compress
-    P.h_rowptr.assign(m + 1, 0);
+    P.h_rowptr.assign(mo + 1, 0);
     P.h_colidx.clear();
     P.h_cptr.clear();
     P.h_cidx.resize(tb.size());
     std::vector<std::pair<int32_t, int32_t>> rowbuf;
     int64_t outc = 0;
-    for (int64_t a = 0; a < m; ++a) {
+    for (int64_t a = 0; a < mo; ++a) {
         rowbuf.clear();
         for (int64_t d = rowcnt[a]; d < rowcnt[a + 1]; ++d) rowbuf.emplace_back(tb[d], ts[d]);
         std::sort(rowbuf.begin(), rowbuf.end());
@@ -399,22 +403,22 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     }  // want_hessian
 
     // gradient replay lists
-    std::vector<int64_t> gcnt(m + 1, 0);
+    std::vector<int64_t> gcnt(mo + 1, 0);
     for (int v = 0; v < nu; ++v)
         for (int64_t e = 0; e < E; ++e)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
-                if (a >= 0) gcnt[a + 1]++;
+                if (a >= out0 && a < out1) gcnt[a - out0 + 1]++;
             }
-    for (int64_t a = 0; a < m; ++a) gcnt[a + 1] += gcnt[a];
+    for (int64_t a = 0; a < mo; ++a) gcnt[a + 1] += gcnt[a];
     P.g_cptr = gcnt;
-    P.g_cidx.resize(gcnt[m]);
+    P.g_cidx.resize(gcnt[mo]);
     std::vector<int64_t> gpos(gcnt.begin(), gcnt.end() - 1);
     for (int64_t e = 0; e < E; ++e)  // element-major so every list is ordered by element
         for (int v = 0; v < nu; ++v)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
-                if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)((e * nu + v) * LPE + q);
+                if (a >= out0 && a < out1) P.g_cidx[gpos[a - out0]++] = (int32_t)((e * nu + v) * LPE + q);
             }
     P.ok = true;
 }
@@ -500,123 +504,31 @@ void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
                  [&](int32_t gi) { const int64_t e = gi / RS; return (uint32_t)(P * NSP + (e % P) * RS + gi % RS); }, PP.G);
 }
 
-namespace {
-int64_t pad16(int64_t v) { return (v + 15) / 16 * 16; }
-
-// one output family (Hessian entries or gradient entries).  cptr/cidx: global contribution lists sorted by
-// element; elem_of(contribution) -> element; owner_of_entry(t) -> owning rank; pos_in_owner(t) -> index
-// inside the owner's block.  Fills dest (for entries this rank contributes to, in entry order) and the
-// owner-side lists of this rank; counts staged values per owner.
-template <class ElemOf, class OwnerOf, class PosOf, class Sink>
-void dist_family(int64_t nout, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx, int rank, int nranks,
-                 const std::vector<int64_t>& elem_part, ElemOf elem_of, OwnerOf owner_of, PosOf pos_of,
-                 std::vector<int64_t>& n_stg /*per owner*/, Sink sink /* (t, owner, pos, staged, stg_index) for my entries */,
-                 std::vector<int32_t>& f_pos, std::vector<int32_t>& f_ptr) {
-    n_stg.assign(nranks, 0);
-    f_pos.clear();
-    f_ptr.assign(1, 0);
-    for (int64_t t = 0; t < nout; ++t) {
-        const int64_t c0 = cptr[t], c1 = cptr[t + 1];
-        if (c1 == c0) continue;
-        // contributing ranks in ascending order (lists are sorted by element)
-        int nsrc = 0, mine = -1, last = -1;
-        for (int64_t c = c0; c < c1; ++c) {
-            const int64_t e = elem_of(cidx[c]);
-            const int r = (int)(std::upper_bound(elem_part.begin(), elem_part.end(), e) - elem_part.begin()) - 1;
-            if (r < last) throw std::runtime_error("internal: contribution list not sorted by element");
-            if (r != last) {
-                if (r == rank) mine = nsrc;
-                ++nsrc;
-                last = r;
+void dist_select_elements(const std::vector<int32_t>& lcols, int64_t E, int NU, int LPE, int B, int rank, int nranks,
+                          const int64_t* out_part, std::vector<int64_t>& rows_sel, int64_t& n_primary_rows) {
+    const int64_t out0 = out_part[rank], out1 = out_part[rank + 1];
+    auto owner = [&](int32_t a) { return (int)(std::upper_bound(out_part, out_part + nranks + 1, (int64_t)a) - out_part) - 1; };
+    std::vector<int64_t> prim, halo;
+    for (int64_t e = 0; e < E; ++e) {
+        bool touch = false;
+        int32_t first_any = -1, first_last = -1;
+        for (int v = 0; v < NU; ++v)
+            for (int q = 0; q < LPE; ++q) {
+                const int32_t a = lcols[((size_t)e * NU + v) * LPE + q];
+                if (a < 0) continue;
+                touch = touch || (a >= out0 && a < out1);
+                if (first_any < 0) first_any = a;
+                if (v == NU - 1 && first_last < 0) first_last = a;
             }
-        }
-        const int owner = owner_of(t);
-        const int64_t pos = pos_of(t, owner);
-        if (nsrc == 1) {
-            if (mine >= 0) sink(t, owner, pos, false, (int64_t)0);
-        } else {
-            const int64_t base = n_stg[owner];
-            n_stg[owner] += nsrc;
-            if (mine >= 0) sink(t, owner, pos, true, base + mine);
-            if (owner == rank) {
-                if (pos > INT32_MAX || base + nsrc > INT32_MAX) throw std::runtime_error("exchange window exceeds int32 indexing");
-                f_pos.push_back((int32_t)pos);
-                f_ptr.push_back((int32_t)(base + nsrc));
-            }
-        }
+        const int32_t key = first_last >= 0 ? first_last : first_any;
+        const int prim_rank = key >= 0 ? owner(key) : 0;
+        if (prim_rank == rank) prim.push_back(e);          // (an element without any dof still counts in the objective)
+        else if (touch) halo.push_back(e);
     }
-}
-}  // namespace
-
-void build_dist_maps(const ElementPlan& G, int rank, int nranks, const int64_t* row_part, const int64_t* out_part,
-                     DistMaps& M) {
-    if (nranks < 1 || nranks > DIST_MAX_RANKS) throw std::runtime_error("number of ranks must be 1..16");
-    if (rank < 0 || rank >= nranks) throw std::runtime_error("rank outside 0..nranks-1");
-    if (!G.ok) throw std::runtime_error("peer exchange needs the element path: " + G.why);
-    M.rank = rank; M.nranks = nranks;
-    M.row_part.assign(row_part, row_part + nranks + 1);
-    M.out_part.assign(out_part, out_part + nranks + 1);
-    const int64_t m = G.m, B = G.B, nnzH = (int64_t)G.h_colidx.size();
-    if (M.row_part[0] != 0 || M.row_part[nranks] != G.nloc) throw std::runtime_error("row partition must cover [0,n)");
-    if (M.out_part[0] != 0 || M.out_part[nranks] != m) throw std::runtime_error("output partition must cover [0,m)");
-    std::vector<int64_t> elem_part(nranks + 1);
-    for (int r = 0; r <= nranks; ++r) {
-        if (M.row_part[r] % B) throw std::runtime_error("row partition splits a broken element");
-        if (r && (M.row_part[r] < M.row_part[r - 1] || M.out_part[r] < M.out_part[r - 1])) throw std::runtime_error("partition offsets must be non-decreasing");
-        elem_part[r] = M.row_part[r] / B;
-    }
-    auto owner_of_row = [&](int64_t a) { return (int)(std::upper_bound(M.out_part.begin(), M.out_part.end(), a) - M.out_part.begin()) - 1; };
-    // row of every global Hessian entry
-    std::vector<int32_t> row_of(nnzH);
-    for (int64_t a = 0; a < m; ++a)
-        for (int64_t t = G.h_rowptr[a]; t < G.h_rowptr[a + 1]; ++t) row_of[t] = (int32_t)a;
-    const int NS = G.lay.NS, RS = G.NU * G.LPE;
-    struct Rec { int owner; int64_t pos; bool staged; int64_t sidx; };
-    std::vector<Rec> hrec, grec;
-    std::vector<int32_t> g_entry;  // unknown of each gradient record
-    std::vector<int64_t> nstg_h, nstg_g;
-    dist_family(nnzH, G.h_cptr, G.h_cidx, rank, nranks, elem_part,
-                [&](int32_t gs) { return (int64_t)(gs / NS); },
-                [&](int64_t t) { return owner_of_row(row_of[t]); },
-                [&](int64_t t, int owner) { return t - (int64_t)G.h_rowptr[M.out_part[owner]]; }, nstg_h,
-                [&](int64_t, int owner, int64_t pos, bool staged, int64_t sidx) { hrec.push_back({owner, pos, staged, sidx}); },
-                M.fh_pos, M.fh_ptr);
-    dist_family(m, G.g_cptr, G.g_cidx, rank, nranks, elem_part,
-                [&](int32_t gi) { return (int64_t)(gi / RS); },
-                [&](int64_t a) { return owner_of_row(a); },
-                [&](int64_t a, int owner) { return a - M.out_part[owner]; }, nstg_g,
-                [&](int64_t a, int owner, int64_t pos, bool staged, int64_t sidx) { grec.push_back({owner, pos, staged, sidx}); g_entry.push_back((int32_t)a); },
-                M.fg_pos, M.fg_ptr);
-    // window layouts of every rank
-    M.lay.assign(nranks, DistLayout());
-    for (int r = 0; r < nranks; ++r) {
-        DistLayout& L = M.lay[r];
-        L.n_own_h = (int64_t)G.h_rowptr[M.out_part[r + 1]] - (int64_t)G.h_rowptr[M.out_part[r]];
-        L.n_own_g = M.out_part[r + 1] - M.out_part[r];
-        L.n_stg_h = nstg_h[r]; L.n_stg_g = nstg_g[r];
-        int64_t o = 0;
-        L.off_h = o; o += pad16(L.n_own_h);
-        L.off_g = o; o += pad16(L.n_own_g);
-        L.off_scal = o; o += 16;
-        L.off_stg_h = o; o += pad16(L.n_stg_h);
-        L.off_stg_g = o; o += pad16(L.n_stg_g);
-        L.off_stg_scal = o; o += pad16(4 * (int64_t)nranks);
-        L.size = o;
-        if (L.size > DIST_OFF_MASK) throw std::runtime_error("exchange window exceeds 2^27 doubles; use more ranks");
-    }
-    auto encode = [&](const Rec& r, bool hess) -> int32_t {
-        const DistLayout& L = M.lay[r.owner];
-        const int64_t off = r.staged ? (hess ? L.off_stg_h : L.off_stg_g) + r.sidx : (hess ? L.off_h : L.off_g) + r.pos;
-        return (int32_t)(((int64_t)r.owner << DIST_RANK_SHIFT) | off);
-    };
-    M.h_dest.resize(hrec.size());
-    for (size_t k = 0; k < hrec.size(); ++k) M.h_dest[k] = encode(hrec[k], true);
-    M.g_dest.assign(m, -1);
-    for (size_t k = 0; k < grec.size(); ++k) M.g_dest[g_entry[k]] = encode(grec[k], false);
-    const int64_t lo = M.out_part[rank], hi = M.out_part[rank + 1];
-    M.own_rowptr.resize(hi - lo + 1);
-    for (int64_t a = lo; a <= hi; ++a) M.own_rowptr[a - lo] = G.h_rowptr[a] - G.h_rowptr[lo];
-    M.own_colidx.assign(G.h_colidx.begin() + G.h_rowptr[lo], G.h_colidx.begin() + G.h_rowptr[hi]);
+    rows_sel.clear();
+    for (int64_t e : prim) for (int l = 0; l < B; ++l) rows_sel.push_back(e * B + l);
+    n_primary_rows = (int64_t)rows_sel.size();
+    for (int64_t e : halo) for (int l = 0; l < B; ++l) rows_sel.push_back(e * B + l);
 }
 
 void build_csr_plan(const std::vector<HostCSR>& D, const HostCSR& R, const BarrierDesc& bar, CsrPlan& P,

@@ -72,16 +72,17 @@ struct ElementPlan {
     bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
     int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
+    int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (whole range unless sharded)
     SlotLayout lay;
     std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1
     int RW = 0;                    // doubles per point record (even)
     std::vector<double> prec;      // [nloc][RW]: derivative rows (dim*B), w, then fine: own_val[NU] + packed
                                    // own_lq bytes (255 = none); coarse: dense id-like rows [NU][B]
     // fixed output pattern + replay lists
-    std::vector<int32_t> h_rowptr, h_colidx;  // m+1, nnzH
+    std::vector<int32_t> h_rowptr, h_colidx;  // m_out+1 (row a - out0), nnzH (global column ids)
     std::vector<int64_t> h_cptr;              // nnzH+1
     std::vector<int32_t> h_cidx;              // contribution -> e*NS + slot
-    std::vector<int64_t> g_cptr;              // m+1
+    std::vector<int64_t> g_cptr;              // m_out+1
     std::vector<int32_t> g_cidx;              // contribution -> (e*NU+v)*LPE + q
     PatchPlan patch;
 };
@@ -99,40 +100,29 @@ struct BarrierDesc {
 
 // D: nD operators restricted to the local rows (nloc x N), R: N x m.
 // Tries to detect the broken-element block structure the fused kernels exploit.
+// out0/out1: keep only the output rows (unknowns) in [out0, out1) (out1 < 0: all m) - a sharded plan whose local
+// quadrature rows contain every element touching those unknowns completes them without any exchange.
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true);
+                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true, int64_t out0 = 0, int64_t out1 = -1);
 
 
-// ---- multi-GPU (one process per GPU): fused peer-memory exchange maps --------------------------------
-// Every rank assembles the contributions of its own quadrature rows (whole elements) and stores each
-// local result straight into the memory of the rank that OWNS the output row (HPCSparseArrays row
-// partition of R'HR and of the gradient): entries fed by one rank only go to their final
-// position in the owner's value array, entries fed by several ranks (element-partition interface) go to
-// a staging area and are summed by the owner in source-rank order.  All maps derive from the replicated
-// global symbolic plan, so no integer exchange is needed.
+// ---- multi-GPU (one process per GPU): owner-computes sharding ---------------------------------------
+// The outputs (gradient entries, rows of R'HR) are split in contiguous blocks of the m unknowns
+// (HPCSparseArrays row partition).  A rank evaluates every broken element that touches one of
+// its rows, so every owned row is completed locally: no Hessian or gradient value crosses NVLink.  Elements
+// on the interface are evaluated by up to two (P = 2) ... a few ranks; that redundancy costs microseconds of
+// arithmetic and replaces the exchange of 50-94 % of all element contributions that the [u dofs | s dofs]
+// numbering of R = blockdiag(R_u, R_s) would force.  Only the three objective scalars
+// are summed across ranks (peer-memory words with embedded epoch flags, kernels_dist.cuh).
 constexpr int DIST_MAX_RANKS = 16;
-constexpr int DIST_RANK_SHIFT = 27;                         // dest = (rank << 27) | offset (doubles)
-constexpr int32_t DIST_OFF_MASK = (1 << DIST_RANK_SHIFT) - 1;
 
-struct DistLayout {  // one rank's exchange window (offsets in doubles; one copy per epoch parity)
-    int64_t n_own_h = 0, n_own_g = 0, n_stg_h = 0, n_stg_g = 0;
-    int64_t off_h = 0, off_g = 0, off_scal = 0, off_stg_h = 0, off_stg_g = 0, off_stg_scal = 0, size = 0;
-};
-
-struct DistMaps {
-    int rank = 0, nranks = 1;
-    std::vector<int64_t> row_part, out_part;   // 0-based offsets, nranks+1 (quadrature rows / unknowns)
-    std::vector<DistLayout> lay;               // every rank's window layout
-    std::vector<int32_t> h_dest;               // per LOCAL Hessian entry (local pattern order)
-    std::vector<int32_t> g_dest;               // per unknown (m); -1: no local contribution
-    std::vector<int32_t> fh_pos, fh_ptr;       // owned multi-source Hessian entries: position, staging range
-    std::vector<int32_t> fg_pos, fg_ptr;       // same for the gradient
-    std::vector<int32_t> own_rowptr, own_colidx;  // owned rows of the global pattern (global column ids)
-};
-
-// `global`: element plan over ALL quadrature rows (host arrays still present).
-void build_dist_maps(const ElementPlan& global, int rank, int nranks, const int64_t* row_part,
-                     const int64_t* out_part, DistMaps& out);
+// Quadrature rows (whole elements) rank `rank` evaluates: every element with a dof in its output block
+// [out_part[rank], out_part[rank+1]).  The objective scalars of an element are counted by exactly one of the ranks
+// that evaluate it anyway - the owner of its first dof of the last state variable (s is never eliminated; any dof /
+// rank 0 as fall-backs) - and those "primary" elements are listed first.  lcols: element -> dof table of the global
+// element plan ([E][NU][LPE]).
+void dist_select_elements(const std::vector<int32_t>& lcols, int64_t E, int NU, int LPE, int B, int rank, int nranks,
+                          const int64_t* out_part, std::vector<int64_t>& rows_sel, int64_t& n_primary_rows);
 
 struct CsrPlan {
     int ND = 0, NU = 0;

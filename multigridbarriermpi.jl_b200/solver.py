@@ -51,23 +51,23 @@ class LevelState:
         self.sharded = False
         if prob.nranks > 1:
             from . import dist as mdist
-            if prob.idx2:
-                raise NotImplementedError("two-cone plans are single-rank for now")
             try:
                 self.plan = mdist.create_peer_plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, prob.block,
-                                                   prob.rank, prob.nranks, group=prob.group, slack=prob.slack)
+                                                   prob.rank, prob.nranks, group=prob.group, slack=prob.slack,
+                                                   idx2=prob.idx2, p2=prob.p2)
                 self.sharded = True
             except capi.MgbError as exc:
-                # the fused peer exchange covers the levels whose gather runs thread-per-entry (the fine ones, where
-                # the work is); a coarse level is assembled redundantly by every rank instead - same inputs, same
-                # kernels, hence bit-identical results on all ranks and no communication.  Every rank takes this
-                # branch together: the refusal depends on the (replicated) operators only.
-                if "peer exchange is implemented" not in str(exc):
+                # only the levels on the element path with thread-per-entry gather (the fine ones, where the work
+                # is) are sharded; any other level - coarse levels, fem3d's Q3 elements and every operator table
+                # on the CSR path - is assembled redundantly by every rank instead: same inputs, same kernels,
+                # hence bit-identical results on all ranks and no communication.  Every rank takes this branch
+                # together: the refusal depends on the (replicated) operators only.
+                if "sharded plans need the element path" not in str(exc):
                     raise
         if self.sharded:
             # the replicated symbolic plan gives the global pattern the solve seam needs (owned row blocks are
             # contiguous, so the global value array is the concatenation of the ranks' owned values)
-            sym = capi.Plan(None, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, slack=prob.slack)
+            sym = capi.Plan(None, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
             rp, ci = sym.pattern()
             m, nnz = sym.m, sym.nnzH
             d = self.plan.dinfo
@@ -75,6 +75,10 @@ class LevelState:
             self.own_g = (d["own0"], d["n_own_g"])
             assert self.own_h[0] + self.own_h[1] == int(rp[d["own1"]])
             self._views = {}
+            # the plan evaluates its own list of quadrature rows (primary elements + halo): Dz0 / c blocks over them
+            self.rows_idx = torch.from_numpy(self.plan.rows).to(dev)
+            self.Dz0_loc = torch.zeros((M.nD, self.plan.rows.size), dtype=torch.float64, device=dev)
+            self._c_cache = None
         else:
             self.plan = capi.Plan(prob.ctx, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p,
                                   slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
@@ -100,14 +104,18 @@ class LevelState:
         self.h_step = torch.zeros(m, dtype=f64).pin_memory()
 
     def assemble(self, s: torch.Tensor, Dz0: torch.Tensor, c: torch.Tensor, t: float, flags: int):
+        """``Dz0`` / ``c``: column-major (nD, n) blocks over ALL quadrature rows (the unknown is replicated)"""
         if not self.sharded:
             self.plan.assemble(s, Dz0, c, t, flags, self.scal, self.grad, self.hval)
             return
-        # sharded: every rank assembles its quadrature rows; the fused peer exchange leaves each rank with its
-        # own rows of R'HR / block of the gradient and the globally summed scalars (mgb_dist_assemble); the
-        # host solve below needs the whole system, so the owned blocks are then replicated (solve seam only).
+        # sharded: every rank evaluates the elements that touch its output rows and completes its own rows of R'HR /
+        # block of the gradient; the objective scalars arrive globally summed (mgb_dist_assemble).  The host solve
+        # below needs the whole system, so the owned blocks are then replicated (solve seam only).
         import torch.distributed as dist
-        ptrs = self.plan.dist_assemble(s, Dz0, c, t, flags)
+        torch.index_select(Dz0, 1, self.rows_idx, out=self.Dz0_loc)
+        if self._c_cache is None or self._c_cache[0] is not c:
+            self._c_cache = (c, torch.index_select(c, 1, self.rows_idx).contiguous())
+        ptrs = self.plan.dist_assemble(s, self.Dz0_loc, self._c_cache[1], t, flags)
         if ptrs not in self._views:
             cnt = (max(self.own_h[1], 1), max(self.own_g[1], 1), 4)
             self._views[ptrs] = tuple(torch.as_tensor(capi.DeviceView(p_, n_), device=self.device) for p_, n_ in zip(ptrs, cnt))
@@ -120,6 +128,14 @@ class LevelState:
             if flags & capi.WANT_GRAD:
                 self.grad[self.own_g[0]: self.own_g[0] + self.own_g[1]] = vg[: self.own_g[1]]
             dist.all_reduce(self.hg, group=self.group)   # every entry has exactly one non-zero contributor: exact
+
+    def read_scal(self) -> torch.Tensor:
+        """scalars on the host; a sharded level whose peer never delivered its partial sums raises on every rank
+        that noticed (the library poisons the scalars instead of returning a partial sum)"""
+        sc = self.scal.cpu()
+        if self.sharded and float(sc[3]) < 0.0 and self.plan.dist_info()["err"]:
+            raise RuntimeError("sharded assembly: a peer's objective partials did not arrive within MGB_DIST_TIMEOUT_S")
+        return sc
 
     def close(self):
         if self.sharded:
@@ -147,20 +163,12 @@ class DeviceProblem:
         self.ctx = ctx or capi.Context(device, self.stream.cuda_stream)
         self.n = M.x.shape[0]
         self.N = M.nu * self.n
-        if self.nranks > 1:
-            from . import dist as mdist
-            self.rows = mdist.element_rows(self.n, self.block, self.rank, self.nranks)
-        else:
-            self.rows = (0, self.n)
-        self.nloc = self.rows[1] - self.rows[0]
         self.levels: Dict[int, LevelState] = {}
-        # operator-only plan with R = I: Dz0 = D z for any fine-space z (this rank's rows)
+        # operator-only plan with R = I: Dz0 = D z for any fine-space z (all quadrature rows: the unknown is
+        # replicated, and a sharded level picks the rows of its own elements out of it)
         self.op_plan = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
-                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2,
-                                 rows=self.rows)
-        self.Dz0 = torch.zeros((M.nD, self.nloc), dtype=torch.float64, device=self.device)  # column-major nloc x nD
-        self.op_plan_full, self.Dz0_full = self.op_plan, self.Dz0     # all rows: levels assembled redundantly
-        self._loc_cache = {}
+                                 slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2)
+        self.Dz0 = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)  # column-major n x nD
         self.stats = dict(assemblies=0, f0_evals=0, solve_s=0.0, assemble_s=0.0)
 
     def level(self, J: int) -> LevelState:
@@ -168,30 +176,11 @@ class DeviceProblem:
             self.levels[J] = LevelState(self, J)
         return self.levels[J]
 
-    def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None, full: bool = False) -> torch.Tensor:
-        """Dz0 = D z on this rank's quadrature rows (``full``: on all rows)"""
-        if full and self.nranks > 1:
-            if self.op_plan_full is self.op_plan:
-                M = self.M
-                self.op_plan_full = capi.Plan(self.ctx, M.D, sp.identity(self.N, format="csr"), M.x, M.w, self.idx, self.p,
-                                              slack=self.slack, force_path=capi.PLAN_NO_HESSIAN, idx2=self.idx2, p2=self.p2)
-                self.Dz0_full = torch.zeros((M.nD, self.n), dtype=torch.float64, device=self.device)
-            out = self.Dz0_full if out is None else out
-            self.op_plan_full.apply_D(z_dev, None, out)
-            return out
+    def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Dz0 = D z on every quadrature row"""
         out = self.Dz0 if out is None else out
         self.op_plan.apply_D(z_dev, None, out)
         return out
-
-    def local_rows(self, a: torch.Tensor) -> torch.Tensor:
-        """this rank's quadrature rows of a column-major (k, n) device block (cached per block)"""
-        if self.nranks == 1:
-            return a
-        hit = self._loc_cache.get(id(a))
-        if hit is None or hit[0] is not a:
-            hit = (a, a[:, self.rows[0]: self.rows[1]].contiguous())
-            self._loc_cache[id(a)] = hit
-        return hit[1]
 
     def close(self):
         """collective on several ranks: nobody unmaps an exchange window a peer may still store into"""
@@ -204,19 +193,17 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
                   alpha: float = 0.1, beta: float = 0.25, solve_fn: Callable = solve):
     """Damped Newton on level J for s -> f(z + R_J s); same decisions as the oracle's ``newton``."""
     lv = prob.level(J)
-    Dz0 = prob.apply_D(z, full=not lv.sharded)
-    if lv.sharded:
-        c = prob.local_rows(c)
+    Dz0 = prob.apply_D(z)
     lv.s.zero_()
     F0, FG, FH = capi.WANT_F0, capi.WANT_GRAD, capi.WANT_HESS
     t0 = time.perf_counter()
     lv.assemble(lv.s, Dz0, c, t, F0 | FG | FH)
-    sc = lv.scal.cpu()
+    sc = lv.read_scal()
     prob.stats["assemblies"] += 1
     y = float(sc[0])
     if not (sc[1] == 1.0 and math.isfinite(y)):
         raise RuntimeError("newton: infeasible start")
-    k, converged = 0, False
+    k, converged, stalled = 0, False, False
     while k < maxit:
         lv.h_hval.copy_(lv.hval, non_blocking=True)
         lv.h_grad.copy_(lv.grad, non_blocking=True)
@@ -239,15 +226,16 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
         while sstep > 1e-12:
             torch.add(lv.s, lv.step, alpha=-sstep, out=lv.trial)
             lv.assemble(lv.trial, Dz0, c, t, F0)
-            sc = lv.scal.cpu()
+            sc = lv.read_scal()
             prob.stats["f0_evals"] += 1
             yn = float(sc[0])
             if sc[1] == 1.0 and math.isfinite(yn) and yn <= y - alpha * sstep * inc:
                 ok = True
                 break
             sstep *= beta
-        if not ok:
+        if not ok:   # no step length decreases the objective: stagnation at rounding level (reported, not hidden)
             converged = True
+            stalled = True
             k -= 1
             break
         lv.s.copy_(lv.trial)
@@ -257,7 +245,7 @@ def newton_device(prob: DeviceProblem, J: int, z: torch.Tensor, c: torch.Tensor,
     prob.stats["assemble_s"] += time.perf_counter() - t0
     # z <- z + R s
     lv.R.mv(lv.s, z, beta=1.0, y0_dev=z)
-    return dict(k=k, converged=converged, y=y)
+    return dict(k=k, converged=converged, stalled=stalled, y=y)
 
 
 @dataclass
@@ -285,6 +273,7 @@ def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, ka
     L = len(prob.M.R_fine)
     t = t0
     ts, its, cdots = [], [], []
+    unconverged, stalls = [], []   # t values whose finest-level Newton hit maxit / whose line search stagnated
     t_begin = time.time()
     kk = 0
     while t <= 1.0 / tol:
@@ -295,25 +284,37 @@ def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, ka
         def level(J, mi):
             sol = newton_device(prob, J, z, c, t, mi, solve_fn=solve_fn)
             row[J] += sol["k"]
+            if J == L - 1:
+                fine_state["converged"], fine_state["stalled"] = sol["converged"], sol["stalled"]
             return sol["converged"]
 
         ok = False
+        fine_state = dict(converged=False, stalled=False)
         if kk > 1:
             ok = level(L - 1, max_newton_fine)
         if not ok:
             for J in range(L):
                 ok = level(J, maxit)
         its.append(row)
+        if not fine_state["converged"]:
+            unconverged.append(t)
+        if fine_state["stalled"]:
+            stalls.append(t)
         # <c, Dz>_w through the objective kernel on the finest plan (s = 0)
         lv = prob.level(L - 1)
-        Dz0 = prob.apply_D(z, full=not lv.sharded)
+        Dz0 = prob.apply_D(z)
         lv.s.zero_()
-        lv.assemble(lv.s, Dz0, prob.local_rows(c) if lv.sharded else c, 0.0, capi.WANT_F0)
-        cdots.append(float(lv.scal.cpu()[2]))
+        lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
+        cdots.append(float(lv.read_scal()[2]))
         if verbose:
             print(f"t={t:.3e} its={row} c.Dz={cdots[-1]:.12e}", file=logfile)
         t *= kappa
-    return dict(ts=np.array(ts), its=np.array(its).T, c_dot_Dz=np.array(cdots), t_elapsed=time.time() - t_begin)
+    if unconverged:
+        import warnings
+        warnings.warn(f"amgb: the finest-level Newton iteration reached maxit={maxit} without converging at t={unconverged}; "
+                      "the returned iterate is not on the central path there", RuntimeWarning)
+    return dict(ts=np.array(ts), its=np.array(its).T, c_dot_Dz=np.array(cdots), t_elapsed=time.time() - t_begin,
+                unconverged_t=np.array(unconverged), line_search_stalls_t=np.array(stalls))
 
 
 def _cm(a: np.ndarray, device) -> torch.Tensor:
@@ -323,11 +324,16 @@ def _cm(a: np.ndarray, device) -> torch.Tensor:
 
 def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float = 0.1, kappa: float = 10.0,
          maxit: int = 50, max_newton: Optional[int] = None, state_variables=DEFAULT_STATE, D=None, f=None, g=None,
-         verbose: bool = False, logfile=None, device: int = 0, solve_fn: Callable = solve, **_ignored) -> AMGBSOL:
+         verbose: bool = False, logfile=None, device: int = 0, solve_fn: Callable = solve, **extra) -> AMGBSOL:
     """Barrier solve of the default p-Laplace-type problem on ``geom`` with GPU assembly.
-    Keyword names follow the reference's documented ``amgb`` keys (docs/src/guide.md:148-152);
-    unknown keys are ignored because ``femNd_mpi_solve`` forwards the same kwargs to the geometry
-    constructor and to ``amgb`` (src/MultiGridBarrierMPI.jl:594-600)."""
+    Keyword names follow the reference's documented ``amgb`` keys (docs/src/guide.md:148-152).  The geometry
+    constructor's keys are accepted and ignored because ``femNd_mpi_solve`` forwards the same kwargs to the geometry
+    constructor and to ``amgb`` (src/MultiGridBarrierMPI.jl:594-600); any other key (e.g. a custom convex set ``Q``)
+    raises instead of being dropped silently."""
+    unknown = sorted(set(extra) - GEOMETRY_KEYS)
+    if unknown:
+        raise TypeError(f"amgb: unsupported keyword(s) {unknown}: the GPU path implements the Euclidian power-cone barrier "
+                        "of the default problem (p, D, f, g, state_variables) only")
     dim = geom.dim
     D = DEFAULT_D[dim] if D is None else list(D)
     f = DEFAULT_F[dim] if f is None else f
@@ -345,13 +351,11 @@ def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float =
     c = _cm(cmat, prob.device)
     # strict feasibility of the start (upstream skips the feasibility phase when it holds)
     lv = prob.level(len(M.R_fine) - 1)
-    Dz0 = prob.apply_D(z, full=not lv.sharded)
+    Dz0 = prob.apply_D(z)
     lv.s.zero_()
-    lv.assemble(lv.s, Dz0, prob.local_rows(c) if lv.sharded else c, 0.0, capi.WANT_F0)
+    lv.assemble(lv.s, Dz0, c, 0.0, capi.WANT_F0)
     sol_feas = None
-    if float(lv.scal.cpu()[1]) != 1.0:
-        if nranks > 1:
-            raise NotImplementedError("the feasibility phase runs on one rank only for now")
+    if float(lv.read_scal()[1]) != 1.0:
         z, sol_feas = feasibility_phase(geom, prob, z, cmat, state_variables, D, tol, t, kappa, maxit, solve_fn, device)
     sol_main = amgb_core(prob, z, c, tol, t, kappa, maxit, max_newton, verbose, solve_fn, logfile)
     zz = z.cpu().numpy().reshape(n, M.nu, order="F")
@@ -359,6 +363,9 @@ def amgb(geom: Geometry, p: float = 1.0, tol: float = math.sqrt(EPS), t: float =
     if nranks > 1:
         prob.close()
     return AMGBSOL(zz, sol_feas, sol_main, "", geom, stats)
+
+
+GEOMETRY_KEYS = {"L", "K", "k", "Ti", "backend", "T", "rest", "n"}
 
 
 def _dist_layout():
@@ -380,7 +387,8 @@ def feasibility_phase(geom, prob: DeviceProblem, z, cmat, state_variables, D, to
     sv1 = tuple(state_variables) + (("feasibility_slack", "full"),)
     D1 = list(D) + [("feasibility_slack", "id")]
     M1 = amg_helper(geom, sv1, D1)
-    prob1 = DeviceProblem(M1, prob.idx, prob.p, slack=True, device=device, ctx=prob.ctx)
+    prob1 = DeviceProblem(M1, prob.idx, prob.p, slack=True, device=device, ctx=prob.ctx, rank=prob.rank, nranks=prob.nranks,
+                          block=prob.block, group=prob.group)
     Dz = prob.apply_D(z).cpu().numpy().T  # n x nD
     q = Dz[:, prob.idx[:-1]]
     s = Dz[:, prob.idx[-1]]
@@ -400,9 +408,11 @@ def feasibility_phase(geom, prob: DeviceProblem, z, cmat, state_variables, D, to
         zt = z1[: prob.N].clone()
         Dz0 = prob.apply_D(zt)
         lvm.s.zero_()
-        lvm.plan.assemble(lvm.s, Dz0, czero, 0.0, capi.WANT_F0, lvm.scal)
-        feasible = float(lvm.scal.cpu()[1]) == 1.0
+        lvm.assemble(lvm.s, Dz0, czero, 0.0, capi.WANT_F0)
+        feasible = float(lvm.read_scal()[1]) == 1.0
         if feasible and float(z1[prob.N:].max().cpu()) < 0:
+            if prob1.nranks > 1:
+                prob1.close()
             return zt, dict(ts=np.array(ts), its=np.array(its))
         t *= kappa
         if t > 1.0 / tol:
@@ -432,7 +442,9 @@ def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float =
     M = amg_helper(geom, PARABOLIC_STATE, Dt)
     n = geom.x.shape[0]
     # cone 1 of the plan = (grad u, s2) with p, cone 2 = (u, s1) with p = 2
-    prob = DeviceProblem(M, idxB, p, slack=False, device=device, idx2=idxA, p2=2.0)
+    rank, nranks, group = _dist_layout()
+    prob = DeviceProblem(M, idxB, p, slack=False, device=device, idx2=idxA, p2=2.0, rank=rank, nranks=nranks,
+                         block=geom.block, group=group)
     dev = prob.device
     ts = np.arange(t0, t1 + 1e-12 * max(1.0, abs(t1)), h)
     S = geom.subspaces["dirichlet"][-1].tocsr()
@@ -463,4 +475,6 @@ def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float =
         c[:, dim + 2] = h / p
         amgb_core(prob, z, _cm(c, dev), tol, t, kappa, maxit, max_newton, verbose, solve_fn)
         snaps.append(z.cpu().numpy().reshape(n, 3, order="F").copy())
+    if nranks > 1:
+        prob.close()
     return ParabolicSOL(geom, ts, snaps)

@@ -1,0 +1,35 @@
+"""torchrun worker (gloo, CPU): every rank builds only its own symbolic DistPlan; the owned pattern blocks, gathered
+over torch.distributed, must reassemble the global pattern, and the primary rows must partition the quadrature rows."""
+import os
+import sys
+
+import numpy as np
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import mgb_b200  # noqa: E402
+from mgb_b200 import capi, dist as mdist  # noqa: E402
+from helpers import problem  # noqa: E402
+
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+for gen, L in (("fem2d", 4), ("fem1d", 6)):
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom)
+    n, m = geom.x.shape[0], pr["R"].shape[1]
+    row_part, out_part = mdist.peer_partitions(n, m, geom.block, world)
+    pl = capi.DistPlan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, rank, world, row_part, out_part)
+    rp, ci = pl.own_pattern()
+    blocks = [None] * world
+    dist.all_gather_object(blocks, (pl.dinfo["own0"], rp, ci, pl.rows[: pl.dinfo["n_primary"]]))
+    grp, gci = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0).pattern()
+    rowptr = np.concatenate([[0]] + [np.diff(b[1]) for b in sorted(blocks, key=lambda b: b[0])]).cumsum()
+    colidx = np.concatenate([b[2] for b in sorted(blocks, key=lambda b: b[0])])
+    assert np.array_equal(rowptr, grp) and np.array_equal(colidx, gci)
+    assert np.array_equal(np.sort(np.concatenate([b[3] for b in blocks])), np.arange(n))
+dist.barrier()
+if rank == 0:
+    print("GLOO_OK")
+dist.destroy_process_group()

@@ -1,5 +1,6 @@
-"""torchrun worker: sharded assembly with the fused peer-memory exchange (CUDA IPC windows over NVLink),
-checked against the oracle on every rank.  Launched by tests/test_dist_peer_gpu.py with >= 2 GPUs."""
+"""torchrun worker: sharded (owner-computes) assembly, fused call - the gather kernel of every rank publishes its
+objective partials into the peers' windows (CUDA IPC over NVLink) and waits for theirs - checked against the oracle
+on every rank.  Launched by tests/test_dist_peer_gpu.py with >= 2 GPUs."""
 import os
 import sys
 
@@ -27,10 +28,9 @@ for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
     n, m = geom.x.shape[0], pr["R"].shape[1]
     plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, geom.block, rank, world)
     d = plan.dinfo
-    r0, r1 = d["row0"], d["row1"]
-    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)[r0:r1]
+    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)[plan.rows]
     cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
-    Dz0_d, c_d = cm(Dz0), cm(pr["c"][r0:r1])
+    Dz0_d, c_d = cm(Dz0), cm(pr["c"][plan.rows])
     Q = O.EuclidianPower(idx=pr["idx"], p=1.0)
     rng = np.random.default_rng(11)
     for step in range(4):
@@ -50,7 +50,7 @@ for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
         errf = abs(scal[0] - f0g) / abs(f0g)
         assert errH < 1e-12 and errg < 1e-12 and errf < 1e-12, (gen, L, step, errH, errg, errf)
         assert scal[1] == 1.0 and plan.dist_info()["err"] == 0
-    # back-to-back epochs without host synchronisation (double-buffered windows, monotone flags)
+    # back-to-back epochs without host synchronisation (two window parities, epoch tags)
     for _ in range(50):
         hp, gp, sp_ = plan.dist_assemble(s_d, Dz0_d, c_d, t, 7)
     h2 = ctx.to_host(hp, d["n_own_h"])

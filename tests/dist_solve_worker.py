@@ -1,6 +1,6 @@
 """torchrun worker: BASELINE.json configs[0] - `fem2d_mpi_solve(Float64; L=3, p=1.0)` on 2 ranks (the reference's
 quick example runs it with `mpiexec -n 2`, docs/src/guide.md:248) - through the API mirror with one GPU per rank:
-every level plan is sharded (fused peer-memory exchange), the solve seam sees the replicated system.
+the finest level plan is sharded (owner-computes), the solve seam sees the replicated system.
 Checked on every rank against the CPU oracle: identical t-schedule and Newton iteration counts per level,
 solution within 1e-9 relative (north_star bar).  Launched by tests/test_dist_peer_gpu.py with >= 2 GPUs."""
 import os
@@ -21,7 +21,8 @@ rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 for name, kw, geom in (("fem2d", dict(L=3, p=1.0), mgb_b200.fem2d(3)), ("fem1d", dict(L=4, p=2.0), mgb_b200.fem1d(4)),
-                       ("fem2d", dict(L=4, p=1.5), mgb_b200.fem2d(4))):
+                       ("fem2d", dict(L=4, p=1.5), mgb_b200.fem2d(4)),
+                       ("fem3d", dict(L=2, p=1.0), mgb_b200.fem3d(2))):   # Q3 elements: CSR path, assembled redundantly
     sol = getattr(api, name + "_mpi_solve")(**kw)          # backend: this job's ranks, one GPU each
     assert sol.stats["nranks"] == world
     native = api.mpi_to_native(sol)                         # collective gather of the row-partitioned solution

@@ -1,101 +1,73 @@
-"""world_size-2 gloo test of the multi-GPU host logic (partition, interface exchange maps, owner-side
-summation).  Local per-rank values come from the oracle restricted to the rank's quadrature rows, so
-no GPU is needed; the CUDA kernels are covered by the gpu tests."""
+"""Host logic of the sharded (owner-computes) plans on CPU: symbolic-only DistPlans (ctx=None).
+
+  * in-process: for 1..5 ranks the owned patterns tile the global pattern bit-exactly, every quadrature row is
+    primary on exactly one rank, and a rank's rows contain every element that touches its output rows;
+  * two processes over gloo (world_size 2): each rank builds only its own plan, the owned blocks are gathered with
+    torch.distributed and must reassemble the global pattern (the N>1 host path without a GPU)."""
 import os
+import subprocess
 import sys
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
-import torch
-import torch.distributed as dist
-import torch.multiprocessing as mp
+
+import mgb_b200
+from mgb_b200 import capi
+from mgb_b200.hpc import uniform_partition
+
+from helpers import problem
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _worker(rank, world, port, gen, L, level, q):
-    try:
-        for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
-            sys.path.insert(0, p)
-        os.environ["MASTER_ADDR"] = "127.0.0.1"
-        os.environ["MASTER_PORT"] = str(port)
-        dist.init_process_group("gloo", rank=rank, world_size=world)
-        import mgb_b200
-        from mgb_b200 import capi
-        from mgb_b200 import dist as mdist
-        import mgb_oracle as O
-        from helpers import problem
-        geom = getattr(mgb_b200, gen)(L)
-        pr = problem(geom, level=level)
-        n, m = geom.x.shape[0], pr["R"].shape[1]
-        row0, row1 = mdist.element_rows(n, geom.block, rank, world)
-        gplan = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0)
-        lplan = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, rows=(row0, row1))
-        grp, gci = gplan.pattern()
-        lrp, lci = lplan.pattern()
-        ex = mdist.build_exchange(rank, world, m, grp.astype(np.int64), gci.astype(np.int64), lrp.astype(np.int64),
-                                  lci.astype(np.int64), torch.device("cpu"))
-        # local contributions from the oracle restricted to this rank's quadrature rows
-        Q = O.EuclidianPower(idx=pr["idx"], p=1.0)
-        t = 0.8
-        Dl = [d[row0:row1] for d in pr["D"]]
-        args = (pr["s"], pr["x"][row0:row1], pr["w"][row0:row1], t * pr["c"][row0:row1], pr["R"], Dl, pr["z0"], Q)
-        Hl = O.f2(*args).tocsr()
-        gl = O.f1(*args)
-        f0l = O.f0(*args)
-        rows = np.repeat(np.arange(m), np.diff(lrp))
-        exch = mdist.Exchanger(ex, torch.device("cpu"), n_loc_h=lplan.nnzH, m=m)
-        hv, gv, sv = exch.views()
-        hv.copy_(torch.from_numpy(np.asarray(Hl[rows, lci]).ravel().copy()))
-        gv.copy_(torch.from_numpy(gl.copy()))
-        sv.copy_(torch.tensor([f0l, 1.0, 0.0, 0.0], dtype=torch.float64))
-        h_own, g_own, scal = exch.exchange()
-        # global oracle
-        argsg = (pr["s"], pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
-        Hg = O.f2(*argsg).tocsr()
-        gg = O.f1(*argsg)
-        lo, hi = int(ex.m_part[rank] - 1), int(ex.m_part[rank + 1] - 1)
-        Hown = sp.csr_matrix((h_own.numpy(), ex.own_colidx, ex.own_rowptr), shape=(hi - lo, m))
-        errH = abs(Hown - Hg[lo:hi]).max() / abs(Hg).max()
-        errg = np.abs(g_own.numpy() - gg[lo:hi]).max() / np.abs(gg).max()
-        errf = abs(float(scal[0]) - O.f0(*argsg)) / abs(O.f0(*argsg))
-        cover = int(sum(ex.h_recv_splits))
-        assert float(scal[1]) == 1.0
-        q.put((rank, float(errH), float(errg), float(errf), cover, (row0, row1), (lo, hi)))
-        dist.destroy_process_group()
-    except Exception as exc:  # pragma: no cover
-        import traceback
-        q.put((rank, "error", traceback.format_exc()))
+@pytest.mark.parametrize("gen,L,slack", [("fem2d", 3, False), ("fem2d", 4, False), ("fem1d", 5, False), ("fem2d", 2, True)])
+@pytest.mark.parametrize("nranks", [1, 2, 3, 5])
+def test_owned_patterns_tile_the_global_pattern(gen, L, slack, nranks):
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom, slack=slack)
+    n, m = geom.x.shape[0], pr["R"].shape[1]
+    glob = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, slack=slack)
+    grp, gci = glob.pattern()
+    row_part, out_part = uniform_partition(n, nranks, geom.block) - 1, uniform_partition(m, nranks) - 1
+    E = [(Dk @ pr["R"]).tocsr() for Dk in pr["D"]]
+    touched = sp.csr_matrix(sum(abs(Ek) for Ek in E))          # n x m: dofs every quadrature row touches
+    prim_all = []
+    for r in range(nranks):
+        pl = capi.DistPlan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, r, nranks, row_part, out_part, slack=slack)
+        d = pl.dinfo
+        lo, hi = d["own0"], d["own1"]
+        assert (lo, hi) == (out_part[r], out_part[r + 1])
+        rp, ci = pl.own_pattern()
+        assert np.array_equal(rp, grp[lo:hi + 1] - grp[lo]) and np.array_equal(ci, gci[grp[lo]:grp[hi]])
+        rows = pl.rows
+        assert len(np.unique(rows)) == len(rows) and len(rows) % geom.block == 0
+        prim_all.append(rows[: d["n_primary"]])
+        # completeness: every quadrature row with a dof in [lo, hi) is evaluated by this rank
+        need = np.flatnonzero(np.diff(touched[:, lo:hi].tocsr().indptr) > 0)
+        assert np.isin(need, rows).all()
+    assert np.array_equal(np.sort(np.concatenate(prim_all)), np.arange(n))
 
 
-@pytest.mark.parametrize("gen,L,level", [("fem1d", 4, None), ("fem2d", 3, None), ("fem2d", 3, 1)])
-def test_two_rank_exchange_matches_global_assembly(gen, L, level):
-    ctx = mp.get_context("spawn")
-    q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000) + {"fem1d": 0, "fem2d": 1}[gen] + (7 if level else 0)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, gen, L, level, q)) for r in range(2)]
-    for p in procs:
-        p.start()
-    res = [q.get(timeout=300) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
-    for r in res:
-        assert r[1] != "error", r[2]
-        rank, errH, errg, errf, cover, rows, own = r
-        assert errH < 1e-12 and errg < 1e-12 and errf < 1e-12, r
-        assert cover > 0
-    rows = sorted(r[5] for r in res)
-    assert rows[0][1] == rows[1][0] and rows[0][0] == 0      # contiguous row blocks
-    owns = sorted(r[6] for r in res)
-    assert owns[0][1] == owns[1][0] and owns[0][0] == 0
+def test_coarse_levels_and_unstructured_operators_refuse_to_shard():
+    """the refusal every rank sees alike (solver.LevelState then assembles the level redundantly)"""
+    geom = mgb_b200.fem2d(4)
+    pr = problem(geom, level=0)
+    n, m = geom.x.shape[0], pr["R"].shape[1]
+    rp, op = uniform_partition(n, 2, geom.block) - 1, uniform_partition(m, 2) - 1
+    with pytest.raises(capi.MgbError, match="sharded plans need the element path"):
+        capi.DistPlan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, 0, 2, rp, op)
+    g3 = mgb_b200.fem3d(1)
+    p3 = problem(g3)
+    n, m = g3.x.shape[0], p3["R"].shape[1]
+    rp, op = uniform_partition(n, 2, g3.block) - 1, uniform_partition(m, 2) - 1
+    with pytest.raises(capi.MgbError, match="sharded plans need the element path"):
+        capi.DistPlan(None, p3["D"], p3["R"], p3["x"], p3["w"], p3["idx"], 1.0, 0, 2, rp, op)
 
 
-def test_partition_rule():
-    from mgb_b200.hpc import uniform_partition
-    assert np.array_equal(uniform_partition(10, 1), [1, 11])            # [1, n+1] for one rank (tools/profile_solve.jl:24)
-    assert np.array_equal(uniform_partition(10, 3), [1, 5, 8, 11])      # first n mod P ranks get the extra row
-    assert np.array_equal(uniform_partition(28, 2, block=7), [1, 15, 29])
-    assert np.array_equal(uniform_partition(21, 2, block=7), [1, 15, 22])
-    p = uniform_partition(229376, 8, block=7)
-    assert p[0] == 1 and p[-1] == 229377 and np.all(np.diff(p) % 7 == 0)
+def test_two_process_gloo_plans_reassemble_the_global_pattern():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29647", os.path.join(ROOT, "tests", "dist_cpu_worker.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
+    assert "GLOO_OK" in res.stdout

@@ -1,9 +1,11 @@
-"""GPU parity of the fused peer-memory exchange (element_kernel -> push_kernel -> finish_kernel).
+"""GPU parity of the sharded (owner-computes) assembly: element_kernel -> gather_kernel on every rank's elements,
+objective scalars summed across ranks through peer-memory words.
 
-Single-GPU box: the ranks are *virtual* - N distributed plans on one device, windows attached by raw
-pointer (mgb_dist_attach_local), all pushes launched before any finish (same stream), so the flag
-protocol, destination maps, staging sums and epoch double-buffering run exactly as on N GPUs.
-With >= 2 GPUs the torchrun worker runs the real thing over CUDA IPC + NVLink (tests/dist_peer_worker.py)."""
+Single-GPU box: the ranks are *virtual* - N distributed plans on one device and one stream, windows attached by
+raw pointer (mgb_dist_attach_local), split mode: every rank's mgb_dist_begin (which publishes its partial sums)
+runs before any mgb_dist_end (which collects them), so no kernel ever waits for another one on the same GPU.
+With >= 2 GPUs the torchrun workers run the fused call (mgb_dist_assemble: the gather kernel itself waits for the
+peers' words) over CUDA IPC + NVLink (tests/dist_peer_worker.py, tests/dist_solve_worker.py)."""
 import os
 import subprocess
 import sys
@@ -32,13 +34,16 @@ def _virtual_ranks(ctx, gen, L, nranks, p=1.0, slack=False, steps=3):
     wins = [pl.window()[0] for pl in plans]
     for pl in plans:
         pl.attach_local(wins)
+    # every quadrature row is "primary" (counted in the scalars) on exactly one rank
+    prim = np.concatenate([pl.rows[: pl.dinfo["n_primary"]] for pl in plans])
+    assert np.array_equal(np.sort(prim), np.arange(n))
     dev = torch.device("cuda", ctx.device)
     Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
     cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
-    ins = [(cm(Dz0[row_part[r]:row_part[r + 1]]), cm(pr["c"][row_part[r]:row_part[r + 1]])) for r in range(nranks)]
+    ins = [(cm(Dz0[pl.rows]), cm(pr["c"][pl.rows])) for pl in plans]
     flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
     rng = np.random.default_rng(5)
-    for step in range(steps):   # several epochs: exercises both window parities and the flag counters
+    for step in range(steps):   # several epochs: exercises both window parities and the epoch tags
         t = 0.8 + 0.1 * step
         if step:
             pr["s"] = pr["s"] + 1e-4 * rng.uniform(-1, 1, size=pr["s"].shape)
@@ -47,12 +52,14 @@ def _virtual_ranks(ctx, gen, L, nranks, p=1.0, slack=False, steps=3):
             pl.begin(s_d, ins[r][0], ins[r][1], t, flags)
         ptrs = [pl.end(t, flags) for pl in plans]
         f0_o, g_o, H_o = oracle_eval(pr, t)
+        scals = []
         for r, pl in enumerate(plans):
             d = pl.dinfo
             hp, gp, sp_ = ptrs[r]
             h_own = ctx.to_host(hp, d["n_own_h"])
             g_own = ctx.to_host(gp, d["n_own_g"])
             scal = ctx.to_host(sp_, 4)
+            scals.append(scal)
             orp, oci = pl.own_pattern()
             lo, hi = d["own0"], d["own1"]
             Hown = sp.csr_matrix((h_own, oci.astype(np.int64), orp.astype(np.int64)), shape=(hi - lo, m))
@@ -60,7 +67,8 @@ def _virtual_ranks(ctx, gen, L, nranks, p=1.0, slack=False, steps=3):
             assert np.abs(g_own - g_o[lo:hi]).max() <= 1e-12 * np.abs(g_o).max()
             assert abs(scal[0] - f0_o) <= 1e-12 * abs(f0_o) and scal[1] == 1.0
             assert pl.dist_info()["err"] == 0
-    # f0-only call (line search): no Hessian/gradient pushes, scalars still cross ranks
+        assert all(np.array_equal(scals[0], sc) for sc in scals), "rank-ordered sums must give identical bits on every rank"
+    # f0-only call (line search): the scalars still cross the ranks
     for r, pl in enumerate(plans):
         pl.begin(s_d, ins[r][0], ins[r][1], t, capi.WANT_F0)
     for pl in plans:
@@ -76,13 +84,62 @@ def test_virtual_ranks_match_oracle(gpu_ctx, gen, L, nranks):
     _virtual_ranks(gpu_ctx, gen, L, nranks)
 
 
-def test_virtual_ranks_p_and_single_rank(gpu_ctx):
+def test_virtual_ranks_p_slack_and_single_rank(gpu_ctx):
     _virtual_ranks(gpu_ctx, "fem2d", 3, 2, p=1.5)
-    _virtual_ranks(gpu_ctx, "fem2d", 3, 1)      # nranks = 1: every entry is single-source
+    _virtual_ranks(gpu_ctx, "fem2d", 3, 2, slack=True)     # three state variables (feasibility phase)
+    _virtual_ranks(gpu_ctx, "fem2d", 3, 1)                 # nranks = 1
 
 
-def test_missing_peer_times_out_without_hanging(gpu_ctx):
-    """a rank whose peer never publishes its flag reports err=1 after the timeout instead of hanging the GPU"""
+def test_sharded_two_cone_plan(gpu_ctx):
+    """the parabolic barrier (two cones, three state variables) shards like the others"""
+    import torch
+    import mgb_b200
+    import mgb_oracle as O
+    from mgb_b200 import capi
+    from mgb_b200.hpc import uniform_partition
+    geom = mgb_b200.fem2d(3)
+    dim, p, t, N = 2, 1.0, 0.6, 3
+    Dt, idxA, idxB = O.parabolic_tables(dim)
+    M = O.amg_helper(geom, O.PARABOLIC_STATE, Dt)
+    n = geom.x.shape[0]
+    rng = np.random.default_rng(5)
+    u = np.sin(geom.x[:, 0]) + geom.x[:, 1] ** 2
+    z0 = O.parabolic_feasible_start(M, u, dim, p)
+    R = M.R_fine[-1]
+    m = R.shape[1]
+    s = 1e-3 * rng.uniform(-1, 1, size=m)
+    c = rng.normal(size=(n, len(Dt)))
+    Q = O.Intersection([O.EuclidianPower(idx=idxA, p=2.0), O.EuclidianPower(idx=idxB, p=p)])
+    args = (s, geom.x, geom.w, t * c, R, M.D, z0, Q)
+    f0, g, H = O.f0(*args), O.f1(*args), O.f2(*args).tocsr()
+    rp, op = uniform_partition(n, N, geom.block) - 1, uniform_partition(m, N) - 1
+    plans = [capi.DistPlan(gpu_ctx, M.D, R, geom.x, geom.w, idxB, p, r, N, rp, op, idx2=idxA, p2=2.0) for r in range(N)]
+    wins = [pl.window()[0] for pl in plans]
+    for pl in plans:
+        pl.attach_local(wins)
+    dev = torch.device("cuda", gpu_ctx.device)
+    Dz0 = np.stack([Dk @ z0 for Dk in M.D], axis=1)
+    cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
+    s_d = torch.from_numpy(s).to(dev)
+    ins = [(cm(Dz0[pl.rows]), cm(c[pl.rows])) for pl in plans]
+    for r, pl in enumerate(plans):
+        pl.begin(s_d, ins[r][0], ins[r][1], t, 7)
+    for pl in plans:
+        hp, gp, sp_ = pl.end(t, 7)
+        d = pl.dinfo
+        orp, oci = pl.own_pattern()
+        lo, hi = d["own0"], d["own1"]
+        Hown = sp.csr_matrix((gpu_ctx.to_host(hp, d["n_own_h"]), oci.astype(np.int64), orp.astype(np.int64)), shape=(hi - lo, m))
+        assert abs(Hown - H[lo:hi]).max() <= 1e-12 * abs(H).max()
+        assert np.abs(gpu_ctx.to_host(gp, d["n_own_g"]) - g[lo:hi]).max() <= 1e-12 * np.abs(g).max()
+        assert abs(gpu_ctx.to_host(sp_, 4)[0] - f0) <= 1e-12 * abs(f0)
+    for pl in plans:
+        pl.close()
+
+
+def test_missing_peer_is_reported_not_summed(gpu_ctx):
+    """a rank whose peer never publishes its scalars must not return a partial sum as the objective: after the
+    time-out the scalars are NaN with all_finite = 0 and the plan's error flag is set (the GPU does not hang)"""
     import torch
     import mgb_b200
     from mgb_b200 import capi
@@ -104,63 +161,17 @@ def test_missing_peer_times_out_without_hanging(gpu_ctx):
     Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
     cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
     s_d = torch.from_numpy(pr["s"]).to(dev)
-    plans[0].begin(s_d, cm(Dz0[rp[0]:rp[1]]), cm(pr["c"][rp[0]:rp[1]]), 1.0, 7)   # rank 1 never runs
-    plans[0].end(1.0, 7)
-    gpu_ctx.sync()
-    assert plans[0].dist_info()["err"] == 1
+    pl = plans[0]
+    pl.begin(s_d, cm(Dz0[pl.rows]), cm(pr["c"][pl.rows]), 1.0, 7)   # rank 1 never runs
+    _, _, sp_ = pl.end(1.0, 7)
+    scal = gpu_ctx.to_host(sp_, 4)
+    assert pl.dist_info()["err"] == 1
+    assert np.isnan(scal[0]) and scal[1] == 0.0
     for pl in plans:
         pl.close()
 
 
-def test_fused_finish_two_streams(gpu_ctx):
-    """mgb_dist_assemble (finish fused into the push kernel's last CTA): two ranks on two streams of one GPU,
-    each waiting in-kernel for the other's epoch flag."""
-    import torch
-    import mgb_b200
-    from mgb_b200 import capi
-    from mgb_b200.hpc import uniform_partition
-    from helpers import problem, oracle_eval
-    geom = mgb_b200.fem2d(4)
-    pr = problem(geom)
-    n, m = geom.x.shape[0], pr["R"].shape[1]
-    rp, op = uniform_partition(n, 2, geom.block) - 1, uniform_partition(m, 2) - 1
-    dev = torch.device("cuda", gpu_ctx.device)
-    streams = [torch.cuda.Stream(dev) for _ in range(2)]
-    ctxs = [capi.Context(gpu_ctx.device, st.cuda_stream) for st in streams]
-    plans = [capi.DistPlan(ctxs[r], pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, r, 2, rp, op) for r in range(2)]
-    wins = [pl.window()[0] for pl in plans]
-    for pl in plans:
-        pl.attach_local(wins)
-    Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)
-    cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
-    ins = [(cm(Dz0[rp[r]:rp[r + 1]]), cm(pr["c"][rp[r]:rp[r + 1]])) for r in range(2)]
-    s_d = torch.from_numpy(pr["s"]).to(dev)
-    torch.cuda.synchronize(dev)
-    t = 0.9
-    f0_o, g_o, H_o = oracle_eval(pr, t)
-    for rep in range(6):   # repeated epochs, alternating which rank launches first
-        order = (0, 1) if rep % 2 == 0 else (1, 0)
-        ptrs = {}
-        for r in order:
-            ptrs[r] = plans[r].dist_assemble(s_d, ins[r][0], ins[r][1], t, 7)
-        for r in range(2):
-            d = plans[r].dinfo
-            hp, gp, sp_ = ptrs[r]
-            h_own, g_own, scal = ctxs[r].to_host(hp, d["n_own_h"]), ctxs[r].to_host(gp, d["n_own_g"]), ctxs[r].to_host(sp_, 4)
-            orp, oci = plans[r].own_pattern()
-            lo, hi = d["own0"], d["own1"]
-            Hown = sp.csr_matrix((h_own, oci.astype(np.int64), orp.astype(np.int64)), shape=(hi - lo, m))
-            assert abs(Hown - H_o[lo:hi]).max() <= 1e-12 * abs(H_o).max()
-            assert np.abs(g_own - g_o[lo:hi]).max() <= 1e-12 * np.abs(g_o).max()
-            assert abs(scal[0] - f0_o) <= 1e-12 * abs(f0_o) and scal[1] == 1.0
-            assert plans[r].dist_info()["err"] == 0
-    for pl in plans:
-        pl.close()
-    for c in ctxs:
-        c.close()
-
-
-def test_two_gpu_peer_exchange_matches_oracle():
+def test_two_gpu_sharded_assembly_matches_oracle():
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -172,7 +183,8 @@ def test_two_gpu_peer_exchange_matches_oracle():
 
 
 def test_two_gpu_sharded_solve_matches_oracle():
-    """configs[0] of BASELINE.json: fem2d_mpi_solve(L=3, p=1.0) on 2 ranks, one GPU each (+ a 1-D and a p=1.5 case)"""
+    """configs[0] of BASELINE.json: fem2d_mpi_solve(L=3, p=1.0) on 2 ranks, one GPU each (+ a 1-D, a p=1.5 and a
+    fem3d case, which falls back to redundant assembly)"""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
