@@ -59,8 +59,7 @@ def test_derivative_identities_at_full_size(gpu_ctx, gen, L):
     assert np.linalg.norm(hv_fd - hv) <= 1e-4 * np.linalg.norm(hv), np.linalg.norm(hv_fd - hv) / np.linalg.norm(hv)
 
 def test_sharded_equals_single_at_full_size(gpu_ctx):
-    """fem2d L=8 on 4 virtual ranks (split mode, one GPU): owned blocks tile the single-plan result bit for bit
-    (same kernels, same per-entry summation order)"""
+    """fem2d L=8 on 4 virtual ranks (split mode, one GPU): owned blocks tile the single-plan result"""
     import torch
     from mgb_b200 import capi
     from mgb_b200 import dist as mdist
@@ -92,7 +91,10 @@ def test_sharded_equals_single_at_full_size(gpu_ctx):
         assert np.array_equal(p.own_pattern()[1], ci[rp[d["own0"]]:rp[d["own1"]]])
     h_all, g_all = np.concatenate(hs), np.concatenate(gs)
     assert h_all.size == plan.nnzH
-    assert np.array_equal(h_all, ref["hval"]) and np.array_equal(g_all, ref["grad"])
+    # (a rank lists its primary elements before its halo elements, so an entry's two contributions may be added in the
+    # other order than in the single plan: agreement to rounding, not bit for bit)
+    assert np.abs(h_all - ref["hval"]).max() <= 1e-13 * np.abs(ref["hval"]).max()
+    assert np.abs(g_all - ref["grad"]).max() <= 1e-13 * np.abs(ref["grad"]).max()
     for p in plans:
         p.close()
 
