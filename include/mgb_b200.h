@@ -142,6 +142,21 @@ int mgb_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, con
                  double t, int32_t flags, double* scal_dev, double* grad_dev, double* hval_dev,
                  double* Dz_dev);
 
+/* CUDA graphs.  mgb_assemble replays an instantiated graph of its two to four kernel launches (captured once per
+ * distinct argument tuple, programmatic dependent-launch edges included; a small LRU cache per plan) whenever the
+ * context runs on a real stream; MGB_GRAPH=0 in the environment keeps plain launches.  For a longer fixed sequence -
+ * e.g. one assembly on every level of a hierarchy - bracket the calls with mgb_graph_begin / mgb_graph_end: between
+ * the two, the library's launches on this context are recorded instead of executed; mgb_graph_launch replays them
+ * with one launch (same buffers, same scalars). */
+typedef struct mgb_graph mgb_graph;
+int mgb_graph_begin(mgb_ctx* ctx);
+int mgb_graph_end(mgb_ctx* ctx, mgb_graph** out);
+int mgb_graph_launch(mgb_graph* graph);
+int mgb_graph_destroy(mgb_graph* graph);
+/* {state (1 graphs in use, 0 not yet decided, -1 off: MGB_GRAPH=0, legacy default stream or capture refused),
+ *  graphs captured, graph launches} of a plan's mgb_assemble cache */
+int mgb_graph_stats(const mgb_plan* plan, int64_t* stats3);
+
 /* Same call through HOST buffers (what a CPU-array caller of f1/f2 sees): copies s (and, when
  * upload_inputs!=0, Dz0 and c) to the device, runs mgb_assemble, copies the requested results back
  * and synchronises. */

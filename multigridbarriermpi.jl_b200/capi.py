@@ -28,6 +28,7 @@ EXPORTS = [
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_plan_create_rows", "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_rows", "mgb_dist_pattern", "mgb_dist_window",
     "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_host_register", "mgb_host_unregister",
+    "mgb_graph_begin", "mgb_graph_end", "mgb_graph_launch", "mgb_graph_destroy", "mgb_graph_stats",
 ]
 
 
@@ -121,6 +122,11 @@ def load(build_if_missing: bool = True):
     lib.mgb_copy_to_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.mgb_host_register.argtypes = [C.c_void_p, C.c_int64]
     lib.mgb_host_unregister.argtypes = [C.c_void_p]
+    lib.mgb_graph_begin.argtypes = [C.c_void_p]
+    lib.mgb_graph_end.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mgb_graph_launch.argtypes = [C.c_void_p]
+    lib.mgb_graph_destroy.argtypes = [C.c_void_p]
+    lib.mgb_graph_stats.argtypes = [C.c_void_p, C.c_void_p]
     lib.mgb_plan_create_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.POINTER(_Csr), C.POINTER(_Csr), C.c_int32,
                                          C.c_void_p, C.c_void_p, C.POINTER(_Barrier), C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_int64, C.c_int64, C.c_int32, C.POINTER(C.c_void_p)]
@@ -231,9 +237,39 @@ class Context:
         _check(load().mgb_copy_to_host(self._h, out.ctypes.data, C.c_void_p(int(src_dev)), out.nbytes))
         return out
 
+    def graph_begin(self):
+        """record (instead of execute) the library's launches on this context until graph_end (mgb_graph_begin)"""
+        _check(load().mgb_graph_begin(self._h))
+
+    def graph_end(self) -> "Graph":
+        h = C.c_void_p()
+        _check(load().mgb_graph_end(self._h, C.byref(h)))
+        return Graph(h)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
             load().mgb_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Graph:
+    """instantiated CUDA graph of a recorded call sequence (mgb_graph)"""
+
+    def __init__(self, h):
+        self._h = h
+
+    def launch(self):
+        _check(load().mgb_graph_launch(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            load().mgb_graph_destroy(self._h)
             self._h = None
 
     def __del__(self):
@@ -375,6 +411,11 @@ class Plan:
                                         _ptr(scal), _ptr(grad), _ptr(hval), _ptr(Dz)))
         assert nd >= 0
         return dict(scal=scal, grad=grad, hval=hval, Dz=Dz)
+
+    def graph_stats(self) -> dict:
+        v = np.zeros(3, dtype=np.int64)
+        _check(load().mgb_graph_stats(self._h, v.ctypes.data))
+        return dict(state=int(v[0]), captures=int(v[1]), launches=int(v[2]))
 
     def apply_D(self, s_dev, Dz0_dev, Dz_dev):
         _check(load().mgb_apply_D(self._h, _ptr(s_dev), _ptr(Dz0_dev), _ptr(Dz_dev)))

@@ -96,6 +96,7 @@ struct mgb_ctx {
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
+    bool capturing = false;   // between mgb_graph_begin and mgb_graph_end: launches are recorded, not executed
     DevBuf<double> flush;  // L2 flush scratch (lazy)
     DevBuf<int> flag;
     DevBuf<double> red;       // reduce_kernel: REDUCE_BLOCKS partials + result (lazy)
@@ -176,6 +177,26 @@ struct mgb_plan {
         }
     };
     std::unique_ptr<Dist> dist;
+    // ---- CUDA-graph cache of mgb_assemble: one instantiated graph per distinct argument tuple (the Newton loop calls
+    // with a handful: trial / accepted iterate x objective-only / full, t changing once per central-path step)
+    struct GraphEntry {
+        const void* key[8] = {nullptr};
+        double t = 0.0;
+        int flags = 0;
+        cudaGraphExec_t exec = nullptr;
+        int kernels = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<GraphEntry> graphs;
+    uint64_t graph_clock = 0;
+    int graph_state = 0;   // 0 untested, 1 in use, -1 disabled (env MGB_GRAPH=0, legacy default stream, or capture refused)
+    int64_t graph_hits = 0, graph_captures = 0;
+};
+
+struct mgb_graph {
+    mgb_ctx* ctx = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    int kernels = 0;
 };
 
 struct mgb_spmat {
@@ -735,6 +756,7 @@ int mgb_plan_destroy(mgb_plan* plan) {
         cudaStreamSynchronize(plan->ctx->stream);
     }
     for (auto& e : plan->ev) if (e) cudaEventDestroy(e);
+    for (auto& g : plan->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
     delete plan;
     return 0;
 }
@@ -755,6 +777,81 @@ int mgb_plan_pattern(const mgb_plan* pl, int32_t* rowptr_host, int32_t* colidx_h
     return 0;
 }
 
+namespace {
+void assemble_direct(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags,
+                     double* scal_dev, double* grad_dev, double* hval_dev, double* Dz_dev) {
+    if (pl->path == MGB_PATH_ELEMENT)
+        assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev);
+    else
+        g_launches += mgb::csr_assemble(pl->csr, pl->d_w.p, s_dev, Dz0_dev, c_dev, t, flags,
+                                        scal_dev ? scal_dev : pl->d_scal_tmp.p, grad_dev, hval_dev, Dz_dev, pl->ctx->stream);
+}
+
+constexpr size_t GRAPH_CACHE = 8;
+
+// One cudaGraphLaunch instead of two to four kernel launches: the launches of an assembly (with their programmatic
+// dependent-launch edges) are captured once per argument tuple and replayed.  Returns false when graphs are off.
+bool assemble_graph(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags,
+                    double* scal_dev, double* grad_dev, double* hval_dev, double* Dz_dev) {
+    mgb_ctx* ctx = pl->ctx;
+    if (pl->graph_state < 0 || ctx->capturing) return false;
+    if (pl->graph_state == 0) {
+        const char* ev = getenv("MGB_GRAPH");
+        // the legacy default stream cannot be captured
+        pl->graph_state = (ctx->stream == nullptr || (ev && atoi(ev) == 0)) ? -1 : 1;
+        if (pl->graph_state < 0) return false;
+    }
+    const void* key[8] = {s_dev, Dz0_dev, c_dev, scal_dev, grad_dev, hval_dev, Dz_dev, nullptr};
+    pl->graph_clock++;
+    for (auto& g : pl->graphs)
+        if (g.exec && g.flags == flags && g.t == t && std::memcmp(g.key, key, sizeof(key)) == 0) {
+            g.last_use = pl->graph_clock;
+            CUDA_OK(cudaGraphLaunch(g.exec, ctx->stream));
+            g_launches += g.kernels;
+            pl->graph_hits++;
+            return true;
+        }
+    // capture
+    const int64_t before = g_launches.load();
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+        cudaGetLastError();
+        pl->graph_state = -1;
+        return false;
+    }
+    bool ok = true;
+    std::string why;
+    try { assemble_direct(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev); }
+    catch (const std::exception& ex) { ok = false; why = ex.what(); }
+    const cudaError_t ec = cudaStreamEndCapture(ctx->stream, &graph);
+    const int kernels = (int)(g_launches.load() - before);
+    g_launches = before;   // recorded, not executed
+    cudaGraphExec_t exec = nullptr;
+    if (ok && ec == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+        cudaGraphDestroy(graph);
+    } else {
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        if (!ok && ec == cudaSuccess) throw std::runtime_error(why);   // a genuine argument error: report it
+        pl->graph_state = -1;   // capture / instantiation refused: plain launches from now on (visible in mgb_graph_stats)
+        return false;
+    }
+    mgb_plan::GraphEntry* slot = nullptr;
+    if (pl->graphs.size() < GRAPH_CACHE) { pl->graphs.emplace_back(); slot = &pl->graphs.back(); }
+    else {
+        slot = &pl->graphs[0];
+        for (auto& g : pl->graphs) if (g.last_use < slot->last_use) slot = &g;
+        if (slot->exec) cudaGraphExecDestroy(slot->exec);
+    }
+    std::memcpy(slot->key, key, sizeof(key));
+    slot->t = t; slot->flags = flags; slot->exec = exec; slot->kernels = kernels; slot->last_use = pl->graph_clock;
+    pl->graph_captures++;
+    CUDA_OK(cudaGraphLaunch(exec, ctx->stream));
+    g_launches += kernels;
+    return true;
+}
+}  // namespace
+
 int mgb_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                  int32_t flags, double* scal_dev, double* grad_dev, double* hval_dev, double* Dz_dev) {
     try {
@@ -762,14 +859,65 @@ int mgb_assemble(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const
         if (!pl->ctx) return fail("mgb_assemble: symbolic-only plan (created without a GPU context); no CPU path exists");
         if ((flags & MGB_WANT_HESS) && !pl->has_hessian) return fail("mgb_assemble: plan was created with MGB_PLAN_NO_HESSIAN");
         CUDA_OK(cudaSetDevice(pl->ctx->device));
-        if (pl->path == MGB_PATH_ELEMENT)
-            assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev);
-        else
-            g_launches += mgb::csr_assemble(pl->csr, pl->d_w.p, s_dev, Dz0_dev, c_dev, t, flags,
-                                            scal_dev ? scal_dev : pl->d_scal_tmp.p, grad_dev, hval_dev, Dz_dev,
-                                            pl->ctx->stream);
+        if (!assemble_graph(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev))
+            assemble_direct(pl, s_dev, Dz0_dev, c_dev, t, flags, scal_dev, grad_dev, hval_dev, Dz_dev);
         return 0;
     } catch (const std::exception& ex) { return fail(std::string("mgb_assemble: ") + ex.what()); }
+}
+
+int mgb_graph_stats(const mgb_plan* pl, int64_t* stats3) {
+    if (!pl || !stats3) return fail("mgb_graph_stats: NULL argument");
+    stats3[0] = pl->graph_state; stats3[1] = pl->graph_captures; stats3[2] = pl->graph_hits;
+    return 0;
+}
+
+int mgb_graph_begin(mgb_ctx* ctx) {
+    try {
+        if (!ctx) return fail("mgb_graph_begin: ctx is NULL");
+        if (ctx->capturing) return fail("mgb_graph_begin: a capture is already open on this context");
+        if (!ctx->stream) return fail("mgb_graph_begin: the legacy default stream cannot be captured; create the context on a real stream");
+        CUDA_OK(cudaSetDevice(ctx->device));
+        CUDA_OK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        ctx->capturing = true;
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_graph_begin: ") + ex.what()); }
+}
+
+int mgb_graph_end(mgb_ctx* ctx, mgb_graph** out) {
+    try {
+        if (!ctx || !out) return fail("mgb_graph_end: NULL argument");
+        if (!ctx->capturing) return fail("mgb_graph_end: no capture open (mgb_graph_begin)");
+        ctx->capturing = false;
+        cudaGraph_t graph = nullptr;
+        CUDA_OK(cudaStreamEndCapture(ctx->stream, &graph));
+        auto g = std::make_unique<mgb_graph>();
+        g->ctx = ctx;
+        size_t nn = 0;
+        CUDA_OK(cudaGraphGetNodes(graph, nullptr, &nn));
+        g->kernels = (int)nn;
+        const cudaError_t e = cudaGraphInstantiate(&g->exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) throw std::runtime_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+        *out = g.release();
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_graph_end: ") + ex.what()); }
+}
+
+int mgb_graph_launch(mgb_graph* g) {
+    try {
+        if (!g || !g->exec) return fail("mgb_graph_launch: NULL graph");
+        CUDA_OK(cudaSetDevice(g->ctx->device));
+        CUDA_OK(cudaGraphLaunch(g->exec, g->ctx->stream));
+        g_launches += g->kernels;
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_graph_launch: ") + ex.what()); }
+}
+
+int mgb_graph_destroy(mgb_graph* g) {
+    if (!g) return 0;
+    if (g->exec) { cudaSetDevice(g->ctx->device); cudaStreamSynchronize(g->ctx->stream); cudaGraphExecDestroy(g->exec); }
+    delete g;
+    return 0;
 }
 
 int mgb_assemble_host(mgb_plan* pl, const double* s_host, const double* Dz0_host, const double* c_host,
