@@ -370,6 +370,18 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
+    ms_sdist = None
+    if sharded:   # the same step starting from a row-distributed unknown (the reference's HPCVector): + all-gather of s
+        s_own = s_d[plan.dinfo["own0"]: plan.dinfo["own1"]].clone()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10 + 3)]
+        for a, b in evs:
+            if flush:
+                flush_buf.sum()
+            a.record()
+            plan.dist_assemble_s(s_own, Dz0_d, c_d, args.t, flags)
+            b.record()
+        torch.cuda.synchronize(dev)
+        ms_sdist = sum(a.elapsed_time(b) for a, b in evs[3:]) / 10
     # ---- parity of the buffers that were just timed (every rank: its owned rows against the oracle's)
     if sharded:
         ho, go, so = window_views(plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags))
@@ -441,7 +453,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         e2e_extra["path"] = "pinned host buffers around mgb_dist_assemble (owned blocks)"
 
     par = [parity[k] if parity else 0.0 for k in ("f0_rel", "grad_rel", "hess_rel")]
-    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms] + par + [float(rows.size), float(n_h)], dtype=f64, device=dev)
+    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms] + par + [float(rows.size), float(n_h), ms_sdist or 0.0], dtype=f64, device=dev)
     mx = vals.clone()
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -498,6 +510,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
                        "iterate": "boundary lift g(x)=[x1^2+x2^2,100] + 1e-3*U(-1,1), seed 20261018",
                        "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
                        "rows_evaluated_max_rank": int(mx[7].cpu()), "rows_total": n, "owned_hessian_entries_max_rank": int(mx[8].cpu()),
+                       "ms_from_row_distributed_s": (float(mx[9].cpu()) if sharded else None),
                        "multi_gpu": None if not sharded else (
                            "owner-computes: a rank evaluates every element touching its output rows (each element on about "
                            "two ranks) and completes its rows of R'HR / block of g locally; only the 3 objective scalars cross "

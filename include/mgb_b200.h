@@ -269,6 +269,17 @@ int mgb_dist_begin(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, c
  * count} (global sums, identical bits on every rank). */
 int mgb_dist_end(mgb_plan* plan, double t, int32_t flags, const double** hval_own_dev,
                  const double** grad_own_dev, const double** scal_dev);
+/* Row-distributed Newton unknown (the reference's s is an HPCVector: every rank holds only its block, the
+ * [out_part[rank], out_part[rank+1]) entries).  mgb_dist_s_publish stores this rank's block into every rank's copy
+ * of the whole vector over NVLink peer memory and raises this rank's epoch flag everywhere; mgb_dist_s_wait enqueues
+ * the wait for all ranks' flags and returns the local copy (valid until the second-next publish); mgb_dist_assemble_s
+ * = publish + wait + mgb_dist_assemble on the gathered vector.  This is the halo exchange of apply_D (R*s reads
+ * entries of s that other ranks own), done once per assembly inside the library. */
+int mgb_dist_s_publish(mgb_plan* plan, const double* s_own_dev);
+int mgb_dist_s_wait(mgb_plan* plan, const double** s_full_dev);
+int mgb_dist_assemble_s(mgb_plan* plan, const double* s_own_dev, const double* Dz0_dev, const double* c_dev, double t,
+                        int32_t flags, const double** hval_own_dev, const double** grad_own_dev,
+                        const double** scal_dev);
 /* the same in one call; the gather kernel itself waits for the peers' words (one process per GPU only) */
 int mgb_dist_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t,
                       int32_t flags, const double** hval_own_dev, const double** grad_own_dev,

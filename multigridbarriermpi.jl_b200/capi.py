@@ -27,7 +27,7 @@ EXPORTS = [
     "mgb_map_barrier", "mgb_all_isfinite", "mgb_reduce", "mgb_diag_scale", "mgb_time_assemble", "mgb_launch_count",
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_plan_create_rows", "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_rows", "mgb_dist_pattern", "mgb_dist_window",
-    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_copy_to_host", "mgb_host_register", "mgb_host_unregister",
+    "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_dist_s_publish", "mgb_dist_s_wait", "mgb_dist_assemble_s", "mgb_copy_to_host", "mgb_host_register", "mgb_host_unregister",
     "mgb_graph_begin", "mgb_graph_end", "mgb_graph_launch", "mgb_graph_destroy", "mgb_graph_stats",
 ]
 
@@ -142,6 +142,10 @@ def load(build_if_missing: bool = True):
                                  C.POINTER(C.c_void_p)]
     lib.mgb_dist_assemble.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
                                       C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+    lib.mgb_dist_s_publish.argtypes = [C.c_void_p, C.c_void_p]
+    lib.mgb_dist_s_wait.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.mgb_dist_assemble_s.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int32,
+                                        C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
     _lib = lib
     return lib
 
@@ -527,6 +531,23 @@ class DistPlan(Plan):
         """-> device pointers (hval_own, grad_own, scal), library-owned"""
         hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _check(load().mgb_dist_end(self._h, float(t), int(flags), C.byref(hp), C.byref(gp), C.byref(sp_)))
+        return int(hp.value), int(gp.value), int(sp_.value)
+
+    def s_publish(self, s_own_dev):
+        """this rank's block of a row-distributed Newton unknown -> every rank's copy of the whole vector"""
+        _check(load().mgb_dist_s_publish(self._h, _ptr(s_own_dev)))
+
+    def s_wait(self) -> int:
+        """enqueue the wait for every rank's block; device pointer of the gathered vector (m doubles, library-owned)"""
+        p = C.c_void_p()
+        _check(load().mgb_dist_s_wait(self._h, C.byref(p)))
+        return int(p.value)
+
+    def dist_assemble_s(self, s_own_dev, Dz0_dev, c_dev, t: float, flags: int):
+        """mgb_dist_assemble_s: all-gather of the distributed unknown inside the library, then the sharded assembly"""
+        hp, gp, sp_ = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(load().mgb_dist_assemble_s(self._h, _ptr(s_own_dev), _ptr(Dz0_dev), _ptr(c_dev), float(t), int(flags),
+                                          C.byref(hp), C.byref(gp), C.byref(sp_)))
         return int(hp.value), int(gp.value), int(sp_.value)
 
     def dist_assemble(self, s_dev, Dz0_dev, c_dev, t: float, flags: int):

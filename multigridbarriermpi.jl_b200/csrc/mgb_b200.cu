@@ -170,6 +170,11 @@ struct mgb_plan {
         unsigned epoch = 0;
         bool finish_pending = false;
         double timeout_s = 30.0;
+        // all-gather of a row-distributed Newton unknown (mgb_dist_s_publish / _wait / mgb_dist_assemble_s): the window
+        // is [scalar words | 16 flags | whole vector, parity 0 | whole vector, parity 1]
+        size_t off_flags = 0, off_full = 0;
+        unsigned long long s_epoch = 0;
+        DevBuf<unsigned int> counter;
         ~Dist() {
             for (int p = 0; p < mgb::DIST_LL_RANKS; ++p)
                 if (peer_ipc[p] && peer[p]) cudaIpcCloseMemHandle(peer[p]);
@@ -1258,7 +1263,11 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
             dd->hval.alloc((size_t)std::max<int64_t>(pl->nnzH, 1)); dd->grad.alloc((size_t)std::max<int64_t>(pl->m_out, 1));
             dd->scal.alloc(4); dd->err.alloc(1);
             CUDA_OK(cudaMemsetAsync(dd->err.p, 0, sizeof(int), st));
-            dd->window_bytes = (size_t)2 * mgb::DIST_LL_RANKS * 8 * sizeof(unsigned long long);
+            dd->off_flags = (size_t)2 * mgb::DIST_LL_RANKS * 8 * sizeof(unsigned long long);
+            dd->off_full = dd->off_flags + 128;
+            dd->window_bytes = dd->off_full + (size_t)2 * std::max<int64_t>(pl->m, 1) * sizeof(double);
+            dd->counter.alloc(1);
+            CUDA_OK(cudaMemsetAsync(dd->counter.p, 0, sizeof(unsigned int), st));
             CUDA_OK(cudaMalloc(&dd->window, dd->window_bytes));
             CUDA_OK(cudaMemsetAsync(dd->window, 0, dd->window_bytes, st));   // epoch tag 0 never matches a live epoch
             CUDA_OK(cudaStreamSynchronize(st));
@@ -1378,6 +1387,63 @@ void dist_launch(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const
     assemble_element(pl, s_dev, Dz0_dev, c_dev, t, flags & 7, dd.scal.p, dd.grad.p, dd.hval.p, nullptr, nullptr, &S);
 }
 }  // namespace
+
+namespace {
+mgb::DistGather make_dist_gather(mgb_plan* pl, const double* s_own_dev) {
+    auto& dd = *pl->dist;
+    mgb::DistGather G{};
+    G.rank = dd.rank; G.nranks = dd.nranks; G.epoch = dd.s_epoch;
+    const size_t par = (size_t)(dd.s_epoch & 1ull);
+    for (int p = 0; p < dd.nranks; ++p) {
+        char* base = static_cast<char*>(dd.peer[p]);
+        G.full[p] = reinterpret_cast<double*>(base + dd.off_full) + par * (size_t)pl->m;
+        G.flag[p] = reinterpret_cast<unsigned long long*>(base + dd.off_flags);
+    }
+    G.own = s_own_dev; G.off = pl->out0; G.count = pl->m_out;
+    G.counter = dd.counter.p; G.timeout_ns = (unsigned long long)(dd.timeout_s * 1e9); G.err = dd.err.p;
+    return G;
+}
+}  // namespace
+
+int mgb_dist_s_publish(mgb_plan* pl, const double* s_own_dev) {
+    try {
+        if (!pl || !pl->dist || !pl->ctx || (!s_own_dev && pl->m_out > 0)) return fail("mgb_dist_s_publish: NULL argument / not a distributed device plan");
+        auto& dd = *pl->dist;
+        if (!dd.attached) return fail("mgb_dist_s_publish: peers not attached (mgb_dist_attach)");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        dd.s_epoch++;
+        const mgb::DistGather G = make_dist_gather(pl, s_own_dev);
+        mgb::dist_s_scatter_kernel<<<(unsigned)std::max<int64_t>((pl->m_out + 255) / 256, 1), 256, 0, pl->ctx->stream>>>(G);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_s_publish: ") + ex.what()); }
+}
+
+int mgb_dist_s_wait(mgb_plan* pl, const double** s_full_dev) {
+    try {
+        if (!pl || !pl->dist || !pl->ctx) return fail("mgb_dist_s_wait: not a distributed device plan");
+        auto& dd = *pl->dist;
+        if (dd.s_epoch == 0) return fail("mgb_dist_s_wait: no mgb_dist_s_publish issued");
+        CUDA_OK(cudaSetDevice(pl->ctx->device));
+        const mgb::DistGather G = make_dist_gather(pl, nullptr);
+        mgb::dist_s_wait_kernel<<<1, 32, 0, pl->ctx->stream>>>(G);
+        g_launches++;
+        CUDA_OK(cudaGetLastError());
+        if (s_full_dev) *s_full_dev = G.full[dd.rank];
+        return 0;
+    } catch (const std::exception& ex) { return fail(std::string("mgb_dist_s_wait: ") + ex.what()); }
+}
+
+int mgb_dist_assemble_s(mgb_plan* pl, const double* s_own_dev, const double* Dz0_dev, const double* c_dev, double t,
+                        int32_t flags, const double** hval_own_dev, const double** grad_own_dev, const double** scal_dev) {
+    const double* s_full = nullptr;
+    int rc = mgb_dist_s_publish(pl, s_own_dev);
+    if (rc) return rc;
+    rc = mgb_dist_s_wait(pl, &s_full);
+    if (rc) return rc;
+    return mgb_dist_assemble(pl, s_full, Dz0_dev, c_dev, t, flags, hval_own_dev, grad_own_dev, scal_dev);
+}
 
 int mgb_dist_begin(mgb_plan* pl, const double* s_dev, const double* Dz0_dev, const double* c_dev, double t, int32_t flags) {
     try {

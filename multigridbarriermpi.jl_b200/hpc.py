@@ -109,30 +109,71 @@ class HPCMatrix:
         return (self.n, self.k)
 
 
+GATHER_STATS = dict(calls=0, seconds=0.0, bytes=0)   # collective gathers of row blocks (setup cost of a solve)
+
+
 class HPCSparseMatrix:
-    """Row-partitioned sparse matrix.  The replicated host CSR is kept (every rank builds the same
-    native geometry, src/MultiGridBarrierMPI.jl:239-240); ``local`` is this rank's row block."""
+    """Row-partitioned sparse matrix: every rank STORES ONLY ITS OWN ROW BLOCK (global column ids), like the reference
+    (src/MultiGridBarrierMPI.jl:216-221).  ``gather()`` / ``.host`` reassemble the whole matrix on every rank with one
+    collective (the `SparseMatrixCSC(A)` gather the reference uses in mpi_to_native, src:357-371) - the symbolic phase
+    of a level needs R whole, once; the assembly itself never gathers."""
 
     def __init__(self, A: sp.spmatrix, backend: Backend, row_partition: Optional[np.ndarray] = None,
-                 Ti=np.int32):
+                 Ti=np.int32, local_block: bool = False, shape=None):
+        """``A``: the whole matrix (every rank builds the same native geometry, src:239-240; the rows of other ranks
+        are dropped here) or, with ``local_block=True``, this rank's rows only (then ``shape`` = global shape)."""
         self.backend = backend
         A = sp.csr_matrix(A)
         A.sort_indices()
-        if A.nnz >= np.iinfo(Ti).max:
-            raise OverflowError("index type too small for this matrix; pass Ti=np.int64 (src/MultiGridBarrierMPI.jl:233-234)")
         self.Ti = Ti
-        self.host = A
-        self.row_partition = uniform_partition(A.shape[0], backend.nranks) if row_partition is None else np.asarray(row_partition)
-        self.col_partition = uniform_partition(A.shape[1], backend.nranks)
+        if local_block:
+            assert shape is not None and row_partition is not None
+            self._shape = tuple(shape)
+            self.row_partition = np.asarray(row_partition)
+            self._local = A
+        else:
+            if A.nnz >= np.iinfo(Ti).max:
+                raise OverflowError("index type too small for this matrix; pass Ti=np.int64 (src/MultiGridBarrierMPI.jl:233-234)")
+            self._shape = A.shape
+            self.row_partition = uniform_partition(A.shape[0], backend.nranks) if row_partition is None else np.asarray(row_partition)
+            lo, hi = self.row_partition[backend.rank] - 1, self.row_partition[backend.rank + 1] - 1
+            self._local = A[lo:hi].copy()
+        self.col_partition = uniform_partition(self._shape[1], backend.nranks)
+        self._whole = self._local if backend.nranks == 1 else None
 
     @property
     def shape(self):
-        return self.host.shape
+        return self._shape
 
     @property
     def local(self) -> sp.csr_matrix:
-        lo, hi = self.row_partition[self.backend.rank] - 1, self.row_partition[self.backend.rank + 1] - 1
-        return self.host[lo:hi]
+        return self._local
+
+    def gather(self) -> sp.csr_matrix:
+        """the whole matrix on every rank: collective over the ranks of the running torch.distributed job"""
+        if self._whole is None:
+            import time
+            import torch.distributed as dist
+            be = self.backend
+            if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() == be.nranks):
+                raise RuntimeError("HPCSparseMatrix.gather: this rank holds rows "
+                                   f"[{self.row_partition[be.rank]}, {self.row_partition[be.rank + 1]}) only and no "
+                                   f"{be.nranks}-rank torch.distributed job is running to gather the others")
+            t0 = time.perf_counter()
+            blocks = [None] * be.nranks
+            loc = self._local
+            dist.all_gather_object(blocks, (loc.indptr, loc.indices, loc.data))
+            whole = sp.vstack([sp.csr_matrix((d, i, p), shape=(len(p) - 1, self._shape[1])) for p, i, d in blocks], format="csr")
+            assert whole.shape == self._shape
+            self._whole = whole
+            GATHER_STATS["calls"] += 1
+            GATHER_STATS["seconds"] += time.perf_counter() - t0
+            GATHER_STATS["bytes"] += int(sum(len(d) * 12 + len(p) * 4 for p, i, d in blocks))
+        return self._whole
+
+    @property
+    def host(self) -> sp.csr_matrix:
+        return self.gather()
 
     @property
     def rowptr(self):
@@ -141,7 +182,8 @@ class HPCSparseMatrix:
 
     @property
     def nnz(self):
-        return self.host.nnz
+        """stored entries of this rank's block"""
+        return self._local.nnz
 
     # ---- the sparse algebra the reference's f2 loop is written in (HPCSparseArrays methods `*`, `'`, `+`:
     # test/test_map_rows_compare.jl:102-123).  Host-side structural operations with Julia's conventions; the

@@ -29,6 +29,19 @@ for gen, L in (("fem2d", 4), ("fem1d", 6)):
     colidx = np.concatenate([b[2] for b in sorted(blocks, key=lambda b: b[0])])
     assert np.array_equal(rowptr, grp) and np.array_equal(colidx, gci)
     assert np.array_equal(np.sort(np.concatenate([b[3] for b in blocks])), np.arange(n))
+# HPC-typed geometry: every rank keeps only its row block of each operator; the whole matrix comes back with one
+# collective gather (what the symbolic phase of a level needs of R, once - reference src/MultiGridBarrierMPI.jl:357-371)
+from mgb_b200 import hpc  # noqa: E402
+geom = mgb_b200.fem2d(3)
+be = hpc.Backend(device="cpu", rank=rank, nranks=world)
+for name in sorted(geom.operators):
+    A = geom.operators[name].tocsr()
+    H = hpc.HPCSparseMatrix(A, be)
+    lo, hi = H.row_partition[rank] - 1, H.row_partition[rank + 1] - 1
+    assert H.local.shape[0] == hi - lo and H.nnz == A[lo:hi].nnz and H.nnz < A.nnz
+    W = H.gather()
+    assert (abs(W - A)).nnz == 0 and W.shape == A.shape
+assert hpc.GATHER_STATS["calls"] == len(geom.operators) and hpc.GATHER_STATS["bytes"] > 0
 dist.barrier()
 if rank == 0:
     print("GLOO_OK")

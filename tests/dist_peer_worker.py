@@ -38,7 +38,11 @@ for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
         if step:
             pr["s"] = pr["s"] + 1e-4 * rng.uniform(-1, 1, size=pr["s"].shape)   # same seed on every rank
         s_d = torch.from_numpy(pr["s"]).to(dev)
-        hp, gp, sp_ = plan.dist_assemble(s_d, Dz0_d, c_d, t, 7)
+        if step % 2 == 1:   # row-distributed unknown: all-gather over NVLink peer memory inside the library
+            s_own = s_d[d["own0"]: d["own1"]].clone()
+            hp, gp, sp_ = plan.dist_assemble_s(s_own, Dz0_d, c_d, t, 7)
+        else:
+            hp, gp, sp_ = plan.dist_assemble(s_d, Dz0_d, c_d, t, 7)
         h_own, g_own, scal = ctx.to_host(hp, d["n_own_h"]), ctx.to_host(gp, d["n_own_g"]), ctx.to_host(sp_, 4)
         argsg = (pr["s"], pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
         Hg, gg, f0g = O.f2(*argsg).tocsr(), O.f1(*argsg), O.f0(*argsg)

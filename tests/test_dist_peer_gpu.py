@@ -48,8 +48,18 @@ def _virtual_ranks(ctx, gen, L, nranks, p=1.0, slack=False, steps=3):
         if step:
             pr["s"] = pr["s"] + 1e-4 * rng.uniform(-1, 1, size=pr["s"].shape)
         s_d = torch.from_numpy(pr["s"]).to(dev)
+        if step % 2 == 1:
+            # row-distributed unknown (the reference's HPCVector): every rank publishes its block, the library
+            # all-gathers it into each rank's window; the assembly then reads the gathered copy
+            for pl in plans:
+                pl.s_publish(s_d[pl.dinfo["own0"]: pl.dinfo["own1"]].clone())
+            s_in = [pl.s_wait() for pl in plans]
+            for pl, ptr in zip(plans, s_in):
+                assert np.array_equal(ctx.to_host(ptr, m), pr["s"])
+        else:
+            s_in = [s_d] * nranks
         for r, pl in enumerate(plans):
-            pl.begin(s_d, ins[r][0], ins[r][1], t, flags)
+            pl.begin(s_in[r], ins[r][0], ins[r][1], t, flags)
         ptrs = [pl.end(t, flags) for pl in plans]
         f0_o, g_o, H_o = oracle_eval(pr, t)
         scals = []
