@@ -302,6 +302,28 @@ bool patch_requested(int force_flags, const mgb::ElementPlan& ep) { return want_
 
 bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
+// Every index the numeric kernels will dereference comes from these frozen lists: check all of them once, on the
+// host, at plan creation (compute-sanitizer is not available on the target pool, so the bounds are enforced here).
+void validate_element_plan(const mgb::ElementPlan& ep) {
+    const int64_t nsel = ep.E * (int64_t)ep.lay.NS, nrel = ep.E * (int64_t)ep.NU * ep.LPE;
+    auto bad = [](const char* what) { throw std::runtime_error(std::string("internal: element plan validation failed: ") + what); };
+    for (int32_t a : ep.lcols) if (a < -1 || a >= ep.m) bad("dof id outside -1..m-1");
+    for (int32_t sl : ep.h_cidx) if (sl < 0 || sl >= nsel) bad("Hessian contribution slot outside the record buffer");
+    for (int32_t sl : ep.g_cidx) if (sl < 0 || sl >= nrel) bad("gradient contribution slot outside the record buffer");
+    if ((int64_t)ep.h_rowptr.size() != ep.m_out + 1 || (int64_t)ep.g_cptr.size() != ep.m_out + 1) bad("row pointer length");
+    if (!ep.h_cptr.empty() && (ep.h_cptr.front() != 0 || ep.h_cptr.back() != (int64_t)ep.h_cidx.size())) bad("contribution pointers");
+    for (size_t t = 1; t < ep.h_cptr.size(); ++t) if (ep.h_cptr[t] < ep.h_cptr[t - 1]) bad("contribution pointers not monotone");
+    for (int64_t a = 0; a < ep.m_out; ++a) {
+        if (ep.h_rowptr[a + 1] < ep.h_rowptr[a]) bad("row pointers not monotone");
+        for (int32_t q = ep.h_rowptr[a]; q < ep.h_rowptr[a + 1]; ++q) {
+            if (ep.h_colidx[q] < 0 || ep.h_colidx[q] >= ep.m) bad("column id outside 0..m-1");
+            if (q > ep.h_rowptr[a] && ep.h_colidx[q] <= ep.h_colidx[q - 1]) bad("columns not strictly increasing in a row");
+        }
+    }
+    if (ep.g_cptr.back() != (int64_t)ep.g_cidx.size()) bad("gradient pointers");
+    for (double v : ep.prec) if (!(v == v)) bad("NaN in an operator record");
+}
+
 void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     const auto& ep = pl->ep;
     mgb::launch_element(ep.B, ep.dim, ep.mode, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
@@ -477,6 +499,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->nnzH = (int64_t)ep.h_colidx.size();
             pl->h_rowptr = ep.h_rowptr; pl->h_colidx = ep.h_colidx;
             pl->n_hcontrib = (int64_t)ep.h_cidx.size(); pl->n_gcontrib = (int64_t)ep.g_cidx.size();
+            validate_element_plan(ep);
             {
                 const double avg = pl->nnzH ? (double)ep.h_cidx.size() / (double)pl->nnzH : 0.0;
                 // lists averaging more than six contributions go to the lanes-per-output gather (fem1d L=16 level 12,

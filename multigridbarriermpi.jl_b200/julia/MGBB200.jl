@@ -44,19 +44,31 @@ function Ctx(dev::Integer = CUDA.deviceid())
     c = Ctx(r[]); finalizer(c -> ccall((:mgb_ctx_destroy, LIB), Cint, (Ptr{Cvoid},), c.h), c); c
 end
 
-# The local block of an HPCSparseMatrix is CSR with 1-based Int32 indices
-# (fields rowptr / colval / nzval, src/MultiGridBarrierMPI.jl:216-221, :364): passed zero-copy.
-csr(A::HPCSparseMatrix) = MgbCsr(size(A, 1), size(A, 2), length(A.nzval),
-                                 pointer(A.rowptr), pointer(A.rowval), pointer(A.nzval), Int32(1))
+# An HPCSparseMatrix holds ONLY this rank's rows, with COMPRESSED column ids (rowval indexes col_indices,
+# src/MultiGridBarrierMPI.jl:216-221) - its arrays are not a global CSR.  Two ways into the library:
+#   * hpc_block(A, rank) below: the rank's block exactly as stored, zero-copy (mgb_plan_create_local), for the operators D;
+#   * GatheredCsr(A): the WHOLE matrix on every rank, through the collective gather the reference itself uses in
+#     mpi_to_native (`SparseMatrixCSC(A)`, src:357-371), converted to CSR (= CSC of the transpose).  The symbolic phase
+#     needs R whole, once per level (a few MB: nnz(R) = 4.6e5 at fem2d L=8); no numeric call gathers anything.
+struct GatheredCsr
+    nrows::Int; ncols::Int
+    rowptr::Vector{Int32}; colidx::Vector{Int32}; vals::Vector{Float64}
+end
+function GatheredCsr(A::HPCSparseMatrix)
+    At = SparseMatrixCSC(transpose(SparseMatrixCSC(A)))      # collective; CSC of A' = CSR of A
+    GatheredCsr(size(A, 1), size(A, 2), Int32.(At.colptr), Int32.(At.rowval), Vector{Float64}(At.nzval))
+end
+csr(G::GatheredCsr) = MgbCsr(G.nrows, G.ncols, length(G.vals), pointer(G.rowptr), pointer(G.colidx), pointer(G.vals), Int32(1))
 
 mutable struct Plan; h::Ptr{Cvoid}; m::Int; nnzH::Int; rowptr::Vector{Int32}; colidx::Vector{Int32}; end
 
 function Plan(ctx::Ctx, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::Matrix{Float64}, w::Vector{Float64};
               idx::Vector{Int}, p::Float64, slack::Bool = false, rows = (0, size(D[1], 1)))
-    Ds = [csr(d) for d in D]; Rs = Ref(csr(R))
+    Dg = [GatheredCsr(d) for d in D]; Rg = GatheredCsr(R)     # collective gathers (setup, once per level)
+    Ds = [csr(d) for d in Dg]; Rs = Ref(csr(Rg))
     bar = Ref(MgbBarrier(idx, p, slack))
     r = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve D R x w begin
+    GC.@preserve Dg Rg x w begin
         check(ccall((:mgb_plan_create, LIB), Cint,
                     (Ptr{Cvoid}, Int64, Int32, Ptr{MgbCsr}, Ref{MgbCsr}, Int32, Ptr{Float64}, Ptr{Float64},
                      Ref{MgbBarrier}, Int64, Int64, Int32, Ref{Ptr{Cvoid}}),
@@ -94,15 +106,16 @@ hpc_block(A::HPCSparseMatrix, rank::Integer) =
     MgbHpcBlock(A.nrows_local, A.ncols_compressed, size(A, 2), A.row_partition[rank + 1] - 1,
                 pointer(A.colptr), pointer(A.rowval), pointer(A.nzval), pointer(A.col_indices), Int32(1))
 
-# Plan from the local blocks: no rank ever needs the global operators (only R is replicated, src:239-240).
+# Plan from the local blocks: no rank ever needs the global operators D (only R is gathered, once).
 function LocalPlan(ctx::Ctx, comm, D::Vector{<:HPCSparseMatrix}, R::HPCSparseMatrix, x::HPCMatrix, w::HPCVector;
                    idx::Vector{Int}, p::Float64, slack::Bool = false)
     rank = MPI.Comm_rank(comm)
-    Ds = [hpc_block(d, rank) for d in D]; Rs = Ref(csr(R))
+    Rg = GatheredCsr(R)
+    Ds = [hpc_block(d, rank) for d in D]; Rs = Ref(csr(Rg))
     bar = Ref(MgbBarrier(idx, p, slack))
     r = Ref{Ptr{Cvoid}}(C_NULL)
     xl = Array(x.A); wl = Array(w.v)          # local rows (HPCMatrix.A / HPCVector.v, src:176)
-    GC.@preserve D R xl wl begin
+    GC.@preserve D Rg xl wl begin
         check(ccall((:mgb_plan_create_local, LIB), Cint,
                     (Ptr{Cvoid}, Int64, Int32, Ptr{MgbHpcBlock}, Ref{MgbCsr}, Int32, Ptr{Float64}, Ptr{Float64},
                      Ref{MgbBarrier}, Int32, Ref{Ptr{Cvoid}}),
@@ -187,24 +200,31 @@ function b200_barrier(; idx::Vector{Int}, p::Float64, ctx::Ctx = Ctx())
     Barrier(f0 = f0, f1 = f1, f2 = f2)
 end
 
-# ---- multi-GPU: one MPI rank per GPU (test/test_2d.jl:17-20), fused peer-memory exchange (mgb_dist_*) ----
+# ---- multi-GPU: one MPI rank per GPU (test/test_2d.jl:17-20), owner-computes sharding (mgb_dist_*) ----
 struct MgbIpcHandle; bytes::NTuple{64,UInt8}; end
 
-mutable struct DistPlan; h::Ptr{Cvoid}; rank::Int; nranks::Int; info::Vector{Int64}; rowptr::Vector{Int32}; colidx::Vector{Int32}; end
+mutable struct DistPlan
+    h::Ptr{Cvoid}; rank::Int; nranks::Int; info::Vector{Int64}
+    rowptr::Vector{Int32}; colidx::Vector{Int32}     # owned rows of the pattern of R'HR (relative rowptr, global columns)
+    rows::Vector{Int64}                              # global ids (0-based) of the quadrature rows this rank evaluates
+end
 
 """
     DistPlan(ctx, comm, D, R, x, w; idx, p, row_part, out_part)
 
-Collective over `comm` (MPI.Comm): every rank passes the SAME replicated operators (exactly what the reference
-holds: fem2d builds the full native mesh on every rank, src:239-240) and the 0-based partition offsets of the
-quadrature rows (whole elements) and of the unknowns (HPCSparseArrays row partition).  The 64-byte CUDA IPC
-handles of the exchange windows travel through one MPI.Allgather; afterwards no MPI/NCCL call is made per step.
+Collective over `comm` (MPI.Comm).  The symbolic phase needs the operators whole, once per level: they are gathered
+here (`GatheredCsr`; in the reference every rank builds the full native mesh anyway, src:239-240) together with the
+0-based partition offsets of the quadrature rows (whole elements) and of the unknowns (HPCSparseArrays row partition).
+The plan evaluates `pl.rows` - every element touching this rank's output rows - and completes its rows of R'HR and its
+block of the gradient locally.  The 64-byte CUDA IPC handles of the scalar windows travel through one MPI.Allgather;
+afterwards no MPI/NCCL call is made per step.
 """
 function DistPlan(ctx::Ctx, comm, D, R, x::Matrix{Float64}, w::Vector{Float64}; idx::Vector{Int}, p::Float64,
                   row_part::Vector{Int64}, out_part::Vector{Int64}, slack::Bool = false)
     rank, nranks = MPI.Comm_rank(comm), MPI.Comm_size(comm)
-    Ds = [csr(d) for d in D]; Rs = Ref(csr(R)); bar = Ref(MgbBarrier(idx, p, slack)); r = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve D R x w row_part out_part begin
+    Dg = [GatheredCsr(d) for d in D]; Rg = GatheredCsr(R)
+    Ds = [csr(d) for d in Dg]; Rs = Ref(csr(Rg)); bar = Ref(MgbBarrier(idx, p, slack)); r = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve Dg Rg x w row_part out_part begin
         check(ccall((:mgb_dist_plan_create, LIB), Cint,
                     (Ptr{Cvoid}, Int64, Int32, Ptr{MgbCsr}, Ref{MgbCsr}, Int32, Ptr{Float64}, Ptr{Float64}, Ref{MgbBarrier},
                      Int32, Int32, Ptr{Int64}, Ptr{Int64}, Ref{Ptr{Cvoid}}),
@@ -217,12 +237,28 @@ function DistPlan(ctx::Ctx, comm, D, R, x::Matrix{Float64}, w::Vector{Float64}; 
     MPI.Barrier(comm)                                       # every window mapped before the first store
     info = zeros(Int64, 16)
     check(ccall((:mgb_dist_info, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}, Int32), r[], info, 16))
-    rp = zeros(Int32, info[6] - info[5] + 1); ci = zeros(Int32, info[3])
+    rp = zeros(Int32, info[6] - info[5] + 1); ci = zeros(Int32, info[3]); rows = zeros(Int64, info[7])
     check(ccall((:mgb_dist_pattern, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}), r[], rp, ci))
-    DistPlan(r[], rank, nranks, info, rp, ci)               # destroy collectively: MPI.Barrier, then mgb_plan_destroy
+    check(ccall((:mgb_dist_rows, LIB), Cint, (Ptr{Cvoid}, Ptr{Int64}), r[], rows))
+    DistPlan(r[], rank, nranks, info, rp, ci, rows)         # destroy collectively: MPI.Barrier, then mgb_plan_destroy
 end
 
-"collective, same order on every rank; returns device pointers (owned H values, owned gradient block, 4 scalars)"
+"""collective, same order on every rank.  `s_own`: this rank's block of the Newton unknown (the local storage of the
+HPCVector, `MultiGridBarrier._raw_array(s)`, src:175-176) - the library all-gathers it over NVLink peer memory;
+`Dz0`, `c`: rows `pl.rows .+ 1` of the n x nD blocks.  Returns device arrays (owned H values in `pl.colidx` order, owned
+gradient block, the 4 global scalars)."""
+function dist_assemble_s!(pl::DistPlan, s_own::CuVector{Float64}, Dz0::CuMatrix{Float64}, c::CuMatrix{Float64}, t::Float64, flags)
+    hp, gp, sp = Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}()
+    GC.@preserve s_own Dz0 c begin
+        check(ccall((:mgb_dist_assemble_s, LIB), Cint,
+                    (Ptr{Cvoid}, CuPtr{Float64}, CuPtr{Float64}, CuPtr{Float64}, Float64, Int32,
+                     Ref{CuPtr{Float64}}, Ref{CuPtr{Float64}}, Ref{CuPtr{Float64}}),
+                    pl.h, pointer(s_own), pointer(Dz0), pointer(c), t, flags, hp, gp, sp))
+    end
+    (unsafe_wrap(CuArray, hp[], pl.info[3]), unsafe_wrap(CuArray, gp[], pl.info[4]), unsafe_wrap(CuArray, sp[], 4))
+end
+
+"the same with a replicated unknown `s` (length m) already on every rank"
 function dist_assemble!(pl::DistPlan, s::CuVector{Float64}, Dz0::CuMatrix{Float64}, c::CuMatrix{Float64}, t::Float64, flags)
     hp, gp, sp = Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}(), Ref{CuPtr{Float64}}()
     GC.@preserve s Dz0 c begin

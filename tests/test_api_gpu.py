@@ -154,3 +154,25 @@ def test_spmat_products_both_orientations(gpu_ctx):
             ref2 = 2.0 * y0 - 0.5 * ref
             assert np.abs(y0_d.cpu().numpy() - ref2).max() <= 1e-13 * ((abs(op) @ np.abs(x)).max() + np.abs(y0).max())
         M.close()
+
+
+def test_diag_scale_numeric(gpu_ctx):
+    """mgb_diag_scale = the diagonal amgb_diag wraps (reference src:137-147, test/test_diag.jl:28-46: spdiagm of 1:10):
+    out = w .* y[:, col] on the device"""
+    import torch
+    dev = torch.device("cuda", gpu_ctx.device)
+    n, k = 1000, 5
+    rng = np.random.default_rng(1)
+    w, y = rng.normal(size=n), rng.normal(size=(n, k))
+    w_d = torch.from_numpy(w).to(dev)
+    y_d = torch.from_numpy(np.ascontiguousarray(y.T)).to(dev)      # column-major n x k
+    out = torch.zeros(n, dtype=torch.float64, device=dev)
+    for col in (0, 3, 4):
+        gpu_ctx.diag_scale(w_d, y_d, n, n, col, out)
+        assert np.array_equal(out.cpu().numpy(), w * y[:, col])
+    # the reference's literal: amgb_diag(1:10) has the diagonal 1..10
+    one = torch.ones(10, dtype=torch.float64, device=dev)
+    z = torch.arange(1, 11, dtype=torch.float64, device=dev)
+    o10 = torch.zeros(10, dtype=torch.float64, device=dev)
+    gpu_ctx.diag_scale(one, z, 10, 10, 0, o10)
+    assert o10.cpu().tolist() == [float(v) for v in range(1, 11)]

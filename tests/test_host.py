@@ -219,3 +219,11 @@ def test_hpc_sparse_algebra_conventions():
     assert abs(ret.host - Ho).max() < 1e-13
     Hd = ret.host.copy(); Hd.eliminate_zeros(); Hoz = Ho.copy(); Hoz.eliminate_zeros()
     assert Hd.nnz == Hoz.nnz
+
+
+def test_amgb_rejects_unknown_keywords_instead_of_dropping_them():
+    """a custom convex set `Q` (or any key the GPU path does not implement) must not be ignored silently; the geometry
+    constructor's keys that femNd_mpi_solve forwards to both calls (reference src:594-600) are accepted"""
+    from mgb_b200 import solver
+    with pytest.raises(TypeError, match="unsupported keyword"):
+        solver.amgb(mgb_b200.fem1d(2), Q=object())
