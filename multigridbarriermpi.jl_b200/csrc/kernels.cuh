@@ -25,6 +25,8 @@ namespace mgb {
 struct ElemParams {
     // geometry / plan (device)
     int64_t E, nloc;
+    int agg;                 // coarse levels: `agg` (power of two <= elements per warp) consecutive elements share their dofs
+                             // (children of one coarse element): their records are summed in the warp and stored once
     int64_t Eprim;           // elements [0, Eprim) count in the objective / <c,Dz> / feasibility scalars (a sharded plan
                              // also evaluates halo elements whose scalars another rank owns); E unless sharded
     const int32_t* lcols;    // [E][NU][LPE] element -> dof (-1: eliminated)
@@ -82,6 +84,21 @@ __device__ __forceinline__ void group_reduce(double (&v)[NV], int lane) {
         }
         len = half;
     }
+}
+
+// Coarse levels: the `agg` consecutive elements of an aligned group (lane groups of one warp) share their dofs, so their
+// butterfly-reduced block entries are summed across the groups before the store: `agg` times fewer records to write and
+// `agg` times shorter contribution lists to replay.  Uniform loop bounds; every lane of the warp takes part.
+template <int K, int LPE>
+__device__ __forceinline__ void agg_reduce(double (&v)[K * LPE], const int agg) {
+    for (int mk = LPE; mk < LPE * agg; mk <<= 1) {
+#pragma unroll
+        for (int r = 0; r < K; ++r) v[r] += shfl_xor_d(v[r], mk);
+    }
+}
+__device__ __forceinline__ double agg_reduce1(double v, const int agg, const int LPE) {
+    for (int mk = LPE; mk < LPE * agg; mk <<= 1) v += shfl_xor_d(v, mk);
+    return v;
 }
 
 struct BarrierOut {
@@ -147,6 +164,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
 
     const bool act_e = e < P.E;
     const bool act = act_e && (l < B);
+    const int agg = FINE ? 1 : P.agg;                                   // see agg_reduce
+    const bool wr = act_e && (FINE || ((threadIdx.x & 31) / LPE) % agg == 0);   // this lane group stores the (summed) record
     const int64_t i = act ? e * B + l : 0;
     const int64_t n = P.nloc;
 
@@ -292,7 +311,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
             ru[q] = r;
         }
         group_reduce<LPE, LPE>(ru, l);
-        if (act_e) rel[l] = ru[0];
+        if (!FINE) ru[0] = agg_reduce1(ru[0], agg, LPE);
+        if (wr) rel[l] = ru[0];
         if (FINE) {
 #pragma unroll
             for (int v = 1; v < NU; ++v)
@@ -304,7 +324,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
 #pragma unroll
                 for (int q = 0; q < LPE; ++q) rs[q] = (q < B) ? aid[FINE ? 0 : v][FINE ? 0 : (q < B ? q : 0)] * gy[D + v] : 0.0;
                 group_reduce<LPE, LPE>(rs, l);
-                if (act_e) rel[v * LPE + l] = rs[0];
+                rs[0] = agg_reduce1(rs[0], agg, LPE);
+                if (wr) rel[v * LPE + l] = rs[0];
             }
         }
     }
@@ -348,7 +369,8 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
             }
         }
         group_reduce<NTRI, LPE>(v, l);
-        if (act_e) {
+        if (!FINE) agg_reduce<NTRI / LPE, LPE>(v, agg);
+        if (wr) {
 #pragma unroll
             for (int r = 0; r < NTRI / LPE; ++r) sel[P.off_uu + r * LPE + l] = v[r];
         }
@@ -392,8 +414,9 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                 for (int q2 = 0; q2 < B; ++q2)
                     v[q * B + q2] = ((TWO && v2 == 1) ? haus * aid[0][FINE ? 0 : q] : bs[q]) * aid[FINE ? 0 : v2][FINE ? 0 : q2];
             group_reduce<NFULL, LPE>(v, l);
+            agg_reduce<NFULL / LPE, LPE>(v, agg);
             const int off = (v2 == 1) ? P.off_us : P.off_ut;
-            if (act_e) {
+            if (wr) {
 #pragma unroll
                 for (int r = 0; r < NFULL / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
@@ -410,8 +433,9 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                 for (int q2 = q; q2 < B; ++q2)
                     v[q * B - q * (q - 1) / 2 + (q2 - q)] = hd * aid[FINE ? 0 : v1][FINE ? 0 : q] * aid[FINE ? 0 : v1][FINE ? 0 : q2];
             group_reduce<NTRI, LPE>(v, l);
+            agg_reduce<NTRI / LPE, LPE>(v, agg);
             const int off = (v1 == 1) ? P.off_ss : P.off_tt;
-            if (act_e) {
+            if (wr) {
 #pragma unroll
                 for (int r = 0; r < NTRI / LPE; ++r) sel[off + r * LPE + l] = v[r];
             }
@@ -427,8 +451,9 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
                     for (int q2 = 0; q2 < B; ++q2)
                         v[q * B + q2] = vss * aid[FINE ? 0 : 1][FINE ? 0 : q] * aid[FINE ? 0 : VT][FINE ? 0 : q2];
                 group_reduce<NFULL, LPE>(v, l);
+                agg_reduce<NFULL / LPE, LPE>(v, agg);
             }
-            if (act_e) {
+            if (wr) {
 #pragma unroll
                 for (int r = 0; r < NFULL / LPE; ++r) sel[P.off_st + r * LPE + l] = v[r];
             }
@@ -469,7 +494,8 @@ __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_
     const int64_t e = tid / LPE;
     const int l = (int)(tid % LPE);
     double v0, v1, v2;
-    element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + e * (int64_t)P.NS, P.rel + e * (NU * LPE), v0, v1, v2);
+    const int64_t er = FINE ? e : e / P.agg;   // record of the element's aggregation group
+    element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + er * (int64_t)P.NS, P.rel + er * (NU * LPE), v0, v1, v2);
     block_scalars(v0, v1, v2, P.part);
 }
 

@@ -305,7 +305,8 @@ bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 // Every index the numeric kernels will dereference comes from these frozen lists: check all of them once, on the
 // host, at plan creation (compute-sanitizer is not available on the target pool, so the bounds are enforced here).
 void validate_element_plan(const mgb::ElementPlan& ep) {
-    const int64_t nsel = ep.E * (int64_t)ep.lay.NS, nrel = ep.E * (int64_t)ep.NU * ep.LPE;
+    const int64_t nrec = (ep.E + ep.agg - 1) / ep.agg;
+    const int64_t nsel = nrec * (int64_t)ep.lay.NS, nrel = nrec * (int64_t)ep.NU * ep.LPE;
     auto bad = [](const char* what) { throw std::runtime_error(std::string("internal: element plan validation failed: ") + what); };
     for (int32_t a : ep.lcols) if (a < -1 || a >= ep.m) bad("dof id outside -1..m-1");
     for (int32_t sl : ep.h_cidx) if (sl < 0 || sl >= nsel) bad("Hessian contribution slot outside the record buffer");
@@ -355,7 +356,7 @@ void launch_dependent(void (*kernel)(Params), unsigned grid, unsigned block, cud
 mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz0, const double* c, double t, double* Dz) {
     const auto& ep = pl->ep;
     mgb::ElemParams P{};
-    P.E = ep.E; P.nloc = ep.nloc; P.Eprim = pl->n_primary / std::max(ep.B, 1);
+    P.E = ep.E; P.nloc = ep.nloc; P.agg = ep.agg; P.Eprim = pl->n_primary / std::max(ep.B, 1);
     P.lcols = pl->d_lcols.p; P.prec = pl->d_prec.p;
     P.s = s; P.Dz0 = Dz0; P.c = c; P.t = t; P.p = pl->bar.p; P.p2 = pl->bar.p2;
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
@@ -486,7 +487,8 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         const bool sharded = out0 != 0 || out1 != pl->m || pl->n_primary != pl->nloc;
         if (sharded && force_path == MGB_PATH_CSR) throw std::runtime_error("sharded plans need the element path");
         if (force_path != MGB_PATH_CSR) {
-            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess, out0, out1);
+            mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess, out0, out1,
+                                    /*allow_agg=*/!want_patch_early(force_flags) && getenv("MGB_NO_AGG") == nullptr);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && sharded) throw std::runtime_error(std::string("sharded plans need the element path: ") + (pl->ep.ok ? "element type not instantiated" : pl->ep.why));
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
@@ -557,8 +559,9 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 pl->rp_h.upload(pp.H, st); pl->rp_g.upload(pp.G, st);
                 CUDA_OK(cudaStreamSynchronize(st));
             }
-            if (pl->patch == 0) pl->d_sel.alloc((size_t)ep.E * ep.lay.NS);
-            pl->d_rel.alloc((size_t)std::max<int64_t>((int64_t)ep.E * ep.NU * ep.LPE, pl->m_out));
+            const int64_t nrec = (ep.E + ep.agg - 1) / ep.agg;   // one record per aggregation group
+            if (pl->patch == 0) pl->d_sel.alloc((size_t)nrec * ep.lay.NS);
+            pl->d_rel.alloc((size_t)std::max<int64_t>(nrec * ep.NU * ep.LPE, pl->m_out));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
             const int epb = pl->patch > 0 ? pl->patch : MGB_ELEM_THREADS / ep.LPE;

@@ -141,7 +141,7 @@ struct UF {
 }  // namespace
 
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian, int64_t out0, int64_t out1) {
+                        const BarrierDesc& bar, ElementPlan& P, bool want_hessian, int64_t out0, int64_t out1, bool allow_agg) {
     P.ok = false;
     const int ND = (int)D.size();
     const int64_t nloc = D[0].nrows, N = D[0].ncols, m = R.ncols;
@@ -257,6 +257,23 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         }
     }
     P.fine = fine;
+    // coarse levels: the children of one coarse element are consecutive elements with identical dofs; the largest
+    // power of two (up to the elements of one warp) for which every aligned group agrees is summed in the kernel
+    P.agg = 1;
+    if (!fine && allow_agg) {
+        const int epw = 32 / LPE;
+        for (int g = 2; g <= epw; g *= 2) {
+            bool same = true;
+            for (int64_t e = 0; e < E && same; ++e) {
+                const int64_t e0 = e / g * g;
+                if (e == e0) continue;
+                same = std::equal(P.lcols.begin() + (size_t)e * nu * LPE, P.lcols.begin() + (size_t)(e + 1) * nu * LPE,
+                                  P.lcols.begin() + (size_t)e0 * nu * LPE);
+            }
+            if (!same) break;
+            P.agg = g;
+        }
+    }
     P.lay.build((int)B, dim, slack, fine);
     const SlotLayout& lay = P.lay;
 
@@ -337,27 +354,29 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
             ts.resize(rowcnt[mo]);
             fillpos.assign(rowcnt.begin(), rowcnt.end() - 1);
         }
-        for (int64_t e = 0; e < E; ++e) {
-            std::fill(U.begin(), U.end(), 0);
-            std::fill(own.begin(), own.end(), -1);
-            for (int k = 0; k < ND; ++k) {
-                const HostCSR& A = Ek[k];
-                const int v = var[k];
-                for (int l = 0; l < (int)B; ++l) {
-                    const int64_t i = e * B + l;
-                    for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
-                        const int q = local_of(v, e, A.idx[p]);
-                        U[(size_t)l * NL + v * B + q] = 1;
-                        if (k == idop[v]) own[v * B + l] = q;
+        for (int64_t e = 0; e < E; e += P.agg) {   // one record per aggregation group (agg = 1: per element)
+            std::fill(pres.begin(), pres.end(), 0);
+            for (int64_t ee = e; ee < std::min<int64_t>(e + P.agg, E); ++ee) {
+                std::fill(U.begin(), U.end(), 0);
+                if (ee == e) std::fill(own.begin(), own.end(), -1);
+                for (int k = 0; k < ND; ++k) {
+                    const HostCSR& A = Ek[k];
+                    const int v = var[k];
+                    for (int l = 0; l < (int)B; ++l) {
+                        const int64_t i = ee * B + l;
+                        for (int64_t p = A.ptr[i]; p < A.ptr[i + 1]; ++p) {
+                            const int q = local_of(v, ee, A.idx[p]);
+                            U[(size_t)l * NL + v * B + q] = 1;
+                            if (k == idop[v] && ee == e) own[v * B + l] = q;
+                        }
                     }
                 }
+                for (int l = 0; l < (int)B; ++l)
+                    for (int a1 = 0; a1 < NL; ++a1)
+                        if (U[(size_t)l * NL + a1])
+                            for (int a2 = 0; a2 < NL; ++a2)
+                                if (U[(size_t)l * NL + a2]) pres[(size_t)a1 * NL + a2] = 1;
             }
-            std::fill(pres.begin(), pres.end(), 0);
-            for (int l = 0; l < (int)B; ++l)
-                for (int a1 = 0; a1 < NL; ++a1)
-                    if (U[(size_t)l * NL + a1])
-                        for (int a2 = 0; a2 < NL; ++a2)
-                            if (U[(size_t)l * NL + a2]) pres[(size_t)a1 * NL + a2] = 1;
             for (int a1 = 0; a1 < NL; ++a1) {
                 const int32_t ga = P.lcols[((size_t)e * nu + a1 / B) * LPE + a1 % B];
                 if (ga < out0 || ga >= out1) continue;   // eliminated dof (-1) or a row another rank owns
@@ -370,12 +389,12 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                     if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
                     const int64_t d = fillpos[ga - out0]++;
                     tb[d] = gb;
-                    ts[d] = (int32_t)(e * lay.NS + sl);
+                    ts[d] = (int32_t)((e / P.agg) * lay.NS + sl);
                 }
             }
         }
     }
-    if ((int64_t)E * lay.NS > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
+    if (((int64_t)E + P.agg - 1) / P.agg * lay.NS > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
     // sort each row by (column, source) and compress
     P.h_rowptr.assign(mo + 1, 0);
     P.h_colidx.clear();
@@ -405,7 +424,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     // gradient replay lists
     std::vector<int64_t> gcnt(mo + 1, 0);
     for (int v = 0; v < nu; ++v)
-        for (int64_t e = 0; e < E; ++e)
+        for (int64_t e = 0; e < E; e += P.agg)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
                 if (a >= out0 && a < out1) gcnt[a - out0 + 1]++;
@@ -414,11 +433,11 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
     P.g_cptr = gcnt;
     P.g_cidx.resize(gcnt[mo]);
     std::vector<int64_t> gpos(gcnt.begin(), gcnt.end() - 1);
-    for (int64_t e = 0; e < E; ++e)  // element-major so every list is ordered by element
+    for (int64_t e = 0; e < E; e += P.agg)  // element-major so every list is ordered by element
         for (int v = 0; v < nu; ++v)
             for (int q = 0; q < (int)B; ++q) {
                 const int32_t a = P.lcols[((size_t)e * nu + v) * LPE + q];
-                if (a >= out0 && a < out1) P.g_cidx[gpos[a - out0]++] = (int32_t)((e * nu + v) * LPE + q);
+                if (a >= out0 && a < out1) P.g_cidx[gpos[a - out0]++] = (int32_t)(((e / P.agg) * nu + v) * LPE + q);
             }
     P.ok = true;
 }

@@ -72,6 +72,8 @@ struct ElementPlan {
     bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
     int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
+    int agg = 1;                   // coarse levels: aligned groups of `agg` consecutive elements share all their dofs (children of
+                                   // one coarse element): one slot / gradient record per group (kernels.cuh agg_reduce)
     int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (whole range unless sharded)
     SlotLayout lay;
     std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1
@@ -103,7 +105,8 @@ struct BarrierDesc {
 // out0/out1: keep only the output rows (unknowns) in [out0, out1) (out1 < 0: all m) - a sharded plan whose local
 // quadrature rows contain every element touching those unknowns completes them without any exchange.
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
-                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true, int64_t out0 = 0, int64_t out1 = -1);
+                        const BarrierDesc& bar, ElementPlan& out, bool want_hessian = true, int64_t out0 = 0, int64_t out1 = -1,
+                        bool allow_agg = true);
 
 
 // ---- multi-GPU (one process per GPU): owner-computes sharding ---------------------------------------

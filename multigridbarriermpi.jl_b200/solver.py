@@ -173,7 +173,9 @@ class DeviceProblem:
 
     def level(self, J: int) -> LevelState:
         if J not in self.levels:
+            t0 = time.perf_counter()
             self.levels[J] = LevelState(self, J)
+            self.stats["plan_s"] = self.stats.get("plan_s", 0.0) + time.perf_counter() - t0   # symbolic phase: once per level
         return self.levels[J]
 
     def apply_D(self, z_dev: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -262,10 +264,13 @@ class AMGBSOL:
 
 @dataclass
 class ParabolicSOL:
-    """Mirror of upstream ParabolicSOL (reference src/MultiGridBarrierMPI.jl:512-516): geometry, ts, u."""
+    """Mirror of upstream ParabolicSOL (reference src/MultiGridBarrierMPI.jl:512-516): geometry, ts, u.
+    ``stats``: per time step wall / assembly / solve-seam seconds, Newton iterations and assembly counts, plus the
+    symbolic-phase seconds spent once for all steps (the "pattern reuse" of config C5)."""
     geometry: Geometry
     ts: np.ndarray
     u: List[np.ndarray]
+    stats: Optional[dict] = None
 
 
 def amgb_core(prob: DeviceProblem, z: torch.Tensor, c: torch.Tensor, tol, t0, kappa, maxit, max_newton_fine,
@@ -434,7 +439,8 @@ def parabolic_tables(dim: int):
 
 def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float = 1.0, p: float = 1.0, f1=None, g=None,
                     tol: float = math.sqrt(EPS), t: float = 0.1, kappa: float = 10.0, maxit: int = 50,
-                    verbose: bool = False, device: int = 0, solve_fn: Callable = solve, **_ignored) -> ParabolicSOL:
+                    verbose: bool = False, device: int = 0, solve_fn: Callable = solve, max_steps: Optional[int] = None,
+                    **_ignored) -> ParabolicSOL:
     dim = geom.dim
     f1 = (lambda x: 0.5) if f1 is None else f1
     g = (lambda tt, x: x[0]) if g is None else g
@@ -464,7 +470,11 @@ def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float =
     u = np.array([g(ts[0], geom.x[i]) for i in range(n)], dtype=float)
     feasible_start(u)
     snaps = [z.cpu().numpy().reshape(n, 3, order="F").copy()]
+    steps_stats = []
     for k in range(len(ts) - 1):
+        if max_steps is not None and k >= max_steps:
+            break
+        w0, before = time.perf_counter(), dict(prob.stats)
         uk = snaps[-1][:, 0]
         u0 = uk.copy()
         u0[bnd] = np.array([g(ts[k + 1], geom.x[i]) for i in bnd], dtype=float)
@@ -473,8 +483,11 @@ def parabolic_solve(geom: Geometry, h: float = 0.2, t0: float = 0.0, t1: float =
         c[:, 0] = h * f1v - uk
         c[:, dim + 1] = 0.5
         c[:, dim + 2] = h / p
-        amgb_core(prob, z, _cm(c, dev), tol, t, kappa, maxit, max_newton, verbose, solve_fn)
+        main = amgb_core(prob, z, _cm(c, dev), tol, t, kappa, maxit, max_newton, verbose, solve_fn)
         snaps.append(z.cpu().numpy().reshape(n, 3, order="F").copy())
+        steps_stats.append(dict(wall_s=time.perf_counter() - w0, newton_its=int(main["its"].sum()),
+                                **{k_: prob.stats.get(k_, 0) - before.get(k_, 0) for k_ in ("assemble_s", "solve_s", "plan_s", "assemblies", "f0_evals")}))
+    stats = dict(steps=steps_stats, plan_s_total=prob.stats.get("plan_s", 0.0), nranks=nranks)
     if nranks > 1:
         prob.close()
-    return ParabolicSOL(geom, ts, snaps)
+    return ParabolicSOL(geom, ts[: len(snaps)], snaps, stats)
