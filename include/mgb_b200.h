@@ -68,8 +68,8 @@ typedef struct {
 #define MGB_PATH_CSR 2     /* general CSR kernels                                              */
 /* OR-ed into force_path: build no Hessian pattern / replay lists (operator-only plan, e.g. Dz0 = D z) */
 #define MGB_PLAN_NO_HESSIAN 16
-/* OR-ed into force_path: keep the two-stage element path (element_kernel + gather_kernel) instead of
- * the patch-fused kernel (A/B comparisons) */
+/* OR-ed into force_path: accepted for compatibility (the two-stage element path - element_kernel +
+ * gather_kernel - is the only element path) */
 #define MGB_PLAN_TWO_STAGE 32
 
 const char* mgb_last_error(void);

@@ -38,34 +38,4 @@ void launch_elem_bd(const ElemParams& P, int mode, bool fine, int flags, int64_t
     }
 }
 
-template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
-void launch_patch_one(const ElemParams& P, const PatchParams& Q, int64_t nblk, size_t smem, cudaStream_t st) {
-    auto kern = patch_kernel<B, D, SLACK, FINE, FLAGS, PATCH>;
-    if (smem > 40 * 1024) inst_check(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "cudaFuncSetAttribute");
-    kern<<<dim3((unsigned)nblk), dim3(PATCH * Pow2Ceil<B>::value), smem, st>>>(P, Q);
-}
-
-template <int B, int D, bool SLACK, bool FINE, int PATCH>
-void launch_patch_flags(const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk, size_t smem, cudaStream_t st) {
-    switch (canonical_flags(flags)) {
-        case 1: launch_patch_one<B, D, SLACK, FINE, 1, PATCH>(P, Q, nblk, smem, st); break;
-        case 7: launch_patch_one<B, D, SLACK, FINE, 7, PATCH>(P, Q, nblk, smem, st); break;
-        case 8: launch_patch_one<B, D, SLACK, FINE, 8, PATCH>(P, Q, nblk, smem, st); break;
-        case 15: launch_patch_one<B, D, SLACK, FINE, 15, PATCH>(P, Q, nblk, smem, st); break;
-        default: throw std::runtime_error("assemble: empty flags");
-    }
-}
-
-template <int B, int D, int PATCH>
-void launch_patch_bd(const ElemParams& P, const PatchParams& Q, bool slack, bool fine, int flags, int64_t nblk, size_t smem,
-                     cudaStream_t st) {
-    if (slack) {
-        if (fine) launch_patch_flags<B, D, true, true, PATCH>(P, Q, flags, nblk, smem, st);
-        else launch_patch_flags<B, D, true, false, PATCH>(P, Q, flags, nblk, smem, st);
-    } else {
-        if (fine) launch_patch_flags<B, D, false, true, PATCH>(P, Q, flags, nblk, smem, st);
-        else launch_patch_flags<B, D, false, false, PATCH>(P, Q, flags, nblk, smem, st);
-    }
-}
-
 }  // namespace mgb

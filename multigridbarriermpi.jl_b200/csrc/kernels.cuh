@@ -117,8 +117,11 @@ template <int D, bool WANT_F, bool WANT_D>
 __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, double p, BarrierOut& o) {
     const double a = 2.0 / p;
     const double mu = barrier_mu(p);
+    // p is uniform over the grid: the branches below are uniform.  The common cases p = 1 and p = 2 need neither pow
+    // nor (mu = 0) log s nor - for p = 1 - the reciprocal of s; a division / a log cost 40-80 instructions each.
+    const bool need_is = (mu != 0.0) || (p != 1.0);
     double sa, sa1, sa2;  // s^a, s^(a-1), s^(a-2)
-    const double is = 1.0 / s;
+    const double is = need_is ? 1.0 / s : 0.0;
     if (p == 1.0) { sa = s * s; sa1 = s; sa2 = 1.0; }
     else if (p == 2.0) { sa = s; sa1 = 1.0; sa2 = is; }
     else { sa = pow(s, a); sa1 = sa * is; sa2 = sa1 * is; }
@@ -127,7 +130,11 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
     for (int j = 0; j < D; ++j) qq += q[j] * q[j];
     const double phi = sa - qq;
     o.feasible = (s > 0.0) && (phi > 0.0);
-    if (WANT_F) o.F = o.feasible ? (-log(phi) - mu * log(s)) : __longlong_as_double(0x7ff0000000000000LL);
+    if (WANT_F) {
+        double f = -log(phi);
+        if (mu != 0.0) f -= mu * log(s);
+        o.F = o.feasible ? f : __longlong_as_double(0x7ff0000000000000LL);
+    }
     if (WANT_D) {
         const double ip = 1.0 / phi, ip2 = ip * ip;
         const double ds = a * sa1;
@@ -145,8 +152,7 @@ __device__ __forceinline__ void barrier_eval(const double (&q)[D], double s, dou
 
 // FLAGS bits: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
 // Per-point work of one element group (LPE lanes).  Writes the element's gradient record to `rel`
-// and its slot record to `sel` (global memory in the two-stage path, shared memory in the patch-
-// fused path; entry r of a butterfly-reduced block is stored at  off + r*LPE + lane).  Returns this
+// and its slot record to `sel` (entry r of a butterfly-reduced block is stored at  off + r*LPE + lane).  Returns this
 // thread's objective / <c,Dz> / infeasibility partials.  Every lane of the group must call it.
 // MODE: 0 = one cone on (grad u, s); 1 = feasibility phase, cone on (grad u, s + tau) plus -log(1 + tau);
 //       2 = two cones (upstream parabolic_solve): A on (u, s1) with exponent p2, B on (grad u, s2) with p.
@@ -497,147 +503,6 @@ __global__ void __launch_bounds__(MGB_ELEM_THREADS, MGB_ELEM_MINBLOCKS) element_
     const int64_t er = FINE ? e : e / P.agg;   // record of the element's aggregation group
     element_body<B, D, MODE, FINE, FLAGS>(P, e, l, P.sel + er * (int64_t)P.NS, P.rel + er * (NU * LPE), v0, v1, v2);
     block_scalars(v0, v1, v2, P.part);
-}
-
-// Patch-fused path: one CTA = PATCH consecutive elements.  Phase A keeps the slot / gradient records
-// in shared memory; phase B replays the patch's frozen lists: entries fed by this patch alone go
-// straight into the CSR value array / gradient, the others leave one partial sum per patch in the
-// export buffers that interface_kernel folds.  No atomics; fixed summation order.
-struct ReplayDev {
-    const int32_t* pp;  const int2* rec;
-    const int32_t* lg_pp;  const int32_t* lg_dest;  const int32_t* lg_ptr;  const uint16_t* lg_idx;
-    double* out;  double* exp;
-    int max_rec;
-};
-
-struct PatchParams {
-    int NSP, RSP;  // shared-memory strides (doubles) of the slot / gradient records
-    ReplayDev H, G;
-};
-
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// replay of one output family from the patch's shared-memory image `img`
-__device__ __forceinline__ void replay(const ReplayDev& R, const int2* __restrict__ rec_s, const double* __restrict__ img,
-                                       const int p) {
-    const int n = R.pp[p + 1] - R.pp[p];
-#pragma unroll 4
-    for (int k = threadIdx.x; k < n; k += blockDim.x) {
-        const int2 rc = rec_s[k];
-        const uint32_t src = (uint32_t)rc.y;
-        double v = img[src & 0xFFFFu];
-        const uint32_t s1 = src >> 16;
-        if (s1 != 0xFFFFu) v += img[s1];
-        if (rc.x >= 0) R.out[rc.x] = v; else R.exp[-1 - rc.x] = v;
-    }
-    for (int k = R.lg_pp[p] + threadIdx.x; k < R.lg_pp[p + 1]; k += blockDim.x) {
-        const int32_t dest = __ldg(&R.lg_dest[k]);
-        const int r0 = __ldg(&R.lg_ptr[k]), r1 = __ldg(&R.lg_ptr[k + 1]);
-        double v = 0.0;
-        for (int r = r0; r < r1; ++r) v += img[__ldg(&R.lg_idx[r])];
-        if (dest >= 0) R.out[dest] = v; else R.exp[-1 - dest] = v;
-    }
-}
-
-template <int B, int D, bool SLACK, bool FINE, int FLAGS, int PATCH>
-__global__ void __launch_bounds__(PATCH * Pow2Ceil<B>::value) patch_kernel(const ElemParams P, const PatchParams Q) {
-    constexpr int LPE = Pow2Ceil<B>::value;
-    constexpr bool WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0;
-    extern __shared__ double smem[];
-    double* img = smem;                                               // PATCH*NSP slot records, then PATCH*RSP gradient records
-    int2* rec_h = reinterpret_cast<int2*>(smem + (size_t)PATCH * (Q.NSP + Q.RSP));
-    int2* rec_g = rec_h + Q.H.max_rec;
-    const int p = blockIdx.x;
-    // stage this patch's replay records with cp.async: their latency hides behind phase A
-    if (WH) {
-        const int n = Q.H.pp[p + 1] - Q.H.pp[p];
-        const int2* src = Q.H.rec + Q.H.pp[p];
-        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_h[k], &src[k]);
-    }
-    if (WG) {
-        const int n = Q.G.pp[p + 1] - Q.G.pp[p];
-        const int2* src = Q.G.rec + Q.G.pp[p];
-        for (int k = threadIdx.x; k < n; k += blockDim.x) cp_async8(&rec_g[k], &src[k]);
-    }
-    const int el = threadIdx.x / LPE;
-    const int l = threadIdx.x % LPE;
-    const int64_t e = (int64_t)blockIdx.x * PATCH + el;
-    double v0, v1, v2;
-    element_body<B, D, SLACK ? 1 : 0, FINE, FLAGS>(P, e, l, img + (size_t)el * Q.NSP,
-                                           img + (size_t)PATCH * Q.NSP + (size_t)el * Q.RSP, v0, v1, v2);
-    if (WG || WH) cp_async_commit_wait_all();
-    block_scalars(v0, v1, v2, P.part);  // contains the __syncthreads that publishes records and staged lists
-    if (WH) replay(Q.H, rec_h, img, p);
-    if (WG) replay(Q.G, rec_g, img, p);
-}
-
-struct InterfaceParams {
-    int64_t n_if, n_gif, nparts;
-    const int32_t* if_t;  const int32_t* if_ptr;  const double* hexp;  double* hval;
-    const int32_t* gif_a; const int32_t* gif_ptr; const double* gexp;  double* grad;
-    const double* part;  double* scal;  double t;
-    int64_t nblk_h, nblk_g;
-    int warp_per_entry;
-};
-
-// Folds the per-patch partial sums of the interface entries (fixed patch order) and the scalar partials.
-static __global__ void __launch_bounds__(256) interface_kernel(const InterfaceParams P) {
-    const int64_t b = blockIdx.x;
-    if (b < P.nblk_h + P.nblk_g) {
-        const bool isg = b >= P.nblk_h;
-        const int64_t nent = isg ? P.n_gif : P.n_if;
-        const int32_t* __restrict__ ptr = isg ? P.gif_ptr : P.if_ptr;
-        const int32_t* __restrict__ idx = isg ? P.gif_a : P.if_t;
-        const double* __restrict__ src = isg ? P.gexp : P.hexp;
-        double* __restrict__ dst = isg ? P.grad : P.hval;
-        const int64_t bb = isg ? b - P.nblk_h : b;
-        if (P.warp_per_entry) {
-            const int64_t j = bb * 8 + (threadIdx.x >> 5);
-            const int lane = threadIdx.x & 31;
-            if (j >= nent) return;
-            double acc = 0.0;
-            for (int r = ptr[j] + lane; r < ptr[j + 1]; r += 32) acc += src[r];
-#pragma unroll
-            for (int mk = 16; mk >= 1; mk >>= 1) acc += shfl_xor_d(acc, mk);
-            if (lane == 0) dst[idx[j]] = acc;
-        } else {
-            const int64_t j = bb * 256 + threadIdx.x;
-            if (j >= nent) return;
-            double acc = 0.0;
-            for (int r = __ldg(&ptr[j]); r < __ldg(&ptr[j + 1]); ++r) acc += src[r];
-            dst[__ldg(&idx[j])] = acc;
-        }
-        return;
-    }
-    __shared__ double sh[3][256];
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int64_t r = threadIdx.x; r < P.nparts; r += blockDim.x) {
-        s0 += P.part[r * 4 + 0];
-        s1 += P.part[r * 4 + 1];
-        s2 += P.part[r * 4 + 2];
-    }
-    sh[0][threadIdx.x] = s0; sh[1][threadIdx.x] = s1; sh[2][threadIdx.x] = s2;
-    __syncthreads();
-    for (int st = blockDim.x / 2; st >= 1; st >>= 1) {
-        if ((int)threadIdx.x < st) {
-            sh[0][threadIdx.x] += sh[0][threadIdx.x + st];
-            sh[1][threadIdx.x] += sh[1][threadIdx.x + st];
-            sh[2][threadIdx.x] += sh[2][threadIdx.x + st];
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0 && P.scal) {
-        P.scal[0] = sh[0][0] + P.t * sh[1][0];
-        P.scal[1] = (sh[2][0] == 0.0) ? 1.0 : 0.0;
-        P.scal[2] = sh[1][0];
-        P.scal[3] = sh[2][0];
-    }
 }
 
 // Cross-rank sum of the three objective scalars without a fence or a collective: every 64-bit word that crosses

@@ -20,11 +20,4 @@ void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, in
     else throw std::runtime_error("element kernel not instantiated for this element type");
 }
 
-void launch_patch(int B, int dim, bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags,
-                  int64_t nblk, size_t smem, cudaStream_t st) {
-    if (B == 2 && dim == 1) launch_patch_1d(slack, fine, patch, P, Q, flags, nblk, smem, st);
-    else if (B == 7 && dim == 2) launch_patch_2d(slack, fine, patch, P, Q, flags, nblk, smem, st);
-    else throw std::runtime_error("patch kernel not instantiated for this element type");
-}
-
 }  // namespace mgb

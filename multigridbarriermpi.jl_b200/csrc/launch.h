@@ -1,4 +1,4 @@
-// Launch entry points of the templated element / patch kernels.  The instantiations live in
+// Launch entry points of the templated element kernels.  The instantiations live in
 // inst_1d.cu / inst_2d.cu so the translation units compile in parallel.
 #pragma once
 #include <cuda_runtime.h>
@@ -14,14 +14,8 @@ bool element_supported(int B, int dim);
 int canonical_flags(int flags);
 
 void launch_element(int B, int dim, int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
-void launch_patch(int B, int dim, bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags,
-                  int64_t nblk, size_t smem, cudaStream_t st);
 
 void launch_element_1d(int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
 void launch_element_2d(int mode, bool fine, const ElemParams& P, int flags, int64_t nblk, cudaStream_t st);
-void launch_patch_1d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
-                     size_t smem, cudaStream_t st);
-void launch_patch_2d(bool slack, bool fine, int patch, const ElemParams& P, const PatchParams& Q, int flags, int64_t nblk,
-                     size_t smem, cudaStream_t st);
 
 }  // namespace mgb

@@ -125,30 +125,6 @@ struct mgb_plan {
     int64_t n_long = 0;
     DevBuf<double> d_prec, d_w, d_sel, d_rel, d_part, d_scal_tmp;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0, n_hstored = 0;
-    // patch-fused path
-    int patch = 0;  // elements per CTA (0 = two-stage path)
-    int NSP = 0, RSP = 0;
-    int64_t n_if = 0, n_gif = 0, n_hexp = 0, n_gexp = 0;
-    bool if_warp = false;
-    struct ReplayBufs {
-        DevBuf<int32_t> pp, rec, lg_pp, lg_dest, lg_ptr, if_dst, if_ptr;
-        DevBuf<uint16_t> lg_idx;
-        DevBuf<double> exp;
-        int max_rec = 0;
-        void upload(const mgb::ReplayLists& L, cudaStream_t st) {
-            pp.upload(L.pp, st); rec.upload(L.rec, st); lg_pp.upload(L.lg_pp, st); lg_dest.upload(L.lg_dest, st);
-            lg_ptr.upload(L.lg_ptr, st); lg_idx.upload(L.lg_idx, st); if_dst.upload(L.if_dst, st); if_ptr.upload(L.if_ptr, st);
-            exp.alloc((size_t)std::max<int64_t>(L.n_exp, 1));
-            max_rec = L.max_rec;
-        }
-        size_t bytes() const { return pp.bytes() + rec.bytes() + lg_pp.bytes() + lg_dest.bytes() + lg_ptr.bytes() + lg_idx.bytes() + if_dst.bytes() + if_ptr.bytes() + exp.bytes(); }
-        mgb::ReplayDev dev(double* out) const {
-            mgb::ReplayDev r{};
-            r.pp = pp.p; r.rec = reinterpret_cast<const int2*>(rec.p); r.lg_pp = lg_pp.p; r.lg_dest = lg_dest.p;
-            r.lg_ptr = lg_ptr.p; r.lg_idx = lg_idx.p; r.out = out; r.exp = exp.p; r.max_rec = max_rec;
-            return r;
-        }
-    } rp_h, rp_g;
     bool has_hessian = true;
     bool long_lists = false;
     // ---- csr path
@@ -293,13 +269,6 @@ int64_t algorithmic_bytes(int64_t n, int64_t N, int nD, int dim, int64_t nnzD, i
     return b;
 }
 
-// The patch-fused kernel is opt-in (MGB_PATCH=16|32|64): measured slower than the two-stage pair at L=8.
-bool want_patch_early(int force_flags) {
-    const char* ev = getenv("MGB_PATCH");
-    return (force_flags & MGB_PLAN_TWO_STAGE) == 0 && ev && atoi(ev) > 0;
-}
-bool patch_requested(int force_flags, const mgb::ElementPlan& ep) { return want_patch_early(force_flags) && ep.mode != 2; }
-
 bool elem_supported(int B, int dim) { return mgb::element_supported(B, dim); }
 
 // Every index the numeric kernels will dereference comes from these frozen lists: check all of them once, on the
@@ -394,32 +363,6 @@ void assemble_element(mgb_plan* pl, const double* s, const double* Dz0, const do
     if ((flags & MGB_STORE_DZ) && !Dz) throw std::runtime_error("MGB_STORE_DZ without Dz buffer");
     if ((flags & MGB_WANT_GRAD) && !grad) throw std::runtime_error("MGB_WANT_GRAD without grad buffer");
     if ((flags & MGB_WANT_HESS) && !hval) throw std::runtime_error("MGB_WANT_HESS without hval buffer");
-    if (pl->patch > 0) {
-        int f = flags & 15;
-        if ((f & 6) == 4) f |= 2;  // Hessian-only requests also produce the gradient (same kernel instance)
-        if ((f & 2) && !grad) grad = pl->d_rel.p;  // scratch target when the caller did not ask for it
-        mgb::PatchParams Q{};
-        Q.NSP = pl->NSP; Q.RSP = pl->RSP;
-        Q.H = pl->rp_h.dev(hval);
-        Q.G = pl->rp_g.dev(grad);
-        const size_t smem = ((size_t)pl->patch * (pl->NSP + pl->RSP)) * sizeof(double) +
-                            ((size_t)pl->rp_h.max_rec + pl->rp_g.max_rec) * sizeof(int2);
-        mgb::launch_patch(ep.B, ep.dim, ep.slack, ep.fine, pl->patch, P, Q, f, pl->nblocks_elem, smem, st);
-        g_launches++;
-        if (mid) CUDA_OK(cudaEventRecord(mid, st));
-        mgb::InterfaceParams I{};
-        I.n_if = (f & 4) ? pl->n_if : 0; I.n_gif = (f & 2) ? pl->n_gif : 0; I.nparts = pl->nblocks_elem;
-        I.if_t = pl->rp_h.if_dst.p; I.if_ptr = pl->rp_h.if_ptr.p; I.hexp = pl->rp_h.exp.p; I.hval = hval;
-        I.gif_a = pl->rp_g.if_dst.p; I.gif_ptr = pl->rp_g.if_ptr.p; I.gexp = pl->rp_g.exp.p; I.grad = grad;
-        I.part = pl->d_part.p; I.scal = scal ? scal : pl->d_scal_tmp.p; I.t = t;
-        I.warp_per_entry = pl->if_warp ? 1 : 0;
-        const int64_t per = pl->if_warp ? 8 : 256;
-        I.nblk_h = (I.n_if + per - 1) / per; I.nblk_g = (I.n_gif + per - 1) / per;
-        mgb::interface_kernel<<<(unsigned)(I.nblk_h + I.nblk_g + 1), 256, 0, st>>>(I);
-        g_launches++;
-        CUDA_OK(cudaGetLastError());
-        return;
-    }
     launch_elem(pl, P, flags);
     if (mid) CUDA_OK(cudaEventRecord(mid, st));
 
@@ -478,7 +421,6 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         cudaStream_t st = host_only ? nullptr : ctx->stream;
         bool use_elem = false;
         const bool want_hess = (force_path & MGB_PLAN_NO_HESSIAN) == 0;
-        const int force_flags = force_path;
         force_path &= 3;
         pl->has_hessian = want_hess;
         if (out1 < 0) out1 = pl->m;
@@ -488,7 +430,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         if (sharded && force_path == MGB_PATH_CSR) throw std::runtime_error("sharded plans need the element path");
         if (force_path != MGB_PATH_CSR) {
             mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess, out0, out1,
-                                    /*allow_agg=*/!want_patch_early(force_flags) && getenv("MGB_NO_AGG") == nullptr);
+                                    /*allow_agg=*/getenv("MGB_NO_AGG") == nullptr);
             use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
             if (!use_elem && sharded) throw std::runtime_error(std::string("sharded plans need the element path: ") + (pl->ep.ok ? "element type not instantiated" : pl->ep.why));
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
@@ -512,9 +454,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             }
           if (!host_only) {
             pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
-            if (patch_requested(force_flags, ep)) {
-                // patch-fused path builds its own lists below
-            } else if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
+            if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
                 pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
                 // chunk only where it pays: lists of a thousand contributions and more (coarsest levels)
                 const int64_t ch = gather_chunk();
@@ -543,29 +483,14 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 CUDA_OK(cudaStreamSynchronize(st));
             }
             pl->d_gcptr.upload(ep.g_cptr, st); pl->d_gcidx.upload(ep.g_cidx, st);
-            int want_patch = 0;
-            if (patch_requested(force_flags, ep)) {
-                want_patch = atoi(getenv("MGB_PATCH"));
-                if (ep.B == 7 && want_patch != 16 && want_patch != 32 && want_patch != 64) want_patch = 16;
-                if (ep.B == 2) want_patch = 64;
-            }
-            if (want_patch > 0) {
-                mgb::build_patch_plan(ep, want_patch);
-                const auto& pp = ep.patch;
-                pl->patch = pp.P; pl->NSP = pp.NSP; pl->RSP = pp.RSP;
-                pl->n_if = (int64_t)pp.H.if_dst.size(); pl->n_gif = (int64_t)pp.G.if_dst.size();
-                pl->n_hexp = pp.H.n_exp; pl->n_gexp = pp.G.n_exp;
-                pl->if_warp = pl->n_if > 0 && (double)pp.H.n_exp / (double)pl->n_if > 16.0;
-                pl->rp_h.upload(pp.H, st); pl->rp_g.upload(pp.G, st);
-                CUDA_OK(cudaStreamSynchronize(st));
-            }
             const int64_t nrec = (ep.E + ep.agg - 1) / ep.agg;   // one record per aggregation group
-            if (pl->patch == 0) pl->d_sel.alloc((size_t)nrec * ep.lay.NS);
+            pl->d_sel.alloc((size_t)nrec * ep.lay.NS);
             pl->d_rel.alloc((size_t)std::max<int64_t>(nrec * ep.NU * ep.LPE, pl->m_out));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
-            const int epb = pl->patch > 0 ? pl->patch : MGB_ELEM_THREADS / ep.LPE;
+            const int epb = MGB_ELEM_THREADS / ep.LPE;
             pl->nblocks_elem = (ep.E + epb - 1) / epb;
+
             pl->d_part.alloc((size_t)pl->nblocks_elem * 4);
             pl->d_scal_tmp.alloc(4);
             CUDA_OK(cudaStreamSynchronize(st));
@@ -1279,7 +1204,7 @@ int mgb_dist_plan_create(mgb_ctx* ctx, int64_t n, int32_t nD, const mgb_csr* D, 
                                       out_part[rank], out_part[rank + 1], MGB_PATH_ELEMENT | MGB_PLAN_TWO_STAGE, &plraw);
         if (rc) return rc;
         std::unique_ptr<mgb_plan, int (*)(mgb_plan*)> pl(plraw, mgb_plan_destroy);
-        if (pl->patch > 0 || pl->long_lists)
+        if (pl->long_lists)
             return fail("mgb_dist_plan_create: sharded plans need the element path: this level's gather runs lanes-per-entry (coarse level)");
         auto dd = std::make_unique<mgb_plan::Dist>();
         dd->rank = rank; dd->nranks = nranks; dd->rows = std::move(rows);

@@ -387,9 +387,11 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                     if (pass == 0) { rowcnt[ga - out0 + 1]++; continue; }
                     const int sl = slot_of(a1, a2, own);
                     if (sl < 0) throw std::runtime_error("internal: structurally present pair without a slot");
+                    const int64_t abs_slot = (e / P.agg) * lay.NS + sl;
+                    if (abs_slot > INT32_MAX) throw std::runtime_error("element slot buffer exceeds int32 indexing");
                     const int64_t d = fillpos[ga - out0]++;
                     tb[d] = gb;
-                    ts[d] = (int32_t)((e / P.agg) * lay.NS + sl);
+                    ts[d] = (int32_t)abs_slot;
                 }
             }
         }
@@ -440,87 +442,6 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
                 if (a >= out0 && a < out1) P.g_cidx[gpos[a - out0]++] = (int32_t)(((e / P.agg) * nu + v) * LPE + q);
             }
     P.ok = true;
-}
-
-namespace {
-// cptr/cidx: per output entry the (element-sorted) global contribution slots; patch_of/local_of map a
-// global slot to its patch and to its 16-bit index inside the patch's shared-memory image.
-template <class PatchOf, class LocalOf>
-void build_replay(int64_t nout, const std::vector<int64_t>& cptr, const std::vector<int32_t>& cidx, int64_t np,
-                  PatchOf patch_of, LocalOf local_of, ReplayLists& L) {
-    struct Grp { int64_t c0, c1, patch; int32_t dest; };
-    std::vector<Grp> groups;
-    groups.reserve((size_t)(nout + nout / 4));
-    std::vector<int32_t> rc(np + 1, 0), lc(np + 1, 0);
-    L.if_ptr.assign(1, 0);
-    int64_t nexp = 0;
-    for (int64_t t = 0; t < nout; ++t) {
-        const int64_t c0 = cptr[t], c1 = cptr[t + 1];
-        if (c1 == c0) continue;
-        const bool single = patch_of(cidx[c0]) == patch_of(cidx[c1 - 1]);  // lists are sorted by element
-        int64_t g0 = c0;
-        while (g0 < c1) {
-            const int64_t pa = patch_of(cidx[g0]);
-            int64_t g1 = g0;
-            while (g1 < c1 && patch_of(cidx[g1]) == pa) ++g1;
-            groups.push_back({g0, g1, pa, single ? (int32_t)t : (int32_t)(-1 - nexp++)});
-            if (g1 - g0 <= 2) rc[pa + 1]++; else lc[pa + 1]++;
-            g0 = g1;
-        }
-        if (!single) { L.if_dst.push_back((int32_t)t); L.if_ptr.push_back((int32_t)nexp); }
-    }
-    if (nexp > INT32_MAX) throw std::runtime_error("export buffer exceeds int32 indexing");
-    L.n_exp = nexp;
-    L.max_rec = 0;
-    for (int64_t q = 0; q < np; ++q) {
-        L.max_rec = std::max(L.max_rec, rc[q + 1]);
-        rc[q + 1] += rc[q];
-        lc[q + 1] += lc[q];
-    }
-    L.pp = rc; L.lg_pp = lc;
-    L.rec.resize((size_t)2 * rc[np]);
-    L.lg_dest.resize(lc[np]);
-    std::vector<int32_t> lcnt(lc[np], 0), rpos(rc.begin(), rc.end() - 1), lpos(lc.begin(), lc.end() - 1);
-    std::vector<int64_t> lsrc0(lc[np], 0);
-    for (const Grp& g : groups) {
-        const int64_t cnt = g.c1 - g.c0;
-        if (cnt <= 2) {
-            const int32_t k = rpos[g.patch]++;
-            const uint32_t s0 = local_of(cidx[g.c0]);
-            const uint32_t s1 = cnt == 2 ? local_of(cidx[g.c0 + 1]) : 0xFFFFu;
-            L.rec[2 * (size_t)k] = g.dest;
-            L.rec[2 * (size_t)k + 1] = (int32_t)(s0 | (s1 << 16));
-        } else {
-            const int32_t k = lpos[g.patch]++;
-            L.lg_dest[k] = g.dest; lcnt[k] = (int32_t)cnt; lsrc0[k] = g.c0;
-        }
-    }
-    L.lg_ptr.assign(lc[np] + 1, 0);
-    for (int64_t k = 0; k < lc[np]; ++k) L.lg_ptr[k + 1] = L.lg_ptr[k] + lcnt[k];
-    L.lg_idx.resize(L.lg_ptr[lc[np]]);
-    for (int64_t k = 0; k < lc[np]; ++k)
-        for (int32_t r = 0; r < lcnt[k]; ++r) L.lg_idx[L.lg_ptr[k] + r] = local_of(cidx[lsrc0[k] + r]);
-}
-}  // namespace
-
-void build_patch_plan(ElementPlan& EP, int elems_per_patch) {
-    PatchPlan& PP = EP.patch;
-    const int NS = EP.lay.NS, LPE = EP.LPE, NU = EP.NU;
-    PP.P = elems_per_patch;
-    PP.npatch = (EP.E + PP.P - 1) / PP.P;
-    int nsp = NS;
-    while (nsp % 16 != LPE % 16) ++nsp;  // consecutive elements land on disjoint shared-memory banks
-    PP.NSP = nsp;
-    PP.RSP = NU * LPE;
-    const int64_t P = PP.P, NSP = PP.NSP, RS = PP.RSP;
-    if (P * (NSP + RS) > 65534) throw std::runtime_error("patch too large for 16-bit local slots");
-    build_replay((int64_t)EP.h_colidx.size(), EP.h_cptr, EP.h_cidx, PP.npatch,
-                 [&](int32_t gs) { return (int64_t)(gs / NS) / P; },
-                 [&](int32_t gs) { const int64_t e = gs / NS; return (uint32_t)((e % P) * NSP + gs % NS); }, PP.H);
-    // gradient records live after the slot records in the patch's shared-memory image
-    build_replay(EP.m, EP.g_cptr, EP.g_cidx, PP.npatch,
-                 [&](int32_t gi) { return (int64_t)(gi / RS) / P; },
-                 [&](int32_t gi) { const int64_t e = gi / RS; return (uint32_t)(P * NSP + (e % P) * RS + gi % RS); }, PP.G);
 }
 
 void dist_select_elements(const std::vector<int32_t>& lcols, int64_t E, int NU, int LPE, int B, int rank, int nranks,

@@ -40,31 +40,6 @@ struct SlotLayout {
     int nfull_pad() const;
 };
 
-// Patch-fused replay lists: a CTA owns P consecutive elements, keeps their slot records in shared
-// memory and finishes every output entry whose contributions all come from the patch; the others get
-// one partial sum per patch in an export buffer that a small interface kernel folds.
-// One output family (Hessian values or gradient entries) of the patch-fused replay.
-struct ReplayLists {
-    std::vector<int32_t> pp;       // npatch+1: records of patch p are [pp[p], pp[p+1])
-    std::vector<int32_t> rec;      // 2 ints per record: dest, src  (dest >= 0: index into the output array,
-                                   // dest < 0: -1-index into the export buffer; src: lo16 first local slot,
-                                   // hi16 second local slot or 0xFFFF)
-    std::vector<int32_t> lg_pp;    // npatch+1: entries with more than two in-patch contributions
-    std::vector<int32_t> lg_dest;
-    std::vector<int32_t> lg_ptr;   // nlong+1 into lg_idx
-    std::vector<uint16_t> lg_idx;
-    std::vector<int32_t> if_dst;   // interface entries: output index
-    std::vector<int32_t> if_ptr;   // n_if+1 into the export buffer (partials of one entry are contiguous)
-    int64_t n_exp = 0;
-    int32_t max_rec = 0;           // longest per-patch record list (sizes the shared-memory staging area)
-};
-
-struct PatchPlan {
-    int P = 0, NSP = 0, RSP = 0;  // elements per patch, smem strides (doubles) of the slot / gradient records
-    int64_t npatch = 0;
-    ReplayLists H, G;              // G's local slots index the gradient records, stored after the slot records
-};
-
 struct ElementPlan {
     bool ok = false;       // element-block structure detected and supported by the fused kernels
     std::string why;       // reason when !ok
@@ -86,11 +61,7 @@ struct ElementPlan {
     std::vector<int32_t> h_cidx;              // contribution -> e*NS + slot
     std::vector<int64_t> g_cptr;              // m_out+1
     std::vector<int32_t> g_cidx;              // contribution -> (e*NU+v)*LPE + q
-    PatchPlan patch;
 };
-
-// Derives the patch-fused lists from the element plan's global contribution lists.
-void build_patch_plan(ElementPlan& P, int elems_per_patch);
 
 struct BarrierDesc {
     int kind = 1, nidx = 0, idx[8] = {0};

@@ -42,20 +42,10 @@ def test_feasibility_slack_variant(gpu_ctx, gen, L):
 @pytest.mark.parametrize("gen,L,level,slack", [("fem1d", 4, None, False), ("fem2d", 4, None, False), ("fem2d", 4, 1, False),
                                                   ("fem2d", 3, None, True), ("fem2d", 3, 0, True)])
 def test_two_stage_element_path(gpu_ctx, gen, L, level, slack):
-    """the element_kernel + gather_kernel pair kept for A/B comparison against the patch-fused kernel"""
+    """MGB_PLAN_TWO_STAGE is accepted for compatibility (the two-stage element path is the only one)"""
     plan, _ = check_against_oracle(gpu_ctx, getattr(mgb_b200, gen)(L), 1.0, t=0.9, level=level, slack=slack,
                                    force_path=capi.PLAN_TWO_STAGE)
     assert plan.info["path"] == capi.PATH_ELEMENT
-
-
-@pytest.mark.parametrize("patch", ["16", "32", "64"])
-def test_patch_fused_path(gpu_ctx, patch, monkeypatch):
-    """opt-in patch-fused kernel (MGB_PATCH): CTA-local records in shared memory + interface partials"""
-    monkeypatch.setenv("MGB_PATCH", patch)
-    check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.0, t=0.9)
-    check_against_oracle(gpu_ctx, mgb_b200.fem2d(4), 1.5, t=0.9, level=1)
-    check_against_oracle(gpu_ctx, mgb_b200.fem2d(3), 1.0, t=0.9, slack=True)
-    check_against_oracle(gpu_ctx, mgb_b200.fem1d(6), 1.0, t=0.9)
 
 
 def test_bitwise_reproducible(gpu_ctx):
