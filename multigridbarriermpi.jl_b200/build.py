@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MGB_B200_LIB") or os.path.join(HERE, "libmgb_b200.so")
 SOURCES = ["mgb_b200.cu", "plan_host.cpp", "launch.cu", "inst_1d.cu", "inst_2d.cu"]
-HEADERS = ["kernels.cuh", "kernels_csr.cuh", "kernels_dist.cuh", "plan_host.h", "launch.h", "inst_common.cuh", os.path.join("..", "..", "include", "mgb_b200.h")]
+HEADERS = ["kernels.cuh", "kernels_dense.cuh", "kernels_csr.cuh", "kernels_dist.cuh", "plan_host.h", "launch.h", "inst_common.cuh", os.path.join("..", "..", "include", "mgb_b200.h")]
 
 
 def _nvcc() -> str:

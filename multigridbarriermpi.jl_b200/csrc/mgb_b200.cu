@@ -17,6 +17,7 @@
 
 #include "kernels.cuh"
 #include "kernels_csr.cuh"
+#include "kernels_dense.cuh"
 #include "kernels_dist.cuh"
 #include "launch.h"
 #include "plan_host.h"
@@ -124,6 +125,10 @@ struct mgb_plan {
     DevBuf<int32_t> d_hlidx, d_hlt;
     int64_t n_long = 0;
     DevBuf<double> d_prec, d_w, d_sel, d_rel, d_part, d_scal_tmp;
+    // dense path (coarse levels of large elements): group dofs, chunk table, dense operator rows
+    DevBuf<int32_t> d_dgdof;
+    DevBuf<int64_t> d_dchunk;
+    DevBuf<double> d_drows;
     int64_t nblocks_elem = 0, n_hcontrib = 0, n_gcontrib = 0, n_hstored = 0;
     bool has_hessian = true;
     bool long_lists = false;
@@ -294,8 +299,36 @@ void validate_element_plan(const mgb::ElementPlan& ep) {
     for (double v : ep.prec) if (!(v == v)) bad("NaN in an operator record");
 }
 
+void launch_dense(const mgb_plan* pl, const mgb::ElemParams& E, int flags) {
+    mgb::DenseParams P{};
+    P.nchunks = pl->ep.d_nchunks; P.nloc = pl->ep.nloc;
+    P.chunk = pl->d_dchunk.p; P.gdof = pl->d_dgdof.p; P.rows = pl->d_drows.p; P.w = pl->d_w.p;
+    P.s = E.s; P.Dz0 = E.Dz0; P.c = E.c; P.t = E.t; P.p = E.p;
+    P.sel = E.sel; P.rel = E.rel; P.part = E.part; P.Dz = E.Dz;
+    static bool opted = false;
+    if (!opted) {
+        CUDA_OK(cudaFuncSetAttribute(mgb::dense_element_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::D_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(mgb::dense_element_kernel<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::D_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(mgb::dense_element_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::D_SMEM));
+        CUDA_OK(cudaFuncSetAttribute(mgb::dense_element_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::D_SMEM));
+        opted = true;
+    }
+    const dim3 g((unsigned)P.nchunks), b(256);
+    cudaStream_t st = pl->ctx->stream;
+    switch (mgb::canonical_flags(flags)) {
+        case 1: mgb::dense_element_kernel<1><<<g, b, mgb::D_SMEM, st>>>(P); break;
+        case 7: mgb::dense_element_kernel<7><<<g, b, mgb::D_SMEM, st>>>(P); break;
+        case 8: mgb::dense_element_kernel<8><<<g, b, mgb::D_SMEM, st>>>(P); break;
+        case 15: mgb::dense_element_kernel<15><<<g, b, mgb::D_SMEM, st>>>(P); break;
+        default: throw std::runtime_error("assemble: empty flags");
+    }
+    g_launches++;
+    CUDA_OK(cudaGetLastError());
+}
+
 void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
     const auto& ep = pl->ep;
+    if (ep.dense) { launch_dense(pl, P, flags); return; }
     mgb::launch_element(ep.B, ep.dim, ep.mode, ep.fine, P, flags, pl->nblocks_elem, pl->ctx->stream);
     g_launches++;
     CUDA_OK(cudaGetLastError());
@@ -431,7 +464,7 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
         if (force_path != MGB_PATH_CSR) {
             mgb::build_element_plan(Dh, Rh, n, wloc.data(), pl->bar, pl->ep, want_hess, out0, out1,
                                     /*allow_agg=*/getenv("MGB_NO_AGG") == nullptr);
-            use_elem = pl->ep.ok && elem_supported(pl->ep.B, pl->ep.dim);
+            use_elem = pl->ep.ok && (pl->ep.dense || elem_supported(pl->ep.B, pl->ep.dim));
             if (!use_elem && sharded) throw std::runtime_error(std::string("sharded plans need the element path: ") + (pl->ep.ok ? "element type not instantiated" : pl->ep.why));
             if (!use_elem && force_path == MGB_PATH_ELEMENT)
                 throw std::runtime_error("element path unavailable: " + (pl->ep.ok ? std::string("element type not instantiated") : pl->ep.why));
@@ -453,7 +486,8 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
                 pl->long_lists = avg > (ev ? atof(ev) : 6.0);
             }
           if (!host_only) {
-            pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st);
+            if (ep.dense) { pl->d_dgdof.upload(ep.d_gdof, st); pl->d_dchunk.upload(ep.d_chunk, st); pl->d_drows.upload(ep.d_rows, st); }
+            else { pl->d_lcols.upload(ep.lcols, st); pl->d_prec.upload(ep.prec, st); }
             if (pl->long_lists) {  // coarse levels: warp-per-entry over the CSR lists
                 pl->d_hcptr.upload(ep.h_cptr, st); pl->d_hcidx.upload(ep.h_cidx, st);
                 // chunk only where it pays: lists of a thousand contributions and more (coarsest levels)
@@ -488,18 +522,18 @@ void finish_plan(std::unique_ptr<mgb_plan>& pl, std::vector<mgb::HostCSR>& Dh, m
             pl->d_rel.alloc((size_t)std::max<int64_t>(nrec * ep.NU * ep.LPE, pl->m_out));
             if (pl->d_sel.p) CUDA_OK(cudaMemsetAsync(pl->d_sel.p, 0, pl->d_sel.bytes(), st));
             CUDA_OK(cudaMemsetAsync(pl->d_rel.p, 0, pl->d_rel.bytes(), st));
-            const int epb = MGB_ELEM_THREADS / ep.LPE;
+            const int epb = ep.dense ? 1 : MGB_ELEM_THREADS / ep.LPE;   // dense path: one CTA per chunk
             pl->nblocks_elem = (ep.E + epb - 1) / epb;
 
             pl->d_part.alloc((size_t)pl->nblocks_elem * 4);
             pl->d_scal_tmp.alloc(4);
             CUDA_OK(cudaStreamSynchronize(st));
             pl->dev_bytes = pl->d_lcols.bytes() + pl->d_prec.bytes() + pl->d_hcptr.bytes() + pl->d_hcidx.bytes() + pl->d_gcptr.bytes() +
-                            pl->d_gcidx.bytes() + pl->ck_h.bytes() + pl->ck_g.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
+                            pl->d_gcidx.bytes() + pl->d_dgdof.bytes() + pl->d_dchunk.bytes() + pl->d_drows.bytes() + pl->ck_h.bytes() + pl->ck_g.bytes() + pl->d_hsrc2.bytes() + pl->d_hlptr.bytes() + pl->d_hlidx.bytes() + pl->d_sel.bytes() + pl->d_rel.bytes() + pl->d_w.bytes();
           }
             // release host copies that are no longer needed
             std::vector<int32_t>().swap(ep.h_cidx); std::vector<int64_t>().swap(ep.h_cptr);
-            std::vector<double>().swap(ep.prec);
+            std::vector<double>().swap(ep.prec); std::vector<double>().swap(ep.d_rows);
             std::vector<int32_t>().swap(ep.h_rowptr); std::vector<int32_t>().swap(ep.h_colidx);
         } else {
             pl->path = MGB_PATH_CSR;

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <iterator>
 #include <numeric>
 #include <stdexcept>
 
@@ -140,6 +141,187 @@ struct UF {
 };
 }  // namespace
 
+
+namespace {
+// See ElementPlan::dense.  Fills the pattern and the replay lists exactly like the element path does, so the
+// upload / gather machinery of the element path is reused unchanged; only stage 1 is a different kernel.
+void build_dense_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const BarrierDesc& bar, ElementPlan& P,
+                      bool want_hessian, int64_t B, const std::vector<int>& var, int dim, int nu, int64_t out0, int64_t out1) {
+    const int ND = (int)D.size(), NB = DENSE_NB;
+    const int64_t nloc = D[0].nrows, m = R.ncols;
+    (void)n_global;
+    if (P.mode != 0 || nu != 2 || dim != 3) { P.why = "element block size not supported by the fused kernels (1..8)"; return; }
+    if (out0 != 0 || out1 != m) { P.why = "dense path does not shard"; return; }
+    if (nloc % B) { P.why = "rows are not whole elements"; return; }
+    const int64_t E = nloc / B;
+    std::vector<HostCSR> Ek(ND);
+    for (int k = 0; k < ND; ++k) Ek[k] = spgemm(D[k], R);
+    // worth it?  products of the list replay ~ sum_i |U_i|^2 / 2 vs ~12 k multiply-adds per point of the dense contraction
+    {
+        double prod = 0.0;
+        for (int64_t i = 0; i < nloc; ++i) {
+            double len = 0.0;
+            for (int k = 0; k < ND; ++k) len += (double)(Ek[k].ptr[i + 1] - Ek[k].ptr[i]);
+            prod += 0.5 * len * len;
+        }
+        if (prod < 1536.0 * (double)nloc) { P.why = "short operator rows: the list replay of the CSR path is cheaper than a dense contraction"; return; }
+    }
+    // dof sets of the fine elements, greedy grouping of consecutive elements
+    std::vector<std::vector<int32_t>> eset((size_t)E * 2);
+    for (int64_t e = 0; e < E; ++e)
+        for (int v = 0; v < 2; ++v) {
+            auto& t = eset[(size_t)e * 2 + v];
+            for (int k = 0; k < ND; ++k) {
+                if (var[k] != v) continue;
+                for (int64_t i = e * B; i < (e + 1) * B; ++i)
+                    for (int64_t q = Ek[k].ptr[i]; q < Ek[k].ptr[i + 1]; ++q) t.push_back(Ek[k].idx[q]);
+            }
+            std::sort(t.begin(), t.end());
+            t.erase(std::unique(t.begin(), t.end()), t.end());
+            if ((int)t.size() > NB) { P.why = "an element touches more than 64 unknowns of one variable"; return; }
+        }
+    std::vector<int64_t> gstart;   // first element of every group
+    std::vector<std::vector<int32_t>> gset;
+    {
+        std::vector<int32_t> cur[2], uni;
+        for (int64_t e = 0; e < E; ++e) {
+            bool fits = e > 0;
+            std::vector<int32_t> nxt[2];
+            for (int v = 0; v < 2 && fits; ++v) {
+                uni.clear();
+                std::set_union(cur[v].begin(), cur[v].end(), eset[(size_t)e * 2 + v].begin(), eset[(size_t)e * 2 + v].end(), std::back_inserter(uni));
+                fits = (int)uni.size() <= NB;
+                nxt[v] = uni;
+            }
+            if (!fits) {
+                if (e > 0) { gset.push_back(cur[0]); gset.push_back(cur[1]); }
+                gstart.push_back(e);
+                cur[0] = eset[(size_t)e * 2]; cur[1] = eset[(size_t)e * 2 + 1];
+            } else { cur[0] = nxt[0]; cur[1] = nxt[1]; }
+        }
+        gset.push_back(cur[0]); gset.push_back(cur[1]);
+        gstart.push_back(E);
+    }
+    const int64_t ng = (int64_t)gstart.size() - 1;
+    P.dense = true; P.fine = false; P.agg = 1;
+    P.B = NB; P.LPE = NB; P.dim = dim; P.NU = nu; P.ND = ND; P.slack = false;
+    P.nloc = nloc; P.m = m; P.out0 = 0; P.m_out = m;
+    P.lay = SlotLayout(); P.lay.B = NB; P.lay.LPE = NB; P.lay.NU = 2; P.lay.dim = dim; P.lay.NS = 3 * NB * NB;
+    P.lay.off_uu = 0; P.lay.off_us = NB * NB; P.lay.off_ss = 2 * NB * NB;
+    P.d_ngroups = ng;
+    P.d_gdof.assign((size_t)ng * 2 * NB, -1);
+    for (int64_t g = 0; g < ng; ++g)
+        for (int v = 0; v < 2; ++v) std::copy(gset[(size_t)g * 2 + v].begin(), gset[(size_t)g * 2 + v].end(), P.d_gdof.begin() + ((size_t)g * 2 + v) * NB);
+    // chunks: about two CTAs per SM on a 148-SM part when the level is small, at most DENSE_CHUNK points each
+    const int64_t chunk_pts = std::min<int64_t>(DENSE_CHUNK, std::max<int64_t>(64, (nloc / 296 + 15) / 16 * 16));
+    std::vector<int64_t> cgroup;
+    for (int64_t g = 0; g < ng; ++g)
+        for (int64_t p0 = gstart[g] * B; p0 < gstart[g + 1] * B; p0 += chunk_pts) {
+            P.d_chunk.push_back(g); P.d_chunk.push_back(p0); P.d_chunk.push_back(std::min<int64_t>(p0 + chunk_pts, gstart[g + 1] * B));
+            cgroup.push_back(g);
+        }
+    const int64_t nch = (int64_t)cgroup.size();
+    P.d_nchunks = nch; P.E = nch;
+    if (nch * (int64_t)P.lay.NS > INT32_MAX) { P.dense = false; P.why = "dense slot buffer exceeds int32 indexing"; return; }
+    // dense operator rows over the group's dofs; per-point support masks (two 64-bit words: u dofs | s dofs)
+    const int NR = dim + 2;   // rows per point: derivative ops (1..dim), u.id (op 0), s.id (op dim+1)
+    P.d_rows.assign((size_t)nloc * NR * NB, 0.0);
+    std::vector<uint64_t> pmask((size_t)nloc * 2, 0);
+    for (int64_t g = 0; g < ng; ++g) {
+        const std::vector<int32_t>* gs[2] = {&gset[(size_t)g * 2], &gset[(size_t)g * 2 + 1]};
+        for (int64_t i = gstart[g] * B; i < gstart[g + 1] * B; ++i)
+            for (int k = 0; k < ND; ++k) {
+                const int v = var[k];
+                const int r = (k == 0) ? dim : (k <= dim ? k - 1 : dim + 1);
+                for (int64_t q = Ek[k].ptr[i]; q < Ek[k].ptr[i + 1]; ++q) {
+                    const int la = (int)(std::lower_bound(gs[v]->begin(), gs[v]->end(), Ek[k].idx[q]) - gs[v]->begin());
+                    P.d_rows[((size_t)i * NR + r) * NB + la] = Ek[k].val[q];
+                    pmask[(size_t)i * 2 + v] |= 1ull << la;
+                }
+            }
+    }
+    // pattern: union over points of support x support, per group through row masks
+    P.h_rowptr.assign(m + 1, 0);
+    P.h_cptr.assign(1, 0);
+    std::vector<uint64_t> rmask((size_t)ng * 2 * NB * 2, 0);   // [group][row: v*NB + la][word: u | s]
+    if (want_hessian) {
+        for (int64_t g = 0; g < ng; ++g)
+            for (int64_t i = gstart[g] * B; i < gstart[g + 1] * B; ++i)
+                for (int v = 0; v < 2; ++v) {
+                    uint64_t mk = pmask[(size_t)i * 2 + v];
+                    while (mk) {
+                        const int la = __builtin_ctzll(mk); mk &= mk - 1;
+                        uint64_t* rm = &rmask[(((size_t)g * 2 + v) * NB + la) * 2];
+                        rm[0] |= pmask[(size_t)i * 2]; rm[1] |= pmask[(size_t)i * 2 + 1];
+                    }
+                }
+        // (row, col, contribution) triples: one per chunk of every group that holds the pair
+        std::vector<int64_t> rowcnt(m + 1, 0);
+        std::vector<int64_t> nchg(ng, 0), ch0(ng, 0);
+        for (int64_t c = 0; c < nch; ++c) { if (nchg[cgroup[c]]++ == 0) ch0[cgroup[c]] = c; }
+        auto for_pairs = [&](auto&& fn) {
+            for (int64_t g = 0; g < ng; ++g)
+                for (int v1 = 0; v1 < 2; ++v1)
+                    for (int la = 0; la < NB; ++la) {
+                        const int32_t ga = P.d_gdof[((size_t)g * 2 + v1) * NB + la];
+                        if (ga < 0) continue;
+                        for (int v2 = 0; v2 < 2; ++v2) {
+                            uint64_t mk = rmask[(((size_t)g * 2 + v1) * NB + la) * 2 + v2];
+                            while (mk) {
+                                const int lb = __builtin_ctzll(mk); mk &= mk - 1;
+                                const int32_t gb = P.d_gdof[((size_t)g * 2 + v2) * NB + lb];
+                                // slot inside a chunk record: uu[la][lb] | us[u la][s lb] | ss[la][lb]; (s, u) reads us transposed
+                                const int slot = (v1 == 0 && v2 == 0) ? la * NB + lb
+                                               : (v1 == 0 && v2 == 1) ? NB * NB + la * NB + lb
+                                               : (v1 == 1 && v2 == 0) ? NB * NB + lb * NB + la
+                                                                      : 2 * NB * NB + la * NB + lb;
+                                fn(g, ga, gb, slot);
+                            }
+                        }
+                    }
+        };
+        for_pairs([&](int64_t g, int32_t ga, int32_t, int) { rowcnt[ga + 1] += nchg[g]; });
+        for (int64_t a = 0; a < m; ++a) rowcnt[a + 1] += rowcnt[a];
+        std::vector<int32_t> tb(rowcnt[m]), ts(rowcnt[m]);
+        std::vector<int64_t> fillpos(rowcnt.begin(), rowcnt.end() - 1);
+        for_pairs([&](int64_t g, int32_t ga, int32_t gb, int slot) {
+            for (int64_t c = ch0[g]; c < ch0[g] + nchg[g]; ++c) {
+                const int64_t d = fillpos[ga]++;
+                tb[d] = gb; ts[d] = (int32_t)(c * P.lay.NS + slot);
+            }
+        });
+        P.h_cidx.resize(tb.size());
+        P.h_cptr.clear();
+        std::vector<std::pair<int32_t, int32_t>> rowbuf;
+        int64_t outc = 0;
+        for (int64_t a = 0; a < m; ++a) {
+            rowbuf.clear();
+            for (int64_t d = rowcnt[a]; d < rowcnt[a + 1]; ++d) rowbuf.emplace_back(tb[d], ts[d]);
+            std::sort(rowbuf.begin(), rowbuf.end());
+            int32_t last = -1;
+            for (auto& pr : rowbuf) {
+                if (pr.first != last) { P.h_colidx.push_back(pr.first); P.h_cptr.push_back(outc); last = pr.first; }
+                P.h_cidx[outc++] = pr.second;
+            }
+            if ((int64_t)P.h_colidx.size() > INT32_MAX) throw std::runtime_error("nnz(H) exceeds int32 indexing");
+            P.h_rowptr[a + 1] = (int32_t)P.h_colidx.size();
+        }
+        P.h_cptr.push_back(outc);
+    }
+    // gradient lists: rel record of a chunk = [u dofs (NB) | s dofs (NB)]
+    std::vector<int64_t> gcnt(m + 1, 0);
+    for (int64_t c = 0; c < nch; ++c)
+        for (int k = 0; k < 2 * NB; ++k) { const int32_t a = P.d_gdof[(size_t)cgroup[c] * 2 * NB + k]; if (a >= 0) gcnt[a + 1]++; }
+    for (int64_t a = 0; a < m; ++a) gcnt[a + 1] += gcnt[a];
+    P.g_cptr = gcnt;
+    P.g_cidx.resize(gcnt[m]);
+    std::vector<int64_t> gpos(gcnt.begin(), gcnt.end() - 1);
+    for (int64_t c = 0; c < nch; ++c)
+        for (int k = 0; k < 2 * NB; ++k) { const int32_t a = P.d_gdof[(size_t)cgroup[c] * 2 * NB + k]; if (a >= 0) P.g_cidx[gpos[a]++] = (int32_t)(c * 2 * NB + k); }
+    P.ok = true;
+}
+}  // namespace
+
 void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n_global, const double* w_local,
                         const BarrierDesc& bar, ElementPlan& P, bool want_hessian, int64_t out0, int64_t out1, bool allow_agg) {
     P.ok = false;
@@ -206,7 +388,11 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
             ++run;
         }
     }
-    if (B < 1 || B > 8) { P.why = "element block size not supported by the fused kernels (1..8)"; return; }
+    if (B > 8) {   // large elements (fem3d Q3): the dense path where it pays, else the general CSR kernels
+        build_dense_plan(D, R, n_global, bar, P, want_hessian, B, var, dim, nu, out0, out1);
+        return;
+    }
+    if (B < 1) { P.why = "element block size not supported by the fused kernels (1..8)"; return; }
     const int64_t E = nloc / B;
     P.B = (int)B; P.dim = dim; P.NU = nu; P.ND = ND; P.slack = slack;
     P.E = E; P.nloc = nloc; P.m = m;

@@ -47,6 +47,17 @@ struct ElementPlan {
     bool slack = false, fine = false;   // slack: three-variable table [u.id; u.d*; v1.id; v2.id] (modes 1 and 2)
     int mode = 0;                       // 0 one cone, 1 feasibility (cone on s + tau, -log(1+tau)), 2 two cones (parabolic)
     int64_t E = 0, nloc = 0, m = 0;
+    // ---- dense path (kernels_dense.cuh): elements with more than 8 nodes whose level operators have long rows - the
+    // coarse levels of fem3d's Q3 hexahedra, where every fine point touches up to 64 unknowns per variable and the
+    // product lists of the CSR path explode.  Consecutive fine elements are grouped (greedily, <= DENSE_NB dofs per
+    // variable: the children of one coarse element), the operators are stored as DENSE rows over the group's dofs, and
+    // a group's points are cut into chunks; one CTA contracts a chunk into full uu / us / ss blocks
+    // (sel record = 3 * DENSE_NB^2 doubles per chunk), which the ordinary gather replays into R'HR.
+    bool dense = false;
+    int64_t d_ngroups = 0, d_nchunks = 0;
+    std::vector<int32_t> d_gdof;   // [group][2][DENSE_NB] global dof or -1
+    std::vector<int64_t> d_chunk;  // [chunk][3] = {group, first point, end point} (local row ids)
+    std::vector<double> d_rows;    // [point][dim + 2][DENSE_NB]: derivative rows (u), u.id row, s.id row over the group's dofs
     int agg = 1;                   // coarse levels: aligned groups of `agg` consecutive elements share all their dofs (children of
                                    // one coarse element): one slot / gradient record per group (kernels.cuh agg_reduce)
     int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (whole range unless sharded)
@@ -89,6 +100,8 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
 // numbering of R = blockdiag(R_u, R_s) would force.  Only the three objective scalars
 // are summed across ranks (peer-memory words with embedded epoch flags, kernels_dist.cuh).
 constexpr int DIST_MAX_RANKS = 16;
+constexpr int DENSE_NB = 64;       // dofs per variable of a dense group (Q3 hexahedron: 4^3 nodes)
+constexpr int DENSE_CHUNK = 512;   // points per chunk (a multiple of the kernel's point tile)
 
 // Quadrature rows (whole elements) rank `rank` evaluates: every element with a dof in its output block
 // [out_part[rank], out_part[rank+1]).  The objective scalars of an element are counted by exactly one of the ranks

@@ -125,3 +125,12 @@ def test_objective_only_call_has_the_bits_of_the_full_assembly(gpu_ctx, gen, L, 
     for rep in range(3):
         one = plan.assemble_host(pr["s"], Dz0, pr["c"], 0.7, 1)["scal"].copy()
         assert np.array_equal(one, full), (one, full)
+
+
+@pytest.mark.parametrize("L,level,p", [(2, 0, 1.0), (3, 0, 1.0), (3, 1, 1.0), (3, 1, 1.5), (4, 2, 1.0)])
+def test_fem3d_coarse_levels_dense_path(gpu_ctx, L, level, p):
+    """coarse levels of fem3d's Q3 hexahedra: every fine point touches up to 64 unknowns per variable - the dense
+    contraction kernel (kernels_dense.cuh: per chunk of a coarse element full uu / us / ss blocks, then the ordinary
+    gather) instead of product lists (reference problem data src/MultiGridBarrierMPI.jl:735-745)"""
+    plan, _ = check_against_oracle(gpu_ctx, mgb_b200.fem3d(L), p, t=0.9, level=level)
+    assert plan.info["path"] == capi.PATH_ELEMENT and plan.info["nodes_per_element"] == 64

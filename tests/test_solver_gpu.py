@@ -46,3 +46,10 @@ def test_feasibility_phase_runs_and_matches():
     sol_g, sol_o = _compare(mgb_b200.fem2d(2), 1.0, g=g)
     assert sol_g.SOL_feasibility is not None and sol_o.SOL_feasibility is not None
     assert np.array_equal(sol_g.SOL_feasibility["its"], sol_o.SOL_feasibility["its"])
+
+
+def test_fem3d_L3_whole_solve_uses_dense_coarse_levels():
+    """config C4 as a whole solve: fem3d (Q3 hexahedra, reference problem data src/MultiGridBarrierMPI.jl:735-745) on a
+    3-level hierarchy - coarse levels on the dense contraction path, the finest on the CSR path - with the oracle's
+    t-schedule, Newton counts per level and iterate"""
+    _compare(mgb_b200.fem3d(3), 1.0)
