@@ -519,7 +519,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
             "clocks": clocks,
             "e2e": dict({"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": int(ginfo["m"] * 8),
                          "d2h_bytes_per_step": int((n_g + n_h + 4) * 8), "host_memory": "pinned / page-locked"}, **e2e_extra),
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "pdl_active": capi.pdl_active(), "cuda_graph": (plan.graph_stats() if not sharded else None),
             "parity": None if parity is None else {"f0_rel": float(mx[4].cpu()), "grad_rel": float(mx[5].cpu()), "hess_rel": float(mx[6].cpu()),
                                                     "against": "CPU oracle on the same inputs; max over ranks of each rank's owned rows",
                                                     "tolerance": 1e-12},
@@ -586,7 +586,7 @@ def main():
         line = {"metric": METRIC, "value": rec["value"], "unit": "ms", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": rec["ms_per_step"], "higher_is_better": False, "scaling": "strong",
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic"}
-        line.update({k: rec[k] for k in ("config", "clocks", "e2e", "gpu_launches", "parity", "roofline", "wall_s_timed_region")})
+        line.update({k: rec[k] for k in ("config", "clocks", "e2e", "gpu_launches", "pdl_active", "cuda_graph", "parity", "roofline", "wall_s_timed_region")})
         if subs:
             line["sub_records"] = subs
         if world == 1 and args.cpu_reps > 0:

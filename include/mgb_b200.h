@@ -294,6 +294,9 @@ int mgb_time_assemble(mgb_plan* plan, const double* s_dev, const double* Dz0_dev
 
 /* number of kernel launches issued through this library since load (bench.py's gpu_launches) */
 int64_t mgb_launch_count(void);
+/* 1 while dependent kernels are launched as programmatic dependent launches (PDL); 0 after MGB_NO_PDL=1 or after the
+ * driver refused the launch attribute once (the library then keeps plain launches for the rest of the process) */
+int mgb_pdl_active(void);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,7 @@ EXPORTS = [
     "mgb_spmat_create", "mgb_spmat_destroy", "mgb_spmat_mv", "mgb_gather_idx", "mgb_scatter_add_idx", "mgb_segsum_idx",
     "mgb_plan_create_rows", "mgb_dist_plan_create", "mgb_dist_info", "mgb_dist_rows", "mgb_dist_pattern", "mgb_dist_window",
     "mgb_dist_export", "mgb_dist_attach", "mgb_dist_attach_local", "mgb_dist_begin", "mgb_dist_end", "mgb_dist_assemble", "mgb_dist_s_publish", "mgb_dist_s_wait", "mgb_dist_assemble_s", "mgb_copy_to_host", "mgb_host_register", "mgb_host_unregister",
-    "mgb_graph_begin", "mgb_graph_end", "mgb_graph_launch", "mgb_graph_destroy", "mgb_graph_stats",
+    "mgb_graph_begin", "mgb_graph_end", "mgb_graph_launch", "mgb_graph_destroy", "mgb_graph_stats", "mgb_pdl_active",
 ]
 
 
@@ -187,6 +187,11 @@ def host_unregister(a: np.ndarray):
 
 def launch_count() -> int:
     return int(load().mgb_launch_count())
+
+
+def pdl_active() -> bool:
+    """programmatic dependent launches in use (False: MGB_NO_PDL=1 or the driver refused the attribute once)"""
+    return bool(load().mgb_pdl_active())
 
 
 class Context:

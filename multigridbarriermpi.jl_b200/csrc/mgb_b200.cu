@@ -26,6 +26,9 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<int64_t> g_launches{0};
+// programmatic dependent launches (PDL) are used until a launch with the attribute is refused once; MGB_NO_PDL=1
+// disables them for A/B runs.  mgb_pdl_active() reports the current state (no silent downgrade).
+bool g_pdl_ok = getenv("MGB_NO_PDL") == nullptr;
 
 int fail(const std::string& msg) {
     g_err = msg;
@@ -337,7 +340,6 @@ void launch_elem(const mgb_plan* pl, const mgb::ElemParams& P, int flags) {
 // Launch as a programmatic dependent of the previous kernel in the stream (PDL): the kernel may start while
 // the element kernel's last wave drains and blocks at griddepcontrol.wait until its records are complete.
 // Falls back to a plain launch when the attribute is rejected (MGB_NO_PDL=1 disables it for A/B runs).
-bool g_pdl_ok = getenv("MGB_NO_PDL") == nullptr;
 
 template <class Params>
 void launch_dependent(void (*kernel)(Params), unsigned grid, unsigned block, cudaStream_t st, const Params& params, bool allow_pdl) {
@@ -595,6 +597,7 @@ extern "C" {
 const char* mgb_last_error(void) { return g_err.c_str(); }
 int mgb_version(void) { return 100; }
 int64_t mgb_launch_count(void) { return g_launches.load(); }
+int mgb_pdl_active(void) { return g_pdl_ok ? 1 : 0; }
 
 int mgb_ctx_create(int device, void* stream, mgb_ctx** out) {
     try {
