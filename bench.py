@@ -12,9 +12,10 @@ apply_D -> barrier F/F1/F2 -> gradient -> Hessian numeric phase -> R'HR values (
   cpu_baseline / --impl reference: the CPU oracle restatement (the Julia reference cannot run here:
             no julia/mpiexec in the image) timed on the host cores.
 
-N > 1 (torchrun): owner-computes sharding - the rows of R'HR and the gradient entries are split over the ranks
-(HPCSparseArrays row partition), a rank evaluates every element touching its rows and completes them locally; only
-the objective scalars cross NVLink (peer-memory words, written and awaited inside the gather kernel, all inside the
+N > 1 (torchrun): owner-computes sharding - the rows of R'HR and the gradient entries are split over the ranks (rank r
+owns block r of every variable: the unknowns are renumbered rank-major at the boundary, `--ownership contiguous` keeps
+the reference's stacked numbering instead), a rank evaluates every element touching its rows and completes them
+locally; only the objective scalars cross NVLink (peer-memory words, written and awaited inside the gather kernel, all inside the
 timed region).  The fixed L=8 problem is split, so scaling = "strong"; `sub_records` adds L=9 on the same GPUs.
 Every line carries `parity`: the buffers that were just timed against the CPU oracle (max over ranks).
 """
@@ -276,10 +277,13 @@ def oracle_outputs(pr, t):
     return O.f0(*args), O.f1(*args), O.f2(*args).tocsr()
 
 
-def parity_block(pr, t, f0, grad_own, hval_own, rowptr, colidx, lo, hi):
-    """relative errors of the buffers that were just timed against the oracle's rows [lo, hi)"""
+def parity_block(pr, t, f0, grad_own, hval_own, rowptr, colidx, lo, hi, perm=None):
+    """relative errors of the buffers that were just timed against the oracle's rows [lo, hi) (``perm``: the plan's
+    renumbering of the unknowns, new -> old: the oracle's outputs are renumbered the same way first)"""
     import scipy.sparse as sp
     f0_o, g_o, H_o = oracle_outputs(pr, t)
+    if perm is not None:
+        g_o, H_o = g_o[perm], H_o[perm][:, perm].tocsr()
     m = H_o.shape[0]
     Hc = sp.csr_matrix((hval_own, colidx.astype(np.int64), rowptr.astype(np.int64)), shape=(hi - lo, m))
     hn, gn = abs(H_o).max(), np.abs(g_o).max()
@@ -301,7 +305,8 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
     sharded = world > 1
     t_plan = time.perf_counter()
     if sharded:
-        plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], B, rank, world)
+        plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"], B, rank, world,
+                                      colocate=args.ownership == "colocated")
         rows = plan.rows
     else:
         plan = capi.Plan(ctx, pr["D"], pr["R"], geom.x, geom.w, pr["idx"], pr["p"])
@@ -309,7 +314,8 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
     t_plan = time.perf_counter() - t_plan
     flags = capi.WANT_F0 | capi.WANT_GRAD | capi.WANT_HESS
     f64 = torch.float64
-    s_d = torch.from_numpy(pr["s"]).to(dev)
+    perm = plan.perm if sharded else None    # rank-major renumbering of the unknowns (dist.colocated_partition)
+    s_d = torch.from_numpy(pr["s"] if perm is None else pr["s"][perm]).to(dev)
     Dz0_d = torch.from_numpy(np.ascontiguousarray(pr["Dz0"][rows].T)).to(dev)   # (nD, n_local) = column-major n_local x nD
     c_d = torch.from_numpy(np.ascontiguousarray(pr["c"][rows].T)).to(dev)
     n_h = plan.dinfo["n_own_h"] if sharded else plan.nnzH
@@ -392,7 +398,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         lo, hi = 0, plan.m
         scal_now, g_now, h_now = scal_d.cpu().numpy(), grad_d.cpu().numpy(), hval_d[:n_h].cpu().numpy()
     rp, ci = plan.pattern()
-    parity = parity_block(pr, args.t, scal_now[0], g_now, h_now, rp, ci, lo, hi) if not args.no_parity else None
+    parity = parity_block(pr, args.t, scal_now[0], g_now, h_now, rp, ci, lo, hi, perm) if not args.no_parity else None
     # per-kernel split (separate pass, not part of `value`): this rank's element / gather kernels
     # (N > 1: the rank's own two kernels without the cross-rank scalar exchange)
     _, ms_elem, ms_gather = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d,
@@ -429,7 +435,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         e2e_extra["path"] = "mgb_assemble_host on arrays page-locked once with mgb_host_register"
     else:
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
-        s_h = pin(pr["s"])
+        s_h = pin(pr["s"] if perm is None else pr["s"][perm])
         hval_h = torch.empty(max(n_h, 1), dtype=f64).pin_memory()
         grad_h = torch.empty(max(n_g, 1), dtype=f64).pin_memory()
         scal_h = torch.empty(4, dtype=f64).pin_memory()
@@ -511,9 +517,13 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
                        "path": "element" if info["path"] == 1 else "csr", "plan_seconds": round(t_plan, 3),
                        "rows_evaluated_max_rank": int(mx[7].cpu()), "rows_total": n, "owned_hessian_entries_max_rank": int(mx[8].cpu()),
                        "ms_from_row_distributed_s": (float(mx[9].cpu()) if sharded else None),
+                       "ownership": None if not sharded else args.ownership,
                        "multi_gpu": None if not sharded else (
-                           "owner-computes: a rank evaluates every element touching its output rows (each element on about "
-                           "two ranks) and completes its rows of R'HR / block of g locally; only the 3 objective scalars cross "
+                           "owner-computes: a rank evaluates every element touching its output rows "
+                           + ("(unknowns renumbered rank-major - rank r owns block r of u AND of s - so that is E/P elements "
+                              "plus a thin halo) " if perm is not None else
+                              "(contiguous blocks of the stacked [u | s] unknowns: each element on about two ranks) ") +
+                           "and completes its rows of R'HR / block of g locally; only the 3 objective scalars cross "
                            "NVLink, as epoch-tagged peer-memory words written and awaited inside the gather kernel; no NCCL on "
                            "the data path")},
             "clocks": clocks,
@@ -548,6 +558,8 @@ def main():
     ap.add_argument("--cpu-reps", type=int, default=3)
     ap.add_argument("--cpu-procs", type=int, default=0, help="processes for the CPU restatement (0 = all cores)")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed buffers")
+    ap.add_argument("--ownership", default="colocated", choices=["colocated", "contiguous"],
+                    help="N > 1: rank r owns block r of every variable (unknowns renumbered rank-major) / a contiguous block of the stacked unknowns")
     ap.add_argument("--sub", default=None, help="comma-separated extra levels timed as sub-records (default: 9 when N > 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

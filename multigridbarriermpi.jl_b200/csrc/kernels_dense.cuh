@@ -6,9 +6,10 @@
 //     points through a two-stage shared-memory ring filled by 1-D bulk copies (TMA: cp.async.bulk + mbarrier);
 //   * phase 1 (two points per warp): apply_D as 64-long dot products (lane = 2 dofs, shuffle reduction), the barrier
 //     at the two points on lanes 0 and 1 side by side, w .* F1 / F2 into shared memory, objective partials;
-//   * phase 2: T = (w F2_qq) A, bs = A' (w F2_qs), hs = (w F2_ss) I_s per point, then a register-tiled contraction:
-//     thread (ty, tx) owns the 4 x 4 tiles [4ty.., 4tx..] of  uu += A' T,  us += bs' I_s,  ss += I_s' hs  over the
-//     chunk's points (48 accumulators), the gradient rides along (threads 0..127, one unknown each);
+//   * phase 2: T = (w F2_qq) A, bs = A' (w F2_qs), hs = (w F2_ss) I_s per point, then the three contractions
+//     uu += A' T,  us += bs' I_s,  ss += I_s' hs  on the FP64 tensor cores (mma.sync m8n8k4 = SASS DMMA.8x8x4): warp w
+//     owns rows [8w, 8w+8) of each 64 x 64 block (8 column tiles, 48 accumulators per lane); the one dense contraction
+//     of this path, and the one place where tensor cores pay.  The gradient rides along (threads 0..127);
 //   * the chunk's full blocks (3 x 64 x 64 doubles) and gradient record go to `sel` / `rel`; the ordinary gather
 //     kernels replay them into the CSR values of R'HR and into g (contribution lists built at plan time).
 // Fixed summation order (points in order inside a chunk, chunks in order in the gather): bit-reproducible.
@@ -22,21 +23,29 @@
 namespace mgb {
 
 constexpr int DN = DENSE_NB;   // 64
+constexpr int DS = DENSE_STRIDE;   // 68: row stride (doubles) of every operand row in shared AND global memory - rows k, k+1,
+                                   // k+2, k+3 of an MMA fragment then fall on distinct 8-byte bank pairs (4t + g mod 16)
 constexpr int DPT = 16;        // points per tile
 constexpr int DNR = 5;         // rows per point: dx dy dz u.id s.id  (dim = 3)
-constexpr int D_TILE_BYTES = DPT * DNR * DN * 8;   // 40 KB
+constexpr int D_TILE_BYTES = DPT * DNR * DS * 8;   // 42.5 KB
 constexpr int D_SMEM = 2 * D_TILE_BYTES            // record ring
                      + 2 * DN * 8                  // unknowns
                      + DPT * 16 * 8                // per point: w F2 (10), w (F1 + t c) (5), pad
-                     + DPT * 3 * DN * 8            // T
-                     + 2 * DPT * DN * 8            // bs, hs
+                     + DPT * 3 * DS * 8            // T
+                     + 2 * DPT * DS * 8            // bs, hs
                      + 64;                         // mbarriers
+
+// D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (SASS DMMA.8x8x4).  Fragment layout (g = lane / 4, t = lane % 4):
+// a = A[g][t], b = B[t][g], c0 / c1 = C[g][2t], C[g][2t + 1].
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
 
 struct DenseParams {
     int64_t nchunks, nloc;
     const int64_t* chunk;   // [nchunks][3] = {group, p0, p1}
     const int32_t* gdof;    // [ngroups][2][DN]
-    const double* rows;     // [nloc][DNR][DN]
+    const double* rows;     // [nloc][DNR][DS]
     const double* w;        // nloc
     const double* s;        // m
     const double* Dz0;      // nloc x 5 or null
@@ -75,10 +84,10 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
     double* zu = reinterpret_cast<double*>(dsm + 2 * D_TILE_BYTES);
     double* zs = zu + DN;
     double* pw = zs + DN;                  // [DPT][16]
-    double* Tt = pw + DPT * 16;            // [DPT][3][DN]
-    double* bs = Tt + DPT * 3 * DN;        // [DPT][DN]
-    double* hs = bs + DPT * DN;            // [DPT][DN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + DPT * DN);
+    double* Tt = pw + DPT * 16;            // [DPT * 3][DS]
+    double* bs = Tt + DPT * 3 * DS;        // [DPT][DS]
+    double* hs = bs + DPT * DS;            // [DPT][DS]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + DPT * DS);
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ch = blockIdx.x;
@@ -96,28 +105,27 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
     __syncthreads();
     auto issue = [&](int tl) {   // tile tl -> stage tl & 1 (thread 0)
         const int64_t q0 = p0 + (int64_t)tl * DPT;
-        const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DN * 8);
+        const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DS * 8);
         d_mbar_expect_tx(bars + (tl & 1), bytes);
-        d_bulk_g2s(tile0 + (size_t)(tl & 1) * (DPT * DNR * DN), P.rows + q0 * (DNR * DN), bytes, bars + (tl & 1));
+        d_bulk_g2s(tile0 + (size_t)(tl & 1) * (DPT * DNR * DS), P.rows + q0 * (DNR * DS), bytes, bars + (tl & 1));
     };
     if (tid == 0 && ntile > 0) issue(0);
 
-    const int ty = tid >> 4, tx = tid & 15, a0 = 4 * ty, b0 = 4 * tx;
-    double uu[4][4], us[4][4], ss[4][4];
+    // warp w owns output rows [8w, 8w + 8) of the three 64 x 64 blocks: 8 column tiles of 8, two accumulators per lane each
+    const int fg = lane >> 2, ft = lane & 3;
+    double uu[8][2], us[8][2], ss[8][2];
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) uu[i][j] = us[i][j] = ss[i][j] = 0.0;
+    for (int i = 0; i < 8; ++i) uu[i][0] = uu[i][1] = us[i][0] = us[i][1] = ss[i][0] = ss[i][1] = 0.0;
     double gacc = 0.0, sc0 = 0.0, sc1 = 0.0, sc2 = 0.0;
 
     for (int tl = 0; tl < ntile; ++tl) {
         __syncthreads();   // the other stage and T / bs / hs / pw are free again
         if (tid == 0 && tl + 1 < ntile) issue(tl + 1);
-        double* tile = tile0 + (size_t)(tl & 1) * (DPT * DNR * DN);
+        double* tile = tile0 + (size_t)(tl & 1) * (DPT * DNR * DS);
         const int npt = (int)min((int64_t)DPT, npts - (int64_t)tl * DPT);
         while (!d_mbar_try_wait(bars + (tl & 1), (unsigned)((tl >> 1) & 1))) {}
         if (npt < DPT)   // the tail of a partial tile was not loaded: it must not contribute (0 * stale NaN)
-            for (int k = npt * DNR * DN + tid; k < DPT * DNR * DN; k += 256) tile[k] = 0.0;
+            for (int k = npt * DNR * DS + tid; k < DPT * DNR * DS; k += 256) tile[k] = 0.0;
         // ---- phase 1: apply_D + barrier, two points per warp.  All lanes form the dot products of both points (lane = 2
         // dofs, xor-shuffle sums leave the totals on every lane); then lane 0 evaluates the first point and lane 1 the
         // second side by side - the barrier is a ~400-instruction dependent chain, running the two as SIMD lanes
@@ -128,10 +136,10 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
             for (int pp = 0; pp < 2; ++pp) {
                 const int pt = 2 * warp + pp;
                 const bool actp = pt < npt;
-                const double* tp = tile + pt * (DNR * DN);
+                const double* tp = tile + pt * (DNR * DS);
 #pragma unroll
-                for (int r = 0; r < 4; ++r) d[pp][r] = actp ? tp[r * DN + lane] * zu[lane] + tp[r * DN + lane + 32] * zu[lane + 32] : 0.0;
-                d[pp][4] = actp ? tp[4 * DN + lane] * zs[lane] + tp[4 * DN + lane + 32] * zs[lane + 32] : 0.0;
+                for (int r = 0; r < 4; ++r) d[pp][r] = actp ? tp[r * DS + lane] * zu[lane] + tp[r * DS + lane + 32] * zu[lane + 32] : 0.0;
+                d[pp][4] = actp ? tp[4 * DS + lane] * zs[lane] + tp[4 * DS + lane + 32] * zs[lane + 32] : 0.0;
             }
 #pragma unroll
             for (int mk = 16; mk >= 1; mk >>= 1)
@@ -185,65 +193,58 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
             for (int idx = tid; idx < DPT * DN; idx += 256) {
                 const int pt = idx / DN, b = idx % DN;
                 const double* o = pw + pt * 16;
-                const double* tp = tile + pt * (DNR * DN);
-                const double A0 = tp[b], A1 = tp[DN + b], A2 = tp[2 * DN + b];
-                Tt[(pt * 3 + 0) * DN + b] = o[0] * A0 + o[1] * A1 + o[2] * A2;
-                Tt[(pt * 3 + 1) * DN + b] = o[1] * A0 + o[3] * A1 + o[4] * A2;
-                Tt[(pt * 3 + 2) * DN + b] = o[2] * A0 + o[4] * A1 + o[5] * A2;
-                bs[pt * DN + b] = o[6] * A0 + o[7] * A1 + o[8] * A2;
-                hs[pt * DN + b] = o[9] * tp[4 * DN + b];
+                const double* tp = tile + pt * (DNR * DS);
+                const double A0 = tp[b], A1 = tp[DS + b], A2 = tp[2 * DS + b];
+                Tt[(pt * 3 + 0) * DS + b] = o[0] * A0 + o[1] * A1 + o[2] * A2;
+                Tt[(pt * 3 + 1) * DS + b] = o[1] * A0 + o[3] * A1 + o[4] * A2;
+                Tt[(pt * 3 + 2) * DS + b] = o[2] * A0 + o[4] * A1 + o[5] * A2;
+                bs[pt * DS + b] = o[6] * A0 + o[7] * A1 + o[8] * A2;
+                hs[pt * DS + b] = o[9] * tp[4 * DS + b];
             }
             __syncthreads();
-        }
-        // ---- phase 2b: register-tiled contraction over the tile's points; gradient on threads 0..127
-        for (int pt = 0; pt < DPT; ++pt) {
-            const double* tp = tile + pt * (DNR * DN);
-            if (WH) {
-                double Aa[3][4], Tb[3][4], ba[4], Ib[4], Ia[4], hb[4];
+            // ---- phase 2b: the three contractions of the tile on the FP64 tensor cores.  K runs over (point, derivative)
+            // for uu (48 = 12 steps of 4) and over the points for us / ss (16 = 4 steps); per step one A fragment and
+            // eight B fragments (8-byte shared loads, conflict free by the row stride) feed eight DMMAs.
+            const int arow = 8 * warp + fg;
+#pragma unroll 4
+            for (int kk = 0; kk < 3 * DPT / 4; ++kk) {
+                const int k = 4 * kk + ft, pt = k / 3, j = k - 3 * pt;
+                const double a = tile[(pt * DNR + j) * DS + arow];
+                const double* brow = Tt + k * DS + fg;
 #pragma unroll
-                for (int j = 0; j < 3; ++j) {
-                    const double2 x0 = *reinterpret_cast<const double2*>(tp + j * DN + a0), x1 = *reinterpret_cast<const double2*>(tp + j * DN + a0 + 2);
-                    Aa[j][0] = x0.x; Aa[j][1] = x0.y; Aa[j][2] = x1.x; Aa[j][3] = x1.y;
-                    const double2 y0 = *reinterpret_cast<const double2*>(Tt + (pt * 3 + j) * DN + b0), y1 = *reinterpret_cast<const double2*>(Tt + (pt * 3 + j) * DN + b0 + 2);
-                    Tb[j][0] = y0.x; Tb[j][1] = y0.y; Tb[j][2] = y1.x; Tb[j][3] = y1.y;
-                }
-                {
-                    const double2 x0 = *reinterpret_cast<const double2*>(bs + pt * DN + a0), x1 = *reinterpret_cast<const double2*>(bs + pt * DN + a0 + 2);
-                    ba[0] = x0.x; ba[1] = x0.y; ba[2] = x1.x; ba[3] = x1.y;
-                    const double2 y0 = *reinterpret_cast<const double2*>(tp + 4 * DN + b0), y1 = *reinterpret_cast<const double2*>(tp + 4 * DN + b0 + 2);
-                    Ib[0] = y0.x; Ib[1] = y0.y; Ib[2] = y1.x; Ib[3] = y1.y;
-                    const double2 u0 = *reinterpret_cast<const double2*>(tp + 4 * DN + a0), u1 = *reinterpret_cast<const double2*>(tp + 4 * DN + a0 + 2);
-                    Ia[0] = u0.x; Ia[1] = u0.y; Ia[2] = u1.x; Ia[3] = u1.y;
-                    const double2 v0 = *reinterpret_cast<const double2*>(hs + pt * DN + b0), v1 = *reinterpret_cast<const double2*>(hs + pt * DN + b0 + 2);
-                    hb[0] = v0.x; hb[1] = v0.y; hb[2] = v1.x; hb[3] = v1.y;
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uu[i][j] = fma(Aa[0][i], Tb[0][j], fma(Aa[1][i], Tb[1][j], fma(Aa[2][i], Tb[2][j], uu[i][j])));
-                        us[i][j] = fma(ba[i], Ib[j], us[i][j]);
-                        ss[i][j] = fma(Ia[i], hb[j], ss[i][j]);
-                    }
+                for (int nt = 0; nt < 8; ++nt) dmma884(uu[nt][0], uu[nt][1], a, brow[8 * nt]);
             }
-            if (WG && tid < 2 * DN) {
+#pragma unroll
+            for (int kk = 0; kk < DPT / 4; ++kk) {
+                const int pt = 4 * kk + ft;
+                const double a1 = bs[pt * DS + arow], a2 = tile[(pt * DNR + 4) * DS + arow];
+                const double* b1 = tile + (pt * DNR + 4) * DS + fg;
+                const double* b2 = hs + pt * DS + fg;
+#pragma unroll
+                for (int nt = 0; nt < 8; ++nt) {
+                    dmma884(us[nt][0], us[nt][1], a1, b1[8 * nt]);
+                    dmma884(ss[nt][0], ss[nt][1], a2, b2[8 * nt]);
+                }
+            }
+        }
+        // ---- gradient on threads 0..127 (one unknown each)
+        if (WG && tid < 2 * DN) {
+            for (int pt = 0; pt < DPT; ++pt) {
+                const double* tp = tile + pt * (DNR * DS);
                 const double* o = pw + pt * 16;
-                if (tid < DN) gacc += tp[tid] * o[11] + tp[DN + tid] * o[12] + tp[2 * DN + tid] * o[13] + tp[3 * DN + tid] * o[10];
-                else gacc += tp[4 * DN + tid - DN] * o[14];
+                if (tid < DN) gacc += tp[tid] * o[11] + tp[DS + tid] * o[12] + tp[2 * DS + tid] * o[13] + tp[3 * DS + tid] * o[10];
+                else gacc += tp[4 * DS + tid - DN] * o[14];
             }
         }
     }
-    // ---- the chunk's records
+    // ---- the chunk's records: lane holds C[g][2t], C[g][2t + 1] of every column tile
     if (WH) {
-        double* rec = P.sel + ch * (int64_t)(3 * DN * DN);
+        double* rec = P.sel + ch * (int64_t)(3 * DN * DN) + (8 * warp + fg) * DN + 2 * ft;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            double2* d0 = reinterpret_cast<double2*>(rec + (a0 + i) * DN + b0);
-            d0[0] = make_double2(uu[i][0], uu[i][1]); d0[1] = make_double2(uu[i][2], uu[i][3]);
-            double2* d1 = reinterpret_cast<double2*>(rec + DN * DN + (a0 + i) * DN + b0);
-            d1[0] = make_double2(us[i][0], us[i][1]); d1[1] = make_double2(us[i][2], us[i][3]);
-            double2* d2 = reinterpret_cast<double2*>(rec + 2 * DN * DN + (a0 + i) * DN + b0);
-            d2[0] = make_double2(ss[i][0], ss[i][1]); d2[1] = make_double2(ss[i][2], ss[i][3]);
+        for (int nt = 0; nt < 8; ++nt) {
+            *reinterpret_cast<double2*>(rec + 8 * nt) = make_double2(uu[nt][0], uu[nt][1]);
+            *reinterpret_cast<double2*>(rec + DN * DN + 8 * nt) = make_double2(us[nt][0], us[nt][1]);
+            *reinterpret_cast<double2*>(rec + 2 * DN * DN + 8 * nt) = make_double2(ss[nt][0], ss[nt][1]);
         }
     }
     if (WG && tid < 2 * DN) P.rel[ch * (2 * DN) + tid] = gacc;

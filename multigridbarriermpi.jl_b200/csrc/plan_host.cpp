@@ -225,7 +225,7 @@ void build_dense_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n
     if (nch * (int64_t)P.lay.NS > INT32_MAX) { P.dense = false; P.why = "dense slot buffer exceeds int32 indexing"; return; }
     // dense operator rows over the group's dofs; per-point support masks (two 64-bit words: u dofs | s dofs)
     const int NR = dim + 2;   // rows per point: derivative ops (1..dim), u.id (op 0), s.id (op dim+1)
-    P.d_rows.assign((size_t)nloc * NR * NB, 0.0);
+    P.d_rows.assign((size_t)nloc * NR * DENSE_STRIDE, 0.0);
     std::vector<uint64_t> pmask((size_t)nloc * 2, 0);
     for (int64_t g = 0; g < ng; ++g) {
         const std::vector<int32_t>* gs[2] = {&gset[(size_t)g * 2], &gset[(size_t)g * 2 + 1]};
@@ -235,7 +235,7 @@ void build_dense_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n
                 const int r = (k == 0) ? dim : (k <= dim ? k - 1 : dim + 1);
                 for (int64_t q = Ek[k].ptr[i]; q < Ek[k].ptr[i + 1]; ++q) {
                     const int la = (int)(std::lower_bound(gs[v]->begin(), gs[v]->end(), Ek[k].idx[q]) - gs[v]->begin());
-                    P.d_rows[((size_t)i * NR + r) * NB + la] = Ek[k].val[q];
+                    P.d_rows[((size_t)i * NR + r) * DENSE_STRIDE + la] = Ek[k].val[q];
                     pmask[(size_t)i * 2 + v] |= 1ull << la;
                 }
             }

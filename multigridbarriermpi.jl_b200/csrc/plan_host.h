@@ -57,7 +57,7 @@ struct ElementPlan {
     int64_t d_ngroups = 0, d_nchunks = 0;
     std::vector<int32_t> d_gdof;   // [group][2][DENSE_NB] global dof or -1
     std::vector<int64_t> d_chunk;  // [chunk][3] = {group, first point, end point} (local row ids)
-    std::vector<double> d_rows;    // [point][dim + 2][DENSE_NB]: derivative rows (u), u.id row, s.id row over the group's dofs
+    std::vector<double> d_rows;    // [point][dim + 2][DENSE_STRIDE]: derivative rows (u), u.id row, s.id row over the group's dofs
     int agg = 1;                   // coarse levels: aligned groups of `agg` consecutive elements share all their dofs (children of
                                    // one coarse element): one slot / gradient record per group (kernels.cuh agg_reduce)
     int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (whole range unless sharded)
@@ -101,6 +101,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
 // are summed across ranks (peer-memory words with embedded epoch flags, kernels_dist.cuh).
 constexpr int DIST_MAX_RANKS = 16;
 constexpr int DENSE_NB = 64;       // dofs per variable of a dense group (Q3 hexahedron: 4^3 nodes)
+constexpr int DENSE_STRIDE = 68;   // doubles between consecutive dense rows (64 + 4 padding: bank-conflict-free MMA fragments)
 constexpr int DENSE_CHUNK = 512;   // points per chunk (a multiple of the kernel's point tile)
 
 // Quadrature rows (whole elements) rank `rank` evaluates: every element with a dof in its output block

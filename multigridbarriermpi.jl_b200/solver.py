@@ -49,6 +49,10 @@ class LevelState:
         M = prob.M
         dev = prob.device
         self.sharded = False
+        # the level's unknowns in the numbering this object works in: a sharded level renumbers them rank-major
+        # (dist.colocated_partition; R_level = R[:, perm]) - Newton on s -> f(z + R_level s) does not care, and z itself
+        # lives in the fine space
+        R_level = M.R_fine[J]
         if prob.nranks > 1:
             from . import dist as mdist
             try:
@@ -56,6 +60,7 @@ class LevelState:
                                                    prob.rank, prob.nranks, group=prob.group, slack=prob.slack,
                                                    idx2=prob.idx2, p2=prob.p2)
                 self.sharded = True
+                R_level = self.plan.R
             except capi.MgbError as exc:
                 # only the levels on the element path with thread-per-entry gather (the fine ones, where the work
                 # is) are sharded; any other level - coarse levels, fem3d's Q3 elements and every operator table
@@ -67,7 +72,7 @@ class LevelState:
         if self.sharded:
             # the replicated symbolic plan gives the global pattern the solve seam needs (owned row blocks are
             # contiguous, so the global value array is the concatenation of the ranks' owned values)
-            sym = capi.Plan(None, M.D, M.R_fine[J], M.x, M.w, prob.idx, prob.p, slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
+            sym = capi.Plan(None, M.D, R_level, M.x, M.w, prob.idx, prob.p, slack=prob.slack, idx2=prob.idx2, p2=prob.p2)
             rp, ci = sym.pattern()
             m, nnz = sym.m, sym.nnzH
             d = self.plan.dinfo
@@ -96,7 +101,7 @@ class LevelState:
         self.hg = torch.zeros(max(nnz, 1) + m, dtype=f64, device=dev)
         self.hval, self.grad = self.hg[: max(nnz, 1)], self.hg[max(nnz, 1):]
         self.scal = torch.zeros(4, dtype=f64, device=dev)
-        self.R = capi.SpMat(prob.ctx, M.R_fine[J])
+        self.R = capi.SpMat(prob.ctx, R_level)
         self.rowptr, self.colidx = rp.astype(np.int64), ci.astype(np.int64)
         # pinned host mirrors for the solve seam
         self.h_hval = torch.zeros(max(nnz, 1), dtype=f64).pin_memory()

@@ -22,11 +22,16 @@ torch.cuda.set_device(lr)
 dev = torch.device("cuda", lr)
 dist.init_process_group("nccl", device_id=dev)
 ctx = capi.Context(lr, torch.cuda.current_stream(dev).cuda_stream)
-for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
+for gen, L, colocate in (("fem2d", 4, True), ("fem2d", 6, True), ("fem2d", 5, False), ("fem1d", 7, True)):
     geom = getattr(mgb_b200, gen)(L)
     pr = problem(geom)
     n, m = geom.x.shape[0], pr["R"].shape[1]
-    plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, geom.block, rank, world)
+    plan = mdist.create_peer_plan(ctx, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, geom.block, rank, world,
+                                  colocate=colocate)
+    # colocate: the unknowns are renumbered rank-major (plan.perm, new -> old); the oracle keeps the reference's
+    # numbering and its outputs are renumbered for the comparison
+    perm = plan.perm if plan.perm is not None else np.arange(m)
+    assert (plan.perm is not None) == colocate
     d = plan.dinfo
     Dz0 = np.stack([Dk @ pr["z0"] for Dk in pr["D"]], axis=1)[plan.rows]
     cm = lambda a: torch.from_numpy(np.ascontiguousarray(a.T)).to(dev)
@@ -37,7 +42,7 @@ for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
         t = 0.8 + 0.05 * step
         if step:
             pr["s"] = pr["s"] + 1e-4 * rng.uniform(-1, 1, size=pr["s"].shape)   # same seed on every rank
-        s_d = torch.from_numpy(pr["s"]).to(dev)
+        s_d = torch.from_numpy(pr["s"][perm]).to(dev)
         if step % 2 == 1:   # row-distributed unknown: all-gather over NVLink peer memory inside the library
             s_own = s_d[d["own0"]: d["own1"]].clone()
             hp, gp, sp_ = plan.dist_assemble_s(s_own, Dz0_d, c_d, t, 7)
@@ -45,7 +50,7 @@ for gen, L in (("fem2d", 4), ("fem2d", 6), ("fem1d", 7)):
             hp, gp, sp_ = plan.dist_assemble(s_d, Dz0_d, c_d, t, 7)
         h_own, g_own, scal = ctx.to_host(hp, d["n_own_h"]), ctx.to_host(gp, d["n_own_g"]), ctx.to_host(sp_, 4)
         argsg = (pr["s"], pr["x"], pr["w"], t * pr["c"], pr["R"], pr["D"], pr["z0"], Q)
-        Hg, gg, f0g = O.f2(*argsg).tocsr(), O.f1(*argsg), O.f0(*argsg)
+        Hg, gg, f0g = O.f2(*argsg).tocsr()[perm][:, perm].tocsr(), O.f1(*argsg)[perm], O.f0(*argsg)
         lo, hi = d["own0"], d["own1"]
         orp, oci = plan.own_pattern()
         Hown = sp.csr_matrix((h_own, oci.astype(np.int64), orp.astype(np.int64)), shape=(hi - lo, m))

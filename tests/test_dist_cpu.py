@@ -49,6 +49,47 @@ def test_owned_patterns_tile_the_global_pattern(gen, L, slack, nranks):
     assert np.array_equal(np.sort(np.concatenate(prim_all)), np.arange(n))
 
 
+@pytest.mark.parametrize("gen,L,slack", [("fem2d", 4, False), ("fem1d", 6, False), ("fem2d", 3, True)])
+@pytest.mark.parametrize("nranks", [2, 3, 4])
+def test_colocated_ownership_is_a_renumbering_and_halves_the_element_work(gen, L, slack, nranks):
+    """dist.colocated_partition: rank r owns block r of EVERY variable (unknowns renumbered rank-major = a column
+    permutation of R).  The owned patterns tile the permuted global pattern, and a rank evaluates about E/P elements
+    instead of the 2E/P of contiguous blocks of the stacked unknowns."""
+    from mgb_b200 import dist as mdist
+    geom = getattr(mgb_b200, gen)(L)
+    pr = problem(geom, slack=slack)
+    n, m = geom.x.shape[0], pr["R"].shape[1]
+    sizes = mdist.variable_blocks(pr["R"], n)
+    assert sizes.sum() == m and len(sizes) == (3 if slack else 2)
+    perm, out_part = mdist.colocated_partition(sizes, nranks)
+    assert np.array_equal(np.sort(perm), np.arange(m)) and out_part[0] == 0 and out_part[-1] == m
+    offs = np.concatenate([[0], np.cumsum(sizes)])
+    for r in range(nranks):   # the owned block holds the rank's uniform block of every variable, back to back
+        own = perm[out_part[r]:out_part[r + 1]]
+        for k, sz in enumerate(sizes):
+            part = uniform_partition(int(sz), nranks) - 1
+            assert np.array_equal(own[(own >= offs[k]) & (own < offs[k + 1])], np.arange(part[r], part[r + 1]) + offs[k])
+    Rp = pr["R"].tocsr()[:, perm].tocsr()
+    grp, gci = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, slack=slack).pattern()
+    H = sp.csr_matrix((np.ones(len(gci)), gci.astype(np.int64), grp.astype(np.int64)), shape=(m, m))
+    Hp = H[perm][:, perm].tocsr()
+    Hp.sort_indices()
+    row_part = uniform_partition(n, nranks, geom.block) - 1
+    cont_part = uniform_partition(m, nranks) - 1
+    prim_all, el_col, el_cont = [], [], []
+    for r in range(nranks):
+        pl = capi.DistPlan(None, pr["D"], Rp, pr["x"], pr["w"], pr["idx"], 1.0, r, nranks, row_part, out_part, slack=slack)
+        lo, hi = pl.dinfo["own0"], pl.dinfo["own1"]
+        rp, ci = pl.own_pattern()
+        assert np.array_equal(rp, Hp.indptr[lo:hi + 1] - Hp.indptr[lo]) and np.array_equal(ci, Hp.indices[Hp.indptr[lo]:Hp.indptr[hi]])
+        prim_all.append(pl.rows[: pl.dinfo["n_primary"]])
+        el_col.append(pl.dinfo["elements"])
+        el_cont.append(capi.DistPlan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, r, nranks, row_part, cont_part,
+                                     slack=slack).dinfo["elements"])
+    assert np.array_equal(np.sort(np.concatenate(prim_all)), np.arange(n))
+    assert max(el_col) < 0.8 * max(el_cont), (el_col, el_cont)
+
+
 def test_coarse_levels_and_unstructured_operators_refuse_to_shard():
     """the refusal every rank sees alike (solver.LevelState then assembles the level redundantly)"""
     geom = mgb_b200.fem2d(4)
