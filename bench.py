@@ -340,16 +340,23 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
                                 for p_, cnt in zip(ptrs, (max(n_h, 1), max(n_g, 1), 4)))
         return views[ptrs]
 
-    def step_multi(nsteps):
+    s_own_al = s_d[plan.dinfo["own0"]: plan.dinfo["own1"]].clone() if sharded else None
+
+    def step_multi(nsteps, align=False):
         """per-step CUDA events on the launching stream, the cross-rank sum of the scalars inside the timed bracket
         (the gather kernel of every rank waits for its peers' words).  All steps are enqueued before the host waits,
-        so the ranks are paced by their GPUs and not by host launch jitter."""
+        so the ranks are paced by their GPUs and not by host launch jitter.  ``align`` (side figure only): a device-side
+        rendezvous (the peer-memory all-gather of s: publish + wait, untimed) lines the ranks up before each start
+        event, which separates skew between the ranks (flush-time differences) from the assembly itself."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
         for r in range(nsteps):
             if flush == 2:
                 flush_buf.sum()  # read-evict: leaves L2 full of clean lines
             elif flush:
                 flush_buf.fill_(float(r))
+            if align:
+                plan.s_publish(s_own_al)
+                plan.s_wait()
             evs[r][0].record()
             plan.dist_assemble(s_d, Dz0_d, c_d, args.t, flags)
             evs[r][1].record()
@@ -376,6 +383,10 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()
+    ms_aligned = None   # side figure: the same steps with the ranks lined up on the device before each start event
+    if sharded:
+        barrier()
+        ms_aligned = step_multi(steps, align=True)
     ms_sdist = None
     if sharded:   # the same step starting from a row-distributed unknown (the reference's HPCVector): + all-gather of s
         s_own = s_d[plan.dinfo["own0"]: plan.dinfo["own1"]].clone()
@@ -459,7 +470,8 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         e2e_extra["path"] = "pinned host buffers around mgb_dist_assemble (owned blocks)"
 
     par = [parity[k] if parity else 0.0 for k in ("f0_rel", "grad_rel", "hess_rel")]
-    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms] + par + [float(rows.size), float(n_h), ms_sdist or 0.0], dtype=f64, device=dev)
+    vals = torch.tensor([ms_total, ms_elem, ms_gather, e2e_ms] + par + [float(rows.size), float(n_h), ms_sdist or 0.0, ms_aligned or 0.0],
+                        dtype=f64, device=dev)
     mx = vals.clone()
     if world > 1:
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
@@ -518,6 +530,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
                        "rows_evaluated_max_rank": int(mx[7].cpu()), "rows_total": n, "owned_hessian_entries_max_rank": int(mx[8].cpu()),
                        "ms_from_row_distributed_s": (float(mx[9].cpu()) if sharded else None),
                        "ownership": None if not sharded else args.ownership,
+                       "ms_rank_aligned": (float(mx[10].cpu()) if sharded else None),
                        "multi_gpu": None if not sharded else (
                            "owner-computes: a rank evaluates every element touching its output rows "
                            + ("(unknowns renumbered rank-major - rank r owns block r of u AND of s - so that is E/P elements "
@@ -593,6 +606,8 @@ def main():
         if rank == 0:
             subs.append({"workload": r["config"]["workload"], "ms_per_step": r["value"], "parity": r["parity"],
                          "rows_evaluated_max_rank": r["config"]["rows_evaluated_max_rank"], "rows_total": r["config"]["rows_total"],
+                         "ms_rank_aligned": r["config"]["ms_rank_aligned"], "ms_from_row_distributed_s": r["config"]["ms_from_row_distributed_s"],
+                         "element_ms": r["roofline"]["assembly"]["element_ms"], "gather_ms": r["roofline"]["assembly"]["gather_ms"],
                          "assembly_frac_of_peak": r["roofline"]["assembly"]["frac"]})
     if rank == 0:
         line = {"metric": METRIC, "value": rec["value"], "unit": "ms", "n_gpus": world, "steps": args.steps,

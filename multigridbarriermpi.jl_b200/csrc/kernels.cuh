@@ -673,7 +673,11 @@ __device__ __forceinline__ double list_sum(const double* __restrict__ src, const
 static __global__ void __launch_bounds__(256) gather_kernel(const GatherParams P) {
     // launch order [long lists | gradient | two-source Hessian entries | scalars]: the list-walking blocks have the
     // longest dependent-load chains, so they start first and overlap the bulk instead of forming the kernel's tail
+    // Several ranks: the scalar block goes FIRST instead of last - it publishes this rank's partial sums the moment the
+    // element kernel has finished and then waits for the peers' words while the rest of the grid gathers, so the
+    // NVLink latency and up to a whole gather of skew between the ranks are hidden behind the kernel's own work.
     int64_t b = blockIdx.x;
+    if (P.dist.nranks > 1) b = (b == 0) ? (int64_t)gridDim.x - 1 : b - 1;
     {
         const int64_t nlg = P.nblk_l + P.nblk_g;
         if (b < nlg) b += P.nblk_h;
