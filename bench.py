@@ -349,6 +349,11 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         rendezvous (the peer-memory all-gather of s: publish + wait, untimed) lines the ranks up before each start
         event, which separates skew between the ranks (flush-time differences) from the assembly itself."""
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(nsteps)]
+        # the barrier in front of the timed region, on the DEVICE: the hosts leave dist.barrier() tens to hundreds of
+        # microseconds apart, and since every assembly waits for every peer, the first step of the early ranks would
+        # absorb that start-up skew (measured at N=8, 6 steps: 76.9 us per step with it, 36.8 without)
+        plan.s_publish(s_own_al)
+        plan.s_wait()
         for r in range(nsteps):
             if flush == 2:
                 flush_buf.sum()  # read-evict: leaves L2 full of clean lines
@@ -379,7 +384,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
         ms_total, _, _ = plan.time_assemble(s_d, Dz0_d, c_d, args.t, flags, scal_d, grad_d, hval_d, steps, flush, split=False)
     else:
         ms_total = step_multi(steps)
-    launches = capi.launch_count() - launches0
+    launches = capi.launch_count() - launches0 - (2 if sharded else 0)   # minus the rendezvous in front of the loop
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop()

@@ -6,10 +6,11 @@
 //     points through a two-stage shared-memory ring filled by 1-D bulk copies (TMA: cp.async.bulk + mbarrier);
 //   * phase 1 (two points per warp): apply_D as 64-long dot products (lane = 2 dofs, shuffle reduction), the barrier
 //     at the two points on lanes 0 and 1 side by side, w .* F1 / F2 into shared memory, objective partials;
-//   * phase 2: T = (w F2_qq) A, bs = A' (w F2_qs), hs = (w F2_ss) I_s per point, then the three contractions
-//     uu += A' T,  us += bs' I_s,  ss += I_s' hs  on the FP64 tensor cores (mma.sync m8n8k4 = SASS DMMA.8x8x4): warp w
-//     owns rows [8w, 8w+8) of each 64 x 64 block (8 column tiles, 48 accumulators per lane); the one dense contraction
-//     of this path, and the one place where tensor cores pay.  The gradient rides along (threads 0..127);
+//   * phase 2: the three contractions  uu += (w F2_qq A)' A,  us += (A' w F2_qs) I_s,  ss += (w F2_ss I_s)' I_s  on the
+//     FP64 tensor cores (mma.sync m8n8k4 = SASS DMMA.8x8x4): warp w owns rows [8w, 8w+8) of each 64 x 64 block (8
+//     column tiles, 48 accumulators per lane), the barrier's small blocks are applied while the A fragments are formed,
+//     the B fragments are the operator rows as they lie in the tile; the one dense contraction of this path, and the
+//     one place where tensor cores pay.  The gradient rides along (one unknown per thread, two halves of the points);
 //   * the chunk's full blocks (3 x 64 x 64 doubles) and gradient record go to `sel` / `rel`; the ordinary gather
 //     kernels replay them into the CSR values of R'HR and into g (contribution lists built at plan time).
 // Fixed summation order (points in order inside a chunk, chunks in order in the gather): bit-reproducible.
@@ -28,11 +29,11 @@ constexpr int DS = DENSE_STRIDE;   // 68: row stride (doubles) of every operand 
 constexpr int DPT = 16;        // points per tile
 constexpr int DNR = 5;         // rows per point: dx dy dz u.id s.id  (dim = 3)
 constexpr int D_TILE_BYTES = DPT * DNR * DS * 8;   // 42.5 KB
+constexpr int DPW = 20;        // doubles per point of the barrier record: w F2_qq (3 x 3), w F2_qs (3), w F2_ss, w (F1 + t c) (5), pad
 constexpr int D_SMEM = 2 * D_TILE_BYTES            // record ring
                      + 2 * DN * 8                  // unknowns
-                     + DPT * 16 * 8                // per point: w F2 (10), w (F1 + t c) (5), pad
-                     + DPT * 3 * DS * 8            // T
-                     + 2 * DPT * DS * 8            // bs, hs
+                     + DPT * DPW * 8               // barrier records of the tile's points
+                     + 2 * DN * 8                  // gradient halves
                      + 64;                         // mbarriers
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (SASS DMMA.8x8x4).  Fragment layout (g = lane / 4, t = lane % 4):
@@ -83,11 +84,9 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
     double* tile0 = reinterpret_cast<double*>(dsm);
     double* zu = reinterpret_cast<double*>(dsm + 2 * D_TILE_BYTES);
     double* zs = zu + DN;
-    double* pw = zs + DN;                  // [DPT][16]
-    double* Tt = pw + DPT * 16;            // [DPT * 3][DS]
-    double* bs = Tt + DPT * 3 * DS;        // [DPT][DS]
-    double* hs = bs + DPT * DS;            // [DPT][DS]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(hs + DPT * DS);
+    double* pw = zs + DN;                  // [DPT][DPW]
+    double* gh = pw + DPT * DPW;           // [2 DN]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(gh + 2 * DN);
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ch = blockIdx.x;
@@ -117,10 +116,30 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
 #pragma unroll
     for (int i = 0; i < 8; ++i) uu[i][0] = uu[i][1] = us[i][0] = us[i][1] = ss[i][0] = ss[i][1] = 0.0;
     double gacc = 0.0, sc0 = 0.0, sc1 = 0.0, sc2 = 0.0;
+    // per-point scalars (c, Dz0, w) of the evaluating lanes, fetched ONE TILE AHEAD: loaded on demand they put a full
+    // DRAM latency into every tile's critical path (the barrier chain starts from them)
+    double ncc[5], ndz[5], nwi = 0.0;
+    auto prefetch = [&](int tl) {
+        const int pt = 2 * warp + lane;
+        const int64_t i = p0 + (int64_t)tl * DPT + pt;
+        const bool on = lane < 2 && i < p1;
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+            ncc[k] = on ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
+            ndz[k] = (on && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+        }
+        nwi = on ? __ldg(&P.w[i]) : 0.0;
+    };
+    if (ntile > 0) prefetch(0);
 
     for (int tl = 0; tl < ntile; ++tl) {
-        __syncthreads();   // the other stage and T / bs / hs / pw are free again
+        __syncthreads();   // the other stage and pw are free again
         if (tid == 0 && tl + 1 < ntile) issue(tl + 1);
+        double cc[5], dz[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) { cc[k] = ncc[k]; dz[k] = ndz[k]; }
+        const double wi = nwi;
+        if (tl + 1 < ntile) prefetch(tl + 1);
         double* tile = tile0 + (size_t)(tl & 1) * (DPT * DNR * DS);
         const int npt = (int)min((int64_t)DPT, npts - (int64_t)tl * DPT);
         while (!d_mbar_try_wait(bars + (tl & 1), (unsigned)((tl >> 1) & 1))) {}
@@ -154,17 +173,13 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
                 double dd[5];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) dd[r] = lane == 0 ? d[0][r] : d[1][r];
-                double* o = pw + pt * 16;
+                double* o = pw + pt * DPW;
                 if (actp) {
-                    double cc[5], dz[5];
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) { cc[k] = __ldg(&P.c[(int64_t)k * n + i]); dz[k] = P.Dz0 ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0; }
                     dz[0] += dd[3]; dz[1] += dd[0]; dz[2] += dd[1]; dz[3] += dd[2]; dz[4] += dd[4];
                     if (WDZ && P.Dz) {
 #pragma unroll
                         for (int k = 0; k < 5; ++k) P.Dz[(int64_t)k * n + i] = dz[k];
                     }
-                    const double wi = __ldg(&P.w[i]);
                     const double qv[3] = {dz[1], dz[2], dz[3]};
                     BarrierOut bo;
                     barrier_eval<3, WF, (WG || WH)>(qv, dz[4], P.p, bo);
@@ -173,67 +188,70 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
                     for (int k = 0; k < 5; ++k) cd = fma(cc[k], dz[k], cd);
                     sc0 += WF ? wi * bo.F : 0.0; sc1 += wi * cd; sc2 += bo.feasible ? 0.0 : 1.0;
                     if (WG || WH) {
-                        o[0] = wi * bo.Hqq[0][0]; o[1] = wi * bo.Hqq[0][1]; o[2] = wi * bo.Hqq[0][2];
-                        o[3] = wi * bo.Hqq[1][1]; o[4] = wi * bo.Hqq[1][2]; o[5] = wi * bo.Hqq[2][2];
-                        o[6] = wi * bo.Hqs[0]; o[7] = wi * bo.Hqs[1]; o[8] = wi * bo.Hqs[2]; o[9] = wi * bo.Hss;
-                        o[10] = wi * (P.t * cc[0]);
-                        o[11] = wi * (bo.gq[0] + P.t * cc[1]); o[12] = wi * (bo.gq[1] + P.t * cc[2]); o[13] = wi * (bo.gq[2] + P.t * cc[3]);
-                        o[14] = wi * (bo.gs + P.t * cc[4]);
+#pragma unroll
+                        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                            for (int j2 = 0; j2 < 3; ++j2) o[3 * j + j2] = wi * bo.Hqq[j < j2 ? j : j2][j < j2 ? j2 : j];
+                            o[9 + j] = wi * bo.Hqs[j];
+                        }
+                        o[12] = wi * bo.Hss;
+                        o[13] = wi * (P.t * cc[0]);
+                        o[14] = wi * (bo.gq[0] + P.t * cc[1]); o[15] = wi * (bo.gq[1] + P.t * cc[2]); o[16] = wi * (bo.gq[2] + P.t * cc[3]);
+                        o[17] = wi * (bo.gs + P.t * cc[4]);
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 15; ++k) o[k] = 0.0;
+                    for (int k = 0; k < 18; ++k) o[k] = 0.0;
                 }
             }
         }
         if (!(WG || WH)) continue;   // objective only: no contraction
         __syncthreads();
-        // ---- phase 2a: per point T = (w F2_qq) A, bs = A' (w F2_qs), hs = (w F2_ss) I_s
+        // ---- phase 2: the three contractions of the tile on the FP64 tensor cores,  uu += (F2_qq A)' A,
+        // us += (A' F2_qs) I_s,  ss += (F2_ss I_s)' I_s.  K runs over (point, derivative) for uu (48 = 12 steps of 4) and
+        // over the points for us / ss (16 = 4 steps).  The barrier's 3 x 3 / 3 x 1 / 1 x 1 blocks are applied on the A
+        // side while the fragment is formed (3 shared loads + 3 FMAs per lane and step), so no scaled copy of the tile is
+        // ever written: the B fragments are the operator rows themselves (8-byte shared loads, conflict free by the row
+        // stride), and us / ss share theirs.
         if (WH) {
-            for (int idx = tid; idx < DPT * DN; idx += 256) {
-                const int pt = idx / DN, b = idx % DN;
-                const double* o = pw + pt * 16;
-                const double* tp = tile + pt * (DNR * DS);
-                const double A0 = tp[b], A1 = tp[DS + b], A2 = tp[2 * DS + b];
-                Tt[(pt * 3 + 0) * DS + b] = o[0] * A0 + o[1] * A1 + o[2] * A2;
-                Tt[(pt * 3 + 1) * DS + b] = o[1] * A0 + o[3] * A1 + o[4] * A2;
-                Tt[(pt * 3 + 2) * DS + b] = o[2] * A0 + o[4] * A1 + o[5] * A2;
-                bs[pt * DS + b] = o[6] * A0 + o[7] * A1 + o[8] * A2;
-                hs[pt * DS + b] = o[9] * tp[4 * DS + b];
-            }
-            __syncthreads();
-            // ---- phase 2b: the three contractions of the tile on the FP64 tensor cores.  K runs over (point, derivative)
-            // for uu (48 = 12 steps of 4) and over the points for us / ss (16 = 4 steps); per step one A fragment and
-            // eight B fragments (8-byte shared loads, conflict free by the row stride) feed eight DMMAs.
             const int arow = 8 * warp + fg;
+#ifndef MGB_DENSE_SKIP_MMA   // (timing experiments only: wrong results)
 #pragma unroll 4
             for (int kk = 0; kk < 3 * DPT / 4; ++kk) {
                 const int k = 4 * kk + ft, pt = k / 3, j = k - 3 * pt;
-                const double a = tile[(pt * DNR + j) * DS + arow];
-                const double* brow = Tt + k * DS + fg;
+                const double* tp = tile + pt * (DNR * DS);
+                const double* o = pw + pt * DPW + 3 * j;
+                const double a = o[0] * tp[arow] + o[1] * tp[DS + arow] + o[2] * tp[2 * DS + arow];
+                const double* brow = tp + j * DS + fg;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) dmma884(uu[nt][0], uu[nt][1], a, brow[8 * nt]);
             }
 #pragma unroll
             for (int kk = 0; kk < DPT / 4; ++kk) {
                 const int pt = 4 * kk + ft;
-                const double a1 = bs[pt * DS + arow], a2 = tile[(pt * DNR + 4) * DS + arow];
-                const double* b1 = tile + (pt * DNR + 4) * DS + fg;
-                const double* b2 = hs + pt * DS + fg;
+                const double* tp = tile + pt * (DNR * DS);
+                const double* o = pw + pt * DPW;
+                const double a1 = o[9] * tp[arow] + o[10] * tp[DS + arow] + o[11] * tp[2 * DS + arow];
+                const double a2 = o[12] * tp[4 * DS + arow];
+                const double* brow = tp + 4 * DS + fg;
 #pragma unroll
                 for (int nt = 0; nt < 8; ++nt) {
-                    dmma884(us[nt][0], us[nt][1], a1, b1[8 * nt]);
-                    dmma884(ss[nt][0], ss[nt][1], a2, b2[8 * nt]);
+                    const double b = brow[8 * nt];
+                    dmma884(us[nt][0], us[nt][1], a1, b);
+                    dmma884(ss[nt][0], ss[nt][1], a2, b);
                 }
             }
+#endif
         }
-        // ---- gradient on threads 0..127 (one unknown each)
-        if (WG && tid < 2 * DN) {
-            for (int pt = 0; pt < DPT; ++pt) {
+        // ---- gradient: thread = (unknown tid % 128, half of the tile's points tid / 128); the halves are added at the end
+        if (WG) {
+            const int un = tid & (2 * DN - 1), h0 = (tid >> 7) * (DPT / 2);
+#pragma unroll 4
+            for (int pt = h0; pt < h0 + DPT / 2; ++pt) {
                 const double* tp = tile + pt * (DNR * DS);
-                const double* o = pw + pt * 16;
-                if (tid < DN) gacc += tp[tid] * o[11] + tp[DS + tid] * o[12] + tp[2 * DS + tid] * o[13] + tp[3 * DS + tid] * o[10];
-                else gacc += tp[4 * DS + tid - DN] * o[14];
+                const double* o = pw + pt * DPW;
+                if (un < DN) gacc += tp[un] * o[14] + tp[DS + un] * o[15] + tp[2 * DS + un] * o[16] + tp[3 * DS + un] * o[13];
+                else gacc += tp[4 * DS + un - DN] * o[17];
             }
         }
     }
@@ -247,7 +265,12 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
             *reinterpret_cast<double2*>(rec + 2 * DN * DN + 8 * nt) = make_double2(ss[nt][0], ss[nt][1]);
         }
     }
-    if (WG && tid < 2 * DN) P.rel[ch * (2 * DN) + tid] = gacc;
+    if (WG) {
+        __syncthreads();
+        if (tid >= 2 * DN) gh[tid - 2 * DN] = gacc;
+        __syncthreads();
+        if (tid < 2 * DN) P.rel[ch * (2 * DN) + tid] = gacc + gh[tid];
+    }
     block_scalars(sc0, sc1, sc2, P.part);
 }
 
