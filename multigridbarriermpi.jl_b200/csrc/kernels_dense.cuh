@@ -30,11 +30,13 @@ constexpr int DPT = 16;        // points per tile
 constexpr int DNR = 5;         // rows per point: dx dy dz u.id s.id  (dim = 3)
 constexpr int D_TILE_BYTES = DPT * DNR * DS * 8;   // 42.5 KB
 constexpr int DPW = 20;        // doubles per point of the barrier record: w F2_qq (3 x 3), w F2_qs (3), w F2_ss, w (F1 + t c) (5), pad
-constexpr int D_SMEM = 2 * D_TILE_BYTES            // record ring
+constexpr int DST = 3;         // ring stages: TMA fills t+2 while the producer warps work on t+1 and the MMA warps on t
+constexpr int D_MMA_WARPS = 8, D_PRO_WARPS = 4;
+constexpr int D_THREADS = 32 * (D_MMA_WARPS + D_PRO_WARPS);   // 384
+constexpr int D_SMEM = DST * D_TILE_BYTES          // operator-row ring
                      + 2 * DN * 8                  // unknowns
-                     + DPT * DPW * 8               // barrier records of the tile's points
-                     + 2 * DN * 8                  // gradient halves
-                     + 64;                         // mbarriers
+                     + DST * DPT * DPW * 8         // barrier records of the tiles' points
+                     + 128;                        // mbarriers
 
 // D(8x8) += A(8x4) * B(4x8) in FP64 on the tensor cores (SASS DMMA.8x8x4).  Fragment layout (g = lane / 4, t = lane % 4):
 // a = A[g][t], b = B[t][g], c0 / c1 = C[g][2t], C[g][2t + 1].
@@ -76,17 +78,27 @@ __device__ __forceinline__ void d_bulk_g2s(void* smem_dst, const void* gsrc, uns
                  ::"r"(d_smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(d_smem_u32(bar)) : "memory");
 }
 
-// FLAGS bits as in the element kernels: 1 objective, 2 gradient, 4 Hessian, 8 store Dz
+__device__ __forceinline__ void d_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(d_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void d_mbar_wait(uint64_t* bar, unsigned parity) {
+    while (!d_mbar_try_wait(bar, parity)) {}
+}
+
+// FLAGS bits as in the element kernels: 1 objective, 2 gradient, 4 Hessian, 8 store Dz.
+// Warp-specialised: warps 0..7 run the tensor-core contraction (+ the gradient) of tile t while warps 8..11
+// ("producers") evaluate apply_D + barrier of tile t+1 and the TMA engine fills tile t+2.  Three mbarriers per ring stage:
+// full (TMA bytes landed), ready (the producers' barrier records are written), empty (everybody is done with the stage).
 template <int FLAGS>
-__global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_constant__ DenseParams P) {
+__global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __grid_constant__ DenseParams P) {
     constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
     extern __shared__ __align__(128) unsigned char dsm[];
     double* tile0 = reinterpret_cast<double*>(dsm);
-    double* zu = reinterpret_cast<double*>(dsm + 2 * D_TILE_BYTES);
+    double* zu = reinterpret_cast<double*>(dsm + DST * D_TILE_BYTES);
     double* zs = zu + DN;
-    double* pw = zs + DN;                  // [DPT][DPW]
-    double* gh = pw + DPT * DPW;           // [2 DN]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(gh + 2 * DN);
+    double* pw0 = zs + DN;                 // [DST][DPT][DPW]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(pw0 + DST * DPT * DPW);
+    uint64_t* full = bars, *ready = bars + DST, *empty = bars + 2 * DST;
     pdl_launch_dependents();
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t ch = blockIdx.x;
@@ -98,178 +110,200 @@ __global__ void __launch_bounds__(256, 1) dense_element_kernel(const __grid_cons
         zu[tid] = a >= 0 ? __ldg(&P.s[a]) : 0.0;   // zu, zs are contiguous
     }
     if (tid == 0) {
-        d_mbar_init(bars + 0, 1); d_mbar_init(bars + 1, 1);
+        for (int st = 0; st < DST; ++st) {
+            d_mbar_init(full + st, 1);
+            d_mbar_init(ready + st, 32 * D_PRO_WARPS);
+            d_mbar_init(empty + st, D_THREADS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int tl) {   // tile tl -> stage tl & 1 (thread 0)
-        const int64_t q0 = p0 + (int64_t)tl * DPT;
-        const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DS * 8);
-        d_mbar_expect_tx(bars + (tl & 1), bytes);
-        d_bulk_g2s(tile0 + (size_t)(tl & 1) * (DPT * DNR * DS), P.rows + q0 * (DNR * DS), bytes, bars + (tl & 1));
-    };
-    if (tid == 0 && ntile > 0) issue(0);
+    double sc0 = 0.0, sc1 = 0.0, sc2 = 0.0;
 
-    // warp w owns output rows [8w, 8w + 8) of the three 64 x 64 blocks: 8 column tiles of 8, two accumulators per lane each
-    const int fg = lane >> 2, ft = lane & 3;
-    double uu[8][2], us[8][2], ss[8][2];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) uu[i][0] = uu[i][1] = us[i][0] = us[i][1] = ss[i][0] = ss[i][1] = 0.0;
-    double gacc = 0.0, sc0 = 0.0, sc1 = 0.0, sc2 = 0.0;
-    // per-point scalars (c, Dz0, w) of the evaluating lanes, fetched ONE TILE AHEAD: loaded on demand they put a full
-    // DRAM latency into every tile's critical path (the barrier chain starts from them)
-    double ncc[5], ndz[5], nwi = 0.0;
-    auto prefetch = [&](int tl) {
-        const int pt = 2 * warp + lane;
-        const int64_t i = p0 + (int64_t)tl * DPT + pt;
-        const bool on = lane < 2 && i < p1;
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            ncc[k] = on ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
-            ndz[k] = (on && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
+    if (warp >= D_MMA_WARPS) {
+        // ================================================================ producers (128 threads)
+        const int ptid = tid - 32 * D_MMA_WARPS, pwarp = warp - D_MMA_WARPS;
+        auto issue = [&](int tl) {   // tile tl -> stage tl % DST (one thread)
+            const int64_t q0 = p0 + (int64_t)tl * DPT;
+            const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DS * 8);
+            d_mbar_expect_tx(full + tl % DST, bytes);
+            d_bulk_g2s(tile0 + (size_t)(tl % DST) * (DPT * DNR * DS), P.rows + q0 * (DNR * DS), bytes, full + tl % DST);
+        };
+        if (ptid == 0) {
+            if (ntile > 0) issue(0);
+            if (ntile > 1) issue(1);
         }
-        nwi = on ? __ldg(&P.w[i]) : 0.0;
-    };
-    if (ntile > 0) prefetch(0);
-
-    for (int tl = 0; tl < ntile; ++tl) {
-        __syncthreads();   // the other stage and pw are free again
-        if (tid == 0 && tl + 1 < ntile) issue(tl + 1);
-        double cc[5], dz[5];
+        // four points per warp; after the transposing reduction lane 8q holds the five dot products of point 4 pwarp + q.
+        // Per-point scalars (c, Dz0, w) of the evaluating lanes are fetched ONE TILE AHEAD: loaded on demand they put a
+        // full DRAM latency into every tile's critical path (the barrier chain starts from them)
+        const bool ev = (lane & 7) == 0;
+        const int ptl = 4 * pwarp + (lane >> 3);
+        double ncc[5], ndz[5], nwi = 0.0;
+        auto prefetch = [&](int tl) {
+            const int64_t i = p0 + (int64_t)tl * DPT + ptl;
+            const bool on = ev && i < p1;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) { cc[k] = ncc[k]; dz[k] = ndz[k]; }
-        const double wi = nwi;
-        if (tl + 1 < ntile) prefetch(tl + 1);
-        double* tile = tile0 + (size_t)(tl & 1) * (DPT * DNR * DS);
-        const int npt = (int)min((int64_t)DPT, npts - (int64_t)tl * DPT);
-        while (!d_mbar_try_wait(bars + (tl & 1), (unsigned)((tl >> 1) & 1))) {}
-        if (npt < DPT)   // the tail of a partial tile was not loaded: it must not contribute (0 * stale NaN)
-            for (int k = npt * DNR * DS + tid; k < DPT * DNR * DS; k += 256) tile[k] = 0.0;
-        // ---- phase 1: apply_D + barrier, two points per warp.  All lanes form the dot products of both points (lane = 2
-        // dofs, xor-shuffle sums leave the totals on every lane); then lane 0 evaluates the first point and lane 1 the
-        // second side by side - the barrier is a ~400-instruction dependent chain, running the two as SIMD lanes
-        // instead of one after the other halves the phase.
-        {
-            double d[2][5];
-#pragma unroll
-            for (int pp = 0; pp < 2; ++pp) {
-                const int pt = 2 * warp + pp;
-                const bool actp = pt < npt;
-                const double* tp = tile + pt * (DNR * DS);
-#pragma unroll
-                for (int r = 0; r < 4; ++r) d[pp][r] = actp ? tp[r * DS + lane] * zu[lane] + tp[r * DS + lane + 32] * zu[lane + 32] : 0.0;
-                d[pp][4] = actp ? tp[4 * DS + lane] * zs[lane] + tp[4 * DS + lane + 32] * zs[lane + 32] : 0.0;
+            for (int k = 0; k < 5; ++k) {
+                ncc[k] = on ? __ldg(&P.c[(int64_t)k * n + i]) : 0.0;
+                ndz[k] = (on && P.Dz0) ? __ldg(&P.Dz0[(int64_t)k * n + i]) : 0.0;
             }
+            nwi = on ? __ldg(&P.w[i]) : 0.0;
+        };
+        if (ntile > 0) prefetch(0);
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int st = tl % DST;
+            const unsigned par = (unsigned)((tl / DST) & 1);
+            double cc[5], dz[5];
 #pragma unroll
-            for (int mk = 16; mk >= 1; mk >>= 1)
+            for (int k = 0; k < 5; ++k) { cc[k] = ncc[k]; dz[k] = ndz[k]; }
+            const double wi = nwi;
+            if (tl + 1 < ntile) prefetch(tl + 1);
+            double* tile = tile0 + (size_t)st * (DPT * DNR * DS);
+            double* pw = pw0 + st * (DPT * DPW);
+            const int npt = (int)min((int64_t)DPT, npts - (int64_t)tl * DPT);
+            d_mbar_wait(full + st, par);
+            if (npt < DPT)   // the tail of a partial tile was not loaded: it must not contribute (0 * stale NaN)
+                for (int k = npt * DNR * DS + ptid; k < DPT * DNR * DS; k += 32 * D_PRO_WARPS) tile[k] = 0.0;
+            // ---- apply_D as 64-long dot products: lane = 2 dofs, 4 points x 5 rows = 20 partial sums per lane, reduced by
+            // a transposing butterfly (xor 16 halves the value set, xor 8 again, then xor 4 / 2 / 1 on the five left)
+            {
+                double d[20];
 #pragma unroll
-                for (int pp = 0; pp < 2; ++pp)
+                for (int pp = 0; pp < 4; ++pp) {
+                    const int pt = 4 * pwarp + pp;
+                    const bool actp = pt < npt;
+                    const double* tp = tile + pt * (DNR * DS);
 #pragma unroll
-                    for (int r = 0; r < 5; ++r) d[pp][r] += shfl_xor_d(d[pp][r], mk);
-            if (lane < 2) {
-                const int pt = 2 * warp + lane;
-                const bool actp = pt < npt;
-                const int64_t i = p0 + (int64_t)tl * DPT + pt;
-                double dd[5];
+                    for (int r = 0; r < 4; ++r) d[pp * 5 + r] = actp ? tp[r * DS + lane] * zu[lane] + tp[r * DS + lane + 32] * zu[lane + 32] : 0.0;
+                    d[pp * 5 + 4] = actp ? tp[4 * DS + lane] * zs[lane] + tp[4 * DS + lane + 32] * zs[lane + 32] : 0.0;
+                }
+                double e[10], dd[5];
+                const bool up1 = (lane & 16) != 0, up2 = (lane & 8) != 0;
 #pragma unroll
-                for (int r = 0; r < 5; ++r) dd[r] = lane == 0 ? d[0][r] : d[1][r];
-                double* o = pw + pt * DPW;
-                if (actp) {
-                    dz[0] += dd[3]; dz[1] += dd[0]; dz[2] += dd[1]; dz[3] += dd[2]; dz[4] += dd[4];
-                    if (WDZ && P.Dz) {
+                for (int i = 0; i < 10; ++i) e[i] = (up1 ? d[i + 10] : d[i]) + shfl_xor_d(up1 ? d[i] : d[i + 10], 16);
 #pragma unroll
-                        for (int k = 0; k < 5; ++k) P.Dz[(int64_t)k * n + i] = dz[k];
-                    }
-                    const double qv[3] = {dz[1], dz[2], dz[3]};
-                    BarrierOut bo;
-                    barrier_eval<3, WF, (WG || WH)>(qv, dz[4], P.p, bo);
-                    double cd = 0.0;
+                for (int i = 0; i < 5; ++i) dd[i] = (up2 ? e[i + 5] : e[i]) + shfl_xor_d(up2 ? e[i] : e[i + 5], 8);
 #pragma unroll
-                    for (int k = 0; k < 5; ++k) cd = fma(cc[k], dz[k], cd);
-                    sc0 += WF ? wi * bo.F : 0.0; sc1 += wi * cd; sc2 += bo.feasible ? 0.0 : 1.0;
-                    if (WG || WH) {
+                for (int mk = 4; mk >= 1; mk >>= 1)
 #pragma unroll
-                        for (int j = 0; j < 3; ++j) {
+                    for (int i = 0; i < 5; ++i) dd[i] += shfl_xor_d(dd[i], mk);
+                if (ev) {
+                    const bool actp = ptl < npt;
+                    const int64_t i = p0 + (int64_t)tl * DPT + ptl;
+                    double* o = pw + ptl * DPW;
+                    if (actp) {
+                        dz[0] += dd[3]; dz[1] += dd[0]; dz[2] += dd[1]; dz[3] += dd[2]; dz[4] += dd[4];
+                        if (WDZ && P.Dz) {
 #pragma unroll
-                            for (int j2 = 0; j2 < 3; ++j2) o[3 * j + j2] = wi * bo.Hqq[j < j2 ? j : j2][j < j2 ? j2 : j];
-                            o[9 + j] = wi * bo.Hqs[j];
+                            for (int k = 0; k < 5; ++k) P.Dz[(int64_t)k * n + i] = dz[k];
                         }
-                        o[12] = wi * bo.Hss;
-                        o[13] = wi * (P.t * cc[0]);
-                        o[14] = wi * (bo.gq[0] + P.t * cc[1]); o[15] = wi * (bo.gq[1] + P.t * cc[2]); o[16] = wi * (bo.gq[2] + P.t * cc[3]);
-                        o[17] = wi * (bo.gs + P.t * cc[4]);
+                        const double qv[3] = {dz[1], dz[2], dz[3]};
+                        BarrierOut bo;
+                        barrier_eval<3, WF, (WG || WH)>(qv, dz[4], P.p, bo);
+                        double cd = 0.0;
+#pragma unroll
+                        for (int k = 0; k < 5; ++k) cd = fma(cc[k], dz[k], cd);
+                        sc0 += WF ? wi * bo.F : 0.0; sc1 += wi * cd; sc2 += bo.feasible ? 0.0 : 1.0;
+                        if (WG || WH) {
+#pragma unroll
+                            for (int j = 0; j < 3; ++j) {
+#pragma unroll
+                                for (int j2 = 0; j2 < 3; ++j2) o[3 * j + j2] = wi * bo.Hqq[j < j2 ? j : j2][j < j2 ? j2 : j];
+                                o[9 + j] = wi * bo.Hqs[j];
+                            }
+                            o[12] = wi * bo.Hss;
+                            o[13] = wi * (P.t * cc[0]);
+                            o[14] = wi * (bo.gq[0] + P.t * cc[1]); o[15] = wi * (bo.gq[1] + P.t * cc[2]); o[16] = wi * (bo.gq[2] + P.t * cc[3]);
+                            o[17] = wi * (bo.gs + P.t * cc[4]);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 18; ++k) o[k] = 0.0;
                     }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 18; ++k) o[k] = 0.0;
                 }
             }
+            d_mbar_arrive(ready + st);            // this thread's part of the tile's barrier records (and zero fill) is written
+            d_mbar_arrive(empty + st);
+            // refill the stage the tensor-core warps are about to leave (tile tl-1 -> tile tl+2).  Waiting here, after this
+            // tile's producer work, keeps the two halves of the CTA one tile apart: producers on tl+1 while the MMAs run tl.
+            if (ptid == 0 && tl + 2 < ntile) {
+                if (tl >= 1) d_mbar_wait(empty + (tl - 1) % DST, (unsigned)(((tl - 1) / DST) & 1));
+                issue(tl + 2);
+            }
         }
-        if (!(WG || WH)) continue;   // objective only: no contraction
-        __syncthreads();
-        // ---- phase 2: the three contractions of the tile on the FP64 tensor cores,  uu += (F2_qq A)' A,
-        // us += (A' F2_qs) I_s,  ss += (F2_ss I_s)' I_s.  K runs over (point, derivative) for uu (48 = 12 steps of 4) and
-        // over the points for us / ss (16 = 4 steps).  The barrier's 3 x 3 / 3 x 1 / 1 x 1 blocks are applied on the A
-        // side while the fragment is formed (3 shared loads + 3 FMAs per lane and step), so no scaled copy of the tile is
-        // ever written: the B fragments are the operator rows themselves (8-byte shared loads, conflict free by the row
-        // stride), and us / ss share theirs.
-        if (WH) {
-            const int arow = 8 * warp + fg;
+    } else {
+        // ================================================================ tensor-core warps (256 threads)
+        // warp w owns output rows [8w, 8w + 8) of the three 64 x 64 blocks: 8 column tiles of 8, two accumulators per lane each
+        const int fg = lane >> 2, ft = lane & 3;
+        double uu[8][2], us[8][2], ss[8][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) uu[i][0] = uu[i][1] = us[i][0] = us[i][1] = ss[i][0] = ss[i][1] = 0.0;
+        const int arow = 8 * warp + fg;
+        double gu = 0.0, gs = 0.0;   // gradient partials of unknowns arow (u) and arow (s) over this lane's points
+        for (int tl = 0; tl < ntile; ++tl) {
+            const int st = tl % DST;
+            const double* tile = tile0 + (size_t)st * (DPT * DNR * DS);
+            const double* pw = pw0 + st * (DPT * DPW);
+            d_mbar_wait(ready + st, (unsigned)((tl / DST) & 1));   // (also without a Hessian: nobody may run a phase ahead)
+            if (WH) {
+                // ---- the three contractions of the tile,  uu += (F2_qq A)' A,  us += (A' F2_qs) I_s,  ss += (F2_ss I_s)' I_s.
+                // K runs over (point, derivative) for uu and over the points for us / ss; a k-step of 4 takes the SAME
+                // derivative of four consecutive points (lane t of a quad: point 4q + t), so a lane keeps its point for
+                // the three uu steps and the us / ss step of a quad: the three derivative rows of its output column are
+                // loaded once, the barrier's 3 x 3 / 3 x 1 / 1 x 1 blocks are applied to them in registers (no scaled copy
+                // of the tile is ever written), and the rows a quad of lanes reads lie 5 * 68 doubles apart - distinct
+                // 8-byte bank pairs for A and B fragments alike.  The B fragments are the operator rows themselves;
+                // us / ss share theirs.
 #ifndef MGB_DENSE_SKIP_MMA   // (timing experiments only: wrong results)
-#pragma unroll 4
-            for (int kk = 0; kk < 3 * DPT / 4; ++kk) {
-                const int k = 4 * kk + ft, pt = k / 3, j = k - 3 * pt;
-                const double* tp = tile + pt * (DNR * DS);
-                const double* o = pw + pt * DPW + 3 * j;
-                const double a = o[0] * tp[arow] + o[1] * tp[DS + arow] + o[2] * tp[2 * DS + arow];
-                const double* brow = tp + j * DS + fg;
+#pragma unroll 2
+                for (int q = 0; q < DPT / 4; ++q) {
+                    const int pt = 4 * q + ft;
+                    const double* tp = tile + pt * (DNR * DS);
+                    const double2* o2 = reinterpret_cast<const double2*>(pw + pt * DPW);
+                    const double t0 = tp[arow], t1 = tp[DS + arow], t2 = tp[2 * DS + arow], t3 = tp[3 * DS + arow], t4 = tp[4 * DS + arow];
+                    double o[18];
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) dmma884(uu[nt][0], uu[nt][1], a, brow[8 * nt]);
-            }
+                    for (int i = 0; i < 9; ++i) { const double2 v = o2[i]; o[2 * i] = v.x; o[2 * i + 1] = v.y; }
+                    // the gradient rides along on the operands already in registers (the FP64 pipe is the tensor pipe:
+                    // a separate pass over the tile by other warps would compete with the DMMAs for it)
+                    gu += t0 * o[14] + t1 * o[15] + t2 * o[16] + t3 * o[13];
+                    gs += t4 * o[17];
 #pragma unroll
-            for (int kk = 0; kk < DPT / 4; ++kk) {
-                const int pt = 4 * kk + ft;
-                const double* tp = tile + pt * (DNR * DS);
-                const double* o = pw + pt * DPW;
-                const double a1 = o[9] * tp[arow] + o[10] * tp[DS + arow] + o[11] * tp[2 * DS + arow];
-                const double a2 = o[12] * tp[4 * DS + arow];
-                const double* brow = tp + 4 * DS + fg;
+                    for (int j = 0; j < 3; ++j) {
+                        const double a = o[3 * j] * t0 + o[3 * j + 1] * t1 + o[3 * j + 2] * t2;
+                        const double* brow = tp + j * DS + fg;
 #pragma unroll
-                for (int nt = 0; nt < 8; ++nt) {
-                    const double b = brow[8 * nt];
-                    dmma884(us[nt][0], us[nt][1], a1, b);
-                    dmma884(ss[nt][0], ss[nt][1], a2, b);
+                        for (int nt = 0; nt < 8; ++nt) dmma884(uu[nt][0], uu[nt][1], a, brow[8 * nt]);
+                    }
+                    const double a1 = o[9] * t0 + o[10] * t1 + o[11] * t2;
+                    const double a2 = o[12] * t4;
+                    const double* brow = tp + 4 * DS + fg;
+#pragma unroll
+                    for (int nt = 0; nt < 8; ++nt) {
+                        const double b = brow[8 * nt];
+                        dmma884(us[nt][0], us[nt][1], a1, b);
+                        dmma884(ss[nt][0], ss[nt][1], a2, b);
+                    }
                 }
-            }
 #endif
+            }
+            d_mbar_arrive(empty + st);
         }
-        // ---- gradient: thread = (unknown tid % 128, half of the tile's points tid / 128); the halves are added at the end
-        if (WG) {
-            const int un = tid & (2 * DN - 1), h0 = (tid >> 7) * (DPT / 2);
-#pragma unroll 4
-            for (int pt = h0; pt < h0 + DPT / 2; ++pt) {
-                const double* tp = tile + pt * (DNR * DS);
-                const double* o = pw + pt * DPW;
-                if (un < DN) gacc += tp[un] * o[14] + tp[DS + un] * o[15] + tp[2 * DS + un] * o[16] + tp[3 * DS + un] * o[13];
-                else gacc += tp[4 * DS + un - DN] * o[17];
+        if (WG) {   // the four lanes of a quad hold the partials of the same unknowns over different points
+            gu += shfl_xor_d(gu, 1); gu += shfl_xor_d(gu, 2);
+            gs += shfl_xor_d(gs, 1); gs += shfl_xor_d(gs, 2);
+            if (ft == 0) { P.rel[ch * (2 * DN) + arow] = gu; P.rel[ch * (2 * DN) + DN + arow] = gs; }
+        }
+        // ---- the chunk's records: lane holds C[g][2t], C[g][2t + 1] of every column tile
+        if (WH) {
+            double* rec = P.sel + ch * (int64_t)(3 * DN * DN) + (8 * warp + fg) * DN + 2 * ft;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                *reinterpret_cast<double2*>(rec + 8 * nt) = make_double2(uu[nt][0], uu[nt][1]);
+                *reinterpret_cast<double2*>(rec + DN * DN + 8 * nt) = make_double2(us[nt][0], us[nt][1]);
+                *reinterpret_cast<double2*>(rec + 2 * DN * DN + 8 * nt) = make_double2(ss[nt][0], ss[nt][1]);
             }
         }
-    }
-    // ---- the chunk's records: lane holds C[g][2t], C[g][2t + 1] of every column tile
-    if (WH) {
-        double* rec = P.sel + ch * (int64_t)(3 * DN * DN) + (8 * warp + fg) * DN + 2 * ft;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            *reinterpret_cast<double2*>(rec + 8 * nt) = make_double2(uu[nt][0], uu[nt][1]);
-            *reinterpret_cast<double2*>(rec + DN * DN + 8 * nt) = make_double2(us[nt][0], us[nt][1]);
-            *reinterpret_cast<double2*>(rec + 2 * DN * DN + 8 * nt) = make_double2(ss[nt][0], ss[nt][1]);
-        }
-    }
-    if (WG) {
-        __syncthreads();
-        if (tid >= 2 * DN) gh[tid - 2 * DN] = gacc;
-        __syncthreads();
-        if (tid < 2 * DN) P.rel[ch * (2 * DN) + tid] = gacc + gh[tid];
     }
     block_scalars(sc0, sc1, sc2, P.part);
 }

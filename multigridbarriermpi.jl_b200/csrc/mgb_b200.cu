@@ -316,7 +316,7 @@ void launch_dense(const mgb_plan* pl, const mgb::ElemParams& E, int flags) {
         CUDA_OK(cudaFuncSetAttribute(mgb::dense_element_kernel<15>, cudaFuncAttributeMaxDynamicSharedMemorySize, mgb::D_SMEM));
         opted = true;
     }
-    const dim3 g((unsigned)P.nchunks), b(256);
+    const dim3 g((unsigned)P.nchunks), b(mgb::D_THREADS);
     cudaStream_t st = pl->ctx->stream;
     switch (mgb::canonical_flags(flags)) {
         case 1: mgb::dense_element_kernel<1><<<g, b, mgb::D_SMEM, st>>>(P); break;
