@@ -30,7 +30,7 @@ constexpr int DPT = 16;        // points per tile
 constexpr int DNR = 5;         // rows per point: dx dy dz u.id s.id  (dim = 3)
 constexpr int D_TILE_BYTES = DPT * DNR * DS * 8;   // 42.5 KB
 constexpr int DPW = 20;        // doubles per point of the barrier record: w F2_qq (3 x 3), w F2_qs (3), w F2_ss, w (F1 + t c) (5), pad
-constexpr int DST = 3;         // ring stages: TMA fills t+2 while the producer warps work on t+1 and the MMA warps on t
+constexpr int DST = 4;         // ring stages: the MMA warps on tile t, the two producer groups on t+1 and t+2, TMA filling t+3
 constexpr int D_MMA_WARPS = 8, D_PRO_WARPS = 4;
 constexpr int D_THREADS = 32 * (D_MMA_WARPS + D_PRO_WARPS);   // 384
 constexpr int D_SMEM = DST * D_TILE_BYTES          // operator-row ring
@@ -87,8 +87,11 @@ __device__ __forceinline__ void d_mbar_wait(uint64_t* bar, unsigned parity) {
 
 // FLAGS bits as in the element kernels: 1 objective, 2 gradient, 4 Hessian, 8 store Dz.
 // Warp-specialised: warps 0..7 run the tensor-core contraction (+ the gradient) of tile t while warps 8..11
-// ("producers") evaluate apply_D + barrier of tile t+1 and the TMA engine fills tile t+2.  Three mbarriers per ring stage:
-// full (TMA bytes landed), ready (the producers' barrier records are written), empty (everybody is done with the stage).
+// ("producers") evaluate apply_D + barrier ahead of them - two groups of two warps taking alternate tiles, because the
+// barrier is a ~400-long dependent FP64 chain that shares the FP64 pipe with the DMMAs (ncu: `stall_math` on every
+// producer instruction): one group alone took longer per tile than the contraction, two may each take two tile periods.
+// Three mbarriers per ring stage: full (TMA bytes landed), ready (the group's barrier records are written), empty
+// (everybody is done with the stage; thread 0 then refills it four tiles ahead).
 template <int FLAGS>
 __global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __grid_constant__ DenseParams P) {
     constexpr bool WF = (FLAGS & 1) != 0, WG = (FLAGS & 2) != 0, WH = (FLAGS & 4) != 0, WDZ = (FLAGS & 8) != 0;
@@ -112,32 +115,30 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __gri
     if (tid == 0) {
         for (int st = 0; st < DST; ++st) {
             d_mbar_init(full + st, 1);
-            d_mbar_init(ready + st, 32 * D_PRO_WARPS);
-            d_mbar_init(empty + st, D_THREADS);
+            d_mbar_init(ready + st, 64);
+            d_mbar_init(empty + st, 32 * D_MMA_WARPS + 64);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     double sc0 = 0.0, sc1 = 0.0, sc2 = 0.0;
+    auto issue = [&](int tl) {   // tile tl -> stage tl % DST (thread 0)
+        const int64_t q0 = p0 + (int64_t)tl * DPT;
+        const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DS * 8);
+        d_mbar_expect_tx(full + tl % DST, bytes);
+        d_bulk_g2s(tile0 + (size_t)(tl % DST) * (DPT * DNR * DS), P.rows + q0 * (DNR * DS), bytes, full + tl % DST);
+    };
+    if (tid == 0)
+        for (int tl = 0; tl < DST && tl < ntile; ++tl) issue(tl);
 
     if (warp >= D_MMA_WARPS) {
-        // ================================================================ producers (128 threads)
-        const int ptid = tid - 32 * D_MMA_WARPS, pwarp = warp - D_MMA_WARPS;
-        auto issue = [&](int tl) {   // tile tl -> stage tl % DST (one thread)
-            const int64_t q0 = p0 + (int64_t)tl * DPT;
-            const unsigned bytes = (unsigned)(min((int64_t)DPT, p1 - q0) * DNR * DS * 8);
-            d_mbar_expect_tx(full + tl % DST, bytes);
-            d_bulk_g2s(tile0 + (size_t)(tl % DST) * (DPT * DNR * DS), P.rows + q0 * (DNR * DS), bytes, full + tl % DST);
-        };
-        if (ptid == 0) {
-            if (ntile > 0) issue(0);
-            if (ntile > 1) issue(1);
-        }
-        // four points per warp; after the transposing reduction lane 8q holds the five dot products of point 4 pwarp + q.
+        // ================================================================ producers (2 groups x 64 threads)
+        const int pwarp = warp - D_MMA_WARPS, grp = pwarp >> 1, wg = pwarp & 1, gtid = tid & 63;
+        // eight points per warp; after the transposing reduction lane 4q holds the five dot products of point 8 wg + q.
         // Per-point scalars (c, Dz0, w) of the evaluating lanes are fetched ONE TILE AHEAD: loaded on demand they put a
         // full DRAM latency into every tile's critical path (the barrier chain starts from them)
-        const bool ev = (lane & 7) == 0;
-        const int ptl = 4 * pwarp + (lane >> 3);
+        const bool ev = (lane & 3) == 0;
+        const int ptl = 8 * wg + (lane >> 2);
         double ncc[5], ndz[5], nwi = 0.0;
         auto prefetch = [&](int tl) {
             const int64_t i = p0 + (int64_t)tl * DPT + ptl;
@@ -149,42 +150,48 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __gri
             }
             nwi = on ? __ldg(&P.w[i]) : 0.0;
         };
-        if (ntile > 0) prefetch(0);
-        for (int tl = 0; tl < ntile; ++tl) {
+        if (grp < ntile) prefetch(grp);
+        const double zu0 = zu[lane], zu1 = zu[lane + 32], zs0 = zs[lane], zs1 = zs[lane + 32];
+        for (int tl = grp; tl < ntile; tl += 2) {
             const int st = tl % DST;
-            const unsigned par = (unsigned)((tl / DST) & 1);
             double cc[5], dz[5];
 #pragma unroll
             for (int k = 0; k < 5; ++k) { cc[k] = ncc[k]; dz[k] = ndz[k]; }
             const double wi = nwi;
-            if (tl + 1 < ntile) prefetch(tl + 1);
+            if (tl + 2 < ntile) prefetch(tl + 2);
             double* tile = tile0 + (size_t)st * (DPT * DNR * DS);
             double* pw = pw0 + st * (DPT * DPW);
             const int npt = (int)min((int64_t)DPT, npts - (int64_t)tl * DPT);
-            d_mbar_wait(full + st, par);
+            d_mbar_wait(full + st, (unsigned)((tl / DST) & 1));
             if (npt < DPT)   // the tail of a partial tile was not loaded: it must not contribute (0 * stale NaN)
-                for (int k = npt * DNR * DS + ptid; k < DPT * DNR * DS; k += 32 * D_PRO_WARPS) tile[k] = 0.0;
-            // ---- apply_D as 64-long dot products: lane = 2 dofs, 4 points x 5 rows = 20 partial sums per lane, reduced by
-            // a transposing butterfly (xor 16 halves the value set, xor 8 again, then xor 4 / 2 / 1 on the five left)
+                for (int k = npt * DNR * DS + gtid; k < DPT * DNR * DS; k += 64) tile[k] = 0.0;
+            // ---- apply_D as 64-long dot products: lane = 2 dofs, 8 points x 5 rows = 40 partial sums per lane, reduced by
+            // a transposing butterfly (xor 16 halves the value set - done while the rows are read, points q and q + 4
+            // together -, xor 8 and xor 4 halve it again, then xor 2 / 1 on the five that are left)
             {
-                double d[20];
-#pragma unroll
-                for (int pp = 0; pp < 4; ++pp) {
-                    const int pt = 4 * pwarp + pp;
+                auto dot5 = [&](int pp, double* out) {
+                    const int pt = 8 * wg + pp;
                     const bool actp = pt < npt;
                     const double* tp = tile + pt * (DNR * DS);
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) d[pp * 5 + r] = actp ? tp[r * DS + lane] * zu[lane] + tp[r * DS + lane + 32] * zu[lane + 32] : 0.0;
-                    d[pp * 5 + 4] = actp ? tp[4 * DS + lane] * zs[lane] + tp[4 * DS + lane + 32] * zs[lane + 32] : 0.0;
+                    for (int r = 0; r < 4; ++r) out[r] = actp ? tp[r * DS + lane] * zu0 + tp[r * DS + lane + 32] * zu1 : 0.0;
+                    out[4] = actp ? tp[4 * DS + lane] * zs0 + tp[4 * DS + lane + 32] * zs1 : 0.0;
+                };
+                const bool up1 = (lane & 16) != 0, up2 = (lane & 8) != 0, up3 = (lane & 4) != 0;
+                double e[20], f[10], dd[5];
+#pragma unroll
+                for (int pp = 0; pp < 4; ++pp) {
+                    double lo[5], hi[5];
+                    dot5(pp, lo); dot5(pp + 4, hi);
+#pragma unroll
+                    for (int r = 0; r < 5; ++r) e[pp * 5 + r] = (up1 ? hi[r] : lo[r]) + shfl_xor_d(up1 ? lo[r] : hi[r], 16);
                 }
-                double e[10], dd[5];
-                const bool up1 = (lane & 16) != 0, up2 = (lane & 8) != 0;
 #pragma unroll
-                for (int i = 0; i < 10; ++i) e[i] = (up1 ? d[i + 10] : d[i]) + shfl_xor_d(up1 ? d[i] : d[i + 10], 16);
+                for (int i = 0; i < 10; ++i) f[i] = (up2 ? e[i + 10] : e[i]) + shfl_xor_d(up2 ? e[i] : e[i + 10], 8);
 #pragma unroll
-                for (int i = 0; i < 5; ++i) dd[i] = (up2 ? e[i + 5] : e[i]) + shfl_xor_d(up2 ? e[i] : e[i + 5], 8);
+                for (int i = 0; i < 5; ++i) dd[i] = (up3 ? f[i + 5] : f[i]) + shfl_xor_d(up3 ? f[i] : f[i + 5], 4);
 #pragma unroll
-                for (int mk = 4; mk >= 1; mk >>= 1)
+                for (int mk = 2; mk >= 1; mk >>= 1)
 #pragma unroll
                     for (int i = 0; i < 5; ++i) dd[i] += shfl_xor_d(dd[i], mk);
                 if (ev) {
@@ -224,12 +231,6 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __gri
             }
             d_mbar_arrive(ready + st);            // this thread's part of the tile's barrier records (and zero fill) is written
             d_mbar_arrive(empty + st);
-            // refill the stage the tensor-core warps are about to leave (tile tl-1 -> tile tl+2).  Waiting here, after this
-            // tile's producer work, keeps the two halves of the CTA one tile apart: producers on tl+1 while the MMAs run tl.
-            if (ptid == 0 && tl + 2 < ntile) {
-                if (tl >= 1) d_mbar_wait(empty + (tl - 1) % DST, (unsigned)(((tl - 1) / DST) & 1));
-                issue(tl + 2);
-            }
         }
     } else {
         // ================================================================ tensor-core warps (256 threads)
@@ -288,6 +289,10 @@ __global__ void __launch_bounds__(D_THREADS, 1) dense_element_kernel(const __gri
 #endif
             }
             d_mbar_arrive(empty + st);
+            if (tid == 0 && tl + DST < ntile) {   // refill this stage once the other warps have left it too
+                d_mbar_wait(empty + st, (unsigned)((tl / DST) & 1));
+                issue(tl + DST);
+            }
         }
         if (WG) {   // the four lanes of a quad hold the partials of the same unknowns over different points
             gu += shfl_xor_d(gu, 1); gu += shfl_xor_d(gu, 2);
