@@ -212,14 +212,37 @@ void build_dense_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t n
     P.d_gdof.assign((size_t)ng * 2 * NB, -1);
     for (int64_t g = 0; g < ng; ++g)
         for (int v = 0; v < 2; ++v) std::copy(gset[(size_t)g * 2 + v].begin(), gset[(size_t)g * 2 + v].end(), P.d_gdof.begin() + ((size_t)g * 2 + v) * NB);
-    // chunks: about two CTAs per SM on a 148-SM part when the level is small, at most DENSE_CHUNK points each
-    const int64_t chunk_pts = std::min<int64_t>(DENSE_CHUNK, std::max<int64_t>(64, (nloc / 296 + 15) / 16 * 16));
+    // chunks: one CTA each, one CTA per SM at a time.  Every group is cut into equal chunks of whole 16-point tiles, at
+    // most DENSE_CHUNK points; the target size is the one whose chunk count fills whole waves of a 148-SM part best
+    // (fem3d L=5 level 2: 512-point chunks make 512 CTAs = 3.46 waves of 32 tiles, 464-point chunks 576 CTAs = 3.89
+    // waves of 29 tiles), small levels get at least ~2 chunks per SM.  Fewer, larger chunks win ties (fewer records).
+    constexpr int64_t SMS = 148;
+    auto split = [&](int64_t npts, int64_t target, int64_t& nchg, int64_t& size) {
+        nchg = std::max<int64_t>(1, (npts + target - 1) / target);
+        size = ((npts + nchg - 1) / nchg + 15) / 16 * 16;
+        nchg = (npts + size - 1) / size;
+    };
+    const int64_t cap = std::min<int64_t>(DENSE_CHUNK, std::max<int64_t>(64, (nloc / (2 * SMS) + 15) / 16 * 16));
+    int64_t best_target = cap, best_cost = INT64_MAX;
+    for (int64_t target = cap; target >= std::max<int64_t>(64, cap / 2); target -= 16) {
+        int64_t total = 0, maxtiles = 0;
+        for (int64_t g = 0; g < ng; ++g) {
+            int64_t nchg, size;
+            split((gstart[g + 1] - gstart[g]) * B, target, nchg, size);
+            total += nchg; maxtiles = std::max(maxtiles, size / 16);
+        }
+        const int64_t cost = (total + SMS - 1) / SMS * (maxtiles + 3);   // + pipeline fill / record write-out per chunk
+        if (cost < best_cost) { best_cost = cost; best_target = target; }
+    }
     std::vector<int64_t> cgroup;
-    for (int64_t g = 0; g < ng; ++g)
-        for (int64_t p0 = gstart[g] * B; p0 < gstart[g + 1] * B; p0 += chunk_pts) {
-            P.d_chunk.push_back(g); P.d_chunk.push_back(p0); P.d_chunk.push_back(std::min<int64_t>(p0 + chunk_pts, gstart[g + 1] * B));
+    for (int64_t g = 0; g < ng; ++g) {
+        int64_t nchg, size;
+        split((gstart[g + 1] - gstart[g]) * B, best_target, nchg, size);
+        for (int64_t p0 = gstart[g] * B; p0 < gstart[g + 1] * B; p0 += size) {
+            P.d_chunk.push_back(g); P.d_chunk.push_back(p0); P.d_chunk.push_back(std::min<int64_t>(p0 + size, gstart[g + 1] * B));
             cgroup.push_back(g);
         }
+    }
     const int64_t nch = (int64_t)cgroup.size();
     P.d_nchunks = nch; P.E = nch;
     if (nch * (int64_t)P.lay.NS > INT32_MAX) { P.dense = false; P.why = "dense slot buffer exceeds int32 indexing"; return; }
