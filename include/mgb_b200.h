@@ -224,6 +224,12 @@ int mgb_copy_to_host(mgb_ctx* ctx, void* dst_host, const void* src_dev, int64_t 
  * halo elements that touch one of its output rows, so every owned row is completed locally and no Hessian or
  * gradient value crosses NVLink; only the objective scalars are summed across ranks, by peer-memory words with
  * embedded epoch tags written from inside the gather kernel (no NCCL call, no fence, no host round trip).
+ * Numbering of the unknowns: the library only sees "rank r owns the contiguous block out_part[r] .. out_part[r+1]".
+ * With R = blockdiag(R_u, R_s) in the reference's stacked numbering such a block is all-u or all-s, and a rank ends up
+ * evaluating every element that touches its u rows plus every element that touches its s rows (~2E/P, all of them
+ * at P=2).  Callers should therefore permute the columns of R rank-major (block r of u, then block r of s, then block
+ * r+1 of u ...: Python mgb_b200.dist.colocated_partition, Julia MGBB200.colocated_partition), pass s in that numbering
+ * and read g and the rows / columns of R'HR in it: E/P elements plus a halo per rank.
  *
  *   1. mgb_dist_plan_create on every rank (same arguments except `rank`; ctx==NULL: symbolic only)
  *   2. mgb_dist_export -> exchange the 64-byte handles between processes (MPI/NCCL/any) -> mgb_dist_attach

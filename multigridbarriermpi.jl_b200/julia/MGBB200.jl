@@ -210,6 +210,31 @@ mutable struct DistPlan
 end
 
 """
+    colocated_partition(sizes, nranks) -> (perm, out_part)
+
+Rank-major renumbering of unknowns stacked by variable (`sizes[k]` = columns of block k of R = blockdiag(R_u, R_s, ..)):
+`perm[new] = old` (1-based), and in the new numbering rank r owns the contiguous block `out_part[r+1]+1 : out_part[r+2]`
+(0-based offsets as the C ABI takes them) = its uniform block of u, then of s, ...  Pass `R[:, perm]` and `s[perm]` to the
+plan; the gradient comes back as `g[perm]`, the Hessian rows / columns in the new numbering.  With the reference's
+stacked numbering a rank owning a block of `[u | s]` evaluates every element touching its u rows AND every element
+touching its s rows (all of them at 2 ranks); renumbered, it evaluates E/P elements plus a halo (same rule as
+`mgb_b200.dist.colocated_partition`, which the Python host side applies by default).
+"""
+function colocated_partition(sizes::Vector{Int}, nranks::Int)
+    block(n, r) = (q = divrem(n, nranks); (r * q[1] + min(r, q[2]), (r + 1) * q[1] + min(r + 1, q[2])))   # 0-based [lo, hi)
+    offs = cumsum([0; sizes])
+    perm = Int[]; out_part = Int64[0]
+    for r in 0:nranks-1
+        for (k, n) in enumerate(sizes)
+            lo, hi = block(n, r)
+            append!(perm, (offs[k] + lo + 1):(offs[k] + hi))
+        end
+        push!(out_part, length(perm))
+    end
+    perm, out_part
+end
+
+"""
     DistPlan(ctx, comm, D, R, x, w; idx, p, row_part, out_part)
 
 Collective over `comm` (MPI.Comm).  The symbolic phase needs the operators whole, once per level: they are gathered
