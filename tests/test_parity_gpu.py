@@ -134,3 +134,13 @@ def test_fem3d_coarse_levels_dense_path(gpu_ctx, L, level, p):
     gather) instead of product lists (reference problem data src/MultiGridBarrierMPI.jl:735-745)"""
     plan, _ = check_against_oracle(gpu_ctx, mgb_b200.fem3d(L), p, t=0.9, level=level)
     assert plan.info["path"] == capi.PATH_ELEMENT and plan.info["nodes_per_element"] == 64
+
+
+@pytest.mark.parametrize("level,p", [(0, 1.0), (1, 1.5), (2, 1.0)])
+def test_dense_path_partial_tiles(gpu_ctx, monkeypatch, level, p):
+    """Q2 hexahedra (27 points per element) forced onto the dense path (it would not pay there): groups of two or three
+    fine elements make chunks of 54 / 81 points, so the 16-point tiles of the TMA ring end in partial tiles - the
+    zero-filled tail must not contribute - and at the finest level a group's dofs fill the 64-wide block only partly."""
+    monkeypatch.setenv("MGB_DENSE_MIN_PRODUCTS", "0")
+    plan, _ = check_against_oracle(gpu_ctx, mgb_b200.fem3d(3, k=2), p, t=0.9, level=level)
+    assert plan.info["path"] == capi.PATH_ELEMENT and plan.info["nodes_per_element"] == 64
