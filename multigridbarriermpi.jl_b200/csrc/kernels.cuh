@@ -45,6 +45,8 @@ struct ElemParams {
     double* part;            // gridDim.x * 4  {f0, cdot, nonfinite count, -}
     double* Dz;              // nloc x ND or null
     int off_uu, off_us, off_ss, off_ut, off_st, off_tt, NS;
+    int mma;                 // coarse fem2d levels (B = 7, one cone, four sibling elements per warp): the warp's 8 x 8 blocks
+                             // are contracted on the FP64 tensor cores; record = full uu | us | ss blocks of 64 doubles
 };
 
 template <int V>
@@ -335,7 +337,45 @@ __device__ __forceinline__ void element_body(const ElemParams& P, const int64_t 
             }
         }
     }
-    if (WH) {
+    constexpr bool CAN_MMA = !FINE && MODE == 0 && B == 7 && D == 2;
+    if (WH && CAN_MMA && P.mma) {
+        // ---- Hessian of a coarse fem2d level on the FP64 tensor cores.  The 28 points of the warp's four sibling elements
+        // share their 7 + 7 coarse dofs, so  uu = sum_pt sum_jj' a_j' (w F2_jj') a_j',  us = sum_pt (a' w F2_qs) i_s',
+        // ss = sum_pt i_s (w F2_ss) i_s'  are three 8 x 8 products with K = the warp's points: 8 steps of
+        // mma.m8n8k4 over four lanes' points each.  Lane (g, t) of a step needs "dof g of point 4 step + t": the operator
+        // values come from that point's record (an L1 hit - its own lane loaded the record a moment ago), the point's six
+        // barrier values by shuffle from its lane.  Replaces 112 products per lane and a 105-value shuffle butterfly.
+        const int lane = threadIdx.x & 31, fg = lane >> 2, ft = lane & 3;
+        const int64_t ew = e - (lane >> 3);   // first element of this warp
+        constexpr int RWC = D * B + 1 + NU * B, RWm = (RWC + 1) / 2 * 2;
+        const double h00 = wi * bo.Hqq[0][0], h01 = wi * bo.Hqq[0][1], h11 = wi * bo.Hqq[1][1];
+        const double hq0 = wi * bo.Hqs[0], hq1 = wi * bo.Hqs[1], hss = wi * bo.Hss;
+        double cuu[2] = {0.0, 0.0}, cus[2] = {0.0, 0.0}, css[2] = {0.0, 0.0};
+#pragma unroll
+        for (int st = 0; st < 8; ++st) {
+            const int src = 4 * st + ft;                       // lane of the point this k index stands for
+            const int64_t pe = ew + (src >> 3);
+            const int pl = src & 7;
+            const bool ok = pl < B && pe < P.E && fg < B;
+            const double* rp = P.prec + (pe * B + pl) * RWm;
+            const double a0 = ok ? __ldg(rp + fg) : 0.0, a1 = ok ? __ldg(rp + B + fg) : 0.0;
+            const double as = ok ? __ldg(rp + D * B + 1 + B + fg) : 0.0;
+            const double H00 = shfl_d(h00, src, 32), H01 = shfl_d(h01, src, 32), H11 = shfl_d(h11, src, 32);
+            const double Q0 = shfl_d(hq0, src, 32), Q1 = shfl_d(hq1, src, 32), SS = shfl_d(hss, src, 32);
+            const double T0 = H00 * a0 + H01 * a1, T1 = H01 * a0 + H11 * a1;
+            const double bsv = Q0 * a0 + Q1 * a1, hsv = SS * as;
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cuu[0]), "+d"(cuu[1]) : "d"(a0), "d"(T0));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cuu[0]), "+d"(cuu[1]) : "d"(a1), "d"(T1));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(cus[0]), "+d"(cus[1]) : "d"(bsv), "d"(as));
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(css[0]), "+d"(css[1]) : "d"(hsv), "d"(as));
+        }
+        if (ew < P.E) {   // lane holds C[g][2t], C[g][2t + 1] of each block
+            double* rec = sel + fg * 8 + 2 * ft;
+            *reinterpret_cast<double2*>(rec + P.off_uu) = make_double2(cuu[0], cuu[1]);
+            *reinterpret_cast<double2*>(rec + P.off_us) = make_double2(cus[0], cus[1]);
+            *reinterpret_cast<double2*>(rec + P.off_ss) = make_double2(css[0], css[1]);
+        }
+    } else if (WH) {
     // ---- Hessian: element-local blocks of sum_jk a_j' (w Y_jk) a_k
     // u-u block (derivative operators only: the u.id row of F2 is identically zero)
     {

@@ -366,6 +366,7 @@ mgb::ElemParams make_elem_params(mgb_plan* pl, const double* s, const double* Dz
     P.sel = pl->d_sel.p; P.rel = pl->d_rel.p; P.part = pl->d_part.p; P.Dz = Dz;
     P.off_uu = ep.lay.off_uu; P.off_us = ep.lay.off_us; P.off_ss = ep.lay.off_ss;
     P.off_ut = ep.lay.off_ut; P.off_st = ep.lay.off_st; P.off_tt = ep.lay.off_tt; P.NS = ep.lay.NS;
+    P.mma = ep.mma ? 1 : 0;
     return P;
 }
 

@@ -99,13 +99,15 @@ static int pow2ceil(int v) {
 }
 static int round_up(int v, int a) { return (v + a - 1) / a * a; }
 
-void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_) {
+void SlotLayout::build(int B_, int dim_, bool slack_, bool fine_, bool mma_) {
     B = B_;
     dim = dim_;
     slack = slack_;
     fine = fine_;
+    mma = mma_;
     LPE = pow2ceil(B);
     NU = 2 + (slack ? 1 : 0);
+    if (mma) { off_uu = 0; off_us = 64; off_ss = 128; NS = 192; return; }
     const int ntri = round_up(B * (B + 1) / 2, LPE);
     const int nfull = fine ? B * LPE : round_up(B * B, LPE);
     const int ndiag = fine ? LPE : ntri;
@@ -486,7 +488,9 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
             P.agg = g;
         }
     }
-    P.lay.build((int)B, dim, slack, fine);
+    // coarse fem2d levels with whole warps of siblings: 8 x 8 blocks on the tensor cores (kernels.cuh, ElemParams::mma)
+    P.mma = !fine && B == 7 && dim == 2 && P.mode == 0 && P.agg == 4 && getenv("MGB_NO_MMA2D") == nullptr;
+    P.lay.build((int)B, dim, slack, fine, P.mma);
     const SlotLayout& lay = P.lay;
 
     // per-point records in element-local columns (one contiguous, 16-byte aligned record per point)
@@ -535,6 +539,7 @@ void build_element_plan(const std::vector<HostCSR>& D, const HostCSR& R, int64_t
         int v1 = a1 / (int)B, q1 = a1 % (int)B, v2 = a2 / (int)B, q2 = a2 % (int)B;
         if (v1 > v2 || (v1 == v2 && q1 > q2)) { std::swap(v1, v2); std::swap(q1, q2); }
         const int NT = lay.ntri_pad(), NF = lay.nfull_pad();
+        if (lay.mma) return ((v1 == 0 && v2 == 0) ? lay.off_uu : (v1 == 0 ? lay.off_us : lay.off_ss)) + q1 * 8 + q2;
         if (v1 == 0 && v2 == 0) return lay.packed(lay.off_uu, lay.tri(q1, q2), NT);
         if (v1 == 0 && v2 == 1) return lay.fine ? lay.off_us + q1 * lay.LPE + q2 : lay.packed(lay.off_us, q1 * lay.B + q2, NF);
         if (v1 == 0 && v2 == 2) return lay.fine ? lay.off_ut + q1 * lay.LPE + q2 : lay.packed(lay.off_ut, q1 * lay.B + q2, NF);

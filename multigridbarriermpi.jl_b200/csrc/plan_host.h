@@ -29,9 +29,10 @@ int64_t count_gram_pattern(const std::vector<HostCSR>& D);
 struct SlotLayout {
     int B = 0, LPE = 0, NU = 0, dim = 0;
     bool slack = false, fine = false;
+    bool mma = false;   // coarse fem2d levels on the tensor cores: full 8 x 8 blocks uu | us | ss (ElemParams::mma)
     int off_uu = 0, off_us = 0, off_ss = 0, off_ut = 0, off_st = 0, off_tt = 0;
     int NS = 0;  // doubles per element
-    void build(int B_, int dim_, bool slack_, bool fine_);
+    void build(int B_, int dim_, bool slack_, bool fine_, bool mma_ = false);
     int tri(int q, int q2) const;  // packed upper-triangle index, q <= q2 < B
     // slot of packed entry pk of a block of padded size npad that went through the transposing
     // butterfly: lane l ends with entries [l*K,(l+1)*K) and stores entry r at  off + r*LPE + l
@@ -60,6 +61,7 @@ struct ElementPlan {
     std::vector<double> d_rows;    // [point][dim + 2][DENSE_STRIDE]: derivative rows (u), u.id row, s.id row over the group's dofs
     int agg = 1;                   // coarse levels: aligned groups of `agg` consecutive elements share all their dofs (children of
                                    // one coarse element): one slot / gradient record per group (kernels.cuh agg_reduce)
+    bool mma = false;              // coarse fem2d level contracted on the tensor cores (SlotLayout::mma)
     int64_t out0 = 0, m_out = 0;   // output rows [out0, out0 + m_out) of the m unknowns (whole range unless sharded)
     SlotLayout lay;
     std::vector<int32_t> lcols;    // [E][NU][LPE]  global dof or -1
