@@ -16,7 +16,7 @@ N > 1 (torchrun): owner-computes sharding - the rows of R'HR and the gradient en
 owns block r of every variable: the unknowns are renumbered rank-major at the boundary, `--ownership contiguous` keeps
 the reference's stacked numbering instead), a rank evaluates every element touching its rows and completes them
 locally; only the objective scalars cross NVLink (peer-memory words, written and awaited inside the gather kernel, all inside the
-timed region).  The fixed L=8 problem is split, so scaling = "strong"; `sub_records` adds L=9 on the same GPUs.
+timed region).  The fixed L=8 problem is split, so scaling = "strong"; `sub_records` adds L=9 (and L=10 at N >= 8) on the same GPUs.
 Every line carries `parity`: the buffers that were just timed against the CPU oracle (max over ranks).
 """
 from __future__ import annotations
@@ -578,7 +578,7 @@ def main():
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle comparison of the timed buffers")
     ap.add_argument("--ownership", default="colocated", choices=["colocated", "contiguous"],
                     help="N > 1: rank r owns block r of every variable (unknowns renumbered rank-major) / a contiguous block of the stacked unknowns")
-    ap.add_argument("--sub", default=None, help="comma-separated extra levels timed as sub-records (default: 9 when N > 1)")
+    ap.add_argument("--sub", default=None, help="comma-separated extra levels timed as sub-records (default: 9 when N > 1, 9,10 when N >= 8; \"\" for none)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -605,7 +605,10 @@ def main():
 
     rec = run_config(args, args.L, rank, world, local_rank, dev, ctx, stream, args.steps, args.warmup)
     subs = []
-    sub_levels = [int(v) for v in (args.sub.split(",") if args.sub else (["9"] if world > 1 and args.sub is None else [])) if v]
+    # default sub-records: L=9 on any sharded run (with L=8 on one GPU and L=9 on four: the weak-scaling pair), plus the
+    # 3.67 M-point L=10 mesh on a full box (strong scaling against profiles/r2_bench_L10_n1.json; adds about a minute)
+    default_sub = [] if world == 1 else (["9", "10"] if world >= 8 else ["9"])
+    sub_levels = [int(v) for v in (args.sub.split(",") if args.sub else (default_sub if args.sub is None else [])) if v]
     for Ls in sub_levels:   # larger meshes on the same GPUs: where sharding has work to split
         r = run_config(args, Ls, rank, world, local_rank, dev, ctx, stream, max(5, args.steps // 5), 3)
         if rank == 0:
