@@ -464,6 +464,7 @@ def run_config(args, L, rank, world, local_rank, dev, ctx, stream, steps, warmup
             scal_h.copy_(so, non_blocking=True)
             torch.cuda.current_stream().synchronize()
 
+        barrier()   # the ranks leave the (CPU) parity check seconds apart; the peer wait inside an assembly times out after 30 s
         for _ in range(3):
             e2e_step()
         barrier()
