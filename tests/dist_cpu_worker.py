@@ -29,6 +29,29 @@ for gen, L in (("fem2d", 4), ("fem1d", 6)):
     colidx = np.concatenate([b[2] for b in sorted(blocks, key=lambda b: b[0])])
     assert np.array_equal(rowptr, grp) and np.array_equal(colidx, gci)
     assert np.array_equal(np.sort(np.concatenate([b[3] for b in blocks])), np.arange(n))
+# the same with the rank-major numbering of the unknowns (dist.colocated_partition): every rank permutes the columns of
+# R alike, the owned blocks tile the permuted pattern, and a rank evaluates fewer quadrature rows than with contiguous
+# blocks of the stacked unknowns
+import scipy.sparse as sp  # noqa: E402
+geom = mgb_b200.fem2d(4)
+pr = problem(geom)
+n, m = geom.x.shape[0], pr["R"].shape[1]
+perm, out_part = mdist.colocated_partition(mdist.variable_blocks(pr["R"], n), world)
+row_part, cont_part = mdist.peer_partitions(n, m, geom.block, world)
+Rp = pr["R"].tocsr()[:, perm].tocsr()
+pl = capi.DistPlan(None, pr["D"], Rp, pr["x"], pr["w"], pr["idx"], 1.0, rank, world, row_part, out_part)
+pc = capi.DistPlan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0, rank, world, row_part, cont_part)
+assert pl.dinfo["n_rows"] < pc.dinfo["n_rows"], (pl.dinfo["n_rows"], pc.dinfo["n_rows"])
+rp, ci = pl.own_pattern()
+blocks = [None] * world
+dist.all_gather_object(blocks, (pl.dinfo["own0"], rp, ci))
+grp, gci = capi.Plan(None, pr["D"], pr["R"], pr["x"], pr["w"], pr["idx"], 1.0).pattern()
+H = sp.csr_matrix((np.ones(len(gci)), gci.astype(np.int64), grp.astype(np.int64)), shape=(m, m))
+Hp = H[perm][:, perm].tocsr()
+Hp.sort_indices()
+rowptr = np.concatenate([[0]] + [np.diff(b[1]) for b in sorted(blocks, key=lambda b: b[0])]).cumsum()
+colidx = np.concatenate([b[2] for b in sorted(blocks, key=lambda b: b[0])])
+assert np.array_equal(rowptr, Hp.indptr) and np.array_equal(colidx, Hp.indices)
 # HPC-typed geometry: every rank keeps only its row block of each operator; the whole matrix comes back with one
 # collective gather (what the symbolic phase of a level needs of R, once - reference src/MultiGridBarrierMPI.jl:357-371)
 from mgb_b200 import hpc  # noqa: E402
